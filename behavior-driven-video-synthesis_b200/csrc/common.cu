@@ -1,0 +1,82 @@
+#include "common.h"
+
+#include <mutex>
+#include <string>
+
+namespace vub {
+
+static thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+void clear_error() { g_last_error.clear(); }
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(static_cast<int>(e), "%s: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// The driver is reached through the runtime (no link-time libcuda dependency), so the library
+// loads on a machine without a GPU and fails loudly only when a launch is attempted.
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+    else cudaGetLastError();  // clear
+  });
+  return fn;
+}
+
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes,
+                     bool weights) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(VUB_E_NODRIVER, "cuTensorMapEncodeTiled unavailable (no CUDA driver/GPU)");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
+                  const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  weights ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    return fail(static_cast<int>(r) > 0 ? static_cast<int>(r) : 1,
+                "cuTensorMapEncodeTiled failed: CUresult %d (rank %d, box0 %u, dims0 %llu)",
+                static_cast<int>(r), rank, box[0], static_cast<unsigned long long>(dims[0]));
+  }
+  return 0;
+}
+
+}  // namespace vub
+
+extern "C" int vub_abi_version(void) { return VUB_ABI_VERSION; }
+extern "C" const char* vub_last_error(void) { return vub::g_last_error.c_str(); }

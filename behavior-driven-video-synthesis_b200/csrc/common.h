@@ -1,0 +1,35 @@
+// Host-side helpers shared by the C-ABI launchers: error reporting and TMA descriptor encoding.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/vunet_b200.h"
+
+namespace vub {
+
+// Records a message retrievable through vub_last_error() and returns `code`.
+int fail(int code, const char* fmt, ...);
+void clear_error();
+
+// Returns 0 when the pending launch error state is clean, else the cudaError_t (and records it).
+int check_launch(const char* what);
+
+inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+inline int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Encodes a tiled bf16 tensor map of rank 2..5 (dims/strides innermost first, strides in bytes for
+// dims 1..rank-1).  swizzle_bytes is 64 or 128 and must equal box[0]*2.  Returns 0 / error code.
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes,
+                     bool weights);
+
+}  // namespace vub

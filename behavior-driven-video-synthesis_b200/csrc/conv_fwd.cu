@@ -1,0 +1,425 @@
+// Forward weight-normalised convolution as an implicit GEMM on tcgen05 (sm_100a).
+//
+//   D[128 pixels, BN channels] (TMEM, fp32) += A[128, BKC] (smem, bf16) * B[BN, BKC]^T (smem, bf16)
+//
+// A k-step is one (source, filter tap, BKC-channel block).  The A tile of a k-step is a 4-D TMA box
+// (BKC channels x TW x TH x TN pixels, TW*TH*TN = 128) of the NHWC activation tensor, shifted by the
+// tap offset; out-of-bounds coordinates (the conv's zero padding, and batch tails) are zero-filled
+// by TMA, so no im2col matrix ever exists.  Stride-2 convs read four parity sub-grids of the input
+// through four tensor maps.  TMA writes the box with 64B/128B swizzle, which is exactly the canonical
+// K-major UMMA operand layout (one pixel = one row).
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane),
+// warps 2..5 = epilogue (TMEM -> registers -> fp32 scale/shift/residual/ELU -> global).
+// One CTA = one 128-pixel tile x one BN tile; several CTAs are resident per SM so one CTA's
+// epilogue overlaps its neighbours' main loops.
+//
+// Replaces: NormConv2d.forward lib/modules.py:140-145 (+ VunetRNB's cat/ELU/add 221-233,
+// DepthToSpace 24-34, Downsample 148-161) of the reference.
+#include <cuda_bf16.h>
+
+#include <cstring>
+#include <mutex>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vub {
+
+constexpr int kTileM = 128;
+constexpr int kConvThreads = 192;
+constexpr int kMaxStages = 8;
+
+struct ConvKParams {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB;
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* out_raw;
+  __nv_bfloat16* out_elu;
+  float* out_f32;
+  int batch, hout, wout;
+  int cout, cout_valid;
+  int nsrc, cblocks, ntaps, stride;
+  int tw, th, tn, tw_log2, th_log2;
+  int tiles_w, tiles_h;
+  int stages;
+  uint32_t flags;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void unpack_bf16x2(uint32_t u, float& a, float& b) {
+  __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
+  float2 f = __bfloat1622float2(t);
+  a = f.x;
+  b = f.y;
+}
+
+// Epilogue for CH (16 or 32) consecutive channels of one pixel held in registers.
+template <int CH>
+__device__ __forceinline__ void epilogue_chunk(const ConvKParams& p, const uint32_t (&acc)[CH],
+                                               const float* s_scale, const float* s_shift,
+                                               int c_local, int c_global, bool valid, int n, int oh,
+                                               int ow) {
+  float y[CH];
+#pragma unroll
+  for (int i = 0; i < CH; ++i)
+    y[i] = fmaf(__uint_as_float(acc[i]), s_scale[c_local + i], s_shift[c_local + i]);
+  if (!valid) return;
+
+  const long long pix = ((long long)n * p.hout + oh) * p.wout + ow;
+  if (p.residual != nullptr) {
+    const uint4* r = reinterpret_cast<const uint4*>(p.residual + pix * p.cout + c_global);
+#pragma unroll
+    for (int j = 0; j < CH / 8; ++j) {
+      uint4 u = __ldg(r + j);
+      float a, b;
+      unpack_bf16x2(u.x, a, b); y[8 * j + 0] += a; y[8 * j + 1] += b;
+      unpack_bf16x2(u.y, a, b); y[8 * j + 2] += a; y[8 * j + 3] += b;
+      unpack_bf16x2(u.z, a, b); y[8 * j + 4] += a; y[8 * j + 5] += b;
+      unpack_bf16x2(u.w, a, b); y[8 * j + 6] += a; y[8 * j + 7] += b;
+    }
+  }
+
+  if (p.flags & VUB_CONV_F32_NCHW) {
+    const long long plane = (long long)p.hout * p.wout;
+    float* o = p.out_f32 + ((long long)n * p.cout_valid) * plane + (long long)oh * p.wout + ow;
+#pragma unroll
+    for (int i = 0; i < CH; ++i)
+      if (c_global + i < p.cout_valid) o[(long long)(c_global + i) * plane] = y[i];
+    return;
+  }
+  if (p.flags & VUB_CONV_F32_NHWC) {
+    float4* o = reinterpret_cast<float4*>(p.out_f32 + pix * p.cout + c_global);
+#pragma unroll
+    for (int j = 0; j < CH / 4; ++j)
+      o[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+    return;
+  }
+
+  long long obase;
+  if (p.flags & VUB_CONV_D2S) {
+    // DepthToSpace(2), DCR order: out[n, 2h+b1, 2w+b2, c'] = conv[n, h, w, (2*b1+b2)*C' + c']
+    const int cq = p.cout >> 2;
+    const int qd = c_global / cq;
+    const int cp = c_global - qd * cq;
+    const long long opix =
+        ((long long)n * (2 * p.hout) + 2 * oh + (qd >> 1)) * (2 * p.wout) + 2 * ow + (qd & 1);
+    obase = opix * cq + cp;
+  } else {
+    obase = pix * p.cout + c_global;
+  }
+  if (p.out_raw != nullptr) {
+    uint4* o = reinterpret_cast<uint4*>(p.out_raw + obase);
+#pragma unroll
+    for (int j = 0; j < CH / 8; ++j)
+      o[j] = make_uint4(pack_bf16x2(y[8 * j + 0], y[8 * j + 1]), pack_bf16x2(y[8 * j + 2], y[8 * j + 3]),
+                        pack_bf16x2(y[8 * j + 4], y[8 * j + 5]), pack_bf16x2(y[8 * j + 6], y[8 * j + 7]));
+  }
+  if (p.out_elu != nullptr) {
+#pragma unroll
+    for (int i = 0; i < CH; ++i) y[i] = elu1(y[i]);
+    uint4* o = reinterpret_cast<uint4*>(p.out_elu + obase);
+#pragma unroll
+    for (int j = 0; j < CH / 8; ++j)
+      o[j] = make_uint4(pack_bf16x2(y[8 * j + 0], y[8 * j + 1]), pack_bf16x2(y[8 * j + 2], y[8 * j + 3]),
+                        pack_bf16x2(y[8 * j + 4], y[8 * j + 5]), pack_bf16x2(y[8 * j + 6], y[8 * j + 7]));
+  }
+}
+
+template <int BN, int BKC>
+__global__ void __launch_bounds__(kConvThreads)
+    conv_fwd_kernel(const __grid_constant__ ConvKParams p) {
+  constexpr int ROWB = BKC * 2;
+  constexpr int A_BYTES = kTileM * ROWB;
+  constexpr int B_BYTES = BN * ROWB;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024B alignment");
+
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  __shared__ uint64_t full_bar[kMaxStages];
+  __shared__ uint64_t empty_bar[kMaxStages];
+  __shared__ uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_scale[BN];
+  __shared__ float s_shift[BN];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.y;
+  int t = blockIdx.x;
+  const int twi = t % p.tiles_w;
+  t /= p.tiles_w;
+  const int thi = t % p.tiles_h;
+  const int tni = t / p.tiles_h;
+  const int w0 = twi * p.tw, h0 = thi * p.th, n0 = tni * p.tn;
+  const int S = p.stages;
+  const int KS = p.nsrc * p.ntaps * p.cblocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<TMEM_COLS>(&tmem_base_slot);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < BN; i += kConvThreads) {
+    s_scale[i] = p.scale[n_tile * BN + i];
+    s_shift[i] = p.shift[n_tile * BN + i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int ks = 0;
+      for (int src = 0; src < p.nsrc; ++src) {
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          int dh = 0, dw = 0, mi = src;
+          if (p.ntaps == 9) {
+            const int r = tap / 3, s = tap - 3 * r;
+            if (p.stride == 1) {
+              dh = r - 1;
+              dw = s - 1;
+            } else {  // input row 2*oh + r - 1: parity (r != 1), coordinate oh - (r == 0)
+              mi = ((r != 1) ? 2 : 0) + ((s != 1) ? 1 : 0);
+              dh = (r == 0) ? -1 : 0;
+              dw = (s == 0) ? -1 : 0;
+            }
+          }
+          for (int cb = 0; cb < p.cblocks; ++cb, ++ks) {
+            const int st = ks % S;
+            const uint32_t ph = (ks / S) & 1;
+            mbar_wait(&empty_bar[st], ph ^ 1);
+            mbar_expect_tx(&full_bar[st], STAGE_BYTES);
+            uint8_t* a = smem + st * STAGE_BYTES;
+            tma_load_4d(a, &p.tmA[mi], &full_bar[st], cb * BKC, w0 + dw, h0 + dh, n0);
+            tma_load_2d(a + A_BYTES, &p.tmB, &full_bar[st], ks * BKC, n_tile * BN);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
+      for (int ks = 0; ks < KS; ++ks) {
+        const int st = ks % S;
+        const uint32_t ph = (ks / S) & 1;
+        mbar_wait(&full_bar[st], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + st * STAGE_BYTES);
+        const uint64_t da = umma_smem_desc_kmajor(a_addr, ROWB);
+        const uint64_t db = umma_smem_desc_kmajor(a_addr + A_BYTES, ROWB);
+#pragma unroll
+        for (int j = 0; j < BKC / 16; ++j)
+          umma_bf16(tmem_base, da + 2 * j, db + 2 * j, idesc, (ks | j) != 0 ? 1u : 0u);
+        umma_commit(&empty_bar[st]);
+      }
+      umma_commit(&tmem_full_bar);
+    }
+  } else {
+    // ------------------------------ epilogue -----------------------------------
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int m = q * 32 + lane;
+    const int dw = m & (p.tw - 1);
+    const int dh = (m >> p.tw_log2) & (p.th - 1);
+    const int dn = m >> (p.tw_log2 + p.th_log2);
+    const int n = n0 + dn, oh = h0 + dh, ow = w0 + dw;
+    const bool valid = n < p.batch;
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    if constexpr (BN >= 32) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld32(trow + c0, acc);
+        tmem_ld_wait();
+        epilogue_chunk<32>(p, acc, s_scale, s_shift, c0, n_tile * BN + c0, valid, n, oh, ow);
+      }
+    } else {
+      uint32_t acc[16];
+      tmem_ld16(trow, acc);
+      tmem_ld_wait();
+      epilogue_chunk<16>(p, acc, s_scale, s_shift, 0, n_tile * BN, valid, n, oh, ow);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+template <int BN, int BKC>
+static int launch_conv(const ConvKParams& kp, dim3 grid, cudaStream_t stream) {
+  constexpr int STAGE_BYTES = (kTileM + BN) * BKC * 2;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_fwd_kernel<BN, BKC>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  });
+  if (attr_err != cudaSuccess)
+    return fail(static_cast<int>(attr_err), "cudaFuncSetAttribute(conv_fwd<%d,%d>): %s", BN, BKC,
+                cudaGetErrorString(attr_err));
+  const size_t smem = static_cast<size_t>(kp.stages) * STAGE_BYTES + 1024;
+  conv_fwd_kernel<BN, BKC><<<grid, kConvThreads, smem, stream>>>(kp);
+  return check_launch("conv_fwd");
+}
+
+static int default_stages(int bn, int bkc, int ksteps) {
+  const int stage_bytes = (kTileM + bn) * bkc * 2;
+  const int budget = (bn >= 128 ? 100 : 56) * 1024;
+  int s = budget / stage_bytes;
+  if (s < 2) s = 2;
+  if (s > kMaxStages) s = kMaxStages;
+  if (s > ksteps) s = ksteps;
+  return s;
+}
+
+}  // namespace vub
+
+using namespace vub;
+
+extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
+  clear_error();
+  if (!d) return fail(VUB_E_NULL, "conv_fwd: desc is NULL");
+  if (!d->x[0] || !d->w || !d->scale || !d->shift) return fail(VUB_E_NULL, "conv_fwd: x/w/scale/shift NULL");
+  if (d->nsrc != 1 && d->nsrc != 2) return fail(VUB_E_SHAPE, "conv_fwd: nsrc must be 1 or 2");
+  if (d->nsrc == 2 && !d->x[1]) return fail(VUB_E_NULL, "conv_fwd: x[1] NULL with nsrc == 2");
+  if (d->c_src != 32 && d->c_src != 64 && d->c_src != 128)
+    return fail(VUB_E_SHAPE, "conv_fwd: c_src %d not in {32,64,128}", d->c_src);
+  if (d->ksize != 1 && d->ksize != 3) return fail(VUB_E_SHAPE, "conv_fwd: ksize must be 1 or 3");
+  if (d->stride != 1 && d->stride != 2) return fail(VUB_E_SHAPE, "conv_fwd: stride must be 1 or 2");
+  if (d->stride == 2 && (d->ksize != 3 || d->nsrc != 1))
+    return fail(VUB_E_SHAPE, "conv_fwd: stride 2 needs ksize 3 and one source");
+  if (d->batch <= 0 || !is_pow2(d->hin) || !is_pow2(d->win))
+    return fail(VUB_E_SHAPE, "conv_fwd: batch %d hin %d win %d (extents must be powers of two)", d->batch,
+                d->hin, d->win);
+  const int hout = d->hin / d->stride, wout = d->win / d->stride;
+  if (hout < 1 || wout < 1) return fail(VUB_E_SHAPE, "conv_fwd: empty output");
+  const int cout = d->cout;
+  if (!(cout == 16 || cout == 32 || cout == 64 || cout == 128 || cout == 256 || cout == 512))
+    return fail(VUB_E_SHAPE, "conv_fwd: cout %d not in {16,32,64,128,256,512}", cout);
+  if (d->cout_valid <= 0 || d->cout_valid > cout) return fail(VUB_E_SHAPE, "conv_fwd: cout_valid");
+  const uint32_t f = d->flags;
+  const bool f32 = (f & (VUB_CONV_F32_NHWC | VUB_CONV_F32_NCHW)) != 0;
+  if ((f & VUB_CONV_F32_NHWC) && (f & VUB_CONV_F32_NCHW)) return fail(VUB_E_FLAGS, "conv_fwd: two f32 layouts");
+  if (f32 && (!d->out_f32 || d->out_raw || d->out_elu || (f & VUB_CONV_D2S)))
+    return fail(VUB_E_FLAGS, "conv_fwd: f32 output excludes bf16 outputs and D2S");
+  if (!f32 && (d->out_f32 || (!d->out_raw && !d->out_elu)))
+    return fail(VUB_E_FLAGS, "conv_fwd: need out_raw and/or out_elu (and no out_f32)");
+  if (!(f & VUB_CONV_F32_NCHW) && d->cout_valid != cout)
+    return fail(VUB_E_FLAGS, "conv_fwd: cout_valid != cout only with F32_NCHW");
+  if ((f & VUB_CONV_D2S) && (d->residual || cout < 128))
+    return fail(VUB_E_FLAGS, "conv_fwd: D2S excludes residual and needs cout >= 128");
+  const void* ptrs[] = {d->x[0], d->x[1], d->w, d->residual, d->out_raw, d->out_elu, d->out_f32};
+  for (const void* q : ptrs)
+    if (q && !aligned16(q)) return fail(VUB_E_ALIGN, "conv_fwd: pointer %p not 16B aligned", q);
+
+  const int bkc = d->c_src >= 64 ? 64 : 32;
+  const int bn = cout > 256 ? 256 : cout;
+
+  ConvKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.scale = d->scale;
+  kp.shift = d->shift;
+  kp.residual = static_cast<const __nv_bfloat16*>(d->residual);
+  kp.out_raw = static_cast<__nv_bfloat16*>(d->out_raw);
+  kp.out_elu = static_cast<__nv_bfloat16*>(d->out_elu);
+  kp.out_f32 = static_cast<float*>(d->out_f32);
+  kp.batch = d->batch;
+  kp.hout = hout;
+  kp.wout = wout;
+  kp.cout = cout;
+  kp.cout_valid = d->cout_valid;
+  kp.nsrc = d->nsrc;
+  kp.cblocks = d->c_src / bkc;
+  kp.ntaps = d->ksize * d->ksize;
+  kp.stride = d->stride;
+  kp.tw = wout < kTileM ? wout : kTileM;
+  kp.th = hout < kTileM / kp.tw ? hout : kTileM / kp.tw;
+  kp.tn = kTileM / (kp.tw * kp.th);
+  kp.tw_log2 = ilog2(kp.tw);
+  kp.th_log2 = ilog2(kp.th);
+  kp.tiles_w = wout / kp.tw;
+  kp.tiles_h = hout / kp.th;
+  const int tiles_n = (d->batch + kp.tn - 1) / kp.tn;
+  kp.flags = f;
+  const int ksteps = kp.nsrc * kp.ntaps * kp.cblocks;
+  kp.stages = d->stages > 0 ? d->stages : default_stages(bn, bkc, ksteps);
+  if (kp.stages > kMaxStages) kp.stages = kMaxStages;
+  if ((size_t)kp.stages * (kTileM + bn) * bkc * 2 + 1024 > 200 * 1024)
+    return fail(VUB_E_SHAPE, "conv_fwd: %d stages do not fit in shared memory", kp.stages);
+
+  // ---- tensor maps ----
+  const uint64_t C = static_cast<uint64_t>(d->c_src);
+  const uint64_t Hin = d->hin, Win = d->win, B = d->batch;
+  const uint32_t boxA[4] = {(uint32_t)bkc, (uint32_t)kp.tw, (uint32_t)kp.th, (uint32_t)kp.tn};
+  int rc;
+  if (d->stride == 1) {
+    const uint64_t dims[4] = {C, Win, Hin, B};
+    const uint64_t strides[3] = {C * 2, Win * C * 2, Hin * Win * C * 2};
+    for (int s = 0; s < d->nsrc; ++s) {
+      rc = encode_tmap_bf16(&kp.tmA[s], d->x[s], 4, dims, strides, boxA, bkc * 2, false);
+      if (rc) return rc;
+    }
+  } else {
+    const uint64_t dims[4] = {C, Win / 2, Hin / 2, B};
+    const uint64_t strides[3] = {2 * C * 2, 2 * Win * C * 2, Hin * Win * C * 2};
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        const char* base = static_cast<const char*>(d->x[0]) + ((uint64_t)ph * Win + pw) * C * 2;
+        rc = encode_tmap_bf16(&kp.tmA[ph * 2 + pw], base, 4, dims, strides, boxA, bkc * 2, false);
+        if (rc) return rc;
+      }
+  }
+  {
+    const uint64_t ktot = (uint64_t)ksteps * bkc;
+    const uint64_t dims[2] = {ktot, (uint64_t)cout};
+    const uint64_t strides[1] = {ktot * 2};
+    const uint32_t boxB[2] = {(uint32_t)bkc, (uint32_t)bn};
+    rc = encode_tmap_bf16(&kp.tmB, d->w, 2, dims, strides, boxB, bkc * 2, true);
+    if (rc) return rc;
+  }
+
+  dim3 grid(kp.tiles_w * kp.tiles_h * tiles_n, cout / bn);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+#define VUB_DISPATCH(BN_, BKC_) \
+  if (bn == BN_ && bkc == BKC_) return launch_conv<BN_, BKC_>(kp, grid, stream);
+  VUB_DISPATCH(16, 32)
+  VUB_DISPATCH(16, 64)
+  VUB_DISPATCH(32, 32)
+  VUB_DISPATCH(32, 64)
+  VUB_DISPATCH(64, 32)
+  VUB_DISPATCH(64, 64)
+  VUB_DISPATCH(128, 32)
+  VUB_DISPATCH(128, 64)
+  VUB_DISPATCH(256, 32)
+  VUB_DISPATCH(256, 64)
+#undef VUB_DISPATCH
+  return fail(VUB_E_SHAPE, "conv_fwd: no kernel for BN %d BKC %d", bn, bkc);
+}

@@ -1,0 +1,328 @@
+// Memory-bound kernels of the VUnet path: weight-norm preparation, the K=3/30 stem, the latent
+// head (sigmoid / exp / reparameterisation / KL partial sums) and the NCHW<->NHWC converters.
+// All are HBM-bound: coalesced accesses, 128-bit vectors where the layout allows, warp-shuffle
+// reductions.
+#include <cuda_bf16.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vub {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum for blockDim.x <= 1024 (multiple of 32); every thread gets the result.
+__device__ __forceinline__ float block_sum(float v, float* red /*[32]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float t = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (warp == 0) {
+    t = warp_sum(t);
+    if (lane == 0) red[0] = t;
+  }
+  __syncthreads();
+  t = red[0];
+  __syncthreads();
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight-norm preparation (lib/modules.py:135-138,144): one block per output channel of any layer.
+//   v_hat = v / ||v||_2 (bf16, packed K order (source, tap, channel)); scale = gamma*g;
+//   shift = gamma*bias + beta.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWnThreads = 128;
+
+__global__ void __launch_bounds__(kWnThreads)
+    wn_prep_kernel(const vub_wn_entry* __restrict__ table, int n_entries) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  // binary search for the entry with row_start <= row < row_start + cout
+  int lo = 0, hi = n_entries - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (table[mid].row_start <= row) lo = mid;
+    else hi = mid - 1;
+  }
+  const vub_wn_entry e = table[lo];
+  const int co = row - e.row_start;
+  if (co >= e.cout) return;
+  const int len = e.cin * e.ktaps;
+  const float* v = e.v + (size_t)co * len;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < len; i += kWnThreads) {
+    const float x = v[i];
+    ss = fmaf(x, x, ss);
+  }
+  ss = block_sum(ss, red);
+  const float inv = 1.0f / sqrtf(ss);
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(e.w_packed) + (size_t)co * e.ktot;
+  for (int i = threadIdx.x; i < len; i += kWnThreads) {
+    const int ci = i / e.ktaps;
+    const int tap = i - ci * e.ktaps;
+    const int src = ci / e.c_src;
+    const int cs = ci - src * e.c_src;
+    out[(src * e.ktaps + tap) * e.c_src + cs] = __float2bfloat16_rn(v[i] * inv);
+  }
+  if (threadIdx.x == 0) {
+    const float ga = e.gamma[co];
+    e.scale[co] = ga * e.g[co];
+    e.shift[co] = fmaf(ga, e.bias[co], e.beta[co]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stem: 1x1 NormConv2d on an NCHW fp32 image -> NHWC bf16 raw + ELU (models/vunets.py:137,250).
+// One thread per pixel: reads are coalesced along W per channel plane, each thread owns COUT
+// accumulators and writes its pixel's COUT*2 contiguous bytes with 128-bit stores.
+// ------------------------------------------------------------------------------------------------
+constexpr int kStemThreads = 128;
+constexpr int kStemMaxCx = 64;
+
+template <int COUT>
+__global__ void __launch_bounds__(kStemThreads)
+    stem_kernel(const float* __restrict__ x, const float* __restrict__ v, const float* __restrict__ g,
+                const float* __restrict__ gamma, const float* __restrict__ beta,
+                const float* __restrict__ bias, int cx, long long hw, long long total_pix,
+                __nv_bfloat16* __restrict__ out_raw, __nv_bfloat16* __restrict__ out_elu) {
+  __shared__ float s_w[COUT * kStemMaxCx];  // [ci][co], already scaled by gamma*g/||v||
+  __shared__ float s_shift[COUT];
+  for (int co = threadIdx.x; co < COUT; co += kStemThreads) {
+    float ss = 0.f;
+    for (int ci = 0; ci < cx; ++ci) ss = fmaf(v[co * cx + ci], v[co * cx + ci], ss);
+    const float sc = gamma[co] * g[co] / sqrtf(ss);
+    for (int ci = 0; ci < cx; ++ci) s_w[ci * COUT + co] = v[co * cx + ci] * sc;
+    s_shift[co] = fmaf(gamma[co], bias[co], beta[co]);
+  }
+  __syncthreads();
+  const long long pix = (long long)blockIdx.x * kStemThreads + threadIdx.x;
+  if (pix >= total_pix) return;
+  const long long n = pix / hw;
+  const long long sp = pix - n * hw;
+  const float* xp = x + n * cx * hw + sp;
+  float acc[COUT];
+#pragma unroll
+  for (int co = 0; co < COUT; ++co) acc[co] = s_shift[co];
+  for (int ci = 0; ci < cx; ++ci) {
+    const float xv = __ldg(xp + (long long)ci * hw);
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] = fmaf(xv, s_w[ci * COUT + co], acc[co]);
+  }
+  if (out_raw != nullptr) {
+    uint4* o = reinterpret_cast<uint4*>(out_raw + pix * COUT);
+#pragma unroll
+    for (int j = 0; j < COUT / 8; ++j) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(acc[8 * j + 0], acc[8 * j + 1]);
+      __nv_bfloat162 b = __floats2bfloat162_rn(acc[8 * j + 2], acc[8 * j + 3]);
+      __nv_bfloat162 c = __floats2bfloat162_rn(acc[8 * j + 4], acc[8 * j + 5]);
+      __nv_bfloat162 d = __floats2bfloat162_rn(acc[8 * j + 6], acc[8 * j + 7]);
+      o[j] = make_uint4(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b),
+                        *reinterpret_cast<uint32_t*>(&c), *reinterpret_cast<uint32_t*>(&d));
+    }
+  }
+  if (out_elu != nullptr) {
+    uint4* o = reinterpret_cast<uint4*>(out_elu + pix * COUT);
+#pragma unroll
+    for (int j = 0; j < COUT / 8; ++j) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(elu1(acc[8 * j + 0]), elu1(acc[8 * j + 1]));
+      __nv_bfloat162 b = __floats2bfloat162_rn(elu1(acc[8 * j + 2]), elu1(acc[8 * j + 3]));
+      __nv_bfloat162 c = __floats2bfloat162_rn(elu1(acc[8 * j + 4]), elu1(acc[8 * j + 5]));
+      __nv_bfloat162 d = __floats2bfloat162_rn(elu1(acc[8 * j + 6]), elu1(acc[8 * j + 7]));
+      o[j] = make_uint4(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b),
+                        *reinterpret_cast<uint32_t*>(&c), *reinterpret_cast<uint32_t*>(&d));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Latent head (models/vunets.py:575,594-597; lib/losses.py:283-291).
+// One thread handles 4 consecutive channels of one pixel: float4 loads of mu and logit from the
+// NHWC conv output, 8-byte bf16 stores to the NHWC operands, scalar stores to the (tiny) NCHW
+// outputs, warp-shuffle + block reduction of the KL summand into one partial per block.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLatThreads = 128;
+
+__global__ void __launch_bounds__(kLatThreads)
+    latent_kernel(const float* __restrict__ ml, const float* __restrict__ eps, int c, int hw,
+                  long long total4, float* __restrict__ mu_o, float* __restrict__ ls_o,
+                  float* __restrict__ z_o, __nv_bfloat16* __restrict__ elu_z,
+                  __nv_bfloat16* __restrict__ elu_mu, float* __restrict__ kl_partial) {
+  __shared__ float red[32];
+  const long long idx = (long long)blockIdx.x * kLatThreads + threadIdx.x;
+  float kl = 0.f;
+  if (idx < total4) {
+    const int c4 = c >> 2;
+    const long long pix = idx / c4;  // n*hw + sp
+    const int ch = static_cast<int>(idx - pix * c4) * 4;
+    const long long n = pix / hw;
+    const int sp = static_cast<int>(pix - n * hw);
+    const float4 m4 = *reinterpret_cast<const float4*>(ml + pix * (2 * c) + ch);
+    const float4 l4 = *reinterpret_cast<const float4*>(ml + pix * (2 * c) + c + ch);
+    const float mu[4] = {m4.x, m4.y, m4.z, m4.w};
+    const float lg[4] = {l4.x, l4.y, l4.z, l4.w};
+    float zz[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long o = (n * c + ch + i) * hw + sp;  // NCHW
+      const float ls = 1.0f / (1.0f + expf(-lg[i]));
+      const float sd = expf(ls);
+      const float e = eps != nullptr ? eps[o] : 0.f;
+      const float z = fmaf(e, sd, mu[i]);
+      zz[i] = z;
+      mu_o[o] = mu[i];
+      ls_o[o] = ls;
+      z_o[o] = z;
+      kl += -ls + 0.5f * (sd * sd + mu[i] * mu[i]);
+    }
+    if (elu_z != nullptr) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(elu1(zz[0]), elu1(zz[1]));
+      __nv_bfloat162 b = __floats2bfloat162_rn(elu1(zz[2]), elu1(zz[3]));
+      *reinterpret_cast<uint2*>(elu_z + pix * c + ch) =
+          make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    }
+    if (elu_mu != nullptr) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(elu1(mu[0]), elu1(mu[1]));
+      __nv_bfloat162 b = __floats2bfloat162_rn(elu1(mu[2]), elu1(mu[3]));
+      *reinterpret_cast<uint2*>(elu_mu + pix * c + ch) =
+          make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    }
+  }
+  kl = block_sum(kl, red);
+  if (threadIdx.x == 0 && kl_partial != nullptr) kl_partial[blockIdx.x] = kl;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Layout converters through a 32x33 shared-memory tile (coalesced on both sides).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    nchw_to_nhwc_kernel(const float* __restrict__ src, int c, int hw, __nv_bfloat16* __restrict__ raw,
+                        __nv_bfloat16* __restrict__ elu) {
+  __shared__ float tile[32][33];
+  const long long n = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int ch = c0 + j, px = p0 + tx;
+    tile[j][tx] = (ch < c && px < hw) ? src[(n * c + ch) * hw + px] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int px = p0 + j, ch = c0 + tx;
+    if (px < hw && ch < c) {
+      const float v = tile[tx][j];
+      const long long o = (n * hw + px) * c + ch;
+      if (raw != nullptr) raw[o] = __float2bfloat16_rn(v);
+      if (elu != nullptr) elu[o] = __float2bfloat16_rn(elu1(v));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, int c, int hw, float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const long long n = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const int px = p0 + j, ch = c0 + tx;
+    tile[j][tx] = (px < hw && ch < c) ? __bfloat162float(src[(n * hw + px) * c + ch]) : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int ch = c0 + j, px = p0 + tx;
+    if (ch < c && px < hw) dst[(n * c + ch) * hw + px] = tile[tx][j];
+  }
+}
+
+}  // namespace vub
+
+using namespace vub;
+
+extern "C" int vub_wn_prep(const vub_wn_entry* table_dev, int32_t n_entries, int32_t total_rows,
+                           void* stream) {
+  clear_error();
+  if (!table_dev) return fail(VUB_E_NULL, "wn_prep: table is NULL");
+  if (n_entries <= 0 || total_rows <= 0) return fail(VUB_E_SHAPE, "wn_prep: empty table");
+  wn_prep_kernel<<<total_rows, kWnThreads, 0, static_cast<cudaStream_t>(stream)>>>(table_dev, n_entries);
+  return check_launch("wn_prep");
+}
+
+extern "C" int vub_stem_fwd(const float* x_nchw, const float* v, const float* g, const float* gamma,
+                            const float* beta, const float* bias, int32_t batch, int32_t cx, int32_t h,
+                            int32_t w, int32_t cout, void* out_raw, void* out_elu, void* stream) {
+  clear_error();
+  if (!x_nchw || !v || !g || !gamma || !beta || !bias) return fail(VUB_E_NULL, "stem_fwd: NULL input");
+  if (!out_raw && !out_elu) return fail(VUB_E_FLAGS, "stem_fwd: no output");
+  if (batch <= 0 || h <= 0 || w <= 0 || cx <= 0 || cx > kStemMaxCx)
+    return fail(VUB_E_SHAPE, "stem_fwd: batch %d cx %d h %d w %d (cx <= %d)", batch, cx, h, w, kStemMaxCx);
+  if ((out_raw && !aligned16(out_raw)) || (out_elu && !aligned16(out_elu)))
+    return fail(VUB_E_ALIGN, "stem_fwd: outputs must be 16B aligned");
+  const long long hw = (long long)h * w, total = hw * batch;
+  const unsigned grid = static_cast<unsigned>((total + kStemThreads - 1) / kStemThreads);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (cout == 32)
+    stem_kernel<32><<<grid, kStemThreads, 0, s>>>(x_nchw, v, g, gamma, beta, bias, cx, hw, total,
+                                                  static_cast<__nv_bfloat16*>(out_raw),
+                                                  static_cast<__nv_bfloat16*>(out_elu));
+  else if (cout == 64)
+    stem_kernel<64><<<grid, kStemThreads, 0, s>>>(x_nchw, v, g, gamma, beta, bias, cx, hw, total,
+                                                  static_cast<__nv_bfloat16*>(out_raw),
+                                                  static_cast<__nv_bfloat16*>(out_elu));
+  else
+    return fail(VUB_E_SHAPE, "stem_fwd: cout %d not in {32,64}", cout);
+  return check_launch("stem_fwd");
+}
+
+extern "C" int32_t vub_latent_num_partials(int32_t batch, int32_t c, int32_t h, int32_t w) {
+  const long long total4 = (long long)batch * h * w * (c / 4);
+  return static_cast<int32_t>((total4 + kLatThreads - 1) / kLatThreads);
+}
+
+extern "C" int vub_latent_fwd(const float* ml_nhwc, const float* eps_nchw, int32_t batch, int32_t c,
+                              int32_t h, int32_t w, float* mu_nchw, float* logstd_nchw, float* z_nchw,
+                              void* elu_z_nhwc, void* elu_mu_nhwc, float* kl_partial, void* stream) {
+  clear_error();
+  if (!ml_nhwc || !mu_nchw || !logstd_nchw || !z_nchw) return fail(VUB_E_NULL, "latent_fwd: NULL pointer");
+  if (batch <= 0 || c <= 0 || (c & 3) || h <= 0 || w <= 0)
+    return fail(VUB_E_SHAPE, "latent_fwd: batch %d c %d h %d w %d (c %% 4 == 0)", batch, c, h, w);
+  if (!aligned16(ml_nhwc)) return fail(VUB_E_ALIGN, "latent_fwd: ml_nhwc not 16B aligned");
+  const long long total4 = (long long)batch * h * w * (c / 4);
+  const unsigned grid = static_cast<unsigned>((total4 + kLatThreads - 1) / kLatThreads);
+  latent_kernel<<<grid, kLatThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      ml_nhwc, eps_nchw, c, h * w, total4, mu_nchw, logstd_nchw, z_nchw,
+      static_cast<__nv_bfloat16*>(elu_z_nhwc), static_cast<__nv_bfloat16*>(elu_mu_nhwc), kl_partial);
+  return check_launch("latent_fwd");
+}
+
+extern "C" int vub_nchw_f32_to_nhwc_bf16(const float* src, int32_t batch, int32_t c, int32_t h,
+                                         int32_t w, void* dst_raw, void* dst_elu, void* stream) {
+  clear_error();
+  if (!src || (!dst_raw && !dst_elu)) return fail(VUB_E_NULL, "nchw_to_nhwc: NULL pointer");
+  if (batch <= 0 || c <= 0 || h <= 0 || w <= 0 || batch > 65535)
+    return fail(VUB_E_SHAPE, "nchw_to_nhwc: bad shape");
+  const int hw = h * w;
+  dim3 grid((hw + 31) / 32, (c + 31) / 32, batch);
+  nchw_to_nhwc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, c, hw, static_cast<__nv_bfloat16*>(dst_raw), static_cast<__nv_bfloat16*>(dst_elu));
+  return check_launch("nchw_to_nhwc");
+}
+
+extern "C" int vub_nhwc_bf16_to_nchw_f32(const void* src, int32_t batch, int32_t c, int32_t h,
+                                         int32_t w, float* dst, void* stream) {
+  clear_error();
+  if (!src || !dst) return fail(VUB_E_NULL, "nhwc_to_nchw: NULL pointer");
+  if (batch <= 0 || c <= 0 || h <= 0 || w <= 0 || batch > 65535)
+    return fail(VUB_E_SHAPE, "nhwc_to_nchw: bad shape");
+  const int hw = h * w;
+  dim3 grid((hw + 31) / 32, (c + 31) / 32, batch);
+  nhwc_to_nchw_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), c, hw, dst);
+  return check_launch("nhwc_to_nchw");
+}

@@ -1,0 +1,143 @@
+/*
+ * vunet_b200 — C ABI of the B200-native VUnet hot path.
+ *
+ * Every entry point takes plain device pointers + sizes and a CUDA stream (as void*), launches
+ * hand-written sm_100a kernels asynchronously on that stream and returns
+ *      0            success
+ *     <0            bad argument (see VUB_E_*; vub_last_error() has a message)
+ *     >0            a cudaError_t / CUresult raised by the launch
+ * Nothing throws across the boundary, the caller owns every buffer, and there is no CPU fallback:
+ * without a CUDA device the launchers return an error.
+ *
+ * Each function cites the reference code (CompVis/behavior-driven-video-synthesis) it replaces.
+ * The Python host (`behavior-driven-video-synthesis_b200/`) binds these with ctypes and registers
+ * them as torch ops; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Tensor conventions: activations inside the path are NHWC bf16 ("raw" = the tensor as produced,
+ * "elu" = ELU(tensor), stored side by side because every consumer wants one or the other, see
+ * SURVEY.md App. B); tensors crossing the module boundary are NCHW fp32 like the reference's.
+ */
+#ifndef VUNET_B200_H_
+#define VUNET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VUB_ABI_VERSION 1
+
+#define VUB_OK 0
+#define VUB_E_NULL (-1)        /* required pointer is NULL */
+#define VUB_E_SHAPE (-2)       /* unsupported shape (non power-of-two extent, bad channel count) */
+#define VUB_E_FLAGS (-3)       /* inconsistent flag / output combination */
+#define VUB_E_ALIGN (-4)       /* pointer not 16-byte aligned */
+#define VUB_E_NODRIVER (-5)    /* CUDA driver entry point unavailable (no GPU / no driver) */
+
+/* vub_conv_desc.flags */
+#define VUB_CONV_D2S 1u        /* store through DepthToSpace(2) (lib/modules.py:24-34, DCR order) */
+#define VUB_CONV_F32_NHWC 2u   /* out_f32 is [B,Ho,Wo,cout] fp32 */
+#define VUB_CONV_F32_NCHW 4u   /* out_f32 is [B,cout_valid,Ho,Wo] fp32 */
+
+/* ABI version of the loaded library (== VUB_ABI_VERSION it was built with). */
+int vub_abi_version(void);
+/* Message for the last non-zero return on this thread ("" if none). */
+const char* vub_last_error(void);
+
+/*
+ * Weight-normalised convolution, forward:  NormConv2d.forward (lib/modules.py:140-145) with the
+ * callers' surrounding elementwise work fused in:
+ *     u      = conv2d(cat[x0, x1], v_hat)            v_hat = v / ||v||  (packed bf16, see vub_wn_prep)
+ *     y      = scale * u + shift (+ residual)        scale = gamma*g, shift = gamma*bias + beta
+ *     out_raw = bf16(y), out_elu = bf16(ELU(y))      (VunetRNB's act_fn, lib/modules.py:225,229)
+ * `x0`/`x1` are the two halves of VunetRNB's torch.cat (lib/modules.py:227) — the concat is never
+ * materialised.  ksize 3 => padding 1, ksize 1 => padding 0 (the only combinations the VUnet uses:
+ * lib/modules.py:153,170,203,214; models/vunets.py:117,288,523,539).  stride 2 = Downsample
+ * (lib/modules.py:148-161).  VUB_CONV_D2S = Upsample's DepthToSpace (lib/modules.py:164-182).
+ * Implicit GEMM on tcgen05: M = 128 output pixels, N = cout tile, K = (source, tap, channel).
+ */
+typedef struct vub_conv_desc {
+  const void* x[2];      /* NHWC bf16 [batch, hin, win, c_src]; x[1] NULL when nsrc == 1 */
+  const void* w;         /* packed bf16 [cout_pad, nsrc*ksize*ksize*c_src], K order (src, tap, c) */
+  const float* scale;    /* [cout_pad] */
+  const float* shift;    /* [cout_pad] */
+  const void* residual;  /* NHWC bf16 [batch, hout, wout, cout] or NULL */
+  void* out_raw;         /* NHWC bf16 or NULL */
+  void* out_elu;         /* NHWC bf16 or NULL */
+  void* out_f32;         /* fp32, layout per flags, or NULL */
+  int32_t nsrc;          /* 1 or 2 */
+  int32_t c_src;         /* channels per source: 32, 64 or 128 */
+  int32_t batch, hin, win;
+  int32_t cout;          /* GEMM N = rows of w (padded to 16/32/64/128/256/512) */
+  int32_t cout_valid;    /* channels actually stored (== cout except for out_conv) */
+  int32_t ksize;         /* 1 or 3 */
+  int32_t stride;        /* 1 or 2 */
+  uint32_t flags;
+  int32_t stages;        /* smem pipeline depth, 0 = library default */
+} vub_conv_desc;
+
+int vub_conv_fwd(const vub_conv_desc* d, void* stream);
+
+/*
+ * Weight-norm preparation for many layers in one launch: replaces the per-forward
+ * `torch.nn.utils.weight_norm` hook of every NormConv2d (lib/modules.py:135-138) and folds
+ * gamma/beta/bias (lib/modules.py:144) into one fp32 scale/shift pair per output channel.
+ * `table` is a DEVICE array of n_entries entries; entry e covers rows
+ * [row_start, row_start + cout) of the launch grid; total_rows = sum of cout.
+ */
+typedef struct vub_wn_entry {
+  const float* v;      /* conv.weight_v [cout, cin, k, k] */
+  const float* g;      /* conv.weight_g [cout] */
+  const float* gamma;  /* gamma [cout] */
+  const float* beta;   /* beta [cout] */
+  const float* bias;   /* conv.bias [cout] */
+  void* w_packed;      /* bf16, first row of this layer in its packed matrix (row pitch ktot) */
+  float* scale;        /* [cout] */
+  float* shift;        /* [cout] */
+  int32_t cout, cin, ktaps, c_src; /* cin = nsrc * c_src; ktaps = k*k */
+  int32_t ktot;        /* row pitch of the packed matrix in elements (= cin*ktaps) */
+  int32_t row_start;
+} vub_wn_entry;
+
+int vub_wn_prep(const vub_wn_entry* table_dev, int32_t n_entries, int32_t total_rows, void* stream);
+
+/*
+ * First 1x1 NormConv2d of EncUp / DecUp (models/vunets.py:117-119,137 and 230-232,250) fused with the
+ * layout/dtype change: x NCHW fp32 [batch, cx, h, w] -> NHWC bf16 [batch, h, w, cout] raw and ELU.
+ * K = cx (3 or 30) is not a tensor-core shape: CUDA-core kernel, HBM bound.  Takes the layer's raw
+ * parameters (weight-norm done in-kernel).  cout must be 32 or 64.
+ */
+int vub_stem_fwd(const float* x_nchw, const float* v, const float* g, const float* gamma,
+                 const float* beta, const float* bias, int32_t batch, int32_t cx, int32_t h,
+                 int32_t w, int32_t cout, void* out_raw, void* out_elu, void* stream);
+
+/*
+ * Latent head: EncDownAlter's squash + reparametrize (models/vunets.py:575,594-597) and the KL
+ * summand of lib/losses.py:283-291, from the fused (mu || logit) conv output.
+ *   ml_nhwc  fp32 [batch, h, w, 2c]  (cols [0,c) = make_latent_params, [c,2c) = make_logstds)
+ *   eps_nchw fp32 [batch, c, h, w]   (torch.randn_like draw, reference order)
+ *   logstd = sigmoid(logit); z = mu + exp(logstd) * eps
+ * Writes mu/logstd/z NCHW fp32 (returned to the caller), ELU(z) and ELU(mu) NHWC bf16 (next convs'
+ * operands; either may be NULL) and one partial sum of (-logstd + 0.5*(exp(2 logstd) + mu^2)) per
+ * block into kl_partial[0 .. vub_latent_num_partials(...)).
+ */
+int32_t vub_latent_num_partials(int32_t batch, int32_t c, int32_t h, int32_t w);
+int vub_latent_fwd(const float* ml_nhwc, const float* eps_nchw, int32_t batch, int32_t c, int32_t h,
+                   int32_t w, float* mu_nchw, float* logstd_nchw, float* z_nchw, void* elu_z_nhwc,
+                   void* elu_mu_nhwc, float* kl_partial, void* stream);
+
+/*
+ * Layout converters at the module boundary (the reference is NCHW fp32 throughout):
+ * NCHW fp32 -> NHWC bf16 raw and/or ELU (DecDownAlter's prior sample, models/vunets.py:352-354),
+ * and NHWC bf16 -> NCHW fp32 for callers that want reference-layout activations.
+ */
+int vub_nchw_f32_to_nhwc_bf16(const float* src, int32_t batch, int32_t c, int32_t h, int32_t w,
+                              void* dst_raw, void* dst_elu, void* stream);
+int vub_nhwc_bf16_to_nchw_f32(const void* src, int32_t batch, int32_t c, int32_t h, int32_t w,
+                              float* dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VUNET_B200_H_ */
