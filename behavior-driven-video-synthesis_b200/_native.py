@@ -1,0 +1,142 @@
+"""ctypes binding of the C-ABI library ``libvunet_b200.so`` (declared in ``include/vunet_b200.h``).
+
+There is deliberately no fallback: if the library is missing or a launcher returns non-zero, a
+``RuntimeError`` is raised.  ``build()`` compiles the library in-tree with nvcc for sm_100a.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvunet_b200.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "vunet_b200.h")
+
+# vub_conv_desc.flags (include/vunet_b200.h)
+CONV_D2S = 1
+CONV_F32_NHWC = 2
+CONV_F32_NCHW = 4
+
+# every extern "C" symbol the header declares; tests check the built library exports all of them
+EXPORTED_SYMBOLS = (
+    "vub_abi_version",
+    "vub_last_error",
+    "vub_conv_fwd",
+    "vub_wn_prep",
+    "vub_stem_fwd",
+    "vub_latent_num_partials",
+    "vub_latent_fwd",
+    "vub_nchw_f32_to_nhwc_bf16",
+    "vub_nhwc_bf16_to_nchw_f32",
+)
+
+
+class ConvDesc(C.Structure):
+    """Mirror of ``vub_conv_desc``."""
+
+    _fields_ = [
+        ("x", C.c_void_p * 2),
+        ("w", C.c_void_p),
+        ("scale", C.c_void_p),
+        ("shift", C.c_void_p),
+        ("residual", C.c_void_p),
+        ("out_raw", C.c_void_p),
+        ("out_elu", C.c_void_p),
+        ("out_f32", C.c_void_p),
+        ("nsrc", C.c_int32),
+        ("c_src", C.c_int32),
+        ("batch", C.c_int32),
+        ("hin", C.c_int32),
+        ("win", C.c_int32),
+        ("cout", C.c_int32),
+        ("cout_valid", C.c_int32),
+        ("ksize", C.c_int32),
+        ("stride", C.c_int32),
+        ("flags", C.c_uint32),
+        ("stages", C.c_int32),
+    ]
+
+
+class WnEntry(C.Structure):
+    """Mirror of ``vub_wn_entry``."""
+
+    _fields_ = [
+        ("v", C.c_void_p),
+        ("g", C.c_void_p),
+        ("gamma", C.c_void_p),
+        ("beta", C.c_void_p),
+        ("bias", C.c_void_p),
+        ("w_packed", C.c_void_p),
+        ("scale", C.c_void_p),
+        ("shift", C.c_void_p),
+        ("cout", C.c_int32),
+        ("cin", C.c_int32),
+        ("ktaps", C.c_int32),
+        ("c_src", C.c_int32),
+        ("ktot", C.c_int32),
+        ("row_start", C.c_int32),
+    ]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def build(verbose: bool = False) -> str:
+    """Compile ``csrc/*.cu`` into ``libvunet_b200.so`` (nvcc, -gencode arch=compute_100a,code=sm_100a)."""
+    proc = subprocess.run(
+        ["make", "-C", CSRC_DIR, "-j8"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True
+    )
+    if verbose:
+        print(proc.stdout)
+    if proc.returncode != 0 or not os.path.exists(LIB_PATH):
+        raise RuntimeError("building libvunet_b200.so failed:\n" + proc.stdout[-4000:])
+    return LIB_PATH
+
+
+def _declare(lib: C.CDLL) -> None:
+    vp, i32, fp = C.c_void_p, C.c_int32, C.c_void_p
+    lib.vub_abi_version.restype = C.c_int
+    lib.vub_abi_version.argtypes = []
+    lib.vub_last_error.restype = C.c_char_p
+    lib.vub_last_error.argtypes = []
+    lib.vub_conv_fwd.restype = C.c_int
+    lib.vub_conv_fwd.argtypes = [C.POINTER(ConvDesc), vp]
+    lib.vub_wn_prep.restype = C.c_int
+    lib.vub_wn_prep.argtypes = [vp, i32, i32, vp]
+    lib.vub_stem_fwd.restype = C.c_int
+    lib.vub_stem_fwd.argtypes = [fp, fp, fp, fp, fp, fp, i32, i32, i32, i32, i32, vp, vp, vp]
+    lib.vub_latent_num_partials.restype = i32
+    lib.vub_latent_num_partials.argtypes = [i32, i32, i32, i32]
+    lib.vub_latent_fwd.restype = C.c_int
+    lib.vub_latent_fwd.argtypes = [fp, fp, i32, i32, i32, i32, fp, fp, fp, vp, vp, fp, vp]
+    lib.vub_nchw_f32_to_nhwc_bf16.restype = C.c_int
+    lib.vub_nchw_f32_to_nhwc_bf16.argtypes = [fp, i32, i32, i32, i32, vp, vp, vp]
+    lib.vub_nhwc_bf16_to_nchw_f32.restype = C.c_int
+    lib.vub_nhwc_bf16_to_nchw_f32.argtypes = [vp, i32, i32, i32, i32, fp, vp]
+
+
+def lib() -> C.CDLL:
+    """The loaded C-ABI library; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} is missing: the CUDA extension is not built. Run "
+                        "`python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)."
+                    )
+                handle = C.CDLL(LIB_PATH)
+                _declare(handle)
+                _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().vub_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed with code {rc}: {msg}")

@@ -1,0 +1,31 @@
+"""KL terms of the VUnet objective — mirror of the reference's ``lib/losses.py:68-78, 283-291``.
+
+``kl_loss(mu, logstd)``: ``mean_b( sum_d(-logstd + 0.5*(exp(logstd)^2 + mu^2)) - 0.5*D )`` and
+``compute_kl_with_prior(means, logstds)``: the mean of ``kl_loss`` over latent scales.
+
+When ``means`` come from this package's forward pass they carry the per-block partial sums the fused
+latent kernel already produced (``vub_latent_fwd``), so no second pass over the latents is made; for
+foreign tensors the same formula is evaluated with torch ops on the tensors' device.
+"""
+from __future__ import annotations
+
+import torch
+
+
+def kl_loss(mu: torch.Tensor, logstd: torch.Tensor) -> torch.Tensor:
+    part = getattr(mu, "_vub_kl_partial", None)
+    if part is not None and getattr(mu, "_vub_logstd", None) is logstd:
+        b = mu.shape[0]
+        dim = mu.numel() // b
+        return part.sum() / b - 0.5 * dim
+    mu2 = mu.reshape(mu.size(0), -1)
+    ls2 = logstd.reshape(logstd.size(0), -1)
+    dim = mu2.shape[1]
+    std = torch.exp(ls2)
+    kl = torch.sum(-ls2 + 0.5 * (std ** 2 + mu2 ** 2), dim=-1) - (0.5 * dim)
+    return kl.mean()
+
+
+def compute_kl_with_prior(means, logstds) -> torch.Tensor:
+    terms = [kl_loss(m, l).unsqueeze(-1) for m, l in zip(means, logstds)]
+    return torch.mean(torch.cat(terms, dim=-1))

@@ -1,0 +1,395 @@
+"""Conv building blocks of the VUnet — host-side mirror of the reference's ``lib/modules.py:11-233``.
+
+Same class names, constructor arguments, parameter names/shapes/registration order (so
+``state_dict()`` round-trips with reference checkpoints) and the same initialisation stream; the
+arithmetic runs in the sm_100a kernels behind ``torch.ops.vunet_b200`` (no torch conv, no CPU path).
+
+Public ``forward`` methods take/return NCHW tensors like the reference.  Internally an activation is
+an :class:`Act` (NHWC bf16, raw and/or ELU'd copy); tensors returned by ``forward`` are NCHW *views*
+of the raw copy that carry their ``Act`` so that chained blocks never convert layouts.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Iterable, List, Optional, Sequence, Tuple, Union
+
+import torch
+from torch import nn
+
+from . import _native as N
+from . import ops
+
+_SUPPORTED_C = (32, 64, 128)
+
+
+class Act:
+    """One activation of the path, NHWC bf16: ``raw`` = as produced, ``elu`` = ELU(raw)."""
+
+    __slots__ = ("raw", "elu")
+
+    def __init__(self, raw: Optional[torch.Tensor], elu: Optional[torch.Tensor]):
+        self.raw = raw
+        self.elu = elu
+
+    @property
+    def any(self) -> torch.Tensor:
+        return self.raw if self.raw is not None else self.elu
+
+    def nchw(self) -> torch.Tensor:
+        """NCHW-shaped (channels-last strided) view of the raw copy that remembers this Act."""
+        if self.raw is None:
+            raise RuntimeError("activation has no raw copy")
+        t = self.raw.permute(0, 3, 1, 2)
+        t._vub_act = self
+        return t
+
+
+def to_act(t: Union[torch.Tensor, Act], need_raw: bool = True, need_elu: bool = True) -> Act:
+    """Accepts an Act, a tensor produced by this package, or any NCHW tensor (converted on the GPU)."""
+    if isinstance(t, Act):
+        act = t
+    else:
+        act = getattr(t, "_vub_act", None)
+    if act is not None and (act.raw is not None or not need_raw) and (act.elu is not None or not need_elu):
+        return act
+    if act is not None and act.raw is not None:
+        t = ops.nhwc_to_nchw(act.raw)
+    if not t.is_cuda:
+        raise RuntimeError("vunet_b200 has no CPU path: inputs must live on a CUDA device")
+    raw, elu = ops.nchw_to_nhwc(t.float(), need_raw, need_elu)
+    return Act(raw, elu)
+
+
+# ------------------------------------------------------------------------------------------------
+# Prepared (weight-normalised, packed) weights
+# ------------------------------------------------------------------------------------------------
+class ConvWeights:
+    """Packed bf16 ``v/||v||`` [cout_pad, K] + fp32 scale/shift of one (possibly merged) conv."""
+
+    __slots__ = ("w", "scale", "shift", "cout", "cout_pad", "nsrc", "c_src", "ksize", "stride")
+
+    def __init__(self, w, scale, shift, cout, cout_pad, nsrc, c_src, ksize, stride):
+        self.w, self.scale, self.shift = w, scale, shift
+        self.cout, self.cout_pad = cout, cout_pad
+        self.nsrc, self.c_src, self.ksize, self.stride = nsrc, c_src, ksize, stride
+
+
+def _pad_cout(c: int) -> int:
+    for p in (16, 32, 64, 128, 256, 512):
+        if c <= p:
+            return p
+    raise NotImplementedError(f"no kernel for {c} output channels")
+
+
+class WeightBank:
+    """All tensor-core convs of a module tree, prepared by ONE ``wn_prep`` launch per refresh.
+
+    ``slots`` is a list of lists of :class:`NormConv2d`; the members of a slot share their input and
+    are packed one after another along the output-channel axis (the latent mu/logstd pair).
+    """
+
+    def __init__(self, slots: Sequence[Sequence["NormConv2d"]]):
+        self.slots = [list(s) for s in slots]
+        self._key = None
+        self._device = None
+        self._views = {}
+
+    @staticmethod
+    def for_module(root: nn.Module) -> "WeightBank":
+        merged_second = {}
+        for m in root.modules():
+            for a, b in getattr(m, "_vub_merged_pairs", ()):
+                merged_second[id(b)] = a
+        slots, index = [], {}
+        for m in root.modules():
+            if isinstance(m, NormConv2d) and not m._vub_stem and id(m) not in merged_second:
+                index[id(m)] = len(slots)
+                slots.append([m])
+        for m in root.modules():
+            if isinstance(m, NormConv2d) and id(m) in merged_second:
+                slots[index[id(merged_second[id(m)])]].append(m)
+        return WeightBank(slots)
+
+    # -- allocation -------------------------------------------------------------------------------
+    def _allocate(self, device: torch.device) -> None:
+        w_off, s_off, rows = 0, 0, 0
+        layout = []
+        for slot in self.slots:
+            first = slot[0]
+            k = first.in_channels * first.kernel_size ** 2
+            cout = sum(m.out_channels for m in slot)
+            for m in slot:
+                if m.in_channels * m.kernel_size ** 2 != k or m._vub_split != first._vub_split:
+                    raise ValueError("merged convs must share their input geometry")
+            nsrc = first._vub_split
+            c_src = first.in_channels // nsrc
+            if c_src not in _SUPPORTED_C:
+                raise NotImplementedError(
+                    f"no tensor-core kernel for {first.in_channels} input channels split {nsrc} ways "
+                    f"(supported per-source channel counts: {_SUPPORTED_C})")
+            cpad = _pad_cout(cout)
+            layout.append((w_off, s_off, k, cout, cpad, nsrc, c_src))
+            w_off += cpad * k
+            s_off += cpad
+        self._w = torch.zeros(w_off, dtype=torch.bfloat16, device=device)
+        self._scale = torch.zeros(s_off, dtype=torch.float32, device=device)
+        self._shift = torch.zeros(s_off, dtype=torch.float32, device=device)
+        entries = []
+        self._views = {}
+        for slot, (wo, so, k, cout, cpad, nsrc, c_src) in zip(self.slots, layout):
+            first = slot[0]
+            w = self._w[wo:wo + cpad * k].view(cpad, k)
+            sc = self._scale[so:so + cpad]
+            sh = self._shift[so:so + cpad]
+            self._views[id(first)] = ConvWeights(w, sc, sh, cout, cpad, nsrc, c_src, first.kernel_size,
+                                                 first.stride)
+            r = 0
+            for m in slot:
+                e = N.WnEntry()
+                e.v = m.conv.weight_v.data_ptr()
+                e.g = m.conv.weight_g.data_ptr()
+                e.gamma = m.gamma.data_ptr()
+                e.beta = m.beta.data_ptr()
+                e.bias = m.conv.bias.data_ptr()
+                e.w_packed = w.data_ptr() + r * k * 2
+                e.scale = sc.data_ptr() + r * 4
+                e.shift = sh.data_ptr() + r * 4
+                e.cout, e.cin, e.ktaps, e.c_src = m.out_channels, m.in_channels, m.kernel_size ** 2, c_src
+                e.ktot, e.row_start = k, rows
+                rows += m.out_channels
+                r += m.out_channels
+                entries.append(e)
+        arr = (N.WnEntry * len(entries))(*entries)
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        self._table = host.to(device)
+        self._n_entries, self._rows = len(entries), rows
+        self._device = device
+
+    def _params(self) -> Iterable[torch.Tensor]:
+        for slot in self.slots:
+            for m in slot:
+                yield m.conv.weight_v
+                yield m.conv.weight_g
+                yield m.gamma
+                yield m.beta
+                yield m.conv.bias
+
+    def refresh(self) -> None:
+        """Re-run weight-norm preparation iff a parameter changed (version or storage)."""
+        params = list(self._params())
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("vunet_b200 has no CPU path: move the module to a CUDA device")
+        ptr_key = tuple(p.data_ptr() for p in params)
+        if self._device != dev or getattr(self, "_ptr_key", None) != ptr_key:
+            self._allocate(dev)
+            self._ptr_key = ptr_key
+            self._key = None
+        key = tuple(p._version for p in params)
+        if key != self._key:
+            ops.wn_prep(self._table, self._n_entries, self._rows)
+            self._key = key
+
+    def get(self, conv: "NormConv2d") -> ConvWeights:
+        return self._views[id(conv)]
+
+
+# ------------------------------------------------------------------------------------------------
+# Modules (names and signatures follow lib/modules.py)
+# ------------------------------------------------------------------------------------------------
+class SpaceToDepth(nn.Module):
+    """lib/modules.py:11-21 (pure index permutation; only ``VunetOrg`` uses it)."""
+
+    def __init__(self, block_size):
+        super().__init__()
+        self.bs = block_size
+
+    def forward(self, x):
+        n, c, h, w = x.size()
+        bs = self.bs
+        x = x.reshape(n, c, h // bs, bs, w // bs, bs).permute(0, 3, 5, 1, 2, 4)
+        return x.reshape(n, c * bs * bs, h // bs, w // bs)
+
+
+class DepthToSpace(nn.Module):
+    """lib/modules.py:24-34, DCR order: out[n,c,bs*h+i,bs*w+j] = in[n,(i*bs+j)*C'+c,h,w].
+
+    Inside the fused path this permutation is the store addressing of the up-sampling conv
+    (``VUB_CONV_D2S``); this module exists for API parity and standalone use.
+    """
+
+    def __init__(self, block_size):
+        super().__init__()
+        self.bs = block_size
+
+    def forward(self, x):
+        n, c, h, w = x.size()
+        bs = self.bs
+        x = x.reshape(n, bs, bs, c // (bs * bs), h, w).permute(0, 3, 4, 1, 5, 2)
+        return x.reshape(n, c // (bs * bs), h * bs, w * bs)
+
+
+class IDAct(nn.Module):
+    def forward(self, input):
+        return input
+
+
+class _WeightNormConvParams(nn.Module):
+    """Holds ``bias``, ``weight_g``, ``weight_v`` under the reference's names (``*.conv.*``)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride, padding):
+        super().__init__()
+        # Same initialisation stream as nn.Conv2d + weight_norm in the reference (lib/modules.py:135-138):
+        # kaiming-uniform v, uniform bias, g = ||v|| per output channel.
+        proto = nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding)
+        v = proto.weight.detach()
+        self.bias = nn.Parameter(proto.bias.detach().clone())
+        self.weight_g = nn.Parameter(torch.norm_except_dim(v, 2, 0).clone())
+        self.weight_v = nn.Parameter(v.clone())
+
+
+class NormConv2d(nn.Module):
+    """Weight-normalised conv with learned affine — lib/modules.py:120-145.
+
+    ``out = gamma * (conv2d(x, g * v/||v||) + bias) + beta``; parameters ``beta, gamma, conv.bias,
+    conv.weight_g, conv.weight_v`` in that order.
+    """
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0):
+        super().__init__()
+        if kernel_size not in (1, 3) or padding != kernel_size // 2 or stride not in (1, 2):
+            raise NotImplementedError("vunet_b200 kernels cover k in {1,3}, padding k//2, stride in {1,2}")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride, self.padding = kernel_size, stride, padding
+        self.beta = nn.Parameter(torch.zeros([1, out_channels, 1, 1], dtype=torch.float32))
+        self.gamma = nn.Parameter(torch.ones([1, out_channels, 1, 1], dtype=torch.float32))
+        self.conv = _WeightNormConvParams(in_channels, out_channels, kernel_size, stride, padding)
+        self._vub_split = 1      # number of concatenated sources feeding this conv
+        self._vub_stem = False   # K too small for tensor cores -> CUDA-core stem kernel
+        self._solo_bank: Optional[WeightBank] = None
+
+    # fused-path entry points -------------------------------------------------------------------
+    def _run(self, bank: WeightBank, srcs: Sequence[torch.Tensor], *, residual=None, want_raw=True,
+             want_elu=True, d2s=False) -> Act:
+        cw = bank.get(self)
+        raw, elu = ops.conv_fwd(srcs, cw.w, cw.scale, cw.shift, ksize=cw.ksize, stride=cw.stride,
+                                residual=residual, want_raw=want_raw, want_elu=want_elu, d2s=d2s)
+        return Act(raw, elu)
+
+    def _run_stem(self, x: torch.Tensor, want_raw=True, want_elu=True) -> Act:
+        c = self.conv
+        raw, elu = ops.stem_fwd(x, c.weight_v, c.weight_g, self.gamma, self.beta, c.bias, want_raw, want_elu)
+        return Act(raw, elu)
+
+    # reference-compatible standalone call -----------------------------------------------------
+    def forward(self, x):
+        if self.kernel_size == 1 and self.in_channels not in _SUPPORTED_C and self.out_channels in (32, 64):
+            if not x.is_cuda:
+                raise RuntimeError("vunet_b200 has no CPU path: inputs must live on a CUDA device")
+            return self._run_stem(x.float()).nchw()
+        if self._solo_bank is None:
+            self._solo_bank = WeightBank([[self]])
+        self._solo_bank.refresh()
+        cw = self._solo_bank.get(self)
+        act = to_act(x, need_raw=True, need_elu=False)
+        if cw.cout_pad == cw.cout and self.stride == 1:
+            out = ops.conv_fwd_f32([act.raw], cw.w, cw.scale, cw.shift, ksize=cw.ksize, layout="nhwc")
+            return out.permute(0, 3, 1, 2)
+        if self.stride == 1:
+            return ops.conv_fwd_f32([act.raw], cw.w, cw.scale, cw.shift, ksize=cw.ksize, layout="nchw",
+                                    cout_valid=cw.cout)
+        return self._run(self._solo_bank, [act.raw]).nchw()
+
+
+class Downsample(nn.Module):
+    """lib/modules.py:148-161: 3x3 stride-2 NormConv2d on the raw activation."""
+
+    def __init__(self, channels, out_channels=None, conv_layer=NormConv2d):
+        super().__init__()
+        self.down = conv_layer(channels, channels if out_channels is None else out_channels,
+                               kernel_size=3, stride=2, padding=1)
+
+    def _run(self, bank, h: Act, want_raw=True, want_elu=True) -> Act:
+        return self.down._run(bank, [h.raw], want_raw=want_raw, want_elu=want_elu)
+
+    def forward(self, x):
+        bank = _solo_bank(self)
+        return self._run(bank, to_act(x, True, False)).nchw()
+
+
+class Upsample(nn.Module):
+    """lib/modules.py:164-182 (sub-pixel branch): 3x3 conv to 4*C' channels + DepthToSpace(2),
+    fused into one kernel (the shuffle is the epilogue's store addressing)."""
+
+    def __init__(self, in_channels, out_channels, subpixel=True, conv_layer=NormConv2d):
+        super().__init__()
+        if not subpixel:
+            raise NotImplementedError("bilinear Upsample (subpixel=False) is outside the B200 hot path; "
+                                      "every shipped config sets subpixel_upsampling: True")
+        self.up = conv_layer(in_channels, 4 * out_channels, 3, padding=1)
+        self.op2 = DepthToSpace(block_size=2)
+
+    def _run(self, bank, h: Act, want_raw=True, want_elu=True) -> Act:
+        return self.up._run(bank, [h.raw], want_raw=want_raw, want_elu=want_elu, d2s=True)
+
+    def forward(self, x):
+        bank = _solo_bank(self)
+        return self._run(bank, to_act(x, True, False)).nchw()
+
+
+class VunetRNB(nn.Module):
+    """Residual block — lib/modules.py:185-233:
+    ``x + conv3x3(ELU(cat[x, nin1x1(ELU(a))]))`` (or ``x + conv3x3(ELU(x))`` without ``a``).
+
+    Fused schedule: ``nin`` reads the stored ELU(a) and stores only ELU(n); the 3x3 conv reads the two
+    ELU'd sources through two TMA maps (no concat tensor), adds the raw ``x`` in its epilogue and
+    stores the result raw and/or ELU'd for its consumers.
+    """
+
+    def __init__(self, channels, a_channels=None, residual=False, kernel_size=3, activate=True,
+                 conv_layer=NormConv2d, act_fn=None, dropout_prob=0.0):
+        super().__init__()
+        if not activate or act_fn is not None or kernel_size != 3:
+            raise NotImplementedError("vunet_b200 VunetRNB fuses ELU and a 3x3 conv (the only variant the VUnet uses)")
+        self.residual = residual
+        self.dout = nn.Dropout(p=dropout_prob)
+        if self.residual:
+            assert a_channels is not None
+            self.nin = conv_layer(a_channels, channels, kernel_size=1)
+            self.nin._vub_split = max(1, a_channels // channels)
+        self.act_fn = nn.ELU()
+        in_c = 2 * channels if self.residual else channels
+        self.conv = conv_layer(in_channels=in_c, out_channels=channels, kernel_size=kernel_size,
+                               padding=kernel_size // 2)
+        self.conv._vub_split = 2 if self.residual else 1
+
+    def _run(self, bank, x: Act, a: Union[None, Act, Sequence[Act]] = None, want_raw=True,
+             want_elu=True) -> Act:
+        if self.dout.p > 0.0 and self.training:
+            raise NotImplementedError("dropout_prob > 0 is not fused (the reference never enables it: SURVEY.md §3.3)")
+        srcs = [x.elu]
+        if a is not None:
+            assert self.residual
+            a_list = [a] if isinstance(a, Act) else list(a)
+            n = self.nin._run(bank, [t.elu for t in a_list], want_raw=False, want_elu=True)
+            srcs.append(n.elu)
+        return self.conv._run(bank, srcs, residual=x.raw, want_raw=want_raw, want_elu=want_elu)
+
+    def forward(self, x, a=None):
+        bank = _solo_bank(self)
+        xa = to_act(x)
+        aa = None if a is None else to_act(a, need_raw=False, need_elu=True)
+        if aa is not None and self.nin._vub_split == 2:
+            c = self.nin.in_channels // 2
+            aa = [Act(None, aa.elu[..., :c].contiguous()), Act(None, aa.elu[..., c:].contiguous())]
+        return self._run(bank, xa, aa).nchw()
+
+
+def _solo_bank(module: nn.Module) -> WeightBank:
+    bank = getattr(module, "_vub_bank", None)
+    if bank is None:
+        bank = WeightBank.for_module(module)
+        object.__setattr__(module, "_vub_bank", bank)
+    bank.refresh()
+    return bank

@@ -1,0 +1,250 @@
+"""Torch-op layer over the C ABI: ``torch.ops.vunet_b200.*``.
+
+Each op validates its tensors, allocates outputs with torch (device memory is torch's job) and
+launches the sm_100a kernel on torch's current CUDA stream through ``_native``.  The ops are
+registered for the CUDA dispatch key only — calling them with CPU tensors raises, by design.
+
+Activation convention inside the path: NHWC bf16 tensors ``[B, H, W, C]``; an activation usually
+exists as a (raw, elu) pair because every consumer wants one of the two.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _native as N
+
+_LIB = torch.library.Library("vunet_b200", "DEF")
+
+_LIB.define(
+    "conv_fwd(Tensor x0, Tensor? x1, Tensor w, Tensor scale, Tensor shift, Tensor? residual, "
+    "int ksize, int stride, int cout_valid, bool want_raw, bool want_elu, bool d2s, int f32_mode, "
+    "int stages) -> Tensor[]"
+)
+_LIB.define("wn_prep(Tensor table, int n_entries, int total_rows) -> ()")
+_LIB.define(
+    "stem_fwd(Tensor x, Tensor v, Tensor g, Tensor gamma, Tensor beta, Tensor bias, bool want_raw, "
+    "bool want_elu) -> Tensor[]"
+)
+_LIB.define("latent_fwd(Tensor ml, Tensor? eps, bool want_elu_z, bool want_elu_mu) -> Tensor[]")
+_LIB.define("nchw_to_nhwc(Tensor x, bool want_raw, bool want_elu) -> Tensor[]")
+_LIB.define("nhwc_to_nchw(Tensor x) -> Tensor")
+
+F32_NONE, F32_NHWC, F32_NCHW = 0, 1, 2
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _check_act(t: torch.Tensor, name: str) -> None:
+    if t.dtype != torch.bfloat16 or t.dim() != 4 or not t.is_contiguous():
+        raise ValueError(f"{name}: expected contiguous NHWC bf16 [B,H,W,C], got {t.dtype} {tuple(t.shape)}")
+
+
+def _conv_fwd_cuda(x0, x1, w, scale, shift, residual, ksize, stride, cout_valid, want_raw, want_elu,
+                   d2s, f32_mode, stages) -> List[torch.Tensor]:
+    _check_act(x0, "conv_fwd x0")
+    B, H, W, c_src = x0.shape
+    nsrc = 1
+    if x1 is not None:
+        _check_act(x1, "conv_fwd x1")
+        if x1.shape != x0.shape:
+            raise ValueError("conv_fwd: both sources must have the same shape")
+        nsrc = 2
+    cout = w.shape[0]
+    if w.dtype != torch.bfloat16 or w.shape[1] != nsrc * ksize * ksize * c_src:
+        raise ValueError(f"conv_fwd: packed weight {tuple(w.shape)} does not match nsrc={nsrc} k={ksize} c_src={c_src}")
+    Ho, Wo = H // stride, W // stride
+    d = N.ConvDesc()
+    d.x[0] = x0.data_ptr()
+    d.x[1] = _p(x1)
+    d.w = w.data_ptr()
+    d.scale = scale.data_ptr()
+    d.shift = shift.data_ptr()
+    d.residual = _p(residual)
+    outs: List[torch.Tensor] = []
+    flags = 0
+    if f32_mode == F32_NONE:
+        if d2s:
+            flags |= N.CONV_D2S
+            oshape = (B, 2 * Ho, 2 * Wo, cout // 4)
+        else:
+            oshape = (B, Ho, Wo, cout)
+        if residual is not None:
+            _check_act(residual, "conv_fwd residual")
+            if tuple(residual.shape) != oshape:
+                raise ValueError("conv_fwd: residual shape mismatch")
+        if want_raw:
+            raw = torch.empty(oshape, dtype=torch.bfloat16, device=x0.device)
+            d.out_raw = raw.data_ptr()
+            outs.append(raw)
+        if want_elu:
+            elu = torch.empty(oshape, dtype=torch.bfloat16, device=x0.device)
+            d.out_elu = elu.data_ptr()
+            outs.append(elu)
+    else:
+        if f32_mode == F32_NHWC:
+            flags |= N.CONV_F32_NHWC
+            out = torch.empty((B, Ho, Wo, cout), dtype=torch.float32, device=x0.device)
+        else:
+            flags |= N.CONV_F32_NCHW
+            out = torch.empty((B, cout_valid, Ho, Wo), dtype=torch.float32, device=x0.device)
+        d.out_f32 = out.data_ptr()
+        outs.append(out)
+    d.nsrc, d.c_src, d.batch, d.hin, d.win = nsrc, c_src, B, H, W
+    d.cout, d.cout_valid, d.ksize, d.stride = cout, cout_valid, ksize, stride
+    d.flags, d.stages = flags, stages
+    N.check(N.lib().vub_conv_fwd(C.byref(d), _stream()), "vub_conv_fwd")
+    return outs
+
+
+def _wn_prep_cuda(table, n_entries, total_rows) -> None:
+    N.check(N.lib().vub_wn_prep(table.data_ptr(), n_entries, total_rows, _stream()), "vub_wn_prep")
+
+
+def _stem_fwd_cuda(x, v, g, gamma, beta, bias, want_raw, want_elu) -> List[torch.Tensor]:
+    if x.dtype != torch.float32 or x.dim() != 4:
+        raise ValueError("stem_fwd: x must be NCHW fp32")
+    x = x.contiguous()
+    B, cx, H, W = x.shape
+    cout = v.shape[0]
+    outs = []
+    raw = elu = None
+    if want_raw:
+        raw = torch.empty((B, H, W, cout), dtype=torch.bfloat16, device=x.device)
+        outs.append(raw)
+    if want_elu:
+        elu = torch.empty((B, H, W, cout), dtype=torch.bfloat16, device=x.device)
+        outs.append(elu)
+    N.check(
+        N.lib().vub_stem_fwd(x.data_ptr(), v.data_ptr(), g.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                             bias.data_ptr(), B, cx, H, W, cout, _p(raw), _p(elu), _stream()),
+        "vub_stem_fwd",
+    )
+    return outs
+
+
+def _latent_fwd_cuda(ml, eps, want_elu_z, want_elu_mu) -> List[torch.Tensor]:
+    if ml.dtype != torch.float32 or ml.dim() != 4 or not ml.is_contiguous():
+        raise ValueError("latent_fwd: ml must be contiguous fp32 NHWC [B,h,w,2C]")
+    B, h, w, c2 = ml.shape
+    c = c2 // 2
+    if eps is not None:
+        if eps.dtype != torch.float32 or tuple(eps.shape) != (B, c, h, w) or not eps.is_contiguous():
+            raise ValueError("latent_fwd: eps must be contiguous fp32 NCHW [B,C,h,w]")
+    dev = ml.device
+    mu = torch.empty((B, c, h, w), dtype=torch.float32, device=dev)
+    ls = torch.empty_like(mu)
+    z = torch.empty_like(mu)
+    ez = torch.empty((B, h, w, c), dtype=torch.bfloat16, device=dev) if want_elu_z else None
+    em = torch.empty((B, h, w, c), dtype=torch.bfloat16, device=dev) if want_elu_mu else None
+    npart = N.lib().vub_latent_num_partials(B, c, h, w)
+    kl = torch.empty((npart,), dtype=torch.float32, device=dev)
+    N.check(
+        N.lib().vub_latent_fwd(ml.data_ptr(), _p(eps), B, c, h, w, mu.data_ptr(), ls.data_ptr(), z.data_ptr(),
+                               _p(ez), _p(em), kl.data_ptr(), _stream()),
+        "vub_latent_fwd",
+    )
+    outs = [mu, ls, z, kl]
+    if ez is not None:
+        outs.append(ez)
+    if em is not None:
+        outs.append(em)
+    return outs
+
+
+def _nchw_to_nhwc_cuda(x, want_raw, want_elu) -> List[torch.Tensor]:
+    if x.dtype != torch.float32 or x.dim() != 4:
+        raise ValueError("nchw_to_nhwc: x must be NCHW fp32")
+    x = x.contiguous()
+    B, c, H, W = x.shape
+    raw = torch.empty((B, H, W, c), dtype=torch.bfloat16, device=x.device) if want_raw else None
+    elu = torch.empty((B, H, W, c), dtype=torch.bfloat16, device=x.device) if want_elu else None
+    N.check(N.lib().vub_nchw_f32_to_nhwc_bf16(x.data_ptr(), B, c, H, W, _p(raw), _p(elu), _stream()),
+            "vub_nchw_f32_to_nhwc_bf16")
+    return [t for t in (raw, elu) if t is not None]
+
+
+def _nhwc_to_nchw_cuda(x) -> torch.Tensor:
+    _check_act(x, "nhwc_to_nchw x")
+    B, H, W, c = x.shape
+    out = torch.empty((B, c, H, W), dtype=torch.float32, device=x.device)
+    N.check(N.lib().vub_nhwc_bf16_to_nchw_f32(x.data_ptr(), B, c, H, W, out.data_ptr(), _stream()),
+            "vub_nhwc_bf16_to_nchw_f32")
+    return out
+
+
+_LIB.impl("conv_fwd", _conv_fwd_cuda, "CUDA")
+_LIB.impl("wn_prep", _wn_prep_cuda, "CUDA")
+_LIB.impl("stem_fwd", _stem_fwd_cuda, "CUDA")
+_LIB.impl("latent_fwd", _latent_fwd_cuda, "CUDA")
+_LIB.impl("nchw_to_nhwc", _nchw_to_nhwc_cuda, "CUDA")
+_LIB.impl("nhwc_to_nchw", _nhwc_to_nchw_cuda, "CUDA")
+
+_ops = torch.ops.vunet_b200
+
+
+# ------------------------------------------------------------------------------------------------
+# Convenience wrappers used by the modules
+# ------------------------------------------------------------------------------------------------
+def conv_fwd(x: Sequence[torch.Tensor], w, scale, shift, *, ksize: int, stride: int = 1,
+             residual: Optional[torch.Tensor] = None, want_raw: bool = True, want_elu: bool = True,
+             d2s: bool = False, cout_valid: Optional[int] = None, stages: int = 0
+             ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """bf16 NHWC outputs: returns (raw or None, elu or None)."""
+    cv = w.shape[0] if cout_valid is None else cout_valid
+    outs = _ops.conv_fwd(x[0], x[1] if len(x) > 1 else None, w, scale, shift, residual, ksize, stride, cv,
+                         want_raw, want_elu, d2s, F32_NONE, stages)
+    it = iter(outs)
+    raw = next(it) if want_raw else None
+    elu = next(it) if want_elu else None
+    return raw, elu
+
+
+def conv_fwd_f32(x: Sequence[torch.Tensor], w, scale, shift, *, ksize: int, layout: str,
+                 cout_valid: Optional[int] = None, stages: int = 0) -> torch.Tensor:
+    """fp32 output, ``layout`` in {"nhwc", "nchw"} (latent head input / out_conv image)."""
+    cv = w.shape[0] if cout_valid is None else cout_valid
+    mode = F32_NHWC if layout == "nhwc" else F32_NCHW
+    return _ops.conv_fwd(x[0], x[1] if len(x) > 1 else None, w, scale, shift, None, ksize, 1, cv, False, False,
+                         False, mode, stages)[0]
+
+
+def wn_prep(table: torch.Tensor, n_entries: int, total_rows: int) -> None:
+    _ops.wn_prep(table, n_entries, total_rows)
+
+
+def stem_fwd(x, v, g, gamma, beta, bias, want_raw=True, want_elu=True):
+    outs = _ops.stem_fwd(x, v, g, gamma, beta, bias, want_raw, want_elu)
+    it = iter(outs)
+    return (next(it) if want_raw else None), (next(it) if want_elu else None)
+
+
+def latent_fwd(ml, eps, want_elu_z=True, want_elu_mu=False):
+    """Returns dict(mu, logstd, z, kl_partial[, elu_z][, elu_mu])."""
+    outs = _ops.latent_fwd(ml, eps, want_elu_z, want_elu_mu)
+    res = {"mu": outs[0], "logstd": outs[1], "z": outs[2], "kl_partial": outs[3]}
+    i = 4
+    if want_elu_z:
+        res["elu_z"] = outs[i]
+        i += 1
+    if want_elu_mu:
+        res["elu_mu"] = outs[i]
+    return res
+
+
+def nchw_to_nhwc(x, want_raw=True, want_elu=True):
+    outs = _ops.nchw_to_nhwc(x, want_raw, want_elu)
+    it = iter(outs)
+    return (next(it) if want_raw else None), (next(it) if want_elu else None)
+
+
+def nhwc_to_nchw(x):
+    return _ops.nhwc_to_nchw(x)

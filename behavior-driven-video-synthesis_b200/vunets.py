@@ -1,0 +1,294 @@
+"""The shape-and-posture VUnet — host-side mirror of the reference's ``models/vunets.py``
+(``VunetAlter`` 426-515, ``EncUp`` 109-148, ``DecUp`` 222-261, ``EncDownAlter`` 520-597,
+``DecDownAlter`` 264-414).
+
+Same constructor (``VunetAlter(init_fn=None, n_channels_x=3, **kwargs)``, unknown kwargs ignored), same
+``forward(x, c)`` / ``transfer(x, c)`` / ``test_forward(c)`` signatures and return structure, same
+sub-module names and ``state_dict`` layout, same latent-noise draws (``torch.randn`` of the reference's
+shapes from the global generator, in the reference's order).  The arithmetic is the fused schedule of
+SURVEY.md App. B executed by sm_100a kernels; there is no torch conv and no CPU path.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import ops
+from .modules import (Act, DepthToSpace, Downsample, NormConv2d, SpaceToDepth, Upsample, VunetRNB,
+                      WeightBank, _solo_bank, to_act)
+
+
+def _draw_eps(shape, device) -> torch.Tensor:
+    """Latent noise exactly as the reference draws it: ``torch.randn_like(std)`` on an NCHW fp32
+    tensor of this shape from the global generator (models/vunets.py:596, 352)."""
+    return torch.randn(shape, dtype=torch.float32, device=device)
+
+
+class EncUp(nn.Module):
+    """models/vunets.py:109-148 — appearance encoder, bottom-up."""
+
+    def __init__(self, n_scales, n_filters, max_filters, nf_in=3, conv_layer=NormConv2d, dropout_prob=0.0):
+        super().__init__()
+        self.n_rnb = 2
+        self.n_scales = n_scales
+        self.nin = conv_layer(in_channels=nf_in, out_channels=n_filters, kernel_size=1)
+        self.nin._vub_stem = True
+        self.blocks = nn.ModuleList()
+        self.downs = nn.ModuleList()
+        nf = n_filters
+        for i in range(self.n_scales):
+            for n in range(self.n_rnb):
+                self.blocks.append(VunetRNB(channels=nf, conv_layer=conv_layer, dropout_prob=dropout_prob))
+            if i + 1 < self.n_scales:
+                out_c = min(2 * nf, max_filters)
+                self.downs.append(Downsample(nf, out_c))
+                nf = out_c
+
+    def _run(self, bank: WeightBank, x: torch.Tensor) -> List[Act]:
+        hs: List[Act] = []
+        h = self.nin._run_stem(x)
+        for i in range(self.n_scales):
+            for n in range(self.n_rnb):
+                h = self.blocks[2 * i + n]._run(bank, h)
+                hs.append(h)
+            if i + 1 < self.n_scales:
+                h = self.downs[i]._run(bank, h)
+        return hs
+
+    def forward(self, x, **kwargs):
+        bank = _solo_bank(self)
+        _require_cuda(x)
+        return [h.nchw() for h in self._run(bank, x.float())]
+
+
+class DecUp(EncUp):
+    """models/vunets.py:222-261 — pose (stickman) encoder; identical structure to :class:`EncUp`."""
+
+    def forward(self, c):
+        return super().forward(c)
+
+
+class EncDownAlter(nn.Module):
+    """models/vunets.py:520-597 — appearance encoder, top-down, with the per-scale latent heads."""
+
+    def __init__(self, n_filters, nf_in, subpixel_upsampling, n_scales=2, conv_layer=NormConv2d,
+                 dropout_prob=0.0):
+        super().__init__()
+        self.nin = conv_layer(nf_in, n_filters, kernel_size=1)
+        self.n_scales = n_scales
+        self.n_rnb = 2
+        self.blocks = nn.ModuleList()
+        self.ups = nn.ModuleList()
+        self.make_latent_params = nn.ModuleList()
+        self.make_logstds = nn.ModuleList()
+        nf = n_filters
+        for i in range(self.n_scales):
+            for n in range(self.n_rnb // 2):
+                self.blocks.append(VunetRNB(channels=nf, a_channels=nf, residual=True, dropout_prob=dropout_prob))
+            self.make_latent_params.append(conv_layer(nf, nf, kernel_size=3, padding=1))
+            self.make_logstds.append(conv_layer(nf, nf, kernel_size=3, padding=1))
+            for n in range(self.n_rnb // 2):
+                self.blocks.append(VunetRNB(channels=nf, a_channels=2 * nf, residual=True))
+            self.ups.append(Upsample(nf, nf, subpixel=True))
+        self.fin_block = VunetRNB(channels=nf, a_channels=nf, residual=True, dropout_prob=dropout_prob)
+        self.squash = nn.Sigmoid()
+        # mu and logstd convs read the same activation: one GEMM with N = 2*nf
+        self._vub_merged_pairs = [(self.make_latent_params[i], self.make_logstds[i]) for i in range(n_scales)]
+
+    def _latent(self, bank, i, h: Act, eps: Optional[torch.Tensor], want_elu_mu: bool):
+        cw = bank.get(self.make_latent_params[i])
+        ml = ops.conv_fwd_f32([h.raw], cw.w, cw.scale, cw.shift, ksize=3, layout="nhwc")
+        B, hh, ww, c2 = ml.shape
+        if eps is None:
+            eps = _draw_eps((B, c2 // 2, hh, ww), ml.device)
+        return ops.latent_fwd(ml, eps, want_elu_z=True, want_elu_mu=want_elu_mu)
+
+    def _run(self, bank, gs: List[Act], eps: Optional[Sequence[torch.Tensor]] = None, skip_dead=False,
+             want_elu_mu=False):
+        """``gs`` is consumed from the back exactly like the reference's ``gs.pop()`` calls.
+        Returns (hs, latents) where latents[i] is the dict from ``ops.latent_fwd``."""
+        hs: List[Act] = []
+        lat = []
+        h = self.nin._run(bank, [gs[-1].raw])
+        for i in range(self.n_scales):
+            h = self.blocks[2 * i]._run(bank, h, gs.pop())
+            hs.append(h)
+            res = self._latent(bank, i, h, None if eps is None else eps[i], want_elu_mu)
+            lat.append(res)
+            last = i + 1 == self.n_scales
+            if skip_dead and last:
+                # the reference computes blocks[2i+1], ups[i] and fin_block here but nothing that
+                # VunetAlter.forward/transfer return depends on them; keep its pops
+                gs.pop()
+                gs.pop()
+                break
+            z_act = Act(None, res["elu_z"])
+            h = self.blocks[2 * i + 1]._run(bank, h, [gs.pop(), z_act], want_elu=False)
+            hs.append(h)
+            h = self.ups[i]._run(bank, h)
+        else:
+            h = self.fin_block._run(bank, h, gs.pop())
+            hs.append(h)
+        return hs, lat
+
+    def forward(self, gs):
+        """Reference signature: pops from the caller's list; returns (hs, means, log_stds, zs)."""
+        bank = _solo_bank(self)
+        acts = [to_act(g) for g in gs]
+        n_before = len(acts)
+        hs, lat = self._run(bank, acts)
+        del gs[len(gs) - (n_before - len(acts)):]  # mirror the reference's in-place pops
+        means = [_tag_kl(r["mu"], r) for r in lat]
+        return [h.nchw() for h in hs], means, [r["logstd"] for r in lat], [r["z"] for r in lat]
+
+
+class DecDownAlter(nn.Module):
+    """models/vunets.py:264-414 — image decoder, top-down, skip connections from :class:`DecUp`."""
+
+    def __init__(self, n_scales, nf_in, nf_last, nf_out, subpixel_upsampling, conv_layer=NormConv2d,
+                 n_latent_scales=2, dropout_prob=0.0):
+        super().__init__()
+        self.n_rnb = 2
+        self.n_scales = n_scales
+        self.n_latent_scales = n_latent_scales
+        self.nin = conv_layer(nf_in, nf_in, kernel_size=1)
+        self.blocks = nn.ModuleList()
+        self.ups = nn.ModuleList()
+        self.auto_blocks = nn.ModuleList()
+        self.out_conv = conv_layer(nf_last, nf_out, kernel_size=3, padding=1)
+        self.depth_to_space = DepthToSpace(block_size=2)
+        self.space_to_depth = SpaceToDepth(block_size=2)
+        nf = nf_in
+        for i in range(self.n_scales):
+            for n in range(self.n_rnb // 2):
+                self.blocks.append(VunetRNB(channels=nf, a_channels=nf, residual=True, conv_layer=conv_layer,
+                                            dropout_prob=dropout_prob))
+            if i < self.n_latent_scales:
+                self.auto_blocks.append(VunetRNB(channels=nf, a_channels=nf, residual=True, conv_layer=conv_layer,
+                                                 dropout_prob=dropout_prob))
+            for n in range(self.n_rnb // 2):
+                self.blocks.append(VunetRNB(channels=nf, a_channels=nf, residual=True, conv_layer=conv_layer,
+                                            dropout_prob=dropout_prob))
+            if i + 1 < self.n_scales:
+                out_c = min(nf_in, nf_last * 2 ** (n_scales - (i + 2)))
+                if not subpixel_upsampling and i >= self.n_latent_scales:
+                    raise NotImplementedError("bilinear up-sampling is outside the B200 hot path")
+                self.ups.append(Upsample(nf, out_c, subpixel=True))
+                nf = out_c
+
+    def _run(self, bank, gs: List[Act], zs_elu: List[Optional[torch.Tensor]], training: bool) -> torch.Tensor:
+        """``zs_elu[i]``: NHWC bf16 ELU(z_i) (posterior sample or mean); ignored when ``training`` is False
+        (then z ~ N(0, I) is drawn like the reference, models/vunets.py:352)."""
+        gs = list(gs)
+        zs_elu = list(zs_elu)
+        h = self.nin._run(bank, [gs[-1].raw])
+        lat_count = 0
+        for i in range(self.n_scales):
+            h = self.blocks[2 * i]._run(bank, h, gs.pop())
+            if i < self.n_latent_scales:
+                if training:
+                    ez = zs_elu.pop(0)
+                else:
+                    B, hh, ww, cc = h.raw.shape
+                    ez = ops.nchw_to_nhwc(_draw_eps((B, cc, hh, ww), h.raw.device), False, True)[1]
+                h = self.auto_blocks[lat_count]._run(bank, h, Act(None, ez))
+                lat_count += 1
+            last = i + 1 == self.n_scales
+            h = self.blocks[2 * i + 1]._run(bank, h, gs.pop(), want_elu=False)
+            if not last:
+                h = self.ups[i]._run(bank, h)
+        assert not gs
+        if training:
+            assert not zs_elu
+        cw = bank.get(self.out_conv)
+        return ops.conv_fwd_f32([h.raw], cw.w, cw.scale, cw.shift, ksize=3, layout="nchw", cout_valid=cw.cout)
+
+    def forward(self, gs, zs_posterior, training):
+        bank = _solo_bank(self)
+        acts = [to_act(g) for g in gs]
+        zs = [to_act(z, need_raw=False, need_elu=True).elu for z in zs_posterior]
+        return self._run(bank, acts, zs, training)
+
+
+def _require_cuda(t: torch.Tensor) -> None:
+    if not t.is_cuda:
+        raise RuntimeError("vunet_b200 has no CPU path: inputs and the module must live on a CUDA device")
+
+
+def _tag_kl(mu: torch.Tensor, res: dict) -> torch.Tensor:
+    """Attach the fused KL partial sums to the returned mean so losses.compute_kl_with_prior can use them."""
+    mu._vub_kl_partial = res["kl_partial"]
+    mu._vub_logstd = res["logstd"]
+    return mu
+
+
+class VunetAlter(nn.Module):
+    """models/vunets.py:426-515."""
+
+    def __init__(self, init_fn=None, n_channels_x=3, **kwargs):
+        super().__init__()
+        self.spatial_size = kwargs["spatial_size"]
+        self.n_scales = (
+            1 + int(np.round(np.log2(kwargs["spatial_size"]))) - kwargs["bottleneck_factor"]
+            if kwargs["n_scales"] < 6 else kwargs["n_scales"]
+        )
+        self.n_scales_x = self.n_scales - kwargs["box_factor"] if n_channels_x > 3 else self.n_scales
+        self.n_channels_x = n_channels_x
+        n_latent_scales = kwargs["n_latent_scales"]
+        dropout_prob = kwargs["dropout_prob"] if "dropout_prob" in kwargs else 0.0
+        if kwargs["conv_layer_type"] != "l1":
+            raise NotImplementedError(
+                "vunet_b200 implements conv_layer_type 'l1' (NormConv2d), the type every shipped config uses")
+        print("Vunet using L1NormConv2d as conv layers.")
+        self.eu = EncUp(self.n_scales_x, n_filters=kwargs["nf_start"], max_filters=kwargs["nf_max"],
+                        conv_layer=NormConv2d, nf_in=n_channels_x, dropout_prob=dropout_prob)
+        self.ed = EncDownAlter(n_filters=kwargs["nf_max"], nf_in=kwargs["nf_max"], conv_layer=NormConv2d,
+                               n_scales=n_latent_scales, subpixel_upsampling=kwargs["subpixel_upsampling"],
+                               dropout_prob=dropout_prob)
+        self.du = DecUp(self.n_scales, n_filters=kwargs["nf_start"], max_filters=kwargs["nf_max"],
+                        conv_layer=NormConv2d, dropout_prob=dropout_prob)
+        self.dd = DecDownAlter(self.n_scales, kwargs["nf_max"], kwargs["nf_start"], nf_out=3,
+                               conv_layer=NormConv2d, n_latent_scales=n_latent_scales,
+                               subpixel_upsampling=kwargs["subpixel_upsampling"], dropout_prob=dropout_prob)
+
+    # ---------------------------------------------------------------------------------------------
+    def _bank(self) -> WeightBank:
+        return _solo_bank(self)
+
+    def _encode(self, bank, x, eps, skip_dead, want_elu_mu):
+        hs = self.eu._run(bank, x.float())
+        hs_all = list(hs)
+        es, lat = self.ed._run(bank, hs, eps=eps, skip_dead=skip_dead, want_elu_mu=want_elu_mu)
+        return hs_all, hs, lat
+
+    def forward(self, x, c, eps: Optional[Sequence[torch.Tensor]] = None):
+        """Returns ``(imgs, means, logstds, (hs, means, logstds))`` like the reference.  ``eps`` optionally
+        injects the latent noise (one NCHW fp32 tensor per latent scale) instead of drawing it."""
+        _require_cuda(x)
+        _require_cuda(c)
+        bank = self._bank()
+        _, hs_left, lat = self._encode(bank, x, eps, skip_dead=True, want_elu_mu=False)
+        gs = self.du._run(bank, c.float())
+        imgs = self.dd._run(bank, gs, [r["elu_z"] for r in lat], True)
+        means = [_tag_kl(r["mu"], r) for r in lat]
+        logstds = [r["logstd"] for r in lat]
+        # like the reference, `hs` is what ed's pops left of eu's outputs
+        activations = ([h.nchw() for h in hs_left], means, logstds)
+        return imgs, means, logstds, activations
+
+    def test_forward(self, c):
+        _require_cuda(c)
+        bank = self._bank()
+        gs = self.du._run(bank, c.float())
+        return self.dd._run(bank, gs, [], False)
+
+    def transfer(self, x, c, eps: Optional[Sequence[torch.Tensor]] = None):
+        _require_cuda(x)
+        _require_cuda(c)
+        bank = self._bank()
+        _, _, lat = self._encode(bank, x, eps, skip_dead=True, want_elu_mu=True)
+        gs = self.du._run(bank, c.float())
+        return self.dd._run(bank, gs, [r["elu_mu"] for r in lat], True)

@@ -1,0 +1,216 @@
+"""GPU (-m gpu): the CUDA path, called through the module API / torch ops / C ABI, against the CPU
+oracle on the same hashed inputs, against the committed golden vectors generated from the reference,
+and through size-independent properties at the BASELINE.json sizes.
+
+Tolerance (BASELINE.json north_star): relative L2 <= 1e-2 for bf16 images / latents; latent noise
+bit-exact with torch's generator.
+"""
+import contextlib
+import io
+
+import pytest
+import torch
+
+import vunet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 1e-2
+
+ARCH = dict(n_latent_scales=2, conv_layer_type="l1", subpixel_upsampling=True, n_scales=0, nf_start=32, nf_max=128)
+H256 = dict(ARCH, spatial_size=256, bottleneck_factor=2, box_factor=2, n_channels_x=3)
+D256 = dict(ARCH, spatial_size=256, bottleneck_factor=2, box_factor=2, n_channels_x=30)
+M128 = dict(ARCH, spatial_size=128, bottleneck_factor=1, box_factor=1, n_channels_x=30)
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def build(cfg, sd=None):
+    import bdvs_b200 as B
+    cfg = {k: v for k, v in cfg.items() if k != "batch"}
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = B.VunetAlter(**cfg)
+    if sd is None:
+        sd = O.det_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()})
+    m.load_state_dict(sd)
+    return m.cuda().eval(), sd
+
+
+def cuda(ts):
+    return [t.cuda() for t in ts]
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["tiny3", "tiny30", "market128"])
+def test_model_matches_reference_golden(golden, name):
+    fx = golden(name)
+    cfg = fx["config"]
+    m, sd = build(cfg)
+    x, c, eps, prior = O.make_inputs(cfg, cfg["batch"])
+    with torch.no_grad():
+        imgs, means, logstds, acts = m(x.cuda(), c.cuda(), eps=cuda(eps))
+        timgs = m.transfer(x.cuda(), c.cuda(), eps=cuda(eps))
+    assert imgs.shape == fx["imgs"].shape and imgs.dtype == torch.float32
+    assert rel(imgs, fx["imgs"]) < BF16_TOL
+    assert rel(timgs, fx["transfer"]) < BF16_TOL
+    for i in range(2):
+        assert rel(means[i], fx["means"][i]) < BF16_TOL
+        assert rel(logstds[i], fx["logstds"][i]) < BF16_TOL
+    # return structure of the reference: activations = (hs left after ed's pops, means, logstds)
+    assert len(acts[0]) == fx["n_hs_left"]
+    assert [tuple(a.shape) for a in acts[0]] == fx["hs_left_shapes"]
+    for a, ref_mean_abs in zip(acts[0], fx["hs_left_mean_abs"]):
+        assert abs(float(a.float().abs().mean()) - ref_mean_abs) < 2e-2 * ref_mean_abs + 1e-3
+    assert acts[1] is means and acts[2] is logstds
+    # fused KL against the reference's value
+    import bdvs_b200 as B
+    kl = float(B.compute_kl_with_prior(means, logstds))
+    assert abs(kl - fx["kl"]) < 5e-3 * abs(fx["kl"])
+
+
+@pytest.mark.parametrize("name", ["tiny3", "tiny30"])
+def test_test_forward_and_submodules_match_golden(golden, name):
+    fx = golden(name)
+    cfg = fx["config"]
+    m, sd = build(cfg)
+    x, c, eps, prior = O.make_inputs(cfg, cfg["batch"])
+    with torch.no_grad():
+        # prior sampling: inject the prior draws through torch.randn the way the module draws them
+        import bdvs_b200.vunets as V
+        draws = iter(cuda(prior))
+        orig = V._draw_eps
+        V._draw_eps = lambda shape, device: next(draws)
+        try:
+            pimgs = m.test_forward(c.cuda())
+        finally:
+            V._draw_eps = orig
+        assert rel(pimgs, fx["test_forward"]) < BF16_TOL
+        # vunet.ed(vunet.eu(x)) as experiments/shape_and_pose_net.py:413 calls it
+        draws = iter(cuda(eps))
+        V._draw_eps = lambda shape, device: next(draws)
+        try:
+            hs_in = m.eu(x.cuda())
+            n_in = len(hs_in)
+            hs, means, logstds, zs = m.ed(hs_in)
+        finally:
+            V._draw_eps = orig
+    assert n_in - len(hs_in) == 5  # ed popped five of eu's outputs in place, like the reference
+    assert [tuple(h.shape) for h in hs] == fx["ed_hs_shapes"]
+    for i in range(2):
+        assert rel(zs[i], fx["zs"][i]) < BF16_TOL
+        assert rel(means[i], fx["means"][i]) < BF16_TOL
+
+
+@pytest.mark.parametrize("cfg,batch", [(H256, 1), (D256, 2), (M128, 3)])
+def test_full_size_configs_match_oracle(cfg, batch):
+    """BASELINE.json configs at their real spatial sizes, small batch so the CPU oracle takes seconds."""
+    m, sd = build(cfg)
+    x, c, eps, _ = O.make_inputs(cfg, batch, tag="full")
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    with torch.no_grad():
+        o_imgs, o_means, o_logstds, o_zs, _ = O.forward(sd, x, c, eps)
+        o_t = O.transfer(sd, x, c, eps)
+        imgs, means, logstds, _ = m(x.cuda(), c.cuda(), eps=cuda(eps))
+        timgs = m.transfer(x.cuda(), c.cuda(), eps=cuda(eps))
+    assert rel(imgs, o_imgs) < BF16_TOL
+    assert rel(timgs, o_t) < BF16_TOL
+    for i in range(2):
+        assert rel(means[i], o_means[i]) < BF16_TOL
+        assert rel(logstds[i], o_logstds[i]) < BF16_TOL
+
+
+def test_latent_noise_is_bit_exact_with_torch_generator():
+    """The module draws eps with torch.randn in the reference's order/shapes: seeding the global generator
+    gives bit-identical results to injecting those very draws (and therefore to the reference's
+    randn_like stream on the same device)."""
+    cfg = dict(H256, spatial_size=64)
+    m, _ = build(cfg)
+    x, c, _, _ = O.make_inputs(cfg, 4, tag="rng")
+    x, c = x.cuda(), c.cuda()
+    shp = O.latent_shapes(4, 64, O.n_scales_of(cfg)[0], 128)
+    torch.manual_seed(1234)
+    e0 = torch.randn(shp[0], device="cuda")
+    e1 = torch.randn(shp[1], device="cuda")
+    with torch.no_grad():
+        a = m(x, c, eps=[e0, e1])
+        torch.manual_seed(1234)
+        b = m(x, c)
+        torch.manual_seed(1234)
+        t1 = m.transfer(x, c)
+        t2 = m.transfer(x, c, eps=[e0, e1])
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1][1], b[1][1]) and torch.equal(a[2][0], b[2][0])
+    assert torch.equal(t1, t2)
+    # z = mu + exp(logstd) * eps exactly, with the injected eps
+    with torch.no_grad():
+        torch.manual_seed(1234)
+        _, mu, ls, z = m.ed(m.eu(x))
+    for i, e in enumerate((e0, e1)):
+        assert rel(z[i], mu[i] + torch.exp(ls[i]) * e) < 1e-6
+
+
+def test_batch_independence_and_determinism_at_full_size():
+    """Size-independent properties at H256 (BASELINE configs[1] shape): frames are independent units —
+    a frame's result does not depend on what else is in the batch — and a rerun is bit-identical."""
+    m, _ = build(H256)
+    B = 8
+    x, c, eps, _ = O.make_inputs(H256, B, tag="prop")
+    x, c, eps = x.cuda(), c.cuda(), cuda(eps)
+    with torch.no_grad():
+        full = m.transfer(x, c, eps=eps)
+        again = m.transfer(x, c, eps=eps)
+        part = m.transfer(x[2:5], c[2:5], eps=[e[2:5].contiguous() for e in eps])
+    assert torch.equal(full, again)
+    assert torch.equal(full[2:5], part)
+    assert torch.isfinite(full).all()
+
+
+def test_ops_reject_bad_inputs():
+    import bdvs_b200 as B
+    with pytest.raises(NotImplementedError):
+        B.NormConv2d(48, 32, 3, padding=1).cuda()(torch.zeros(1, 48, 8, 8, device="cuda"))
+    with pytest.raises(RuntimeError):  # non power-of-two extent is refused by the C ABI, not silently mis-tiled
+        B.NormConv2d(32, 32, 3, padding=1).cuda()(torch.zeros(1, 32, 12, 12, device="cuda"))
+
+
+def test_standalone_blocks_match_oracle():
+    """Block-level parity through the reference-style public forward() of each module (NCHW in/out)."""
+    import bdvs_b200 as B
+    with contextlib.redirect_stdout(io.StringIO()):
+        pass
+    torch.manual_seed(0)
+    x = O.det_uniform("blk_x", (2, 64, 16, 16))
+    a = O.det_uniform("blk_a", (2, 64, 16, 16))
+    # VunetRNB with skip
+    blk = B.VunetRNB(channels=64, a_channels=64, residual=True)
+    shapes = {k: tuple(v.shape) for k, v in blk.state_dict().items()}
+    sd = O.det_state_dict(shapes)
+    blk.load_state_dict(sd)
+    ref = O.rnb({("b." + k): v for k, v in sd.items()}, "b", x, a)
+    got = blk.cuda()(x.cuda(), a.cuda())
+    assert got.shape == ref.shape and rel(got, ref) < BF16_TOL
+    # VunetRNB without skip, NormConv2d 3x3, Downsample, Upsample
+    blk2 = B.VunetRNB(channels=64)
+    sd2 = O.det_state_dict({k: tuple(v.shape) for k, v in blk2.state_dict().items()})
+    blk2.load_state_dict(sd2)
+    assert rel(blk2.cuda()(x.cuda()), O.rnb({("b." + k): v for k, v in sd2.items()}, "b", x)) < BF16_TOL
+    nc = B.NormConv2d(64, 128, 3, padding=1)
+    sd3 = O.det_state_dict({k: tuple(v.shape) for k, v in nc.state_dict().items()})
+    nc.load_state_dict(sd3)
+    assert rel(nc.cuda()(x.cuda()), O.norm_conv({("c." + k): v for k, v in sd3.items()}, "c", x)) < BF16_TOL
+    dn = B.Downsample(64, 128)
+    sd4 = O.det_state_dict({k: tuple(v.shape) for k, v in dn.state_dict().items()})
+    dn.load_state_dict(sd4)
+    assert rel(dn.cuda()(x.cuda()), O.norm_conv({("d." + k): v for k, v in sd4.items()}, "d.down", x, stride=2)) < BF16_TOL
+    up = B.Upsample(64, 32)
+    sd5 = O.det_state_dict({k: tuple(v.shape) for k, v in up.state_dict().items()})
+    up.load_state_dict(sd5)
+    assert rel(up.cuda()(x.cuda()), O.upsample({("u." + k): v for k, v in sd5.items()}, "u", x)) < BF16_TOL
+    # stem-shaped 1x1 conv on an RGB image
+    st = B.NormConv2d(3, 32, 1)
+    sd6 = O.det_state_dict({k: tuple(v.shape) for k, v in st.state_dict().items()})
+    st.load_state_dict(sd6)
+    img = O.det_uniform("img", (2, 3, 32, 32))
+    assert rel(st.cuda()(img.cuda()), O.norm_conv({("s." + k): v for k, v in sd6.items()}, "s", img)) < BF16_TOL

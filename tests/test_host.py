@@ -1,0 +1,138 @@
+"""CPU: host-side logic — module structure / state_dict layout / init stream / ctor contract, the C-ABI
+library (loads, exports every symbol the header declares), and loud failure without a GPU."""
+import contextlib
+import ctypes
+import io
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+import vunet_oracle as O
+from conftest import REFERENCE_ROOT, ROOT
+
+import bdvs_b200 as B
+from bdvs_b200 import _native
+
+H256 = dict(spatial_size=256, bottleneck_factor=2, n_scales=0, box_factor=2, n_latent_scales=2,
+            conv_layer_type="l1", nf_start=32, nf_max=128, subpixel_upsampling=True)
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+@pytest.mark.parametrize("name", ["tiny3", "tiny30", "market128"])
+def test_state_dict_layout_matches_reference_fixture(golden, name):
+    fx = golden(name)
+    cfg = dict(fx["config"])
+    cfg.pop("batch")
+    m = quiet(B.VunetAlter, **cfg)
+    got = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    assert got == [(k, tuple(s)) for k, s in fx["param_shapes"]]  # names, shapes AND registration order
+    assert all(v.dtype == torch.float32 for v in m.state_dict().values())
+    # reference-generated checkpoint loads strictly, and round-trips
+    sd = O.det_state_dict(dict(fx["param_shapes"]))
+    m.load_state_dict(sd, strict=True)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k])
+
+
+def test_ctor_contract():
+    m = quiet(B.VunetAlter, n_channels_x=3, unknown_key=1, dataset="Human3.6m", **H256)  # unknown kwargs ignored
+    assert (m.n_scales, m.n_scales_x, m.spatial_size, m.n_channels_x) == (7, 7, 256, 3)
+    assert len(m.state_dict()) == 495 and sum(v.numel() for v in m.state_dict().values()) == 14601516
+    m30 = quiet(B.VunetAlter, n_channels_x=30, **H256)
+    assert m30.n_scales_x == 5 and len(m30.state_dict()) == 465
+    for sub in ("eu", "ed", "du", "dd"):
+        assert hasattr(m, sub)
+    with pytest.raises(KeyError):
+        quiet(B.VunetAlter, n_channels_x=3)  # required kwargs, like the reference
+    with pytest.raises(NotImplementedError):
+        quiet(B.VunetAlter, **dict(H256, conv_layer_type="l2"))
+    # dropout_prob never reaches the ctor in the reference's callers -> p = 0 everywhere
+    assert all(mod.p == 0.0 for mod in m.modules() if isinstance(mod, torch.nn.Dropout))
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_ROOT), reason="reference tree only exists in the build container")
+def test_same_seed_gives_reference_initialisation():
+    sys.path.insert(0, REFERENCE_ROOT)
+    from models.vunets import VunetAlter as RefVunet
+    cfg = dict(H256, spatial_size=64, nf_max=64)
+    torch.manual_seed(42)
+    ref = quiet(RefVunet, n_channels_x=30, **cfg)
+    torch.manual_seed(42)
+    mine = quiet(B.VunetAlter, n_channels_x=30, **cfg)
+    rsd, msd = ref.state_dict(), mine.state_dict()
+    assert list(rsd.keys()) == list(msd.keys())
+    for k in rsd:
+        assert torch.equal(rsd[k], msd[k]), k  # bit-identical: same RNG stream, same formulas
+
+
+def test_no_cpu_fallback():
+    m = quiet(B.VunetAlter, n_channels_x=3, **dict(H256, spatial_size=32, bottleneck_factor=1))
+    x = torch.zeros(1, 3, 32, 32)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(x, x)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m.transfer(x, x)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        B.NormConv2d(32, 32, 3, padding=1)(torch.zeros(1, 32, 8, 8))
+    with pytest.raises(NotImplementedError):  # torch op registered for CUDA only
+        torch.ops.vunet_b200.nhwc_to_nchw(torch.zeros(1, 2, 2, 8, dtype=torch.bfloat16))
+
+
+def test_kl_matches_oracle():
+    mu = [O.det_normal("m0", (3, 8, 2, 2)), O.det_normal("m1", (3, 8, 4, 4))]
+    ls = [torch.sigmoid(O.det_normal("l0", (3, 8, 2, 2))), torch.sigmoid(O.det_normal("l1", (3, 8, 4, 4)))]
+    assert torch.allclose(B.compute_kl_with_prior(mu, ls), O.compute_kl_with_prior(mu, ls), rtol=1e-6)
+    assert torch.allclose(B.kl_loss(mu[0], ls[0]), O.kl_loss(mu[0], ls[0]), rtol=1e-6)
+
+
+def test_space_depth_modules():
+    x = O.det_uniform("sd", (2, 8, 4, 6))
+    assert torch.equal(B.DepthToSpace(2)(x), O.depth_to_space(x))
+    assert torch.equal(B.SpaceToDepth(2)(B.DepthToSpace(2)(x)), x)
+
+
+# ---- C ABI ------------------------------------------------------------------------------------
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "vunet_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vub_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert header_symbols() == sorted(_native.EXPORTED_SYMBOLS)
+
+
+def test_library_loads_and_exports_every_symbol():
+    if not os.path.exists(_native.LIB_PATH):
+        _native.build()
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for sym in header_symbols():
+        assert hasattr(lib, sym), sym
+    assert _native.lib().vub_abi_version() == 1
+    # struct mirrors must match the C layout (pointers first, then int32 fields)
+    assert ctypes.sizeof(_native.ConvDesc) == 9 * 8 + 11 * 4 + 4  # padded to 8
+    assert ctypes.sizeof(_native.WnEntry) == 8 * 8 + 6 * 4
+
+
+def test_bad_arguments_are_reported_not_crashed():
+    lib = _native.lib()
+    assert lib.vub_conv_fwd(None, None) == -1  # VUB_E_NULL
+    assert b"NULL" in lib.vub_last_error()
+    d = _native.ConvDesc()
+    d.x[0] = 16; d.w = 16; d.scale = 16; d.shift = 16
+    d.nsrc, d.c_src, d.batch, d.hin, d.win, d.cout, d.cout_valid, d.ksize, d.stride = 1, 48, 1, 8, 8, 32, 32, 3, 1
+    assert lib.vub_conv_fwd(ctypes.byref(d), None) == -2  # VUB_E_SHAPE: c_src 48
+    d.c_src, d.hin = 32, 12
+    assert lib.vub_conv_fwd(ctypes.byref(d), None) == -2  # non power-of-two extent
+    d.hin = 8
+    assert lib.vub_conv_fwd(ctypes.byref(d), None) == -3  # VUB_E_FLAGS: no output requested
+    assert lib.vub_stem_fwd(None, None, None, None, None, None, 1, 3, 8, 8, 32, None, None, None) == -1
+    assert lib.vub_wn_prep(None, 1, 1, None) == -1
+    assert lib.vub_latent_num_partials(2, 128, 4, 4) == 8
