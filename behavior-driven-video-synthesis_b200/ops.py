@@ -34,6 +34,26 @@ _LIB.define("nhwc_to_nchw(Tensor x) -> Tensor")
 
 F32_NONE, F32_NHWC, F32_NCHW = 0, 1, 2
 
+# ---- launch accounting (bench.py's "gpu_launches" and per-kernel roofline) -----------------------
+LAUNCHES = 0          # kernels of THIS package launched since import (graph replays are counted by the caller)
+_PROFILER = None      # set by profiler.KernelProfiler: records CUDA events around every launch
+
+
+def _launch(name: str, fn, *args, flops: float = 0.0, bytes_: float = 0.0) -> int:
+    """Run one C-ABI launcher; count it and, when a profiler is active, time it with CUDA events
+    on the launching stream."""
+    global LAUNCHES
+    LAUNCHES += 1
+    if _PROFILER is None:
+        return fn(*args)
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    rc = fn(*args)
+    ev1.record()
+    _PROFILER.add(name, ev0, ev1, flops, bytes_)
+    return rc
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -101,12 +121,19 @@ def _conv_fwd_cuda(x0, x1, w, scale, shift, residual, ksize, stride, cout_valid,
     d.nsrc, d.c_src, d.batch, d.hin, d.win = nsrc, c_src, B, H, W
     d.cout, d.cout_valid, d.ksize, d.stride = cout, cout_valid, ksize, stride
     d.flags, d.stages = flags, stages
-    N.check(N.lib().vub_conv_fwd(C.byref(d), _stream()), "vub_conv_fwd")
+    bn = min(cout, 256)
+    bkc = 64 if c_src >= 64 else 32
+    out_bytes = sum(o.numel() * o.element_size() for o in outs)
+    in_bytes = nsrc * x0.numel() * 2 + w.numel() * 2 + (residual.numel() * 2 if residual is not None else 0)
+    flops = 2.0 * B * Ho * Wo * cout_valid * w.shape[1]
+    N.check(_launch(f"conv_fwd<{bn},{bkc}>", N.lib().vub_conv_fwd, C.byref(d), _stream(), flops=flops,
+                    bytes_=float(in_bytes + out_bytes)), "vub_conv_fwd")
     return outs
 
 
 def _wn_prep_cuda(table, n_entries, total_rows) -> None:
-    N.check(N.lib().vub_wn_prep(table.data_ptr(), n_entries, total_rows, _stream()), "vub_wn_prep")
+    N.check(_launch("wn_prep", N.lib().vub_wn_prep, table.data_ptr(), n_entries, total_rows, _stream()),
+            "vub_wn_prep")
 
 
 def _stem_fwd_cuda(x, v, g, gamma, beta, bias, want_raw, want_elu) -> List[torch.Tensor]:
@@ -123,9 +150,11 @@ def _stem_fwd_cuda(x, v, g, gamma, beta, bias, want_raw, want_elu) -> List[torch
     if want_elu:
         elu = torch.empty((B, H, W, cout), dtype=torch.bfloat16, device=x.device)
         outs.append(elu)
+    nbytes = float(x.numel() * 4 + sum(o.numel() * 2 for o in outs))
     N.check(
-        N.lib().vub_stem_fwd(x.data_ptr(), v.data_ptr(), g.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                             bias.data_ptr(), B, cx, H, W, cout, _p(raw), _p(elu), _stream()),
+        _launch(f"stem<{cout}>", N.lib().vub_stem_fwd, x.data_ptr(), v.data_ptr(), g.data_ptr(), gamma.data_ptr(),
+                beta.data_ptr(), bias.data_ptr(), B, cx, H, W, cout, _p(raw), _p(elu), _stream(),
+                flops=2.0 * B * H * W * cx * cout, bytes_=nbytes),
         "vub_stem_fwd",
     )
     return outs
@@ -147,9 +176,11 @@ def _latent_fwd_cuda(ml, eps, want_elu_z, want_elu_mu) -> List[torch.Tensor]:
     em = torch.empty((B, h, w, c), dtype=torch.bfloat16, device=dev) if want_elu_mu else None
     npart = N.lib().vub_latent_num_partials(B, c, h, w)
     kl = torch.empty((npart,), dtype=torch.float32, device=dev)
+    n = B * c * h * w
+    nbytes = float(n * (8 + 4 + 12) + (n * 2 if want_elu_z else 0) + (n * 2 if want_elu_mu else 0))
     N.check(
-        N.lib().vub_latent_fwd(ml.data_ptr(), _p(eps), B, c, h, w, mu.data_ptr(), ls.data_ptr(), z.data_ptr(),
-                               _p(ez), _p(em), kl.data_ptr(), _stream()),
+        _launch("latent", N.lib().vub_latent_fwd, ml.data_ptr(), _p(eps), B, c, h, w, mu.data_ptr(), ls.data_ptr(),
+                z.data_ptr(), _p(ez), _p(em), kl.data_ptr(), _stream(), bytes_=nbytes),
         "vub_latent_fwd",
     )
     outs = [mu, ls, z, kl]
@@ -167,8 +198,9 @@ def _nchw_to_nhwc_cuda(x, want_raw, want_elu) -> List[torch.Tensor]:
     B, c, H, W = x.shape
     raw = torch.empty((B, H, W, c), dtype=torch.bfloat16, device=x.device) if want_raw else None
     elu = torch.empty((B, H, W, c), dtype=torch.bfloat16, device=x.device) if want_elu else None
-    N.check(N.lib().vub_nchw_f32_to_nhwc_bf16(x.data_ptr(), B, c, H, W, _p(raw), _p(elu), _stream()),
-            "vub_nchw_f32_to_nhwc_bf16")
+    nbytes = float(x.numel() * 4 + (x.numel() * 2 if want_raw else 0) + (x.numel() * 2 if want_elu else 0))
+    N.check(_launch("nchw_to_nhwc", N.lib().vub_nchw_f32_to_nhwc_bf16, x.data_ptr(), B, c, H, W, _p(raw), _p(elu),
+                    _stream(), bytes_=nbytes), "vub_nchw_f32_to_nhwc_bf16")
     return [t for t in (raw, elu) if t is not None]
 
 
@@ -176,8 +208,8 @@ def _nhwc_to_nchw_cuda(x) -> torch.Tensor:
     _check_act(x, "nhwc_to_nchw x")
     B, H, W, c = x.shape
     out = torch.empty((B, c, H, W), dtype=torch.float32, device=x.device)
-    N.check(N.lib().vub_nhwc_bf16_to_nchw_f32(x.data_ptr(), B, c, H, W, out.data_ptr(), _stream()),
-            "vub_nhwc_bf16_to_nchw_f32")
+    N.check(_launch("nhwc_to_nchw", N.lib().vub_nhwc_bf16_to_nchw_f32, x.data_ptr(), B, c, H, W, out.data_ptr(),
+                    _stream(), bytes_=float(x.numel() * 6)), "vub_nhwc_bf16_to_nchw_f32")
     return out
 
 

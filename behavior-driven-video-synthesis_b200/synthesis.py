@@ -1,0 +1,87 @@
+"""Batched frame synthesis — the forward-only caller of the VUnet.
+
+The reference renders behavior-net pose sequences one frame at a time with batch 1 and a host sync
+per frame (``data/data_conversions_3d.py:1130-1173``: ``synth_model.transfer(app_img, stickman)`` then
+``.cpu()``).  :class:`FrameSynthesizer` runs the same ``VunetAlter.transfer`` on whole batches of
+frames, captured once in a CUDA graph (~90 kernel launches per batch, ~40 of them launch-bound), with
+pinned-host staging for callers that hold their stickmen on the host.  Frames are independent units:
+multi-GPU rendering shards them with :func:`shard_range` and needs no collective.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import ops
+
+
+def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous, balanced [begin, end) share of ``n_items`` frames (or sequences) for ``rank``."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    base, rem = divmod(n_items, world_size)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+class FrameSynthesizer:
+    """``imgs = FrameSynthesizer(model, batch)(x, c)`` == ``model.transfer(x, c)`` for a fixed batch size.
+
+    x: appearance ``[batch, n_channels_x, Sx, Sx]`` fp32, c: stickmen ``[batch, 3, S, S]`` fp32 (NCHW, values
+    in [-1, 1]); returns ``[batch, 3, S, S]`` fp32 (a static buffer, overwritten by the next call).
+    The latent noise is drawn inside the graph from torch's CUDA generator, like the reference.
+    """
+
+    def __init__(self, model, batch: int, device: Optional[torch.device] = None, use_graph: bool = True):
+        self.model = model.eval()
+        self.batch = batch
+        p = next(model.parameters())
+        self.device = torch.device(device) if device is not None else p.device
+        if self.device.type != "cuda":
+            raise RuntimeError("vunet_b200 has no CPU path: move the module to a CUDA device")
+        s = model.spatial_size
+        sx = s // 2 ** (model.n_scales - model.n_scales_x)
+        self.x = torch.zeros(batch, model.n_channels_x, sx, sx, dtype=torch.float32, device=self.device)
+        self.c = torch.zeros(batch, 3, s, s, dtype=torch.float32, device=self.device)
+        self.graph = None
+        self.launches_per_call = 0
+        self._out = None
+        with torch.no_grad():
+            model._bank()  # weight-norm preparation happens outside the graph
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    before = ops.LAUNCHES
+                    self._out = model.transfer(self.x, self.c)
+                    self.launches_per_call = ops.LAUNCHES - before
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            if use_graph:
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self._out = model.transfer(self.x, self.c)
+
+    def refresh_weights(self) -> None:
+        """Call after the model's parameters changed (re-runs weight-norm prep into the same buffers)."""
+        self.model._bank()
+
+    def run(self) -> torch.Tensor:
+        """Synthesize from the static input buffers ``self.x`` / ``self.c``."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            with torch.no_grad():
+                self._out = self.model.transfer(self.x, self.c)
+        return self._out
+
+    def __call__(self, x: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
+        self.x.copy_(x, non_blocking=True)
+        self.c.copy_(c, non_blocking=True)
+        return self.run()
+
+    def render_host(self, x_host: torch.Tensor, c_host: torch.Tensor, out_host: torch.Tensor) -> None:
+        """Host (pinned) buffers in, host (pinned) frames out; asynchronous on the current stream."""
+        self.x.copy_(x_host, non_blocking=True)
+        self.c.copy_(c_host, non_blocking=True)
+        out_host.copy_(self.run(), non_blocking=True)

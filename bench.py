@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""Benchmark of the VUnet hot path (contract: see the task statement / DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload synth|train]
+
+Default workload = BASELINE.json configs[1]: VunetAlter Human3.6m settings (256x256, bottleneck_factor 2,
+box_factor 2, 3 appearance channels), forward-only frame synthesis (``transfer``), bf16 tensor-core
+compute, 64 frames per GPU per step; frames are sharded over ranks with no collective (weak scaling).
+A "step" is one pass of the hot path over one 64-frame batch of synthetic frames.
+
+  value  frames/s, whole job, inputs resident in HBM, CUDA-graph replay timed with CUDA events
+  e2e    frames/s through the public API (FrameSynthesizer.render_host) with pinned HOST buffers:
+         host->device copies of x and c and the device->host copy of the frames inside the timed region
+  roofline / kernels   per-kernel CUDA-event timing of one instrumented step (outside the timed region)
+  cpu_baseline         the CPU oracle (oracle/vunet_oracle.py, a port of the reference's PyTorch path) on a
+                       bounded sample, all host threads
+``--impl reference`` times that CPU port alone and prints the same line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import io
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+ARCH = dict(n_latent_scales=2, conv_layer_type="l1", subpixel_upsampling=True, n_scales=0, nf_start=32, nf_max=128)
+H256 = dict(ARCH, spatial_size=256, bottleneck_factor=2, box_factor=2, n_channels_x=3)
+WORKLOAD = "VunetAlter H3.6M-256 (256x256, bottleneck_factor=2, box=2, n_channels_x=3) transfer(x,c) forward-only"
+FRAMES_PER_GPU = 64
+# live convs of the reference graph, forward/transfer, per frame
+GFLOP_PER_FRAME = 43.064
+METRIC = "VUnet 256x256 frame synthesis throughput (fwd)"
+UNIT = "frames/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                f = [s.strip() for s in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def build_model(device):
+    import bdvs_b200 as B
+    import vunet_oracle as O
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = B.VunetAlter(**H256)
+    sd = O.det_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()})
+    model.load_state_dict(sd)
+    return model.to(device).eval(), sd
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_port_fps(sample_frames: int, iters: int, warmup: int = 1):
+    """frames/s of the CPU oracle (port of the reference's PyTorch path) on `sample_frames` H256 frames."""
+    import vunet_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    with contextlib.redirect_stdout(io.StringIO()):
+        import bdvs_b200 as B
+        shapes = {k: tuple(v.shape) for k, v in B.VunetAlter(**H256).state_dict().items()}
+    sd = O.det_state_dict(shapes)
+    x, c, eps, _ = O.make_inputs(H256, sample_frames, tag="cpu")
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + iters):
+            t0 = time.perf_counter()
+            O.transfer(sd, x, c, eps)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return sample_frames / statistics.median(times), threads, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 4
+    t_all0 = time.perf_counter()
+    fps, threads, times = cpu_port_fps(sample, iters=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+    ms = 1e3 * statistics.median(times)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": max(1, args.steps), "warmup": max(1, min(args.warmup, 2)), "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": sample, "device": "cpu"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} frames/step of the same H256 transfer workload, fp32, torch CPU "
+                                   f"({threads} threads); the reference is pure Python/PyTorch and is absent on the "
+                                   "GPU box, so its port oracle/vunet_oracle.py (pinned to reference outputs) is timed"},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t_all0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import bdvs_b200 as B
+    from bdvs_b200 import ops
+    from bdvs_b200.profiler import KernelProfiler
+    from bdvs_b200.synthesis import FrameSynthesizer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    peaks = load_peaks()
+    model, sd = build_model(device)
+    Bf = FRAMES_PER_GPU
+    torch.manual_seed(42 + rank)
+    synth = FrameSynthesizer(model, Bf, device)
+    synth.x.uniform_(-1, 1)
+    synth.c.uniform_(-1, 1)
+    K, W = args.steps, max(3, args.warmup)
+
+    # ---- value: device-resident inputs, graph replay, CUDA events ----
+    for _ in range(W):
+        synth.run()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(K):
+        synth.run()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / K
+    value = world * Bf * K / (ms_total * 1e-3)
+    launches = synth.launches_per_call * K
+
+    # ---- e2e: pinned host buffers through the public API, copies inside the timed region ----
+    xh = torch.empty(synth.x.shape, dtype=torch.float32).uniform_(-1, 1).pin_memory()
+    ch = torch.empty(synth.c.shape, dtype=torch.float32).uniform_(-1, 1).pin_memory()
+    oh = torch.empty((Bf, 3, H256["spatial_size"], H256["spatial_size"]), dtype=torch.float32).pin_memory()
+    for _ in range(2):
+        synth.render_host(xh, ch, oh)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        synth.render_host(xh, ch, oh)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    e2e = world * Bf * K / (ms_e2e * 1e-3)
+    h2d = xh.numel() * 4 + ch.numel() * 4
+    d2h = oh.numel() * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel roofline: one instrumented eager step (CUDA events around every launch) ----
+    with torch.no_grad():
+        for _ in range(2):
+            model.transfer(synth.x, synth.c)
+        with KernelProfiler() as kp:
+            model.transfer(synth.x, synth.c)
+        prof = kp.summary()
+    total_kernel_ms = sum(r["ms"] for r in prof.values())
+    kernels = []
+    for name, r in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+        tf = r["flops"] / (r["ms"] * 1e-3) / 1e12 if r["ms"] > 0 else 0.0
+        gb = r["bytes"] / (r["ms"] * 1e-3) / 1e9 if r["ms"] > 0 else 0.0
+        kernels.append({"kernel": name, "launches": r["launches"], "ms": round(r["ms"], 4),
+                        "share": round(r["ms"] / total_kernel_ms, 4), "tflops": round(tf, 2), "gbs": round(gb, 1),
+                        "frac_tensor": round(tf / peaks["bf16_tflops_sustained"], 4),
+                        "frac_hbm": round(gb / peaks["hbm_gbs"], 4)})
+    top = kernels[0]
+    t_tc = prof[top["kernel"]]["flops"] / (peaks["bf16_tflops_sustained"] * 1e12)
+    t_hbm = prof[top["kernel"]]["bytes"] / (peaks["hbm_gbs"] * 1e9)
+    if t_hbm >= t_tc:
+        roofline = {"bound": "hbm", "achieved": top["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": round(top["gbs"] / peaks["hbm_gbs"], 4), "traffic": None}
+    else:
+        roofline = {"bound": "tensor", "achieved": top["tflops"], "peak": peaks["bf16_tflops_sustained"],
+                    "unit": "TFLOP/s", "frac": round(top["tflops"] / peaks["bf16_tflops_sustained"], 4), "traffic": None}
+    roofline.update({"kernel": top["kernel"], "launches_per_step": top["launches"], "share_of_step": top["share"],
+                     "peak_source": peaks["source"] + (" (sustained)" if roofline["bound"] == "tensor" else ""),
+                     "avg_launch_ms": round(top["ms"] / top["launches"], 4)})
+    whole = {"conv_tflops_per_gpu": round(GFLOP_PER_FRAME * Bf / ms_step, 2),
+             "frac_tensor_peak_sustained": round(GFLOP_PER_FRAME * Bf / ms_step / peaks["bf16_tflops_sustained"], 4),
+             "blended_roofline_frames_per_s_per_gpu": 25100.0,
+             "frac_of_blended_roofline": round(value / world / 25100.0, 4)}
+
+    # ---- CPU baseline (bounded sample) ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        fps, threads, times = cpu_port_fps(4, iters=3, warmup=1)
+        cpu = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "4 frames/iter x 3 iters (+1 warm-up) of the same H256 transfer workload, fp32 torch CPU, "
+                         "oracle/vunet_oracle.py (port of the reference's PyTorch path, pinned to reference outputs)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": Bf, "global_frames_per_step": Bf * world,
+                   "parallelism": f"frames sharded over {world} GPU(s), no collective",
+                   "cache": "inputs + activations per step (~14 GB) far exceed the 126 MB L2: no flush needed",
+                   "execution": "CUDA graph replay of model.transfer (latent noise drawn inside the graph)",
+                   "algorithmic_gflop_per_frame": GFLOP_PER_FRAME},
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / K},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "whole_step": whole,
+        "kernels": kernels,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -410,7 +410,7 @@ static void perf_conv(const char* name, int B, int H, int W, int c_src, int nsrc
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   for (int i = 0; i < 3; ++i) vub_conv_fwd(&d, nullptr);
   CK(cudaDeviceSynchronize());
-  const int iters = 10;
+  const int iters = 20;
   CK(cudaEventRecord(e0));
   for (int i = 0; i < iters; ++i) vub_conv_fwd(&d, nullptr);
   CK(cudaEventRecord(e1));
@@ -426,6 +426,13 @@ static void perf_conv(const char* name, int B, int H, int W, int c_src, int nsrc
 
 int main(int argc, char** argv) {
   const bool perf = argc > 1 && !strcmp(argv[1], "perf");
+  if (argc >= 14 && !strcmp(argv[1], "layer")) {
+    // layer B H W c_src nsrc cout k stride res dual d2s stages  -> time one layer shape (for ncu captures)
+    int a[12];
+    for (int i = 0; i < 12; ++i) a[i] = atoi(argv[2 + i]);
+    perf_conv("layer", a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8] != 0, a[9] != 0, a[10] != 0, a[11]);
+    return 0;
+  }
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
   printf("device: %s  sm_%d%d  SMs=%d  abi=%d\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount,
