@@ -22,6 +22,7 @@
 #include <mutex>
 
 #include "common.h"
+#include "conv_epilogue.cuh"
 #include "ptx.cuh"
 
 namespace vub {
@@ -33,102 +34,31 @@ constexpr int kMaxStages = 8;
 struct ConvKParams {
   CUtensorMap tmA[4];
   CUtensorMap tmB;
-  const float* scale;
-  const float* shift;
-  const __nv_bfloat16* residual;
-  __nv_bfloat16* out_raw;
-  __nv_bfloat16* out_elu;
-  float* out_f32;
-  int batch, hout, wout;
-  int cout, cout_valid;
+  EpiParams ep;
+  int batch;
   int nsrc, cblocks, ntaps, stride;
   int tw, th, tn, tw_log2, th_log2;
   int tiles_w, tiles_h;
   int stages;
-  uint32_t flags;
 };
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
-__device__ __forceinline__ void unpack_bf16x2(uint32_t u, float& a, float& b) {
-  __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
-  float2 f = __bfloat1622float2(t);
-  a = f.x;
-  b = f.y;
-}
 
 // Epilogue for CH (16 or 32) consecutive channels of one pixel held in registers.
 template <int CH>
-__device__ __forceinline__ void epilogue_chunk(const ConvKParams& p, const uint32_t (&acc)[CH],
-                                               const float* s_scale, const float* s_shift,
-                                               int c_local, int c_global, bool valid, int n, int oh,
-                                               int ow) {
+__device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const uint32_t (&acc)[CH],
+                                               const float* s_scale, const float* s_shift, int c_local,
+                                               int c_global, bool valid, int n, int oh, int ow) {
   float y[CH];
 #pragma unroll
   for (int i = 0; i < CH; ++i)
     y[i] = fmaf(__uint_as_float(acc[i]), s_scale[c_local + i], s_shift[c_local + i]);
   if (!valid) return;
-
-  const long long pix = ((long long)n * p.hout + oh) * p.wout + ow;
   if (p.residual != nullptr) {
+    const long long pix = ((long long)n * p.hout + oh) * p.wout + ow;
     const uint4* r = reinterpret_cast<const uint4*>(p.residual + pix * p.cout + c_global);
 #pragma unroll
-    for (int j = 0; j < CH / 8; ++j) {
-      uint4 u = __ldg(r + j);
-      float a, b;
-      unpack_bf16x2(u.x, a, b); y[8 * j + 0] += a; y[8 * j + 1] += b;
-      unpack_bf16x2(u.y, a, b); y[8 * j + 2] += a; y[8 * j + 3] += b;
-      unpack_bf16x2(u.z, a, b); y[8 * j + 4] += a; y[8 * j + 5] += b;
-      unpack_bf16x2(u.w, a, b); y[8 * j + 6] += a; y[8 * j + 7] += b;
-    }
+    for (int j = 0; j < CH / 8; ++j) add_bf16x8(__ldg(r + j), &y[8 * j]);
   }
-
-  if (p.flags & VUB_CONV_F32_NCHW) {
-    const long long plane = (long long)p.hout * p.wout;
-    float* o = p.out_f32 + ((long long)n * p.cout_valid) * plane + (long long)oh * p.wout + ow;
-#pragma unroll
-    for (int i = 0; i < CH; ++i)
-      if (c_global + i < p.cout_valid) o[(long long)(c_global + i) * plane] = y[i];
-    return;
-  }
-  if (p.flags & VUB_CONV_F32_NHWC) {
-    float4* o = reinterpret_cast<float4*>(p.out_f32 + pix * p.cout + c_global);
-#pragma unroll
-    for (int j = 0; j < CH / 4; ++j)
-      o[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-    return;
-  }
-
-  long long obase;
-  if (p.flags & VUB_CONV_D2S) {
-    // DepthToSpace(2), DCR order: out[n, 2h+b1, 2w+b2, c'] = conv[n, h, w, (2*b1+b2)*C' + c']
-    const int cq = p.cout >> 2;
-    const int qd = c_global / cq;
-    const int cp = c_global - qd * cq;
-    const long long opix =
-        ((long long)n * (2 * p.hout) + 2 * oh + (qd >> 1)) * (2 * p.wout) + 2 * ow + (qd & 1);
-    obase = opix * cq + cp;
-  } else {
-    obase = pix * p.cout + c_global;
-  }
-  if (p.out_raw != nullptr) {
-    uint4* o = reinterpret_cast<uint4*>(p.out_raw + obase);
-#pragma unroll
-    for (int j = 0; j < CH / 8; ++j)
-      o[j] = make_uint4(pack_bf16x2(y[8 * j + 0], y[8 * j + 1]), pack_bf16x2(y[8 * j + 2], y[8 * j + 3]),
-                        pack_bf16x2(y[8 * j + 4], y[8 * j + 5]), pack_bf16x2(y[8 * j + 6], y[8 * j + 7]));
-  }
-  if (p.out_elu != nullptr) {
-#pragma unroll
-    for (int i = 0; i < CH; ++i) y[i] = elu1(y[i]);
-    uint4* o = reinterpret_cast<uint4*>(p.out_elu + obase);
-#pragma unroll
-    for (int j = 0; j < CH / 8; ++j)
-      o[j] = make_uint4(pack_bf16x2(y[8 * j + 0], y[8 * j + 1]), pack_bf16x2(y[8 * j + 2], y[8 * j + 3]),
-                        pack_bf16x2(y[8 * j + 4], y[8 * j + 5]), pack_bf16x2(y[8 * j + 6], y[8 * j + 7]));
-  }
+  epi_store<CH>(p, y, c_global, n, oh, ow);
 }
 
 template <int BN, int BKC>
@@ -180,62 +110,76 @@ __global__ void __launch_bounds__(kConvThreads)
     tmem_relinquish();
   }
   for (int i = threadIdx.x; i < BN; i += kConvThreads) {
-    s_scale[i] = p.scale[n_tile * BN + i];
-    s_shift[i] = p.shift[n_tile * BN + i];
+    s_scale[i] = p.ep.scale[n_tile * BN + i];
+    s_shift[i] = p.ep.shift[n_tile * BN + i];
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
+  // Producer / MMA loops are executed by all lanes of their warp (warp-uniform control flow); the TMA /
+  // tcgen05 instructions are issued from `if (elect_one())` blocks so ptxas emits back-to-back UTCHMMA
+  // with uniform-register descriptors instead of a per-lane "waterfall" loop around each one.
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
-      int ks = 0;
-      for (int src = 0; src < p.nsrc; ++src) {
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-          int dh = 0, dw = 0, mi = src;
-          if (p.ntaps == 9) {
-            const int r = tap / 3, s = tap - 3 * r;
-            if (p.stride == 1) {
-              dh = r - 1;
-              dw = s - 1;
-            } else {  // input row 2*oh + r - 1: parity (r != 1), coordinate oh - (r == 0)
-              mi = ((r != 1) ? 2 : 0) + ((s != 1) ? 1 : 0);
-              dh = (r == 0) ? -1 : 0;
-              dw = (s == 0) ? -1 : 0;
-            }
+    int ks = 0, st = 0;
+    uint32_t ph = 0;
+    for (int src = 0; src < p.nsrc; ++src) {
+      for (int tap = 0; tap < p.ntaps; ++tap) {
+        int dh = 0, dw = 0, mi = src;
+        if (p.ntaps == 9) {
+          const int r = tap / 3, s = tap - 3 * r;
+          if (p.stride == 1) {
+            dh = r - 1;
+            dw = s - 1;
+          } else {  // input row 2*oh + r - 1: parity (r != 1), coordinate oh - (r == 0)
+            mi = ((r != 1) ? 2 : 0) + ((s != 1) ? 1 : 0);
+            dh = (r == 0) ? -1 : 0;
+            dw = (s == 0) ? -1 : 0;
           }
-          for (int cb = 0; cb < p.cblocks; ++cb, ++ks) {
-            const int st = ks % S;
-            const uint32_t ph = (ks / S) & 1;
-            mbar_wait(&empty_bar[st], ph ^ 1);
+        }
+        for (int cb = 0; cb < p.cblocks; ++cb, ++ks) {
+          mbar_wait(&empty_bar[st], ph ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(&full_bar[st], STAGE_BYTES);
             uint8_t* a = smem + st * STAGE_BYTES;
             tma_load_4d(a, &p.tmA[mi], &full_bar[st], cb * BKC, w0 + dw, h0 + dh, n0);
             tma_load_2d(a + A_BYTES, &p.tmB, &full_bar[st], ks * BKC, n_tile * BN);
+          }
+          __syncwarp();
+          if (++st == S) {
+            st = 0;
+            ph ^= 1;
           }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
-      for (int ks = 0; ks < KS; ++ks) {
-        const int st = ks % S;
-        const uint32_t ph = (ks / S) & 1;
-        mbar_wait(&full_bar[st], ph);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + st * STAGE_BYTES);
-        const uint64_t da = umma_smem_desc_kmajor(a_addr, ROWB);
-        const uint64_t db = umma_smem_desc_kmajor(a_addr + A_BYTES, ROWB);
+    constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
+    const uint32_t desc_hi = umma_desc_hi_kmajor(ROWB);
+    const uint32_t smem_lo = umma_desc_lo(smem_u32(smem));
+    int st = 0;
+    uint32_t ph = 0;
+    for (int ks = 0; ks < KS; ++ks) {
+      mbar_wait(&full_bar[st], ph);
+      tc_fence_after();
+      const uint32_t a_lo = smem_lo + st * (STAGE_BYTES >> 4);
+      const uint32_t b_lo = a_lo + (A_BYTES >> 4);
+      if (elect_one()) {
 #pragma unroll
         for (int j = 0; j < BKC / 16; ++j)
-          umma_bf16(tmem_base, da + 2 * j, db + 2 * j, idesc, (ks | j) != 0 ? 1u : 0u);
+          umma_bf16(tmem_base, umma_desc_join(desc_hi, a_lo + 2 * j), umma_desc_join(desc_hi, b_lo + 2 * j),
+                    idesc, (ks | j) != 0 ? 1u : 0u);
         umma_commit(&empty_bar[st]);
+        if (ks == KS - 1) umma_commit(&tmem_full_bar);
       }
-      umma_commit(&tmem_full_bar);
+      __syncwarp();
+      if (++st == S) {
+        st = 0;
+        ph ^= 1;
+      }
     }
   } else {
     // ------------------------------ epilogue -----------------------------------
@@ -250,18 +194,62 @@ __global__ void __launch_bounds__(kConvThreads)
     tc_fence_after();
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     if constexpr (BN >= 32) {
+      const bool bf16_out = (p.ep.flags & (VUB_CONV_F32_NHWC | VUB_CONV_F32_NCHW)) == 0;
+      if (bf16_out) {
+        // All MMAs (hence all TMA loads) of this CTA are complete: the pipeline stages are free and
+        // serve as the per-warp staging tiles of the coalesced store path.
+        constexpr int GW = BN < 128 ? BN : 128;
+        const uint32_t st_raw = smem_u32(smem) + q * EpiStage<GW>::WARP_BYTES;
+        const uint32_t st_elu = st_raw + EpiStage<GW>::TILE_BYTES;
+        auto coord = [&](int row, int& rn, int& roh, int& row_w) {
+          const int mm = q * 32 + row;
+          rn = n0 + (mm >> (p.tw_log2 + p.th_log2));
+          roh = h0 + ((mm >> p.tw_log2) & (p.th - 1));
+          row_w = w0 + (mm & (p.tw - 1));
+          return rn < p.batch;
+        };
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t acc[32];
-        tmem_ld32(trow + c0, acc);
-        tmem_ld_wait();
-        epilogue_chunk<32>(p, acc, s_scale, s_shift, c0, n_tile * BN + c0, valid, n, oh, ow);
+        for (int g0 = 0; g0 < BN; g0 += GW) {
+#pragma unroll 1
+          for (int c0 = g0; c0 < g0 + GW; c0 += 32) {
+            uint32_t acc[32];
+            tmem_ld32(trow + c0, acc);
+            tmem_ld_wait();
+            float y[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) y[i] = fmaf(__uint_as_float(acc[i]), s_scale[c0 + i], s_shift[c0 + i]);
+            if (p.ep.residual != nullptr && valid) {
+              const long long pix = ((long long)n * p.ep.hout + oh) * p.ep.wout + ow;
+              const uint4* r = reinterpret_cast<const uint4*>(p.ep.residual + pix * p.ep.cout + n_tile * BN + c0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) add_bf16x8(__ldg(r + j), &y[8 * j]);
+            }
+            if (p.ep.out_raw != nullptr) stage_put32<GW>(st_raw, lane, c0 - g0, y);
+            if (p.ep.out_elu != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) y[i] = elu1(y[i]);
+              stage_put32<GW>(st_elu, lane, c0 - g0, y);
+            }
+          }
+          __syncwarp();
+          if (p.ep.out_raw != nullptr) stage_flush<GW>(st_raw, p.ep.out_raw, p.ep, lane, n_tile * BN + g0, coord);
+          if (p.ep.out_elu != nullptr) stage_flush<GW>(st_elu, p.ep.out_elu, p.ep, lane, n_tile * BN + g0, coord);
+          __syncwarp();
+        }
+      } else {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t acc[32];
+          tmem_ld32(trow + c0, acc);
+          tmem_ld_wait();
+          epilogue_chunk<32>(p.ep, acc, s_scale, s_shift, c0, n_tile * BN + c0, valid, n, oh, ow);
+        }
       }
     } else {
       uint32_t acc[16];
       tmem_ld16(trow, acc);
       tmem_ld_wait();
-      epilogue_chunk<16>(p, acc, s_scale, s_shift, 0, n_tile * BN, valid, n, oh, ow);
+      epilogue_chunk<16>(p.ep, acc, s_scale, s_shift, 0, n_tile * BN, valid, n, oh, ow);
     }
   }
 
@@ -285,10 +273,19 @@ static int launch_conv(const ConvKParams& kp, dim3 grid, cudaStream_t stream) {
   if (attr_err != cudaSuccess)
     return fail(static_cast<int>(attr_err), "cudaFuncSetAttribute(conv_fwd<%d,%d>): %s", BN, BKC,
                 cudaGetErrorString(attr_err));
-  const size_t smem = static_cast<size_t>(kp.stages) * STAGE_BYTES + 1024;
+  size_t smem = static_cast<size_t>(kp.stages) * STAGE_BYTES;
+  constexpr int GW = BN < 128 ? BN : 128;
+  constexpr size_t kStaging = BN >= 32 ? 4 * (size_t)EpiStage<(GW < 32 ? 32 : GW)>::WARP_BYTES : 0;
+  if constexpr (kStaging > 0) {
+    if (smem < kStaging) smem = kStaging;  // the epilogue reuses the (then idle) pipeline stages
+  }
+  smem += 1024;
   conv_fwd_kernel<BN, BKC><<<grid, kConvThreads, smem, stream>>>(kp);
   return check_launch("conv_fwd");
 }
+
+bool conv_rows_applicable(const vub_conv_desc* d);            // conv_rows.cu
+int conv_rows_launch(const vub_conv_desc* d, cudaStream_t stream);
 
 static int default_stages(int bn, int bkc, int ksteps) {
   const int stage_bytes = (kTileM + bn) * bkc * 2;
@@ -340,22 +337,25 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
   for (const void* q : ptrs)
     if (q && !aligned16(q)) return fail(VUB_E_ALIGN, "conv_fwd: pointer %p not 16B aligned", q);
 
+  if (conv_rows_applicable(d)) return conv_rows_launch(d, static_cast<cudaStream_t>(stream_v));
+
   const int bkc = d->c_src >= 64 ? 64 : 32;
   const int bn = cout > 256 ? 256 : cout;
 
   ConvKParams kp;
   memset(&kp, 0, sizeof(kp));
-  kp.scale = d->scale;
-  kp.shift = d->shift;
-  kp.residual = static_cast<const __nv_bfloat16*>(d->residual);
-  kp.out_raw = static_cast<__nv_bfloat16*>(d->out_raw);
-  kp.out_elu = static_cast<__nv_bfloat16*>(d->out_elu);
-  kp.out_f32 = static_cast<float*>(d->out_f32);
+  kp.ep.scale = d->scale;
+  kp.ep.shift = d->shift;
+  kp.ep.residual = static_cast<const __nv_bfloat16*>(d->residual);
+  kp.ep.out_raw = static_cast<__nv_bfloat16*>(d->out_raw);
+  kp.ep.out_elu = static_cast<__nv_bfloat16*>(d->out_elu);
+  kp.ep.out_f32 = static_cast<float*>(d->out_f32);
+  kp.ep.hout = hout;
+  kp.ep.wout = wout;
+  kp.ep.cout = cout;
+  kp.ep.cout_valid = d->cout_valid;
+  kp.ep.flags = f;
   kp.batch = d->batch;
-  kp.hout = hout;
-  kp.wout = wout;
-  kp.cout = cout;
-  kp.cout_valid = d->cout_valid;
   kp.nsrc = d->nsrc;
   kp.cblocks = d->c_src / bkc;
   kp.ntaps = d->ksize * d->ksize;
@@ -368,9 +368,8 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
   kp.tiles_w = wout / kp.tw;
   kp.tiles_h = hout / kp.th;
   const int tiles_n = (d->batch + kp.tn - 1) / kp.tn;
-  kp.flags = f;
   const int ksteps = kp.nsrc * kp.ntaps * kp.cblocks;
-  kp.stages = d->stages > 0 ? d->stages : default_stages(bn, bkc, ksteps);
+  kp.stages = d->stages > 0 ? d->stages : default_stages(bn, bkc, ksteps);  // stages < 0: force this kernel
   if (kp.stages > kMaxStages) kp.stages = kMaxStages;
   if ((size_t)kp.stages * (kTileM + bn) * bkc * 2 + 1024 > 200 * 1024)
     return fail(VUB_E_SHAPE, "conv_fwd: %d stages do not fit in shared memory", kp.stages);

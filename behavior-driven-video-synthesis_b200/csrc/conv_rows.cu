@@ -1,0 +1,479 @@
+// Row-streaming forward convolution for the wide, thin layers of the VUnet (output width >= 128,
+// <= 64 channels per source, <= 128 output channels; stride 1; 3x3 or 1x1) — the layers that are
+// HBM-bound or nearly so (32->32 @256^2, 64->64 @128^2, the skip `nin`s, ups.5,
+// out_conv).
+//
+// One CTA owns a strip of TH output rows x 128 output columns of one image:
+//   * the packed weights of ALL taps stay resident in shared memory for the CTA's lifetime;
+//   * every input row (130 pixels incl. the conv halo, out-of-bounds zero-filled by TMA) is loaded from
+//     L2/HBM ONCE into a ring of row buffers and feeds the 3 output rows that need it;
+//   * the 9 filter taps are 9 UMMA descriptors into those buffers — a tap's column shift is a start
+//     address offset of s * row_bytes into the swizzled buffer (verified on hardware:
+//     profiles/r01_exp_rowshift.log), so no im2col copy exists in shared memory either;
+//   * accumulators are double-buffered in TMEM; two epilogue warpgroups alternate output rows, each
+//     prefetching its next row's residual while the tensor core works on the other buffer.
+// L2->SM traffic per output row drops from 9 (+ weights) row-reads in the per-tap kernel to
+// (TH+2)/TH row-reads, which is what lets these layers approach the HBM roofline.
+//
+// Replaces the same reference code as conv_fwd.cu (lib/modules.py:140-145, 221-233, 24-34).
+#include <cuda_bf16.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "common.h"
+#include "conv_epilogue.cuh"
+#include "ptx.cuh"
+
+namespace vub {
+
+constexpr int kRowsThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue A, warps 6-9 epilogue B
+constexpr int kRowsMaxRing = 8;
+constexpr int kRowsW = 128;  // output columns per CTA = UMMA M
+
+struct RowsKParams {
+  CUtensorMap tmA[2];
+  CUtensorMap tmB;
+  EpiParams ep;
+  int batch;
+  int nsrc, ntaps;
+  int strips_w;         // wout / 128
+  long long total_rows; // strips_w * batch * hout: output rows of 128 pixels, the unit of work
+  int ring;             // row-buffer ring slots
+};
+
+template <int BKC>
+struct RowsGeom {
+  static constexpr int ROWB = BKC * 2;
+  // 130 rows are written per source; buffers are padded to keep every buffer 1024B aligned
+  static constexpr int SRC_BYTES = (BKC == 64) ? 136 * 128 : 144 * 64;
+};
+
+// Walks the CTA's contiguous range [g, g_end) of output rows.  Row index g = ((strip_w * B + n) * H + h);
+// a "segment" is a maximal run of rows inside one image (the unit that shares halo rows).
+struct RowWalker {
+  long long g, g_end;
+  int H, B;
+  int n, h, w0;   // current row
+  int seg_left;   // rows left in the current segment, including the current one
+  __device__ __forceinline__ void init(long long g0, long long g1, int H_, int B_) {
+    g = g0;
+    g_end = g1;
+    H = H_;
+    B = B_;
+    decode();
+  }
+  __device__ __forceinline__ void decode() {
+    if (g >= g_end) {
+      seg_left = 0;
+      return;
+    }
+    h = static_cast<int>(g % H);
+    const long long t = g / H;
+    n = static_cast<int>(t % B);
+    w0 = static_cast<int>(t / B) * 128;
+    const long long left = g_end - g;
+    seg_left = (H - h) < left ? (H - h) : static_cast<int>(left);
+  }
+  __device__ __forceinline__ bool valid() const { return g < g_end; }
+  __device__ __forceinline__ void next_row() {
+    ++g;
+    ++h;
+    if (--seg_left == 0) decode();
+  }
+  __device__ __forceinline__ void next_segment() {
+    g += seg_left;
+    decode();
+  }
+};
+
+template <int BN, int BKC, int NTAPS, int NSRC>
+__global__ void __launch_bounds__(kRowsThreads, 1)
+    conv_rows_kernel(const __grid_constant__ RowsKParams p) {
+  using G = RowsGeom<BKC>;
+  constexpr int ROWB = G::ROWB;
+  constexpr int SRC_BYTES = G::SRC_BYTES;
+  constexpr int WT_BYTES = BN * ROWB;  // one (source, tap) weight tile
+  constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  constexpr int CH = BN >= 32 ? 32 : 16;
+  constexpr int NCHUNK = BN / CH;
+  constexpr int halo = NTAPS == 9 ? 1 : 0;
+  constexpr int kdim = NTAPS == 9 ? 3 : 1;
+  constexpr int slot_bytes = NSRC * SRC_BYTES;
+  constexpr bool STAGED = BN >= 32 && BN <= 64;  // coalesced bf16 I/O through smem staging
+  constexpr int SGW = STAGED ? BN : 32;
+
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  __shared__ uint64_t w_full;
+  __shared__ uint64_t slot_full[kRowsMaxRing];
+  __shared__ uint64_t slot_empty[kRowsMaxRing];
+  __shared__ uint64_t acc_full[2];
+  __shared__ uint64_t acc_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_scale[BN];
+  __shared__ float s_shift[BN];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int R = p.ring;
+  uint8_t* wsm = smem;                             // [NSRC*NTAPS][BN][ROWB]
+  uint8_t* ring = smem + NSRC * NTAPS * WT_BYTES;  // [R][NSRC][SRC_BYTES]
+  uint8_t* staging = ring + R * slot_bytes;        // [8 epilogue warps][2][32][BN*2+16]
+
+  // this CTA's contiguous, balanced share of the output rows
+  const long long g_begin = p.total_rows * blockIdx.x / gridDim.x;
+  const long long g_end = p.total_rows * (blockIdx.x + 1) / gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(&w_full, 1);
+    for (int i = 0; i < R; ++i) {
+      mbar_init(&slot_full[i], 1);
+      mbar_init(&slot_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);  // one arrival per epilogue warp of the owning warpgroup
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<TMEM_COLS>(&tmem_base_slot);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < BN; i += kRowsThreads) {
+    s_scale[i] = p.ep.scale[i];
+    s_shift[i] = p.ep.shift[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  // Producer and MMA warps run their loops with ALL lanes (warp-uniform control flow); the TMA /
+  // tcgen05 instructions are issued from inside `if (elect_one())` blocks.  ptxas recognises the
+  // elect.sync idiom and emits back-to-back UTCHMMA with uniform-register descriptors; a plain
+  // `if (lane == 0)` made it wrap every tcgen05.mma in a per-lane "waterfall" loop (~70 cycles per MMA,
+  // measured: profiles/r01_exp_rates.log).
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    constexpr int ntiles = NSRC * NTAPS;
+    if (elect_one()) {
+      mbar_expect_tx(&w_full, ntiles * WT_BYTES);
+      for (int i = 0; i < ntiles; ++i) tma_load_2d(wsm + i * WT_BYTES, &p.tmB, &w_full, i * BKC, 0);
+    }
+    __syncwarp();
+    constexpr uint32_t row_tx = NSRC * (kRowsW + 2 * halo) * ROWB;
+    int st = 0;
+    uint32_t ph = 0;
+    RowWalker rw;
+    for (rw.init(g_begin, g_end, p.ep.hout, p.batch); rw.valid(); rw.next_segment()) {
+      const int n_in_rows = rw.seg_left + 2 * halo;
+      for (int ir = 0; ir < n_in_rows; ++ir) {
+        mbar_wait(&slot_empty[st], ph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&slot_full[st], row_tx);
+          uint8_t* dst = ring + st * slot_bytes;
+#pragma unroll
+          for (int s = 0; s < NSRC; ++s)
+            tma_load_4d(dst + s * SRC_BYTES, &p.tmA[s], &slot_full[st], 0, rw.w0 - halo, rw.h - halo + ir, rw.n);
+        }
+        __syncwarp();
+        if (++st == R) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------
+    constexpr uint32_t idesc = umma_idesc_bf16(kRowsW, BN);
+    const uint32_t desc_hi = umma_desc_hi_kmajor(ROWB);
+    mbar_wait(&w_full, 0);
+    const uint32_t w_lo = umma_desc_lo(smem_u32(wsm));
+    const uint32_t ring_lo = umma_desc_lo(smem_u32(ring));
+    constexpr uint32_t slot_units = static_cast<uint32_t>(slot_bytes) >> 4;
+    int slot0 = 0;                       // ring slot of this output row's first input row
+    int wait_slot = 0;                   // next slot whose arrival has not been observed yet
+    uint32_t wait_ph = 0;
+    int rows_seen = 0, rows_needed = 0;  // running input-row counters
+    uint32_t go = 0;                     // running output-row counter
+    RowWalker rw;
+    for (rw.init(g_begin, g_end, p.ep.hout, p.batch); rw.valid(); rw.next_segment()) {
+      const int th = rw.seg_left;
+      for (int orow = 0; orow < th; ++orow, ++go) {
+        const uint32_t b = go & 1;
+        mbar_wait(&acc_empty[b], ((go >> 1) & 1) ^ 1);
+        rows_needed += (orow == 0) ? 1 + 2 * halo : 1;
+        for (; rows_seen < rows_needed; ++rows_seen) {
+          mbar_wait(&slot_full[wait_slot], wait_ph);
+          if (++wait_slot == R) {
+            wait_slot = 0;
+            wait_ph ^= 1;
+          }
+        }
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + b * BN;
+        // ring slots of the kdim input rows this output row reads
+        int sl[3];
+        sl[0] = slot0;
+        sl[1] = slot0 + 1 >= R ? slot0 + 1 - R : slot0 + 1;
+        sl[2] = slot0 + 2 >= R ? slot0 + 2 - R : slot0 + 2;
+        const bool last = orow == th - 1;
+        if (elect_one()) {
+#pragma unroll
+          for (int s = 0; s < NSRC; ++s) {
+#pragma unroll
+            for (int r = 0; r < kdim; ++r) {
+              const uint32_t a_lo = ring_lo + sl[r] * slot_units + s * (SRC_BYTES >> 4);
+              const uint32_t b_lo = w_lo + (s * NTAPS + r * kdim) * (WT_BYTES >> 4);
+#pragma unroll
+              for (int q = 0; q < kdim; ++q) {
+#pragma unroll
+                for (int j = 0; j < BKC / 16; ++j)
+                  umma_bf16(d_tmem, umma_desc_join(desc_hi, a_lo + q * (ROWB >> 4) + 2 * j),
+                            umma_desc_join(desc_hi, b_lo + q * (WT_BYTES >> 4) + 2 * j), idesc,
+                            (s | r | q | j) != 0 ? 1u : 0u);
+              }
+            }
+          }
+          umma_commit(&acc_full[b]);
+          umma_commit(&slot_empty[sl[0]]);  // input row `orow` is not needed by later output rows
+          if (last && halo) {               // the segment's last output row also releases the halo rows
+            umma_commit(&slot_empty[sl[1]]);
+            umma_commit(&slot_empty[sl[2]]);
+          }
+        }
+        __syncwarp();
+        slot0 = sl[1];
+        if (last && halo) slot0 = sl[2] + 1 >= R ? sl[2] + 1 - R : sl[2] + 1;
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (two warpgroups, alternating rows) ----------------
+    const int g = (warp - 2) >> 2;  // warpgroup 0: warps 2-5 (even running rows), 1: warps 6-9 (odd)
+    const int q = warp & 3;         // TMEM lane quarter this warp may read
+    const int m = q * 32 + lane;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * BN;
+    const bool has_res = p.ep.residual != nullptr;
+    const bool bf16_out = (p.ep.flags & (VUB_CONV_F32_NHWC | VUB_CONV_F32_NCHW)) == 0;
+    const uint32_t t0 = smem_u32(staging) + (warp - 2) * EpiStage<SGW>::WARP_BYTES;  // residual in / raw out
+    const uint32_t t1 = t0 + EpiStage<SGW>::TILE_BYTES;                               // elu out
+    constexpr int CPR = SGW / 8;
+    uint4 rblk[CPR];  // STAGED: this warp's 32-pixel residual block of its NEXT row, linear 16B chunks
+
+    // element offset of channel 0 of pixel (n, oh, w0 + q*32) == start of this warp's contiguous block
+    auto block_off = [&](const RowWalker& r) {
+      return (((long long)r.n * p.ep.hout + r.h) * p.ep.wout + r.w0 + q * 32) * (long long)p.ep.cout;
+    };
+    auto prefetch_res = [&](const RowWalker& r) {
+      const uint4* src = reinterpret_cast<const uint4*>(p.ep.residual + block_off(r));
+#pragma unroll
+      for (int k = 0; k < CPR; ++k) rblk[k] = __ldg(src + lane + 32 * k);
+    };
+
+    RowWalker cur, ahead;  // `ahead` runs two rows in front (this warpgroup's next row)
+    cur.init(g_begin, g_end, p.ep.hout, p.batch);
+    if (g == 1 && cur.valid()) cur.next_row();
+    ahead = cur;
+    if (STAGED && has_res && bf16_out && cur.valid()) prefetch_res(cur);
+    uint32_t cnt = 0;  // rows this warpgroup has processed (its TMEM buffer's phase counter)
+    while (cur.valid()) {
+      if (ahead.valid()) ahead.next_row();
+      if (ahead.valid()) ahead.next_row();
+      const int n = cur.n, oh = cur.h, ow = cur.w0 + m;
+      if constexpr (STAGED) {
+        if (has_res && bf16_out) {
+          stage_fill_linear<SGW>(t0, rblk, lane);  // residual block -> staging; lanes then read their own row
+          __syncwarp();
+          if (ahead.valid()) prefetch_res(ahead);
+        }
+      }
+      mbar_wait(&acc_full[g], cnt & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c) {
+        uint32_t acc[CH];
+        if constexpr (CH == 32) tmem_ld32(trow + c * CH, acc);
+        else tmem_ld16(trow + c * CH, acc);
+        tmem_ld_wait();
+        if (c == NCHUNK - 1) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[g]);
+        }
+        float y[CH];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) y[i] = fmaf(__uint_as_float(acc[i]), s_scale[c * CH + i], s_shift[c * CH + i]);
+        if constexpr (STAGED) {
+          if (bf16_out) {
+            if (has_res) {
+#pragma unroll
+              for (int j = 0; j < CH / 8; ++j)
+                add_bf16x8(lds128(t0 + lane * EpiStage<SGW>::PITCH + c * CH * 2 + 16 * j), &y[8 * j]);
+            }
+            if (p.ep.out_raw != nullptr) stage_put32<SGW>(t0, lane, c * CH, y);
+            if (p.ep.out_elu != nullptr) {
+#pragma unroll
+              for (int i = 0; i < CH; ++i) y[i] = elu1(y[i]);
+              stage_put32<SGW>(t1, lane, c * CH, y);
+            }
+            continue;
+          }
+        }
+        if (has_res) {
+          const long long pix = ((long long)n * p.ep.hout + oh) * p.ep.wout + ow;
+          const uint4* r = reinterpret_cast<const uint4*>(p.ep.residual + pix * p.ep.cout + c * CH);
+#pragma unroll
+          for (int j = 0; j < CH / 8; ++j) add_bf16x8(__ldg(r + j), &y[8 * j]);
+        }
+        epi_store<CH>(p.ep, y, c * CH, n, oh, ow);
+      }
+      if constexpr (STAGED) {
+        if (bf16_out) {
+          const long long off = block_off(cur);
+          __syncwarp();
+          if (p.ep.out_raw != nullptr) stage_flush_linear<SGW>(t0, p.ep.out_raw + off, lane);
+          if (p.ep.out_elu != nullptr) stage_flush_linear<SGW>(t1, p.ep.out_elu + off, lane);
+          __syncwarp();
+        }
+      }
+      ++cnt;
+      cur = ahead;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int BN, int BKC, int NTAPS, int NSRC>
+static int launch_rows_t(const RowsKParams& kp, int grid, size_t smem, cudaStream_t stream) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_rows_kernel<BN, BKC, NTAPS, NSRC>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+  });
+  if (attr_err != cudaSuccess)
+    return fail(static_cast<int>(attr_err), "cudaFuncSetAttribute(conv_rows<%d,%d>): %s", BN, BKC,
+                cudaGetErrorString(attr_err));
+  conv_rows_kernel<BN, BKC, NTAPS, NSRC><<<grid, kRowsThreads, smem, stream>>>(kp);
+  return check_launch("conv_rows");
+}
+
+template <int BN, int BKC>
+static int launch_rows(const RowsKParams& kp, int grid, size_t smem, cudaStream_t stream) {
+  if (kp.ntaps == 9 && kp.nsrc == 1) return launch_rows_t<BN, BKC, 9, 1>(kp, grid, smem, stream);
+  if (kp.ntaps == 9 && kp.nsrc == 2) return launch_rows_t<BN, BKC, 9, 2>(kp, grid, smem, stream);
+  if (kp.ntaps == 1 && kp.nsrc == 1) return launch_rows_t<BN, BKC, 1, 1>(kp, grid, smem, stream);
+  return launch_rows_t<BN, BKC, 1, 2>(kp, grid, smem, stream);
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+static size_t rows_staging_bytes(int bn) {
+  return (bn >= 32 && bn <= 64) ? (size_t)8 * 2 * 32 * (bn * 2 + 16) : 0;
+}
+
+// Returns true when the row-streaming kernel covers this (already validated) descriptor.
+bool conv_rows_applicable(const vub_conv_desc* d) {
+  const int disabled = env_int("VUB_DISABLE_ROWS", 0);
+  if (disabled || d->stages < 0) return false;
+  if (d->stride != 1 || d->win < kRowsW || d->hin < 2 || d->c_src > 64 || d->cout > 128) return false;
+  if (d->c_src == 32 && d->cout > 64) return false;
+  const int bkc = d->c_src;  // one channel block per source
+  const int taps = d->ksize * d->ksize;
+  const size_t wbytes = (size_t)d->nsrc * taps * d->cout * bkc * 2;
+  const size_t slot = (size_t)d->nsrc * (bkc == 64 ? 136 * 128 : 144 * 64);
+  const int min_ring = taps == 9 ? 4 : 2;
+  return wbytes + min_ring * slot + rows_staging_bytes(d->cout) + 2048 <= 224 * 1024;
+}
+
+int conv_rows_launch(const vub_conv_desc* d, cudaStream_t stream) {
+  const int bkc = d->c_src;
+  const int taps = d->ksize * d->ksize;
+  const int bn = d->cout;
+  RowsKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.ep.scale = d->scale;
+  kp.ep.shift = d->shift;
+  kp.ep.residual = static_cast<const __nv_bfloat16*>(d->residual);
+  kp.ep.out_raw = static_cast<__nv_bfloat16*>(d->out_raw);
+  kp.ep.out_elu = static_cast<__nv_bfloat16*>(d->out_elu);
+  kp.ep.out_f32 = static_cast<float*>(d->out_f32);
+  kp.ep.hout = d->hin;
+  kp.ep.wout = d->win;
+  kp.ep.cout = d->cout;
+  kp.ep.cout_valid = d->cout_valid;
+  kp.ep.flags = d->flags;
+  kp.batch = d->batch;
+  kp.nsrc = d->nsrc;
+  kp.ntaps = taps;
+  kp.strips_w = d->win / kRowsW;
+  kp.total_rows = (long long)kp.strips_w * d->batch * d->hin;
+  const size_t wbytes = (size_t)d->nsrc * taps * bn * bkc * 2;
+  const size_t slot = (size_t)d->nsrc * (bkc == 64 ? 136 * 128 : 144 * 64);
+  const int ring_env = env_int("VUB_ROWS_RING", 0);
+  const size_t staging = rows_staging_bytes(bn);
+  int ring = static_cast<int>((216 * 1024 - wbytes - staging) / slot);
+  if (ring_env > 0) ring = ring_env;
+  const int min_ring = taps == 9 ? 4 : 2;
+  if (ring > kRowsMaxRing) ring = kRowsMaxRing;
+  if (ring < min_ring) ring = min_ring;
+  kp.ring = ring;
+  const size_t smem = wbytes + ring * slot + staging + 1024;
+
+  const uint64_t C = d->c_src, Hin = d->hin, Win = d->win, B = d->batch;
+  const uint64_t dims[4] = {C, Win, Hin, B};
+  const uint64_t strides[3] = {C * 2, Win * C * 2, Hin * Win * C * 2};
+  const uint32_t boxA[4] = {(uint32_t)bkc, (uint32_t)(kRowsW + (taps == 9 ? 2 : 0)), 1u, 1u};
+  int rc;
+  for (int s = 0; s < d->nsrc; ++s) {
+    rc = encode_tmap_bf16(&kp.tmA[s], d->x[s], 4, dims, strides, boxA, bkc * 2, false);
+    if (rc) return rc;
+  }
+  const uint64_t ktot = (uint64_t)d->nsrc * taps * bkc;
+  const uint64_t dimsb[2] = {ktot, (uint64_t)d->cout};
+  const uint64_t stridesb[1] = {ktot * 2};
+  const uint32_t boxB[2] = {(uint32_t)bkc, (uint32_t)bn};
+  rc = encode_tmap_bf16(&kp.tmB, d->w, 2, dimsb, stridesb, boxB, bkc * 2, true);
+  if (rc) return rc;
+
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  // persistent: one CTA per SM, each with a contiguous balanced range of output rows (>= 2 rows each)
+  const int grid_env = env_int("VUB_ROWS_GRID", 0);
+  long long want = kp.total_rows / 2 < n_sm ? kp.total_rows / 2 : n_sm;
+  if (grid_env > 0) want = grid_env;
+  const int grid = want < 1 ? 1 : static_cast<int>(want);
+#define VUB_ROWS_DISPATCH(BN_, BKC_) \
+  if (bn == BN_ && bkc == BKC_) return launch_rows<BN_, BKC_>(kp, grid, smem, stream);
+  VUB_ROWS_DISPATCH(16, 32)
+  VUB_ROWS_DISPATCH(32, 32)
+  VUB_ROWS_DISPATCH(64, 32)
+  VUB_ROWS_DISPATCH(16, 64)
+  VUB_ROWS_DISPATCH(32, 64)
+  VUB_ROWS_DISPATCH(64, 64)
+  VUB_ROWS_DISPATCH(128, 64)
+#undef VUB_ROWS_DISPATCH
+  return fail(VUB_E_SHAPE, "conv_rows: no kernel for BN %d BKC %d", bn, bkc);
+}
+
+}  // namespace vub

@@ -118,6 +118,32 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, executed by ALL lanes of a converged warp with warp-uniform operands; only lanes with
+// `issue != 0` (exactly one lane) issue the instruction.  Keeping the C++ control flow convergent lets
+// ptxas keep the descriptors in uniform registers without the per-lane "waterfall" loop it emits when
+// the asm sits inside a divergent `if (lane == 0)` region.
+__device__ __forceinline__ void umma_bf16_pred(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                               uint32_t idesc, uint32_t accumulate, uint32_t issue) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pred(uint64_t* bar, uint32_t issue) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(issue)
+      : "memory");
+}
 // All previously issued MMAs of this thread arrive on `bar` when complete
 // (implicitly performs tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -167,6 +193,18 @@ __device__ __forceinline__ uint64_t umma_smem_desc_kmajor(uint32_t smem_addr, ui
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) |
          (layout << 61);
 }
+// The same descriptor split for hot loops: the upper word is constant per operand layout, the lower
+// word is (address >> 4) | LBO, so advancing an operand is one 32-bit add.
+__device__ __forceinline__ uint32_t umma_desc_hi_kmajor(uint32_t row_bytes) {
+  const uint32_t layout = (row_bytes == 128) ? 2u : 4u;
+  return ((8u * row_bytes) >> 4) | (1u << 14) | (layout << 29);
+}
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);
+}
+__device__ __forceinline__ uint64_t umma_desc_join(uint32_t hi, uint32_t lo) {
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
 // Instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M = 128, N = n.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
   return (1u << 4)            // D format: fp32
@@ -176,6 +214,31 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
          | ((m >> 4) << 24);  // M / 16
 }
 
-__device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }
+// ELU(alpha = 1) for values about to be rounded to bf16: exp via one ex2.approx (5 instructions per
+// element) instead of expm1f (~30 dependent instructions, which made the conv epilogues latency- and
+// issue-bound).  Absolute error < 1.2e-7 (fp32 cancellation of exp(v)-1 near 0), i.e. far below the
+// bf16 rounding of the stored value for every |ELU(v)| > 1e-4 and negligible in absolute terms below.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float elu1(float v) {
+  const float e = ex2_approx(v * 1.4426950408889634f) - 1.0f;
+  return v > 0.f ? v : e;
+}
+
+// Explicit shared-space 128-bit accesses (keeps ptxas from falling back to generic LD/ST when a
+// shared pointer flows through selects).
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)
+               : "memory");
+  return v;
+}
 
 }  // namespace vub

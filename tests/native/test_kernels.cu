@@ -466,6 +466,31 @@ int main(int argc, char** argv) {
       {"3x3 128->128 @32x32 B2 stages=5",                  2, 32, 32, 128, 1, 128, 128, 3, 1, true, true, true, false, false, false, 5},
   };
   for (const ConvCase& c : cases) run_conv_case(c);
+  // row-streaming kernel (output width >= 128, <= 64 channels per source)
+  const ConvCase row_cases[] = {
+      {"rows 3x3 64->64 @16x128 B2 +res dual",             2, 16, 128, 64, 1, 64, 64, 3, 1, true, true, true, false, false, false, 0},
+      {"rows 3x3 32->32 @256x256 B1 +res dual (full size)", 1, 256, 256, 32, 1, 32, 32, 3, 1, true, true, true, false, false, false, 0},
+      {"rows 1x1 32->32 @16x256 B2 elu only",              2, 16, 256, 32, 1, 32, 32, 1, 1, false, false, true, false, false, false, 0},
+      {"rows 1x1 64->64 @8x128 B3 dual",                   3, 8, 128, 64, 1, 64, 64, 1, 1, false, true, true, false, false, false, 0},
+      {"rows 3x3 64->128 D2S @16x128 B1 dual",             1, 16, 128, 64, 1, 128, 128, 3, 1, false, true, true, true, false, false, 0},
+      {"rows 3x3 [32|32]->32 @32x256 B2 cat +res raw",     2, 32, 256, 32, 2, 32, 32, 3, 1, true, true, false, false, false, false, 0},
+      {"rows 3x3 64->64 @128x128 B2 +res dual",            2, 128, 128, 64, 1, 64, 64, 3, 1, true, true, true, false, false, false, 0},
+  };
+  for (const ConvCase& c : row_cases) run_conv_case(c);
+  setenv("VUB_ROWS_GRID", "7", 1);  // few persistent CTAs: long row ranges that cross image boundaries, ring wraps
+  {
+    const ConvCase c1 = {"rows persistent grid=7: 3x3 32->32 @64x128 B6 +res dual", 6, 64, 128, 32, 1, 32, 32, 3, 1, true, true, true, false, false, false, 0};
+    const ConvCase c2 = {"rows persistent grid=7: 1x1 32->32 @64x128 B6 dual", 6, 64, 128, 32, 1, 32, 32, 1, 1, false, true, true, false, false, false, 0};
+    const ConvCase c3 = {"rows persistent grid=7: 3x3 64->64 @64x128 B5 +res dual", 5, 64, 128, 64, 1, 64, 64, 3, 1, true, true, true, false, false, false, 0};
+    run_conv_case(c1);
+    run_conv_case(c2);
+    run_conv_case(c3);
+  }
+  unsetenv("VUB_ROWS_GRID");
+  setenv("VUB_DISABLE_ROWS", "1", 1);  // same wide shapes through the per-tap kernel
+  run_conv_case(row_cases[0]);
+  run_conv_case(row_cases[4]);
+  unsetenv("VUB_DISABLE_ROWS");
   test_wn_prep();
   test_stem(2, 3, 32, 64);
   test_stem(3, 30, 16, 16);
@@ -476,7 +501,7 @@ int main(int argc, char** argv) {
 
   if (perf) {
     const int B = 16;
-    for (int st : {0, 2, 4, 6}) {
+    for (int st : {0, -1}) {  // 0: library default (row-streaming where applicable); -1: per-tap kernel
       perf_conv("32->32 3x3 @256^2 +res dual", B, 256, 256, 32, 1, 32, 3, 1, true, true, false, st);
       perf_conv("[32|32]->32 3x3 @256^2 +res dual", B, 256, 256, 32, 2, 32, 3, 1, true, true, false, st);
       perf_conv("64->64 3x3 @128^2 +res dual", B, 128, 128, 64, 1, 64, 3, 1, true, true, false, st);
