@@ -21,8 +21,11 @@
 #include <cstring>
 #include <mutex>
 
+#include <cstdlib>
+
 #include "common.h"
 #include "conv_epilogue.cuh"
+#include "conv_tiles.cuh"
 #include "ptx.cuh"
 
 namespace vub {
@@ -338,6 +341,78 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
     if (q && !aligned16(q)) return fail(VUB_E_ALIGN, "conv_fwd: pointer %p not 16B aligned", q);
 
   if (conv_rows_applicable(d)) return conv_rows_launch(d, static_cast<cudaStream_t>(stream_v));
+
+  // Measured at 64 frames (profiles/r01_tiles_vs_pertap.log): the persistent tile kernel wins for the
+  // stride-2 and N >= 256 (up-sampling / latent) layers, the two-CTAs-per-SM per-tap kernel below for the
+  // stride-1 N <= 128 layers.  VUB_FWD_TILES=1 / =0 forces one or the other.
+  const char* force = getenv("VUB_FWD_TILES");
+  const bool want_tiles = force ? force[0] == '1' : (d->stride == 2 || cout >= 256);
+  if (want_tiles && d->stages >= 0) {
+    // persistent tile kernel, k-step table = (source, tap, channel block)
+    TileJob job;
+    memset(&job, 0, sizeof(job));
+    const int C = d->c_src;
+    const int bkc_ = C >= 64 ? 64 : 32;
+    const int cblocks = C / bkc_;
+    const int taps = d->ksize * d->ksize;
+    job.bkc = bkc_;
+    job.w = d->w;
+    job.ktot = (long long)d->nsrc * taps * C;
+    job.n_total = cout;
+    job.batch = d->batch;
+    job.hout = hout;
+    job.wout = wout;
+    if (d->stride == 1) {
+      job.n_src = d->nsrc;
+      for (int sidx = 0; sidx < d->nsrc; ++sidx)
+        job.src[sidx] = TileSrc{d->x[sidx], C, d->win, d->hin, (long long)C, (long long)d->win * C,
+                                (long long)d->hin * d->win * C};
+    } else {
+      job.n_src = 4;
+      for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw)
+          job.src[ph * 2 + pw] =
+              TileSrc{static_cast<const char*>(d->x[0]) + ((long long)ph * d->win + pw) * C * 2, C, d->win / 2,
+                      d->hin / 2, 2LL * C, 2LL * d->win * C, (long long)d->hin * d->win * C};
+    }
+    int ks = 0;
+    for (int sidx = 0; sidx < d->nsrc; ++sidx)
+      for (int tap = 0; tap < taps; ++tap) {
+        int dh = 0, dw = 0, mi = sidx;
+        if (taps == 9) {
+          const int r = tap / 3, q = tap % 3;
+          if (d->stride == 1) {
+            dh = r - 1;
+            dw = q - 1;
+          } else {  // input row 2*oh + r - 1: parity (r != 1), coordinate oh - (r == 0)
+            mi = ((r != 1) ? 2 : 0) + ((q != 1) ? 1 : 0);
+            dh = (r == 0) ? -1 : 0;
+            dw = (q == 0) ? -1 : 0;
+          }
+        }
+        for (int cb = 0; cb < cblocks; ++cb, ++ks)
+          job.ksteps[ks] = KStep{(uint8_t)mi, (int8_t)dh, (int8_t)dw, (uint8_t)cb, (uint16_t)ks, 0};
+      }
+    job.n_ksteps = ks;
+    TileEpi& e = job.epi;
+    e.scale = d->scale;
+    e.shift = d->shift;
+    e.addend = static_cast<const __nv_bfloat16*>(d->residual);
+    e.mask_elu = nullptr;
+    e.out_raw = static_cast<__nv_bfloat16*>(d->out_raw);
+    e.out_elu = static_cast<__nv_bfloat16*>(d->out_elu);
+    e.out_f32 = static_cast<float*>(d->out_f32);
+    const bool d2s = (f & VUB_CONV_D2S) != 0;
+    e.out_h = d2s ? 2 * hout : hout;
+    e.out_w = d2s ? 2 * wout : wout;
+    e.out_c = d2s ? cout / 4 : cout;
+    e.c_off = 0;
+    e.pix_stride = 1;
+    e.pix_off_h = e.pix_off_w = 0;
+    e.n_valid = d->cout_valid;
+    e.flags = f;
+    return conv_tiles_launch(job, static_cast<cudaStream_t>(stream_v));
+  }
 
   const int bkc = d->c_src >= 64 ? 64 : 32;
   const int bn = cout > 256 ? 256 : cout;

@@ -1,0 +1,439 @@
+// Persistent, warp-specialised implicit-GEMM tile kernel on tcgen05 (sm_100a) driven by a k-step table.
+//
+//   D[128 pixels, BN] (TMEM fp32, double-buffered) += A[128, BKC] (smem) * B[BN, BKC]^T (smem)   per k-step
+//
+// One CTA per SM loops over (pixel tile, N tile) pairs.  Warp 0 streams k-steps through a shared-memory
+// ring with TMA (A = a 4-D box of an NHWC activation tensor or of a strided parity view of one, shifted
+// by the k-step's pixel offset, out-of-bounds zero-filled; B = a tile of the packed weight matrix),
+// running ahead across tile boundaries; warp 1 issues tcgen05.mma into alternating TMEM buffers; two
+// epilogue warpgroups alternate tiles, so tile i's epilogue overlaps tile i+1's main loop.
+// The epilogue is table-free but mode-driven (TileEpi): fp32 scale/shift, optional ELU'-mask multiply
+// (data gradients), optional addend (residual / upstream gradient), raw and/or ELU bf16 outputs staged
+// through shared memory and written with coalesced 16-byte chunks, DepthToSpace or strided pixel
+// scatter, or fp32 NHWC / NCHW outputs.
+//
+// Users: vub_conv_fwd (every conv the row-streaming kernel does not take) and vub_conv_dgrad.
+// Replaces NormConv2d.forward / its autograd backward w.r.t. the input (lib/modules.py:140-145) with the
+// surrounding VunetRNB / Upsample / Downsample elementwise work fused in.
+#include "conv_tiles.cuh"
+
+#include <cstring>
+#include <mutex>
+
+#include "common.h"
+#include "conv_epilogue.cuh"
+#include "ptx.cuh"
+
+namespace vub {
+
+constexpr int kTilesThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9 epilogue warpgroups
+constexpr int kTilesMaxStages = 8;
+constexpr int kTilesMaxN = 512;
+
+struct TilesKParams {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB;
+  KStep ksteps[kTileMaxKSteps];
+  TileEpi ep;
+  int n_ksteps;
+  int batch, hout, wout;
+  int n_total;
+  int tw, th, tn, tw_log2, th_log2;
+  int tiles_w, tiles_h;
+  int n_ntiles;
+  int total_tiles;
+  int stages;
+};
+
+__device__ __forceinline__ long long tile_out_offset(const TileEpi& e, int col, int n, int oh, int ow) {
+  if (e.flags & VUB_CONV_F32_NCHW)
+    return (((long long)n * e.n_valid + col) * e.out_h + oh) * e.out_w + ow;
+  if (e.flags & VUB_CONV_D2S) {
+    const int qd = col / e.out_c;
+    const int cp = col - qd * e.out_c;
+    const long long opix = ((long long)n * e.out_h + 2 * oh + (qd >> 1)) * e.out_w + 2 * ow + (qd & 1);
+    return opix * e.out_c + cp;
+  }
+  const long long opix =
+      ((long long)n * e.out_h + oh * e.pix_stride + e.pix_off_h) * e.out_w + ow * e.pix_stride + e.pix_off_w;
+  return opix * e.out_c + e.c_off + col;
+}
+
+template <int BN, int BKC>
+__global__ void __launch_bounds__(kTilesThreads, 1)
+    conv_tiles_kernel(const __grid_constant__ TilesKParams p) {
+  constexpr int ROWB = BKC * 2;
+  constexpr int A_BYTES = 128 * ROWB;
+  constexpr int B_BYTES = BN * ROWB;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  constexpr int GW = BN >= 64 ? 64 : 32;  // channels staged per epilogue pass
+  constexpr bool STAGED = BN >= 32;
+  static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024B alignment");
+
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  __shared__ uint64_t full_bar[kTilesMaxStages];
+  __shared__ uint64_t empty_bar[kTilesMaxStages];
+  __shared__ uint64_t acc_full[2];
+  __shared__ uint64_t acc_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_scale[kTilesMaxN];
+  __shared__ float s_shift[kTilesMaxN];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = p.stages;
+  const int KS = p.n_ksteps;
+  uint8_t* staging = smem + S * STAGE_BYTES;  // [8 epilogue warps][2][32][GW*2+16]
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<TMEM_COLS>(&tmem_base_slot);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < p.n_total; i += kTilesThreads) {
+    s_scale[i] = p.ep.scale != nullptr ? p.ep.scale[i] : 1.0f;
+    s_shift[i] = p.ep.shift != nullptr ? p.ep.shift[i] : 0.0f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  auto tile_coords = [&](int tile, int& n_tile, int& n0, int& h0, int& w0) {
+    n_tile = tile % p.n_ntiles;
+    int t = tile / p.n_ntiles;
+    const int twi = t % p.tiles_w;
+    t /= p.tiles_w;
+    const int thi = t % p.tiles_h;
+    const int tni = t / p.tiles_h;
+    w0 = twi * p.tw;
+    h0 = thi * p.th;
+    n0 = tni * p.tn;
+  };
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    int st = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int n_tile, n0, h0, w0;
+      tile_coords(tile, n_tile, n0, h0, w0);
+      for (int ks = 0; ks < KS; ++ks) {
+        const KStep k = p.ksteps[ks];
+        mbar_wait(&empty_bar[st], ph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&full_bar[st], STAGE_BYTES);
+          uint8_t* a = smem + st * STAGE_BYTES;
+          tma_load_4d(a, &p.tmA[k.map], &full_bar[st], k.cblk * BKC, w0 + k.dw, h0 + k.dh, n0);
+          tma_load_2d(a + A_BYTES, &p.tmB, &full_bar[st], k.bblk * BKC, n_tile * BN);
+        }
+        __syncwarp();
+        if (++st == S) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+    const uint32_t desc_hi = umma_desc_hi_kmajor(ROWB);
+    const uint32_t smem_lo = umma_desc_lo(smem_u32(smem));
+    int st = 0;
+    uint32_t ph = 0;
+    uint32_t lt = 0;  // local tile counter
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      const uint32_t b = lt & 1;
+      mbar_wait(&acc_empty[b], ((lt >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + b * BN;
+      for (int ks = 0; ks < KS; ++ks) {
+        mbar_wait(&full_bar[st], ph);
+        tc_fence_after();
+        const uint32_t a_lo = smem_lo + st * (STAGE_BYTES >> 4);
+        const uint32_t b_lo = a_lo + (A_BYTES >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < BKC / 16; ++j)
+            umma_bf16(d_tmem, umma_desc_join(desc_hi, a_lo + 2 * j), umma_desc_join(desc_hi, b_lo + 2 * j), idesc,
+                      (ks | j) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[st]);
+          if (ks == KS - 1) umma_commit(&acc_full[b]);
+        }
+        __syncwarp();
+        if (++st == S) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (two warpgroups, alternating tiles) ---------------
+    const int g = (warp - 2) >> 2;
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int m = q * 32 + lane;
+    const int dw = m & (p.tw - 1);
+    const int dh = (m >> p.tw_log2) & (p.th - 1);
+    const int dn = m >> (p.tw_log2 + p.th_log2);
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * BN;
+    const uint32_t t0 = smem_u32(staging) + (warp - 2) * EpiStage<GW>::WARP_BYTES;  // addend in / raw out
+    const uint32_t t1 = t0 + EpiStage<GW>::TILE_BYTES;                              // mask in / elu out
+    const TileEpi& e = p.ep;
+    const bool f32_out = (e.flags & (VUB_CONV_F32_NHWC | VUB_CONV_F32_NCHW)) != 0;
+    constexpr int CPR = GW / 8;
+    uint32_t cnt = 0;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      if ((lt & 1) != (uint32_t)g) continue;
+      int n_tile, n0, h0, w0;
+      tile_coords(tile, n_tile, n0, h0, w0);
+      const int n = n0 + dn, oh = h0 + dh, ow = w0 + dw;
+      const bool valid = n < p.batch;
+      // pixel of staged row `row` of this warp
+      auto row_pixel = [&](int row, int& rn, int& roh, int& row_w) {
+        const int mm = q * 32 + row;
+        rn = n0 + (mm >> (p.tw_log2 + p.th_log2));
+        roh = h0 + ((mm >> p.tw_log2) & (p.th - 1));
+        row_w = w0 + (mm & (p.tw - 1));
+        return rn < p.batch;
+      };
+      auto stage_fill = [&](uint32_t tile_addr, const __nv_bfloat16* src, int col0) {
+#pragma unroll
+        for (int k = 0; k < CPR; ++k) {
+          const int c = lane + 32 * k;
+          const int row = c / CPR;
+          const int col = c - row * CPR;
+          int rn, roh, row_w;
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (row_pixel(row, rn, roh, row_w))
+            v = __ldg(reinterpret_cast<const uint4*>(src + tile_out_offset(e, col0 + col * 8, rn, roh, row_w)));
+          sts128(tile_addr + row * EpiStage<GW>::PITCH + col * 16, v);
+        }
+      };
+      auto stage_flush_out = [&](uint32_t tile_addr, __nv_bfloat16* dst, int col0) {
+#pragma unroll
+        for (int k = 0; k < CPR; ++k) {
+          const int c = lane + 32 * k;
+          const int row = c / CPR;
+          const int col = c - row * CPR;
+          int rn, roh, row_w;
+          if (row_pixel(row, rn, roh, row_w))
+            *reinterpret_cast<uint4*>(dst + tile_out_offset(e, col0 + col * 8, rn, roh, row_w)) =
+                lds128(tile_addr + row * EpiStage<GW>::PITCH + col * 16);
+        }
+      };
+
+      mbar_wait(&acc_full[g], cnt & 1);
+      tc_fence_after();
+      if constexpr (STAGED) {
+#pragma unroll 1
+        for (int g0 = 0; g0 < BN; g0 += GW) {
+          const int col0 = n_tile * BN + g0;  // first GEMM column of this group
+          if (!f32_out) {
+            if (e.addend != nullptr) stage_fill(t0, e.addend, col0);
+            if (e.mask_elu != nullptr) stage_fill(t1, e.mask_elu, col0);
+            __syncwarp();
+          }
+#pragma unroll 1
+          for (int c0 = g0; c0 < g0 + GW; c0 += 32) {
+            uint32_t acc[32];
+            tmem_ld32(trow + c0, acc);
+            tmem_ld_wait();
+            if (c0 + 32 == BN) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&acc_empty[g]);
+            }
+            float y[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              y[i] = fmaf(__uint_as_float(acc[i]), s_scale[n_tile * BN + c0 + i], s_shift[n_tile * BN + c0 + i]);
+            if (f32_out) {
+              if (valid) {
+                if (e.flags & VUB_CONV_F32_NCHW) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i)
+                    if (n_tile * BN + c0 + i < e.n_valid)
+                      e.out_f32[tile_out_offset(e, n_tile * BN + c0 + i, n, oh, ow)] = y[i];
+                } else {
+                  float4* o = reinterpret_cast<float4*>(e.out_f32 + tile_out_offset(e, n_tile * BN + c0, n, oh, ow));
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) o[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+                }
+              }
+              continue;
+            }
+            const uint32_t my = lane * EpiStage<GW>::PITCH + (c0 - g0) * 2;
+            if (e.mask_elu != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float ev[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                add_bf16x8(lds128(t1 + my + 16 * j), ev);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) y[8 * j + i] *= ev[i] > 0.f ? 1.0f : ev[i] + 1.0f;
+              }
+            }
+            if (e.addend != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) add_bf16x8(lds128(t0 + my + 16 * j), &y[8 * j]);
+            }
+            if (e.out_raw != nullptr) stage_put32<GW>(t0, lane, c0 - g0, y);
+            if (e.out_elu != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) y[i] = elu1(y[i]);
+              stage_put32<GW>(t1, lane, c0 - g0, y);
+            }
+          }
+          if (!f32_out) {
+            __syncwarp();
+            if (e.out_raw != nullptr) stage_flush_out(t0, e.out_raw, col0);
+            if (e.out_elu != nullptr) stage_flush_out(t1, e.out_elu, col0);
+            __syncwarp();
+          }
+        }
+      } else {
+        // BN == 16: fp32 NCHW output of out_conv-like layers
+        uint32_t acc[16];
+        tmem_ld16(trow, acc);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[g]);
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int col = n_tile * BN + i;
+            const float y = fmaf(__uint_as_float(acc[i]), s_scale[col], s_shift[col]);
+            if (e.flags & VUB_CONV_F32_NCHW) {
+              if (col < e.n_valid) e.out_f32[tile_out_offset(e, col, n, oh, ow)] = y;
+            } else if (e.flags & VUB_CONV_F32_NHWC) {
+              e.out_f32[tile_out_offset(e, col, n, oh, ow)] = y;
+            }
+          }
+        }
+      }
+      ++cnt;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int BN, int BKC>
+static int launch_tiles(const TilesKParams& kp, int grid, size_t smem, cudaStream_t stream) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_tiles_kernel<BN, BKC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    220 * 1024);
+  });
+  if (attr_err != cudaSuccess)
+    return fail(static_cast<int>(attr_err), "cudaFuncSetAttribute(conv_tiles<%d,%d>): %s", BN, BKC,
+                cudaGetErrorString(attr_err));
+  conv_tiles_kernel<BN, BKC><<<grid, kTilesThreads, smem, stream>>>(kp);
+  return check_launch("conv_tiles");
+}
+
+int conv_tiles_launch(const TileJob& job, cudaStream_t stream) {
+  const int bkc = job.bkc;
+  if (bkc != 32 && bkc != 64) return fail(VUB_E_SHAPE, "conv_tiles: bkc %d", bkc);
+  const int n_total = job.n_total;
+  if (n_total > kTilesMaxN) return fail(VUB_E_SHAPE, "conv_tiles: N %d > %d", n_total, kTilesMaxN);
+  int bn = n_total > 256 ? 256 : n_total;
+  if (!(bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256) || n_total % bn)
+    return fail(VUB_E_SHAPE, "conv_tiles: N %d not tileable", n_total);
+  if (job.n_ksteps <= 0 || job.n_ksteps > kTileMaxKSteps) return fail(VUB_E_SHAPE, "conv_tiles: %d k-steps", job.n_ksteps);
+  if (!is_pow2(job.hout) || !is_pow2(job.wout)) return fail(VUB_E_SHAPE, "conv_tiles: tile grid %dx%d", job.hout, job.wout);
+  if (job.epi.mask_elu && job.epi.out_elu) return fail(VUB_E_FLAGS, "conv_tiles: mask and elu output share a staging tile");
+
+  TilesKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  memcpy(kp.ksteps, job.ksteps, sizeof(KStep) * job.n_ksteps);
+  kp.ep = job.epi;
+  kp.n_ksteps = job.n_ksteps;
+  kp.batch = job.batch;
+  kp.hout = job.hout;
+  kp.wout = job.wout;
+  kp.n_total = n_total;
+  kp.tw = job.wout < 128 ? job.wout : 128;
+  kp.th = job.hout < 128 / kp.tw ? job.hout : 128 / kp.tw;
+  kp.tn = 128 / (kp.tw * kp.th);
+  kp.tw_log2 = ilog2(kp.tw);
+  kp.th_log2 = ilog2(kp.th);
+  kp.tiles_w = job.wout / kp.tw;
+  kp.tiles_h = job.hout / kp.th;
+  const int tiles_n = (job.batch + kp.tn - 1) / kp.tn;
+  kp.n_ntiles = n_total / bn;
+  kp.total_tiles = kp.tiles_w * kp.tiles_h * tiles_n * kp.n_ntiles;
+
+  const int gw = bn >= 64 ? 64 : 32;
+  const size_t staging = bn >= 32 ? (size_t)8 * 2 * 32 * (gw * 2 + 16) : 0;
+  const size_t stage_bytes = (size_t)(128 + bn) * bkc * 2;
+  int stages = static_cast<int>((212 * 1024 - staging) / stage_bytes);
+  if (stages > kTilesMaxStages) stages = kTilesMaxStages;
+  if (stages < 2) return fail(VUB_E_SHAPE, "conv_tiles: pipeline does not fit");
+  kp.stages = stages;
+  const size_t smem = stages * stage_bytes + staging + 1024;
+
+  const uint32_t boxA[4] = {(uint32_t)bkc, (uint32_t)kp.tw, (uint32_t)kp.th, (uint32_t)kp.tn};
+  int rc;
+  for (int s = 0; s < job.n_src; ++s) {
+    const TileSrc& t = job.src[s];
+    const uint64_t dims[4] = {(uint64_t)t.channels, (uint64_t)t.w, (uint64_t)t.h, (uint64_t)job.batch};
+    const uint64_t strides[3] = {(uint64_t)t.stride_w * 2, (uint64_t)t.stride_h * 2, (uint64_t)t.stride_n * 2};
+    rc = encode_tmap_bf16(&kp.tmA[s], t.base, 4, dims, strides, boxA, bkc * 2, false);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)job.ktot, (uint64_t)n_total};
+    const uint64_t strides[1] = {(uint64_t)job.ktot * 2};
+    const uint32_t boxB[2] = {(uint32_t)bkc, (uint32_t)bn};
+    rc = encode_tmap_bf16(&kp.tmB, job.w, 2, dims, strides, boxB, bkc * 2, true);
+    if (rc) return rc;
+  }
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  const int grid = kp.total_tiles < n_sm ? kp.total_tiles : n_sm;
+
+#define VUB_TILES_DISPATCH(BN_, BKC_) \
+  if (bn == BN_ && bkc == BKC_) return launch_tiles<BN_, BKC_>(kp, grid, smem, stream);
+  VUB_TILES_DISPATCH(16, 32)
+  VUB_TILES_DISPATCH(16, 64)
+  VUB_TILES_DISPATCH(32, 32)
+  VUB_TILES_DISPATCH(32, 64)
+  VUB_TILES_DISPATCH(64, 32)
+  VUB_TILES_DISPATCH(64, 64)
+  VUB_TILES_DISPATCH(128, 32)
+  VUB_TILES_DISPATCH(128, 64)
+  VUB_TILES_DISPATCH(256, 32)
+  VUB_TILES_DISPATCH(256, 64)
+#undef VUB_TILES_DISPATCH
+  return fail(VUB_E_SHAPE, "conv_tiles: no kernel for BN %d BKC %d", bn, bkc);
+}
+
+}  // namespace vub
