@@ -31,7 +31,14 @@ EXPORTED_SYMBOLS = (
     "vub_latent_fwd",
     "vub_nchw_f32_to_nhwc_bf16",
     "vub_nhwc_bf16_to_nchw_f32",
+    "vub_nchw_f32_to_nhwc_bf16_pad",
+    "vub_conv_dgrad",
+    "vub_conv_wgrad",
+    "vub_wn_bwd",
+    "vub_stem_bwd",
+    "vub_latent_bwd",
 )
+ABI_VERSION = 2
 
 
 class ConvDesc(C.Structure):
@@ -78,6 +85,78 @@ class WnEntry(C.Structure):
         ("c_src", C.c_int32),
         ("ktot", C.c_int32),
         ("row_start", C.c_int32),
+        ("wd", C.c_void_p),
+        ("wd_cout", C.c_int32),
+        ("wd_col0", C.c_int32),
+    ]
+
+
+class DgradDesc(C.Structure):
+    """Mirror of ``vub_dgrad_desc``."""
+
+    _fields_ = [
+        ("dy", C.c_void_p),
+        ("wd", C.c_void_p),
+        ("dx", C.c_void_p * 2),
+        ("mask_elu", C.c_void_p * 2),
+        ("addend", C.c_void_p * 2),
+        ("addend2", C.c_void_p * 2),
+        ("nsrc", C.c_int32),
+        ("c_src", C.c_int32),
+        ("batch", C.c_int32),
+        ("hin", C.c_int32),
+        ("win", C.c_int32),
+        ("cout_k", C.c_int32),
+        ("ksize", C.c_int32),
+        ("stride", C.c_int32),
+        ("flags", C.c_uint32),
+    ]
+
+
+class WgradDesc(C.Structure):
+    """Mirror of ``vub_wgrad_desc``."""
+
+    _fields_ = [
+        ("dy", C.c_void_p),
+        ("x", C.c_void_p * 2),
+        ("gt", C.c_void_p),
+        ("dy_sum", C.c_void_p),
+        ("nsrc", C.c_int32),
+        ("c_src", C.c_int32),
+        ("batch", C.c_int32),
+        ("hin", C.c_int32),
+        ("win", C.c_int32),
+        ("cout_k", C.c_int32),
+        ("gt_pitch", C.c_int32),
+        ("ksize", C.c_int32),
+        ("stride", C.c_int32),
+        ("flags", C.c_uint32),
+    ]
+
+
+class WnbEntry(C.Structure):
+    """Mirror of ``vub_wnb_entry``."""
+
+    _fields_ = [
+        ("v", C.c_void_p),
+        ("g", C.c_void_p),
+        ("gamma", C.c_void_p),
+        ("bias", C.c_void_p),
+        ("gt", C.c_void_p),
+        ("dy_sum", C.c_void_p),
+        ("d_v", C.c_void_p),
+        ("d_g", C.c_void_p),
+        ("d_gamma", C.c_void_p),
+        ("d_beta", C.c_void_p),
+        ("d_bias", C.c_void_p),
+        ("cout", C.c_int32),
+        ("cin", C.c_int32),
+        ("ktaps", C.c_int32),
+        ("c_src", C.c_int32),
+        ("gt_pitch", C.c_int32),
+        ("gt_col0", C.c_int32),
+        ("row_start", C.c_int32),
+        ("pad", C.c_int32),
     ]
 
 
@@ -117,6 +196,18 @@ def _declare(lib: C.CDLL) -> None:
     lib.vub_nchw_f32_to_nhwc_bf16.argtypes = [fp, i32, i32, i32, i32, vp, vp, vp]
     lib.vub_nhwc_bf16_to_nchw_f32.restype = C.c_int
     lib.vub_nhwc_bf16_to_nchw_f32.argtypes = [vp, i32, i32, i32, i32, fp, vp]
+    lib.vub_nchw_f32_to_nhwc_bf16_pad.restype = C.c_int
+    lib.vub_nchw_f32_to_nhwc_bf16_pad.argtypes = [fp, i32, i32, i32, i32, i32, vp, vp]
+    lib.vub_conv_dgrad.restype = C.c_int
+    lib.vub_conv_dgrad.argtypes = [C.POINTER(DgradDesc), vp]
+    lib.vub_conv_wgrad.restype = C.c_int
+    lib.vub_conv_wgrad.argtypes = [C.POINTER(WgradDesc), vp]
+    lib.vub_wn_bwd.restype = C.c_int
+    lib.vub_wn_bwd.argtypes = [vp, i32, i32, i32, vp]
+    lib.vub_stem_bwd.restype = C.c_int
+    lib.vub_stem_bwd.argtypes = [fp, vp, i32, i32, i32, i32, i32, fp, fp, vp]
+    lib.vub_latent_bwd.restype = C.c_int
+    lib.vub_latent_bwd.argtypes = [fp, fp, fp, fp, fp, vp, i32, i32, i32, i32, vp, vp]
 
 
 def lib() -> C.CDLL:

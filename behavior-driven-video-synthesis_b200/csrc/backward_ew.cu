@@ -1,0 +1,292 @@
+// Memory-bound kernels of the training half of the VUnet path: parameter gradients of all
+// weight-normalised convs from their weight correlations (one launch per step), the stem's weight
+// correlation (K = 3/30 input channels: CUDA cores), the latent head's backward and the image-gradient
+// layout converter.  Coalesced accesses, warp-shuffle / shared-memory reductions, fp32 arithmetic.
+//
+// Replaces what autograd runs in the reference: aten::_weight_norm_interface_backward and the mul/add
+// backward of lib/modules.py:135-145, sigmoid/exp/mul/add backward of models/vunets.py:575,594-597.
+#include <cuda_bf16.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vub {
+
+__device__ __forceinline__ float warp_sum_b(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Two block-wide sums at once (blockDim.x multiple of 32, <= 1024); every thread gets both.
+__device__ __forceinline__ float2 block_sum2(float a, float b, float2* red /*[32]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  a = warp_sum_b(a);
+  b = warp_sum_b(b);
+  if (lane == 0) red[warp] = make_float2(a, b);
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float2 t = (threadIdx.x < nw) ? red[threadIdx.x] : make_float2(0.f, 0.f);
+  if (warp == 0) {
+    t.x = warp_sum_b(t.x);
+    t.y = warp_sum_b(t.y);
+    if (lane == 0) red[0] = t;
+  }
+  __syncthreads();
+  t = red[0];
+  __syncthreads();
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight-norm / affine parameter gradients: one block per output channel of any layer.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWnbThreads = 128;
+
+__global__ void __launch_bounds__(kWnbThreads)
+    wn_bwd_kernel(const vub_wnb_entry* __restrict__ table, int n_entries, int accumulate) {
+  __shared__ float2 red[32];
+  const int row = blockIdx.x;
+  int lo = 0, hi = n_entries - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (table[mid].row_start <= row) lo = mid;
+    else hi = mid - 1;
+  }
+  const vub_wnb_entry e = table[lo];
+  const int co = row - e.row_start;
+  if (co >= e.cout) return;
+  const int len = e.cin * e.ktaps;
+  const float* v = e.v + (size_t)co * len;
+  const float* gcol = e.gt + e.gt_col0 + co;
+  // correlation element of weight index i = (ci, tap): row (src*ktaps + tap)*c_src + cs of gt
+  auto g_at = [&](int i) {
+    const int ci = i / e.ktaps;
+    const int tap = i - ci * e.ktaps;
+    const int src = ci / e.c_src;
+    const int cs = ci - src * e.c_src;
+    return gcol[(size_t)((src * e.ktaps + tap) * e.c_src + cs) * e.gt_pitch];
+  };
+  float ss = 0.f, vg = 0.f;
+  for (int i = threadIdx.x; i < len; i += kWnbThreads) {
+    const float x = v[i];
+    ss = fmaf(x, x, ss);
+    vg = fmaf(x, g_at(i), vg);
+  }
+  const float2 r = block_sum2(ss, vg, red);
+  const float inv = 1.0f / sqrtf(r.x);
+  const float dot = r.y * inv;  // v_hat . G
+  const float ga = e.gamma[co], gg = e.g[co], bi = e.bias[co];
+  const float S = e.dy_sum[e.gt_col0 + co];
+  const float k = ga * gg * inv;
+  float* dv = e.d_v + (size_t)co * len;
+  for (int i = threadIdx.x; i < len; i += kWnbThreads) {
+    const float val = k * (g_at(i) - v[i] * inv * dot);
+    dv[i] = accumulate ? dv[i] + val : val;
+  }
+  if (threadIdx.x == 0) {
+    const float dg = ga * dot, dgam = fmaf(gg, dot, bi * S), dbeta = S, dbias = ga * S;
+    if (accumulate) {
+      e.d_g[co] += dg;
+      e.d_gamma[co] += dgam;
+      e.d_beta[co] += dbeta;
+      e.d_bias[co] += dbias;
+    } else {
+      e.d_g[co] = dg;
+      e.d_gamma[co] = dgam;
+      e.d_beta[co] = dbeta;
+      e.d_bias[co] = dbias;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stem correlation: gt[ci][co] += sum_pix x[n, ci, pix] * dy[n, pix, co];  dy_sum[co] += sum dy.
+// 256 threads = 32 output channels x 8 input-channel groups; 64-pixel chunks staged in shared memory
+// (x coalesced along pixels per channel plane, dy as contiguous 64-byte / 128-byte pixel rows).
+// ------------------------------------------------------------------------------------------------
+constexpr int kSbThreads = 256;
+constexpr int kSbPix = 64;
+constexpr int kSbMaxCx = 64;
+
+template <int COUT>
+__global__ void __launch_bounds__(kSbThreads)
+    stem_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int cx, int hw,
+                    long long n_chunks, float* __restrict__ gt, float* __restrict__ dy_sum) {
+  constexpr int NG = kSbThreads / COUT;        // input-channel groups
+  constexpr int MAXA = kSbMaxCx / NG + 1;
+  __shared__ float xs[kSbMaxCx][kSbPix + 1];
+  __shared__ float ds[kSbPix][COUT + 1];
+  const int co = threadIdx.x % COUT, grp = threadIdx.x / COUT;
+  float acc[MAXA];
+#pragma unroll
+  for (int k = 0; k < MAXA; ++k) acc[k] = 0.f;
+  float sdy = 0.f;
+  const int chunks_per_img = hw / kSbPix;
+  for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+    const long long n = ch / chunks_per_img;
+    const int p0 = static_cast<int>(ch - n * chunks_per_img) * kSbPix;
+    for (int i = threadIdx.x; i < cx * kSbPix; i += kSbThreads) {
+      const int ci = i / kSbPix, pp = i - ci * kSbPix;
+      xs[ci][pp] = __ldg(x + (n * cx + ci) * hw + p0 + pp);
+    }
+    const __nv_bfloat16* dp = dy + (n * hw + p0) * COUT;
+    for (int i = threadIdx.x; i < kSbPix * COUT; i += kSbThreads) ds[i / COUT][i % COUT] = __bfloat162float(dp[i]);
+    __syncthreads();
+#pragma unroll 4
+    for (int pp = 0; pp < kSbPix; ++pp) {
+      const float d = ds[pp][co];
+      if (grp == 0) sdy += d;
+#pragma unroll
+      for (int k = 0; k < MAXA; ++k) {
+        const int ci = grp + k * NG;
+        if (ci < cx) acc[k] = fmaf(xs[ci][pp], d, acc[k]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < MAXA; ++k) {
+    const int ci = grp + k * NG;
+    if (ci < cx) atomicAdd(gt + ci * COUT + co, acc[k]);
+  }
+  if (grp == 0) atomicAdd(dy_sum + co, sdy);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Latent head backward: one thread per 4 channels of one pixel (mirror of latent_kernel).
+// ------------------------------------------------------------------------------------------------
+constexpr int kLbThreads = 128;
+
+__global__ void __launch_bounds__(kLbThreads)
+    latent_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ ls, const float* __restrict__ eps,
+                      const float* __restrict__ d_mu, const float* __restrict__ d_ls,
+                      const __nv_bfloat16* __restrict__ dz, int c, int hw, long long total4,
+                      __nv_bfloat16* __restrict__ d_ml) {
+  const long long idx = (long long)blockIdx.x * kLbThreads + threadIdx.x;
+  if (idx >= total4) return;
+  const int c4 = c >> 2;
+  const long long pix = idx / c4;
+  const int ch = static_cast<int>(idx - pix * c4) * 4;
+  const long long n = pix / hw;
+  const int sp = static_cast<int>(pix - n * hw);
+  float dzv[4] = {0.f, 0.f, 0.f, 0.f};
+  if (dz != nullptr) {
+    const uint2 u = *reinterpret_cast<const uint2*>(dz + pix * c + ch);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+    dzv[0] = __low2float(a); dzv[1] = __high2float(a); dzv[2] = __low2float(b); dzv[3] = __high2float(b);
+  }
+  float gm[4], gl[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long o = (n * c + ch + i) * hw + sp;  // NCHW
+    const float l = ls[o];
+    const float e = eps != nullptr ? eps[o] : 0.f;
+    const float dm = (d_mu != nullptr ? d_mu[o] : 0.f) + dzv[i];
+    const float dl = (d_ls != nullptr ? d_ls[o] : 0.f) + dzv[i] * e * expf(l);
+    gm[i] = dm;
+    gl[i] = dl * l * (1.0f - l);
+  }
+  (void)mu;
+  __nv_bfloat162 a = __floats2bfloat162_rn(gm[0], gm[1]), b = __floats2bfloat162_rn(gm[2], gm[3]);
+  *reinterpret_cast<uint2*>(d_ml + pix * (2 * c) + ch) =
+      make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+  a = __floats2bfloat162_rn(gl[0], gl[1]);
+  b = __floats2bfloat162_rn(gl[2], gl[3]);
+  *reinterpret_cast<uint2*>(d_ml + pix * (2 * c) + c + ch) =
+      make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCHW fp32 [B, c, hw] -> NHWC bf16 [B, hw, c_pad] with zero-filled pad channels; one thread per pixel.
+// ------------------------------------------------------------------------------------------------
+template <int CPAD>
+__global__ void __launch_bounds__(256)
+    nchw_to_nhwc_pad_kernel(const float* __restrict__ src, int c, long long hw, long long total,
+                            __nv_bfloat16* __restrict__ dst) {
+  const long long pix = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (pix >= total) return;
+  const long long n = pix / hw, sp = pix - n * hw;
+  float v[CPAD];
+#pragma unroll
+  for (int i = 0; i < CPAD; ++i) v[i] = i < c ? __ldg(src + (n * c + i) * hw + sp) : 0.f;
+  uint4* o = reinterpret_cast<uint4*>(dst + pix * CPAD);
+#pragma unroll
+  for (int j = 0; j < CPAD / 8; ++j) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+    __nv_bfloat162 cc = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+    __nv_bfloat162 d = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+    o[j] = make_uint4(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b),
+                      *reinterpret_cast<uint32_t*>(&cc), *reinterpret_cast<uint32_t*>(&d));
+  }
+}
+
+}  // namespace vub
+
+using namespace vub;
+
+extern "C" int vub_wn_bwd(const vub_wnb_entry* table_dev, int32_t n_entries, int32_t total_rows,
+                          int32_t accumulate, void* stream) {
+  clear_error();
+  if (!table_dev) return fail(VUB_E_NULL, "wn_bwd: table is NULL");
+  if (n_entries <= 0 || total_rows <= 0) return fail(VUB_E_SHAPE, "wn_bwd: empty table");
+  wn_bwd_kernel<<<total_rows, kWnbThreads, 0, static_cast<cudaStream_t>(stream)>>>(table_dev, n_entries, accumulate);
+  return check_launch("wn_bwd");
+}
+
+extern "C" int vub_stem_bwd(const float* x_nchw, const void* dy_nhwc, int32_t batch, int32_t cx, int32_t h,
+                            int32_t w, int32_t cout, float* gt, float* dy_sum, void* stream) {
+  clear_error();
+  if (!x_nchw || !dy_nhwc || !gt || !dy_sum) return fail(VUB_E_NULL, "stem_bwd: NULL pointer");
+  const long long hw = (long long)h * w;
+  if (batch <= 0 || cx <= 0 || cx > kSbMaxCx || hw <= 0 || hw % kSbPix || hw > (1 << 30))
+    return fail(VUB_E_SHAPE, "stem_bwd: batch %d cx %d h %d w %d (cx <= %d, h*w %% %d == 0)", batch, cx, h, w,
+                kSbMaxCx, kSbPix);
+  const long long n_chunks = (long long)batch * (hw / kSbPix);
+  const unsigned grid = static_cast<unsigned>(n_chunks < 148 * 4 ? n_chunks : 148 * 4);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (cout == 32)
+    stem_bwd_kernel<32><<<grid, kSbThreads, 0, s>>>(x_nchw, static_cast<const __nv_bfloat16*>(dy_nhwc), cx,
+                                                    static_cast<int>(hw), n_chunks, gt, dy_sum);
+  else if (cout == 64)
+    stem_bwd_kernel<64><<<grid, kSbThreads, 0, s>>>(x_nchw, static_cast<const __nv_bfloat16*>(dy_nhwc), cx,
+                                                    static_cast<int>(hw), n_chunks, gt, dy_sum);
+  else
+    return fail(VUB_E_SHAPE, "stem_bwd: cout %d not in {32,64}", cout);
+  return check_launch("stem_bwd");
+}
+
+extern "C" int vub_latent_bwd(const float* mu_nchw, const float* logstd_nchw, const float* eps_nchw,
+                              const float* d_mu_nchw, const float* d_ls_nchw, const void* dz_nhwc, int32_t batch,
+                              int32_t c, int32_t h, int32_t w, void* d_ml_nhwc, void* stream) {
+  clear_error();
+  if (!logstd_nchw || !d_ml_nhwc) return fail(VUB_E_NULL, "latent_bwd: NULL pointer");
+  if (batch <= 0 || c <= 0 || (c & 3) || h <= 0 || w <= 0)
+    return fail(VUB_E_SHAPE, "latent_bwd: batch %d c %d h %d w %d (c %% 4 == 0)", batch, c, h, w);
+  const long long total4 = (long long)batch * h * w * (c / 4);
+  const unsigned grid = static_cast<unsigned>((total4 + kLbThreads - 1) / kLbThreads);
+  latent_bwd_kernel<<<grid, kLbThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      mu_nchw, logstd_nchw, eps_nchw, d_mu_nchw, d_ls_nchw, static_cast<const __nv_bfloat16*>(dz_nhwc), c, h * w,
+      total4, static_cast<__nv_bfloat16*>(d_ml_nhwc));
+  return check_launch("latent_bwd");
+}
+
+extern "C" int vub_nchw_f32_to_nhwc_bf16_pad(const float* src, int32_t batch, int32_t c, int32_t h, int32_t w,
+                                             int32_t c_pad, void* dst, void* stream) {
+  clear_error();
+  if (!src || !dst) return fail(VUB_E_NULL, "nchw_to_nhwc_pad: NULL pointer");
+  if (batch <= 0 || c <= 0 || h <= 0 || w <= 0 || c > c_pad) return fail(VUB_E_SHAPE, "nchw_to_nhwc_pad: bad shape");
+  if (!aligned16(dst)) return fail(VUB_E_ALIGN, "nchw_to_nhwc_pad: dst not 16B aligned");
+  const long long hw = (long long)h * w, total = hw * batch;
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (c_pad == 32)
+    nchw_to_nhwc_pad_kernel<32><<<grid, 256, 0, s>>>(src, c, hw, total, static_cast<__nv_bfloat16*>(dst));
+  else if (c_pad == 16)
+    nchw_to_nhwc_pad_kernel<16><<<grid, 256, 0, s>>>(src, c, hw, total, static_cast<__nv_bfloat16*>(dst));
+  else
+    return fail(VUB_E_SHAPE, "nchw_to_nhwc_pad: c_pad %d not in {16,32}", c_pad);
+  return check_launch("nchw_to_nhwc_pad");
+}

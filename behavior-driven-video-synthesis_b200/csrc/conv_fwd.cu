@@ -394,7 +394,7 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
           job.ksteps[ks] = KStep{(uint8_t)mi, (int8_t)dh, (int8_t)dw, (uint8_t)cb, (uint16_t)ks, 0};
       }
     job.n_ksteps = ks;
-    TileEpi& e = job.epi;
+    TileEpi& e = job.epi[0];
     e.scale = d->scale;
     e.shift = d->shift;
     e.addend = static_cast<const __nv_bfloat16*>(d->residual);

@@ -34,7 +34,9 @@ struct TilesKParams {
   CUtensorMap tmA[4];
   CUtensorMap tmB;
   KStep ksteps[kTileMaxKSteps];
-  TileEpi ep;
+  TileEpi ep[2];
+  int n_split;      // N tiles [0, n_split) use ep[0], the rest ep[1]
+  int stage_tiles;  // staging tiles per epilogue warp: 2, or 3 when an addend2 is present
   int n_ksteps;
   int batch, hout, wout;
   int n_total;
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(kTilesThreads, 1)
   const int lane = threadIdx.x & 31;
   const int S = p.stages;
   const int KS = p.n_ksteps;
-  uint8_t* staging = smem + S * STAGE_BYTES;  // [8 epilogue warps][2][32][GW*2+16]
+  uint8_t* staging = smem + S * STAGE_BYTES;  // [8 epilogue warps][stage_tiles][32][GW*2+16]
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA[0]);
@@ -108,8 +110,8 @@ __global__ void __launch_bounds__(kTilesThreads, 1)
     tmem_relinquish();
   }
   for (int i = threadIdx.x; i < p.n_total; i += kTilesThreads) {
-    s_scale[i] = p.ep.scale != nullptr ? p.ep.scale[i] : 1.0f;
-    s_shift[i] = p.ep.shift != nullptr ? p.ep.shift[i] : 0.0f;
+    s_scale[i] = p.ep[0].scale != nullptr ? p.ep[0].scale[i] : 1.0f;
+    s_shift[i] = p.ep[0].shift != nullptr ? p.ep[0].shift[i] : 0.0f;
   }
   tc_fence_before();
   __syncthreads();
@@ -193,10 +195,9 @@ __global__ void __launch_bounds__(kTilesThreads, 1)
     const int dh = (m >> p.tw_log2) & (p.th - 1);
     const int dn = m >> (p.tw_log2 + p.th_log2);
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * BN;
-    const uint32_t t0 = smem_u32(staging) + (warp - 2) * EpiStage<GW>::WARP_BYTES;  // addend in / raw out
+    const uint32_t t0 = smem_u32(staging) + (warp - 2) * p.stage_tiles * EpiStage<GW>::TILE_BYTES;  // addend in / raw out
     const uint32_t t1 = t0 + EpiStage<GW>::TILE_BYTES;                              // mask in / elu out
-    const TileEpi& e = p.ep;
-    const bool f32_out = (e.flags & (VUB_CONV_F32_NHWC | VUB_CONV_F32_NCHW)) != 0;
+    const uint32_t t2 = t1 + EpiStage<GW>::TILE_BYTES;                              // addend2 in (stage_tiles == 3)
     constexpr int CPR = GW / 8;
     uint32_t cnt = 0;
     uint32_t lt = 0;
@@ -206,6 +207,10 @@ __global__ void __launch_bounds__(kTilesThreads, 1)
       tile_coords(tile, n_tile, n0, h0, w0);
       const int n = n0 + dn, oh = h0 + dh, ow = w0 + dw;
       const bool valid = n < p.batch;
+      const int ei = n_tile >= p.n_split ? 1 : 0;
+      const TileEpi& e = p.ep[ei];
+      const int ecol = (n_tile - (ei ? p.n_split : 0)) * BN;  // first column of this tile as the epilogue numbers it
+      const bool f32_out = (e.flags & (VUB_CONV_F32_NHWC | VUB_CONV_F32_NCHW)) != 0;
       // pixel of staged row `row` of this warp
       auto row_pixel = [&](int row, int& rn, int& roh, int& row_w) {
         const int mm = q * 32 + row;
@@ -245,10 +250,11 @@ __global__ void __launch_bounds__(kTilesThreads, 1)
       if constexpr (STAGED) {
 #pragma unroll 1
         for (int g0 = 0; g0 < BN; g0 += GW) {
-          const int col0 = n_tile * BN + g0;  // first GEMM column of this group
+          const int col0 = ecol + g0;  // first (epilogue-local) column of this group
           if (!f32_out) {
             if (e.addend != nullptr) stage_fill(t0, e.addend, col0);
             if (e.mask_elu != nullptr) stage_fill(t1, e.mask_elu, col0);
+            if (e.addend2 != nullptr) stage_fill(t2, e.addend2, col0);
             __syncwarp();
           }
 #pragma unroll 1
@@ -270,10 +276,10 @@ __global__ void __launch_bounds__(kTilesThreads, 1)
                 if (e.flags & VUB_CONV_F32_NCHW) {
 #pragma unroll
                   for (int i = 0; i < 32; ++i)
-                    if (n_tile * BN + c0 + i < e.n_valid)
-                      e.out_f32[tile_out_offset(e, n_tile * BN + c0 + i, n, oh, ow)] = y[i];
+                    if (ecol + c0 + i < e.n_valid)
+                      e.out_f32[tile_out_offset(e, ecol + c0 + i, n, oh, ow)] = y[i];
                 } else {
-                  float4* o = reinterpret_cast<float4*>(e.out_f32 + tile_out_offset(e, n_tile * BN + c0, n, oh, ow));
+                  float4* o = reinterpret_cast<float4*>(e.out_f32 + tile_out_offset(e, ecol + c0, n, oh, ow));
 #pragma unroll
                   for (int j = 0; j < 8; ++j) o[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
                 }
@@ -293,6 +299,10 @@ __global__ void __launch_bounds__(kTilesThreads, 1)
             if (e.addend != nullptr) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) add_bf16x8(lds128(t0 + my + 16 * j), &y[8 * j]);
+            }
+            if (e.addend2 != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) add_bf16x8(lds128(t2 + my + 16 * j), &y[8 * j]);
             }
             if (e.out_raw != nullptr) stage_put32<GW>(t0, lane, c0 - g0, y);
             if (e.out_elu != nullptr) {
@@ -319,8 +329,8 @@ __global__ void __launch_bounds__(kTilesThreads, 1)
         if (valid) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const int col = n_tile * BN + i;
-            const float y = fmaf(__uint_as_float(acc[i]), s_scale[col], s_shift[col]);
+            const int col = ecol + i;
+            const float y = fmaf(__uint_as_float(acc[i]), s_scale[n_tile * BN + i], s_shift[n_tile * BN + i]);
             if (e.flags & VUB_CONV_F32_NCHW) {
               if (col < e.n_valid) e.out_f32[tile_out_offset(e, col, n, oh, ow)] = y;
             } else if (e.flags & VUB_CONV_F32_NHWC) {
@@ -359,17 +369,27 @@ int conv_tiles_launch(const TileJob& job, cudaStream_t stream) {
   if (bkc != 32 && bkc != 64) return fail(VUB_E_SHAPE, "conv_tiles: bkc %d", bkc);
   const int n_total = job.n_total;
   if (n_total > kTilesMaxN) return fail(VUB_E_SHAPE, "conv_tiles: N %d > %d", n_total, kTilesMaxN);
-  int bn = n_total > 256 ? 256 : n_total;
+  int bn = job.bn > 0 ? job.bn : (n_total > 256 ? 256 : n_total);
   if (!(bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256) || n_total % bn)
-    return fail(VUB_E_SHAPE, "conv_tiles: N %d not tileable", n_total);
+    return fail(VUB_E_SHAPE, "conv_tiles: N %d not tileable by %d", n_total, bn);
+  if (job.n_split % bn) return fail(VUB_E_SHAPE, "conv_tiles: split %d not a multiple of the N tile %d", job.n_split, bn);
   if (job.n_ksteps <= 0 || job.n_ksteps > kTileMaxKSteps) return fail(VUB_E_SHAPE, "conv_tiles: %d k-steps", job.n_ksteps);
   if (!is_pow2(job.hout) || !is_pow2(job.wout)) return fail(VUB_E_SHAPE, "conv_tiles: tile grid %dx%d", job.hout, job.wout);
-  if (job.epi.mask_elu && job.epi.out_elu) return fail(VUB_E_FLAGS, "conv_tiles: mask and elu output share a staging tile");
+  const int n_epi = job.n_split > 0 && job.n_split < n_total ? 2 : 1;
+  bool any_addend2 = false;
+  for (int i = 0; i < n_epi; ++i) {
+    if (job.epi[i].mask_elu && job.epi[i].out_elu)
+      return fail(VUB_E_FLAGS, "conv_tiles: mask and elu output share a staging tile");
+    any_addend2 = any_addend2 || job.epi[i].addend2 != nullptr;
+  }
 
   TilesKParams kp;
   memset(&kp, 0, sizeof(kp));
   memcpy(kp.ksteps, job.ksteps, sizeof(KStep) * job.n_ksteps);
-  kp.ep = job.epi;
+  kp.ep[0] = job.epi[0];
+  kp.ep[1] = job.epi[n_epi - 1];
+  kp.n_split = n_epi == 2 ? job.n_split / bn : n_total / bn;
+  kp.stage_tiles = any_addend2 ? 3 : 2;
   kp.n_ksteps = job.n_ksteps;
   kp.batch = job.batch;
   kp.hout = job.hout;
@@ -387,7 +407,7 @@ int conv_tiles_launch(const TileJob& job, cudaStream_t stream) {
   kp.total_tiles = kp.tiles_w * kp.tiles_h * tiles_n * kp.n_ntiles;
 
   const int gw = bn >= 64 ? 64 : 32;
-  const size_t staging = bn >= 32 ? (size_t)8 * 2 * 32 * (gw * 2 + 16) : 0;
+  const size_t staging = bn >= 32 ? (size_t)8 * kp.stage_tiles * 32 * (gw * 2 + 16) : 0;
   const size_t stage_bytes = (size_t)(128 + bn) * bkc * 2;
   int stages = static_cast<int>((212 * 1024 - staging) / stage_bytes);
   if (stages > kTilesMaxStages) stages = kTilesMaxStages;

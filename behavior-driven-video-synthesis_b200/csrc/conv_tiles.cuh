@@ -34,6 +34,7 @@ struct TileEpi {
   const float* scale;            // per GEMM column, or nullptr (identity)
   const float* shift;            // per GEMM column, or nullptr (zero)
   const __nv_bfloat16* addend;   // added after scale/shift; same addressing as the bf16 outputs; or nullptr
+  const __nv_bfloat16* addend2;  // second addend (dgrad: residual identity path + earlier skip contributions)
   const __nv_bfloat16* mask_elu; // dgrad: y *= ELU'(x) reconstructed from the stored ELU(x): e > 0 ? 1 : e + 1
   __nv_bfloat16* out_raw;
   __nv_bfloat16* out_elu;
@@ -53,10 +54,14 @@ struct TileJob {
   const void* w;         // packed weights [n_total rows][ktot] bf16, K-major
   long long ktot;        // row pitch of w in elements
   int n_total;           // GEMM N (rows of w used); multiple of the N tile
+  int bn;                // N tile override (0 = min(n_total, 256))
+  int n_split;           // GEMM columns [0, n_split) use epi[0], the rest epi[1] with columns renumbered from 0
+                         // (0 = no split; must be a multiple of the N tile).  scale/shift always come from epi[0]
+                         // and are indexed by the global GEMM column.
   int batch, hout, wout; // tile grid: output pixels enumerated (n, oh, ow) over hout x wout
   KStep ksteps[kTileMaxKSteps];
   int n_ksteps;
-  TileEpi epi;
+  TileEpi epi[2];
 };
 
 int conv_tiles_launch(const TileJob& job, cudaStream_t stream);

@@ -1,0 +1,419 @@
+// Weight correlation of the weight-normalised convs (vub_conv_wgrad) on tcgen05 (sm_100a).
+//
+//   gt[(src, tap, ci)][co] += sum_pix dy[pix, co] * x_src[pix + off(tap), ci]        (fp32)
+//   dy_sum[co]             += sum_pix dy[pix, co]
+//
+// The contraction index is the PIXEL, the slow index of both NHWC operands, so both UMMA operands are
+// MN-major: a TMA box [channels, pixels] written with 128B/64B swizzle IS the canonical MN-major
+// operand layout (LBO = stride between 64-/32-channel boxes, SBO = 8 pixel rows; measured:
+// profiles/r01_exp_mnmajor.log).  One k-step = 64 pixels:
+//   A = dy box(es)  [128 output channels x 64 pixels]   (M = 128; layers with fewer output channels
+//                                                         replicate their box with a block stride of 0)
+//   B = x boxes shifted by each tap of the CTA's tap group, every box = one block of D columns
+//   D[co, (tap, ci)] (TMEM, fp32) accumulates over ALL pixel tiles the CTA owns; an extra N = 16 block of
+//   constant ones yields dy_sum from the same A operand.
+// Work split: grid = (tap group) x (128-channel M tile) x (pixel range); every CTA adds its partial
+// correlation to gt with coalesced red.global.add.f32 (lane = output channel).
+// Upsample convs read dy through the four parity maps of the shuffled gradient; Downsample convs read x
+// through its four parity maps (same tap -> map/shift table as the forward kernel).
+//
+// Replaces autograd's convolution_backward (weight gradient) of lib/modules.py:143.
+#include <cuda_bf16.h>
+
+#include <cstring>
+#include <mutex>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vub {
+
+constexpr int kWgThreads = 192;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kWgKP = 64;         // pixels per k-step
+constexpr int kWgMaxStages = 6;
+constexpr int kWgMaxGroups = 6;
+constexpr int kWgMaxBoxes = 9;    // B boxes per tap group
+constexpr int kWgOnesBytes = 2048;
+
+struct WgBBox {
+  int16_t map;       // B tensor map (source or parity view)
+  int8_t dh, dw;     // pixel shift relative to the dy tile
+  int16_t chan;      // first channel of the box
+  int32_t gt_row;    // gt row of the box's first column
+};
+struct WgABox {
+  int16_t map;
+  int16_t chan;
+};
+
+struct WgKParams {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB[4];
+  WgABox abox[4 * 4];                          // [m_tile][box]
+  WgBBox bbox[kWgMaxGroups][kWgMaxBoxes];
+  int nb[kWgMaxGroups];                        // boxes per group
+  float* gt;
+  float* dy_sum;
+  int gt_pitch;
+  int ca, na;            // channels per A box, boxes per M tile (na * ca <= 128)
+  int m_rows;            // valid rows of an M tile (min(cout_k, 128))
+  int cb;                // channels per B box
+  int n_groups, n_mtiles, n_split;
+  int tw, th, tn;        // pixel tile (tw * th * tn = 64)
+  int tiles_w, tiles_h;
+  int total_tiles;
+  int stages;
+};
+
+// Shared-memory descriptor of an MN-major operand made of TMA boxes [channels x pixels] (swizzle = row
+// bytes): LBO = byte stride between consecutive channel blocks (boxes), SBO = 8 pixel rows.
+__device__ __forceinline__ uint32_t umma_desc_hi_mn(uint32_t row_bytes) {
+  const uint32_t layout = (row_bytes == 128) ? 2u : 4u;
+  return ((8u * row_bytes) >> 4) | (1u << 14) | (layout << 29);
+}
+__device__ __forceinline__ uint32_t umma_desc_lo_mn(uint32_t smem_addr, uint32_t block_stride) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | ((block_stride >> 4) << 16);
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_constant__ WgKParams p) {
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  __shared__ uint64_t full_bar[kWgMaxStages];
+  __shared__ uint64_t empty_bar[kWgMaxStages];
+  __shared__ uint64_t acc_full;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = p.stages;
+
+  // work assignment: blockIdx.x = (split * n_mtiles + mt) * n_groups + grp
+  int bid = blockIdx.x;
+  const int grp = bid % p.n_groups;
+  bid /= p.n_groups;
+  const int mt = bid % p.n_mtiles;
+  const int split = bid / p.n_mtiles;
+  const int t_begin = static_cast<int>((long long)p.total_tiles * split / p.n_split);
+  const int t_end = static_cast<int>((long long)p.total_tiles * (split + 1) / p.n_split);
+  const int nb = p.nb[grp];
+  const bool with_sum = grp == 0;
+
+  const int a_rowb = p.ca * 2, b_rowb = p.cb * 2;
+  const int a_box = kWgKP * a_rowb, b_box = kWgKP * b_rowb;
+  const int a_bytes = p.na * a_box;
+  const int stage_bytes = a_bytes + kWgMaxBoxes * 0 + nb * b_box;  // boxes are packed per group
+  const int stage_pitch = (stage_bytes + 1023) & ~1023;
+  uint8_t* ones = smem;                 // 2 KB of bf16 1.0
+  uint8_t* ring = smem + kWgOnesBytes;  // [S][stage_pitch]
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&p.tmB[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(&acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<512>(&tmem_base_slot);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < kWgOnesBytes / 4; i += kWgThreads)
+    reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;  // two bf16 1.0
+  // make the generic-proxy writes of `ones` visible to the tensor-core (async) proxy
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  const int n_cols = nb * p.cb;  // D columns of this CTA (the ones block follows at column n_cols)
+
+  auto tile_origin = [&](int tile, int& n0, int& h0, int& w0) {
+    const int twi = tile % p.tiles_w;
+    int t = tile / p.tiles_w;
+    const int thi = t % p.tiles_h;
+    const int tni = t / p.tiles_h;
+    w0 = twi * p.tw;
+    h0 = thi * p.th;
+    n0 = tni * p.tn;
+  };
+
+  if (t_begin < t_end) {
+    if (warp == 0) {
+      // ------------------------------ TMA producer ------------------------------
+      int st = 0;
+      uint32_t ph = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        int n0, h0, w0;
+        tile_origin(tile, n0, h0, w0);
+        mbar_wait(&empty_bar[st], ph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&full_bar[st], stage_bytes);
+          uint8_t* dst = ring + st * stage_pitch;
+          for (int i = 0; i < p.na; ++i) {
+            const WgABox ab = p.abox[mt * 4 + i];
+            tma_load_4d(dst + i * a_box, &p.tmA[ab.map], &full_bar[st], ab.chan, w0, h0, n0);
+          }
+          for (int j = 0; j < nb; ++j) {
+            const WgBBox bb = p.bbox[grp][j];
+            tma_load_4d(dst + a_bytes + j * b_box, &p.tmB[bb.map], &full_bar[st], bb.chan, w0 + bb.dw, h0 + bb.dh, n0);
+          }
+        }
+        __syncwarp();
+        if (++st == S) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+    } else if (warp == 1) {
+      // ------------------------------ MMA issuer --------------------------------
+      const uint32_t a_hi = umma_desc_hi_mn(a_rowb), b_hi = umma_desc_hi_mn(b_rowb);
+      const uint32_t a_blk = p.na * p.ca >= 128 ? a_box : 0;  // fewer than 128 channels: replicate the box(es)
+      const uint32_t ones_lo = umma_desc_lo_mn(smem_u32(ones), 0);
+      const uint32_t ones_hi = umma_desc_hi_mn(128);
+      constexpr uint32_t kMajorMN = (1u << 15) | (1u << 16);
+      const uint32_t idesc_ones = umma_idesc_bf16(128, 16) | kMajorMN;
+      int st = 0;
+      uint32_t ph = 0;
+      bool first = true;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        mbar_wait(&full_bar[st], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(ring + st * stage_pitch);
+        const uint32_t b_addr = a_addr + a_bytes;
+        if (elect_one()) {
+#pragma unroll 1
+          for (int j = 0; j < kWgKP / 16; ++j) {
+            const uint64_t da = umma_desc_join(a_hi, umma_desc_lo_mn(a_addr + j * 16 * a_rowb, a_blk));
+            const uint32_t acc = (first && j == 0) ? 0u : 1u;
+            // column chunks of at most 256 D columns (whole boxes)
+            int box0 = 0;
+            while (box0 < nb) {
+              int nbox = nb - box0;
+              const int max_box = 256 / p.cb;
+              if (nbox > max_box) nbox = max_box;
+              const uint64_t db =
+                  umma_desc_join(b_hi, umma_desc_lo_mn(b_addr + box0 * b_box + j * 16 * b_rowb, b_box));
+              umma_bf16(tmem_base + box0 * p.cb, da, db, umma_idesc_bf16(128, nbox * p.cb) | kMajorMN, acc);
+              box0 += nbox;
+            }
+            if (with_sum) umma_bf16(tmem_base + n_cols, da, umma_desc_join(ones_hi, ones_lo), idesc_ones, acc);
+          }
+          umma_commit(&empty_bar[st]);
+          if (tile == t_end - 1) umma_commit(&acc_full);
+        }
+        __syncwarp();
+        first = false;
+        if (++st == S) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+    } else {
+      // ------------------------------ epilogue: TMEM -> red.global.add ------------------------------
+      const int q = warp & 3;
+      const int row = q * 32 + lane;  // D row = output channel within the M tile
+      mbar_wait(&acc_full, 0);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+      const bool row_ok = row < p.m_rows;
+      const int co = mt * 128 + row;
+      for (int j = 0; j < nb; ++j) {
+        const int gt_row = p.bbox[grp][j].gt_row;
+        for (int c0 = 0; c0 < p.cb; c0 += 32) {
+          uint32_t acc[32];
+          tmem_ld32(trow + j * p.cb + c0, acc);
+          tmem_ld_wait();
+          if (row_ok) {
+            float* dst = p.gt + (size_t)(gt_row + c0) * p.gt_pitch + co;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) atomicAdd(dst + (size_t)i * p.gt_pitch, __uint_as_float(acc[i]));
+          }
+        }
+      }
+      if (with_sum) {
+        uint32_t acc[16];
+        tmem_ld16(trow + n_cols, acc);
+        tmem_ld_wait();
+        if (row_ok) atomicAdd(p.dy_sum + co, __uint_as_float(acc[0]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace vub
+
+using namespace vub;
+
+extern "C" int vub_conv_wgrad(const vub_wgrad_desc* d, void* stream_v) {
+  clear_error();
+  if (!d) return fail(VUB_E_NULL, "conv_wgrad: desc is NULL");
+  if (!d->dy || !d->x[0] || !d->gt || !d->dy_sum) return fail(VUB_E_NULL, "conv_wgrad: dy/x/gt/dy_sum NULL");
+  if (d->nsrc != 1 && d->nsrc != 2) return fail(VUB_E_SHAPE, "conv_wgrad: nsrc must be 1 or 2");
+  if (d->nsrc == 2 && !d->x[1]) return fail(VUB_E_NULL, "conv_wgrad: x[1] NULL with nsrc == 2");
+  const int C = d->c_src;
+  if (C != 32 && C != 64 && C != 128) return fail(VUB_E_SHAPE, "conv_wgrad: c_src %d not in {32,64,128}", C);
+  if (d->ksize != 1 && d->ksize != 3) return fail(VUB_E_SHAPE, "conv_wgrad: ksize must be 1 or 3");
+  if (d->stride != 1 && d->stride != 2) return fail(VUB_E_SHAPE, "conv_wgrad: stride must be 1 or 2");
+  const bool d2s = (d->flags & VUB_CONV_D2S) != 0;
+  if (d->stride == 2 && (d->ksize != 3 || d->nsrc != 1 || d2s))
+    return fail(VUB_E_SHAPE, "conv_wgrad: stride 2 needs ksize 3, one source, no D2S");
+  if (d->batch <= 0 || !is_pow2(d->hin) || !is_pow2(d->win) || d->hin < d->stride || d->win < d->stride)
+    return fail(VUB_E_SHAPE, "conv_wgrad: batch %d hin %d win %d", d->batch, d->hin, d->win);
+  const int cout_k = d->cout_k;
+  if (cout_k < 32 || cout_k > 512 || cout_k % 32 || (cout_k > 32 && cout_k % 64) || (cout_k > 64 && cout_k % 128))
+    return fail(VUB_E_SHAPE, "conv_wgrad: cout_k %d", cout_k);
+  if (d->gt_pitch < cout_k) return fail(VUB_E_SHAPE, "conv_wgrad: gt_pitch %d < cout_k %d", d->gt_pitch, cout_k);
+  const int cmap = d2s ? cout_k / 4 : cout_k;
+  if (cmap % 32) return fail(VUB_E_SHAPE, "conv_wgrad: %d channels per dy map", cmap);
+  const void* ptrs[] = {d->dy, d->x[0], d->x[1]};
+  for (const void* q : ptrs)
+    if (q && !aligned16(q)) return fail(VUB_E_ALIGN, "conv_wgrad: pointer %p not 16B aligned", q);
+
+  const int taps = d->ksize * d->ksize;
+  const int ho = d->hin / d->stride, wo = d->win / d->stride;  // dy grid == tile grid (conv output pixels)
+
+  WgKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.gt = d->gt;
+  kp.dy_sum = d->dy_sum;
+  kp.gt_pitch = d->gt_pitch;
+  // ---- A side: dy ----
+  kp.ca = cmap >= 64 ? 64 : 32;
+  const int m_rows = cout_k < 128 ? cout_k : 128;
+  kp.m_rows = m_rows;
+  kp.na = m_rows / kp.ca;
+  kp.n_mtiles = (cout_k + 127) / 128;
+  for (int mt = 0; mt < kp.n_mtiles; ++mt)
+    for (int i = 0; i < kp.na; ++i) {
+      const int co0 = mt * 128 + i * kp.ca;
+      kp.abox[mt * 4 + i] = WgABox{(int16_t)(d2s ? co0 / cmap : 0), (int16_t)(d2s ? co0 % cmap : co0)};
+    }
+  // ---- B side: x, grouped by (source, tap row) or (source) ----
+  kp.cb = C >= 64 ? 64 : 32;
+  const int cblocks = C / kp.cb;
+  const bool merge_rows = taps == 9 && 9 * C <= 448;  // all 9 taps of a source fit one CTA's TMEM
+  int g = 0;
+  for (int s = 0; s < d->nsrc; ++s) {
+    const int n_rowgroups = (taps == 9 && !merge_rows) ? 3 : 1;
+    for (int rg = 0; rg < n_rowgroups; ++rg, ++g) {
+      if (g >= kWgMaxGroups) return fail(VUB_E_SHAPE, "conv_wgrad: too many tap groups");
+      int j = 0;
+      for (int tap = 0; tap < taps; ++tap) {
+        const int r = tap / d->ksize, q = tap % d->ksize;
+        if (n_rowgroups == 3 && r != rg) continue;
+        int dh = 0, dw = 0, mi = s;
+        if (taps == 9) {
+          if (d->stride == 1) {
+            dh = r - 1;
+            dw = q - 1;
+          } else {  // input pixel 2*o + r - 1: parity map (r != 1, q != 1), coordinate o - (r == 0)
+            mi = ((r != 1) ? 2 : 0) + ((q != 1) ? 1 : 0);
+            dh = (r == 0) ? -1 : 0;
+            dw = (q == 0) ? -1 : 0;
+          }
+        }
+        for (int cbk = 0; cbk < cblocks; ++cbk, ++j) {
+          if (j >= kWgMaxBoxes) return fail(VUB_E_SHAPE, "conv_wgrad: too many boxes in a tap group");
+          kp.bbox[g][j] = WgBBox{(int16_t)mi, (int8_t)dh, (int8_t)dw, (int16_t)(cbk * kp.cb),
+                                 (s * taps + tap) * C + cbk * kp.cb};
+        }
+      }
+      kp.nb[g] = j;
+    }
+  }
+  kp.n_groups = g;
+  int max_nb = 0;
+  for (int i = 0; i < g; ++i) max_nb = kp.nb[i] > max_nb ? kp.nb[i] : max_nb;
+  if (max_nb * kp.cb + 16 > 512) return fail(VUB_E_SHAPE, "conv_wgrad: %d accumulator columns", max_nb * kp.cb);
+
+  // ---- pixel tiles of 64 ----
+  kp.tw = wo < kWgKP ? wo : kWgKP;
+  kp.th = ho < kWgKP / kp.tw ? ho : kWgKP / kp.tw;
+  kp.tn = kWgKP / (kp.tw * kp.th);
+  kp.tiles_w = wo / kp.tw;
+  kp.tiles_h = ho / kp.th;
+  const int tiles_n = (d->batch + kp.tn - 1) / kp.tn;
+  kp.total_tiles = kp.tiles_w * kp.tiles_h * tiles_n;
+
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  int n_split = n_sm / (kp.n_groups * kp.n_mtiles);
+  if (n_split < 1) n_split = 1;
+  if (n_split > kp.total_tiles) n_split = kp.total_tiles;
+  kp.n_split = n_split;
+
+  const size_t stage_bytes = (size_t)kp.na * kWgKP * kp.ca * 2 + (size_t)max_nb * kWgKP * kp.cb * 2;
+  const size_t stage_pitch = (stage_bytes + 1023) & ~(size_t)1023;
+  int stages = static_cast<int>((200 * 1024 - kWgOnesBytes) / stage_pitch);
+  if (stages > kWgMaxStages) stages = kWgMaxStages;
+  if (stages < 2) return fail(VUB_E_SHAPE, "conv_wgrad: pipeline does not fit");
+  kp.stages = stages;
+  const size_t smem = kWgOnesBytes + stages * stage_pitch + 1024;
+
+  // ---- tensor maps ----
+  int rc;
+  {
+    const uint32_t boxA[4] = {(uint32_t)kp.ca, (uint32_t)kp.tw, (uint32_t)kp.th, (uint32_t)kp.tn};
+    if (!d2s) {
+      const uint64_t dims[4] = {(uint64_t)cout_k, (uint64_t)wo, (uint64_t)ho, (uint64_t)d->batch};
+      const uint64_t str[3] = {(uint64_t)cout_k * 2, (uint64_t)wo * cout_k * 2, (uint64_t)ho * wo * cout_k * 2};
+      rc = encode_tmap_bf16(&kp.tmA[0], d->dy, 4, dims, str, boxA, kp.ca * 2, false);
+      if (rc) return rc;
+    } else {
+      const uint64_t W = wo, H = ho;
+      const uint64_t dims[4] = {(uint64_t)cmap, W, H, (uint64_t)d->batch};
+      const uint64_t str[3] = {2ull * cmap * 2, 4ull * W * cmap * 2, 4ull * H * W * cmap * 2};
+      for (int b1 = 0; b1 < 2; ++b1)
+        for (int b2 = 0; b2 < 2; ++b2) {
+          const char* base = static_cast<const char*>(d->dy) + ((uint64_t)b1 * 2 * W + b2) * cmap * 2;
+          rc = encode_tmap_bf16(&kp.tmA[b1 * 2 + b2], base, 4, dims, str, boxA, kp.ca * 2, false);
+          if (rc) return rc;
+        }
+    }
+    const uint32_t boxB[4] = {(uint32_t)kp.cb, (uint32_t)kp.tw, (uint32_t)kp.th, (uint32_t)kp.tn};
+    const uint64_t Cc = C, Hin = d->hin, Win = d->win;
+    if (d->stride == 1) {
+      const uint64_t dims[4] = {Cc, Win, Hin, (uint64_t)d->batch};
+      const uint64_t str[3] = {Cc * 2, Win * Cc * 2, Hin * Win * Cc * 2};
+      for (int s = 0; s < d->nsrc; ++s) {
+        rc = encode_tmap_bf16(&kp.tmB[s], d->x[s], 4, dims, str, boxB, kp.cb * 2, false);
+        if (rc) return rc;
+      }
+    } else {
+      const uint64_t dims[4] = {Cc, Win / 2, Hin / 2, (uint64_t)d->batch};
+      const uint64_t str[3] = {2 * Cc * 2, 2 * Win * Cc * 2, Hin * Win * Cc * 2};
+      for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw) {
+          const char* base = static_cast<const char*>(d->x[0]) + ((uint64_t)ph * Win + pw) * Cc * 2;
+          rc = encode_tmap_bf16(&kp.tmB[ph * 2 + pw], base, 4, dims, str, boxB, kp.cb * 2, false);
+          if (rc) return rc;
+        }
+    }
+  }
+
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+  });
+  if (attr_err != cudaSuccess)
+    return fail(static_cast<int>(attr_err), "cudaFuncSetAttribute(conv_wgrad): %s", cudaGetErrorString(attr_err));
+  const int grid = kp.n_groups * kp.n_mtiles * kp.n_split;
+  conv_wgrad_kernel<<<grid, kWgThreads, smem, static_cast<cudaStream_t>(stream_v)>>>(kp);
+  return check_launch("conv_wgrad");
+}

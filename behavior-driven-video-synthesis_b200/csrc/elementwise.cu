@@ -71,6 +71,17 @@ __global__ void __launch_bounds__(kWnThreads)
     const int cs = ci - src * e.c_src;
     out[(src * e.ktaps + tap) * e.c_src + cs] = __float2bfloat16_rn(v[i] * inv);
   }
+  if (e.wd != nullptr) {
+    // data-gradient weights: row = input channel (source-major), column = (tap, output channel), scaled
+    const float sc = e.gamma[co] * e.g[co] * inv;
+    __nv_bfloat16* wd = static_cast<__nv_bfloat16*>(e.wd);
+    const size_t pitch = (size_t)e.ktaps * e.wd_cout;
+    for (int i = threadIdx.x; i < len; i += kWnThreads) {
+      const int ci = i / e.ktaps;
+      const int tap = i - ci * e.ktaps;
+      wd[(size_t)ci * pitch + (size_t)tap * e.wd_cout + e.wd_col0 + co] = __float2bfloat16_rn(v[i] * sc);
+    }
+  }
   if (threadIdx.x == 0) {
     const float ga = e.gamma[co];
     e.scale[co] = ga * e.g[co];

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VUB_ABI_VERSION 1
+#define VUB_ABI_VERSION 2
 
 #define VUB_OK 0
 #define VUB_E_NULL (-1)        /* required pointer is NULL */
@@ -98,6 +98,11 @@ typedef struct vub_wn_entry {
   int32_t cout, cin, ktaps, c_src; /* cin = nsrc * c_src; ktaps = k*k */
   int32_t ktot;        /* row pitch of the packed matrix in elements (= cin*ktaps) */
   int32_t row_start;
+  /* data-gradient weights (training): wd[(src*c_src + c)][tap*wd_cout + wd_col0 + co] =
+   * bf16(scale[co] * v_hat[co, src, tap, c]) — the matrix vub_conv_dgrad contracts dy with.  NULL = skip. */
+  void* wd;
+  int32_t wd_cout;     /* K extent per tap of wd (output channels of the whole slot, padded to 32) */
+  int32_t wd_col0;     /* first column of this conv inside a tap block (merged convs) */
 } vub_wn_entry;
 
 int vub_wn_prep(const vub_wn_entry* table_dev, int32_t n_entries, int32_t total_rows, void* stream);
@@ -136,6 +141,115 @@ int vub_nchw_f32_to_nhwc_bf16(const float* src, int32_t batch, int32_t c, int32_
                               void* dst_raw, void* dst_elu, void* stream);
 int vub_nhwc_bf16_to_nchw_f32(const void* src, int32_t batch, int32_t c, int32_t h, int32_t w,
                               float* dst, void* stream);
+
+/* Same converter with the channel axis zero-padded to c_pad (multiple of 8) — the image gradient
+ * d(loss)/d(imgs) [batch, 3, h, w] entering the backward pass of dd.out_conv (models/vunets.py:411). */
+int vub_nchw_f32_to_nhwc_bf16_pad(const float* src, int32_t batch, int32_t c, int32_t h, int32_t w,
+                                  int32_t c_pad, void* dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Training half of the path.  The reference gets these from autograd (convolution_backward, ELU /
+ * add / cat / sigmoid / exp backward kernels, aten::_weight_norm_interface_backward); here each conv
+ * needs exactly two tensor-core launches (data gradient, weight correlation) plus one reduction
+ * launch per step for every layer's weight-norm / affine parameter gradients.
+ * ---------------------------------------------------------------------------------------------- */
+
+/*
+ * Data gradient of a NormConv2d (autograd of lib/modules.py:143-144 w.r.t. x) with the backward of the
+ * surrounding VunetRNB elementwise ops fused into the epilogue:
+ *     dx_s = ELU'(x_s) * conv_transpose(dy, scale * v_hat)_s  + addend_s + addend2_s
+ * ELU' is rebuilt from the stored ELU(x_s) copy (e > 0 ? 1 : e + 1; mask_elu[s] NULL = the conv read
+ * the raw tensor); addend / addend2 carry gradient contributions of other consumers (the residual
+ * identity path, skip connections) and may alias dx_s (in-place accumulation).
+ * dy: NHWC bf16 [batch, hout, wout, cout_k]; with VUB_CONV_D2S the gradient of the SHUFFLED tensor
+ * [batch, 2*hin, 2*win, cout_k/4].  stride 2 (Downsample) is computed per input-pixel parity class.
+ */
+typedef struct vub_dgrad_desc {
+  const void* dy;
+  const void* wd;            /* [nsrc*c_src, ksize*ksize*cout_k] bf16 (vub_wn_entry.wd) */
+  void* dx[2];               /* NHWC bf16 [batch, hin, win, c_src] per source */
+  const void* mask_elu[2];
+  const void* addend[2];
+  const void* addend2[2];
+  int32_t nsrc, c_src;
+  int32_t batch, hin, win;   /* extents of the conv INPUT */
+  int32_t cout_k;            /* K extent per tap = output channels padded to a multiple of 32 */
+  int32_t ksize, stride;
+  uint32_t flags;            /* VUB_CONV_D2S */
+} vub_dgrad_desc;
+
+int vub_conv_dgrad(const vub_dgrad_desc* d, void* stream);
+
+/*
+ * Weight correlation of a NormConv2d (the raw part of convolution_backward w.r.t. the weight):
+ *     gt[(src, tap, c)][co] += sum_pixels dy[pix, co] * x_src[pix + tap offset, c]
+ *     dy_sum[co]            += sum_pixels dy[pix, co]
+ * on tcgen05 with both operands MN-major (pixels are the contraction index).  fp32, ACCUMULATED with
+ * red.global.add (the caller zeroes gt / dy_sum once per step); split over pixel ranges across CTAs.
+ * x[s] is the tensor the forward conv read (the ELU'd copy inside a VunetRNB).
+ */
+typedef struct vub_wgrad_desc {
+  const void* dy;            /* as in vub_dgrad_desc */
+  const void* x[2];          /* NHWC bf16 [batch, hin, win, c_src] */
+  float* gt;                 /* [nsrc*ksize*ksize*c_src][gt_pitch] */
+  float* dy_sum;             /* [gt_pitch] */
+  int32_t nsrc, c_src;
+  int32_t batch, hin, win;
+  int32_t cout_k;            /* channels of dy (multiple of 32; out_conv: 32 with 3 valid) */
+  int32_t gt_pitch;          /* >= cout_k */
+  int32_t ksize, stride;
+  uint32_t flags;            /* VUB_CONV_D2S */
+} vub_wgrad_desc;
+
+int vub_conv_wgrad(const vub_wgrad_desc* d, void* stream);
+
+/*
+ * Parameter gradients of every NormConv2d from its weight correlation, one launch for all layers
+ * (replaces aten::_weight_norm_interface_backward + the mul/add backward of lib/modules.py:144).
+ * With u = conv(x, v_hat), out = s*u + t, s = gamma*g, t = gamma*bias + beta, G = gt[:, co], S = dy_sum[co]:
+ *     d_beta = S, d_bias = gamma*S, d_g = gamma*(v_hat.G), d_gamma = g*(v_hat.G) + bias*S,
+ *     d_v = (gamma*g/||v||) * (G - v_hat*(v_hat.G))
+ * accumulate != 0 adds to the gradient buffers instead of overwriting them.
+ */
+typedef struct vub_wnb_entry {
+  const float* v;
+  const float* g;
+  const float* gamma;
+  const float* bias;
+  const float* gt;           /* this conv's correlation: element (k, co) at gt[k*gt_pitch + gt_col0 + co] */
+  const float* dy_sum;       /* element co at dy_sum[gt_col0 + co] */
+  float* d_v;
+  float* d_g;
+  float* d_gamma;
+  float* d_beta;
+  float* d_bias;
+  int32_t cout, cin, ktaps, c_src;
+  int32_t gt_pitch, gt_col0;
+  int32_t row_start;
+  int32_t pad;
+} vub_wnb_entry;
+
+int vub_wn_bwd(const vub_wnb_entry* table_dev, int32_t n_entries, int32_t total_rows, int32_t accumulate,
+               void* stream);
+
+/*
+ * Backward of the stem (first 1x1 NormConv2d on the NCHW fp32 input, vub_stem_fwd): correlation of the
+ * output gradient with the input, gt[ci][co] += sum dy[pix, co]*x[pix, ci], dy_sum[co] += sum dy.
+ * The stem needs no data gradient (its input is the image).  gt pitch = cout.
+ */
+int vub_stem_bwd(const float* x_nchw, const void* dy_nhwc, int32_t batch, int32_t cx, int32_t h, int32_t w,
+                 int32_t cout, float* gt, float* dy_sum, void* stream);
+
+/*
+ * Backward of the latent head (vub_latent_fwd): z = mu + exp(ls)*eps, ls = sigmoid(logit).
+ *   d_mu_tot = d_mu + dz,  d_ls_tot = d_ls + dz*eps*exp(ls),  d_logit = d_ls_tot*ls*(1-ls)
+ * d_mu / d_ls: NCHW fp32 gradients w.r.t. the returned means / logstds (NULL = zero); dz: NHWC bf16
+ * gradient w.r.t. z from the decoder (NULL = zero).  Writes d_ml NHWC bf16 [batch, h, w, 2c], the
+ * gradient of the fused (mu || logit) conv output.
+ */
+int vub_latent_bwd(const float* mu_nchw, const float* logstd_nchw, const float* eps_nchw, const float* d_mu_nchw,
+                   const float* d_ls_nchw, const void* dz_nhwc, int32_t batch, int32_t c, int32_t h, int32_t w,
+                   void* d_ml_nhwc, void* stream);
 
 #ifdef __cplusplus
 }

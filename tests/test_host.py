@@ -115,7 +115,7 @@ def test_library_loads_and_exports_every_symbol():
     lib = ctypes.CDLL(_native.LIB_PATH)
     for sym in header_symbols():
         assert hasattr(lib, sym), sym
-    assert _native.lib().vub_abi_version() == 1
+    assert _native.lib().vub_abi_version() == _native.ABI_VERSION
     # struct mirrors must match the C layout (pointers first, then int32 fields)
     assert ctypes.sizeof(_native.ConvDesc) == 9 * 8 + 11 * 4 + 4  # padded to 8
     assert ctypes.sizeof(_native.WnEntry) == 8 * 8 + 6 * 4
