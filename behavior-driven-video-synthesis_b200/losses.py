@@ -14,7 +14,8 @@ import torch
 
 def kl_loss(mu: torch.Tensor, logstd: torch.Tensor) -> torch.Tensor:
     part = getattr(mu, "_vub_kl_partial", None)
-    if part is not None and getattr(mu, "_vub_logstd", None) is logstd:
+    differentiable = torch.is_grad_enabled() and (mu.requires_grad or logstd.requires_grad)
+    if part is not None and getattr(mu, "_vub_logstd", None) is logstd and not differentiable:
         b = mu.shape[0]
         dim = mu.numel() // b
         return part.sum() / b - 0.5 * dim

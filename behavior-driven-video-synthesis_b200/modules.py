@@ -26,11 +26,19 @@ _SUPPORTED_C = (32, 64, 128)
 class Act:
     """One activation of the path, NHWC bf16: ``raw`` = as produced, ``elu`` = ELU(raw)."""
 
-    __slots__ = ("raw", "elu")
+    __slots__ = ("raw", "elu", "grad")
 
     def __init__(self, raw: Optional[torch.Tensor], elu: Optional[torch.Tensor]):
         self.raw = raw
         self.elu = elu
+        self.grad = None  # training: NHWC bf16 gradient w.r.t. the raw value, accumulated by the backward schedule
+
+    def pick(self, mode: str) -> torch.Tensor:
+        """The copy a consumer reads: ``"raw"`` or ``"elu"``."""
+        t = self.raw if mode == "raw" else self.elu
+        if t is None:
+            raise RuntimeError(f"activation has no {mode} copy")
+        return t
 
     @property
     def any(self) -> torch.Tensor:
@@ -67,12 +75,15 @@ def to_act(t: Union[torch.Tensor, Act], need_raw: bool = True, need_elu: bool = 
 class ConvWeights:
     """Packed bf16 ``v/||v||`` [cout_pad, K] + fp32 scale/shift of one (possibly merged) conv."""
 
-    __slots__ = ("w", "scale", "shift", "cout", "cout_pad", "nsrc", "c_src", "ksize", "stride")
+    __slots__ = ("w", "scale", "shift", "cout", "cout_pad", "nsrc", "c_src", "ksize", "stride", "wd", "cout_k",
+                 "slot")
 
-    def __init__(self, w, scale, shift, cout, cout_pad, nsrc, c_src, ksize, stride):
+    def __init__(self, w, scale, shift, cout, cout_pad, nsrc, c_src, ksize, stride, wd=None, cout_k=0, slot=-1):
         self.w, self.scale, self.shift = w, scale, shift
         self.cout, self.cout_pad = cout, cout_pad
         self.nsrc, self.c_src, self.ksize, self.stride = nsrc, c_src, ksize, stride
+        # training: data-gradient weights [nsrc*c_src, k*k*cout_k] (bf16, pre-scaled), cout_k = cout padded to 32
+        self.wd, self.cout_k, self.slot = wd, cout_k, slot
 
 
 def _pad_cout(c: int) -> int:
@@ -94,6 +105,8 @@ class WeightBank:
         self._key = None
         self._device = None
         self._views = {}
+        self._with_wd = False
+        self.tape = None  # training: list the forward pass appends its records to (training.Tape)
 
     @staticmethod
     def for_module(root: nn.Module) -> "WeightBank":
@@ -112,8 +125,8 @@ class WeightBank:
         return WeightBank(slots)
 
     # -- allocation -------------------------------------------------------------------------------
-    def _allocate(self, device: torch.device) -> None:
-        w_off, s_off, rows = 0, 0, 0
+    def _allocate(self, device: torch.device, with_wd: bool) -> None:
+        w_off, s_off, rows, wd_off = 0, 0, 0, 0
         layout = []
         for slot in self.slots:
             first = slot[0]
@@ -129,21 +142,27 @@ class WeightBank:
                     f"no tensor-core kernel for {first.in_channels} input channels split {nsrc} ways "
                     f"(supported per-source channel counts: {_SUPPORTED_C})")
             cpad = _pad_cout(cout)
-            layout.append((w_off, s_off, k, cout, cpad, nsrc, c_src))
+            cout_k = (cout + 31) // 32 * 32
+            layout.append((w_off, s_off, k, cout, cpad, nsrc, c_src, wd_off, cout_k))
             w_off += cpad * k
             s_off += cpad
+            wd_off += k * cout_k
         self._w = torch.zeros(w_off, dtype=torch.bfloat16, device=device)
+        self._wd = torch.zeros(wd_off if with_wd else 0, dtype=torch.bfloat16, device=device)
+        self._with_wd = with_wd
         self._scale = torch.zeros(s_off, dtype=torch.float32, device=device)
         self._shift = torch.zeros(s_off, dtype=torch.float32, device=device)
         entries = []
         self._views = {}
-        for slot, (wo, so, k, cout, cpad, nsrc, c_src) in zip(self.slots, layout):
+        for si, (slot, (wo, so, k, cout, cpad, nsrc, c_src, wdo, cout_k)) in enumerate(zip(self.slots, layout)):
             first = slot[0]
             w = self._w[wo:wo + cpad * k].view(cpad, k)
             sc = self._scale[so:so + cpad]
             sh = self._shift[so:so + cpad]
+            taps = first.kernel_size ** 2
+            wd = self._wd[wdo:wdo + k * cout_k].view(nsrc * c_src, taps * cout_k) if with_wd else None
             self._views[id(first)] = ConvWeights(w, sc, sh, cout, cpad, nsrc, c_src, first.kernel_size,
-                                                 first.stride)
+                                                 first.stride, wd=wd, cout_k=cout_k, slot=si)
             r = 0
             for m in slot:
                 e = N.WnEntry()
@@ -157,6 +176,8 @@ class WeightBank:
                 e.shift = sh.data_ptr() + r * 4
                 e.cout, e.cin, e.ktaps, e.c_src = m.out_channels, m.in_channels, m.kernel_size ** 2, c_src
                 e.ktot, e.row_start = k, rows
+                if with_wd:
+                    e.wd, e.wd_cout, e.wd_col0 = wd.data_ptr(), cout_k, r
                 rows += m.out_channels
                 r += m.out_channels
                 entries.append(e)
@@ -175,15 +196,17 @@ class WeightBank:
                 yield m.beta
                 yield m.conv.bias
 
-    def refresh(self) -> None:
-        """Re-run weight-norm preparation iff a parameter changed (version or storage)."""
+    def refresh(self, with_wd: bool = False) -> None:
+        """Re-run weight-norm preparation iff a parameter changed (version or storage).  ``with_wd`` also
+        prepares the data-gradient weight matrices the training path needs (kept once requested)."""
         params = list(self._params())
         dev = params[0].device
         if dev.type != "cuda":
             raise RuntimeError("vunet_b200 has no CPU path: move the module to a CUDA device")
         ptr_key = tuple(p.data_ptr() for p in params)
-        if self._device != dev or getattr(self, "_ptr_key", None) != ptr_key:
-            self._allocate(dev)
+        with_wd = with_wd or self._with_wd
+        if self._device != dev or getattr(self, "_ptr_key", None) != ptr_key or with_wd != self._with_wd:
+            self._allocate(dev, with_wd)
             self._ptr_key = ptr_key
             self._key = None
         key = tuple(p._version for p in params)
@@ -267,20 +290,39 @@ class NormConv2d(nn.Module):
         self.conv = _WeightNormConvParams(in_channels, out_channels, kernel_size, stride, padding)
         self._vub_split = 1      # number of concatenated sources feeding this conv
         self._vub_stem = False   # K too small for tensor cores -> CUDA-core stem kernel
+        self._vub_owner = None   # top-level sub-network ("eu" / "ed" / "du" / "dd"): gradient bucket of this conv
         self._solo_bank: Optional[WeightBank] = None
 
     # fused-path entry points -------------------------------------------------------------------
-    def _run(self, bank: WeightBank, srcs: Sequence[torch.Tensor], *, residual=None, want_raw=True,
-             want_elu=True, d2s=False) -> Act:
+    def _run(self, bank: WeightBank, srcs: Sequence[Tuple[Act, str]], *, residual: Optional[Act] = None,
+             want_raw=True, want_elu=True, d2s=False) -> Act:
+        """``srcs``: the concatenated inputs as (activation, "raw" | "elu") pairs; ``residual`` is added raw."""
         cw = bank.get(self)
-        raw, elu = ops.conv_fwd(srcs, cw.w, cw.scale, cw.shift, ksize=cw.ksize, stride=cw.stride,
-                                residual=residual, want_raw=want_raw, want_elu=want_elu, d2s=d2s)
-        return Act(raw, elu)
+        raw, elu = ops.conv_fwd([a.pick(m) for a, m in srcs], cw.w, cw.scale, cw.shift, ksize=cw.ksize,
+                                stride=cw.stride, residual=None if residual is None else residual.raw,
+                                want_raw=want_raw, want_elu=want_elu, d2s=d2s)
+        out = Act(raw, elu)
+        if bank.tape is not None:
+            bank.tape.conv(self, srcs, residual, out, d2s)
+        return out
 
-    def _run_stem(self, x: torch.Tensor, want_raw=True, want_elu=True) -> Act:
+    def _run_f32(self, bank: WeightBank, srcs: Sequence[Tuple[Act, str]], layout: str):
+        """fp32 output (latent head input NHWC / image NCHW).  Returns (tensor, gradient slot or None)."""
+        cw = bank.get(self)
+        out = ops.conv_fwd_f32([a.pick(m) for a, m in srcs], cw.w, cw.scale, cw.shift, ksize=cw.ksize, layout=layout,
+                               cout_valid=cw.cout)
+        slot = None
+        if bank.tape is not None:
+            slot = bank.tape.conv(self, srcs, None, None, False)
+        return out, slot
+
+    def _run_stem(self, x: torch.Tensor, want_raw=True, want_elu=True, bank: Optional[WeightBank] = None) -> Act:
         c = self.conv
         raw, elu = ops.stem_fwd(x, c.weight_v, c.weight_g, self.gamma, self.beta, c.bias, want_raw, want_elu)
-        return Act(raw, elu)
+        out = Act(raw, elu)
+        if bank is not None and bank.tape is not None:
+            bank.tape.stem(self, x, out)
+        return out
 
     # reference-compatible standalone call -----------------------------------------------------
     def forward(self, x):
@@ -299,7 +341,7 @@ class NormConv2d(nn.Module):
         if self.stride == 1:
             return ops.conv_fwd_f32([act.raw], cw.w, cw.scale, cw.shift, ksize=cw.ksize, layout="nchw",
                                     cout_valid=cw.cout)
-        return self._run(self._solo_bank, [act.raw]).nchw()
+        return self._run(self._solo_bank, [(act, "raw")]).nchw()
 
 
 class Downsample(nn.Module):
@@ -311,7 +353,7 @@ class Downsample(nn.Module):
                                kernel_size=3, stride=2, padding=1)
 
     def _run(self, bank, h: Act, want_raw=True, want_elu=True) -> Act:
-        return self.down._run(bank, [h.raw], want_raw=want_raw, want_elu=want_elu)
+        return self.down._run(bank, [(h, "raw")], want_raw=want_raw, want_elu=want_elu)
 
     def forward(self, x):
         bank = _solo_bank(self)
@@ -331,7 +373,7 @@ class Upsample(nn.Module):
         self.op2 = DepthToSpace(block_size=2)
 
     def _run(self, bank, h: Act, want_raw=True, want_elu=True) -> Act:
-        return self.up._run(bank, [h.raw], want_raw=want_raw, want_elu=want_elu, d2s=True)
+        return self.up._run(bank, [(h, "raw")], want_raw=want_raw, want_elu=want_elu, d2s=True)
 
     def forward(self, x):
         bank = _solo_bank(self)
@@ -368,13 +410,13 @@ class VunetRNB(nn.Module):
              want_elu=True) -> Act:
         if self.dout.p > 0.0 and self.training:
             raise NotImplementedError("dropout_prob > 0 is not fused (the reference never enables it: SURVEY.md §3.3)")
-        srcs = [x.elu]
+        srcs = [(x, "elu")]
         if a is not None:
             assert self.residual
             a_list = [a] if isinstance(a, Act) else list(a)
-            n = self.nin._run(bank, [t.elu for t in a_list], want_raw=False, want_elu=True)
-            srcs.append(n.elu)
-        return self.conv._run(bank, srcs, residual=x.raw, want_raw=want_raw, want_elu=want_elu)
+            n = self.nin._run(bank, [(t, "elu") for t in a_list], want_raw=False, want_elu=True)
+            srcs.append((n, "elu"))
+        return self.conv._run(bank, srcs, residual=x, want_raw=want_raw, want_elu=want_elu)
 
     def forward(self, x, a=None):
         bank = _solo_bank(self)

@@ -31,6 +31,19 @@ _LIB.define(
 _LIB.define("latent_fwd(Tensor ml, Tensor? eps, bool want_elu_z, bool want_elu_mu) -> Tensor[]")
 _LIB.define("nchw_to_nhwc(Tensor x, bool want_raw, bool want_elu) -> Tensor[]")
 _LIB.define("nhwc_to_nchw(Tensor x) -> Tensor")
+# ---- training half (mutating ops: gradient buffers are accumulated in place) ----------------------
+_LIB.define(
+    "conv_dgrad(Tensor dy, Tensor wd, Tensor(a!) dx0, Tensor(b!)? dx1, Tensor? mask0, Tensor? mask1, "
+    "Tensor? add0, Tensor? add1, Tensor? add20, Tensor? add21, int ksize, int stride, bool d2s) -> ()"
+)
+_LIB.define(
+    "conv_wgrad(Tensor dy, Tensor x0, Tensor? x1, Tensor(a!) gt, Tensor(b!) dy_sum, int ksize, int stride, "
+    "bool d2s) -> ()"
+)
+_LIB.define("wn_bwd(Tensor table, int n_entries, int total_rows, bool accumulate) -> ()")
+_LIB.define("stem_bwd(Tensor x, Tensor dy, Tensor(a!) gt, Tensor(b!) dy_sum) -> ()")
+_LIB.define("latent_bwd(Tensor logstd, Tensor? eps, Tensor? d_mu, Tensor? d_ls, Tensor? dz) -> Tensor")
+_LIB.define("nchw_to_nhwc_pad(Tensor x, int c_pad) -> Tensor")
 
 F32_NONE, F32_NHWC, F32_NCHW = 0, 1, 2
 
@@ -126,7 +139,8 @@ def _conv_fwd_cuda(x0, x1, w, scale, shift, residual, ksize, stride, cout_valid,
     out_bytes = sum(o.numel() * o.element_size() for o in outs)
     in_bytes = nsrc * x0.numel() * 2 + w.numel() * 2 + (residual.numel() * 2 if residual is not None else 0)
     flops = 2.0 * B * Ho * Wo * cout_valid * w.shape[1]
-    N.check(_launch(f"conv_fwd<{bn},{bkc}>", N.lib().vub_conv_fwd, C.byref(d), _stream(), flops=flops,
+    tag = f"conv_fwd<{bn},{bkc}> {nsrc}x{c_src}->{cout} k{ksize} s{stride}{' d2s' if d2s else ''} @{H}x{W}"
+    N.check(_launch(tag, N.lib().vub_conv_fwd, C.byref(d), _stream(), flops=flops,
                     bytes_=float(in_bytes + out_bytes)), "vub_conv_fwd")
     return outs
 
@@ -152,7 +166,7 @@ def _stem_fwd_cuda(x, v, g, gamma, beta, bias, want_raw, want_elu) -> List[torch
         outs.append(elu)
     nbytes = float(x.numel() * 4 + sum(o.numel() * 2 for o in outs))
     N.check(
-        _launch(f"stem<{cout}>", N.lib().vub_stem_fwd, x.data_ptr(), v.data_ptr(), g.data_ptr(), gamma.data_ptr(),
+        _launch(f"stem<{cout}> {cx}->{cout} @{H}x{W}", N.lib().vub_stem_fwd, x.data_ptr(), v.data_ptr(), g.data_ptr(), gamma.data_ptr(),
                 beta.data_ptr(), bias.data_ptr(), B, cx, H, W, cout, _p(raw), _p(elu), _stream(),
                 flops=2.0 * B * H * W * cx * cout, bytes_=nbytes),
         "vub_stem_fwd",
@@ -213,7 +227,123 @@ def _nhwc_to_nchw_cuda(x) -> torch.Tensor:
     return out
 
 
+def _conv_dgrad_cuda(dy, wd, dx0, dx1, mask0, mask1, add0, add1, add20, add21, ksize, stride, d2s) -> None:
+    _check_act(dy, "conv_dgrad dy")
+    _check_act(dx0, "conv_dgrad dx0")
+    B, H, W, c_src = dx0.shape
+    nsrc = 1 if dx1 is None else 2
+    taps = ksize * ksize
+    if wd.dtype != torch.bfloat16 or wd.dim() != 2 or wd.shape[0] != nsrc * c_src or wd.shape[1] % taps:
+        raise ValueError(f"conv_dgrad: wd {tuple(wd.shape)} does not match nsrc={nsrc} c_src={c_src} k={ksize}")
+    cout_k = wd.shape[1] // taps
+    Ho, Wo = H // stride, W // stride
+    want = (B, 2 * Ho, 2 * Wo, cout_k // 4) if d2s else (B, Ho, Wo, cout_k)
+    if tuple(dy.shape) != want:
+        raise ValueError(f"conv_dgrad: dy {tuple(dy.shape)} != {want}")
+    for t in (dx1, mask0, mask1, add0, add1, add20, add21):
+        if t is not None and (t.shape != dx0.shape or t.dtype != torch.bfloat16 or not t.is_contiguous()):
+            raise ValueError("conv_dgrad: dx / mask / addend tensors must be contiguous NHWC bf16 of the input shape")
+    d = N.DgradDesc()
+    d.dy, d.wd = dy.data_ptr(), wd.data_ptr()
+    d.dx[0], d.dx[1] = dx0.data_ptr(), _p(dx1)
+    d.mask_elu[0], d.mask_elu[1] = _p(mask0), _p(mask1)
+    d.addend[0], d.addend[1] = _p(add0), _p(add1)
+    d.addend2[0], d.addend2[1] = _p(add20), _p(add21)
+    d.nsrc, d.c_src, d.batch, d.hin, d.win = nsrc, c_src, B, H, W
+    d.cout_k, d.ksize, d.stride, d.flags = cout_k, ksize, stride, (N.CONV_D2S if d2s else 0)
+    n_extra = sum(t is not None for t in (mask0, mask1, add0, add1, add20, add21))
+    nbytes = float(dy.numel() * 2 + wd.numel() * 2 + dx0.numel() * 2 * (nsrc + n_extra))
+    flops = 2.0 * B * Ho * Wo * cout_k * taps * nsrc * c_src
+    tag = f"conv_dgrad {nsrc}x{c_src}<-{cout_k} k{ksize} s{stride}{' d2s' if d2s else ''} @{H}x{W}"
+    N.check(_launch(tag, N.lib().vub_conv_dgrad, C.byref(d), _stream(), flops=flops,
+                    bytes_=nbytes), "vub_conv_dgrad")
+
+
+def _conv_wgrad_cuda(dy, x0, x1, gt, dy_sum, ksize, stride, d2s) -> None:
+    _check_act(dy, "conv_wgrad dy")
+    _check_act(x0, "conv_wgrad x0")
+    B, H, W, c_src = x0.shape
+    nsrc = 1
+    if x1 is not None:
+        _check_act(x1, "conv_wgrad x1")
+        if x1.shape != x0.shape:
+            raise ValueError("conv_wgrad: both sources must have the same shape")
+        nsrc = 2
+    taps = ksize * ksize
+    Ho, Wo = H // stride, W // stride
+    cout_k = dy.shape[3] * 4 if d2s else dy.shape[3]
+    want = (B, 2 * Ho, 2 * Wo, cout_k // 4) if d2s else (B, Ho, Wo, cout_k)
+    if tuple(dy.shape) != want:
+        raise ValueError(f"conv_wgrad: dy {tuple(dy.shape)} != {want}")
+    if (gt.dtype != torch.float32 or gt.dim() != 2 or gt.shape[0] != nsrc * taps * c_src or gt.shape[1] < cout_k
+            or gt.stride(1) != 1 or dy_sum.dtype != torch.float32 or dy_sum.numel() < cout_k):
+        raise ValueError(f"conv_wgrad: gt {tuple(gt.shape)} / dy_sum do not match K={nsrc * taps * c_src}, cout_k={cout_k}")
+    d = N.WgradDesc()
+    d.dy, d.gt, d.dy_sum = dy.data_ptr(), gt.data_ptr(), dy_sum.data_ptr()
+    d.x[0], d.x[1] = x0.data_ptr(), _p(x1)
+    d.nsrc, d.c_src, d.batch, d.hin, d.win = nsrc, c_src, B, H, W
+    d.cout_k, d.gt_pitch, d.ksize, d.stride, d.flags = cout_k, gt.stride(0), ksize, stride, (N.CONV_D2S if d2s else 0)
+    nbytes = float(dy.numel() * 2 + nsrc * x0.numel() * 2 + gt.shape[0] * cout_k * 4)
+    flops = 2.0 * B * Ho * Wo * cout_k * taps * nsrc * c_src
+    tag = f"conv_wgrad {nsrc}x{c_src}x{cout_k} k{ksize} s{stride}{' d2s' if d2s else ''} @{H}x{W}"
+    N.check(_launch(tag, N.lib().vub_conv_wgrad, C.byref(d), _stream(), flops=flops,
+                    bytes_=nbytes), "vub_conv_wgrad")
+
+
+def _wn_bwd_cuda(table, n_entries, total_rows, accumulate) -> None:
+    N.check(_launch("wn_bwd", N.lib().vub_wn_bwd, table.data_ptr(), n_entries, total_rows, int(accumulate), _stream()),
+            "vub_wn_bwd")
+
+
+def _stem_bwd_cuda(x, dy, gt, dy_sum) -> None:
+    if x.dtype != torch.float32 or x.dim() != 4 or not x.is_contiguous():
+        raise ValueError("stem_bwd: x must be contiguous NCHW fp32")
+    _check_act(dy, "stem_bwd dy")
+    B, cx, H, W = x.shape
+    cout = dy.shape[3]
+    if tuple(dy.shape) != (B, H, W, cout) or gt.numel() != cx * cout or dy_sum.numel() < cout:
+        raise ValueError("stem_bwd: shape mismatch")
+    N.check(_launch(f"stem_bwd<{cout}>", N.lib().vub_stem_bwd, x.data_ptr(), dy.data_ptr(), B, cx, H, W, cout,
+                    gt.data_ptr(), dy_sum.data_ptr(), _stream(), flops=2.0 * B * H * W * cx * cout,
+                    bytes_=float(x.numel() * 4 + dy.numel() * 2)), "vub_stem_bwd")
+
+
+def _latent_bwd_cuda(logstd, eps, d_mu, d_ls, dz) -> torch.Tensor:
+    if logstd.dtype != torch.float32 or logstd.dim() != 4 or not logstd.is_contiguous():
+        raise ValueError("latent_bwd: logstd must be contiguous NCHW fp32")
+    B, c, h, w = logstd.shape
+    for t in (eps, d_mu, d_ls):
+        if t is not None and (t.dtype != torch.float32 or t.shape != logstd.shape or not t.is_contiguous()):
+            raise ValueError("latent_bwd: eps / d_mu / d_ls must be contiguous NCHW fp32 like logstd")
+    if dz is not None:
+        _check_act(dz, "latent_bwd dz")
+        if tuple(dz.shape) != (B, h, w, c):
+            raise ValueError("latent_bwd: dz shape mismatch")
+    out = torch.empty((B, h, w, 2 * c), dtype=torch.bfloat16, device=logstd.device)
+    N.check(_launch("latent_bwd", N.lib().vub_latent_bwd, None, logstd.data_ptr(), _p(eps), _p(d_mu), _p(d_ls), _p(dz),
+                    B, c, h, w, out.data_ptr(), _stream(), bytes_=float(logstd.numel() * 22)), "vub_latent_bwd")
+    return out
+
+
+def _nchw_to_nhwc_pad_cuda(x, c_pad) -> torch.Tensor:
+    if x.dtype != torch.float32 or x.dim() != 4:
+        raise ValueError("nchw_to_nhwc_pad: x must be NCHW fp32")
+    x = x.contiguous()
+    B, c, H, W = x.shape
+    out = torch.empty((B, H, W, c_pad), dtype=torch.bfloat16, device=x.device)
+    N.check(_launch("nchw_to_nhwc_pad", N.lib().vub_nchw_f32_to_nhwc_bf16_pad, x.data_ptr(), B, c, H, W, c_pad,
+                    out.data_ptr(), _stream(), bytes_=float(x.numel() * 4 + out.numel() * 2)),
+            "vub_nchw_f32_to_nhwc_bf16_pad")
+    return out
+
+
 _LIB.impl("conv_fwd", _conv_fwd_cuda, "CUDA")
+_LIB.impl("conv_dgrad", _conv_dgrad_cuda, "CUDA")
+_LIB.impl("conv_wgrad", _conv_wgrad_cuda, "CUDA")
+_LIB.impl("wn_bwd", _wn_bwd_cuda, "CUDA")
+_LIB.impl("stem_bwd", _stem_bwd_cuda, "CUDA")
+_LIB.impl("latent_bwd", _latent_bwd_cuda, "CUDA")
+_LIB.impl("nchw_to_nhwc_pad", _nchw_to_nhwc_pad_cuda, "CUDA")
 _LIB.impl("wn_prep", _wn_prep_cuda, "CUDA")
 _LIB.impl("stem_fwd", _stem_fwd_cuda, "CUDA")
 _LIB.impl("latent_fwd", _latent_fwd_cuda, "CUDA")
@@ -280,3 +410,35 @@ def nchw_to_nhwc(x, want_raw=True, want_elu=True):
 
 def nhwc_to_nchw(x):
     return _ops.nhwc_to_nchw(x)
+
+
+# ---- training half ------------------------------------------------------------------------------
+def conv_dgrad(dy, wd, dx, *, mask=(None, None), addend=(None, None), addend2=(None, None), ksize: int,
+               stride: int = 1, d2s: bool = False) -> None:
+    """``dx[s] = ELU'(mask[s]) * dgrad_s + addend[s] + addend2[s]`` for every source (in place into dx)."""
+    dx = list(dx) + [None] * (2 - len(dx))
+    mask = list(mask) + [None] * (2 - len(mask))
+    addend = list(addend) + [None] * (2 - len(addend))
+    addend2 = list(addend2) + [None] * (2 - len(addend2))
+    _ops.conv_dgrad(dy, wd, dx[0], dx[1], mask[0], mask[1], addend[0], addend[1], addend2[0], addend2[1], ksize,
+                    stride, d2s)
+
+
+def conv_wgrad(dy, x, gt, dy_sum, *, ksize: int, stride: int = 1, d2s: bool = False) -> None:
+    _ops.conv_wgrad(dy, x[0], x[1] if len(x) > 1 else None, gt, dy_sum, ksize, stride, d2s)
+
+
+def wn_bwd(table: torch.Tensor, n_entries: int, total_rows: int, accumulate: bool = False) -> None:
+    _ops.wn_bwd(table, n_entries, total_rows, accumulate)
+
+
+def stem_bwd(x, dy, gt, dy_sum) -> None:
+    _ops.stem_bwd(x, dy, gt, dy_sum)
+
+
+def latent_bwd(logstd, eps, d_mu, d_ls, dz) -> torch.Tensor:
+    return _ops.latent_bwd(logstd, eps, d_mu, d_ls, dz)
+
+
+def nchw_to_nhwc_pad(x, c_pad: int) -> torch.Tensor:
+    return _ops.nchw_to_nhwc_pad(x, c_pad)

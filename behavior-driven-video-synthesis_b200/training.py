@@ -1,0 +1,335 @@
+"""Training half of the VUnet path: the backward schedule over the fused forward graph.
+
+The reference trains through autograd (``loss.backward()`` in ``experiments/shape_and_pose_net.py:429-432``):
+~600 eager forward kernels leave a graph of conv / ELU / cat / add / weight-norm nodes behind and autograd
+replays it.  Here the forward pass of :class:`~.vunets.VunetAlter` appends one record per fused launch to
+a :class:`Tape`; ONE ``torch.autograd.Function`` spans the whole model, and its backward walks the tape in
+reverse issuing, per conv, one weight-correlation launch (``vub_conv_wgrad``) and one data-gradient launch
+(``vub_conv_dgrad``, ELU' masks / residual adds / skip accumulation fused into its epilogue).  Parameter
+gradients of all layers of a sub-network come from ONE ``vub_wn_bwd`` launch and are written straight into
+flat per-sub-network buckets (``dd``, ``du``, ``ed``, ``eu`` — reverse forward order); ``param.grad`` are
+views of those buckets, so the data-parallel gradient exchange is one in-place NCCL all-reduce per bucket
+on a side stream, overlapped with the rest of the backward pass (replacing ``nn.DataParallel``'s
+per-step broadcast / gather / reduce, ``shape_and_pose_net.py:213-214``).
+
+Gradients flow from ``imgs``, ``means`` and ``logstds``; the ``activations`` list is returned detached
+(no caller of the reference reads it).  The 25 parameters of the dead branch
+(``ed.blocks[3]``, ``ed.ups[1]``, ``ed.fin_block``) keep ``grad = None`` like in the reference.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _native as N
+from . import ops
+from .modules import Act, NormConv2d, WeightBank
+
+OWNER_ORDER = ("dd", "du", "ed", "eu")  # reverse forward order = order in which backward finishes them
+
+
+class GradSlot:
+    """Gradient holder for a conv output that is not an :class:`Act` (fp32 latent-head input, image)."""
+
+    __slots__ = ("grad",)
+
+    def __init__(self):
+        self.grad = None
+
+
+class Tape:
+    """Records of one forward pass, in launch order."""
+
+    def __init__(self):
+        self.recs: List[tuple] = []
+        self.img_slot: Optional[GradSlot] = None
+        self.latents: List[dict] = []
+
+    def conv(self, conv: NormConv2d, srcs, residual: Optional[Act], out: Optional[Act], d2s: bool):
+        slot = out if out is not None else GradSlot()
+        self.recs.append(("conv", conv, list(srcs), residual, slot, d2s))
+        return slot
+
+    def stem(self, conv: NormConv2d, x: torch.Tensor, out: Act):
+        self.recs.append(("stem", conv, x.contiguous(), out))
+
+    def latent(self, ml_slot: GradSlot, res: dict, eps: torch.Tensor):
+        rec = {"ml_slot": ml_slot, "logstd": res["logstd"], "eps": eps, "z_act": res["z_act"], "d_mu": None,
+               "d_ls": None}
+        self.latents.append(rec)
+        self.recs.append(("latent", rec))
+
+
+# --------------------------------------------------------------------------------------------------
+class GradBank:
+    """Weight-correlation scratch + flat gradient buckets for the convs that appear on a tape."""
+
+    def __init__(self, model: torch.nn.Module, bank: WeightBank, tape: Tape):
+        convs: List[NormConv2d] = []   # slot leaders and stems, in tape order
+        seen = set()
+        for rec in tape.recs:
+            if rec[0] in ("conv", "stem") and id(rec[1]) not in seen:
+                seen.add(id(rec[1]))
+                convs.append(rec[1])
+        self.key = tuple(sorted(seen))
+        dev = next(model.parameters()).device
+        members: Dict[int, List[NormConv2d]] = {}
+        for slot in bank.slots:
+            members[id(slot[0])] = slot
+        # ---- correlation scratch: gt [K, pitch] + dy_sum [pitch] per conv slot / stem ----
+        off = 0
+        place = {}
+        for cv in convs:
+            if cv._vub_stem:
+                k, pitch = cv.in_channels, cv.out_channels
+            else:
+                cw = bank.get(cv)
+                k, pitch = cw.nsrc * cw.ksize * cw.ksize * cw.c_src, cw.cout_k
+            place[id(cv)] = (off, k, pitch)
+            off += (k + 1) * pitch
+        self._gbuf = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.gt, self.dy_sum = {}, {}
+        for cv in convs:
+            o, k, pitch = place[id(cv)]
+            self.gt[id(cv)] = self._gbuf[o:o + k * pitch].view(k, pitch)
+            self.dy_sum[id(cv)] = self._gbuf[o + k * pitch:o + (k + 1) * pitch]
+        # ---- gradient buckets per owner, parameters in registration order ----
+        live = []  # every NormConv2d that receives gradients
+        for cv in convs:
+            live.extend([cv] if cv._vub_stem else members[id(cv)])
+        live_ids = {id(m) for m in live}
+        self.buckets: Dict[str, torch.Tensor] = {}
+        self.grads: Dict[int, torch.Tensor] = {}   # id(param) -> view of its bucket
+        self.params: Dict[str, List[torch.nn.Parameter]] = {}
+        self._tables = {}
+        leader_of = {}
+        for cv in convs:
+            for j, m in enumerate([cv] if cv._vub_stem else members[id(cv)]):
+                leader_of[id(m)] = cv
+        for owner in OWNER_ORDER:
+            sub = getattr(model, owner, None)
+            if sub is None:
+                continue
+            mods = [m for m in sub.modules() if isinstance(m, NormConv2d) and id(m) in live_ids]
+            if not mods:
+                continue
+            plist = []
+            for m in mods:
+                plist.extend([m.beta, m.gamma, m.conv.bias, m.conv.weight_g, m.conv.weight_v])
+            total = sum(p.numel() for p in plist)
+            flat = torch.zeros(total, dtype=torch.float32, device=dev)
+            o = 0
+            for p in plist:
+                self.grads[id(p)] = flat[o:o + p.numel()].view(p.shape)
+                o += p.numel()
+            self.buckets[owner] = flat
+            self.params[owner] = plist
+            entries, rows = [], 0
+            for m in mods:
+                cv = leader_of[id(m)]
+                e = N.WnbEntry()
+                e.v, e.g = m.conv.weight_v.data_ptr(), m.conv.weight_g.data_ptr()
+                e.gamma, e.bias = m.gamma.data_ptr(), m.conv.bias.data_ptr()
+                e.gt, e.dy_sum = self.gt[id(cv)].data_ptr(), self.dy_sum[id(cv)].data_ptr()
+                e.d_v, e.d_g = self.grads[id(m.conv.weight_v)].data_ptr(), self.grads[id(m.conv.weight_g)].data_ptr()
+                e.d_gamma, e.d_beta = self.grads[id(m.gamma)].data_ptr(), self.grads[id(m.beta)].data_ptr()
+                e.d_bias = self.grads[id(m.conv.bias)].data_ptr()
+                if m._vub_stem:
+                    c_src, col0 = m.in_channels, 0
+                else:
+                    cw = bank.get(cv)
+                    c_src = cw.c_src
+                    col0 = sum(x.out_channels for x in members[id(cv)][:members[id(cv)].index(m)])
+                e.cout, e.cin, e.ktaps, e.c_src = m.out_channels, m.in_channels, m.kernel_size ** 2, c_src
+                e.gt_pitch, e.gt_col0, e.row_start = place[id(cv)][2], col0, rows
+                rows += m.out_channels
+                entries.append(e)
+            arr = (N.WnbEntry * len(entries))(*entries)
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            self._tables[owner] = (host.to(dev), len(entries), rows)
+        self._ptr_key = tuple(p.data_ptr() for ps in self.params.values() for p in ps)
+
+    def matches(self, tape: Tape, model) -> bool:
+        ids = {id(r[1]) for r in tape.recs if r[0] in ("conv", "stem")}
+        if tuple(sorted(ids)) != self.key:
+            return False
+        return self._ptr_key == tuple(p.data_ptr() for ps in self.params.values() for p in ps)
+
+    def zero(self) -> None:
+        self._gbuf.zero_()
+
+    def finish_owner(self, owner: str) -> None:
+        """All correlations of this sub-network are complete: produce its parameter gradients."""
+        if owner not in self._tables:
+            return
+        plist = self.params[owner]
+        # accumulate iff the parameters still hold OUR views from an earlier backward (no zero_grad in between)
+        held = [p.grad is not None and p.grad.data_ptr() == self.grads[id(p)].data_ptr() for p in plist]
+        accumulate = all(held)
+        extra = None
+        if not accumulate and any(p.grad is not None for p in plist):
+            extra = [(p, p.grad) for p in plist if p.grad is not None and p.grad.data_ptr() != self.grads[id(p)].data_ptr()]
+        table, n, rows = self._tables[owner]
+        ops.wn_bwd(table, n, rows, accumulate)
+        for p in plist:
+            p.grad = self.grads[id(p)]
+        if extra:
+            for p, old in extra:  # foreign gradient tensors (e.g. zero_grad(set_to_none=False) copies): keep their sum
+                p.grad.add_(old)
+
+
+# --------------------------------------------------------------------------------------------------
+def run_backward(model, bank: WeightBank, tape: Tape, d_imgs: Optional[torch.Tensor], reducer=None) -> None:
+    """Walk the tape in reverse; parameter gradients land in ``param.grad`` (views of flat buckets)."""
+    gb: Optional[GradBank] = getattr(model, "_vub_grad_bank", None)
+    if gb is None or not gb.matches(tape, model):
+        gb = GradBank(model, bank, tape)
+        object.__setattr__(model, "_vub_grad_bank", gb)
+    gb.zero()
+    if d_imgs is not None and tape.img_slot is not None:
+        tape.img_slot.grad = ops.nchw_to_nhwc_pad(d_imgs.float(), 32)
+    current = None
+    for rec in reversed(tape.recs):
+        kind = rec[0]
+        owner = rec[1]._vub_owner if kind != "latent" else "ed"
+        if owner != current:
+            if current is not None:
+                gb.finish_owner(current)
+                if reducer is not None:
+                    reducer.bucket_ready(current, gb.buckets.get(current))
+            current = owner
+        if kind == "conv":
+            _, conv, srcs, residual, out, d2s = rec
+            dy = out.grad
+            if dy is None:
+                continue
+            cw = bank.get(conv)
+            ops.conv_wgrad(dy, [a.pick(m) for a, m in srcs], gb.gt[id(conv)], gb.dy_sum[id(conv)], ksize=cw.ksize,
+                           stride=cw.stride, d2s=d2s)
+            dx, mask, add1, add2 = [], [], [], []
+            for a, m in srcs:
+                existed = a.grad is not None
+                if not existed:
+                    a.grad = torch.empty_like(a.pick(m))
+                dx.append(a.grad)
+                mask.append(a.elu if m == "elu" else None)
+                a1 = a.grad if existed else None
+                a2 = dy if residual is a else None
+                if a1 is None:
+                    a1, a2 = a2, None
+                add1.append(a1)
+                add2.append(a2)
+            ops.conv_dgrad(dy, cw.wd, dx, mask=mask, addend=add1, addend2=add2, ksize=cw.ksize, stride=cw.stride,
+                           d2s=d2s)
+            out.grad = None
+        elif kind == "stem":
+            _, conv, x, out = rec
+            if out.grad is not None:
+                ops.stem_bwd(x, out.grad, gb.gt[id(conv)], gb.dy_sum[id(conv)])
+                out.grad = None
+        else:
+            r = rec[1]
+            dz = r["z_act"].grad
+            if dz is None and r["d_mu"] is None and r["d_ls"] is None:
+                continue
+            r["ml_slot"].grad = ops.latent_bwd(r["logstd"], r["eps"], r["d_mu"], r["d_ls"], dz)
+            r["z_act"].grad = None
+    if current is not None:
+        gb.finish_owner(current)
+        if reducer is not None:
+            reducer.bucket_ready(current, gb.buckets.get(current))
+    if reducer is not None:
+        reducer.finish()
+
+
+class _VunetTrainFn(torch.autograd.Function):
+    """The whole VunetAlter forward as ONE autograd node (see module docstring)."""
+
+    @staticmethod
+    def forward(ctx, model, x, c, eps, anchor):
+        bank: WeightBank = model._bank(with_wd=True)
+        tape = Tape()
+        bank.tape = tape
+        try:
+            imgs, lat, hs_left = model._forward_impl(bank, x, c, eps)
+        finally:
+            bank.tape = None
+        ctx.model, ctx.bank, ctx.tape = model, bank, tape
+        ctx.set_materialize_grads(False)
+        means = [r["mu"] for r in lat]
+        logstds = [r["logstd"] for r in lat]
+        hs = [h.nchw() for h in hs_left]
+        ctx.mark_non_differentiable(*hs)
+        ctx.n_lat = len(lat)
+        return (imgs, *means, *logstds, *hs)
+
+    @staticmethod
+    def backward(ctx, d_imgs, *rest):
+        tape: Tape = ctx.tape
+        if tape is None:
+            raise RuntimeError("vunet_b200: backward through the same forward pass twice is not supported")
+        n = ctx.n_lat
+        for i, rec in enumerate(tape.latents):
+            d_mu, d_ls = rest[i], rest[n + i]
+            rec["d_mu"] = None if d_mu is None else d_mu.float().contiguous()
+            rec["d_ls"] = None if d_ls is None else d_ls.float().contiguous()
+        run_backward(ctx.model, ctx.bank, tape, None if d_imgs is None else d_imgs.contiguous(),
+                     reducer=getattr(ctx.model, "_vub_reducer", None))
+        ctx.tape = None  # activations and gradient buffers are released here
+        return None, None, None, None, None
+
+
+def train_forward(model, x, c, eps: Optional[Sequence[torch.Tensor]]):
+    """``VunetAlter.forward`` under autograd: returns (imgs, means, logstds, hs_left)."""
+    anchor = getattr(model, "_vub_anchor", None)
+    if anchor is None or anchor.device != x.device:
+        anchor = torch.zeros(1, device=x.device, requires_grad=True)
+        object.__setattr__(model, "_vub_anchor", anchor)
+    outs = _VunetTrainFn.apply(model, x, c, None if eps is None else list(eps), anchor)
+    n = model.ed.n_scales
+    imgs, means, logstds, hs = outs[0], list(outs[1:1 + n]), list(outs[1 + n:1 + 2 * n]), list(outs[1 + 2 * n:])
+    return imgs, means, logstds, hs
+
+
+# --------------------------------------------------------------------------------------------------
+class BucketReducer:
+    """Data-parallel gradient exchange: one in-place all-reduce (mean) per flat bucket, issued on a side
+    stream the moment the bucket's ``vub_wn_bwd`` has been enqueued, so it overlaps the remaining backward
+    launches; ``finish`` makes the compute stream wait for all of them (before ``optimizer.step``).
+
+    Works with any ``torch.distributed`` backend (NCCL over NVLink on the B200 box; gloo in the CPU tests,
+    where the "stream" logic degenerates to synchronous calls)."""
+
+    def __init__(self, process_group=None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = process_group
+        self.world = dist.get_world_size(process_group)
+        self._stream = None
+        self.bytes_last = 0
+        self.bytes_per_step = 0
+
+    def bucket_ready(self, owner: str, flat: Optional[torch.Tensor]) -> None:
+        if flat is None or self.world == 1:
+            return
+        self.bytes_last += flat.numel() * flat.element_size()
+        if flat.is_cuda:
+            if self._stream is None:
+                self._stream = torch.cuda.Stream(device=flat.device)
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(self._stream):
+                self._stream.wait_event(ev)
+                flat.div_(self.world)
+                self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM, group=self.group)
+            flat.record_stream(self._stream)
+        else:
+            flat.div_(self.world)
+            self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def finish(self) -> None:
+        if self._stream is not None:
+            torch.cuda.current_stream().wait_stream(self._stream)
+        self.bytes_per_step, self.bytes_last = self.bytes_last, 0

@@ -49,7 +49,7 @@ class EncUp(nn.Module):
 
     def _run(self, bank: WeightBank, x: torch.Tensor) -> List[Act]:
         hs: List[Act] = []
-        h = self.nin._run_stem(x)
+        h = self.nin._run_stem(x, bank=bank)
         for i in range(self.n_scales):
             for n in range(self.n_rnb):
                 h = self.blocks[2 * i + n]._run(bank, h)
@@ -99,12 +99,17 @@ class EncDownAlter(nn.Module):
         self._vub_merged_pairs = [(self.make_latent_params[i], self.make_logstds[i]) for i in range(n_scales)]
 
     def _latent(self, bank, i, h: Act, eps: Optional[torch.Tensor], want_elu_mu: bool):
-        cw = bank.get(self.make_latent_params[i])
-        ml = ops.conv_fwd_f32([h.raw], cw.w, cw.scale, cw.shift, ksize=3, layout="nhwc")
+        ml, ml_slot = self.make_latent_params[i]._run_f32(bank, [(h, "raw")], "nhwc")  # (mu || logit), one GEMM
         B, hh, ww, c2 = ml.shape
         if eps is None:
             eps = _draw_eps((B, c2 // 2, hh, ww), ml.device)
-        return ops.latent_fwd(ml, eps, want_elu_z=True, want_elu_mu=want_elu_mu)
+        res = ops.latent_fwd(ml, eps, want_elu_z=True, want_elu_mu=want_elu_mu)
+        res["z_act"] = Act(None, res["elu_z"])
+        if want_elu_mu:
+            res["mu_act"] = Act(None, res["elu_mu"])
+        if bank.tape is not None:
+            bank.tape.latent(ml_slot, res, eps)
+        return res
 
     def _run(self, bank, gs: List[Act], eps: Optional[Sequence[torch.Tensor]] = None, skip_dead=False,
              want_elu_mu=False):
@@ -112,7 +117,7 @@ class EncDownAlter(nn.Module):
         Returns (hs, latents) where latents[i] is the dict from ``ops.latent_fwd``."""
         hs: List[Act] = []
         lat = []
-        h = self.nin._run(bank, [gs[-1].raw])
+        h = self.nin._run(bank, [(gs[-1], "raw")])
         for i in range(self.n_scales):
             h = self.blocks[2 * i]._run(bank, h, gs.pop())
             hs.append(h)
@@ -125,8 +130,7 @@ class EncDownAlter(nn.Module):
                 gs.pop()
                 gs.pop()
                 break
-            z_act = Act(None, res["elu_z"])
-            h = self.blocks[2 * i + 1]._run(bank, h, [gs.pop(), z_act], want_elu=False)
+            h = self.blocks[2 * i + 1]._run(bank, h, [gs.pop(), res["z_act"]], want_elu=False)
             hs.append(h)
             h = self.ups[i]._run(bank, h)
         else:
@@ -179,22 +183,22 @@ class DecDownAlter(nn.Module):
                 self.ups.append(Upsample(nf, out_c, subpixel=True))
                 nf = out_c
 
-    def _run(self, bank, gs: List[Act], zs_elu: List[Optional[torch.Tensor]], training: bool) -> torch.Tensor:
-        """``zs_elu[i]``: NHWC bf16 ELU(z_i) (posterior sample or mean); ignored when ``training`` is False
-        (then z ~ N(0, I) is drawn like the reference, models/vunets.py:352)."""
+    def _run(self, bank, gs: List[Act], zs: List[Act], training: bool) -> torch.Tensor:
+        """``zs[i]``: activation holding ELU(z_i) (posterior sample or mean); ignored when ``training`` is
+        False (then z ~ N(0, I) is drawn like the reference, models/vunets.py:352)."""
         gs = list(gs)
-        zs_elu = list(zs_elu)
-        h = self.nin._run(bank, [gs[-1].raw])
+        zs = list(zs)
+        h = self.nin._run(bank, [(gs[-1], "raw")])
         lat_count = 0
         for i in range(self.n_scales):
             h = self.blocks[2 * i]._run(bank, h, gs.pop())
             if i < self.n_latent_scales:
                 if training:
-                    ez = zs_elu.pop(0)
+                    z = zs.pop(0)
                 else:
                     B, hh, ww, cc = h.raw.shape
-                    ez = ops.nchw_to_nhwc(_draw_eps((B, cc, hh, ww), h.raw.device), False, True)[1]
-                h = self.auto_blocks[lat_count]._run(bank, h, Act(None, ez))
+                    z = Act(None, ops.nchw_to_nhwc(_draw_eps((B, cc, hh, ww), h.raw.device), False, True)[1])
+                h = self.auto_blocks[lat_count]._run(bank, h, z)
                 lat_count += 1
             last = i + 1 == self.n_scales
             h = self.blocks[2 * i + 1]._run(bank, h, gs.pop(), want_elu=False)
@@ -202,14 +206,16 @@ class DecDownAlter(nn.Module):
                 h = self.ups[i]._run(bank, h)
         assert not gs
         if training:
-            assert not zs_elu
-        cw = bank.get(self.out_conv)
-        return ops.conv_fwd_f32([h.raw], cw.w, cw.scale, cw.shift, ksize=3, layout="nchw", cout_valid=cw.cout)
+            assert not zs
+        img, slot = self.out_conv._run_f32(bank, [(h, "raw")], "nchw")
+        if bank.tape is not None:
+            bank.tape.img_slot = slot
+        return img
 
     def forward(self, gs, zs_posterior, training):
         bank = _solo_bank(self)
         acts = [to_act(g) for g in gs]
-        zs = [to_act(z, need_raw=False, need_elu=True).elu for z in zs_posterior]
+        zs = [to_act(z, need_raw=False, need_elu=True) for z in zs_posterior]
         return self._run(bank, acts, zs, training)
 
 
@@ -253,10 +259,35 @@ class VunetAlter(nn.Module):
         self.dd = DecDownAlter(self.n_scales, kwargs["nf_max"], kwargs["nf_start"], nf_out=3,
                                conv_layer=NormConv2d, n_latent_scales=n_latent_scales,
                                subpixel_upsampling=kwargs["subpixel_upsampling"], dropout_prob=dropout_prob)
+        for owner in ("eu", "ed", "du", "dd"):
+            for m in getattr(self, owner).modules():
+                if isinstance(m, NormConv2d):
+                    m._vub_owner = owner
 
     # ---------------------------------------------------------------------------------------------
-    def _bank(self) -> WeightBank:
-        return _solo_bank(self)
+    def _bank(self, with_wd: bool = False) -> WeightBank:
+        bank = _solo_bank(self)
+        if with_wd and not bank._with_wd:
+            bank.refresh(with_wd=True)
+        return bank
+
+    def enable_data_parallel(self, process_group=None):
+        """Average parameter gradients over the ranks of ``process_group`` (default: the world) with one
+        all-reduce per sub-network bucket, overlapped with the backward pass.  One process per GPU; call
+        after ``torch.distributed.init_process_group``.  Replaces ``nn.DataParallel(vunet)``
+        (experiments/shape_and_pose_net.py:213-214).  Returns ``self``."""
+        from .training import BucketReducer
+        object.__setattr__(self, "_vub_reducer", BucketReducer(process_group))
+        return self
+
+    def _wants_grad(self) -> bool:
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
+    def _forward_impl(self, bank, x, c, eps):
+        _, hs_left, lat = self._encode(bank, x, eps, skip_dead=True, want_elu_mu=False)
+        gs = self.du._run(bank, c.float())
+        imgs = self.dd._run(bank, gs, [r["z_act"] for r in lat], True)
+        return imgs, lat, hs_left
 
     def _encode(self, bank, x, eps, skip_dead, want_elu_mu):
         hs = self.eu._run(bank, x.float())
@@ -269,10 +300,12 @@ class VunetAlter(nn.Module):
         injects the latent noise (one NCHW fp32 tensor per latent scale) instead of drawing it."""
         _require_cuda(x)
         _require_cuda(c)
+        if self._wants_grad():
+            from .training import train_forward
+            imgs, means, logstds, hs = train_forward(self, x, c, eps)
+            return imgs, means, logstds, (hs, means, logstds)
         bank = self._bank()
-        _, hs_left, lat = self._encode(bank, x, eps, skip_dead=True, want_elu_mu=False)
-        gs = self.du._run(bank, c.float())
-        imgs = self.dd._run(bank, gs, [r["elu_z"] for r in lat], True)
+        imgs, lat, hs_left = self._forward_impl(bank, x, c, eps)
         means = [_tag_kl(r["mu"], r) for r in lat]
         logstds = [r["logstd"] for r in lat]
         # like the reference, `hs` is what ed's pops left of eu's outputs
@@ -291,4 +324,4 @@ class VunetAlter(nn.Module):
         bank = self._bank()
         _, _, lat = self._encode(bank, x, eps, skip_dead=True, want_elu_mu=True)
         gs = self.du._run(bank, c.float())
-        return self.dd._run(bank, gs, [r["elu_mu"] for r in lat], True)
+        return self.dd._run(bank, gs, [r["mu_act"] for r in lat], True)

@@ -44,6 +44,13 @@ FRAMES_PER_GPU = 64
 GFLOP_PER_FRAME = 43.064
 METRIC = "VUnet 256x256 frame synthesis throughput (fwd)"
 UNIT = "frames/s"
+# BASELINE.json configs[2]: DeepFashion settings, training step, batch 32 per GPU
+D256 = dict(ARCH, spatial_size=256, bottleneck_factor=2, box_factor=2, n_channels_x=30)
+TRAIN_WORKLOAD = ("VunetAlter DeepFashion-256 (256x256, bottleneck_factor=2, box=2, n_channels_x=30) training step: "
+                  "forward + MSE/KL surrogate loss + backward + gradient all-reduce + fused Adam")
+TRAIN_BATCH_PER_GPU = 32
+# live convs, forward 34.000 GFLOP/sample; training = fwd + dgrad + wgrad minus the stems' dgrad
+TRAIN_GFLOP_PER_SAMPLE = 3 * 34.000 - 2e-9 * (64 * 64 * 32 * 30 + 256 * 256 * 32 * 3)
 
 
 def load_peaks():
@@ -122,6 +129,115 @@ def cpu_port_fps(sample_frames: int, iters: int, warmup: int = 1):
             if i >= warmup:
                 times.append(dt)
     return sample_frames / statistics.median(times), threads, times
+
+
+def cpu_port_train_sps(sample: int, iters: int, warmup: int = 1):
+    """samples/s of the CPU oracle's forward + autograd backward on `sample` D256 samples."""
+    import vunet_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    with contextlib.redirect_stdout(io.StringIO()):
+        import bdvs_b200 as B
+        shapes = {k: tuple(v.shape) for k, v in B.VunetAlter(**D256).state_dict().items()}
+    sd = {k: v.requires_grad_(True) for k, v in O.det_state_dict(shapes).items()}
+    x, c, eps, _ = O.make_inputs(D256, sample, tag="cpu")
+    target = O.det_uniform("target", (sample, 3, 256, 256))
+    times = []
+    for i in range(warmup + iters):
+        t0 = time.perf_counter()
+        imgs, means, logstds, _, _ = O.forward(sd, x, c, eps)
+        loss = torch.mean((imgs - target) ** 2) + 1e-3 * O.compute_kl_with_prior(means, logstds)
+        loss.backward()
+        for v in sd.values():
+            v.grad = None
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return sample / statistics.median(times), threads
+
+
+def run_train_section(args, device, world, rank, barrier, peaks):
+    """BASELINE.json configs[2]: training step throughput (samples/s), reported next to the headline line."""
+    import torch.distributed as dist
+    import bdvs_b200 as B
+    import vunet_oracle as O
+    from bdvs_b200 import ops
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = B.VunetAlter(**D256)
+    sd = O.det_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()})
+    model.load_state_dict(sd)
+    model = model.to(device).train()
+    if world > 1:
+        model.enable_data_parallel()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.5, 0.9), fused=True)
+    Bt = TRAIN_BATCH_PER_GPU
+    g = torch.Generator(device=device).manual_seed(1234 + rank)
+    x = torch.rand(Bt, 30, 64, 64, device=device, generator=g) * 2 - 1
+    c = torch.rand(Bt, 3, 256, 256, device=device, generator=g) * 2 - 1
+    target = torch.rand(Bt, 3, 256, 256, device=device, generator=g) * 2 - 1
+    xh, ch, th = (t.cpu().pin_memory() for t in (x, c, target))
+    loss_h = torch.zeros(1).pin_memory()
+
+    def step(xx, cc, tt):
+        imgs, means, logstds, _ = model(xx, cc)
+        loss = torch.mean((imgs - tt) ** 2) + 1e-3 * B.compute_kl_with_prior(means, logstds)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    K = max(5, args.steps // 5)
+    W = 3
+    for _ in range(W):
+        step(x, c, target)
+    barrier()
+    before = ops.LAUNCHES
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(K):
+        loss = step(x, c, target)
+    ev1.record()
+    barrier()
+    launches = ops.LAUNCHES - before
+    ms = ev0.elapsed_time(ev1)
+    # e2e: inputs and target from pinned host memory every step, loss read back every step
+    for _ in range(2):
+        step(x.copy_(xh, non_blocking=True), c.copy_(ch, non_blocking=True), target.copy_(th, non_blocking=True))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        loss = step(x.copy_(xh, non_blocking=True), c.copy_(ch, non_blocking=True), target.copy_(th, non_blocking=True))
+        loss_h.copy_(loss.detach().reshape(1), non_blocking=True)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    value = world * Bt * K / (ms * 1e-3)
+    red = getattr(model, "_vub_reducer", None)
+    out = {
+        "metric": "VUnet 256x256 training throughput (fwd+bwd+all-reduce+Adam)", "value": value, "unit": "samples/s",
+        "steps": K, "warmup": W, "ms_per_step": ms / K, "dtype": "bf16", "scaling": "weak",
+        "config": {"workload": TRAIN_WORKLOAD, "samples_per_gpu_per_step": Bt, "global_batch": Bt * world,
+                   "parallelism": f"dp{world}: batch sharded, one flat-bucket all-reduce per sub-network overlapped "
+                                  "with backward" if world > 1 else "single GPU",
+                   "algorithmic_gflop_per_sample": round(TRAIN_GFLOP_PER_SAMPLE, 3)},
+        "e2e": {"value": world * Bt * K / (ms_e2e * 1e-3), "unit": "samples/s",
+                "h2d_bytes_per_step": (xh.numel() + ch.numel() + th.numel()) * 4, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / K},
+        "gpu_launches": launches,
+        "allreduce_bytes_per_step": getattr(red, "bytes_per_step", 0),
+        "conv_tflops_per_gpu": round(TRAIN_GFLOP_PER_SAMPLE * Bt * K / ms, 2),
+        "frac_tensor_peak_sustained": round(TRAIN_GFLOP_PER_SAMPLE * Bt * K / ms / peaks["bf16_tflops_sustained"], 4),
+        "loss": float(loss),
+    }
+    del model, opt
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_reference(args):
@@ -225,6 +341,14 @@ def run_ours(args):
     h2d = xh.numel() * 4 + ch.numel() * 4
     d2h = oh.numel() * 4
 
+    train = None
+    if not args.no_train:
+        try:
+            train = run_train_section(args, device, world, rank, barrier, peaks)
+        except Exception as exc:  # the headline (synthesis) line must survive a failure of the second workload
+            train = {"error": f"{type(exc).__name__}: {exc}"[:400]}
+            barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -255,6 +379,15 @@ def run_ours(args):
     else:
         roofline = {"bound": "tensor", "achieved": top["tflops"], "peak": peaks["bf16_tflops_sustained"],
                     "unit": "TFLOP/s", "frac": round(top["tflops"] / peaks["bf16_tflops_sustained"], 4), "traffic": None}
+    traffic_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(traffic_path):
+        with open(traffic_path) as f:
+            tr = json.load(f).get(top["kernel"])
+        if tr:  # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture
+            roofline["traffic"] = tr["dram_read"] + tr["dram_write"]
+            roofline["traffic_source"] = "profiles/ncu_traffic.json (ncu --set full, per launch, same workload)"
+    roofline["algorithmic_bytes_per_launch"] = prof[top["kernel"]]["bytes"] / top["launches"]
+    roofline["algorithmic_flops_per_launch"] = prof[top["kernel"]]["flops"] / top["launches"]
     roofline.update({"kernel": top["kernel"], "launches_per_step": top["launches"], "share_of_step": top["share"],
                      "peak_source": peaks["source"] + (" (sustained)" if roofline["bound"] == "tensor" else ""),
                      "avg_launch_ms": round(top["ms"] / top["launches"], 4)})
@@ -270,6 +403,11 @@ def run_ours(args):
         cpu = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "4 frames/iter x 3 iters (+1 warm-up) of the same H256 transfer workload, fp32 torch CPU, "
                          "oracle/vunet_oracle.py (port of the reference's PyTorch path, pinned to reference outputs)"}
+        if isinstance(train, dict) and "value" in train:
+            sps, threads = cpu_port_train_sps(2, iters=2, warmup=1)
+            train["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
+                                     "sample": "2 samples/iter x 2 iters (+1 warm-up) of the same D256 forward+backward, "
+                                               "fp32 torch CPU autograd through oracle/vunet_oracle.py"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -288,6 +426,7 @@ def run_ours(args):
         "whole_step": whole,
         "kernels": kernels,
         "cpu_baseline": cpu,
+        "train": train,
     }
     print(json.dumps(line))
     if world > 1:
@@ -301,6 +440,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step workload (configs[2])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,0 +1,157 @@
+"""GPU (-m gpu): the training half — forward + hand-written backward schedule through the module API,
+against the CPU oracle's autograd on the same hashed inputs and against the gradient fixtures generated
+from the reference (tests/golden/*.pt: loss, per-parameter gradient norms, a few full gradients, the
+set of parameters the reference leaves without gradient).
+
+Tolerance (BASELINE.json north_star): relative L2 <= 1e-2 on the CONCATENATED gradient (bf16 operands,
+fp32 accumulation); single tensors are looser (PyTorch's own bf16 autocast reaches
+1e-2..4e-2 on individual small tensors).
+"""
+import contextlib
+import io
+
+import pytest
+import torch
+
+import vunet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+GRAD_TOL = 1e-2
+ARCH = dict(n_latent_scales=2, conv_layer_type="l1", subpixel_upsampling=True, n_scales=0, nf_start=32, nf_max=128)
+D256 = dict(ARCH, spatial_size=256, bottleneck_factor=2, box_factor=2, n_channels_x=30)
+
+
+def build(cfg):
+    import bdvs_b200 as B
+    cfg = {k: v for k, v in cfg.items() if k != "batch"}
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = B.VunetAlter(**cfg)
+    sd = O.det_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()})
+    m.load_state_dict(sd)
+    return m.cuda().train(), sd
+
+
+def oracle_loss_and_grads(sd, cfg, x, c, eps, target, kl_weight=1e-3):
+    sd_g = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    imgs, means, logstds, _, _ = O.forward(sd_g, x, c, eps)
+    loss = torch.mean((imgs - target) ** 2) + kl_weight * O.compute_kl_with_prior(means, logstds)
+    loss.backward()
+    return float(loss), {k: v.grad for k, v in sd_g.items()}
+
+
+def our_loss_and_grads(m, x, c, eps, target, kl_weight=1e-3):
+    import bdvs_b200 as B
+    imgs, means, logstds, acts = m(x.cuda(), c.cuda(), eps=[e.cuda() for e in eps])
+    assert imgs.requires_grad and means[0].requires_grad and logstds[1].requires_grad
+    loss = torch.mean((imgs - target.cuda()) ** 2) + kl_weight * B.compute_kl_with_prior(means, logstds)
+    loss.backward()
+    torch.cuda.synchronize()
+    return float(loss), {k: (p.grad.detach().float().cpu() if p.grad is not None else None)
+                         for k, p in m.named_parameters()}
+
+
+def concat_rel(got, ref, keys):
+    num = sum(float((got[k] - ref[k]).pow(2).sum()) for k in keys)
+    den = sum(float(ref[k].pow(2).sum()) for k in keys)
+    return (num / den) ** 0.5
+
+
+def check_grads(got, ref, tag):
+    none_ref = sorted(k for k, g in ref.items() if g is None or float(g.abs().max()) == 0.0)
+    none_got = sorted(k for k, g in got.items() if g is None)
+    assert none_got == none_ref, f"{tag}: parameters without gradient differ"
+    keys = [k for k in ref if k not in none_ref]
+    for k in keys:
+        assert torch.isfinite(got[k]).all(), k
+    total = concat_rel(got, ref, keys)
+    per_owner = {o: concat_rel(got, ref, [k for k in keys if k.startswith(o + ".")]) for o in ("eu", "ed", "du", "dd")}
+    worst = max(keys, key=lambda k: float((got[k] - ref[k]).norm() / ref[k].norm().clamp_min(1e-12)))
+    worst_err = float((got[worst] - ref[worst]).norm() / ref[worst].norm().clamp_min(1e-12))
+    print(f"{tag}: concatenated grad rel-L2 {total:.3e}, per sub-network {per_owner}, worst tensor {worst} {worst_err:.3e}")
+    assert total < GRAD_TOL, (tag, total)
+    assert all(v < 2 * GRAD_TOL for v in per_owner.values()), per_owner
+    assert worst_err < 0.15, (worst, worst_err)
+
+
+@pytest.mark.parametrize("name", ["tiny3", "tiny30", "market128"])
+def test_gradients_match_oracle_and_reference_fixture(golden, name):
+    fx = golden(name)
+    cfg = fx["config"]
+    m, sd = build(cfg)
+    x, c, eps, _ = O.make_inputs(cfg, cfg["batch"])
+    target = O.det_uniform("target", (cfg["batch"], 3, cfg["spatial_size"], cfg["spatial_size"]))
+    loss, got = our_loss_and_grads(m, x, c, eps, target)
+    ref_loss, ref = oracle_loss_and_grads(sd, cfg, x, c, eps, target)
+    assert abs(loss - ref_loss) < 2e-2 * abs(ref_loss)
+    assert abs(loss - fx["loss"]) < 2e-2 * abs(fx["loss"])
+    check_grads(got, ref, name)
+    # fixtures from the reference itself
+    assert sorted(k for k, g in got.items() if g is None) == fx["grad_is_none"]
+    num = den = 0.0
+    for k, n_ref in fx["grad_norms"].items():
+        num += (float(got[k].norm()) - n_ref) ** 2
+        den += n_ref ** 2
+    assert (num / den) ** 0.5 < GRAD_TOL
+    for k, g_ref in fx["grad_full"].items():
+        assert float((got[k] - g_ref).norm() / g_ref.norm()) < 5e-2, k
+
+
+def test_gradients_d256_training_config():
+    # BASELINE.json configs[2] (DeepFashion 256x256, 30 appearance channels) at batch 2
+    m, sd = build(D256)
+    x, c, eps, _ = O.make_inputs(D256, 2)
+    target = O.det_uniform("target", (2, 3, 256, 256))
+    loss, got = our_loss_and_grads(m, x, c, eps, target)
+    ref_loss, ref = oracle_loss_and_grads(sd, D256, x, c, eps, target)
+    assert abs(loss - ref_loss) < 2e-2 * abs(ref_loss)
+    check_grads(got, ref, "D256")
+
+
+def test_grad_accumulation_zero_grad_and_optimizer_step(golden):
+    fx = golden("tiny3")
+    cfg = fx["config"]
+    m, sd = build(cfg)
+    x, c, eps, _ = O.make_inputs(cfg, cfg["batch"])
+    target = O.det_uniform("target", (cfg["batch"], 3, cfg["spatial_size"], cfg["spatial_size"]))
+    _, g1 = our_loss_and_grads(m, x, c, eps, target)
+    _, g2 = our_loss_and_grads(m, x, c, eps, target)  # no zero_grad in between: gradients accumulate
+    keys = [k for k, g in g1.items() if g is not None]
+    assert concat_rel(g2, {k: 2 * g1[k] for k in keys}, keys) < 1e-3
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4, betas=(0.5, 0.9))
+    opt.zero_grad()
+    assert all(p.grad is None for p in m.parameters())
+    loss0, g3 = our_loss_and_grads(m, x, c, eps, target)
+    assert concat_rel(g3, g1, keys) < 1e-3  # deterministic up to the order of fp32 atomics
+    before = {k: p.detach().clone() for k, p in m.named_parameters()}
+    opt.step()
+    changed = [k for k, p in m.named_parameters() if not torch.equal(p, before[k])]
+    assert sorted(changed) == sorted(keys)
+    opt.zero_grad()
+    loss1, _ = our_loss_and_grads(m, x, c, eps, target)  # weight-norm prep must have been refreshed
+    assert loss1 < loss0
+    # the same Adam step taken by the CPU oracle (fp32 autograd) lands on the same loss
+    sd_o = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    opt_o = torch.optim.Adam(list(sd_o.values()), lr=1e-4, betas=(0.5, 0.9))
+
+    def oracle_loss():
+        imgs, means, logstds, _, _ = O.forward(sd_o, x, c, eps)
+        return torch.mean((imgs - target) ** 2) + 1e-3 * O.compute_kl_with_prior(means, logstds)
+
+    oracle_loss().backward()
+    opt_o.step()
+    with torch.no_grad():
+        ref1 = float(oracle_loss())
+    assert abs(loss1 - ref1) < 2e-2 * abs(ref1)
+
+
+def test_no_grad_forward_is_unchanged_by_training_mode(golden):
+    fx = golden("tiny3")
+    cfg = fx["config"]
+    m, sd = build(cfg)
+    x, c, eps, _ = O.make_inputs(cfg, cfg["batch"])
+    with torch.no_grad():
+        a = m(x.cuda(), c.cuda(), eps=[e.cuda() for e in eps])[0]
+    b = m(x.cuda(), c.cuda(), eps=[e.cuda() for e in eps])[0]
+    assert not a.requires_grad and b.requires_grad
+    assert torch.equal(a, b.detach())

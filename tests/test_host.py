@@ -118,7 +118,10 @@ def test_library_loads_and_exports_every_symbol():
     assert _native.lib().vub_abi_version() == _native.ABI_VERSION
     # struct mirrors must match the C layout (pointers first, then int32 fields)
     assert ctypes.sizeof(_native.ConvDesc) == 9 * 8 + 11 * 4 + 4  # padded to 8
-    assert ctypes.sizeof(_native.WnEntry) == 8 * 8 + 6 * 4
+    assert ctypes.sizeof(_native.WnEntry) == 8 * 8 + 6 * 4 + 8 + 2 * 4
+    assert ctypes.sizeof(_native.DgradDesc) == 10 * 8 + 9 * 4 + 4  # padded to 8
+    assert ctypes.sizeof(_native.WgradDesc) == 5 * 8 + 10 * 4
+    assert ctypes.sizeof(_native.WnbEntry) == 11 * 8 + 8 * 4
 
 
 def test_bad_arguments_are_reported_not_crashed():
@@ -136,3 +139,17 @@ def test_bad_arguments_are_reported_not_crashed():
     assert lib.vub_stem_fwd(None, None, None, None, None, None, 1, 3, 8, 8, 32, None, None, None) == -1
     assert lib.vub_wn_prep(None, 1, 1, None) == -1
     assert lib.vub_latent_num_partials(2, 128, 4, 4) == 8
+    # training entry points validate before touching the device too
+    assert lib.vub_conv_dgrad(None, None) == -1
+    assert lib.vub_conv_wgrad(None, None) == -1
+    assert lib.vub_wn_bwd(None, 1, 1, 0, None) == -1
+    assert lib.vub_stem_bwd(None, None, 1, 3, 8, 8, 32, None, None, None) == -1
+    assert lib.vub_latent_bwd(None, None, None, None, None, None, 1, 128, 4, 4, None, None) == -1
+    g = _native.DgradDesc()
+    g.dy = 16; g.wd = 16; g.dx[0] = 16
+    g.nsrc, g.c_src, g.batch, g.hin, g.win, g.cout_k, g.ksize, g.stride = 1, 32, 1, 8, 8, 48, 3, 1
+    assert lib.vub_conv_dgrad(ctypes.byref(g), None) == -2  # cout_k 48 not a multiple of 32
+    w = _native.WgradDesc()
+    w.dy = 16; w.x[0] = 16; w.gt = 16; w.dy_sum = 16
+    w.nsrc, w.c_src, w.batch, w.hin, w.win, w.cout_k, w.gt_pitch, w.ksize, w.stride = 1, 32, 1, 8, 8, 64, 32, 3, 1
+    assert lib.vub_conv_wgrad(ctypes.byref(w), None) == -2  # gt_pitch < cout_k
