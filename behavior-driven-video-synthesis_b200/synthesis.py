@@ -47,6 +47,11 @@ class FrameSynthesizer:
         self.graph = None
         self.launches_per_call = 0
         self._out = None
+        # host pipeline (render_host): staging buffers + copy streams so that the host->device copy of batch
+        # k+1 and the device->host copy of batch k-1 overlap the kernels of batch k (PCIe is full duplex)
+        self._depth = 2
+        self._slot = 0
+        self._stage_in = None
         with torch.no_grad():
             model._bank()  # weight-norm preparation happens outside the graph
             side = torch.cuda.Stream(device=self.device)
@@ -80,8 +85,53 @@ class FrameSynthesizer:
         self.c.copy_(c, non_blocking=True)
         return self.run()
 
+    def _init_pipeline(self) -> None:
+        dev = self.device
+        self._stage_in = [(torch.empty_like(self.x), torch.empty_like(self.c)) for _ in range(self._depth)]
+        self._stage_out = [torch.empty_like(self._out) for _ in range(self._depth)]
+        self._h2d = torch.cuda.Stream(device=dev)
+        self._d2h = torch.cuda.Stream(device=dev)
+        mk = lambda: [torch.cuda.Event() for _ in range(self._depth)]  # noqa: E731
+        self._in_ready, self._in_free, self._out_ready, self._out_free = mk(), mk(), mk(), mk()
+        cur = torch.cuda.current_stream(dev)
+        for i in range(self._depth):
+            self._in_free[i].record(cur)
+            self._out_free[i].record(cur)
+
     def render_host(self, x_host: torch.Tensor, c_host: torch.Tensor, out_host: torch.Tensor) -> None:
-        """Host (pinned) buffers in, host (pinned) frames out; asynchronous on the current stream."""
-        self.x.copy_(x_host, non_blocking=True)
-        self.c.copy_(c_host, non_blocking=True)
-        out_host.copy_(self.run(), non_blocking=True)
+        """Host (pinned) buffers in, host (pinned) frames out.  Asynchronous and pipelined over consecutive
+        calls: copies run on their own streams through double-buffered staging tensors, the kernels on the
+        current stream.  ``out_host`` is valid after :meth:`join` + a stream/device synchronize (or after the
+        next-but-one call has been synchronized); ``x_host`` / ``c_host`` may be refilled once the call after
+        the next has been issued, or after :meth:`join`."""
+        if self._stage_in is None:
+            self._init_pipeline()
+        i = self._slot
+        self._slot = (i + 1) % self._depth
+        cur = torch.cuda.current_stream(self.device)
+        sx, sc = self._stage_in[i]
+        self._h2d.wait_event(self._in_free[i])          # kernels of the previous user of this slot have read it
+        with torch.cuda.stream(self._h2d):
+            sx.copy_(x_host, non_blocking=True)
+            sc.copy_(c_host, non_blocking=True)
+            self._in_ready[i].record(self._h2d)
+        cur.wait_event(self._in_ready[i])
+        self.x.copy_(sx, non_blocking=True)              # device-to-device into the graph's static inputs
+        self.c.copy_(sc, non_blocking=True)
+        self._in_free[i].record(cur)
+        out = self.run()
+        cur.wait_event(self._out_free[i])                # the previous download from this slot has finished
+        so = self._stage_out[i]
+        so.copy_(out, non_blocking=True)
+        self._out_ready[i].record(cur)
+        self._d2h.wait_event(self._out_ready[i])
+        with torch.cuda.stream(self._d2h):
+            out_host.copy_(so, non_blocking=True)
+            self._out_free[i].record(self._d2h)
+
+    def join(self) -> None:
+        """Make the current stream wait for every copy issued by :meth:`render_host`."""
+        if self._stage_in is not None:
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_stream(self._h2d)
+            cur.wait_stream(self._d2h)
