@@ -34,6 +34,7 @@ EXPORTED_SYMBOLS = (
     "vub_nchw_f32_to_nhwc_bf16_pad",
     "vub_conv_dgrad",
     "vub_conv_wgrad",
+    "vub_conv_wgrad_splits",
     "vub_wn_bwd",
     "vub_stem_bwd",
     "vub_latent_bwd",
@@ -121,6 +122,9 @@ class WgradDesc(C.Structure):
         ("x", C.c_void_p * 2),
         ("gt", C.c_void_p),
         ("dy_sum", C.c_void_p),
+        ("split_stride", C.c_int64),
+        ("sum_stride", C.c_int32),
+        ("n_split", C.c_int32),
         ("nsrc", C.c_int32),
         ("c_src", C.c_int32),
         ("batch", C.c_int32),
@@ -156,6 +160,9 @@ class WnbEntry(C.Structure):
         ("gt_pitch", C.c_int32),
         ("gt_col0", C.c_int32),
         ("row_start", C.c_int32),
+        ("n_split", C.c_int32),
+        ("split_stride", C.c_int64),
+        ("sum_stride", C.c_int32),
         ("pad", C.c_int32),
     ]
 
@@ -200,6 +207,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.vub_nchw_f32_to_nhwc_bf16_pad.argtypes = [fp, i32, i32, i32, i32, i32, vp, vp]
     lib.vub_conv_dgrad.restype = C.c_int
     lib.vub_conv_dgrad.argtypes = [C.POINTER(DgradDesc), vp]
+    lib.vub_conv_wgrad_splits.restype = i32
+    lib.vub_conv_wgrad_splits.argtypes = [C.POINTER(WgradDesc)]
     lib.vub_conv_wgrad.restype = C.c_int
     lib.vub_conv_wgrad.argtypes = [C.POINTER(WgradDesc), vp]
     lib.vub_wn_bwd.restype = C.c_int

@@ -42,10 +42,12 @@ __device__ __forceinline__ float2 block_sum2(float a, float b, float2* red /*[32
 // Weight-norm / affine parameter gradients: one block per output channel of any layer.
 // ------------------------------------------------------------------------------------------------
 constexpr int kWnbThreads = 128;
+constexpr int kWnbMaxLen = 2304;  // cin * k * k of the largest layer (256 x 3 x 3)
 
 __global__ void __launch_bounds__(kWnbThreads)
     wn_bwd_kernel(const vub_wnb_entry* __restrict__ table, int n_entries, int accumulate) {
   __shared__ float2 red[32];
+  __shared__ float g_s[kWnbMaxLen];  // this channel's correlation, summed over the pixel splits, in weight order
   const int row = blockIdx.x;
   int lo = 0, hi = n_entries - 1;
   while (lo < hi) {
@@ -58,15 +60,20 @@ __global__ void __launch_bounds__(kWnbThreads)
   if (co >= e.cout) return;
   const int len = e.cin * e.ktaps;
   const float* v = e.v + (size_t)co * len;
-  const float* gcol = e.gt + e.gt_col0 + co;
-  // correlation element of weight index i = (ci, tap): row (src*ktaps + tap)*c_src + cs of gt
-  auto g_at = [&](int i) {
-    const int ci = i / e.ktaps;
-    const int tap = i - ci * e.ktaps;
-    const int src = ci / e.c_src;
-    const int cs = ci - src * e.c_src;
-    return gcol[(size_t)((src * e.ktaps + tap) * e.c_src + cs) * e.gt_pitch];
-  };
+  const float* grow = e.gt + (size_t)(e.gt_col0 + co) * e.gt_pitch;
+  // sum the pixel splits (coalesced along k), stored at the weight index i = (ci, tap) of column
+  // k = (src*ktaps + tap)*c_src + cs
+  for (int k = threadIdx.x; k < len; k += kWnbThreads) {
+    float g = 0.f;
+    for (int sidx = 0; sidx < e.n_split; ++sidx) g += grow[(size_t)sidx * e.split_stride + k];
+    const int cs = k % e.c_src;
+    const int t = k / e.c_src;
+    const int tap = t % e.ktaps;
+    const int src = t / e.ktaps;
+    g_s[(src * e.c_src + cs) * e.ktaps + tap] = g;
+  }
+  __syncthreads();
+  auto g_at = [&](int i) { return g_s[i]; };
   float ss = 0.f, vg = 0.f;
   for (int i = threadIdx.x; i < len; i += kWnbThreads) {
     const float x = v[i];
@@ -77,7 +84,8 @@ __global__ void __launch_bounds__(kWnbThreads)
   const float inv = 1.0f / sqrtf(r.x);
   const float dot = r.y * inv;  // v_hat . G
   const float ga = e.gamma[co], gg = e.g[co], bi = e.bias[co];
-  const float S = e.dy_sum[e.gt_col0 + co];
+  float S = 0.f;
+  for (int sidx = 0; sidx < e.n_split; ++sidx) S += e.dy_sum[(size_t)sidx * e.sum_stride + e.gt_col0 + co];
   const float k = ga * gg * inv;
   float* dv = e.d_v + (size_t)co * len;
   for (int i = threadIdx.x; i < len; i += kWnbThreads) {
@@ -101,56 +109,75 @@ __global__ void __launch_bounds__(kWnbThreads)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Stem correlation: gt[ci][co] += sum_pix x[n, ci, pix] * dy[n, pix, co];  dy_sum[co] += sum dy.
-// 256 threads = 32 output channels x 8 input-channel groups; 64-pixel chunks staged in shared memory
-// (x coalesced along pixels per channel plane, dy as contiguous 64-byte / 128-byte pixel rows).
+// Stem correlation: gt[co][ci] += sum_pix x[n, ci, pix] * dy[n, pix, co];  dy_sum[co] += sum dy.
+// One warp per 32-pixel chunk: lane l holds x[ci][p0 + l] for every input channel (coalesced 128-byte
+// loads per channel plane) and owns output channel(s) l (COUT/32 per lane); the chunk's dy rows
+// (32 x COUT bf16, contiguous) are staged in shared memory with 16-byte loads; per pixel the x values are
+// broadcast with warp shuffles.  Accumulators live in registers over the warp's whole pixel range; one
+// shared-memory reduction per block and one red.global.add per (ci, co) and block at the end.
 // ------------------------------------------------------------------------------------------------
 constexpr int kSbThreads = 256;
-constexpr int kSbPix = 64;
-constexpr int kSbMaxCx = 64;
+constexpr int kSbWarps = kSbThreads / 32;
+constexpr int kSbPix = 32;
+constexpr int kSbMaxCx = 32;
 
-template <int COUT>
+template <int COUT, int CXMAX>
 __global__ void __launch_bounds__(kSbThreads)
     stem_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int cx, int hw,
                     long long n_chunks, float* __restrict__ gt, float* __restrict__ dy_sum) {
-  constexpr int NG = kSbThreads / COUT;        // input-channel groups
-  constexpr int MAXA = kSbMaxCx / NG + 1;
-  __shared__ float xs[kSbMaxCx][kSbPix + 1];
-  __shared__ float ds[kSbPix][COUT + 1];
-  const int co = threadIdx.x % COUT, grp = threadIdx.x / COUT;
-  float acc[MAXA];
+  constexpr int PER = COUT / 32;
+  __shared__ __align__(16) __nv_bfloat16 ds[kSbWarps][kSbPix * COUT];
+  __shared__ float red[CXMAX + 1][COUT];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[CXMAX][PER];
+  float sdy[PER];
 #pragma unroll
-  for (int k = 0; k < MAXA; ++k) acc[k] = 0.f;
-  float sdy = 0.f;
+  for (int t = 0; t < PER; ++t) {
+    sdy[t] = 0.f;
+#pragma unroll
+    for (int ci = 0; ci < CXMAX; ++ci) acc[ci][t] = 0.f;
+  }
+  for (int i = threadIdx.x; i < (CXMAX + 1) * COUT; i += kSbThreads) (&red[0][0])[i] = 0.f;
   const int chunks_per_img = hw / kSbPix;
-  for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+  for (long long ch = (long long)blockIdx.x * kSbWarps + warp; ch < n_chunks; ch += (long long)gridDim.x * kSbWarps) {
     const long long n = ch / chunks_per_img;
     const int p0 = static_cast<int>(ch - n * chunks_per_img) * kSbPix;
-    for (int i = threadIdx.x; i < cx * kSbPix; i += kSbThreads) {
-      const int ci = i / kSbPix, pp = i - ci * kSbPix;
-      xs[ci][pp] = __ldg(x + (n * cx + ci) * hw + p0 + pp);
-    }
-    const __nv_bfloat16* dp = dy + (n * hw + p0) * COUT;
-    for (int i = threadIdx.x; i < kSbPix * COUT; i += kSbThreads) ds[i / COUT][i % COUT] = __bfloat162float(dp[i]);
-    __syncthreads();
-#pragma unroll 4
-    for (int pp = 0; pp < kSbPix; ++pp) {
-      const float d = ds[pp][co];
-      if (grp == 0) sdy += d;
+    float xr[CXMAX];
 #pragma unroll
-      for (int k = 0; k < MAXA; ++k) {
-        const int ci = grp + k * NG;
-        if (ci < cx) acc[k] = fmaf(xs[ci][pp], d, acc[k]);
+    for (int ci = 0; ci < CXMAX; ++ci) xr[ci] = ci < cx ? __ldg(x + (n * cx + ci) * hw + p0 + lane) : 0.f;
+    const uint4* src = reinterpret_cast<const uint4*>(dy + (n * hw + p0) * COUT);
+    uint4* dst = reinterpret_cast<uint4*>(ds[warp]);
+#pragma unroll
+    for (int k = 0; k < COUT / 8; ++k) dst[lane + 32 * k] = __ldg(src + lane + 32 * k);
+    __syncwarp();
+#pragma unroll 4
+    for (int j = 0; j < kSbPix; ++j) {
+      float d[PER];
+#pragma unroll
+      for (int t = 0; t < PER; ++t) {
+        d[t] = __bfloat162float(ds[warp][j * COUT + lane * PER + t]);
+        sdy[t] += d[t];
+      }
+#pragma unroll
+      for (int ci = 0; ci < CXMAX; ++ci) {
+        const float xv = __shfl_sync(0xffffffffu, xr[ci], j);
+#pragma unroll
+        for (int t = 0; t < PER; ++t) acc[ci][t] = fmaf(xv, d[t], acc[ci][t]);
       }
     }
-    __syncthreads();
+    __syncwarp();
   }
+  __syncthreads();
 #pragma unroll
-  for (int k = 0; k < MAXA; ++k) {
-    const int ci = grp + k * NG;
-    if (ci < cx) atomicAdd(gt + ci * COUT + co, acc[k]);
+  for (int t = 0; t < PER; ++t) {
+#pragma unroll
+    for (int ci = 0; ci < CXMAX; ++ci)
+      if (ci < cx) atomicAdd(&red[ci][lane * PER + t], acc[ci][t]);
+    atomicAdd(&red[CXMAX][lane * PER + t], sdy[t]);
   }
-  if (grp == 0) atomicAdd(dy_sum + co, sdy);
+  __syncthreads();
+  for (int i = threadIdx.x; i < cx * COUT; i += kSbThreads) atomicAdd(gt + i, red[i % cx][i / cx]);  // gt[co][ci]
+  for (int i = threadIdx.x; i < COUT; i += kSbThreads) atomicAdd(dy_sum + i, red[CXMAX][i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -245,14 +272,19 @@ extern "C" int vub_stem_bwd(const float* x_nchw, const void* dy_nhwc, int32_t ba
     return fail(VUB_E_SHAPE, "stem_bwd: batch %d cx %d h %d w %d (cx <= %d, h*w %% %d == 0)", batch, cx, h, w,
                 kSbMaxCx, kSbPix);
   const long long n_chunks = (long long)batch * (hw / kSbPix);
-  const unsigned grid = static_cast<unsigned>(n_chunks < 148 * 4 ? n_chunks : 148 * 4);
+  const long long blocks = (n_chunks + kSbWarps - 1) / kSbWarps;
+  const unsigned grid = static_cast<unsigned>(blocks < 148 * 4 ? blocks : 148 * 4);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (cout == 32)
-    stem_bwd_kernel<32><<<grid, kSbThreads, 0, s>>>(x_nchw, static_cast<const __nv_bfloat16*>(dy_nhwc), cx,
-                                                    static_cast<int>(hw), n_chunks, gt, dy_sum);
+  const __nv_bfloat16* dyp = static_cast<const __nv_bfloat16*>(dy_nhwc);
+  const int hwi = static_cast<int>(hw);
+  if (cout == 32 && cx <= 4)
+    stem_bwd_kernel<32, 4><<<grid, kSbThreads, 0, s>>>(x_nchw, dyp, cx, hwi, n_chunks, gt, dy_sum);
+  else if (cout == 32)
+    stem_bwd_kernel<32, kSbMaxCx><<<grid, kSbThreads, 0, s>>>(x_nchw, dyp, cx, hwi, n_chunks, gt, dy_sum);
+  else if (cout == 64 && cx <= 4)
+    stem_bwd_kernel<64, 4><<<grid, kSbThreads, 0, s>>>(x_nchw, dyp, cx, hwi, n_chunks, gt, dy_sum);
   else if (cout == 64)
-    stem_bwd_kernel<64><<<grid, kSbThreads, 0, s>>>(x_nchw, static_cast<const __nv_bfloat16*>(dy_nhwc), cx,
-                                                    static_cast<int>(hw), n_chunks, gt, dy_sum);
+    stem_bwd_kernel<64, kSbMaxCx><<<grid, kSbThreads, 0, s>>>(x_nchw, dyp, cx, hwi, n_chunks, gt, dy_sum);
   else
     return fail(VUB_E_SHAPE, "stem_bwd: cout %d not in {32,64}", cout);
   return check_launch("stem_bwd");

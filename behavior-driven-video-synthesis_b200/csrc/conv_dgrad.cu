@@ -17,8 +17,12 @@
 #include <cstring>
 
 #include "common.h"
+#include "conv_slab.cuh"
 #include "conv_tiles.cuh"
 
+namespace vub {
+bool conv_rows_dgrad(const vub_dgrad_desc* d, cudaStream_t stream, int* rc);  // conv_rows.cu
+}
 using namespace vub;
 
 extern "C" int vub_conv_dgrad(const vub_dgrad_desc* d, void* stream_v) {
@@ -70,6 +74,32 @@ extern "C" int vub_conv_dgrad(const vub_dgrad_desc* d, void* stream_v) {
     e.out_c = C;
     e.pix_stride = 1;
     e.n_valid = C;
+  }
+
+  {  // HBM-bound wide, thin layers: row-streaming kernel in data-gradient mode
+    int rrc = 0;
+    if (conv_rows_dgrad(d, stream, &rrc)) return rrc;
+  }
+
+  if (d->stride == 1 && !d2s && d->ksize == 3 && (d->nsrc == 1 || C % 128 == 0) &&
+      conv_slab_shape_ok(cout_k, d->hin, d->win, d->nsrc * C)) {
+    // same shapes as the forward slab kernel with the channel roles swapped: A = dy, taps mirrored
+    SlabJob sj;
+    memset(&sj, 0, sizeof(sj));
+    sj.x[0] = d->dy;
+    sj.nsrc = 1;
+    sj.c_src = cout_k;
+    sj.batch = d->batch;
+    sj.h = d->hin;
+    sj.w = d->win;
+    sj.w_packed = d->wd;
+    sj.ktot = (long long)taps * cout_k;
+    sj.n_total = d->nsrc * C;
+    sj.flip = 1;
+    sj.n_split = d->nsrc == 2 ? C : 0;
+    sj.epi[0] = job.epi[0];
+    sj.epi[1] = job.epi[1];
+    return conv_slab_launch(sj, stream);
   }
 
   if (d->stride == 1) {

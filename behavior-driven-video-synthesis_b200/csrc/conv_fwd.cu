@@ -25,6 +25,7 @@
 
 #include "common.h"
 #include "conv_epilogue.cuh"
+#include "conv_slab.cuh"
 #include "conv_tiles.cuh"
 #include "ptx.cuh"
 
@@ -341,6 +342,36 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
     if (q && !aligned16(q)) return fail(VUB_E_ALIGN, "conv_fwd: pointer %p not 16B aligned", q);
 
   if (conv_rows_applicable(d)) return conv_rows_launch(d, static_cast<cudaStream_t>(stream_v));
+
+  // tensor-core-bound 3x3 layers at 64x64 / 32x32: activation-slab kernel (A and weight reuse in smem)
+  if (d->ksize == 3 && d->stride == 1 && d->stages >= 0 && !f32 && conv_slab_shape_ok(d->c_src, d->hin, d->win, cout)) {
+    SlabJob job;
+    memset(&job, 0, sizeof(job));
+    job.x[0] = d->x[0];
+    job.x[1] = d->x[1];
+    job.nsrc = d->nsrc;
+    job.c_src = d->c_src;
+    job.batch = d->batch;
+    job.h = d->hin;
+    job.w = d->win;
+    job.w_packed = d->w;
+    job.ktot = (long long)d->nsrc * 9 * d->c_src;
+    job.n_total = cout;
+    TileEpi& e = job.epi[0];
+    e.scale = d->scale;
+    e.shift = d->shift;
+    e.addend = static_cast<const __nv_bfloat16*>(d->residual);
+    e.out_raw = static_cast<__nv_bfloat16*>(d->out_raw);
+    e.out_elu = static_cast<__nv_bfloat16*>(d->out_elu);
+    const bool d2s_ = (f & VUB_CONV_D2S) != 0;
+    e.out_h = d2s_ ? 2 * hout : hout;
+    e.out_w = d2s_ ? 2 * wout : wout;
+    e.out_c = d2s_ ? cout / 4 : cout;
+    e.pix_stride = 1;
+    e.n_valid = d->cout_valid;
+    e.flags = f;
+    return conv_slab_launch(job, static_cast<cudaStream_t>(stream_v));
+  }
 
   // Measured at 64 frames (profiles/r01_tiles_vs_pertap.log): the persistent tile kernel wins for the
   // stride-2 and N >= 256 (up-sampling / latent) layers, the two-CTAs-per-SM per-tap kernel below for the

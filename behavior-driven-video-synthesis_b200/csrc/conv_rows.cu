@@ -24,7 +24,9 @@
 
 #include "common.h"
 #include "conv_epilogue.cuh"
+#include "conv_tiles.cuh"
 #include "ptx.cuh"
+#include "tile_epilogue.cuh"
 
 namespace vub {
 
@@ -41,6 +43,13 @@ struct RowsKParams {
   int strips_w;         // wout / 128
   long long total_rows; // strips_w * batch * hout: output rows of 128 pixels, the unit of work
   int ring;             // row-buffer ring slots
+  // data-gradient mode (vub_conv_dgrad on the wide, thin layers): taps mirrored, mode-driven shared epilogue
+  // (ELU' mask, two addends); with two halves the accumulator columns [0, BN/2) and [BN/2, BN) go to the two
+  // sources of a concat.
+  int flip;
+  int n_halves;         // 0 = forward epilogue (ep), 1 or 2 = data-gradient epilogue (bwd[])
+  int stage_tiles;      // staging tiles per epilogue warp in data-gradient mode
+  TileEpi bwd[2];
 };
 
 template <int BKC>
@@ -148,8 +157,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
     tmem_relinquish();
   }
   for (int i = threadIdx.x; i < BN; i += kRowsThreads) {
-    s_scale[i] = p.ep.scale[i];
-    s_shift[i] = p.ep.shift[i];
+    s_scale[i] = p.ep.scale != nullptr ? p.ep.scale[i] : 1.0f;
+    s_shift[i] = p.ep.shift != nullptr ? p.ep.shift[i] : 0.0f;
   }
   tc_fence_before();
   __syncthreads();
@@ -232,14 +241,15 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
 #pragma unroll
             for (int r = 0; r < kdim; ++r) {
               const uint32_t a_lo = ring_lo + sl[r] * slot_units + s * (SRC_BYTES >> 4);
-              const uint32_t b_lo = w_lo + (s * NTAPS + r * kdim) * (WT_BYTES >> 4);
 #pragma unroll
               for (int q = 0; q < kdim; ++q) {
+                // data gradient: the geometric tap (r, q) carries the weights of the mirrored tap
+                const int wt = p.flip ? (NTAPS - 1) - (r * kdim + q) : r * kdim + q;
+                const uint32_t b_lo = w_lo + (s * NTAPS + wt) * (WT_BYTES >> 4);
 #pragma unroll
                 for (int j = 0; j < BKC / 16; ++j)
                   umma_bf16(d_tmem, umma_desc_join(desc_hi, a_lo + q * (ROWB >> 4) + 2 * j),
-                            umma_desc_join(desc_hi, b_lo + q * (WT_BYTES >> 4) + 2 * j), idesc,
-                            (s | r | q | j) != 0 ? 1u : 0u);
+                            umma_desc_join(desc_hi, b_lo + 2 * j), idesc, (s | r | q | j) != 0 ? 1u : 0u);
               }
             }
           }
@@ -281,6 +291,33 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
     RowWalker cur, ahead;  // `ahead` runs two rows in front (this warpgroup's next row)
     cur.init(g_begin, g_end, p.ep.hout, p.batch);
     if (g == 1 && cur.valid()) cur.next_row();
+    if constexpr (BN == 32 || BN == 64) {
+      if (p.n_halves > 0) {
+        // ---- data-gradient mode: the shared mode-driven epilogue, one 128-pixel row = one tile ----
+        const EpiGeom gm{kRowsW, 1, 7, 0, p.batch};
+        const uint32_t b0 = smem_u32(staging) + (warp - 2) * p.stage_tiles * EpiStage<32>::TILE_BYTES;
+        const uint32_t b1 = b0 + EpiStage<32>::TILE_BYTES, b2 = b1 + EpiStage<32>::TILE_BYTES;
+        uint32_t cntb = 0;
+        while (cur.valid()) {
+          mbar_wait(&acc_full[g], cntb & 1);
+          tc_fence_after();
+          if (p.n_halves == 1) {
+            tile_epilogue_staged<BN, 32>(p.bwd[0], gm, s_scale, s_shift, trow, b0, b1, b2, lane, q, 0, cur.n, cur.h,
+                                         cur.w0, &acc_empty[g]);
+          } else {
+            if constexpr (BN == 64) {
+              tile_epilogue_staged<32, 32>(p.bwd[0], gm, s_scale, s_shift, trow, b0, b1, b2, lane, q, 0, cur.n, cur.h,
+                                           cur.w0, nullptr);
+              tile_epilogue_staged<32, 32>(p.bwd[1], gm, s_scale + 32, s_shift + 32, trow + 32, b0, b1, b2, lane, q, 0,
+                                           cur.n, cur.h, cur.w0, &acc_empty[g]);
+            }
+          }
+          ++cntb;
+          cur.next_row();
+          if (cur.valid()) cur.next_row();
+        }
+      }
+    }
     ahead = cur;
     if (STAGED && has_res && bf16_out && cur.valid()) prefetch_res(cur);
     uint32_t cnt = 0;  // rows this warpgroup has processed (its TMEM buffer's phase counter)
@@ -387,68 +424,72 @@ static size_t rows_staging_bytes(int bn) {
   return (bn >= 32 && bn <= 64) ? (size_t)8 * 2 * 32 * (bn * 2 + 16) : 0;
 }
 
-// Returns true when the row-streaming kernel covers this (already validated) descriptor.
-bool conv_rows_applicable(const vub_conv_desc* d) {
-  const int disabled = env_int("VUB_DISABLE_ROWS", 0);
-  if (disabled || d->stages < 0) return false;
-  if (d->stride != 1 || d->win < kRowsW || d->hin < 2 || d->c_src > 64 || d->cout > 128) return false;
-  if (d->c_src == 32 && d->cout > 64) return false;
-  const int bkc = d->c_src;  // one channel block per source
-  const int taps = d->ksize * d->ksize;
-  const size_t wbytes = (size_t)d->nsrc * taps * d->cout * bkc * 2;
-  const size_t slot = (size_t)d->nsrc * (bkc == 64 ? 136 * 128 : 144 * 64);
+// One launch of the row-streaming kernel, forward or data-gradient mode.
+struct RowsJob {
+  const void* x[2];     // A sources, NHWC bf16 [batch, h, w, c_src]
+  int nsrc, c_src;
+  int batch, h, w;
+  const void* w_packed; // [bn rows][nsrc * taps * c_src] bf16
+  int bn, taps;
+  EpiParams ep;         // forward epilogue (scale / shift always come from here; may be NULL = identity)
+  int flip, n_halves, stage_tiles;
+  TileEpi bwd[2];
+};
+
+static bool rows_shape_ok(int nsrc, int c_src, int bn, int taps, int h, int w, size_t staging) {
+  if (env_int("VUB_DISABLE_ROWS", 0)) return false;
+  if (w < kRowsW || h < 2 || c_src > 64 || bn > 128) return false;
+  if (c_src == 32 && bn > 64) return false;
+  const size_t wbytes = (size_t)nsrc * taps * bn * c_src * 2;
+  const size_t slot = (size_t)nsrc * (c_src == 64 ? 136 * 128 : 144 * 64);
   const int min_ring = taps == 9 ? 4 : 2;
-  return wbytes + min_ring * slot + rows_staging_bytes(d->cout) + 2048 <= 224 * 1024;
+  return wbytes + min_ring * slot + staging + 2048 <= 224 * 1024;
 }
 
-int conv_rows_launch(const vub_conv_desc* d, cudaStream_t stream) {
-  const int bkc = d->c_src;
-  const int taps = d->ksize * d->ksize;
-  const int bn = d->cout;
+static int rows_job_launch(const RowsJob& j, cudaStream_t stream) {
+  const int bkc = j.c_src;
   RowsKParams kp;
   memset(&kp, 0, sizeof(kp));
-  kp.ep.scale = d->scale;
-  kp.ep.shift = d->shift;
-  kp.ep.residual = static_cast<const __nv_bfloat16*>(d->residual);
-  kp.ep.out_raw = static_cast<__nv_bfloat16*>(d->out_raw);
-  kp.ep.out_elu = static_cast<__nv_bfloat16*>(d->out_elu);
-  kp.ep.out_f32 = static_cast<float*>(d->out_f32);
-  kp.ep.hout = d->hin;
-  kp.ep.wout = d->win;
-  kp.ep.cout = d->cout;
-  kp.ep.cout_valid = d->cout_valid;
-  kp.ep.flags = d->flags;
-  kp.batch = d->batch;
-  kp.nsrc = d->nsrc;
-  kp.ntaps = taps;
-  kp.strips_w = d->win / kRowsW;
-  kp.total_rows = (long long)kp.strips_w * d->batch * d->hin;
-  const size_t wbytes = (size_t)d->nsrc * taps * bn * bkc * 2;
-  const size_t slot = (size_t)d->nsrc * (bkc == 64 ? 136 * 128 : 144 * 64);
+  kp.ep = j.ep;
+  kp.ep.hout = j.h;
+  kp.ep.wout = j.w;
+  kp.batch = j.batch;
+  kp.nsrc = j.nsrc;
+  kp.ntaps = j.taps;
+  kp.strips_w = j.w / kRowsW;
+  kp.total_rows = (long long)kp.strips_w * j.batch * j.h;
+  kp.flip = j.flip;
+  kp.n_halves = j.n_halves;
+  kp.stage_tiles = j.stage_tiles;
+  kp.bwd[0] = j.bwd[0];
+  kp.bwd[1] = j.bwd[1];
+  const size_t wbytes = (size_t)j.nsrc * j.taps * j.bn * bkc * 2;
+  const size_t slot = (size_t)j.nsrc * (bkc == 64 ? 136 * 128 : 144 * 64);
   const int ring_env = env_int("VUB_ROWS_RING", 0);
-  const size_t staging = rows_staging_bytes(bn);
+  size_t staging = rows_staging_bytes(j.bn);
+  if (j.n_halves > 0) staging = (size_t)8 * j.stage_tiles * EpiStage<32>::TILE_BYTES;
   int ring = static_cast<int>((216 * 1024 - wbytes - staging) / slot);
   if (ring_env > 0) ring = ring_env;
-  const int min_ring = taps == 9 ? 4 : 2;
+  const int min_ring = j.taps == 9 ? 4 : 2;
   if (ring > kRowsMaxRing) ring = kRowsMaxRing;
   if (ring < min_ring) ring = min_ring;
   kp.ring = ring;
   const size_t smem = wbytes + ring * slot + staging + 1024;
 
-  const uint64_t C = d->c_src, Hin = d->hin, Win = d->win, B = d->batch;
+  const uint64_t C = j.c_src, Hin = j.h, Win = j.w, B = j.batch;
   const uint64_t dims[4] = {C, Win, Hin, B};
   const uint64_t strides[3] = {C * 2, Win * C * 2, Hin * Win * C * 2};
-  const uint32_t boxA[4] = {(uint32_t)bkc, (uint32_t)(kRowsW + (taps == 9 ? 2 : 0)), 1u, 1u};
+  const uint32_t boxA[4] = {(uint32_t)bkc, (uint32_t)(kRowsW + (j.taps == 9 ? 2 : 0)), 1u, 1u};
   int rc;
-  for (int s = 0; s < d->nsrc; ++s) {
-    rc = encode_tmap_bf16(&kp.tmA[s], d->x[s], 4, dims, strides, boxA, bkc * 2, false);
+  for (int s = 0; s < j.nsrc; ++s) {
+    rc = encode_tmap_bf16(&kp.tmA[s], j.x[s], 4, dims, strides, boxA, bkc * 2, false);
     if (rc) return rc;
   }
-  const uint64_t ktot = (uint64_t)d->nsrc * taps * bkc;
-  const uint64_t dimsb[2] = {ktot, (uint64_t)d->cout};
+  const uint64_t ktot = (uint64_t)j.nsrc * j.taps * bkc;
+  const uint64_t dimsb[2] = {ktot, (uint64_t)j.bn};
   const uint64_t stridesb[1] = {ktot * 2};
-  const uint32_t boxB[2] = {(uint32_t)bkc, (uint32_t)bn};
-  rc = encode_tmap_bf16(&kp.tmB, d->w, 2, dimsb, stridesb, boxB, bkc * 2, true);
+  const uint32_t boxB[2] = {(uint32_t)bkc, (uint32_t)j.bn};
+  rc = encode_tmap_bf16(&kp.tmB, j.w_packed, 2, dimsb, stridesb, boxB, bkc * 2, true);
   if (rc) return rc;
 
   static int n_sm = 0;
@@ -463,6 +504,7 @@ int conv_rows_launch(const vub_conv_desc* d, cudaStream_t stream) {
   long long want = kp.total_rows / 2 < n_sm ? kp.total_rows / 2 : n_sm;
   if (grid_env > 0) want = grid_env;
   const int grid = want < 1 ? 1 : static_cast<int>(want);
+  const int bn = j.bn;
 #define VUB_ROWS_DISPATCH(BN_, BKC_) \
   if (bn == BN_ && bkc == BKC_) return launch_rows<BN_, BKC_>(kp, grid, smem, stream);
   VUB_ROWS_DISPATCH(16, 32)
@@ -474,6 +516,87 @@ int conv_rows_launch(const vub_conv_desc* d, cudaStream_t stream) {
   VUB_ROWS_DISPATCH(128, 64)
 #undef VUB_ROWS_DISPATCH
   return fail(VUB_E_SHAPE, "conv_rows: no kernel for BN %d BKC %d", bn, bkc);
+}
+
+// Returns true when the row-streaming kernel covers this (already validated) descriptor.
+bool conv_rows_applicable(const vub_conv_desc* d) {
+  if (d->stages < 0 || d->stride != 1) return false;
+  return rows_shape_ok(d->nsrc, d->c_src, d->cout, d->ksize * d->ksize, d->hin, d->win, rows_staging_bytes(d->cout));
+}
+
+int conv_rows_launch(const vub_conv_desc* d, cudaStream_t stream) {
+  RowsJob j;
+  memset(&j, 0, sizeof(j));
+  j.x[0] = d->x[0];
+  j.x[1] = d->x[1];
+  j.nsrc = d->nsrc;
+  j.c_src = d->c_src;
+  j.batch = d->batch;
+  j.h = d->hin;
+  j.w = d->win;
+  j.w_packed = d->w;
+  j.bn = d->cout;
+  j.taps = d->ksize * d->ksize;
+  j.ep.scale = d->scale;
+  j.ep.shift = d->shift;
+  j.ep.residual = static_cast<const __nv_bfloat16*>(d->residual);
+  j.ep.out_raw = static_cast<__nv_bfloat16*>(d->out_raw);
+  j.ep.out_elu = static_cast<__nv_bfloat16*>(d->out_elu);
+  j.ep.out_f32 = static_cast<float*>(d->out_f32);
+  j.ep.cout = d->cout;
+  j.ep.cout_valid = d->cout_valid;
+  j.ep.flags = d->flags;
+  return rows_job_launch(j, stream);
+}
+
+// Data gradient of a stride-1 conv on the wide, thin layers (dy has 32 or 64 channels, width >= 128):
+// returns true and sets *rc when the row-streaming kernel took the job (one launch per <= 64 output columns).
+bool conv_rows_dgrad(const vub_dgrad_desc* d, cudaStream_t stream, int* rc) {
+  const int C = d->c_src, taps = d->ksize * d->ksize;
+  if (d->stride != 1 || (d->flags & VUB_CONV_D2S) || (d->cout_k != 32 && d->cout_k != 64) || (C != 32 && C != 64))
+    return false;
+  bool any_addend2 = false;
+  for (int s = 0; s < d->nsrc; ++s) any_addend2 = any_addend2 || d->addend2[s] != nullptr;
+  const int stage_tiles = any_addend2 ? 3 : 2;
+  const size_t staging = (size_t)8 * stage_tiles * EpiStage<32>::TILE_BYTES;
+  const bool merged = d->nsrc * C <= 64;  // both halves of a concat in one launch (N = 64)
+  const int bn = merged ? d->nsrc * C : C;
+  if (!rows_shape_ok(1, d->cout_k, bn, taps, d->hin, d->win, staging)) return false;
+  const int n_launch = merged ? 1 : d->nsrc;
+  for (int l = 0; l < n_launch; ++l) {
+    RowsJob j;
+    memset(&j, 0, sizeof(j));
+    j.x[0] = d->dy;
+    j.nsrc = 1;
+    j.c_src = d->cout_k;
+    j.batch = d->batch;
+    j.h = d->hin;
+    j.w = d->win;
+    j.w_packed = static_cast<const char*>(d->wd) + (size_t)l * C * taps * d->cout_k * 2;  // rows of source l
+    j.bn = bn;
+    j.taps = taps;
+    j.ep.cout = bn;
+    j.ep.cout_valid = bn;
+    j.flip = 1;
+    j.n_halves = merged ? d->nsrc : 1;
+    j.stage_tiles = stage_tiles;
+    for (int hh = 0; hh < j.n_halves; ++hh) {
+      const int s = merged ? hh : l;
+      TileEpi& e = j.bwd[hh];
+      e.addend = static_cast<const __nv_bfloat16*>(d->addend[s]);
+      e.addend2 = static_cast<const __nv_bfloat16*>(d->addend2[s]);
+      e.mask_elu = static_cast<const __nv_bfloat16*>(d->mask_elu[s]);
+      e.out_raw = static_cast<__nv_bfloat16*>(d->dx[s]);
+      e.out_h = d->hin;
+      e.out_w = d->win;
+      e.out_c = C;
+      e.pix_stride = 1;
+      e.n_valid = C;
+    }
+    *rc = rows_job_launch(j, stream);
+    if (*rc) return true;
+  }
+  return true;
 }
 
 }  // namespace vub

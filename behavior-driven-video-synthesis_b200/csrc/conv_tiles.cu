@@ -23,6 +23,7 @@
 #include "common.h"
 #include "conv_epilogue.cuh"
 #include "ptx.cuh"
+#include "tile_epilogue.cuh"
 
 namespace vub {
 
@@ -46,20 +47,6 @@ struct TilesKParams {
   int total_tiles;
   int stages;
 };
-
-__device__ __forceinline__ long long tile_out_offset(const TileEpi& e, int col, int n, int oh, int ow) {
-  if (e.flags & VUB_CONV_F32_NCHW)
-    return (((long long)n * e.n_valid + col) * e.out_h + oh) * e.out_w + ow;
-  if (e.flags & VUB_CONV_D2S) {
-    const int qd = col / e.out_c;
-    const int cp = col - qd * e.out_c;
-    const long long opix = ((long long)n * e.out_h + 2 * oh + (qd >> 1)) * e.out_w + 2 * ow + (qd & 1);
-    return opix * e.out_c + cp;
-  }
-  const long long opix =
-      ((long long)n * e.out_h + oh * e.pix_stride + e.pix_off_h) * e.out_w + ow * e.pix_stride + e.pix_off_w;
-  return opix * e.out_c + e.c_off + col;
-}
 
 template <int BN, int BKC>
 __global__ void __launch_bounds__(kTilesThreads, 1)
@@ -198,7 +185,6 @@ __global__ void __launch_bounds__(kTilesThreads, 1)
     const uint32_t t0 = smem_u32(staging) + (warp - 2) * p.stage_tiles * EpiStage<GW>::TILE_BYTES;  // addend in / raw out
     const uint32_t t1 = t0 + EpiStage<GW>::TILE_BYTES;                              // mask in / elu out
     const uint32_t t2 = t1 + EpiStage<GW>::TILE_BYTES;                              // addend2 in (stage_tiles == 3)
-    constexpr int CPR = GW / 8;
     uint32_t cnt = 0;
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
@@ -211,113 +197,11 @@ __global__ void __launch_bounds__(kTilesThreads, 1)
       const TileEpi& e = p.ep[ei];
       const int ecol = (n_tile - (ei ? p.n_split : 0)) * BN;  // first column of this tile as the epilogue numbers it
       const bool f32_out = (e.flags & (VUB_CONV_F32_NHWC | VUB_CONV_F32_NCHW)) != 0;
-      // pixel of staged row `row` of this warp
-      auto row_pixel = [&](int row, int& rn, int& roh, int& row_w) {
-        const int mm = q * 32 + row;
-        rn = n0 + (mm >> (p.tw_log2 + p.th_log2));
-        roh = h0 + ((mm >> p.tw_log2) & (p.th - 1));
-        row_w = w0 + (mm & (p.tw - 1));
-        return rn < p.batch;
-      };
-      auto stage_fill = [&](uint32_t tile_addr, const __nv_bfloat16* src, int col0) {
-#pragma unroll
-        for (int k = 0; k < CPR; ++k) {
-          const int c = lane + 32 * k;
-          const int row = c / CPR;
-          const int col = c - row * CPR;
-          int rn, roh, row_w;
-          uint4 v = make_uint4(0u, 0u, 0u, 0u);
-          if (row_pixel(row, rn, roh, row_w))
-            v = __ldg(reinterpret_cast<const uint4*>(src + tile_out_offset(e, col0 + col * 8, rn, roh, row_w)));
-          sts128(tile_addr + row * EpiStage<GW>::PITCH + col * 16, v);
-        }
-      };
-      auto stage_flush_out = [&](uint32_t tile_addr, __nv_bfloat16* dst, int col0) {
-#pragma unroll
-        for (int k = 0; k < CPR; ++k) {
-          const int c = lane + 32 * k;
-          const int row = c / CPR;
-          const int col = c - row * CPR;
-          int rn, roh, row_w;
-          if (row_pixel(row, rn, roh, row_w))
-            *reinterpret_cast<uint4*>(dst + tile_out_offset(e, col0 + col * 8, rn, roh, row_w)) =
-                lds128(tile_addr + row * EpiStage<GW>::PITCH + col * 16);
-        }
-      };
-
       mbar_wait(&acc_full[g], cnt & 1);
       tc_fence_after();
       if constexpr (STAGED) {
-#pragma unroll 1
-        for (int g0 = 0; g0 < BN; g0 += GW) {
-          const int col0 = ecol + g0;  // first (epilogue-local) column of this group
-          if (!f32_out) {
-            if (e.addend != nullptr) stage_fill(t0, e.addend, col0);
-            if (e.mask_elu != nullptr) stage_fill(t1, e.mask_elu, col0);
-            if (e.addend2 != nullptr) stage_fill(t2, e.addend2, col0);
-            __syncwarp();
-          }
-#pragma unroll 1
-          for (int c0 = g0; c0 < g0 + GW; c0 += 32) {
-            uint32_t acc[32];
-            tmem_ld32(trow + c0, acc);
-            tmem_ld_wait();
-            if (c0 + 32 == BN) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&acc_empty[g]);
-            }
-            float y[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              y[i] = fmaf(__uint_as_float(acc[i]), s_scale[n_tile * BN + c0 + i], s_shift[n_tile * BN + c0 + i]);
-            if (f32_out) {
-              if (valid) {
-                if (e.flags & VUB_CONV_F32_NCHW) {
-#pragma unroll
-                  for (int i = 0; i < 32; ++i)
-                    if (ecol + c0 + i < e.n_valid)
-                      e.out_f32[tile_out_offset(e, ecol + c0 + i, n, oh, ow)] = y[i];
-                } else {
-                  float4* o = reinterpret_cast<float4*>(e.out_f32 + tile_out_offset(e, ecol + c0, n, oh, ow));
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) o[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-                }
-              }
-              continue;
-            }
-            const uint32_t my = lane * EpiStage<GW>::PITCH + (c0 - g0) * 2;
-            if (e.mask_elu != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float ev[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                add_bf16x8(lds128(t1 + my + 16 * j), ev);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) y[8 * j + i] *= ev[i] > 0.f ? 1.0f : ev[i] + 1.0f;
-              }
-            }
-            if (e.addend != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) add_bf16x8(lds128(t0 + my + 16 * j), &y[8 * j]);
-            }
-            if (e.addend2 != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) add_bf16x8(lds128(t2 + my + 16 * j), &y[8 * j]);
-            }
-            if (e.out_raw != nullptr) stage_put32<GW>(t0, lane, c0 - g0, y);
-            if (e.out_elu != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) y[i] = elu1(y[i]);
-              stage_put32<GW>(t1, lane, c0 - g0, y);
-            }
-          }
-          if (!f32_out) {
-            __syncwarp();
-            if (e.out_raw != nullptr) stage_flush_out(t0, e.out_raw, col0);
-            if (e.out_elu != nullptr) stage_flush_out(t1, e.out_elu, col0);
-            __syncwarp();
-          }
-        }
+        tile_epilogue_staged<BN, GW>(e, EpiGeom{p.tw, p.th, p.tw_log2, p.th_log2, p.batch}, s_scale + n_tile * BN,
+                                     s_shift + n_tile * BN, trow, t0, t1, t2, lane, q, ecol, n0, h0, w0, &acc_empty[g]);
       } else {
         // BN == 16: fp32 NCHW output of out_conv-like layers
         uint32_t acc[16];

@@ -1,7 +1,7 @@
 // Weight correlation of the weight-normalised convs (vub_conv_wgrad) on tcgen05 (sm_100a).
 //
-//   gt[(src, tap, ci)][co] += sum_pix dy[pix, co] * x_src[pix + off(tap), ci]        (fp32)
-//   dy_sum[co]             += sum_pix dy[pix, co]
+//   gt[split][co][(src, tap, ci)] = sum_{pix in split} dy[pix, co] * x_src[pix + off(tap), ci]        (fp32)
+//   dy_sum[split][co]             = sum_{pix in split} dy[pix, co]
 //
 // The contraction index is the PIXEL, the slow index of both NHWC operands, so both UMMA operands are
 // MN-major: a TMA box [channels, pixels] written with 128B/64B swizzle IS the canonical MN-major
@@ -9,17 +9,23 @@
 // profiles/r01_exp_mnmajor.log).  One k-step = 64 pixels:
 //   A = dy box(es)  [128 output channels x 64 pixels]   (M = 128; layers with fewer output channels
 //                                                         replicate their box with a block stride of 0)
-//   B = x boxes shifted by each tap of the CTA's tap group, every box = one block of D columns
+//   B = x boxes of the CTA's tap group.  For 3x3 stride-1 convs at width >= 16 ONE box per (tap row,
+//       channel block) is loaded with a one-pixel halo on both sides, and the three column taps are three
+//       N blocks of the SAME box whose block stride (LBO) is one pixel row: a pixel shift is a start-address
+//       offset in the MN-major layout (profiles/r01_exp_mnmajor.log), so x is read 3x instead of 9x.
+//       Otherwise (1x1, stride 2, tiny maps) every tap is its own shifted box = one block of D columns.
 //   D[co, (tap, ci)] (TMEM, fp32) accumulates over ALL pixel tiles the CTA owns; an extra N = 16 block of
 //   constant ones yields dy_sum from the same A operand.
-// Work split: grid = (tap group) x (128-channel M tile) x (pixel range); every CTA adds its partial
-// correlation to gt with coalesced red.global.add.f32 (lane = output channel).
+// Work split: grid = (tap group) x (128-channel M tile) x (pixel range = split); every CTA stores its partial
+// correlation into the split's slice of the workspace with coalesced plain stores; vub_wn_bwd sums the splits
+// (deterministic, no atomics: fp32 reductions to global memory were 3x the cost of the MMA main loop).
 // Upsample convs read dy through the four parity maps of the shuffled gradient; Downsample convs read x
 // through its four parity maps (same tap -> map/shift table as the forward kernel).
 //
 // Replaces autograd's convolution_backward (weight gradient) of lib/modules.py:143.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -30,16 +36,16 @@ namespace vub {
 
 constexpr int kWgThreads = 192;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 constexpr int kWgKP = 64;         // pixels per k-step
-constexpr int kWgMaxStages = 6;
+constexpr int kWgMaxStages = 16;
 constexpr int kWgMaxGroups = 6;
 constexpr int kWgMaxBoxes = 9;    // B boxes per tap group
 constexpr int kWgOnesBytes = 2048;
 
 struct WgBBox {
   int16_t map;       // B tensor map (source or parity view)
-  int8_t dh, dw;     // pixel shift relative to the dy tile
+  int8_t dh, dw;     // pixel shift of the box origin relative to the dy tile (halo boxes: dw = -1)
   int16_t chan;      // first channel of the box
-  int32_t gt_row;    // gt row of the box's first column
+  int32_t gt_row;    // gt row of the box's first column (halo boxes: of column tap 0; + c_src per column tap)
 };
 struct WgABox {
   int16_t map;
@@ -52,12 +58,18 @@ struct WgKParams {
   WgABox abox[4 * 4];                          // [m_tile][box]
   WgBBox bbox[kWgMaxGroups][kWgMaxBoxes];
   int nb[kWgMaxGroups];                        // boxes per group
-  float* gt;
-  float* dy_sum;
+  float* gt;             // partial correlations [n_split][cout_k][gt_pitch]
+  float* dy_sum;         // partial sums [n_split][cout_k]
   int gt_pitch;
+  long long split_stride;  // floats between the gt slices of consecutive splits
+  int sum_stride;          // floats between the dy_sum slices of consecutive splits
   int ca, na;            // channels per A box, boxes per M tile (na * ca <= 128)
   int m_rows;            // valid rows of an M tile (min(cout_k, 128))
   int cb;                // channels per B box
+  int halo;              // 1: B boxes carry a one-pixel halo and serve the 3 column taps (ndw = 3)
+  int c_src;             // gt row stride between column taps of a halo box
+  int b_box_pitch;       // bytes between consecutive B boxes of a stage (1024-aligned)
+  int b_box_bytes;       // bytes TMA writes per B box
   int n_groups, n_mtiles, n_split;
   int tw, th, tn;        // pixel tile (tw * th * tn = 64)
   int tiles_w, tiles_h;
@@ -100,10 +112,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
   const bool with_sum = grp == 0;
 
   const int a_rowb = p.ca * 2, b_rowb = p.cb * 2;
-  const int a_box = kWgKP * a_rowb, b_box = kWgKP * b_rowb;
+  const int a_box = kWgKP * a_rowb, b_box = p.b_box_pitch;
   const int a_bytes = p.na * a_box;
-  const int stage_bytes = a_bytes + kWgMaxBoxes * 0 + nb * b_box;  // boxes are packed per group
-  const int stage_pitch = (stage_bytes + 1023) & ~1023;
+  const int stage_bytes = a_bytes + nb * p.b_box_bytes;  // bytes TMA delivers per stage
+  const int stage_pitch = (a_bytes + nb * b_box + 1023) & ~1023;
+  const int ndw = p.halo ? 3 : 1;
   uint8_t* ones = smem;                 // 2 KB of bf16 1.0
   uint8_t* ring = smem + kWgOnesBytes;  // [S][stage_pitch]
 
@@ -131,7 +144,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
-  const int n_cols = nb * p.cb;  // D columns of this CTA (the ones block follows at column n_cols)
+  const int n_cols = nb * ndw * p.cb;  // D columns of this CTA (the ones block follows at column n_cols)
 
   auto tile_origin = [&](int tile, int& n0, int& h0, int& w0) {
     const int twi = tile % p.tiles_w;
@@ -172,67 +185,104 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
       }
     } else if (warp == 1) {
       // ------------------------------ MMA issuer --------------------------------
+      // Everything that does not depend on the stage is hoisted out of the loop: the issuing thread is a single
+      // lane, and descriptor arithmetic with divisions / parameter loads inside the loop made it the bottleneck
+      // (ncu source view: ~340 instructions per K slice, profiles/r01_wgrad_issue_bound.txt).
       const uint32_t a_hi = umma_desc_hi_mn(a_rowb), b_hi = umma_desc_hi_mn(b_rowb);
       const uint32_t a_blk = p.na * p.ca >= 128 ? a_box : 0;  // fewer than 128 channels: replicate the box(es)
-      const uint32_t ones_lo = umma_desc_lo_mn(smem_u32(ones), 0);
-      const uint32_t ones_hi = umma_desc_hi_mn(128);
+      const uint32_t a_lo_c = (a_blk >> 4) << 16;
+      const uint64_t d_ones = umma_desc_join(umma_desc_hi_mn(128), umma_desc_lo_mn(smem_u32(ones), 0));
       constexpr uint32_t kMajorMN = (1u << 15) | (1u << 16);
-      const uint32_t idesc_ones = umma_idesc_bf16(128, 16) | kMajorMN;
+      constexpr uint32_t idesc_ones = umma_idesc_bf16(128, 16) | kMajorMN;
+      // per-CTA MMA list of one K slice: at most 3 MMAs (halo: one per box; otherwise chunks of <= 256 columns)
+      uint32_t m_rel[3] = {0u, 0u, 0u}, m_col[3] = {0u, 0u, 0u}, m_idesc[3] = {0u, 0u, 0u}, m_lo_c[3] = {0u, 0u, 0u};
+      int n_m = 0;
+      if (p.halo) {
+        for (int bx = 0; bx < nb && bx < 3; ++bx, ++n_m) {
+          m_rel[bx] = bx * b_box;
+          m_col[bx] = bx * 3 * p.cb;
+          m_idesc[bx] = umma_idesc_bf16(128, 3 * p.cb) | kMajorMN;
+          m_lo_c[bx] = (static_cast<uint32_t>(b_rowb) >> 4) << 16;  // block stride = one pixel row
+        }
+      } else {
+        const int max_box = 256 / p.cb;
+        for (int box0 = 0; box0 < nb && n_m < 3; ++n_m) {
+          const int nbox = nb - box0 < max_box ? nb - box0 : max_box;
+          m_rel[n_m] = box0 * b_box;
+          m_col[n_m] = box0 * p.cb;
+          m_idesc[n_m] = umma_idesc_bf16(128, nbox * p.cb) | kMajorMN;
+          m_lo_c[n_m] = (static_cast<uint32_t>(b_box) >> 4) << 16;
+          box0 += nbox;
+        }
+      }
+      uint32_t a_off[4], b_off[4];  // byte offsets of the 4 K slices (16 pixels each) inside a box
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int px = j * 16;
+        a_off[j] = px * a_rowb;
+        b_off[j] = p.halo ? ((px / p.tw) * (p.tw + 2) + (px % p.tw)) * b_rowb : px * b_rowb;
+      }
+      const uint32_t ring_addr = smem_u32(ring);
       int st = 0;
       uint32_t ph = 0;
-      bool first = true;
+      uint32_t acc = 0u;
       for (int tile = t_begin; tile < t_end; ++tile) {
         mbar_wait(&full_bar[st], ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(ring + st * stage_pitch);
+        const uint32_t a_addr = ring_addr + st * stage_pitch;
         const uint32_t b_addr = a_addr + a_bytes;
         if (elect_one()) {
-#pragma unroll 1
-          for (int j = 0; j < kWgKP / 16; ++j) {
-            const uint64_t da = umma_desc_join(a_hi, umma_desc_lo_mn(a_addr + j * 16 * a_rowb, a_blk));
-            const uint32_t acc = (first && j == 0) ? 0u : 1u;
-            // column chunks of at most 256 D columns (whole boxes)
-            int box0 = 0;
-            while (box0 < nb) {
-              int nbox = nb - box0;
-              const int max_box = 256 / p.cb;
-              if (nbox > max_box) nbox = max_box;
-              const uint64_t db =
-                  umma_desc_join(b_hi, umma_desc_lo_mn(b_addr + box0 * b_box + j * 16 * b_rowb, b_box));
-              umma_bf16(tmem_base + box0 * p.cb, da, db, umma_idesc_bf16(128, nbox * p.cb) | kMajorMN, acc);
-              box0 += nbox;
-            }
-            if (with_sum) umma_bf16(tmem_base + n_cols, da, umma_desc_join(ones_hi, ones_lo), idesc_ones, acc);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint64_t da = umma_desc_join(a_hi, (((a_addr + a_off[j]) & 0x3FFFFu) >> 4) | a_lo_c);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+              if (i < n_m)
+                umma_bf16(tmem_base + m_col[i], da,
+                          umma_desc_join(b_hi, (((b_addr + m_rel[i] + b_off[j]) & 0x3FFFFu) >> 4) | m_lo_c[i]), m_idesc[i],
+                          acc);
+            if (with_sum) umma_bf16(tmem_base + n_cols, da, d_ones, idesc_ones, acc);
+            acc = 1u;
           }
           umma_commit(&empty_bar[st]);
           if (tile == t_end - 1) umma_commit(&acc_full);
         }
         __syncwarp();
-        first = false;
+        acc = 1u;
         if (++st == S) {
           st = 0;
           ph ^= 1;
         }
       }
     } else {
-      // ------------------------------ epilogue: TMEM -> red.global.add ------------------------------
+      // ------------------------------ epilogue: TMEM -> this split's partial correlation ----------------------
+      // Plain coalesced stores into the split's private slice of the workspace (vub_wn_bwd sums the splits):
+      // fp32 reductions to global memory cost ~4 cycles per lane and dominated the kernel (128 x 384 values per
+      // CTA), and the result is now bit-reproducible.  Each 32x32 accumulator block is transposed through shared
+      // memory (the pipeline ring is idle by now) so that a warp writes 128 contiguous bytes of one gt row.
       const int q = warp & 3;
-      const int row = q * 32 + lane;  // D row = output channel within the M tile
+      const int row0 = q * 32;  // first D row (= output channel within the M tile) of this warp
       mbar_wait(&acc_full, 0);
       tc_fence_after();
-      const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-      const bool row_ok = row < p.m_rows;
-      const int co = mt * 128 + row;
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(row0) << 16);
+      float* tp = reinterpret_cast<float*>(ring) + q * (32 * 33);
+      float* gt_split = p.gt + (size_t)split * p.split_stride;
       for (int j = 0; j < nb; ++j) {
-        const int gt_row = p.bbox[grp][j].gt_row;
-        for (int c0 = 0; c0 < p.cb; c0 += 32) {
-          uint32_t acc[32];
-          tmem_ld32(trow + j * p.cb + c0, acc);
-          tmem_ld_wait();
-          if (row_ok) {
-            float* dst = p.gt + (size_t)(gt_row + c0) * p.gt_pitch + co;
+        for (int dwi = 0; dwi < ndw; ++dwi) {
+          const int gt_col = p.bbox[grp][j].gt_row + dwi * p.c_src;
+          for (int c0 = 0; c0 < p.cb; c0 += 32) {
+            uint32_t acc[32];
+            tmem_ld32(trow + (j * ndw + dwi) * p.cb + c0, acc);
+            tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) atomicAdd(dst + (size_t)i * p.gt_pitch, __uint_as_float(acc[i]));
+            for (int i = 0; i < 32; ++i) tp[lane * 33 + i] = __uint_as_float(acc[i]);
+            __syncwarp();
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              const int row = row0 + r;
+              if (row < p.m_rows) gt_split[(size_t)(mt * 128 + row) * p.gt_pitch + gt_col + c0 + lane] = tp[r * 33 + lane];
+            }
+            __syncwarp();
           }
         }
       }
@@ -240,7 +290,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
         uint32_t acc[16];
         tmem_ld16(trow + n_cols, acc);
         tmem_ld_wait();
-        if (row_ok) atomicAdd(p.dy_sum + co, __uint_as_float(acc[0]));
+        const int row = row0 + lane;
+        if (row < p.m_rows) p.dy_sum[(size_t)split * p.sum_stride + mt * 128 + row] = __uint_as_float(acc[0]);
       }
     }
   }
@@ -254,12 +305,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
 
 using namespace vub;
 
-extern "C" int vub_conv_wgrad(const vub_wgrad_desc* d, void* stream_v) {
-  clear_error();
-  if (!d) return fail(VUB_E_NULL, "conv_wgrad: desc is NULL");
-  if (!d->dy || !d->x[0] || !d->gt || !d->dy_sum) return fail(VUB_E_NULL, "conv_wgrad: dy/x/gt/dy_sum NULL");
+// Fills everything of the launch parameters that depends on shapes only (no pointers, no tensor maps) and
+// returns the best number of pixel splits in *best_split.
+static int wgrad_plan(const vub_wgrad_desc* d, WgKParams& kp, int* best_split, int* max_nb_out) {
   if (d->nsrc != 1 && d->nsrc != 2) return fail(VUB_E_SHAPE, "conv_wgrad: nsrc must be 1 or 2");
-  if (d->nsrc == 2 && !d->x[1]) return fail(VUB_E_NULL, "conv_wgrad: x[1] NULL with nsrc == 2");
   const int C = d->c_src;
   if (C != 32 && C != 64 && C != 128) return fail(VUB_E_SHAPE, "conv_wgrad: c_src %d not in {32,64,128}", C);
   if (d->ksize != 1 && d->ksize != 3) return fail(VUB_E_SHAPE, "conv_wgrad: ksize must be 1 or 3");
@@ -272,21 +321,12 @@ extern "C" int vub_conv_wgrad(const vub_wgrad_desc* d, void* stream_v) {
   const int cout_k = d->cout_k;
   if (cout_k < 32 || cout_k > 512 || cout_k % 32 || (cout_k > 32 && cout_k % 64) || (cout_k > 64 && cout_k % 128))
     return fail(VUB_E_SHAPE, "conv_wgrad: cout_k %d", cout_k);
-  if (d->gt_pitch < cout_k) return fail(VUB_E_SHAPE, "conv_wgrad: gt_pitch %d < cout_k %d", d->gt_pitch, cout_k);
   const int cmap = d2s ? cout_k / 4 : cout_k;
   if (cmap % 32) return fail(VUB_E_SHAPE, "conv_wgrad: %d channels per dy map", cmap);
-  const void* ptrs[] = {d->dy, d->x[0], d->x[1]};
-  for (const void* q : ptrs)
-    if (q && !aligned16(q)) return fail(VUB_E_ALIGN, "conv_wgrad: pointer %p not 16B aligned", q);
-
   const int taps = d->ksize * d->ksize;
   const int ho = d->hin / d->stride, wo = d->win / d->stride;  // dy grid == tile grid (conv output pixels)
 
-  WgKParams kp;
   memset(&kp, 0, sizeof(kp));
-  kp.gt = d->gt;
-  kp.dy_sum = d->dy_sum;
-  kp.gt_pitch = d->gt_pitch;
   // ---- A side: dy ----
   kp.ca = cmap >= 64 ? 64 : 32;
   const int m_rows = cout_k < 128 ? cout_k : 128;
@@ -298,16 +338,41 @@ extern "C" int vub_conv_wgrad(const vub_wgrad_desc* d, void* stream_v) {
       const int co0 = mt * 128 + i * kp.ca;
       kp.abox[mt * 4 + i] = WgABox{(int16_t)(d2s ? co0 / cmap : 0), (int16_t)(d2s ? co0 % cmap : co0)};
     }
+  // ---- pixel tiles of 64 ----
+  kp.tw = wo < kWgKP ? wo : kWgKP;
+  kp.th = ho < kWgKP / kp.tw ? ho : kWgKP / kp.tw;
+  kp.tn = kWgKP / (kp.tw * kp.th);
+  kp.tiles_w = wo / kp.tw;
+  kp.tiles_h = ho / kp.th;
+  const int tiles_n = (d->batch + kp.tn - 1) / kp.tn;
+  kp.total_tiles = kp.tiles_w * kp.tiles_h * tiles_n;
+
   // ---- B side: x, grouped by (source, tap row) or (source) ----
   kp.cb = C >= 64 ? 64 : 32;
+  kp.c_src = C;
   const int cblocks = C / kp.cb;
   const bool merge_rows = taps == 9 && 9 * C <= 448;  // all 9 taps of a source fit one CTA's TMEM
+  static const bool no_halo = getenv("VUB_WGRAD_NO_HALO") != nullptr && getenv("VUB_WGRAD_NO_HALO")[0] == '1';
+  kp.halo = (taps == 9 && d->stride == 1 && kp.tw >= 16 && !no_halo) ? 1 : 0;
+  kp.b_box_bytes = (kp.tw + 2 * kp.halo) * kp.th * kp.tn * kp.cb * 2;
+  kp.b_box_pitch = (kp.b_box_bytes + 1023) & ~1023;
   int g = 0;
   for (int s = 0; s < d->nsrc; ++s) {
     const int n_rowgroups = (taps == 9 && !merge_rows) ? 3 : 1;
     for (int rg = 0; rg < n_rowgroups; ++rg, ++g) {
       if (g >= kWgMaxGroups) return fail(VUB_E_SHAPE, "conv_wgrad: too many tap groups");
       int j = 0;
+      if (kp.halo) {
+        // one halo box per (tap row, channel block); its 3 N blocks are the column taps q = 0, 1, 2
+        for (int r = 0; r < 3; ++r) {
+          if (n_rowgroups == 3 && r != rg) continue;
+          for (int cbk = 0; cbk < cblocks; ++cbk, ++j)
+            kp.bbox[g][j] = WgBBox{(int16_t)s, (int8_t)(r - 1), (int8_t)-1, (int16_t)(cbk * kp.cb),
+                                   (s * taps + r * 3) * C + cbk * kp.cb};
+        }
+        kp.nb[g] = j;
+        continue;
+      }
       for (int tap = 0; tap < taps; ++tap) {
         const int r = tap / d->ksize, q = tap % d->ksize;
         if (n_rowgroups == 3 && r != rg) continue;
@@ -334,16 +399,9 @@ extern "C" int vub_conv_wgrad(const vub_wgrad_desc* d, void* stream_v) {
   kp.n_groups = g;
   int max_nb = 0;
   for (int i = 0; i < g; ++i) max_nb = kp.nb[i] > max_nb ? kp.nb[i] : max_nb;
-  if (max_nb * kp.cb + 16 > 512) return fail(VUB_E_SHAPE, "conv_wgrad: %d accumulator columns", max_nb * kp.cb);
-
-  // ---- pixel tiles of 64 ----
-  kp.tw = wo < kWgKP ? wo : kWgKP;
-  kp.th = ho < kWgKP / kp.tw ? ho : kWgKP / kp.tw;
-  kp.tn = kWgKP / (kp.tw * kp.th);
-  kp.tiles_w = wo / kp.tw;
-  kp.tiles_h = ho / kp.th;
-  const int tiles_n = (d->batch + kp.tn - 1) / kp.tn;
-  kp.total_tiles = kp.tiles_w * kp.tiles_h * tiles_n;
+  const int cols_per_box = (kp.halo ? 3 : 1) * kp.cb;
+  if (max_nb * cols_per_box + 16 > 512)
+    return fail(VUB_E_SHAPE, "conv_wgrad: %d accumulator columns", max_nb * cols_per_box);
 
   static int n_sm = 0;
   if (n_sm == 0) {
@@ -355,9 +413,51 @@ extern "C" int vub_conv_wgrad(const vub_wgrad_desc* d, void* stream_v) {
   int n_split = n_sm / (kp.n_groups * kp.n_mtiles);
   if (n_split < 1) n_split = 1;
   if (n_split > kp.total_tiles) n_split = kp.total_tiles;
-  kp.n_split = n_split;
+  *best_split = n_split;
+  *max_nb_out = max_nb;
+  return 0;
+}
 
-  const size_t stage_bytes = (size_t)kp.na * kWgKP * kp.ca * 2 + (size_t)max_nb * kWgKP * kp.cb * 2;
+extern "C" int32_t vub_conv_wgrad_splits(const vub_wgrad_desc* d) {
+  clear_error();
+  if (!d) return fail(VUB_E_NULL, "conv_wgrad_splits: desc is NULL");
+  WgKParams kp;
+  int best = 0, max_nb = 0;
+  const int rc = wgrad_plan(d, kp, &best, &max_nb);
+  return rc ? rc : best;
+}
+
+extern "C" int vub_conv_wgrad(const vub_wgrad_desc* d, void* stream_v) {
+  clear_error();
+  if (!d) return fail(VUB_E_NULL, "conv_wgrad: desc is NULL");
+  if (!d->dy || !d->x[0] || !d->gt || !d->dy_sum) return fail(VUB_E_NULL, "conv_wgrad: dy/x/gt/dy_sum NULL");
+  if (d->nsrc == 2 && !d->x[1]) return fail(VUB_E_NULL, "conv_wgrad: x[1] NULL with nsrc == 2");
+  WgKParams kp;
+  int best = 0, max_nb = 0;
+  int rc = wgrad_plan(d, kp, &best, &max_nb);
+  if (rc) return rc;
+  const int C = d->c_src, cout_k = d->cout_k;
+  const bool d2s = (d->flags & VUB_CONV_D2S) != 0;
+  const int cmap = d2s ? cout_k / 4 : cout_k;
+  const int ho = d->hin / d->stride, wo = d->win / d->stride;
+  const int ktot = d->nsrc * d->ksize * d->ksize * C;
+  if (d->gt_pitch < ktot) return fail(VUB_E_SHAPE, "conv_wgrad: gt_pitch %d < K = %d", d->gt_pitch, ktot);
+  if (d->n_split < 1 || d->n_split > kp.total_tiles || d->n_split > 1024)
+    return fail(VUB_E_SHAPE, "conv_wgrad: n_split %d not in [1, %d] (vub_conv_wgrad_splits suggests %d)", d->n_split,
+                kp.total_tiles < 1024 ? kp.total_tiles : 1024, best);
+  if (d->n_split > 1 && (d->split_stride < (int64_t)cout_k * d->gt_pitch || d->sum_stride < cout_k))
+    return fail(VUB_E_SHAPE, "conv_wgrad: split strides too small");
+  const void* ptrs[] = {d->dy, d->x[0], d->x[1]};
+  for (const void* q : ptrs)
+    if (q && !aligned16(q)) return fail(VUB_E_ALIGN, "conv_wgrad: pointer %p not 16B aligned", q);
+  kp.gt = d->gt;
+  kp.dy_sum = d->dy_sum;
+  kp.gt_pitch = d->gt_pitch;
+  kp.split_stride = d->split_stride;
+  kp.sum_stride = d->sum_stride;
+  kp.n_split = d->n_split;
+
+  const size_t stage_bytes = (size_t)kp.na * kWgKP * kp.ca * 2 + (size_t)max_nb * kp.b_box_pitch;
   const size_t stage_pitch = (stage_bytes + 1023) & ~(size_t)1023;
   int stages = static_cast<int>((200 * 1024 - kWgOnesBytes) / stage_pitch);
   if (stages > kWgMaxStages) stages = kWgMaxStages;
@@ -366,7 +466,6 @@ extern "C" int vub_conv_wgrad(const vub_wgrad_desc* d, void* stream_v) {
   const size_t smem = kWgOnesBytes + stages * stage_pitch + 1024;
 
   // ---- tensor maps ----
-  int rc;
   {
     const uint32_t boxA[4] = {(uint32_t)kp.ca, (uint32_t)kp.tw, (uint32_t)kp.th, (uint32_t)kp.tn};
     if (!d2s) {
@@ -385,7 +484,7 @@ extern "C" int vub_conv_wgrad(const vub_wgrad_desc* d, void* stream_v) {
           if (rc) return rc;
         }
     }
-    const uint32_t boxB[4] = {(uint32_t)kp.cb, (uint32_t)kp.tw, (uint32_t)kp.th, (uint32_t)kp.tn};
+    const uint32_t boxB[4] = {(uint32_t)kp.cb, (uint32_t)(kp.tw + 2 * kp.halo), (uint32_t)kp.th, (uint32_t)kp.tn};
     const uint64_t Cc = C, Hin = d->hin, Win = d->win;
     if (d->stride == 1) {
       const uint64_t dims[4] = {Cc, Win, Hin, (uint64_t)d->batch};

@@ -1,0 +1,166 @@
+// Mode-driven epilogue shared by the persistent tile kernel (conv_tiles.cu) and the slab kernel
+// (conv_slab.cu): one warp drains its 32 TMEM lanes (= 32 pixels) x BN accumulator columns.
+//   y = scale * acc + shift;  y *= ELU'(mask) (data gradients);  y += addend (+ addend2);
+//   bf16 raw and/or ELU(y) outputs staged through shared memory (coalesced 16-byte chunks), DepthToSpace or
+//   strided pixel scatter, or fp32 NHWC / NCHW outputs.
+// Fuses lib/modules.py:144, 225-233, 24-34 (forward) and their autograd counterparts (backward).
+#pragma once
+#include "conv_epilogue.cuh"
+#include "conv_tiles.cuh"
+#include "ptx.cuh"
+
+namespace vub {
+
+struct EpiGeom {
+  int tw, th, tw_log2, th_log2;  // a 128-pixel tile = tw x th pixels of 128 / (tw * th) images
+  int batch;
+};
+
+__device__ __forceinline__ long long tile_out_offset(const TileEpi& e, int col, int n, int oh, int ow) {
+  if (e.flags & VUB_CONV_F32_NCHW)
+    return (((long long)n * e.n_valid + col) * e.out_h + oh) * e.out_w + ow;
+  if (e.flags & VUB_CONV_D2S) {
+    const int qd = col / e.out_c;
+    const int cp = col - qd * e.out_c;
+    const long long opix = ((long long)n * e.out_h + 2 * oh + (qd >> 1)) * e.out_w + 2 * ow + (qd & 1);
+    return opix * e.out_c + cp;
+  }
+  const long long opix =
+      ((long long)n * e.out_h + oh * e.pix_stride + e.pix_off_h) * e.out_w + ow * e.pix_stride + e.pix_off_w;
+  return opix * e.out_c + e.c_off + col;
+}
+
+// `trow`: TMEM address of this warp's lane quarter at the accumulator's first column; `t0/t1/t2`: this warp's
+// staging tiles (32 rows x (GW*2+16) bytes each; t2 only when an addend2 is present); `s_scale/s_shift`: already
+// offset to the tile's first GEMM column; `ecol`: the tile's first column as the epilogue `e` numbers it;
+// (n0, h0, w0): tile origin.  Arrives once (lane 0) on `acc_empty` (unless NULL) as soon as the accumulator has
+// been read.
+template <int BN, int GW>
+__device__ __forceinline__ void tile_epilogue_staged(const TileEpi& e, const EpiGeom gm, const float* s_scale,
+                                                     const float* s_shift, uint32_t trow, uint32_t t0, uint32_t t1,
+                                                     uint32_t t2, int lane, int q, int ecol, int n0, int h0, int w0,
+                                                     uint64_t* acc_empty) {
+  constexpr int CPR = GW / 8;
+  const int m = q * 32 + lane;
+  const int n = n0 + (m >> (gm.tw_log2 + gm.th_log2));
+  const int oh = h0 + ((m >> gm.tw_log2) & (gm.th - 1));
+  const int ow = w0 + (m & (gm.tw - 1));
+  const bool valid = n < gm.batch;
+  const bool f32_out = (e.flags & (VUB_CONV_F32_NHWC | VUB_CONV_F32_NCHW)) != 0;
+  // pixel of staged row `row` of this warp
+  auto row_pixel = [&](int row, int& rn, int& roh, int& row_w) {
+    const int mm = q * 32 + row;
+    rn = n0 + (mm >> (gm.tw_log2 + gm.th_log2));
+    roh = h0 + ((mm >> gm.tw_log2) & (gm.th - 1));
+    row_w = w0 + (mm & (gm.tw - 1));
+    return rn < gm.batch;
+  };
+  // All loads of a tensor are issued before the first shared-memory store: sts128 is a volatile asm with a
+  // memory clobber, so a load -> store -> load -> store sequence serialises CPR global-memory latencies
+  // (measured: the ELU' mask alone doubled the data-gradient time of the HBM-bound layers).
+  auto stage_fill = [&](uint32_t tile_addr, const __nv_bfloat16* src, int col0) {
+    uint4 v[CPR];
+#pragma unroll
+    for (int k = 0; k < CPR; ++k) {
+      const int c = lane + 32 * k;
+      const int row = c / CPR;
+      const int col = c - row * CPR;
+      int rn, roh, row_w;
+      v[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (row_pixel(row, rn, roh, row_w))
+        v[k] = *reinterpret_cast<const uint4*>(src + tile_out_offset(e, col0 + col * 8, rn, roh, row_w));  // may alias the output
+    }
+#pragma unroll
+    for (int k = 0; k < CPR; ++k) {
+      const int c = lane + 32 * k;
+      const int row = c / CPR;
+      const int col = c - row * CPR;
+      sts128(tile_addr + row * EpiStage<GW>::PITCH + col * 16, v[k]);
+    }
+  };
+  auto stage_flush_out = [&](uint32_t tile_addr, __nv_bfloat16* dst, int col0) {
+#pragma unroll
+    for (int k = 0; k < CPR; ++k) {
+      const int c = lane + 32 * k;
+      const int row = c / CPR;
+      const int col = c - row * CPR;
+      int rn, roh, row_w;
+      if (row_pixel(row, rn, roh, row_w))
+        *reinterpret_cast<uint4*>(dst + tile_out_offset(e, col0 + col * 8, rn, roh, row_w)) =
+            lds128(tile_addr + row * EpiStage<GW>::PITCH + col * 16);
+    }
+  };
+
+#pragma unroll 1
+  for (int g0 = 0; g0 < BN; g0 += GW) {
+    const int col0 = ecol + g0;  // first (epilogue-local) column of this group
+    if (!f32_out) {
+      if (e.addend != nullptr) stage_fill(t0, e.addend, col0);
+      if (e.mask_elu != nullptr) stage_fill(t1, e.mask_elu, col0);
+      if (e.addend2 != nullptr) stage_fill(t2, e.addend2, col0);
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int c0 = g0; c0 < g0 + GW; c0 += 32) {
+      uint32_t acc[32];
+      tmem_ld32(trow + c0, acc);
+      tmem_ld_wait();
+      if (c0 + 32 == BN) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0 && acc_empty != nullptr) mbar_arrive(acc_empty);
+      }
+      float y[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        y[i] = fmaf(__uint_as_float(acc[i]), s_scale[c0 + i], s_shift[c0 + i]);
+      if (f32_out) {
+        if (valid) {
+          if (e.flags & VUB_CONV_F32_NCHW) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (ecol + c0 + i < e.n_valid)
+                e.out_f32[tile_out_offset(e, ecol + c0 + i, n, oh, ow)] = y[i];
+          } else {
+            float4* o = reinterpret_cast<float4*>(e.out_f32 + tile_out_offset(e, ecol + c0, n, oh, ow));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+          }
+        }
+        continue;
+      }
+      const uint32_t my = lane * EpiStage<GW>::PITCH + (c0 - g0) * 2;
+      if (e.mask_elu != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float ev[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          add_bf16x8(lds128(t1 + my + 16 * j), ev);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[8 * j + i] *= ev[i] > 0.f ? 1.0f : ev[i] + 1.0f;
+        }
+      }
+      if (e.addend != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) add_bf16x8(lds128(t0 + my + 16 * j), &y[8 * j]);
+      }
+      if (e.addend2 != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) add_bf16x8(lds128(t2 + my + 16 * j), &y[8 * j]);
+      }
+      if (e.out_raw != nullptr) stage_put32<GW>(t0, lane, c0 - g0, y);
+      if (e.out_elu != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) y[i] = elu1(y[i]);
+        stage_put32<GW>(t1, lane, c0 - g0, y);
+      }
+    }
+    if (!f32_out) {
+      __syncwarp();
+      if (e.out_raw != nullptr) stage_flush_out(t0, e.out_raw, col0);
+      if (e.out_elu != nullptr) stage_flush_out(t1, e.out_elu, col0);
+      __syncwarp();
+    }
+  }
+}
+
+}  // namespace vub

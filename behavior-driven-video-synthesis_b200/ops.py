@@ -259,6 +259,23 @@ def _conv_dgrad_cuda(dy, wd, dx0, dx1, mask0, mask1, add0, add1, add20, add21, k
                     bytes_=nbytes), "vub_conv_dgrad")
 
 
+def _wgrad_desc(dy_shape, x_shape, nsrc, ksize, stride, d2s) -> "N.WgradDesc":
+    B, H, W, c_src = x_shape
+    d = N.WgradDesc()
+    d.nsrc, d.c_src, d.batch, d.hin, d.win = nsrc, c_src, B, H, W
+    d.cout_k = dy_shape[3] * 4 if d2s else dy_shape[3]
+    d.ksize, d.stride, d.flags = ksize, stride, (N.CONV_D2S if d2s else 0)
+    return d
+
+
+def wgrad_splits(dy_shape, x_shape, nsrc: int, ksize: int, stride: int, d2s: bool) -> int:
+    """Number of pixel splits ``vub_conv_wgrad`` should use for this shape (sizes the partial buffers)."""
+    n = N.lib().vub_conv_wgrad_splits(C.byref(_wgrad_desc(dy_shape, x_shape, nsrc, ksize, stride, d2s)))
+    if n <= 0:
+        N.check(n if n else 1, "vub_conv_wgrad_splits")
+    return n
+
+
 def _conv_wgrad_cuda(dy, x0, x1, gt, dy_sum, ksize, stride, d2s) -> None:
     _check_act(dy, "conv_wgrad dy")
     _check_act(x0, "conv_wgrad x0")
@@ -275,15 +292,16 @@ def _conv_wgrad_cuda(dy, x0, x1, gt, dy_sum, ksize, stride, d2s) -> None:
     want = (B, 2 * Ho, 2 * Wo, cout_k // 4) if d2s else (B, Ho, Wo, cout_k)
     if tuple(dy.shape) != want:
         raise ValueError(f"conv_wgrad: dy {tuple(dy.shape)} != {want}")
-    if (gt.dtype != torch.float32 or gt.dim() != 2 or gt.shape[0] != nsrc * taps * c_src or gt.shape[1] < cout_k
-            or gt.stride(1) != 1 or dy_sum.dtype != torch.float32 or dy_sum.numel() < cout_k):
-        raise ValueError(f"conv_wgrad: gt {tuple(gt.shape)} / dy_sum do not match K={nsrc * taps * c_src}, cout_k={cout_k}")
-    d = N.WgradDesc()
+    if (gt.dtype != torch.float32 or gt.dim() != 3 or gt.shape[1] < cout_k or gt.shape[2] != nsrc * taps * c_src
+            or gt.stride(2) != 1 or dy_sum.dtype != torch.float32 or dy_sum.dim() != 2
+            or dy_sum.shape[0] != gt.shape[0] or dy_sum.shape[1] < cout_k or dy_sum.stride(1) != 1):
+        raise ValueError(f"conv_wgrad: gt {tuple(gt.shape)} / dy_sum {tuple(dy_sum.shape)} do not match "
+                         f"[n_split, cout_k={cout_k}, K={nsrc * taps * c_src}]")
+    d = _wgrad_desc(dy.shape, x0.shape, nsrc, ksize, stride, d2s)
     d.dy, d.gt, d.dy_sum = dy.data_ptr(), gt.data_ptr(), dy_sum.data_ptr()
     d.x[0], d.x[1] = x0.data_ptr(), _p(x1)
-    d.nsrc, d.c_src, d.batch, d.hin, d.win = nsrc, c_src, B, H, W
-    d.cout_k, d.gt_pitch, d.ksize, d.stride, d.flags = cout_k, gt.stride(0), ksize, stride, (N.CONV_D2S if d2s else 0)
-    nbytes = float(dy.numel() * 2 + nsrc * x0.numel() * 2 + gt.shape[0] * cout_k * 4)
+    d.n_split, d.split_stride, d.sum_stride, d.gt_pitch = gt.shape[0], gt.stride(0), dy_sum.stride(0), gt.stride(1)
+    nbytes = float(dy.numel() * 2 + nsrc * x0.numel() * 2 + gt.numel() * 4)
     flops = 2.0 * B * Ho * Wo * cout_k * taps * nsrc * c_src
     tag = f"conv_wgrad {nsrc}x{c_src}x{cout_k} k{ksize} s{stride}{' d2s' if d2s else ''} @{H}x{W}"
     N.check(_launch(tag, N.lib().vub_conv_wgrad, C.byref(d), _stream(), flops=flops,
@@ -301,7 +319,7 @@ def _stem_bwd_cuda(x, dy, gt, dy_sum) -> None:
     _check_act(dy, "stem_bwd dy")
     B, cx, H, W = x.shape
     cout = dy.shape[3]
-    if tuple(dy.shape) != (B, H, W, cout) or gt.numel() != cx * cout or dy_sum.numel() < cout:
+    if tuple(dy.shape) != (B, H, W, cout) or gt.numel() != cx * cout or dy_sum.numel() != cout:
         raise ValueError("stem_bwd: shape mismatch")
     N.check(_launch(f"stem_bwd<{cout}>", N.lib().vub_stem_bwd, x.data_ptr(), dy.data_ptr(), B, cx, H, W, cout,
                     gt.data_ptr(), dy_sum.data_ptr(), _stream(), flops=2.0 * B * H * W * cx * cout,

@@ -62,6 +62,17 @@ class Tape:
 
 
 # --------------------------------------------------------------------------------------------------
+def _tape_signature(tape: "Tape") -> tuple:
+    """Which convs ran on which input shapes: the gradient bank (split counts, buffer sizes) depends on both."""
+    sig = []
+    for rec in tape.recs:
+        if rec[0] == "conv":
+            sig.append((id(rec[1]), tuple(rec[2][0][0].pick(rec[2][0][1]).shape)))
+        elif rec[0] == "stem":
+            sig.append((id(rec[1]), tuple(rec[2].shape)))
+    return tuple(sig)
+
+
 class GradBank:
     """Weight-correlation scratch + flat gradient buckets for the convs that appear on a tape."""
 
@@ -72,28 +83,47 @@ class GradBank:
             if rec[0] in ("conv", "stem") and id(rec[1]) not in seen:
                 seen.add(id(rec[1]))
                 convs.append(rec[1])
-        self.key = tuple(sorted(seen))
+        self.key = _tape_signature(tape)
         dev = next(model.parameters()).device
         members: Dict[int, List[NormConv2d]] = {}
         for slot in bank.slots:
             members[id(slot[0])] = slot
-        # ---- correlation scratch: gt [K, pitch] + dy_sum [pitch] per conv slot / stem ----
-        off = 0
-        place = {}
-        for cv in convs:
-            if cv._vub_stem:
-                k, pitch = cv.in_channels, cv.out_channels
-            else:
+        # ---- correlation scratch per conv slot: partial correlations gt [n_split, rows = output channels, K] and
+        #      partial sums dy_sum [n_split, rows], written (not accumulated) by vub_conv_wgrad; stems keep one
+        #      atomically accumulated slice that is zeroed every step ----
+        shapes = {}
+        for rec in tape.recs:
+            if rec[0] == "conv" and id(rec[1]) not in shapes:
+                _, cv, srcs, _, _, d2s = rec
                 cw = bank.get(cv)
-                k, pitch = cw.nsrc * cw.ksize * cw.ksize * cw.c_src, cw.cout_k
-            place[id(cv)] = (off, k, pitch)
-            off += (k + 1) * pitch
+                xs = tuple(srcs[0][0].pick(srcs[0][1]).shape)
+                B_, H_, W_, _ = xs
+                ho, wo = H_ // cw.stride, W_ // cw.stride
+                dys = (B_, 2 * ho, 2 * wo, cw.cout_k // 4) if d2s else (B_, ho, wo, cw.cout_k)
+                shapes[id(cv)] = ops.wgrad_splits(dys, xs, cw.nsrc, cw.ksize, cw.stride, d2s)
+        off, stem_floats = 0, 0
+        place = {}
+        for cv in convs:  # stems first: they share one zeroed region at the front of the buffer
+            if cv._vub_stem:
+                k, rows = cv.in_channels, cv.out_channels
+                place[id(cv)] = (off, k, rows, 1)
+                off += (k + 1) * rows
+        stem_floats = off
+        for cv in convs:
+            if not cv._vub_stem:
+                cw = bank.get(cv)
+                k, rows = cw.nsrc * cw.ksize * cw.ksize * cw.c_src, cw.cout_k
+                ns = shapes[id(cv)]
+                off = (off + 3) // 4 * 4
+                place[id(cv)] = (off, k, rows, ns)
+                off += ns * (k + 1) * rows
         self._gbuf = torch.zeros(off, dtype=torch.float32, device=dev)
+        self._stem_region = self._gbuf[:stem_floats]
         self.gt, self.dy_sum = {}, {}
         for cv in convs:
-            o, k, pitch = place[id(cv)]
-            self.gt[id(cv)] = self._gbuf[o:o + k * pitch].view(k, pitch)
-            self.dy_sum[id(cv)] = self._gbuf[o + k * pitch:o + (k + 1) * pitch]
+            o, k, rows, ns = place[id(cv)]
+            self.gt[id(cv)] = self._gbuf[o:o + ns * k * rows].view(ns, rows, k)
+            self.dy_sum[id(cv)] = self._gbuf[o + ns * k * rows:o + ns * (k + 1) * rows].view(ns, rows)
         # ---- gradient buckets per owner, parameters in registration order ----
         live = []  # every NormConv2d that receives gradients
         for cv in convs:
@@ -142,7 +172,9 @@ class GradBank:
                     c_src = cw.c_src
                     col0 = sum(x.out_channels for x in members[id(cv)][:members[id(cv)].index(m)])
                 e.cout, e.cin, e.ktaps, e.c_src = m.out_channels, m.in_channels, m.kernel_size ** 2, c_src
-                e.gt_pitch, e.gt_col0, e.row_start = place[id(cv)][2], col0, rows
+                e.gt_pitch, e.gt_col0, e.row_start = place[id(cv)][1], col0, rows
+                ns = place[id(cv)][3]
+                e.n_split, e.split_stride, e.sum_stride = ns, place[id(cv)][1] * place[id(cv)][2], place[id(cv)][2]
                 rows += m.out_channels
                 entries.append(e)
             arr = (N.WnbEntry * len(entries))(*entries)
@@ -151,13 +183,13 @@ class GradBank:
         self._ptr_key = tuple(p.data_ptr() for ps in self.params.values() for p in ps)
 
     def matches(self, tape: Tape, model) -> bool:
-        ids = {id(r[1]) for r in tape.recs if r[0] in ("conv", "stem")}
-        if tuple(sorted(ids)) != self.key:
+        if _tape_signature(tape) != self.key:
             return False
         return self._ptr_key == tuple(p.data_ptr() for ps in self.params.values() for p in ps)
 
     def zero(self) -> None:
-        self._gbuf.zero_()
+        if self._stem_region.numel():
+            self._stem_region.zero_()  # only the stems accumulate (atomics); conv partials are overwritten
 
     def finish_owner(self, owner: str) -> None:
         """All correlations of this sub-network are complete: produce its parameter gradients."""
@@ -226,7 +258,7 @@ def run_backward(model, bank: WeightBank, tape: Tape, d_imgs: Optional[torch.Ten
         elif kind == "stem":
             _, conv, x, out = rec
             if out.grad is not None:
-                ops.stem_bwd(x, out.grad, gb.gt[id(conv)], gb.dy_sum[id(conv)])
+                ops.stem_bwd(x, out.grad, gb.gt[id(conv)][0], gb.dy_sum[id(conv)][0])
                 out.grad = None
         else:
             r = rec[1]

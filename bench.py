@@ -221,10 +221,12 @@ def run_train_section(args, device, world, rank, barrier, peaks):
     red = getattr(model, "_vub_reducer", None)
     # per-kernel timing of one instrumented step (CUDA events around every launch, outside the timed region)
     tk = []
+    # every rank runs the instrumented step (it contains the gradient all-reduce); only rank 0 times it
+    from bdvs_b200.profiler import KernelProfiler
+    with (KernelProfiler() if rank == 0 else contextlib.nullcontext()) as kp:
+        step(x, c, target)
+    barrier()
     if rank == 0:
-        from bdvs_b200.profiler import KernelProfiler
-        with KernelProfiler() as kp:
-            step(x, c, target)
         prof = kp.summary()
         tot = sum(r["ms"] for r in prof.values())
         agg = {}

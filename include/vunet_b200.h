@@ -182,25 +182,31 @@ int vub_conv_dgrad(const vub_dgrad_desc* d, void* stream);
 
 /*
  * Weight correlation of a NormConv2d (the raw part of convolution_backward w.r.t. the weight):
- *     gt[(src, tap, c)][co] += sum_pixels dy[pix, co] * x_src[pix + tap offset, c]
- *     dy_sum[co]            += sum_pixels dy[pix, co]
- * on tcgen05 with both operands MN-major (pixels are the contraction index).  fp32, ACCUMULATED with
- * red.global.add (the caller zeroes gt / dy_sum once per step); split over pixel ranges across CTAs.
+ *     gt[split][co][(src, tap, c)] = sum_{pixels of the split} dy[pix, co] * x_src[pix + tap offset, c]
+ *     dy_sum[split][co]            = sum_{pixels of the split} dy[pix, co]
+ * on tcgen05 with both operands MN-major (pixels are the contraction index), fp32.  The pixel range is split
+ * over CTAs; every split WRITES its own slice (plain stores: no atomics, bit-reproducible, nothing to zero) and
+ * vub_wn_bwd sums the slices.  vub_conv_wgrad_splits returns the split count that fills the GPU for a given
+ * shape (pointers ignored); the caller sizes gt / dy_sum for the n_split it passes.
  * x[s] is the tensor the forward conv read (the ELU'd copy inside a VunetRNB).
  */
 typedef struct vub_wgrad_desc {
   const void* dy;            /* as in vub_dgrad_desc */
   const void* x[2];          /* NHWC bf16 [batch, hin, win, c_src] */
-  float* gt;                 /* [nsrc*ksize*ksize*c_src][gt_pitch] */
-  float* dy_sum;             /* [gt_pitch] */
+  float* gt;                 /* [n_split][cout_k][gt_pitch] (slices split_stride floats apart) */
+  float* dy_sum;             /* [n_split][cout_k] (slices sum_stride floats apart) */
+  int64_t split_stride;
+  int32_t sum_stride;
+  int32_t n_split;           /* 1 .. min(#64-pixel tiles, 1024) */
   int32_t nsrc, c_src;
   int32_t batch, hin, win;
   int32_t cout_k;            /* channels of dy (multiple of 32; out_conv: 32 with 3 valid) */
-  int32_t gt_pitch;          /* >= cout_k */
+  int32_t gt_pitch;          /* row pitch of gt in floats: >= nsrc*ksize*ksize*c_src */
   int32_t ksize, stride;
   uint32_t flags;            /* VUB_CONV_D2S */
 } vub_wgrad_desc;
 
+int32_t vub_conv_wgrad_splits(const vub_wgrad_desc* d);
 int vub_conv_wgrad(const vub_wgrad_desc* d, void* stream);
 
 /*
@@ -216,8 +222,9 @@ typedef struct vub_wnb_entry {
   const float* g;
   const float* gamma;
   const float* bias;
-  const float* gt;           /* this conv's correlation: element (k, co) at gt[k*gt_pitch + gt_col0 + co] */
-  const float* dy_sum;       /* element co at dy_sum[gt_col0 + co] */
+  const float* gt;           /* partial correlations: element (split, co, k) at
+                                gt[split*split_stride + (gt_col0 + co)*gt_pitch + k] */
+  const float* dy_sum;       /* element (split, co) at dy_sum[split*sum_stride + gt_col0 + co] */
   float* d_v;
   float* d_g;
   float* d_gamma;
@@ -226,6 +233,9 @@ typedef struct vub_wnb_entry {
   int32_t cout, cin, ktaps, c_src;
   int32_t gt_pitch, gt_col0;
   int32_t row_start;
+  int32_t n_split;           /* slices to sum (>= 1) */
+  int64_t split_stride;
+  int32_t sum_stride;
   int32_t pad;
 } vub_wnb_entry;
 
@@ -234,8 +244,8 @@ int vub_wn_bwd(const vub_wnb_entry* table_dev, int32_t n_entries, int32_t total_
 
 /*
  * Backward of the stem (first 1x1 NormConv2d on the NCHW fp32 input, vub_stem_fwd): correlation of the
- * output gradient with the input, gt[ci][co] += sum dy[pix, co]*x[pix, ci], dy_sum[co] += sum dy.
- * The stem needs no data gradient (its input is the image).  gt pitch = cout.
+ * output gradient with the input, gt[co][ci] += sum dy[pix, co]*x[pix, ci], dy_sum[co] += sum dy.
+ * The stem needs no data gradient (its input is the image).  gt pitch = cx.
  */
 int vub_stem_bwd(const float* x_nchw, const void* dy_nhwc, int32_t batch, int32_t cx, int32_t h, int32_t w,
                  int32_t cout, float* gt, float* dy_sum, void* stream);

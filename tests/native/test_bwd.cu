@@ -192,7 +192,7 @@ static void run_wgrad(const BwdCase& c) {
   const size_t dy_elems = (size_t)c.B * Ho * Wo * c.cout_k;
   const size_t x_elems = (size_t)c.B * c.H * c.W * c.c_src;
   const int KR = c.nsrc * taps * c.c_src;
-  const int pitch = c.cout_k + 32;  // exercise gt_pitch > cout_k
+  const int pitch = KR + 32;  // exercise gt_pitch > K
   std::vector<float> dy = rand_bf16(dy_elems, 1.0f), x[2];
   for (int s = 0; s < c.nsrc; ++s) x[s] = rand_bf16(x_elems, 1.0f);
   DyView dv{&dy, Ho, Wo, c.cout_k, c.d2s};
@@ -222,14 +222,21 @@ static void run_wgrad(const BwdCase& c) {
   d_dy.up(to_bf16(dy));
   d_x0.up(to_bf16(x[0]));
   if (c.nsrc == 2) d_x1.up(to_bf16(x[1]));
-  DevBuf<float> d_gt((size_t)KR * pitch), d_sum(pitch);
-  d_gt.zero();
-  d_sum.zero();
   vub_wgrad_desc d;
   memset(&d, 0, sizeof(d));
-  d.dy = d_dy.p; d.x[0] = d_x0.p; d.x[1] = c.nsrc == 2 ? d_x1.p : nullptr; d.gt = d_gt.p; d.dy_sum = d_sum.p;
   d.nsrc = c.nsrc; d.c_src = c.c_src; d.batch = c.B; d.hin = c.H; d.win = c.W; d.cout_k = c.cout_k; d.gt_pitch = pitch;
   d.ksize = c.ksize; d.stride = c.stride; d.flags = c.d2s ? VUB_CONV_D2S : 0;
+  const int ns = vub_conv_wgrad_splits(&d);
+  if (ns <= 0) {
+    printf("[FAIL] wgrad %-58s splits rc=%d (%s)\n", c.name, ns, vub_last_error());
+    ++g_fail;
+    return;
+  }
+  const size_t slice = (size_t)c.cout_k * pitch + 64;  // exercise split_stride > cout_k * pitch
+  DevBuf<float> d_gt(slice * ns), d_sum((size_t)(c.cout_k + 8) * ns);
+  CK(cudaMemset(d_gt.p, 0, d_gt.n * sizeof(float)));  // pad regions must stay untouched (checked below)
+  d.dy = d_dy.p; d.x[0] = d_x0.p; d.x[1] = c.nsrc == 2 ? d_x1.p : nullptr; d.gt = d_gt.p; d.dy_sum = d_sum.p;
+  d.n_split = ns; d.split_stride = (int64_t)slice; d.sum_stride = c.cout_k + 8;
   const int rc = vub_conv_wgrad(&d, nullptr);
   if (rc) {
     printf("[FAIL] wgrad %-58s launch rc=%d (%s)\n", c.name, rc, vub_last_error());
@@ -241,11 +248,20 @@ static void run_wgrad(const BwdCase& c) {
   auto sm = d_sum.down();
   const float scale = sqrtf((float)c.B * Ho * Wo);  // typical magnitude of a correlation of +-1 noise
   Cmp cg, cs, cz;
-  for (int k = 0; k < KR; ++k) {
-    for (int co = 0; co < c.cout_k; ++co) cg.add(gt[(size_t)k * pitch + co], (float)ref[(size_t)k * c.cout_k + co], 2e-3f * scale, 2e-3f);
-    for (int co = c.cout_k; co < pitch; ++co) cz.add(gt[(size_t)k * pitch + co], 0.f, 0.f, 0.f);
+  for (int co = 0; co < c.cout_k; ++co) {
+    for (int k = 0; k < KR; ++k) {
+      double g = 0;
+      for (int sp = 0; sp < ns; ++sp) g += gt[sp * slice + (size_t)co * pitch + k];
+      cg.add((float)g, (float)ref[(size_t)k * c.cout_k + co], 2e-3f * scale, 2e-3f);
+    }
+    for (int sp = 0; sp < ns; ++sp)
+      for (int k = KR; k < pitch; ++k) cz.add(gt[sp * slice + (size_t)co * pitch + k], 0.f, 0.f, 0.f);
   }
-  for (int co = 0; co < c.cout_k; ++co) cs.add(sm[co], (float)ref_sum[co], 2e-3f * scale, 2e-3f);
+  for (int co = 0; co < c.cout_k; ++co) {
+    double g = 0;
+    for (int sp = 0; sp < ns; ++sp) g += sm[(size_t)sp * (c.cout_k + 8) + co];
+    cs.add((float)g, (float)ref_sum[co], 2e-3f * scale, 2e-3f);
+  }
   report(std::string("wgrad ") + c.name + " gt", cg);
   report(std::string("wgrad ") + c.name + " dy_sum", cs);
   report(std::string("wgrad ") + c.name + " pad columns untouched", cz);
@@ -310,14 +326,16 @@ static void test_wn_bwd() {
   int rows = 0;
   for (int l = 0; l < nl; ++l) {
     const L& q = layers[l];
-    const int taps = q.k * q.k, len = q.cin * taps, pitch = q.cout + 5, col0 = 3;
+    const int taps = q.k * q.k, len = q.cin * taps, pitch = len + 4, col0 = 3;
     v[l].resize((size_t)q.cout * len);
     for (auto& t : v[l]) t = frand();
     g[l].resize(q.cout); ga[l].resize(q.cout); bi[l].resize(q.cout);
     for (int i = 0; i < q.cout; ++i) { g[l][i] = 0.5f + fabsf(frand()); ga[l][i] = 0.7f + 0.6f * fabsf(frand()); bi[l][i] = 0.1f * frand(); }
-    gt[l].resize((size_t)len * pitch);
+    const int ns = l + 1;  // 1..4 pixel splits, summed by the kernel
+    const size_t sstride = (size_t)(q.cout + col0) * pitch + 12;
+    gt[l].resize(sstride * ns);
     for (auto& t : gt[l]) t = 3.f * frand();
-    sm[l].resize(pitch);
+    sm[l].resize((size_t)(q.cout + col0 + 2) * ns);
     for (auto& t : sm[l]) t = 5.f * frand();
     auto mk = [&](const std::vector<float>& h) { auto* b = new DevBuf<float>(h.size()); b->up(h); bufs[l].push_back(b); return b->p; };
     auto out = [&](size_t n) { auto* b = new DevBuf<float>(n); bufs[l].push_back(b); return b->p; };
@@ -326,6 +344,7 @@ static void test_wn_bwd() {
     e.v = mk(v[l]); e.g = mk(g[l]); e.gamma = mk(ga[l]); e.bias = mk(bi[l]); e.gt = mk(gt[l]); e.dy_sum = mk(sm[l]);
     e.d_v = out(v[l].size()); e.d_g = out(q.cout); e.d_gamma = out(q.cout); e.d_beta = out(q.cout); e.d_bias = out(q.cout);
     e.cout = q.cout; e.cin = q.cin; e.ktaps = taps; e.c_src = q.c_src; e.gt_pitch = pitch; e.gt_col0 = col0; e.row_start = rows;
+    e.n_split = ns; e.split_stride = (int64_t)sstride; e.sum_stride = q.cout + col0 + 2;
     rows += q.cout;
   }
   vub_wnb_entry* dtab;
@@ -337,17 +356,23 @@ static void test_wn_bwd() {
   Cmp cv, cs;
   for (int l = 0; l < nl; ++l) {
     const L& q = layers[l];
-    const int taps = q.k * q.k, len = q.cin * taps, pitch = q.cout + 5, col0 = 3;
+    const int taps = q.k * q.k, len = q.cin * taps, pitch = len + 4, col0 = 3;
+    const int ns = l + 1;
+    const size_t sstride = (size_t)(q.cout + col0) * pitch + 12;
     auto dv = bufs[l][6]->down(); auto dg = bufs[l][7]->down(); auto dga = bufs[l][8]->down();
     auto dbe = bufs[l][9]->down(); auto dbi = bufs[l][10]->down();
     for (int co = 0; co < q.cout; ++co) {
       double ss = 0, vg = 0;
       auto G = [&](int i) {
         const int ci = i / taps, t = i % taps, s = ci / q.c_src, cs_ = ci % q.c_src;
-        return (double)gt[l][(size_t)((s * taps + t) * q.c_src + cs_) * pitch + col0 + co];
+        double g = 0;
+        for (int sp = 0; sp < ns; ++sp) g += gt[l][sp * sstride + (size_t)(col0 + co) * pitch + (s * taps + t) * q.c_src + cs_];
+        return g;
       };
       for (int i = 0; i < len; ++i) { const double x = v[l][(size_t)co * len + i]; ss += x * x; vg += x * G(i); }
-      const double inv = 1.0 / sqrt(ss), dot = vg * inv, S = sm[l][col0 + co];
+      double S = 0;
+      for (int sp = 0; sp < ns; ++sp) S += sm[l][(size_t)sp * (q.cout + col0 + 2) + col0 + co];
+      const double inv = 1.0 / sqrt(ss), dot = vg * inv;
       for (int i = 0; i < len; ++i)
         cv.add(dv[(size_t)co * len + i], (float)(ga[l][co] * g[l][co] * inv * (G(i) - v[l][(size_t)co * len + i] * inv * dot)), 1e-4f, 1e-4f);
       cs.add(dg[co], (float)(ga[l][co] * dot), 1e-4f, 1e-4f);
@@ -384,7 +409,7 @@ static void test_stem_bwd(int B, int cx, int H, int W) {
       double a = 0;
       for (int n = 0; n < B; ++n)
         for (int p = 0; p < H * W; ++p) a += (double)x[((size_t)n * cx + ci) * H * W + p] * dy[((size_t)n * H * W + p) * cout + co];
-      c.add(gt[ci * cout + co], (float)a, 1e-3f * scale, 1e-3f);
+      c.add(gt[co * cx + ci], (float)a, 1e-3f * scale, 1e-3f);
     }
   }
   char nm[96];
@@ -449,13 +474,15 @@ static void perf_bwd(const char* name, int B, int H, int W, int c_src, int nsrc,
   const int KR = nsrc * taps * c_src;
   DevBuf<__nv_bfloat16> d_dy(dy_elems), d_x0(x_elems), d_x1(nsrc == 2 ? x_elems : 8), d_wd((size_t)nsrc * c_src * taps * cout_k);
   DevBuf<__nv_bfloat16> d_dx0(x_elems), d_dx1(nsrc == 2 ? x_elems : 8);
-  DevBuf<float> d_gt((size_t)KR * cout_k), d_sum(cout_k);
-  d_dy.zero(); d_x0.zero(); d_x1.zero(); d_wd.zero(); d_gt.zero(); d_sum.zero();
   vub_wgrad_desc wg;
   memset(&wg, 0, sizeof(wg));
-  wg.dy = d_dy.p; wg.x[0] = d_x0.p; wg.x[1] = nsrc == 2 ? d_x1.p : nullptr; wg.gt = d_gt.p; wg.dy_sum = d_sum.p;
-  wg.nsrc = nsrc; wg.c_src = c_src; wg.batch = B; wg.hin = H; wg.win = W; wg.cout_k = cout_k; wg.gt_pitch = cout_k;
+  wg.nsrc = nsrc; wg.c_src = c_src; wg.batch = B; wg.hin = H; wg.win = W; wg.cout_k = cout_k; wg.gt_pitch = KR;
   wg.ksize = ksize; wg.stride = stride; wg.flags = d2s ? VUB_CONV_D2S : 0;
+  const int ns = vub_conv_wgrad_splits(&wg) > 0 ? vub_conv_wgrad_splits(&wg) : 1;
+  DevBuf<float> d_gt((size_t)KR * cout_k * ns), d_sum((size_t)cout_k * ns);
+  d_dy.zero(); d_x0.zero(); d_x1.zero(); d_wd.zero();
+  wg.dy = d_dy.p; wg.x[0] = d_x0.p; wg.x[1] = nsrc == 2 ? d_x1.p : nullptr; wg.gt = d_gt.p; wg.dy_sum = d_sum.p;
+  wg.n_split = ns; wg.split_stride = (int64_t)KR * cout_k; wg.sum_stride = cout_k;
   vub_dgrad_desc dg;
   memset(&dg, 0, sizeof(dg));
   dg.dy = d_dy.p; dg.wd = d_wd.p; dg.dx[0] = d_dx0.p; dg.dx[1] = nsrc == 2 ? d_dx1.p : nullptr;
@@ -465,7 +492,11 @@ static void perf_bwd(const char* name, int B, int H, int W, int c_src, int nsrc,
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   const double flop = 2.0 * B * Ho * Wo * (double)cout_k * KR;
-  for (int which = 0; which < 2; ++which) {
+  for (int which = 0; which < 3; ++which) {
+    if (which == 2) {  // data gradient without the ELU' mask (epilogue reads nothing)
+      dg.mask_elu[0] = nullptr;
+      dg.mask_elu[1] = nullptr;
+    }
     auto go = [&]() { return which == 0 ? vub_conv_wgrad(&wg, nullptr) : vub_conv_dgrad(&dg, nullptr); };
     int rc = 0;
     for (int i = 0; i < 3; ++i) rc |= go();
@@ -479,14 +510,24 @@ static void perf_bwd(const char* name, int B, int H, int W, int c_src, int nsrc,
     float ms;
     CK(cudaEventElapsedTime(&ms, e0, e1));
     ms /= iters;
-    const double bytes = which == 0 ? 2.0 * (dy_elems + nsrc * (double)x_elems) : 2.0 * (dy_elems + 2.0 * nsrc * (double)x_elems);
-    printf("[PERF] %s %-40s %8.3f ms  %7.1f TFLOP/s  %7.1f GB/s(algorithmic)\n", which ? "dgrad" : "wgrad", name, ms,
+    const double bytes = which == 0 ? 2.0 * (dy_elems + nsrc * (double)x_elems)
+                                    : 2.0 * (dy_elems + (which == 1 ? 2.0 : 1.0) * nsrc * (double)x_elems);
+    printf("[PERF] %s %-40s %8.3f ms  %7.1f TFLOP/s  %7.1f GB/s(algorithmic)\n",
+           which == 0 ? "wgrad" : (which == 1 ? "dgrad" : "dgrad(no mask)"), name, ms,
            flop / ms * 1e-9, bytes / ms * 1e-6);
   }
 }
 
 int main(int argc, char** argv) {
   const bool perf = argc > 1 && !strcmp(argv[1], "perf");
+  if (!perf && !getenv("VUB_ENABLE_SLAB")) setenv("VUB_ENABLE_SLAB", "1", 1);  // correctness runs cover the opt-in slab kernel
+  if (argc >= 11 && !strcmp(argv[1], "layer")) {
+    // layer B H W c_src nsrc cout_k k stride d2s  -> time wgrad + dgrad of one layer shape (for ncu captures)
+    int a[9];
+    for (int i = 0; i < 9; ++i) a[i] = atoi(argv[2 + i]);
+    perf_bwd("layer", a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8] != 0);
+    return 0;
+  }
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
   printf("device: %s  SMs=%d  abi=%d\n", prop.name, prop.multiProcessorCount, vub_abi_version());
@@ -512,6 +553,29 @@ int main(int argc, char** argv) {
   };
   for (const BwdCase& c : cases) run_dgrad(c);
   for (const BwdCase& c : cases) run_wgrad(c);
+  // shapes the activation-slab kernel takes over (data gradient with mirrored taps)
+  const BwdCase slab_cases[] = {
+      {"slab 3x3 128->128 @32x32 B2 mask+add+add2 inplace",   2, 32, 32, 128, 1, 128, 3, 1, false, true, true, true, true},
+      {"slab 3x3 [128|128]->128 @64x64 B1 cat mask+add2",     1, 64, 64, 128, 2, 128, 3, 1, false, true, false, true, false},
+      {"slab 3x3 128->256 (wide dy) @32x32 B2 addend",        2, 32, 32, 128, 1, 256, 3, 1, false, false, true, false, false},
+      {"slab 3x3 128->64 @64x64 B1 plain",                    1, 64, 64, 128, 1, 64, 3, 1, false, false, false, false, false},
+  };
+  for (const BwdCase& c : slab_cases) run_dgrad(c);
+  // shapes the row-streaming kernel takes over in data-gradient mode (width >= 128, <= 64 channels)
+  const BwdCase rows_cases[] = {
+      {"rows 1x1 32->32 @8x256 B2 mask+addend inplace",       2, 8, 256, 32, 1, 32, 1, 1, false, true, true, false, true},
+      {"rows 3x3 64->64 @8x128 B2 mask+add+add2 inplace",     2, 8, 128, 64, 1, 64, 3, 1, false, true, true, true, true},
+      {"rows 3x3 [64|64]->64 @16x128 B1 cat (two launches)",  1, 16, 128, 64, 2, 64, 3, 1, false, true, false, true, false},
+      {"rows 1x1 64->64 @4x128 B3 mask",                      3, 4, 128, 64, 1, 64, 1, 1, false, true, false, false, false},
+      {"rows 3x3 32->3(32) out_conv @32x128 B2",              2, 32, 128, 32, 1, 32, 3, 1, false, false, false, false, false},
+  };
+  for (const BwdCase& c : rows_cases) run_dgrad(c);
+  setenv("VUB_ROWS_GRID", "5", 1);  // few persistent CTAs: row ranges cross image boundaries, ring wraps
+  {
+    const BwdCase c1 = {"rows grid=5: 3x3 [32|32]->32 @32x128 B5 cat mask+add2", 5, 32, 128, 32, 2, 32, 3, 1, false, true, false, true, false};
+    run_dgrad(c1);
+  }
+  unsetenv("VUB_ROWS_GRID");
   {
     const BwdCase big = {"3x3 64->64 @128x128 B2 (many pixel tiles per CTA)", 2, 128, 128, 64, 1, 64, 3, 1, false, true, false, true, false};
     run_wgrad(big);

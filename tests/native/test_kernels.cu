@@ -426,6 +426,7 @@ static void perf_conv(const char* name, int B, int H, int W, int c_src, int nsrc
 
 int main(int argc, char** argv) {
   const bool perf = argc > 1 && !strcmp(argv[1], "perf");
+  if (!perf && !getenv("VUB_ENABLE_SLAB")) setenv("VUB_ENABLE_SLAB", "1", 1);  // correctness runs cover the opt-in slab kernel
   if (argc >= 14 && !strcmp(argv[1], "layer")) {
     // layer B H W c_src nsrc cout k stride res dual d2s stages  -> time one layer shape (for ncu captures)
     int a[12];
@@ -466,6 +467,16 @@ int main(int argc, char** argv) {
       {"3x3 128->128 @32x32 B2 stages=5",                  2, 32, 32, 128, 1, 128, 128, 3, 1, true, true, true, false, false, false, 5},
   };
   for (const ConvCase& c : cases) run_conv_case(c);
+  // activation-slab kernel (3x3 stride 1, >= 64 channels per source, 64x64 / 32x32)
+  const ConvCase slab_cases[] = {
+      {"slab 3x3 128->128 @64x64 B2 +res dual",            2, 64, 64, 128, 1, 128, 128, 3, 1, true, true, true, false, false, false, 0},
+      {"slab 3x3 [128|128]->128 @32x32 B3 cat +res dual",  3, 32, 32, 128, 2, 128, 128, 3, 1, true, true, true, false, false, false, 0},
+      {"slab 3x3 64->128 @64x64 B1 raw",                   1, 64, 64, 64, 1, 128, 128, 3, 1, false, true, false, false, false, false, 0},
+      {"slab 3x3 128->256 D2S @64x64 B1 dual",             1, 64, 64, 128, 1, 256, 256, 3, 1, false, true, true, true, false, false, 0},
+      {"slab 3x3 128->512 D2S @32x32 B2 elu",              2, 32, 32, 128, 1, 512, 512, 3, 1, false, false, true, true, false, false, 0},
+      {"slab 3x3 128->128 @32x32 B41 (items > SMs) +res",  41, 32, 32, 128, 1, 128, 128, 3, 1, true, true, true, false, false, false, 0},
+  };
+  for (const ConvCase& c : slab_cases) run_conv_case(c);
   // row-streaming kernel (output width >= 128, <= 64 channels per source)
   const ConvCase row_cases[] = {
       {"rows 3x3 64->64 @16x128 B2 +res dual",             2, 16, 128, 64, 1, 64, 64, 3, 1, true, true, true, false, false, false, 0},

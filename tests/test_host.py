@@ -120,8 +120,8 @@ def test_library_loads_and_exports_every_symbol():
     assert ctypes.sizeof(_native.ConvDesc) == 9 * 8 + 11 * 4 + 4  # padded to 8
     assert ctypes.sizeof(_native.WnEntry) == 8 * 8 + 6 * 4 + 8 + 2 * 4
     assert ctypes.sizeof(_native.DgradDesc) == 10 * 8 + 9 * 4 + 4  # padded to 8
-    assert ctypes.sizeof(_native.WgradDesc) == 5 * 8 + 10 * 4
-    assert ctypes.sizeof(_native.WnbEntry) == 11 * 8 + 8 * 4
+    assert ctypes.sizeof(_native.WgradDesc) == 6 * 8 + 12 * 4
+    assert ctypes.sizeof(_native.WnbEntry) == 11 * 8 + 8 * 4 + 8 + 2 * 4
 
 
 def test_bad_arguments_are_reported_not_crashed():
@@ -152,4 +152,9 @@ def test_bad_arguments_are_reported_not_crashed():
     w = _native.WgradDesc()
     w.dy = 16; w.x[0] = 16; w.gt = 16; w.dy_sum = 16
     w.nsrc, w.c_src, w.batch, w.hin, w.win, w.cout_k, w.gt_pitch, w.ksize, w.stride = 1, 32, 1, 8, 8, 64, 32, 3, 1
-    assert lib.vub_conv_wgrad(ctypes.byref(w), None) == -2  # gt_pitch < cout_k
+    w.n_split = 1
+    assert lib.vub_conv_wgrad(ctypes.byref(w), None) == -2  # gt_pitch < K = 288
+    w.gt_pitch = 288
+    assert lib.vub_conv_wgrad_splits(ctypes.byref(w)) == 1  # one 64-pixel tile -> one split (pure host planning)
+    w.n_split = 5
+    assert lib.vub_conv_wgrad(ctypes.byref(w), None) == -2  # more splits than pixel tiles
