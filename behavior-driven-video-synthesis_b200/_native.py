@@ -32,6 +32,8 @@ EXPORTED_SYMBOLS = (
     "vub_nchw_f32_to_nhwc_bf16",
     "vub_nhwc_bf16_to_nchw_f32",
     "vub_nchw_f32_to_nhwc_bf16_pad",
+    "vub_conv_fwd_f32",
+    "vub_nchw_f32_to_nhwc_f32",
     "vub_conv_dgrad",
     "vub_conv_wgrad",
     "vub_conv_wgrad_splits",
@@ -89,6 +91,31 @@ class WnEntry(C.Structure):
         ("wd", C.c_void_p),
         ("wd_cout", C.c_int32),
         ("wd_col0", C.c_int32),
+        ("w32", C.c_void_p),
+    ]
+
+
+class ConvF32Desc(C.Structure):
+    """Mirror of ``vub_conv_f32_desc`` (fp32 validation path)."""
+
+    _fields_ = [
+        ("x", C.c_void_p * 2),
+        ("w", C.c_void_p),
+        ("scale", C.c_void_p),
+        ("shift", C.c_void_p),
+        ("residual", C.c_void_p),
+        ("out_raw", C.c_void_p),
+        ("out_elu", C.c_void_p),
+        ("nsrc", C.c_int32),
+        ("c_src", C.c_int32),
+        ("batch", C.c_int32),
+        ("hin", C.c_int32),
+        ("win", C.c_int32),
+        ("cout", C.c_int32),
+        ("w_pitch", C.c_int32),
+        ("ksize", C.c_int32),
+        ("stride", C.c_int32),
+        ("flags", C.c_uint32),
     ]
 
 
@@ -205,6 +232,10 @@ def _declare(lib: C.CDLL) -> None:
     lib.vub_nhwc_bf16_to_nchw_f32.argtypes = [vp, i32, i32, i32, i32, fp, vp]
     lib.vub_nchw_f32_to_nhwc_bf16_pad.restype = C.c_int
     lib.vub_nchw_f32_to_nhwc_bf16_pad.argtypes = [fp, i32, i32, i32, i32, i32, vp, vp]
+    lib.vub_conv_fwd_f32.restype = C.c_int
+    lib.vub_conv_fwd_f32.argtypes = [C.POINTER(ConvF32Desc), vp]
+    lib.vub_nchw_f32_to_nhwc_f32.restype = C.c_int
+    lib.vub_nchw_f32_to_nhwc_f32.argtypes = [fp, i32, i32, i32, i32, fp, fp, vp]
     lib.vub_conv_dgrad.restype = C.c_int
     lib.vub_conv_dgrad.argtypes = [C.POINTER(DgradDesc), vp]
     lib.vub_conv_wgrad_splits.restype = i32

@@ -63,13 +63,24 @@ __global__ void __launch_bounds__(kWnThreads)
   }
   ss = block_sum(ss, red);
   const float inv = 1.0f / sqrtf(ss);
-  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(e.w_packed) + (size_t)co * e.ktot;
-  for (int i = threadIdx.x; i < len; i += kWnThreads) {
-    const int ci = i / e.ktaps;
-    const int tap = i - ci * e.ktaps;
-    const int src = ci / e.c_src;
-    const int cs = ci - src * e.c_src;
-    out[(src * e.ktaps + tap) * e.c_src + cs] = __float2bfloat16_rn(v[i] * inv);
+  if (e.w_packed != nullptr) {
+    __nv_bfloat16* out = static_cast<__nv_bfloat16*>(e.w_packed) + (size_t)co * e.ktot;
+    for (int i = threadIdx.x; i < len; i += kWnThreads) {
+      const int ci = i / e.ktaps;
+      const int tap = i - ci * e.ktaps;
+      const int src = ci / e.c_src;
+      const int cs = ci - src * e.c_src;
+      out[(src * e.ktaps + tap) * e.c_src + cs] = __float2bfloat16_rn(v[i] * inv);
+    }
+  }
+  if (e.w32 != nullptr) {  // fp32 validation path: [k][co], unscaled
+    for (int i = threadIdx.x; i < len; i += kWnThreads) {
+      const int ci = i / e.ktaps;
+      const int tap = i - ci * e.ktaps;
+      const int src = ci / e.c_src;
+      const int cs = ci - src * e.c_src;
+      e.w32[(size_t)((src * e.ktaps + tap) * e.c_src + cs) * e.wd_cout + e.wd_col0 + co] = v[i] * inv;
+    }
   }
   if (e.wd != nullptr) {
     // data-gradient weights: row = input channel (source-major), column = (tap, output channel), scaled

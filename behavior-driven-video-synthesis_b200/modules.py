@@ -107,6 +107,7 @@ class WeightBank:
         self._views = {}
         self._with_wd = False
         self.tape = None  # training: list the forward pass appends its records to (training.Tape)
+        self.precision = "bf16"  # validation.WeightBank32 says "fp32"
 
     @staticmethod
     def for_module(root: nn.Module) -> "WeightBank":
@@ -298,6 +299,12 @@ class NormConv2d(nn.Module):
              want_raw=True, want_elu=True, d2s=False) -> Act:
         """``srcs``: the concatenated inputs as (activation, "raw" | "elu") pairs; ``residual`` is added raw."""
         cw = bank.get(self)
+        if bank.precision == "fp32":  # validation mode: same schedule, fp32 CUDA-core conv
+            raw, elu = ops.conv_fwd32([a.pick(m) for a, m in srcs], cw.w32, cw.scale, cw.shift, cout=cw.cout,
+                                      ksize=cw.ksize, stride=cw.stride,
+                                      residual=None if residual is None else residual.raw, want_raw=want_raw,
+                                      want_elu=want_elu, d2s=d2s)
+            return Act(raw, elu)
         raw, elu = ops.conv_fwd([a.pick(m) for a, m in srcs], cw.w, cw.scale, cw.shift, ksize=cw.ksize,
                                 stride=cw.stride, residual=None if residual is None else residual.raw,
                                 want_raw=want_raw, want_elu=want_elu, d2s=d2s)
@@ -309,6 +316,10 @@ class NormConv2d(nn.Module):
     def _run_f32(self, bank: WeightBank, srcs: Sequence[Tuple[Act, str]], layout: str):
         """fp32 output (latent head input NHWC / image NCHW).  Returns (tensor, gradient slot or None)."""
         cw = bank.get(self)
+        if bank.precision == "fp32":
+            out, _ = ops.conv_fwd32([a.pick(m) for a, m in srcs], cw.w32, cw.scale, cw.shift, cout=cw.cout, ksize=cw.ksize,
+                                    want_raw=True, want_elu=False, nchw=layout == "nchw")
+            return out, None
         out = ops.conv_fwd_f32([a.pick(m) for a, m in srcs], cw.w, cw.scale, cw.shift, ksize=cw.ksize, layout=layout,
                                cout_valid=cw.cout)
         slot = None
@@ -317,6 +328,9 @@ class NormConv2d(nn.Module):
         return out, slot
 
     def _run_stem(self, x: torch.Tensor, want_raw=True, want_elu=True, bank: Optional[WeightBank] = None) -> Act:
+        if bank is not None and bank.precision == "fp32":
+            x_nhwc, _ = ops.nchw_to_nhwc32(x, True, False)
+            return self._run(bank, [(Act(x_nhwc, None), "raw")], want_raw=want_raw, want_elu=want_elu)
         c = self.conv
         raw, elu = ops.stem_fwd(x, c.weight_v, c.weight_g, self.gamma, self.beta, c.bias, want_raw, want_elu)
         out = Act(raw, elu)

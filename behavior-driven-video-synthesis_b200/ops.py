@@ -31,6 +31,12 @@ _LIB.define(
 _LIB.define("latent_fwd(Tensor ml, Tensor? eps, bool want_elu_z, bool want_elu_mu) -> Tensor[]")
 _LIB.define("nchw_to_nhwc(Tensor x, bool want_raw, bool want_elu) -> Tensor[]")
 _LIB.define("nhwc_to_nchw(Tensor x) -> Tensor")
+# ---- fp32 validation path -----------------------------------------------------------------------
+_LIB.define(
+    "conv_fwd32(Tensor x0, Tensor? x1, Tensor w, Tensor scale, Tensor shift, Tensor? residual, int cout, int ksize, "
+    "int stride, bool want_raw, bool want_elu, bool d2s, bool nchw) -> Tensor[]"
+)
+_LIB.define("nchw_to_nhwc32(Tensor x, bool want_raw, bool want_elu) -> Tensor[]")
 # ---- training half (mutating ops: gradient buffers are accumulated in place) ----------------------
 _LIB.define(
     "conv_dgrad(Tensor dy, Tensor wd, Tensor(a!) dx0, Tensor(b!)? dx1, Tensor? mask0, Tensor? mask1, "
@@ -355,7 +361,51 @@ def _nchw_to_nhwc_pad_cuda(x, c_pad) -> torch.Tensor:
     return out
 
 
+def _conv_fwd32_cuda(x0, x1, w, scale, shift, residual, cout, ksize, stride, want_raw, want_elu, d2s, nchw):
+    for t in (x0, x1, residual):
+        if t is not None and (t.dtype != torch.float32 or t.dim() != 4 or not t.is_contiguous()):
+            raise ValueError("conv_fwd32: activations must be contiguous NHWC fp32")
+    B, H, W, c_src = x0.shape
+    nsrc = 1 if x1 is None else 2
+    if w.dtype != torch.float32 or w.dim() != 2 or w.shape[0] != nsrc * ksize * ksize * c_src or w.shape[1] < cout:
+        raise ValueError(f"conv_fwd32: weight {tuple(w.shape)} does not match K={nsrc * ksize * ksize * c_src}, cout={cout}")
+    Ho, Wo = H // stride, W // stride
+    oshape = (B, cout, Ho, Wo) if nchw else ((B, 2 * Ho, 2 * Wo, cout // 4) if d2s else (B, Ho, Wo, cout))
+    d = N.ConvF32Desc()
+    d.x[0], d.x[1] = x0.data_ptr(), _p(x1)
+    d.w, d.scale, d.shift, d.residual = w.data_ptr(), scale.data_ptr(), shift.data_ptr(), _p(residual)
+    outs = []
+    if want_raw:
+        raw = torch.empty(oshape, dtype=torch.float32, device=x0.device)
+        d.out_raw = raw.data_ptr()
+        outs.append(raw)
+    if want_elu:
+        elu = torch.empty(oshape, dtype=torch.float32, device=x0.device)
+        d.out_elu = elu.data_ptr()
+        outs.append(elu)
+    d.nsrc, d.c_src, d.batch, d.hin, d.win, d.cout = nsrc, c_src, B, H, W, cout
+    d.w_pitch, d.ksize, d.stride = w.stride(0), ksize, stride
+    d.flags = (N.CONV_D2S if d2s else 0) | (N.CONV_F32_NCHW if nchw else 0)
+    N.check(_launch(f"conv_fwd32 {nsrc}x{c_src}->{cout} k{ksize} s{stride} @{H}x{W}", N.lib().vub_conv_fwd_f32, C.byref(d),
+                    _stream(), flops=2.0 * B * Ho * Wo * cout * w.shape[0]), "vub_conv_fwd_f32")
+    return outs
+
+
+def _nchw_to_nhwc32_cuda(x, want_raw, want_elu):
+    if x.dtype != torch.float32 or x.dim() != 4:
+        raise ValueError("nchw_to_nhwc32: x must be NCHW fp32")
+    x = x.contiguous()
+    B, c, H, W = x.shape
+    raw = torch.empty((B, H, W, c), dtype=torch.float32, device=x.device) if want_raw else None
+    elu = torch.empty((B, H, W, c), dtype=torch.float32, device=x.device) if want_elu else None
+    N.check(_launch("nchw_to_nhwc32", N.lib().vub_nchw_f32_to_nhwc_f32, x.data_ptr(), B, c, H, W, _p(raw), _p(elu),
+                    _stream()), "vub_nchw_f32_to_nhwc_f32")
+    return [t for t in (raw, elu) if t is not None]
+
+
 _LIB.impl("conv_fwd", _conv_fwd_cuda, "CUDA")
+_LIB.impl("conv_fwd32", _conv_fwd32_cuda, "CUDA")
+_LIB.impl("nchw_to_nhwc32", _nchw_to_nhwc32_cuda, "CUDA")
 _LIB.impl("conv_dgrad", _conv_dgrad_cuda, "CUDA")
 _LIB.impl("conv_wgrad", _conv_wgrad_cuda, "CUDA")
 _LIB.impl("wn_bwd", _wn_bwd_cuda, "CUDA")
@@ -428,6 +478,23 @@ def nchw_to_nhwc(x, want_raw=True, want_elu=True):
 
 def nhwc_to_nchw(x):
     return _ops.nhwc_to_nchw(x)
+
+
+# ---- fp32 validation path -------------------------------------------------------------------------
+def conv_fwd32(x: Sequence[torch.Tensor], w, scale, shift, *, cout: int, ksize: int, stride: int = 1,
+               residual: Optional[torch.Tensor] = None, want_raw: bool = True, want_elu: bool = True,
+               d2s: bool = False, nchw: bool = False):
+    """fp32 NHWC (or NCHW image) outputs: returns (raw or None, elu or None)."""
+    outs = _ops.conv_fwd32(x[0], x[1] if len(x) > 1 else None, w, scale, shift, residual, cout, ksize, stride,
+                           want_raw, want_elu, d2s, nchw)
+    it = iter(outs)
+    return (next(it) if want_raw else None), (next(it) if want_elu else None)
+
+
+def nchw_to_nhwc32(x, want_raw=True, want_elu=True):
+    outs = _ops.nchw_to_nhwc32(x, want_raw, want_elu)
+    it = iter(outs)
+    return (next(it) if want_raw else None), (next(it) if want_elu else None)
 
 
 # ---- training half ------------------------------------------------------------------------------

@@ -103,6 +103,12 @@ class EncDownAlter(nn.Module):
         B, hh, ww, c2 = ml.shape
         if eps is None:
             eps = _draw_eps((B, c2 // 2, hh, ww), ml.device)
+        if bank.precision == "fp32":  # validation mode: fp32 ELU(z) / ELU(mu) operands
+            res = ops.latent_fwd(ml, eps, want_elu_z=False, want_elu_mu=False)
+            res["z_act"] = Act(None, ops.nchw_to_nhwc32(res["z"], False, True)[1])
+            if want_elu_mu:
+                res["mu_act"] = Act(None, ops.nchw_to_nhwc32(res["mu"], False, True)[1])
+            return res
         res = ops.latent_fwd(ml, eps, want_elu_z=True, want_elu_mu=want_elu_mu)
         res["z_act"] = Act(None, res["elu_z"])
         if want_elu_mu:
@@ -197,7 +203,8 @@ class DecDownAlter(nn.Module):
                     z = zs.pop(0)
                 else:
                     B, hh, ww, cc = h.raw.shape
-                    z = Act(None, ops.nchw_to_nhwc(_draw_eps((B, cc, hh, ww), h.raw.device), False, True)[1])
+                    conv = ops.nchw_to_nhwc32 if bank.precision == "fp32" else ops.nchw_to_nhwc
+                    z = Act(None, conv(_draw_eps((B, cc, hh, ww), h.raw.device), False, True)[1])
                 h = self.auto_blocks[lat_count]._run(bank, h, z)
                 lat_count += 1
             last = i + 1 == self.n_scales
@@ -266,6 +273,16 @@ class VunetAlter(nn.Module):
 
     # ---------------------------------------------------------------------------------------------
     def _bank(self, with_wd: bool = False) -> WeightBank:
+        if getattr(self, "validation_fp32", False):
+            if with_wd:
+                raise NotImplementedError("the fp32 validation mode is forward-only (training runs in bf16)")
+            bank32 = getattr(self, "_vub_bank32", None)
+            if bank32 is None:
+                from .validation import WeightBank32
+                bank32 = WeightBank32(self)
+                object.__setattr__(self, "_vub_bank32", bank32)
+            bank32.refresh()
+            return bank32
         bank = _solo_bank(self)
         if with_wd and not bank._with_wd:
             bank.refresh(with_wd=True)
@@ -281,6 +298,8 @@ class VunetAlter(nn.Module):
         return self
 
     def _wants_grad(self) -> bool:
+        if getattr(self, "validation_fp32", False):
+            return False  # forward-only: outputs carry no autograd history in validation mode
         return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
     def _forward_impl(self, bank, x, c, eps):

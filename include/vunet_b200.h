@@ -103,6 +103,9 @@ typedef struct vub_wn_entry {
   void* wd;
   int32_t wd_cout;     /* K extent per tap of wd (output channels of the whole slot, padded to 32) */
   int32_t wd_col0;     /* first column of this conv inside a tap block (merged convs) */
+  /* fp32 validation path: w32[(src*ktaps + tap)*c_src + c][wd_col0 + co] = v_hat (row pitch wd_cout floats).
+   * NULL = skip.  w_packed may be NULL when only w32 is wanted. */
+  float* w32;
 } vub_wn_entry;
 
 int vub_wn_prep(const vub_wn_entry* table_dev, int32_t n_entries, int32_t total_rows, void* stream);
@@ -146,6 +149,29 @@ int vub_nhwc_bf16_to_nchw_f32(const void* src, int32_t batch, int32_t c, int32_t
  * d(loss)/d(imgs) [batch, 3, h, w] entering the backward pass of dd.out_conv (models/vunets.py:411). */
 int vub_nchw_f32_to_nhwc_bf16_pad(const float* src, int32_t batch, int32_t c, int32_t h, int32_t w,
                                   int32_t c_pad, void* dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * fp32 validation path (BASELINE.json north_star: relative L2 <= 1e-4 against the reference in an
+ * fp32 validation mode).  Same fused conv as vub_conv_fwd with fp32 NHWC activations, fp32 weights
+ * (vub_wn_entry.w32) and fp32 FMA accumulation on CUDA cores; any channel counts (the stems included).
+ * Output layout: NHWC [batch, hout, wout, cout]; VUB_CONV_D2S: shuffled NHWC; VUB_CONV_F32_NCHW: NCHW
+ * (the image).  A checker for the fused schedule, not a fast path.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vub_conv_f32_desc {
+  const float* x[2];       /* NHWC fp32 [batch, hin, win, c_src] */
+  const float* w;          /* [nsrc*ksize*ksize*c_src][w_pitch] fp32, 16-byte aligned */
+  const float* scale;
+  const float* shift;
+  const float* residual;   /* same layout as the output, or NULL */
+  float* out_raw;
+  float* out_elu;
+  int32_t nsrc, c_src, batch, hin, win, cout, w_pitch, ksize, stride;
+  uint32_t flags;
+} vub_conv_f32_desc;
+
+int vub_conv_fwd_f32(const vub_conv_f32_desc* d, void* stream);
+int vub_nchw_f32_to_nhwc_f32(const float* src, int32_t batch, int32_t c, int32_t h, int32_t w, float* dst_raw,
+                             float* dst_elu, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Training half of the path.  The reference gets these from autograd (convolution_backward, ELU /

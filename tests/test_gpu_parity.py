@@ -214,3 +214,54 @@ def test_standalone_blocks_match_oracle():
     st.load_state_dict(sd6)
     img = O.det_uniform("img", (2, 3, 32, 32))
     assert rel(st.cuda()(img.cuda()), O.norm_conv({("s." + k): v for k, v in sd6.items()}, "s", img)) < BF16_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+FP32_TOL = 1e-4  # BASELINE.json north_star: "1e-4 in an fp32-accumulate validation mode"
+
+
+@pytest.mark.parametrize("name", ["tiny3", "tiny30", "market128"])
+def test_fp32_validation_mode_matches_reference_to_1e4(golden, name):
+    import bdvs_b200 as B
+    fx = golden(name)
+    cfg = fx["config"]
+    m, sd = build(cfg)
+    x, c, eps, prior = O.make_inputs(cfg, cfg["batch"])
+    with torch.no_grad(), B.fp32_validation(m):
+        imgs, means, logstds, acts = m(x.cuda(), c.cuda(), eps=cuda(eps))
+        timgs = m.transfer(x.cuda(), c.cuda(), eps=cuda(eps))
+    assert imgs.dtype == torch.float32 and acts[0][0].dtype == torch.float32
+    errs = {"imgs": rel(imgs, fx["imgs"]), "transfer": rel(timgs, fx["transfer"])}
+    for i in range(2):
+        errs[f"mean{i}"] = rel(means[i], fx["means"][i])
+        errs[f"logstd{i}"] = rel(logstds[i], fx["logstds"][i])
+    kl = float(B.compute_kl_with_prior(means, logstds))
+    errs["kl"] = abs(kl - fx["kl"]) / abs(fx["kl"])
+    if "test_forward" in fx:
+        import bdvs_b200.vunets as V
+        draws = iter(cuda(prior))
+        orig = V._draw_eps
+        V._draw_eps = lambda shape, device: next(draws)  # the reference's randn_like draws, injected
+        try:
+            with torch.no_grad(), B.fp32_validation(m):
+                pimgs = m.test_forward(c.cuda())
+        finally:
+            V._draw_eps = orig
+        errs["test_forward"] = rel(pimgs, fx["test_forward"])
+    print(name, {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < FP32_TOL, errs
+    # leaving the mode restores the bf16 tensor-core path
+    with torch.no_grad():
+        imgs_bf16 = m(x.cuda(), c.cuda(), eps=cuda(eps))[0]
+    assert 1e-4 < rel(imgs_bf16, fx["imgs"]) < BF16_TOL
+
+
+def test_fp32_validation_mode_is_forward_only(golden):
+    import bdvs_b200 as B
+    cfg = golden("tiny3")["config"]
+    m, sd = build(cfg)
+    m.train()
+    x, c, eps, _ = O.make_inputs(cfg, cfg["batch"])
+    with B.fp32_validation(m):
+        imgs = m(x.cuda(), c.cuda(), eps=cuda(eps))[0]
+    assert not imgs.requires_grad
