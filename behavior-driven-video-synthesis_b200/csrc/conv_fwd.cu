@@ -446,7 +446,14 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
   }
 
   const int bkc = d->c_src >= 64 ? 64 : 32;
-  const int bn = cout > 256 ? 256 : cout;
+  int bn = cout > 256 ? 256 : cout;
+  {
+    // Small maps (<= 16x16): a handful of 128-pixel tiles leaves most SMs idle while each CTA streams the whole
+    // K loop at the per-SM TMA rate.  Split N over more CTAs (each re-reads the A boxes, 4x smaller weight tiles)
+    // until the grid covers about two thirds of the chip.
+    const long long pix_tiles = ((long long)d->batch * hout * wout + kTileM - 1) / kTileM;
+    while (bn > 32 && pix_tiles * (cout / bn) < 96 && !(f & VUB_CONV_F32_NHWC)) bn >>= 1;
+  }
 
   ConvKParams kp;
   memset(&kp, 0, sizeof(kp));

@@ -124,8 +124,9 @@ __global__ void __launch_bounds__(kStemThreads)
     s_shift[co] = fmaf(gamma[co], bias[co], beta[co]);
   }
   __syncthreads();
-  const long long pix = (long long)blockIdx.x * kStemThreads + threadIdx.x;
-  if (pix >= total_pix) return;
+  const long long pix_raw = (long long)blockIdx.x * kStemThreads + threadIdx.x;
+  const bool valid = pix_raw < total_pix;
+  const long long pix = valid ? pix_raw : total_pix - 1;  // tail threads compute a duplicate, store nothing
   const long long n = pix / hw;
   const long long sp = pix - n * hw;
   const float* xp = x + n * cx * hw + sp;
@@ -137,28 +138,38 @@ __global__ void __launch_bounds__(kStemThreads)
 #pragma unroll
     for (int co = 0; co < COUT; ++co) acc[co] = fmaf(xv, s_w[ci * COUT + co], acc[co]);
   }
-  if (out_raw != nullptr) {
-    uint4* o = reinterpret_cast<uint4*>(out_raw + pix * COUT);
+  // Coalesced stores: a thread owns one pixel (COUT*2 contiguous bytes), so direct 16-byte stores from the
+  // 32 lanes of a warp hit 32 different 64/128-byte segments per instruction.  The block's 128 pixels are one
+  // contiguous span of the NHWC output: stage them in shared memory (padded pitch) and write the span linearly.
+  constexpr int PITCH = COUT * 2 + 16;
+  constexpr int CPR = COUT / 8;  // 16-byte chunks per pixel
+  __shared__ __align__(16) uint8_t s_out[kStemThreads * PITCH];
+  const long long pix0 = (long long)blockIdx.x * kStemThreads;
 #pragma unroll
-    for (int j = 0; j < COUT / 8; ++j) {
-      __nv_bfloat162 a = __floats2bfloat162_rn(acc[8 * j + 0], acc[8 * j + 1]);
-      __nv_bfloat162 b = __floats2bfloat162_rn(acc[8 * j + 2], acc[8 * j + 3]);
-      __nv_bfloat162 c = __floats2bfloat162_rn(acc[8 * j + 4], acc[8 * j + 5]);
-      __nv_bfloat162 d = __floats2bfloat162_rn(acc[8 * j + 6], acc[8 * j + 7]);
-      o[j] = make_uint4(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b),
-                        *reinterpret_cast<uint32_t*>(&c), *reinterpret_cast<uint32_t*>(&d));
+  for (int which = 0; which < 2; ++which) {
+    __nv_bfloat16* out = which == 0 ? out_raw : out_elu;
+    if (out == nullptr) continue;
+    __syncthreads();  // previous pass has been read back
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < CPR; ++j) {
+        float t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = which == 0 ? acc[8 * j + i] : elu1(acc[8 * j + i]);
+        __nv_bfloat162 a = __floats2bfloat162_rn(t[0], t[1]), b2 = __floats2bfloat162_rn(t[2], t[3]);
+        __nv_bfloat162 c2 = __floats2bfloat162_rn(t[4], t[5]), d2 = __floats2bfloat162_rn(t[6], t[7]);
+        *reinterpret_cast<uint4*>(s_out + threadIdx.x * PITCH + j * 16) =
+            make_uint4(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b2),
+                       *reinterpret_cast<uint32_t*>(&c2), *reinterpret_cast<uint32_t*>(&d2));
+      }
     }
-  }
-  if (out_elu != nullptr) {
-    uint4* o = reinterpret_cast<uint4*>(out_elu + pix * COUT);
+    __syncthreads();
+    uint4* dst = reinterpret_cast<uint4*>(out + pix0 * COUT);
 #pragma unroll
-    for (int j = 0; j < COUT / 8; ++j) {
-      __nv_bfloat162 a = __floats2bfloat162_rn(elu1(acc[8 * j + 0]), elu1(acc[8 * j + 1]));
-      __nv_bfloat162 b = __floats2bfloat162_rn(elu1(acc[8 * j + 2]), elu1(acc[8 * j + 3]));
-      __nv_bfloat162 c = __floats2bfloat162_rn(elu1(acc[8 * j + 4]), elu1(acc[8 * j + 5]));
-      __nv_bfloat162 d = __floats2bfloat162_rn(elu1(acc[8 * j + 6]), elu1(acc[8 * j + 7]));
-      o[j] = make_uint4(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b),
-                        *reinterpret_cast<uint32_t*>(&c), *reinterpret_cast<uint32_t*>(&d));
+    for (int k = 0; k < CPR; ++k) {
+      const int c = threadIdx.x + kStemThreads * k;  // chunk index inside the block's span
+      const int row = c / CPR, col = c - row * CPR;
+      if (pix0 + row < total_pix) dst[c] = *reinterpret_cast<const uint4*>(s_out + row * PITCH + col * 16);
     }
   }
 }

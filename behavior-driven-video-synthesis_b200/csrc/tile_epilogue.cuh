@@ -95,9 +95,40 @@ __device__ __forceinline__ void tile_epilogue_staged(const TileEpi& e, const Epi
   for (int g0 = 0; g0 < BN; g0 += GW) {
     const int col0 = ecol + g0;  // first (epilogue-local) column of this group
     if (!f32_out) {
-      if (e.addend != nullptr) stage_fill(t0, e.addend, col0);
-      if (e.mask_elu != nullptr) stage_fill(t1, e.mask_elu, col0);
-      if (e.addend2 != nullptr) stage_fill(t2, e.addend2, col0);
+      if constexpr (GW == 32) {
+        // HBM-bound layers: put the loads of ALL input tensors in flight before the first store (3x the
+        // memory-level parallelism of one tensor at a time; 8 epilogue warps x 16 B x 4 chunks per tensor cannot
+        // cover the DRAM latency otherwise)
+        uint4 va[CPR], vm[CPR], vb[CPR];
+#pragma unroll
+        for (int k = 0; k < CPR; ++k) {
+          const int c = lane + 32 * k;
+          const int row = c / CPR;
+          const int col = c - row * CPR;
+          int rn, roh, row_w;
+          va[k] = vm[k] = vb[k] = make_uint4(0u, 0u, 0u, 0u);
+          if (row_pixel(row, rn, roh, row_w)) {
+            const long long off = tile_out_offset(e, col0 + col * 8, rn, roh, row_w);
+            if (e.addend != nullptr) va[k] = *reinterpret_cast<const uint4*>(e.addend + off);  // may alias the output
+            if (e.mask_elu != nullptr) vm[k] = *reinterpret_cast<const uint4*>(e.mask_elu + off);
+            if (e.addend2 != nullptr) vb[k] = *reinterpret_cast<const uint4*>(e.addend2 + off);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < CPR; ++k) {
+          const int c = lane + 32 * k;
+          const int row = c / CPR;
+          const int col = c - row * CPR;
+          const uint32_t so = row * EpiStage<GW>::PITCH + col * 16;
+          if (e.addend != nullptr) sts128(t0 + so, va[k]);
+          if (e.mask_elu != nullptr) sts128(t1 + so, vm[k]);
+          if (e.addend2 != nullptr) sts128(t2 + so, vb[k]);
+        }
+      } else {
+        if (e.addend != nullptr) stage_fill(t0, e.addend, col0);
+        if (e.mask_elu != nullptr) stage_fill(t1, e.mask_elu, col0);
+        if (e.addend2 != nullptr) stage_fill(t2, e.addend2, col0);
+      }
       __syncwarp();
     }
 #pragma unroll 1
