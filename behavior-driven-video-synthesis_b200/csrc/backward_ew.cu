@@ -64,8 +64,17 @@ __global__ void __launch_bounds__(kWnbThreads)
   // sum the pixel splits (coalesced along k), stored at the weight index i = (ci, tap) of column
   // k = (src*ktaps + tap)*c_src + cs
   for (int k = threadIdx.x; k < len; k += kWnbThreads) {
-    float g = 0.f;
-    for (int sidx = 0; sidx < e.n_split; ++sidx) g += grow[(size_t)sidx * e.split_stride + k];
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;  // independent chains: keep 4+ loads in flight per thread
+    int sidx = 0;
+    for (; sidx + 4 <= e.n_split; sidx += 4) {
+      const float* q = grow + (size_t)sidx * e.split_stride + k;
+      g0 += __ldg(q);
+      g1 += __ldg(q + e.split_stride);
+      g2 += __ldg(q + 2 * e.split_stride);
+      g3 += __ldg(q + 3 * e.split_stride);
+    }
+    for (; sidx < e.n_split; ++sidx) g0 += __ldg(grow + (size_t)sidx * e.split_stride + k);
+    const float g = (g0 + g1) + (g2 + g3);
     const int cs = k % e.c_src;
     const int t = k / e.c_src;
     const int tap = t % e.ktaps;

@@ -344,7 +344,7 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
   if (conv_rows_applicable(d)) return conv_rows_launch(d, static_cast<cudaStream_t>(stream_v));
 
   // tensor-core-bound 3x3 layers at 64x64 / 32x32: activation-slab kernel (A and weight reuse in smem)
-  if (d->ksize == 3 && d->stride == 1 && d->stages >= 0 && !f32 && conv_slab_shape_ok(d->c_src, d->hin, d->win, cout)) {
+  if (d->ksize == 3 && d->stride == 1 && d->stages >= 0 && !f32 && conv_slab_shape_ok(d->c_src, d->hin, d->win, cout, d->nsrc * 9 * d->c_src)) {
     SlabJob job;
     memset(&job, 0, sizeof(job));
     job.x[0] = d->x[0];
@@ -483,6 +483,12 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
   const int tiles_n = (d->batch + kp.tn - 1) / kp.tn;
   const int ksteps = kp.nsrc * kp.ntaps * kp.cblocks;
   kp.stages = d->stages > 0 ? d->stages : default_stages(bn, bkc, ksteps);  // stages < 0: force this kernel
+  if (d->stages <= 0 && (long long)kp.tiles_w * kp.tiles_h * tiles_n * (cout / bn) <= 148) {
+    // at most one CTA per SM: nothing to share the shared memory with, and with two stages only 40 KB are in
+    // flight per L2/HBM round trip -> take the whole budget (the small-map layers are latency bound)
+    const int deep = 190 * 1024 / ((kTileM + bn) * bkc * 2);
+    kp.stages = deep < ksteps ? deep : ksteps;
+  }
   if (kp.stages > kMaxStages) kp.stages = kMaxStages;
   if ((size_t)kp.stages * (kTileM + bn) * bkc * 2 + 1024 > 200 * 1024)
     return fail(VUB_E_SHAPE, "conv_fwd: %d stages do not fit in shared memory", kp.stages);

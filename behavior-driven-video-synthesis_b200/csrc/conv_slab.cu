@@ -226,18 +226,23 @@ __global__ void __launch_bounds__(kSlabThreads, 1) conv_slab_kernel(const __grid
 }
 
 // ------------------------------------------------------------------------------------------------
-bool conv_slab_shape_ok(int c_src, int h, int w, int n_total) {
-  // Opt-in (VUB_ENABLE_SLAB=1): measured on B200 the kernel halves the L2 -> SM traffic but is not faster
-  // than the two-CTAs-per-SM per-tap kernel yet (only one 96 KB slab step in flight per SM).
-  static const bool enabled = getenv("VUB_ENABLE_SLAB") != nullptr && getenv("VUB_ENABLE_SLAB")[0] == '1';
-  if (!enabled) return false;
+bool conv_slab_shape_ok(int c_src, int h, int w, int n_total, int k_total) {
+  // Measured on B200 (profiles/r01_bench_v5.json vs r01_bench_slab.json): the kernel halves the L2 -> SM traffic
+  // and wins where the K loop or the N extent is long enough to amortise its deeper, coarser pipeline — the
+  // concat layers (K >= 2304: +10 % forward) and their data gradients (N = 256: +43 %) — but loses to the
+  // two-CTAs-per-SM per-tap kernel on the single-source 128 -> 128 layers.
+  // VUB_ENABLE_SLAB=1 forces it for every supported shape, =0 disables it.
+  static const char* env = getenv("VUB_ENABLE_SLAB");
+  if (env != nullptr && env[0] == '0') return false;
   if (c_src % 64 || (w != 32 && w != 64)) return false;
   const int R = 256 / w;
-  return h % R == 0 && n_total % kSlabBN == 0 && n_total <= kSlabMaxN;
+  if (h % R != 0 || n_total % kSlabBN != 0 || n_total > kSlabMaxN) return false;
+  if (env != nullptr && env[0] == '1') return true;
+  return k_total >= 2304 || n_total >= 256;
 }
 
 int conv_slab_launch(const SlabJob& job, cudaStream_t stream) {
-  if (!conv_slab_shape_ok(job.c_src, job.h, job.w, job.n_total))
+  if (!conv_slab_shape_ok(job.c_src, job.h, job.w, job.n_total, 1 << 30))
     return fail(VUB_E_SHAPE, "conv_slab: unsupported shape c %d %dx%d N %d", job.c_src, job.h, job.w, job.n_total);
   if (job.n_split % kSlabBN) return fail(VUB_E_SHAPE, "conv_slab: split %d not a multiple of %d", job.n_split, kSlabBN);
   SlabKParams kp;

@@ -6,8 +6,8 @@
 // The contraction index is the PIXEL, the slow index of both NHWC operands, so both UMMA operands are
 // MN-major: a TMA box [channels, pixels] written with 128B/64B swizzle IS the canonical MN-major
 // operand layout (LBO = stride between 64-/32-channel boxes, SBO = 8 pixel rows; measured:
-// profiles/r01_exp_mnmajor.log).  One k-step = 64 pixels:
-//   A = dy box(es)  [128 output channels x 64 pixels]   (M = 128; layers with fewer output channels
+// profiles/r01_exp_mnmajor.log).  One k-step = 128 pixels (64 on tiny maps):
+//   A = dy box(es)  [128 output channels x 128 pixels]   (M = 128; layers with fewer output channels
 //                                                         replicate their box with a block stride of 0)
 //   B = x boxes of the CTA's tap group.  For 3x3 stride-1 convs at width >= 16 ONE box per (tap row,
 //       channel block) is loaded with a one-pixel halo on both sides, and the three column taps are three
@@ -35,7 +35,8 @@
 namespace vub {
 
 constexpr int kWgThreads = 192;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
-constexpr int kWgKP = 64;         // pixels per k-step
+constexpr int kWgMaxKP = 128;     // pixels per k-step: 128 (TMA costs >= ~384 cycles per box: 64-pixel boxes
+                                  // made the stream box-count bound), 64 for tiny maps
 constexpr int kWgMaxStages = 16;
 constexpr int kWgMaxGroups = 6;
 constexpr int kWgMaxBoxes = 9;    // B boxes per tap group
@@ -71,7 +72,8 @@ struct WgKParams {
   int b_box_pitch;       // bytes between consecutive B boxes of a stage (1024-aligned)
   int b_box_bytes;       // bytes TMA writes per B box
   int n_groups, n_mtiles, n_split;
-  int tw, th, tn;        // pixel tile (tw * th * tn = 64)
+  int kp_pix;            // pixels per k-step (64 or 128)
+  int tw, th, tn;        // pixel tile (tw * th * tn = kp_pix)
   int tiles_w, tiles_h;
   int total_tiles;
   int stages;
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
   const bool with_sum = grp == 0;
 
   const int a_rowb = p.ca * 2, b_rowb = p.cb * 2;
-  const int a_box = kWgKP * a_rowb, b_box = p.b_box_pitch;
+  const int a_box = p.kp_pix * a_rowb, b_box = p.b_box_pitch;
   const int a_bytes = p.na * a_box;
   const int stage_bytes = a_bytes + nb * p.b_box_bytes;  // bytes TMA delivers per stage
   const int stage_pitch = (a_bytes + nb * b_box + 1023) & ~1023;
@@ -215,9 +217,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
           box0 += nbox;
         }
       }
-      uint32_t a_off[4], b_off[4];  // byte offsets of the 4 K slices (16 pixels each) inside a box
+      constexpr int kMaxSlices = kWgMaxKP / 16;
+      const int n_slices = p.kp_pix / 16;
+      uint32_t a_off[kMaxSlices], b_off[kMaxSlices];  // byte offsets of the K slices (16 pixels each) inside a box
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < kMaxSlices; ++j) {
         const int px = j * 16;
         a_off[j] = px * a_rowb;
         b_off[j] = p.halo ? ((px / p.tw) * (p.tw + 2) + (px % p.tw)) * b_rowb : px * b_rowb;
@@ -233,7 +237,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
         const uint32_t b_addr = a_addr + a_bytes;
         if (elect_one()) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < kMaxSlices; ++j) {
+            if (j >= n_slices) break;
             const uint64_t da = umma_desc_join(a_hi, (((a_addr + a_off[j]) & 0x3FFFFu) >> 4) | a_lo_c);
 #pragma unroll
             for (int i = 0; i < 3; ++i)
@@ -307,7 +312,7 @@ using namespace vub;
 
 // Fills everything of the launch parameters that depends on shapes only (no pointers, no tensor maps) and
 // returns the best number of pixel splits in *best_split.
-static int wgrad_plan(const vub_wgrad_desc* d, WgKParams& kp, int* best_split, int* max_nb_out) {
+static int wgrad_plan_kp(const vub_wgrad_desc* d, WgKParams& kp, int* best_split, int* max_nb_out, int kp_pix) {
   if (d->nsrc != 1 && d->nsrc != 2) return fail(VUB_E_SHAPE, "conv_wgrad: nsrc must be 1 or 2");
   const int C = d->c_src;
   if (C != 32 && C != 64 && C != 128) return fail(VUB_E_SHAPE, "conv_wgrad: c_src %d not in {32,64,128}", C);
@@ -339,9 +344,11 @@ static int wgrad_plan(const vub_wgrad_desc* d, WgKParams& kp, int* best_split, i
       kp.abox[mt * 4 + i] = WgABox{(int16_t)(d2s ? co0 / cmap : 0), (int16_t)(d2s ? co0 % cmap : co0)};
     }
   // ---- pixel tiles of 64 ----
-  kp.tw = wo < kWgKP ? wo : kWgKP;
-  kp.th = ho < kWgKP / kp.tw ? ho : kWgKP / kp.tw;
-  kp.tn = kWgKP / (kp.tw * kp.th);
+  kp.kp_pix = kp_pix;
+  const int KP = kp.kp_pix;
+  kp.tw = wo < KP ? wo : KP;
+  kp.th = ho < KP / kp.tw ? ho : KP / kp.tw;
+  kp.tn = KP / (kp.tw * kp.th);
   kp.tiles_w = wo / kp.tw;
   kp.tiles_h = ho / kp.th;
   const int tiles_n = (d->batch + kp.tn - 1) / kp.tn;
@@ -418,6 +425,24 @@ static int wgrad_plan(const vub_wgrad_desc* d, WgKParams& kp, int* best_split, i
   return 0;
 }
 
+static size_t wgrad_stage_pitch(const WgKParams& kp, int max_nb) {
+  const size_t stage_bytes = (size_t)kp.na * kp.kp_pix * kp.ca * 2 + (size_t)max_nb * kp.b_box_pitch;
+  return (stage_bytes + 1023) & ~(size_t)1023;
+}
+
+// 128-pixel k-steps when the map is large enough and at least 3 pipeline stages fit, else 64-pixel k-steps.
+static int wgrad_plan(const vub_wgrad_desc* d, WgKParams& kp, int* best_split, int* max_nb_out) {
+  static const bool kp64 = getenv("VUB_WGRAD_KP64") != nullptr && getenv("VUB_WGRAD_KP64")[0] == '1';
+  const long long pixels = (long long)d->batch * (d->hin / (d->stride > 0 ? d->stride : 1)) *
+                           (d->win / (d->stride > 0 ? d->stride : 1));
+  if (pixels >= 4 * kWgMaxKP && !kp64) {
+    const int rc = wgrad_plan_kp(d, kp, best_split, max_nb_out, kWgMaxKP);
+    if (rc) return rc;
+    if ((200 * 1024 - kWgOnesBytes) / wgrad_stage_pitch(kp, *max_nb_out) >= 3) return 0;
+  }
+  return wgrad_plan_kp(d, kp, best_split, max_nb_out, 64);
+}
+
 extern "C" int32_t vub_conv_wgrad_splits(const vub_wgrad_desc* d) {
   clear_error();
   if (!d) return fail(VUB_E_NULL, "conv_wgrad_splits: desc is NULL");
@@ -457,8 +482,7 @@ extern "C" int vub_conv_wgrad(const vub_wgrad_desc* d, void* stream_v) {
   kp.sum_stride = d->sum_stride;
   kp.n_split = d->n_split;
 
-  const size_t stage_bytes = (size_t)kp.na * kWgKP * kp.ca * 2 + (size_t)max_nb * kp.b_box_pitch;
-  const size_t stage_pitch = (stage_bytes + 1023) & ~(size_t)1023;
+  const size_t stage_pitch = wgrad_stage_pitch(kp, max_nb);
   int stages = static_cast<int>((200 * 1024 - kWgOnesBytes) / stage_pitch);
   if (stages > kWgMaxStages) stages = kWgMaxStages;
   if (stages < 2) return fail(VUB_E_SHAPE, "conv_wgrad: pipeline does not fit");
