@@ -337,6 +337,31 @@ class VunetAlter(nn.Module):
         gs = self.du._run(bank, c.float())
         return self.dd._run(bank, gs, [], False)
 
+    # ---- sequence-level split of `transfer` ----------------------------------------
+    def encode_appearance(self, x, eps: Optional[Sequence[torch.Tensor]] = None):
+        """The appearance half of :meth:`transfer` — ``eu`` + ``ed`` — run ONCE per appearance image.
+        The reference re-encodes the (constant) appearance image for every frame of a sequence
+        (``data/data_conversions_3d.py:1130-1165``); the posterior means are all the decoder needs.
+        Returns an opaque list to hand to :meth:`decode_pose`."""
+        _require_cuda(x)
+        bank = self._bank()
+        _, _, lat = self._encode(bank, x, eps, skip_dead=True, want_elu_mu=True)
+        return [r["mu_act"] for r in lat]
+
+    def decode_pose(self, c, appearance, frames_per_appearance: int = 1):
+        """The pose half of :meth:`transfer` — ``du`` + ``dd`` — for ``c`` = ``[S * T, 3, H, W]`` stickmen of ``S``
+        sequences with ``T = frames_per_appearance`` frames each (sequence-major), ``appearance`` from
+        :meth:`encode_appearance` on the ``S`` appearance images.  Equals
+        ``transfer(x.repeat_interleave(T, 0), c)`` with one latent-noise draw per sequence instead of per frame."""
+        _require_cuda(c)
+        bank = self._bank()
+        if frames_per_appearance > 1:  # tiny tensors (128 x 4^2 / 8^2 per sequence): plain torch indexing
+            appearance = [Act(None, a.elu.repeat_interleave(frames_per_appearance, dim=0)) for a in appearance]
+        if appearance[0].elu.shape[0] != c.shape[0]:
+            raise ValueError("decode_pose: c must hold frames_per_appearance frames for every appearance image")
+        gs = self.du._run(bank, c.float())
+        return self.dd._run(bank, gs, list(appearance), True)
+
     def transfer(self, x, c, eps: Optional[Sequence[torch.Tensor]] = None):
         _require_cuda(x)
         _require_cuda(c)

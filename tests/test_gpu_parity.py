@@ -265,3 +265,24 @@ def test_fp32_validation_mode_is_forward_only(golden):
     with B.fp32_validation(m):
         imgs = m(x.cuda(), c.cuda(), eps=cuda(eps))[0]
     assert not imgs.requires_grad
+
+
+def test_sequence_level_encoder_reuse_equals_per_frame_transfer():
+    """encode_appearance once per sequence + decode_pose over its frames == transfer on the repeated appearance
+    image with the same latent noise."""
+    from bdvs_b200.synthesis import SequenceSynthesizer
+    cfg = dict(H256, spatial_size=64)
+    m, _ = build(cfg)
+    S, T = 2, 3
+    x, _, eps, _ = O.make_inputs(cfg, S, tag="seq")
+    _, c, _, _ = O.make_inputs(cfg, S * T, tag="seqc")
+    with torch.no_grad():
+        app = m.encode_appearance(x.cuda(), eps=cuda(eps))
+        seq = m.decode_pose(c.cuda(), app, T)
+        ref = m.transfer(x.cuda().repeat_interleave(T, 0), c.cuda(), eps=[e.cuda().repeat_interleave(T, 0) for e in eps])
+    assert torch.equal(seq, ref)
+    synth = SequenceSynthesizer(m, S, T)
+    out = synth(x.cuda(), c.cuda())
+    assert out.shape == ref.shape and bool(torch.isfinite(out).all())
+    with pytest.raises(ValueError):
+        m.decode_pose(c.cuda()[:4], app, T)
