@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = (
     "vub_nchw_f32_to_nhwc_bf16",
     "vub_nhwc_bf16_to_nchw_f32",
     "vub_nchw_f32_to_nhwc_bf16_pad",
+    "vub_frames_to_uint8",
     "vub_conv_fwd_f32",
     "vub_nchw_f32_to_nhwc_f32",
     "vub_conv_dgrad",
@@ -232,6 +233,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.vub_nhwc_bf16_to_nchw_f32.argtypes = [vp, i32, i32, i32, i32, fp, vp]
     lib.vub_nchw_f32_to_nhwc_bf16_pad.restype = C.c_int
     lib.vub_nchw_f32_to_nhwc_bf16_pad.argtypes = [fp, i32, i32, i32, i32, i32, vp, vp]
+    lib.vub_frames_to_uint8.restype = C.c_int
+    lib.vub_frames_to_uint8.argtypes = [fp, i32, i32, i32, vp, vp]
     lib.vub_conv_fwd_f32.restype = C.c_int
     lib.vub_conv_fwd_f32.argtypes = [C.POINTER(ConvF32Desc), vp]
     lib.vub_nchw_f32_to_nhwc_f32.restype = C.c_int

@@ -274,9 +274,39 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Frame epilogue of the rendering loop: scale_img(x) * 255 -> HWC uint8 (lib/utils.py:658-668,
+// data/data_conversions_3d.py:1166-1173).  Same fp32 operations in the same order as the reference
+// ((x + 1) / 2, clamp to [0, 1], * 255, truncation) => bit-exact.  One thread per pixel: three coalesced
+// plane reads, one 3-byte store.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    frames_to_uint8_kernel(const float* __restrict__ src, long long hw, long long total, uint8_t* __restrict__ dst) {
+  const long long pix = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (pix >= total) return;
+  const long long n = pix / hw, sp = pix - n * hw;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float o = (__ldg(src + (n * 3 + c) * hw + sp) + 1.0f) / 2.0f;
+    o = fminf(fmaxf(o, 0.0f), 1.0f) * 255.0f;
+    dst[pix * 3 + c] = static_cast<uint8_t>(static_cast<int>(o));
+  }
+}
+
 }  // namespace vub
 
 using namespace vub;
+
+extern "C" int vub_frames_to_uint8(const float* img_nchw, int32_t batch, int32_t h, int32_t w, uint8_t* out_nhwc,
+                                   void* stream) {
+  clear_error();
+  if (!img_nchw || !out_nhwc) return fail(VUB_E_NULL, "frames_to_uint8: NULL pointer");
+  if (batch <= 0 || h <= 0 || w <= 0) return fail(VUB_E_SHAPE, "frames_to_uint8: bad shape");
+  const long long hw = (long long)h * w, total = hw * batch;
+  frames_to_uint8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      img_nchw, hw, total, out_nhwc);
+  return check_launch("frames_to_uint8");
+}
 
 extern "C" int vub_wn_prep(const vub_wn_entry* table_dev, int32_t n_entries, int32_t total_rows,
                            void* stream) {

@@ -31,6 +31,7 @@ _LIB.define(
 _LIB.define("latent_fwd(Tensor ml, Tensor? eps, bool want_elu_z, bool want_elu_mu) -> Tensor[]")
 _LIB.define("nchw_to_nhwc(Tensor x, bool want_raw, bool want_elu) -> Tensor[]")
 _LIB.define("nhwc_to_nchw(Tensor x) -> Tensor")
+_LIB.define("frames_to_uint8(Tensor imgs) -> Tensor")
 # ---- fp32 validation path -----------------------------------------------------------------------
 _LIB.define(
     "conv_fwd32(Tensor x0, Tensor? x1, Tensor w, Tensor scale, Tensor shift, Tensor? residual, int cout, int ksize, "
@@ -403,7 +404,19 @@ def _nchw_to_nhwc32_cuda(x, want_raw, want_elu):
     return [t for t in (raw, elu) if t is not None]
 
 
+def _frames_to_uint8_cuda(imgs):
+    if imgs.dtype != torch.float32 or imgs.dim() != 4 or imgs.shape[1] != 3:
+        raise ValueError("frames_to_uint8: imgs must be NCHW fp32 with 3 channels")
+    imgs = imgs.contiguous()
+    B, _, H, W = imgs.shape
+    out = torch.empty((B, H, W, 3), dtype=torch.uint8, device=imgs.device)
+    N.check(_launch("frames_to_uint8", N.lib().vub_frames_to_uint8, imgs.data_ptr(), B, H, W, out.data_ptr(), _stream(),
+                    bytes_=float(imgs.numel() * 5)), "vub_frames_to_uint8")
+    return out
+
+
 _LIB.impl("conv_fwd", _conv_fwd_cuda, "CUDA")
+_LIB.impl("frames_to_uint8", _frames_to_uint8_cuda, "CUDA")
 _LIB.impl("conv_fwd32", _conv_fwd32_cuda, "CUDA")
 _LIB.impl("nchw_to_nhwc32", _nchw_to_nhwc32_cuda, "CUDA")
 _LIB.impl("conv_dgrad", _conv_dgrad_cuda, "CUDA")
@@ -478,6 +491,11 @@ def nchw_to_nhwc(x, want_raw=True, want_elu=True):
 
 def nhwc_to_nchw(x):
     return _ops.nhwc_to_nchw(x)
+
+
+def frames_to_uint8(imgs: torch.Tensor) -> torch.Tensor:
+    """``(scale_img(imgs) * 255).permute(0, 2, 3, 1)`` as uint8 (the reference's video-frame conversion)."""
+    return _ops.frames_to_uint8(imgs)
 
 
 # ---- fp32 validation path -------------------------------------------------------------------------

@@ -145,6 +145,13 @@ int vub_nchw_f32_to_nhwc_bf16(const float* src, int32_t batch, int32_t c, int32_
 int vub_nhwc_bf16_to_nchw_f32(const void* src, int32_t batch, int32_t c, int32_t h, int32_t w,
                               float* dst, void* stream);
 
+/*
+ * Frame epilogue of the video-rendering loop: (scale_img(rgb) * 255).permute(0,2,3,1).astype(uint8)
+ * (lib/utils.py:658-668, data/data_conversions_3d.py:1166-1173) — NCHW fp32 [batch, 3, h, w] in [-1, 1] ->
+ * NHWC uint8 [batch, h, w, 3], bit-exact with the reference expression.  Quarters the device->host bytes.
+ */
+int vub_frames_to_uint8(const float* img_nchw, int32_t batch, int32_t h, int32_t w, uint8_t* out_nhwc, void* stream);
+
 /* Same converter with the channel axis zero-padded to c_pad (multiple of 8) — the image gradient
  * d(loss)/d(imgs) [batch, 3, h, w] entering the backward pass of dd.out_conv (models/vunets.py:411). */
 int vub_nchw_f32_to_nhwc_bf16_pad(const float* src, int32_t batch, int32_t c, int32_t h, int32_t w,

@@ -286,3 +286,21 @@ def test_sequence_level_encoder_reuse_equals_per_frame_transfer():
     assert out.shape == ref.shape and bool(torch.isfinite(out).all())
     with pytest.raises(ValueError):
         m.decode_pose(c.cuda()[:4], app, T)
+
+
+def test_uint8_frame_epilogue_is_bit_exact_with_reference_expression():
+    """(scale_img(rgb) * 255).permute(0, 2, 3, 1).astype(uint8) — lib/utils.py:658-668,
+    data/data_conversions_3d.py:1166-1173."""
+    from bdvs_b200 import ops
+    from bdvs_b200.synthesis import FrameSynthesizer
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(3, 3, 32, 64, generator=g) * 3 - 1.5)  # includes values outside [-1, 1]
+    x[0, 0, 0, :4] = torch.tensor([-1.0, 1.0, 0.0, 0.9999999])
+    ref = (torch.clamp((x + 1.0) / 2.0, 0.0, 1.0) * 255.0).permute(0, 2, 3, 1).numpy().astype("uint8")
+    got = ops.frames_to_uint8(x.cuda()).cpu().numpy()
+    assert got.shape == ref.shape and (got == ref).all()
+    cfg = dict(H256, spatial_size=64)
+    m, _ = build(cfg)
+    fs = FrameSynthesizer(m, 2, uint8_frames=True)
+    out = fs.run()
+    assert out.dtype == torch.uint8 and tuple(out.shape) == (2, 64, 64, 3)
