@@ -376,8 +376,13 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
   // Measured at 64 frames (profiles/r01_tiles_vs_pertap.log): the persistent tile kernel wins for the
   // stride-2 and N >= 256 (up-sampling / latent) layers, the two-CTAs-per-SM per-tap kernel below for the
   // stride-1 N <= 128 layers.  VUB_FWD_TILES=1 / =0 forces one or the other.
+  // On small maps (fewer CTAs than SMs) the persistent kernel's two or three 48 KB stages leave a lone CTA
+  // latency bound (18 k-steps x ~2 us at 4x4); the per-tap kernel with its N split and deep pipeline is 3-5x
+  // faster there.
   const char* force = getenv("VUB_FWD_TILES");
-  const bool want_tiles = force ? force[0] == '1' : (d->stride == 2 || cout >= 256);
+  const long long px_tiles = ((long long)d->batch * hout * wout + kTileM - 1) / kTileM;
+  const bool small_grid = px_tiles * (cout > 256 ? cout / 256 : 1) < 148;
+  const bool want_tiles = force ? force[0] == '1' : ((d->stride == 2 || cout >= 256) && !small_grid);
   if (want_tiles && d->stages >= 0) {
     // persistent tile kernel, k-step table = (source, tap, channel block)
     TileJob job;
@@ -452,7 +457,7 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
     // K loop at the per-SM TMA rate.  Split N over more CTAs (each re-reads the A boxes, 4x smaller weight tiles)
     // until the grid covers about two thirds of the chip.
     const long long pix_tiles = ((long long)d->batch * hout * wout + kTileM - 1) / kTileM;
-    while (bn > 32 && pix_tiles * (cout / bn) < 96 && !(f & VUB_CONV_F32_NHWC)) bn >>= 1;
+    while (bn > 32 && pix_tiles * (cout / bn) < 96) bn >>= 1;
   }
 
   ConvKParams kp;
