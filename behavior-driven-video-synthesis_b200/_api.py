@@ -4,6 +4,7 @@ from ._native import build as build_native
 from .losses import compute_kl_with_prior, kl_loss
 from .modules import (Act, DepthToSpace, Downsample, IDAct, NormConv2d, SpaceToDepth, Upsample, VunetRNB,
                       WeightBank, to_act)
+from .optim import FusedAdam
 from .validation import fp32_validation
 from .vunets import DecDownAlter, DecUp, EncDownAlter, EncUp, VunetAlter
 
@@ -11,5 +12,5 @@ __all__ = [
     "VunetAlter", "EncUp", "EncDownAlter", "DecUp", "DecDownAlter",
     "NormConv2d", "VunetRNB", "Downsample", "Upsample", "DepthToSpace", "SpaceToDepth", "IDAct",
     "compute_kl_with_prior", "kl_loss", "Act", "to_act", "WeightBank", "build_native",
-    "fp32_validation",
+    "fp32_validation", "FusedAdam",
 ]

@@ -39,6 +39,7 @@ EXPORTED_SYMBOLS = (
     "vub_conv_wgrad",
     "vub_conv_wgrad_splits",
     "vub_wn_bwd",
+    "vub_adam_wn_step",
     "vub_stem_bwd",
     "vub_latent_bwd",
 )
@@ -195,6 +196,14 @@ class WnbEntry(C.Structure):
     ]
 
 
+class AdamEntry(C.Structure):
+    """Mirror of ``vub_adam_entry``."""
+
+    _fields_ = ([("wn", WnEntry)]
+                + [(f"{a}_{b}", C.c_void_p) for a in ("d", "m", "s") for b in ("v", "g", "gamma", "beta", "bias")]
+                + [("lr", C.c_float), ("pad", C.c_int32)])
+
+
 _lib = None
 _lock = threading.Lock()
 
@@ -245,6 +254,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.vub_conv_wgrad_splits.argtypes = [C.POINTER(WgradDesc)]
     lib.vub_conv_wgrad.restype = C.c_int
     lib.vub_conv_wgrad.argtypes = [C.POINTER(WgradDesc), vp]
+    lib.vub_adam_wn_step.restype = C.c_int
+    lib.vub_adam_wn_step.argtypes = [vp, i32, i32, C.c_float, C.c_float, C.c_float, i32, vp]
     lib.vub_wn_bwd.restype = C.c_int
     lib.vub_wn_bwd.argtypes = [vp, i32, i32, i32, vp]
     lib.vub_stem_bwd.restype = C.c_int

@@ -40,20 +40,8 @@ __device__ __forceinline__ float block_sum(float v, float* red /*[32]*/) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kWnThreads = 128;
 
-__global__ void __launch_bounds__(kWnThreads)
-    wn_prep_kernel(const vub_wn_entry* __restrict__ table, int n_entries) {
-  __shared__ float red[32];
-  const int row = blockIdx.x;
-  // binary search for the entry with row_start <= row < row_start + cout
-  int lo = 0, hi = n_entries - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (table[mid].row_start <= row) lo = mid;
-    else hi = mid - 1;
-  }
-  const vub_wn_entry e = table[lo];
-  const int co = row - e.row_start;
-  if (co >= e.cout) return;
+// One output channel `co` of one conv: normalise its weight row and emit every prepared form.
+__device__ __forceinline__ void wn_emit_row(const vub_wn_entry& e, int co, float* red /*[32]*/) {
   const int len = e.cin * e.ktaps;
   const float* v = e.v + (size_t)co * len;
   float ss = 0.f;
@@ -93,11 +81,85 @@ __global__ void __launch_bounds__(kWnThreads)
       wd[(size_t)ci * pitch + (size_t)tap * e.wd_cout + e.wd_col0 + co] = __float2bfloat16_rn(v[i] * sc);
     }
   }
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && e.scale != nullptr) {
     const float ga = e.gamma[co];
     e.scale[co] = ga * e.g[co];
     e.shift[co] = fmaf(ga, e.bias[co], e.beta[co]);
   }
+}
+
+__global__ void __launch_bounds__(kWnThreads)
+    wn_prep_kernel(const vub_wn_entry* __restrict__ table, int n_entries) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  // binary search for the entry with row_start <= row < row_start + cout
+  int lo = 0, hi = n_entries - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (table[mid].row_start <= row) lo = mid;
+    else hi = mid - 1;
+  }
+  const vub_wn_entry e = table[lo];
+  const int co = row - e.row_start;
+  if (co >= e.cout) return;
+  wn_emit_row(e, co, red);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused optimizer step: Adam on the five parameter tensors of every NormConv2d AND the
+// weight-norm preparation of the updated weights for the next forward/backward, one pass over the
+// parameters (the reference: torch.optim.Adam(betas=(0.5, 0.9)) over ~470 tensors,
+// experiments/shape_and_pose_net.py:237-246, then the weight_norm hook of every conv in the next forward).
+//   m = b1*m + (1-b1)*g;  s = b2*s + (1-b2)*g*g;  p -= (lr / (1-b1^t)) * m / (sqrt(s) / sqrt(1-b2^t) + eps)
+// One block per output channel: the v row is updated, then (after a block barrier) normalised and packed
+// by the same code as vub_wn_prep.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float adam_update(float p, float g, float& m, float& s, float b1, float b2, float step_size,
+                                             float inv_sqrt_bc2, float eps) {
+  m = fmaf(b1, m, (1.0f - b1) * g);
+  s = fmaf(b2, s, (1.0f - b2) * g * g);
+  return p - step_size * m / (sqrtf(s) * inv_sqrt_bc2 + eps);
+}
+
+__global__ void __launch_bounds__(kWnThreads)
+    adam_wn_kernel(const vub_adam_entry* __restrict__ table, int n_entries, float b1, float b2, float eps, float bc1,
+                   float inv_sqrt_bc2) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  int lo = 0, hi = n_entries - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (table[mid].wn.row_start <= row) lo = mid;
+    else hi = mid - 1;
+  }
+  const vub_adam_entry e = table[lo];
+  const int co = row - e.wn.row_start;
+  if (co >= e.wn.cout) return;
+  const float step_size = e.lr / bc1;
+  const int len = e.wn.cin * e.wn.ktaps;
+  const size_t off = (size_t)co * len;
+  float* v = const_cast<float*>(e.wn.v) + off;
+  for (int i = threadIdx.x; i < len; i += kWnThreads) {
+    float m = e.m_v[off + i], sq = e.s_v[off + i];
+    v[i] = adam_update(v[i], e.d_v[off + i], m, sq, b1, b2, step_size, inv_sqrt_bc2, eps);
+    e.m_v[off + i] = m;
+    e.s_v[off + i] = sq;
+  }
+  if (threadIdx.x < 4) {
+    // the four per-channel scalars: g, gamma, beta, bias
+    float* ps[4] = {const_cast<float*>(e.wn.g), const_cast<float*>(e.wn.gamma), const_cast<float*>(e.wn.beta),
+                    const_cast<float*>(e.wn.bias)};
+    const float* gs[4] = {e.d_g, e.d_gamma, e.d_beta, e.d_bias};
+    float* ms[4] = {e.m_g, e.m_gamma, e.m_beta, e.m_bias};
+    float* ss[4] = {e.s_g, e.s_gamma, e.s_beta, e.s_bias};
+    const int t = threadIdx.x;
+    float m = ms[t][co], sq = ss[t][co];
+    ps[t][co] = adam_update(ps[t][co], gs[t][co], m, sq, b1, b2, step_size, inv_sqrt_bc2, eps);
+    ms[t][co] = m;
+    ss[t][co] = sq;
+  }
+  __syncthreads();  // the updated row and scalars are visible to the whole block
+  wn_emit_row(e.wn, co, red);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -315,6 +377,19 @@ extern "C" int vub_wn_prep(const vub_wn_entry* table_dev, int32_t n_entries, int
   if (n_entries <= 0 || total_rows <= 0) return fail(VUB_E_SHAPE, "wn_prep: empty table");
   wn_prep_kernel<<<total_rows, kWnThreads, 0, static_cast<cudaStream_t>(stream)>>>(table_dev, n_entries);
   return check_launch("wn_prep");
+}
+
+extern "C" int vub_adam_wn_step(const vub_adam_entry* table_dev, int32_t n_entries, int32_t total_rows, float beta1,
+                                float beta2, float eps, int32_t step, void* stream) {
+  clear_error();
+  if (!table_dev) return fail(VUB_E_NULL, "adam_wn_step: table is NULL");
+  if (n_entries <= 0 || total_rows <= 0 || step < 1) return fail(VUB_E_SHAPE, "adam_wn_step: empty table or step < 1");
+  if (!(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f)) return fail(VUB_E_SHAPE, "adam_wn_step: betas");
+  const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
+  const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
+  adam_wn_kernel<<<total_rows, kWnThreads, 0, static_cast<cudaStream_t>(stream)>>>(table_dev, n_entries, beta1, beta2, eps,
+                                                                                  bc1, 1.0f / sqrtf(bc2));
+  return check_launch("adam_wn_step");
 }
 
 extern "C" int vub_stem_fwd(const float* x_nchw, const float* v, const float* g, const float* gamma,

@@ -93,6 +93,20 @@ def _pad_cout(c: int) -> int:
     raise NotImplementedError(f"no kernel for {c} output channels")
 
 
+# Parameters can also change through raw device pointers (optim.FusedAdam), which autograd version counters do
+# not see: such writers bump this epoch, and every bank's cache key includes it.
+_WEIGHT_EPOCH = [0]
+
+
+def bump_weight_epoch() -> int:
+    _WEIGHT_EPOCH[0] += 1
+    return _WEIGHT_EPOCH[0]
+
+
+def weights_key(params) -> tuple:
+    return (_WEIGHT_EPOCH[0],) + tuple(p._version for p in params)
+
+
 class WeightBank:
     """All tensor-core convs of a module tree, prepared by ONE ``wn_prep`` launch per refresh.
 
@@ -108,6 +122,10 @@ class WeightBank:
         self._with_wd = False
         self.tape = None  # training: list the forward pass appends its records to (training.Tape)
         self.precision = "bf16"  # validation.WeightBank32 says "fp32"
+
+    def __deepcopy__(self, memo):
+        # a cache of device pointers into ONE module tree: copy.deepcopy(model) starts without it and rebuilds lazily
+        return None
 
     @staticmethod
     def for_module(root: nn.Module) -> "WeightBank":
@@ -155,6 +173,7 @@ class WeightBank:
         self._shift = torch.zeros(s_off, dtype=torch.float32, device=device)
         entries = []
         self._views = {}
+        self._entry_of = {}  # id(NormConv2d) -> its host-side WnEntry (optim.FusedAdam embeds it)
         for si, (slot, (wo, so, k, cout, cpad, nsrc, c_src, wdo, cout_k)) in enumerate(zip(self.slots, layout)):
             first = slot[0]
             w = self._w[wo:wo + cpad * k].view(cpad, k)
@@ -182,6 +201,7 @@ class WeightBank:
                 rows += m.out_channels
                 r += m.out_channels
                 entries.append(e)
+                self._entry_of[id(m)] = e
         arr = (N.WnEntry * len(entries))(*entries)
         host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
         self._table = host.to(device)
@@ -210,10 +230,14 @@ class WeightBank:
             self._allocate(dev, with_wd)
             self._ptr_key = ptr_key
             self._key = None
-        key = tuple(p._version for p in params)
+        key = weights_key(params)
         if key != self._key:
             ops.wn_prep(self._table, self._n_entries, self._rows)
             self._key = key
+
+    def mark_current(self) -> None:
+        """The prepared weights were just re-emitted by another launch (optim.FusedAdam)."""
+        self._key = weights_key(list(self._params()))
 
     def get(self, conv: "NormConv2d") -> ConvWeights:
         return self._views[id(conv)]

@@ -48,6 +48,7 @@ _LIB.define(
     "bool d2s) -> ()"
 )
 _LIB.define("wn_bwd(Tensor table, int n_entries, int total_rows, bool accumulate) -> ()")
+_LIB.define("adam_wn_step(Tensor table, int n_entries, int total_rows, float beta1, float beta2, float eps, int step) -> ()")
 _LIB.define("stem_bwd(Tensor x, Tensor dy, Tensor(a!) gt, Tensor(b!) dy_sum) -> ()")
 _LIB.define("latent_bwd(Tensor logstd, Tensor? eps, Tensor? d_mu, Tensor? d_ls, Tensor? dz) -> Tensor")
 _LIB.define("nchw_to_nhwc_pad(Tensor x, int c_pad) -> Tensor")
@@ -320,6 +321,11 @@ def _wn_bwd_cuda(table, n_entries, total_rows, accumulate) -> None:
             "vub_wn_bwd")
 
 
+def _adam_wn_step_cuda(table, n_entries, total_rows, beta1, beta2, eps, step) -> None:
+    N.check(_launch("adam_wn_step", N.lib().vub_adam_wn_step, table.data_ptr(), n_entries, total_rows, beta1, beta2, eps,
+                    step, _stream()), "vub_adam_wn_step")
+
+
 def _stem_bwd_cuda(x, dy, gt, dy_sum) -> None:
     if x.dtype != torch.float32 or x.dim() != 4 or not x.is_contiguous():
         raise ValueError("stem_bwd: x must be contiguous NCHW fp32")
@@ -422,6 +428,7 @@ _LIB.impl("nchw_to_nhwc32", _nchw_to_nhwc32_cuda, "CUDA")
 _LIB.impl("conv_dgrad", _conv_dgrad_cuda, "CUDA")
 _LIB.impl("conv_wgrad", _conv_wgrad_cuda, "CUDA")
 _LIB.impl("wn_bwd", _wn_bwd_cuda, "CUDA")
+_LIB.impl("adam_wn_step", _adam_wn_step_cuda, "CUDA")
 _LIB.impl("stem_bwd", _stem_bwd_cuda, "CUDA")
 _LIB.impl("latent_bwd", _latent_bwd_cuda, "CUDA")
 _LIB.impl("nchw_to_nhwc_pad", _nchw_to_nhwc_pad_cuda, "CUDA")
@@ -533,6 +540,11 @@ def conv_wgrad(dy, x, gt, dy_sum, *, ksize: int, stride: int = 1, d2s: bool = Fa
 
 def wn_bwd(table: torch.Tensor, n_entries: int, total_rows: int, accumulate: bool = False) -> None:
     _ops.wn_bwd(table, n_entries, total_rows, accumulate)
+
+
+def adam_wn_step(table: torch.Tensor, n_entries: int, total_rows: int, beta1: float, beta2: float, eps: float,
+                 step: int) -> None:
+    _ops.adam_wn_step(table, n_entries, total_rows, beta1, beta2, eps, step)
 
 
 def stem_bwd(x, dy, gt, dy_sum) -> None:

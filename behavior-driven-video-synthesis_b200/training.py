@@ -182,6 +182,9 @@ class GradBank:
             self._tables[owner] = (host.to(dev), len(entries), rows)
         self._ptr_key = tuple(p.data_ptr() for ps in self.params.values() for p in ps)
 
+    def __deepcopy__(self, memo):
+        return None  # pointer cache of one module tree (see WeightBank.__deepcopy__)
+
     def matches(self, tape: Tape, model) -> bool:
         if _tape_signature(tape) != self.key:
             return False

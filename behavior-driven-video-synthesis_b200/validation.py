@@ -17,6 +17,7 @@ from torch import nn
 
 from . import _native as N
 from . import ops
+from .modules import weights_key
 
 
 class ConvWeights32:
@@ -34,6 +35,9 @@ class WeightBank32:
     prepared by one ``wn_prep`` launch that emits fp32 matrices only."""
 
     precision = "fp32"
+
+    def __deepcopy__(self, memo):
+        return None  # pointer cache of one module tree (see WeightBank.__deepcopy__)
 
     def __init__(self, root: nn.Module):
         from .modules import NormConv2d
@@ -108,7 +112,7 @@ class WeightBank32:
         if ptr_key != self._ptr_key:
             self._allocate(dev)
             self._ptr_key, self._key = ptr_key, None
-        key = tuple(p._version for p in params)
+        key = weights_key(params)
         if key != self._key:
             ops.wn_prep(self._table, self._n_entries, self._rows)
             self._key = key

@@ -276,6 +276,26 @@ int vub_wn_bwd(const vub_wnb_entry* table_dev, int32_t n_entries, int32_t total_
                void* stream);
 
 /*
+ * Fused optimizer step: torch.optim.Adam (no weight decay, no amsgrad; the reference uses
+ * betas = (0.5, 0.9), experiments/shape_and_pose_net.py:237-246) on beta / gamma / bias / weight_g / weight_v of
+ * every listed NormConv2d, fused with the weight-norm preparation (vub_wn_prep) of the UPDATED weights for the
+ * next step: one pass over the parameters, one launch.  `wn` describes the conv exactly like vub_wn_prep's entry
+ * (prepared outputs may be NULL, e.g. for the stems); gradients and moment buffers have the parameters' shapes;
+ * `step` is the 1-based step count (bias correction); `lr` is per entry (parameter groups).
+ */
+typedef struct vub_adam_entry {
+  vub_wn_entry wn;
+  const float *d_v, *d_g, *d_gamma, *d_beta, *d_bias;
+  float *m_v, *m_g, *m_gamma, *m_beta, *m_bias;   /* exp_avg */
+  float *s_v, *s_g, *s_gamma, *s_beta, *s_bias;   /* exp_avg_sq */
+  float lr;
+  int32_t pad;
+} vub_adam_entry;
+
+int vub_adam_wn_step(const vub_adam_entry* table_dev, int32_t n_entries, int32_t total_rows, float beta1, float beta2,
+                     float eps, int32_t step, void* stream);
+
+/*
  * Backward of the stem (first 1x1 NormConv2d on the NCHW fp32 input, vub_stem_fwd): correlation of the
  * output gradient with the input, gt[co][ci] += sum dy[pix, co]*x[pix, ci], dy_sum[co] += sum dy.
  * The stem needs no data gradient (its input is the image).  gt pitch = cx.

@@ -123,6 +123,7 @@ def test_library_loads_and_exports_every_symbol():
     assert ctypes.sizeof(_native.DgradDesc) == 10 * 8 + 9 * 4 + 4  # padded to 8
     assert ctypes.sizeof(_native.WgradDesc) == 6 * 8 + 12 * 4
     assert ctypes.sizeof(_native.WnbEntry) == 11 * 8 + 8 * 4 + 8 + 2 * 4
+    assert ctypes.sizeof(_native.AdamEntry) == ctypes.sizeof(_native.WnEntry) + 15 * 8 + 2 * 4
 
 
 def test_bad_arguments_are_reported_not_crashed():
