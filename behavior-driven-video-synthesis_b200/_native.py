@@ -19,12 +19,15 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "vunet_b200.h")
 CONV_D2S = 1
 CONV_F32_NHWC = 2
 CONV_F32_NCHW = 4
+CONV_ELU_IN0 = 8
+CONV_ELU_IN1 = 16
 
 # every extern "C" symbol the header declares; tests check the built library exports all of them
 EXPORTED_SYMBOLS = (
     "vub_abi_version",
     "vub_last_error",
     "vub_conv_fwd",
+    "vub_conv_fwd_elu_in_ok",
     "vub_wn_prep",
     "vub_stem_fwd",
     "vub_latent_num_partials",
@@ -254,6 +257,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.vub_conv_wgrad_splits.argtypes = [C.POINTER(WgradDesc)]
     lib.vub_conv_wgrad.restype = C.c_int
     lib.vub_conv_wgrad.argtypes = [C.POINTER(WgradDesc), vp]
+    lib.vub_conv_fwd_elu_in_ok.restype = C.c_int
+    lib.vub_conv_fwd_elu_in_ok.argtypes = [i32] * 7
     lib.vub_adam_wn_step.restype = C.c_int
     lib.vub_adam_wn_step.argtypes = [vp, i32, i32, C.c_float, C.c_float, C.c_float, i32, vp]
     lib.vub_wn_bwd.restype = C.c_int

@@ -94,25 +94,40 @@ __device__ __forceinline__ void epi_store(const EpiParams& p, float (&y)[CH], in
 // After tcgen05.ld a lane owns ONE pixel and all its channels, so a direct `st.global.v4` per lane hits
 // 32 different cache lines per warp instruction and the L1 tag stage (1 line/cycle) becomes the
 // bottleneck of every HBM-bound layer (ncu: profiles/r01_ncu_notes.md).  Instead each warp parks its
-// 32 pixels x GW channels in shared memory (row pitch GW*2+16 bytes: the 16-byte pad makes both the
-// row-wise writes and the linear read-back bank-conflict free) and writes them back with consecutive
-// lanes covering consecutive 16-byte chunks, i.e. 512 contiguous bytes per warp instruction.
+// 32 pixels x GW channels in shared memory and writes them back with consecutive lanes covering
+// consecutive 16-byte chunks, i.e. 512 contiguous bytes per warp instruction.
+//
+// Layout: unpadded rows of GW*2 bytes with an XOR swizzle of the 16-byte chunk index, chosen so that BOTH
+// access patterns are bank-conflict free for 128-bit accesses (a quarter warp = 8 lanes must touch 8
+// different 16-byte bank groups): "row per lane" (lane r, fixed chunk) and "linear" (8 consecutive chunks).
+// The earlier +16-byte row pad made only the first pattern conflict free; the linear pass took 2 wavefronts
+// per quarter warp, and ncu showed the shared-memory data pipe (LSU wavefronts + the tensor core's operand
+// reads) saturated in the row-streaming kernel (profiles/r01_ncu_rows_smem.txt).
 // ------------------------------------------------------------------------------------------------
 template <int GW>
 struct EpiStage {
-  static constexpr int PITCH = GW * 2 + 16;
+  static constexpr int CPR = GW / 8;                 // 16-byte chunks per staged row
+  static constexpr int PITCH = GW * 2;
   static constexpr int TILE_BYTES = 32 * PITCH;      // one staged copy (raw OR elu) of a warp's tile
   static constexpr int WARP_BYTES = 2 * TILE_BYTES;  // raw + elu
+  // byte offset of 16-byte chunk `chunk` of staged row `row`
+  __device__ __forceinline__ static uint32_t off(int row, int chunk) {
+    if constexpr (CPR >= 8) {
+      return row * PITCH + ((chunk ^ (row & 7)) << 4);
+    } else {
+      constexpr int RP = 8 / CPR;  // rows per 128 bytes
+      return row * PITCH + ((chunk ^ ((row / RP) & (CPR - 1))) << 4);
+    }
+  }
 };
 
 // Stage 32 consecutive channels (starting at channel `c` of the group) of this lane's pixel.
 // `tile` is a shared-space byte address.
 template <int GW>
 __device__ __forceinline__ void stage_put32(uint32_t tile, int lane, int c, const float (&y)[32]) {
-  const uint32_t dst = tile + lane * EpiStage<GW>::PITCH + c * 2;
 #pragma unroll
   for (int j = 0; j < 4; ++j)
-    sts128(dst + 16 * j,
+    sts128(tile + EpiStage<GW>::off(lane, (c >> 3) + j),
            make_uint4(pack_bf16x2(y[8 * j + 0], y[8 * j + 1]), pack_bf16x2(y[8 * j + 2], y[8 * j + 3]),
                       pack_bf16x2(y[8 * j + 4], y[8 * j + 5]), pack_bf16x2(y[8 * j + 6], y[8 * j + 7])));
 }
@@ -143,7 +158,7 @@ __device__ __forceinline__ void stage_flush(uint32_t tile, __nv_bfloat16* out, c
     const int col = c - row * CPR;
     int n, oh, ow;
     if (coord(row, n, oh, ow)) {
-      const uint4 v = lds128(tile + row * EpiStage<GW>::PITCH + col * 16);
+      const uint4 v = lds128(tile + EpiStage<GW>::off(row, col));
       *reinterpret_cast<uint4*>(out + epi_out_offset(p, c_group + col * 8, n, oh, ow)) = v;
     }
   }
@@ -160,7 +175,7 @@ __device__ __forceinline__ void stage_flush_linear(uint32_t tile, __nv_bfloat16*
     const int c = lane + 32 * k;
     const int row = c / CPR;
     const int col = c - row * CPR;
-    dst[c] = lds128(tile + row * EpiStage<GW>::PITCH + col * 16);
+    dst[c] = lds128(tile + EpiStage<GW>::off(row, col));
   }
 }
 
@@ -174,7 +189,7 @@ __device__ __forceinline__ void stage_fill_linear(uint32_t tile, const uint4 (&c
     const int c = lane + 32 * k;
     const int row = c / CPR;
     const int col = c - row * CPR;
-    sts128(tile + row * EpiStage<GW>::PITCH + col * 16, chunks[k]);
+    sts128(tile + EpiStage<GW>::off(row, col), chunks[k]);
   }
 }
 

@@ -305,6 +305,21 @@ static int default_stages(int bn, int bkc, int ksteps) {
 
 using namespace vub;
 
+extern "C" int vub_conv_fwd_elu_in_ok(int32_t nsrc, int32_t c_src, int32_t cout, int32_t ksize, int32_t stride,
+                                      int32_t hin, int32_t win) {
+  vub_conv_desc d;
+  memset(&d, 0, sizeof(d));
+  d.nsrc = nsrc;
+  d.c_src = c_src;
+  d.cout = cout;
+  d.ksize = ksize;
+  d.stride = stride;
+  d.hin = hin;
+  d.win = win;
+  d.flags = VUB_CONV_ELU_IN0;
+  return conv_rows_applicable(&d) ? 1 : 0;
+}
+
 extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
   clear_error();
   if (!d) return fail(VUB_E_NULL, "conv_fwd: desc is NULL");
@@ -342,6 +357,9 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
     if (q && !aligned16(q)) return fail(VUB_E_ALIGN, "conv_fwd: pointer %p not 16B aligned", q);
 
   if (conv_rows_applicable(d)) return conv_rows_launch(d, static_cast<cudaStream_t>(stream_v));
+  if (f & (VUB_CONV_ELU_IN0 | VUB_CONV_ELU_IN1))
+    return fail(VUB_E_FLAGS, "conv_fwd: ELU-on-load is only implemented by the row-streaming kernel "
+                             "(see vub_conv_fwd_elu_in_ok) — store an ELU copy for this layer");
 
   // tensor-core-bound 3x3 layers at 64x64 / 32x32: activation-slab kernel (A and weight reuse in smem)
   if (d->ksize == 3 && d->stride == 1 && d->stages >= 0 && !f32 && conv_slab_shape_ok(d->c_src, d->hin, d->win, cout, d->nsrc * 9 * d->c_src)) {

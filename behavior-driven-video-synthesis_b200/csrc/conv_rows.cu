@@ -30,7 +30,8 @@
 
 namespace vub {
 
-constexpr int kRowsThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue A, warps 6-9 epilogue B
+constexpr int kRowsThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue A, warps 6-9 epilogue B
+constexpr int kRowsThreadsElu = 448;  // + warps 10-13: ELU-on-load transform of freshly landed input rows
 constexpr int kRowsMaxRing = 8;
 constexpr int kRowsW = 128;  // output columns per CTA = UMMA M
 
@@ -50,6 +51,10 @@ struct RowsKParams {
   int n_halves;         // 0 = forward epilogue (ep), 1 or 2 = data-gradient epilogue (bwd[])
   int stage_tiles;      // staging tiles per epilogue warp in data-gradient mode
   TileEpi bwd[2];
+  // ELU-on-load (VUB_CONV_ELU_IN0/1): bit s set = source s holds RAW activations; four extra warps apply ELU to
+  // every input row in place in its ring slot before the tensor core reads it, so the producer of that tensor
+  // never writes an ELU copy to HBM and the residual (the same raw tensor) is an L2 hit.
+  int elu_in;
 };
 
 template <int BKC>
@@ -97,8 +102,20 @@ struct RowWalker {
   }
 };
 
-template <int BN, int BKC, int NTAPS, int NSRC>
-__global__ void __launch_bounds__(kRowsThreads, 1)
+// ELU on 8 packed bf16 values (fp32 math, one MUFU.EX2 each)
+__device__ __forceinline__ void elu_bf16x8(uint4& v) {
+  float f[8];
+  unpack_bf16x2(v.x, f[0], f[1]);
+  unpack_bf16x2(v.y, f[2], f[3]);
+  unpack_bf16x2(v.z, f[4], f[5]);
+  unpack_bf16x2(v.w, f[6], f[7]);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) f[k] = elu1(f[k]);
+  v = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+template <int BN, int BKC, int NTAPS, int NSRC, bool ELU_IN>
+__global__ void __launch_bounds__(ELU_IN ? kRowsThreadsElu : kRowsThreads, 1)
     conv_rows_kernel(const __grid_constant__ RowsKParams p) {
   using G = RowsGeom<BKC>;
   constexpr int ROWB = G::ROWB;
@@ -119,6 +136,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
   __shared__ uint64_t w_full;
   __shared__ uint64_t slot_full[kRowsMaxRing];
   __shared__ uint64_t slot_empty[kRowsMaxRing];
+  __shared__ uint64_t slot_ready[kRowsMaxRing];  // ELU-on-load: the slot's rows have been transformed
   __shared__ uint64_t acc_full[2];
   __shared__ uint64_t acc_empty[2];
   __shared__ uint32_t tmem_base_slot;
@@ -145,6 +163,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
     for (int i = 0; i < R; ++i) {
       mbar_init(&slot_full[i], 1);
       mbar_init(&slot_empty[i], 1);
+      mbar_init(&slot_ready[i], 4);  // one arrival per transform warp
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
@@ -213,6 +232,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
     uint32_t wait_ph = 0;
     int rows_seen = 0, rows_needed = 0;  // running input-row counters
     uint32_t go = 0;                     // running output-row counter
+    uint64_t* const in_bar = ELU_IN ? slot_ready : slot_full;
     RowWalker rw;
     for (rw.init(g_begin, g_end, p.ep.hout, p.batch); rw.valid(); rw.next_segment()) {
       const int th = rw.seg_left;
@@ -221,7 +241,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
         mbar_wait(&acc_empty[b], ((go >> 1) & 1) ^ 1);
         rows_needed += (orow == 0) ? 1 + 2 * halo : 1;
         for (; rows_seen < rows_needed; ++rows_seen) {
-          mbar_wait(&slot_full[wait_slot], wait_ph);
+          mbar_wait(&in_bar[wait_slot], wait_ph);
           if (++wait_slot == R) {
             wait_slot = 0;
             wait_ph ^= 1;
@@ -265,6 +285,55 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
         if (last && halo) slot0 = sl[2] + 1 >= R ? sl[2] + 1 - R : sl[2] + 1;
       }
     }
+  } else if (warp >= 10) {
+    // ------------------------------ ELU-on-load transform ---------------------------------------
+    // Elementwise and in place, so the TMA swizzle inside the slot does not matter: the box footprint is the
+    // contiguous first (128 + 2*halo) * ROWB bytes of each source's buffer.
+    if constexpr (!ELU_IN) return;
+    const int tw = warp - 10;
+    constexpr int n_chunks = (kRowsW + 2 * halo) * ROWB / 16;
+    int st = 0;
+    uint32_t ph = 0;
+    RowWalker rw;
+    for (rw.init(g_begin, g_end, p.ep.hout, p.batch); rw.valid(); rw.next_segment()) {
+      const int n_in_rows = rw.seg_left + 2 * halo;
+      for (int ir = 0; ir < n_in_rows; ++ir) {
+        mbar_wait(&slot_full[st], ph);
+#pragma unroll
+        for (int s = 0; s < NSRC; ++s) {
+          if (!((p.elu_in >> s) & 1)) continue;
+          const uint32_t base = smem_u32(ring + st * slot_bytes + s * SRC_BYTES);
+          // full passes: 4 independent 16-byte chunks (32 elements) in flight per lane, no branches, so the
+          // MUFU / FP32 latencies of one chunk hide behind the other three
+          constexpr int n_full = n_chunks / 512;
+#pragma unroll 1
+          for (int it = 0; it < n_full; ++it) {
+            const uint32_t a0 = base + 16 * (it * 512 + tw * 32 + lane);
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = lds128(a0 + u * 2048);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) elu_bf16x8(v[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) sts128(a0 + u * 2048, v[u]);
+          }
+          constexpr int n_tail = n_chunks - n_full * 512;  // the halo pixels: 8 (C = 32) or 16 (C = 64) chunks
+          if (n_tail > 0 && tw == 0 && lane < n_tail) {
+            const uint32_t a0 = base + 16 * (n_full * 512 + lane);
+            uint4 v = lds128(a0);
+            elu_bf16x8(v);
+            sts128(a0, v);
+          }
+        }
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&slot_ready[st]);
+        if (++st == R) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+    }
   } else {
     // ------------------------------ epilogue (two warpgroups, alternating rows) ----------------
     const int g = (warp - 2) >> 2;  // warpgroup 0: warps 2-5 (even running rows), 1: warps 6-9 (odd)
@@ -298,17 +367,19 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
         const uint32_t b0 = smem_u32(staging) + (warp - 2) * p.stage_tiles * EpiStage<32>::TILE_BYTES;
         const uint32_t b1 = b0 + EpiStage<32>::TILE_BYTES, b2 = b1 + EpiStage<32>::TILE_BYTES;
         uint32_t cntb = 0;
+        const float* sc = p.ep.scale != nullptr ? s_scale : nullptr;  // data gradients: identity, skip the loads
+        const float* sh = p.ep.scale != nullptr ? s_shift : nullptr;
         while (cur.valid()) {
           mbar_wait(&acc_full[g], cntb & 1);
           tc_fence_after();
           if (p.n_halves == 1) {
-            tile_epilogue_staged<BN, 32>(p.bwd[0], gm, s_scale, s_shift, trow, b0, b1, b2, lane, q, 0, cur.n, cur.h,
+            tile_epilogue_staged<BN, 32>(p.bwd[0], gm, sc, sh, trow, b0, b1, b2, lane, q, 0, cur.n, cur.h,
                                          cur.w0, &acc_empty[g]);
           } else {
             if constexpr (BN == 64) {
-              tile_epilogue_staged<32, 32>(p.bwd[0], gm, s_scale, s_shift, trow, b0, b1, b2, lane, q, 0, cur.n, cur.h,
+              tile_epilogue_staged<32, 32>(p.bwd[0], gm, sc, sh, trow, b0, b1, b2, lane, q, 0, cur.n, cur.h,
                                            cur.w0, nullptr);
-              tile_epilogue_staged<32, 32>(p.bwd[1], gm, s_scale + 32, s_shift + 32, trow + 32, b0, b1, b2, lane, q, 0,
+              tile_epilogue_staged<32, 32>(p.bwd[1], gm, sc ? sc + 32 : nullptr, sh ? sh + 32 : nullptr, trow + 32, b0, b1, b2, lane, q, 0,
                                            cur.n, cur.h, cur.w0, &acc_empty[g]);
             }
           }
@@ -325,6 +396,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
       if (ahead.valid()) ahead.next_row();
       if (ahead.valid()) ahead.next_row();
       const int n = cur.n, oh = cur.h, ow = cur.w0 + m;
+      // (Loading the residual straight into per-lane registers instead of staging it was measured: no gain at
+      // BN = 32 and 18 % slower at BN = 64 — 32 cache lines per load instruction; profiles/r01_ncu_rows_smem.txt.)
       if constexpr (STAGED) {
         if (has_res && bf16_out) {
           stage_fill_linear<SGW>(t0, rblk, lane);  // residual block -> staging; lanes then read their own row
@@ -353,7 +426,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
             if (has_res) {
 #pragma unroll
               for (int j = 0; j < CH / 8; ++j)
-                add_bf16x8(lds128(t0 + lane * EpiStage<SGW>::PITCH + c * CH * 2 + 16 * j), &y[8 * j]);
+                add_bf16x8(lds128(t0 + EpiStage<SGW>::off(lane, c * (CH / 8) + j)), &y[8 * j]);
             }
             if (p.ep.out_raw != nullptr) stage_put32<SGW>(t0, lane, c * CH, y);
             if (p.ep.out_elu != nullptr) {
@@ -392,23 +465,34 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int BN, int BKC, int NTAPS, int NSRC>
+template <int BN, int BKC, int NTAPS, int NSRC, bool ELU_IN = false>
 static int launch_rows_t(const RowsKParams& kp, int grid, size_t smem, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_rows_kernel<BN, BKC, NTAPS, NSRC>,
+    attr_err = cudaFuncSetAttribute(conv_rows_kernel<BN, BKC, NTAPS, NSRC, ELU_IN>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
   });
   if (attr_err != cudaSuccess)
     return fail(static_cast<int>(attr_err), "cudaFuncSetAttribute(conv_rows<%d,%d>): %s", BN, BKC,
                 cudaGetErrorString(attr_err));
-  conv_rows_kernel<BN, BKC, NTAPS, NSRC><<<grid, kRowsThreads, smem, stream>>>(kp);
+  conv_rows_kernel<BN, BKC, NTAPS, NSRC, ELU_IN><<<grid, ELU_IN ? kRowsThreadsElu : kRowsThreads, smem, stream>>>(kp);
   return check_launch("conv_rows");
 }
 
 template <int BN, int BKC>
 static int launch_rows(const RowsKParams& kp, int grid, size_t smem, cudaStream_t stream) {
+  if (kp.elu_in) {  // ELU-on-load: the square layers of the residual blocks and their 1x1 skip convs
+    if constexpr (BN == BKC && (BN == 32 || BN == 64)) {
+      if (kp.ntaps == 9 && kp.nsrc == 1) return launch_rows_t<BN, BKC, 9, 1, true>(kp, grid, smem, stream);
+      if (kp.ntaps == 1 && kp.nsrc == 1) return launch_rows_t<BN, BKC, 1, 1, true>(kp, grid, smem, stream);
+      if constexpr (BN == 32) {
+        if (kp.ntaps == 9 && kp.nsrc == 2) return launch_rows_t<BN, BKC, 9, 2, true>(kp, grid, smem, stream);
+      }
+    }
+    return fail(VUB_E_FLAGS, "conv_rows: no ELU-on-load variant for BN %d BKC %d taps %d nsrc %d", BN, BKC, kp.ntaps,
+                kp.nsrc);
+  }
   if (kp.ntaps == 9 && kp.nsrc == 1) return launch_rows_t<BN, BKC, 9, 1>(kp, grid, smem, stream);
   if (kp.ntaps == 9 && kp.nsrc == 2) return launch_rows_t<BN, BKC, 9, 2>(kp, grid, smem, stream);
   if (kp.ntaps == 1 && kp.nsrc == 1) return launch_rows_t<BN, BKC, 1, 1>(kp, grid, smem, stream);
@@ -421,7 +505,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 static size_t rows_staging_bytes(int bn) {
-  return (bn >= 32 && bn <= 64) ? (size_t)8 * 2 * 32 * (bn * 2 + 16) : 0;
+  return (bn >= 32 && bn <= 64) ? (size_t)8 * 2 * 32 * (bn * 2) : 0;
 }
 
 // One launch of the row-streaming kernel, forward or data-gradient mode.
@@ -434,6 +518,7 @@ struct RowsJob {
   EpiParams ep;         // forward epilogue (scale / shift always come from here; may be NULL = identity)
   int flip, n_halves, stage_tiles;
   TileEpi bwd[2];
+  int elu_in;           // VUB_CONV_ELU_IN bits, as a source mask
 };
 
 static bool rows_shape_ok(int nsrc, int c_src, int bn, int taps, int h, int w, size_t staging) {
@@ -463,6 +548,7 @@ static int rows_job_launch(const RowsJob& j, cudaStream_t stream) {
   kp.stage_tiles = j.stage_tiles;
   kp.bwd[0] = j.bwd[0];
   kp.bwd[1] = j.bwd[1];
+  kp.elu_in = j.elu_in & ((1 << j.nsrc) - 1);
   const size_t wbytes = (size_t)j.nsrc * j.taps * j.bn * bkc * 2;
   const size_t slot = (size_t)j.nsrc * (bkc == 64 ? 136 * 128 : 144 * 64);
   const int ring_env = env_int("VUB_ROWS_RING", 0);
@@ -521,6 +607,12 @@ static int rows_job_launch(const RowsJob& j, cudaStream_t stream) {
 // Returns true when the row-streaming kernel covers this (already validated) descriptor.
 bool conv_rows_applicable(const vub_conv_desc* d) {
   if (d->stages < 0 || d->stride != 1) return false;
+  if (d->flags & (VUB_CONV_ELU_IN0 | VUB_CONV_ELU_IN1)) {
+    // variants instantiated in launch_rows
+    const bool square = d->cout == d->c_src && (d->cout == 32 || d->cout == 64);
+    const bool shape = (d->nsrc == 1 && (d->ksize == 3 || d->ksize == 1)) || (d->nsrc == 2 && d->ksize == 3 && d->cout == 32);
+    if (!square || !shape) return false;
+  }
   return rows_shape_ok(d->nsrc, d->c_src, d->cout, d->ksize * d->ksize, d->hin, d->win, rows_staging_bytes(d->cout));
 }
 
@@ -546,6 +638,7 @@ int conv_rows_launch(const vub_conv_desc* d, cudaStream_t stream) {
   j.ep.cout = d->cout;
   j.ep.cout_valid = d->cout_valid;
   j.ep.flags = d->flags;
+  j.elu_in = ((d->flags & VUB_CONV_ELU_IN0) ? 1 : 0) | ((d->flags & VUB_CONV_ELU_IN1) ? 2 : 0);
   return rows_job_launch(j, stream);
 }
 

@@ -200,8 +200,9 @@ __global__ void __launch_bounds__(kTilesThreads, 1)
       mbar_wait(&acc_full[g], cnt & 1);
       tc_fence_after();
       if constexpr (STAGED) {
-        tile_epilogue_staged<BN, GW>(e, EpiGeom{p.tw, p.th, p.tw_log2, p.th_log2, p.batch}, s_scale + n_tile * BN,
-                                     s_shift + n_tile * BN, trow, t0, t1, t2, lane, q, ecol, n0, h0, w0, &acc_empty[g]);
+        const bool affine = p.ep[0].scale != nullptr;  // data gradients run with the identity
+        tile_epilogue_staged<BN, GW>(e, EpiGeom{p.tw, p.th, p.tw_log2, p.th_log2, p.batch},
+                                     affine ? s_scale + n_tile * BN : nullptr, affine ? s_shift + n_tile * BN : nullptr, trow, t0, t1, t2, lane, q, ecol, n0, h0, w0, &acc_empty[g]);
       } else {
         // BN == 16: fp32 NCHW output of out_conv-like layers
         uint32_t acc[16];

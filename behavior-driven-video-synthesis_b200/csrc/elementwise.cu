@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 
 #include "common.h"
+#include "conv_epilogue.cuh"
 #include "ptx.cuh"
 
 namespace vub {
@@ -202,10 +203,9 @@ __global__ void __launch_bounds__(kStemThreads)
   }
   // Coalesced stores: a thread owns one pixel (COUT*2 contiguous bytes), so direct 16-byte stores from the
   // 32 lanes of a warp hit 32 different 64/128-byte segments per instruction.  The block's 128 pixels are one
-  // contiguous span of the NHWC output: stage them in shared memory (padded pitch) and write the span linearly.
-  constexpr int PITCH = COUT * 2 + 16;
+  // contiguous span of the NHWC output: stage them in shared memory (swizzled, see EpiStage) and write the span linearly.
   constexpr int CPR = COUT / 8;  // 16-byte chunks per pixel
-  __shared__ __align__(16) uint8_t s_out[kStemThreads * PITCH];
+  __shared__ __align__(128) uint8_t s_out[kStemThreads * COUT * 2];
   const long long pix0 = (long long)blockIdx.x * kStemThreads;
 #pragma unroll
   for (int which = 0; which < 2; ++which) {
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kStemThreads)
         for (int i = 0; i < 8; ++i) t[i] = which == 0 ? acc[8 * j + i] : elu1(acc[8 * j + i]);
         __nv_bfloat162 a = __floats2bfloat162_rn(t[0], t[1]), b2 = __floats2bfloat162_rn(t[2], t[3]);
         __nv_bfloat162 c2 = __floats2bfloat162_rn(t[4], t[5]), d2 = __floats2bfloat162_rn(t[6], t[7]);
-        *reinterpret_cast<uint4*>(s_out + threadIdx.x * PITCH + j * 16) =
+        *reinterpret_cast<uint4*>(s_out + EpiStage<COUT>::off(threadIdx.x, j)) =
             make_uint4(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b2),
                        *reinterpret_cast<uint32_t*>(&c2), *reinterpret_cast<uint32_t*>(&d2));
       }
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(kStemThreads)
     for (int k = 0; k < CPR; ++k) {
       const int c = threadIdx.x + kStemThreads * k;  // chunk index inside the block's span
       const int row = c / CPR, col = c - row * CPR;
-      if (pix0 + row < total_pix) dst[c] = *reinterpret_cast<const uint4*>(s_out + row * PITCH + col * 16);
+      if (pix0 + row < total_pix) dst[c] = *reinterpret_cast<const uint4*>(s_out + EpiStage<COUT>::off(row, col));
     }
   }
 }

@@ -31,8 +31,8 @@ __device__ __forceinline__ long long tile_out_offset(const TileEpi& e, int col, 
 }
 
 // `trow`: TMEM address of this warp's lane quarter at the accumulator's first column; `t0/t1/t2`: this warp's
-// staging tiles (32 rows x (GW*2+16) bytes each; t2 only when an addend2 is present); `s_scale/s_shift`: already
-// offset to the tile's first GEMM column; `ecol`: the tile's first column as the epilogue `e` numbers it;
+// staging tiles (EpiStage<GW>::TILE_BYTES each; t2 only when an addend2 is present); `s_scale/s_shift`: already
+// offset to the tile's first GEMM column (both NULL = identity); `ecol`: the tile's first column as the epilogue `e` numbers it;
 // (n0, h0, w0): tile origin.  Arrives once (lane 0) on `acc_empty` (unless NULL) as soon as the accumulator has
 // been read.
 template <int BN, int GW>
@@ -75,7 +75,7 @@ __device__ __forceinline__ void tile_epilogue_staged(const TileEpi& e, const Epi
       const int c = lane + 32 * k;
       const int row = c / CPR;
       const int col = c - row * CPR;
-      sts128(tile_addr + row * EpiStage<GW>::PITCH + col * 16, v[k]);
+      sts128(tile_addr + EpiStage<GW>::off(row, col), v[k]);
     }
   };
   auto stage_flush_out = [&](uint32_t tile_addr, __nv_bfloat16* dst, int col0) {
@@ -87,42 +87,30 @@ __device__ __forceinline__ void tile_epilogue_staged(const TileEpi& e, const Epi
       int rn, roh, row_w;
       if (row_pixel(row, rn, roh, row_w))
         *reinterpret_cast<uint4*>(dst + tile_out_offset(e, col0 + col * 8, rn, roh, row_w)) =
-            lds128(tile_addr + row * EpiStage<GW>::PITCH + col * 16);
+            lds128(tile_addr + EpiStage<GW>::off(row, col));
     }
   };
 
 #pragma unroll 1
   for (int g0 = 0; g0 < BN; g0 += GW) {
     const int col0 = ecol + g0;  // first (epilogue-local) column of this group
+    uint4 va[4], vm[4], vb[4];   // GW == 32: this lane's addend / mask / addend2 values
     if (!f32_out) {
       if constexpr (GW == 32) {
-        // HBM-bound layers: put the loads of ALL input tensors in flight before the first store (3x the
-        // memory-level parallelism of one tensor at a time; 8 epilogue warps x 16 B x 4 chunks per tensor cannot
-        // cover the DRAM latency otherwise)
-        uint4 va[CPR], vm[CPR], vb[CPR];
+        // HBM-bound layers: every lane loads ITS OWN pixel's 32 channels of all input tensors straight into
+        // registers, all loads in flight before the first use.  No shared-memory staging for inputs: these kernels
+        // are bound by the shared-memory data pipe (tensor-core operand reads + staging), and the warp's four
+        // 16-byte loads per tensor still cover whole sectors, so L2 traffic is unchanged.
 #pragma unroll
-        for (int k = 0; k < CPR; ++k) {
-          const int c = lane + 32 * k;
-          const int row = c / CPR;
-          const int col = c - row * CPR;
-          int rn, roh, row_w;
-          va[k] = vm[k] = vb[k] = make_uint4(0u, 0u, 0u, 0u);
-          if (row_pixel(row, rn, roh, row_w)) {
-            const long long off = tile_out_offset(e, col0 + col * 8, rn, roh, row_w);
-            if (e.addend != nullptr) va[k] = *reinterpret_cast<const uint4*>(e.addend + off);  // may alias the output
-            if (e.mask_elu != nullptr) vm[k] = *reinterpret_cast<const uint4*>(e.mask_elu + off);
-            if (e.addend2 != nullptr) vb[k] = *reinterpret_cast<const uint4*>(e.addend2 + off);
+        for (int j = 0; j < 4; ++j) va[j] = vm[j] = vb[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const long long off = tile_out_offset(e, col0 + j * 8, n, oh, ow);
+            if (e.addend != nullptr) va[j] = *reinterpret_cast<const uint4*>(e.addend + off);  // may alias the output
+            if (e.mask_elu != nullptr) vm[j] = *reinterpret_cast<const uint4*>(e.mask_elu + off);
+            if (e.addend2 != nullptr) vb[j] = *reinterpret_cast<const uint4*>(e.addend2 + off);
           }
-        }
-#pragma unroll
-        for (int k = 0; k < CPR; ++k) {
-          const int c = lane + 32 * k;
-          const int row = c / CPR;
-          const int col = c - row * CPR;
-          const uint32_t so = row * EpiStage<GW>::PITCH + col * 16;
-          if (e.addend != nullptr) sts128(t0 + so, va[k]);
-          if (e.mask_elu != nullptr) sts128(t1 + so, vm[k]);
-          if (e.addend2 != nullptr) sts128(t2 + so, vb[k]);
         }
       } else {
         if (e.addend != nullptr) stage_fill(t0, e.addend, col0);
@@ -142,9 +130,13 @@ __device__ __forceinline__ void tile_epilogue_staged(const TileEpi& e, const Epi
         if (lane == 0 && acc_empty != nullptr) mbar_arrive(acc_empty);
       }
       float y[32];
+      if (s_scale != nullptr) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        y[i] = fmaf(__uint_as_float(acc[i]), s_scale[c0 + i], s_shift[c0 + i]);
+        for (int i = 0; i < 32; ++i) y[i] = fmaf(__uint_as_float(acc[i]), s_scale[c0 + i], s_shift[c0 + i]);
+      } else {  // identity affine (data gradients): no broadcast loads from shared memory
+#pragma unroll
+        for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(acc[i]);
+      }
       if (f32_out) {
         if (valid) {
           if (e.flags & VUB_CONV_F32_NCHW) {
@@ -160,23 +152,30 @@ __device__ __forceinline__ void tile_epilogue_staged(const TileEpi& e, const Epi
         }
         continue;
       }
-      const uint32_t my = lane * EpiStage<GW>::PITCH + (c0 - g0) * 2;
+      const int ch0 = (c0 - g0) >> 3;  // first 16-byte chunk of these 32 channels in this lane's staged row
       if (e.mask_elu != nullptr) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float ev[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          add_bf16x8(lds128(t1 + my + 16 * j), ev);
+          if constexpr (GW == 32) add_bf16x8(vm[j], ev);
+          else add_bf16x8(lds128(t1 + EpiStage<GW>::off(lane, ch0 + j)), ev);
 #pragma unroll
           for (int i = 0; i < 8; ++i) y[8 * j + i] *= ev[i] > 0.f ? 1.0f : ev[i] + 1.0f;
         }
       }
       if (e.addend != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) add_bf16x8(lds128(t0 + my + 16 * j), &y[8 * j]);
+        for (int j = 0; j < 4; ++j) {
+          if constexpr (GW == 32) add_bf16x8(va[j], &y[8 * j]);
+          else add_bf16x8(lds128(t0 + EpiStage<GW>::off(lane, ch0 + j)), &y[8 * j]);
+        }
       }
       if (e.addend2 != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) add_bf16x8(lds128(t2 + my + 16 * j), &y[8 * j]);
+        for (int j = 0; j < 4; ++j) {
+          if constexpr (GW == 32) add_bf16x8(vb[j], &y[8 * j]);
+          else add_bf16x8(lds128(t2 + EpiStage<GW>::off(lane, ch0 + j)), &y[8 * j]);
+        }
       }
       if (e.out_raw != nullptr) stage_put32<GW>(t0, lane, c0 - g0, y);
       if (e.out_elu != nullptr) {

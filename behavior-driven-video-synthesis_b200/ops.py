@@ -10,6 +10,7 @@ exists as a (raw, elu) pair because every consumer wants one of the two (SURVEY.
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -21,7 +22,7 @@ _LIB = torch.library.Library("vunet_b200", "DEF")
 _LIB.define(
     "conv_fwd(Tensor x0, Tensor? x1, Tensor w, Tensor scale, Tensor shift, Tensor? residual, "
     "int ksize, int stride, int cout_valid, bool want_raw, bool want_elu, bool d2s, int f32_mode, "
-    "int stages) -> Tensor[]"
+    "int stages, int elu_in=0) -> Tensor[]"
 )
 _LIB.define("wn_prep(Tensor table, int n_entries, int total_rows) -> ()")
 _LIB.define(
@@ -90,7 +91,7 @@ def _check_act(t: torch.Tensor, name: str) -> None:
 
 
 def _conv_fwd_cuda(x0, x1, w, scale, shift, residual, ksize, stride, cout_valid, want_raw, want_elu,
-                   d2s, f32_mode, stages) -> List[torch.Tensor]:
+                   d2s, f32_mode, stages, elu_in=0) -> List[torch.Tensor]:
     _check_act(x0, "conv_fwd x0")
     B, H, W, c_src = x0.shape
     nsrc = 1
@@ -141,13 +142,20 @@ def _conv_fwd_cuda(x0, x1, w, scale, shift, residual, ksize, stride, cout_valid,
         outs.append(out)
     d.nsrc, d.c_src, d.batch, d.hin, d.win = nsrc, c_src, B, H, W
     d.cout, d.cout_valid, d.ksize, d.stride = cout, cout_valid, ksize, stride
+    if elu_in & 1:
+        flags |= N.CONV_ELU_IN0
+    if elu_in & 2:
+        flags |= N.CONV_ELU_IN1
     d.flags, d.stages = flags, stages
     bn = min(cout, 256)
     bkc = 64 if c_src >= 64 else 32
     out_bytes = sum(o.numel() * o.element_size() for o in outs)
-    in_bytes = nsrc * x0.numel() * 2 + w.numel() * 2 + (residual.numel() * 2 if residual is not None else 0)
+    # distinct bytes: a residual that IS one of the sources (lean activations: raw x feeds both) is read once
+    res_distinct = residual is not None and residual.data_ptr() not in (x0.data_ptr(), -1 if x1 is None else x1.data_ptr())
+    in_bytes = nsrc * x0.numel() * 2 + w.numel() * 2 + (residual.numel() * 2 if res_distinct else 0)
     flops = 2.0 * B * Ho * Wo * cout_valid * w.shape[1]
-    tag = f"conv_fwd<{bn},{bkc}> {nsrc}x{c_src}->{cout} k{ksize} s{stride}{' d2s' if d2s else ''} @{H}x{W}"
+    tag = (f"conv_fwd<{bn},{bkc}> {nsrc}x{c_src}->{cout} k{ksize} s{stride}{' d2s' if d2s else ''}"
+           f"{' elu-in' if elu_in else ''} @{H}x{W}")
     N.check(_launch(tag, N.lib().vub_conv_fwd, C.byref(d), _stream(), flops=flops,
                     bytes_=float(in_bytes + out_bytes)), "vub_conv_fwd")
     return outs
@@ -446,16 +454,23 @@ _ops = torch.ops.vunet_b200
 # ------------------------------------------------------------------------------------------------
 def conv_fwd(x: Sequence[torch.Tensor], w, scale, shift, *, ksize: int, stride: int = 1,
              residual: Optional[torch.Tensor] = None, want_raw: bool = True, want_elu: bool = True,
-             d2s: bool = False, cout_valid: Optional[int] = None, stages: int = 0
+             d2s: bool = False, cout_valid: Optional[int] = None, stages: int = 0, elu_in: int = 0
              ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
-    """bf16 NHWC outputs: returns (raw or None, elu or None)."""
+    """bf16 NHWC outputs: returns (raw or None, elu or None).  ``elu_in``: bit s set = source s is a RAW
+    activation to which the kernel applies ELU while loading (only where :func:`elu_in_ok`)."""
     cv = w.shape[0] if cout_valid is None else cout_valid
     outs = _ops.conv_fwd(x[0], x[1] if len(x) > 1 else None, w, scale, shift, residual, ksize, stride, cv,
-                         want_raw, want_elu, d2s, F32_NONE, stages)
+                         want_raw, want_elu, d2s, F32_NONE, stages, elu_in)
     it = iter(outs)
     raw = next(it) if want_raw else None
     elu = next(it) if want_elu else None
     return raw, elu
+
+
+@functools.lru_cache(maxsize=None)
+def elu_in_ok(nsrc: int, c_src: int, cout: int, ksize: int, stride: int, h: int, w: int) -> bool:
+    """Host query (vub_conv_fwd_elu_in_ok): can a conv of this geometry apply ELU to its sources on load?"""
+    return bool(N.lib().vub_conv_fwd_elu_in_ok(nsrc, c_src, cout, ksize, stride, h, w))
 
 
 def conv_fwd_f32(x: Sequence[torch.Tensor], w, scale, shift, *, ksize: int, layout: str,

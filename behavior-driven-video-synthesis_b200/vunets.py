@@ -17,7 +17,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .modules import (Act, DepthToSpace, Downsample, NormConv2d, SpaceToDepth, Upsample, VunetRNB,
+from .modules import (lean_elu, Act, DepthToSpace, Downsample, NormConv2d, SpaceToDepth, Upsample, VunetRNB,
                       WeightBank, _solo_bank, to_act)
 
 
@@ -49,13 +49,17 @@ class EncUp(nn.Module):
 
     def _run(self, bank: WeightBank, x: torch.Tensor) -> List[Act]:
         hs: List[Act] = []
-        h = self.nin._run_stem(x, bank=bank)
+        # ELU copies are skipped where every reader (the next block's 3x3, a skip connection's 1x1) applies ELU on load
+        hh, ww = x.shape[2], x.shape[3]
+        h = self.nin._run_stem(x, bank=bank, want_elu=not lean_elu(bank, self.nin.out_channels, hh, ww))
         for i in range(self.n_scales):
             for n in range(self.n_rnb):
-                h = self.blocks[2 * i + n]._run(bank, h)
+                blk = self.blocks[2 * i + n]
+                h = blk._run(bank, h, want_elu=not lean_elu(bank, blk.conv.out_channels, hh, ww))
                 hs.append(h)
             if i + 1 < self.n_scales:
-                h = self.downs[i]._run(bank, h)
+                hh, ww = hh // 2, ww // 2
+                h = self.downs[i]._run(bank, h, want_elu=not lean_elu(bank, self.downs[i].down.out_channels, hh, ww))
         return hs
 
     def forward(self, x, **kwargs):
@@ -197,7 +201,8 @@ class DecDownAlter(nn.Module):
         h = self.nin._run(bank, [(gs[-1], "raw")])
         lat_count = 0
         for i in range(self.n_scales):
-            h = self.blocks[2 * i]._run(bank, h, gs.pop())
+            B_, hh, ww, cc = h.raw.shape
+            h = self.blocks[2 * i]._run(bank, h, gs.pop(), want_elu=not lean_elu(bank, cc, hh, ww, concat=True))
             if i < self.n_latent_scales:
                 if training:
                     z = zs.pop(0)
@@ -210,7 +215,8 @@ class DecDownAlter(nn.Module):
             last = i + 1 == self.n_scales
             h = self.blocks[2 * i + 1]._run(bank, h, gs.pop(), want_elu=False)
             if not last:
-                h = self.ups[i]._run(bank, h)
+                co = self.ups[i].up.out_channels // 4
+                h = self.ups[i]._run(bank, h, want_elu=not lean_elu(bank, co, 2 * hh, 2 * ww, concat=True))
         assert not gs
         if training:
             assert not zs

@@ -39,6 +39,8 @@ extern "C" {
 #define VUB_CONV_D2S 1u        /* store through DepthToSpace(2) (lib/modules.py:24-34, DCR order) */
 #define VUB_CONV_F32_NHWC 2u   /* out_f32 is [B,Ho,Wo,cout] fp32 */
 #define VUB_CONV_F32_NCHW 4u   /* out_f32 is [B,cout_valid,Ho,Wo] fp32 */
+#define VUB_CONV_ELU_IN0 8u    /* x[0] holds RAW activations: apply ELU while loading (VunetRNB's ELU(x), */
+#define VUB_CONV_ELU_IN1 16u   /* lib/modules.py:225-231); same for x[1].  Only where vub_conv_fwd_elu_in_ok() */
 
 /* ABI version of the loaded library (== VUB_ABI_VERSION it was built with). */
 int vub_abi_version(void);
@@ -78,6 +80,14 @@ typedef struct vub_conv_desc {
 } vub_conv_desc;
 
 int vub_conv_fwd(const vub_conv_desc* d, void* stream);
+
+/*
+ * Pure host query: 1 when vub_conv_fwd accepts VUB_CONV_ELU_IN0/1 for a conv of this geometry (it is served by
+ * the row-streaming kernel, which can apply ELU to its input rows in shared memory), else 0.  Lets the caller
+ * decide whether the producer of a tensor has to store an ELU copy at all.
+ */
+int vub_conv_fwd_elu_in_ok(int32_t nsrc, int32_t c_src, int32_t cout, int32_t ksize, int32_t stride, int32_t hin,
+                           int32_t win);
 
 /*
  * Weight-norm preparation for many layers in one launch: replaces the per-forward

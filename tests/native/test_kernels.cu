@@ -83,6 +83,8 @@ struct ConvCase {
   int stages;
 };
 
+static int g_elu_in = 0;  // VUB_CONV_ELU_IN source mask for the next run_conv_case calls
+
 static void run_conv_case(const ConvCase& cc) {
   const int taps = cc.ksize * cc.ksize;
   const int K = cc.nsrc * taps * cc.c_src;
@@ -93,6 +95,11 @@ static void run_conv_case(const ConvCase& cc) {
     x[s].resize(in_elems);
     for (auto& v : x[s]) v = bf16r(frand());
   }
+  // ELU-on-load: the device gets the raw values, the reference convolves bf16(ELU(raw))
+  std::vector<float> xraw[2] = {x[0], x[1]};
+  for (int s = 0; s < cc.nsrc; ++s)
+    if ((g_elu_in >> s) & 1)
+      for (auto& v : x[s]) v = bf16r(v > 0.f ? v : expm1f(v));
   std::vector<float> w((size_t)cc.cout * K, 0.f);
   for (int co = 0; co < cc.cout_valid; ++co)
     for (int k = 0; k < K; ++k) w[(size_t)co * K + k] = bf16r(frand() * 0.08f);
@@ -139,8 +146,8 @@ static void run_conv_case(const ConvCase& cc) {
   DevBuf<float> dscale(cc.cout), dshift(cc.cout);
   DevBuf<__nv_bfloat16> dres(cc.residual ? out_elems : 8), draw(out_elems), delu(out_elems);
   DevBuf<float> df32(out_elems);
-  dx0.up(to_bf16(x[0]));
-  if (cc.nsrc == 2) dx1.up(to_bf16(x[1]));
+  dx0.up(to_bf16(xraw[0]));
+  if (cc.nsrc == 2) dx1.up(to_bf16(xraw[1]));
   dw.up(to_bf16(w));
   dscale.up(scale);
   dshift.up(shift);
@@ -167,7 +174,8 @@ static void run_conv_case(const ConvCase& cc) {
   d.cout_valid = cc.cout_valid;
   d.ksize = cc.ksize;
   d.stride = cc.stride;
-  d.flags = (cc.d2s ? VUB_CONV_D2S : 0) | (cc.f32nhwc ? VUB_CONV_F32_NHWC : 0) | (cc.f32nchw ? VUB_CONV_F32_NCHW : 0);
+  d.flags = (cc.d2s ? VUB_CONV_D2S : 0) | (cc.f32nhwc ? VUB_CONV_F32_NHWC : 0) | (cc.f32nchw ? VUB_CONV_F32_NCHW : 0) |
+            ((g_elu_in & 1) ? VUB_CONV_ELU_IN0 : 0) | ((g_elu_in & 2) ? VUB_CONV_ELU_IN1 : 0);
   d.stages = cc.stages;
   int rc = vub_conv_fwd(&d, nullptr);
   if (rc != 0) {
@@ -406,6 +414,10 @@ static void perf_conv(const char* name, int B, int H, int W, int c_src, int nsrc
   d.residual = residual ? dres.p : nullptr; d.out_raw = draw.p; d.out_elu = dual ? delu.p : nullptr;
   d.nsrc = nsrc; d.c_src = c_src; d.batch = B; d.hin = H; d.win = W; d.cout = cout; d.cout_valid = cout;
   d.ksize = ksize; d.stride = stride; d.flags = d2s ? VUB_CONV_D2S : 0; d.stages = stages;
+  if (g_elu_in) {  // lean I/O: raw source(s) transformed on load; the residual IS the raw source (an L2 hit)
+    d.flags |= ((g_elu_in & 1) ? VUB_CONV_ELU_IN0 : 0) | ((g_elu_in & 2) ? VUB_CONV_ELU_IN1 : 0);
+    if (residual) d.residual = dx0.p;
+  }
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   for (int i = 0; i < 3; ++i) vub_conv_fwd(&d, nullptr);
@@ -419,7 +431,7 @@ static void perf_conv(const char* name, int B, int H, int W, int c_src, int nsrc
   CK(cudaEventElapsedTime(&ms, e0, e1));
   ms /= iters;
   const double flop = 2.0 * B * Ho * Wo * (double)cout * K;
-  const double bytes = 2.0 * (nsrc * (double)in_elems + out_elems * (1 + (dual ? 1 : 0) + (residual ? 1 : 0)) + (double)cout * K);
+  const double bytes = 2.0 * (nsrc * (double)in_elems + out_elems * (1 + (dual ? 1 : 0) + (residual && !g_elu_in ? 1 : 0)) + (double)cout * K);
   printf("[PERF] %-44s st=%d  %8.3f ms  %7.1f TFLOP/s  %7.1f GB/s(algorithmic)\n", name, stages, ms,
          flop / ms * 1e-9, bytes / ms * 1e-6);
 }
@@ -427,6 +439,7 @@ static void perf_conv(const char* name, int B, int H, int W, int c_src, int nsrc
 int main(int argc, char** argv) {
   const bool perf = argc > 1 && !strcmp(argv[1], "perf");
   if (!perf && !getenv("VUB_ENABLE_SLAB")) setenv("VUB_ENABLE_SLAB", "1", 1);  // correctness runs cover the opt-in slab kernel
+  if (getenv("VUB_TEST_ELU_IN")) g_elu_in = atoi(getenv("VUB_TEST_ELU_IN"));
   if (argc >= 14 && !strcmp(argv[1], "layer")) {
     // layer B H W c_src nsrc cout k stride res dual d2s stages  -> time one layer shape (for ncu captures)
     int a[12];
@@ -488,6 +501,27 @@ int main(int argc, char** argv) {
       {"rows 3x3 64->64 @128x128 B2 +res dual",            2, 128, 128, 64, 1, 64, 64, 3, 1, true, true, true, false, false, false, 0},
   };
   for (const ConvCase& c : row_cases) run_conv_case(c);
+  // ELU-on-load (raw sources transformed in shared memory by the row kernel's extra warps)
+  {
+    const ConvCase e1 = {"rows elu-in 3x3 32->32 @256x256 B1 +res raw", 1, 256, 256, 32, 1, 32, 32, 3, 1, true, true, false, false, false, false, 0};
+    const ConvCase e2 = {"rows elu-in 3x3 64->64 @128x128 B2 +res dual", 2, 128, 128, 64, 1, 64, 64, 3, 1, true, true, true, false, false, false, 0};
+    const ConvCase e3 = {"rows elu-in 1x1 32->32 @16x256 B2 elu only", 2, 16, 256, 32, 1, 32, 32, 1, 1, false, false, true, false, false, false, 0};
+    const ConvCase e4 = {"rows elu-in 1x1 64->64 @8x128 B3 elu only", 3, 8, 128, 64, 1, 64, 64, 1, 1, false, false, true, false, false, false, 0};
+    const ConvCase e5 = {"rows elu-in(src0) 3x3 [32|32]->32 @32x256 B2 cat +res raw", 2, 32, 256, 32, 2, 32, 32, 3, 1, true, true, false, false, false, false, 0};
+    g_elu_in = 1;
+    run_conv_case(e1);
+    run_conv_case(e2);
+    run_conv_case(e3);
+    run_conv_case(e4);
+    run_conv_case(e5);
+    setenv("VUB_ROWS_GRID", "5", 1);
+    run_conv_case(e2);
+    run_conv_case(e5);
+    unsetenv("VUB_ROWS_GRID");
+    g_elu_in = 3;
+    run_conv_case(e5);
+    g_elu_in = 0;
+  }
   setenv("VUB_ROWS_GRID", "7", 1);  // few persistent CTAs: long row ranges that cross image boundaries, ring wraps
   {
     const ConvCase c1 = {"rows persistent grid=7: 3x3 32->32 @64x128 B6 +res dual", 6, 64, 128, 32, 1, 32, 32, 3, 1, true, true, true, false, false, false, 0};
@@ -512,6 +546,14 @@ int main(int argc, char** argv) {
 
   if (perf) {
     const int B = 16;
+    for (int e : {0, 1}) {  // (raw, elu) pair I/O vs lean I/O: raw source with ELU on load, raw output only
+      g_elu_in = e;
+      perf_conv(e ? "lean 32->32 3x3 @256^2 +res raw, elu-in" : "pair 32->32 3x3 @256^2 +res dual", 64, 256, 256, 32, 1, 32, 3, 1, true, e == 0, false, 0);
+      perf_conv(e ? "lean 64->64 3x3 @128^2 +res raw, elu-in" : "pair 64->64 3x3 @128^2 +res dual", 64, 128, 128, 64, 1, 64, 3, 1, true, e == 0, false, 0);
+      perf_conv(e ? "lean [32|32]->32 3x3 @256^2 +res raw, elu-in" : "pair [32|32]->32 3x3 @256^2 +res dual", 64, 256, 256, 32, 2, 32, 3, 1, true, e == 0, false, 0);
+      perf_conv(e ? "lean 32->32 1x1 @256^2 elu-in" : "pair 32->32 1x1 @256^2", 64, 256, 256, 32, 1, 32, 1, 1, false, false, false, 0);
+    }
+    g_elu_in = 0;
     for (int st : {0, -1}) {  // 0: library default (row-streaming where applicable); -1: per-tap kernel
       perf_conv("32->32 3x3 @256^2 +res dual", B, 256, 256, 32, 1, 32, 3, 1, true, true, false, st);
       perf_conv("[32|32]->32 3x3 @256^2 +res dual", B, 256, 256, 32, 2, 32, 3, 1, true, true, false, st);

@@ -107,8 +107,9 @@ def test_fused_adam_state_dict_round_trip_and_lr_change():
         o.zero_grad()
         _loss(m, x, c, eps).backward()
         o.step()
+    # not bit-equal: the stem weight gradient accumulates with float atomics (order varies run to run)
     for (n, pa), pb in zip(a.named_parameters(), b.named_parameters()):
-        assert torch.equal(pa, pb[1]), n
+        torch.testing.assert_close(pa, pb[1], rtol=1e-5, atol=2e-7, msg=n)
 
 
 def test_fused_adam_invalidates_other_weight_caches():
