@@ -55,6 +55,11 @@ struct RowsKParams {
   // every input row in place in its ring slot before the tensor core reads it, so the producer of that tensor
   // never writes an ELU copy to HBM and the residual (the same raw tensor) is an L2 hit.
   int elu_in;
+  // A operand in tensor memory (3x3 only): every input row is copied shared -> tensor memory three times (one
+  // copy per column tap, tcgen05.cp from a shifted start row) when it arrives and the nine taps' MMAs read A from
+  // there, so the tensor core fetches an input row from shared memory 3 times instead of 9 — the shared-memory
+  // data pipe is what bounds this kernel (profiles/r01_ncu_rows_smem.txt).
+  int atm;
 };
 
 template <int BKC>
@@ -129,6 +134,12 @@ __global__ void __launch_bounds__(ELU_IN ? kRowsThreadsElu : kRowsThreads, 1)
   constexpr int slot_bytes = NSRC * SRC_BYTES;
   constexpr bool STAGED = BN >= 32 && BN <= 64;  // coalesced bf16 I/O through smem staging
   constexpr int SGW = STAGED ? BN : 32;
+  // A-in-TMEM mode: [2 accumulators][3 row slots][NSRC][kdim column shifts][BKC / 2 columns]
+  constexpr int COPY_COLS = BKC / 2;
+  constexpr int TSLOT_COLS = kdim * NSRC * COPY_COLS;
+  constexpr uint32_t ATM_NEED = 2 * BN + 3 * TSLOT_COLS;
+  constexpr uint32_t ATM_COLS = ATM_NEED <= 128 ? 128 : ATM_NEED <= 256 ? 256 : 512;
+  constexpr bool ATM_OK = NTAPS == 9 && ATM_NEED <= 512;
 
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
@@ -171,8 +182,10 @@ __global__ void __launch_bounds__(ELU_IN ? kRowsThreadsElu : kRowsThreads, 1)
     }
     fence_mbar_init();
   }
+  const bool atm = ATM_OK && p.atm != 0;
   if (warp == 2) {
-    tmem_alloc<TMEM_COLS>(&tmem_base_slot);
+    if (atm) tmem_alloc<ATM_COLS>(&tmem_base_slot);
+    else tmem_alloc<TMEM_COLS>(&tmem_base_slot);
     tmem_relinquish();
   }
   for (int i = threadIdx.x; i < BN; i += kRowsThreads) {
@@ -234,6 +247,71 @@ __global__ void __launch_bounds__(ELU_IN ? kRowsThreadsElu : kRowsThreads, 1)
     uint32_t go = 0;                     // running output-row counter
     uint64_t* const in_bar = ELU_IN ? slot_ready : slot_full;
     RowWalker rw;
+    if constexpr (ATM_OK) {
+      if (atm) {
+        // ---- A operand in tensor memory ----
+        const uint32_t a_tmem0 = tmem_base + 2 * BN;
+        int t_head = 0;   // TMEM row slot the next arriving input row is copied to
+        int t_first = 0;  // TMEM row slot of the current output row's first input row
+        for (rw.init(g_begin, g_end, p.ep.hout, p.batch); rw.valid(); rw.next_segment()) {
+          const int th = rw.seg_left;
+          for (int orow = 0; orow < th; ++orow, ++go) {
+            const uint32_t b = go & 1;
+            if (orow == 0) t_first = t_head;
+            const int n_new = (orow == 0) ? 1 + 2 * halo : 1;
+            for (int i = 0; i < n_new; ++i) {
+              mbar_wait(&in_bar[wait_slot], wait_ph);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t src_lo = ring_lo + wait_slot * slot_units;
+                const uint32_t dst = a_tmem0 + t_head * TSLOT_COLS;
+#pragma unroll
+                for (int s = 0; s < NSRC; ++s)
+#pragma unroll
+                  for (int q = 0; q < kdim; ++q)
+#pragma unroll
+                    for (int j = 0; j < BKC / 16; ++j)
+                      tmem_cp_128x256b(dst + (s * kdim + q) * COPY_COLS + 8 * j,
+                                       umma_desc_join(desc_hi, src_lo + s * (SRC_BYTES >> 4) + q * (ROWB >> 4) + 2 * j));
+                umma_commit(&slot_empty[wait_slot]);  // the shared-memory slot is free once the copies are done
+              }
+              __syncwarp();
+              if (++wait_slot == R) {
+                wait_slot = 0;
+                wait_ph ^= 1;
+              }
+              if (++t_head == 3) t_head = 0;
+            }
+            const uint32_t d_tmem = tmem_base + b * BN;
+            mbar_wait(&acc_empty[b], ((go >> 1) & 1) ^ 1);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int s = 0; s < NSRC; ++s) {
+#pragma unroll
+                for (int r = 0; r < kdim; ++r) {
+                  const int ts = t_first + r >= 3 ? t_first + r - 3 : t_first + r;
+                  const uint32_t a_row = a_tmem0 + ts * TSLOT_COLS + s * kdim * COPY_COLS;
+#pragma unroll
+                  for (int q = 0; q < kdim; ++q) {
+                    const int wt = p.flip ? (NTAPS - 1) - (r * kdim + q) : r * kdim + q;
+                    const uint32_t b_lo = w_lo + (s * NTAPS + wt) * (WT_BYTES >> 4);
+#pragma unroll
+                    for (int j = 0; j < BKC / 16; ++j)
+                      umma_bf16_ts(d_tmem, a_row + q * COPY_COLS + 8 * j, umma_desc_join(desc_hi, b_lo + 2 * j), idesc,
+                                   (s | r | q | j) != 0 ? 1u : 0u);
+                  }
+                }
+              }
+              umma_commit(&acc_full[b]);
+            }
+            __syncwarp();
+            if (++t_first == 3) t_first = 0;
+          }
+        }
+      }
+    }
+    if (!atm)
     for (rw.init(g_begin, g_end, p.ep.hout, p.batch); rw.valid(); rw.next_segment()) {
       const int th = rw.seg_left;
       for (int orow = 0; orow < th; ++orow, ++go) {
@@ -461,7 +539,10 @@ __global__ void __launch_bounds__(ELU_IN ? kRowsThreadsElu : kRowsThreads, 1)
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (warp == 2) {
+    if (atm) tmem_dealloc<ATM_COLS>(tmem_base);
+    else tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -549,6 +630,7 @@ static int rows_job_launch(const RowsJob& j, cudaStream_t stream) {
   kp.bwd[0] = j.bwd[0];
   kp.bwd[1] = j.bwd[1];
   kp.elu_in = j.elu_in & ((1 << j.nsrc) - 1);
+  kp.atm = (j.taps == 9 && 2 * j.bn + 3 * 3 * j.nsrc * (bkc / 2) <= 512 && env_int("VUB_ROWS_ATM", 1)) ? 1 : 0;
   const size_t wbytes = (size_t)j.nsrc * j.taps * j.bn * bkc * 2;
   const size_t slot = (size_t)j.nsrc * (bkc == 64 ? 136 * 128 : 144 * 64);
   const int ring_env = env_int("VUB_ROWS_RING", 0);

@@ -122,6 +122,25 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (128 rows x 16 bf16 = 8 packed 32-bit columns) sits in tensor
+// memory, put there by tmem_cp_128x256b.  Verified on hardware: tests/native/exp_atmem.cu.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Shared memory -> tensor memory: 128 rows x 256 bits (one K16 slice of a K-major bf16 operand tile, same
+// descriptor format and swizzle as an MMA operand, any start row) into 128 lanes x 8 columns at `taddr`.
+// Executes in issue order with the tcgen05.mma instructions of the same thread.
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;\n" ::"r"(taddr), "l"(sdesc) : "memory");
+}
 // Same, executed by ALL lanes of a converged warp with warp-uniform operands; only lanes with
 // `issue != 0` (exactly one lane) issue the instruction.  Keeping the C++ control flow convergent lets
 // ptxas keep the descriptors in uniform registers without the per-lane "waterfall" loop it emits when

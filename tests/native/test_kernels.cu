@@ -532,6 +532,9 @@ int main(int argc, char** argv) {
     run_conv_case(c3);
   }
   unsetenv("VUB_ROWS_GRID");
+  setenv("VUB_ROWS_ATM", "0", 1);  // A operand from shared memory (the default keeps it in tensor memory)
+  for (const ConvCase& c : row_cases) run_conv_case(c);
+  unsetenv("VUB_ROWS_ATM");
   setenv("VUB_DISABLE_ROWS", "1", 1);  // same wide shapes through the per-tap kernel
   run_conv_case(row_cases[0]);
   run_conv_case(row_cases[4]);
