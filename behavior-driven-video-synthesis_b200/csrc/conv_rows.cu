@@ -119,9 +119,16 @@ __device__ __forceinline__ void elu_bf16x8(uint4& v) {
   v = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
 }
 
-template <int BN, int BKC, int NTAPS, int NSRC, bool ELU_IN>
-__global__ void __launch_bounds__(ELU_IN ? kRowsThreadsElu : kRowsThreads, 1)
+// MODE: 0 = forward, 1 = forward with ELU-on-load (4 extra transform warps), 2 = data gradient.  Separate
+// instantiations keep each kernel's code small: with both epilogues in one kernel (~9000 SASS instructions) ncu
+// showed 16 % of the warp stalls waiting for instruction fetch.
+constexpr int kRowsFwd = 0, kRowsFwdElu = 1, kRowsBwd = 2;
+
+template <int BN, int BKC, int NTAPS, int NSRC, int MODE>
+__global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsThreads, 1)
     conv_rows_kernel(const __grid_constant__ RowsKParams p) {
+  constexpr bool ELU_IN = MODE == kRowsFwdElu;
+  constexpr bool BWD = MODE == kRowsBwd;
   using G = RowsGeom<BKC>;
   constexpr int ROWB = G::ROWB;
   constexpr int SRC_BYTES = G::SRC_BYTES;
@@ -438,35 +445,81 @@ __global__ void __launch_bounds__(ELU_IN ? kRowsThreadsElu : kRowsThreads, 1)
     RowWalker cur, ahead;  // `ahead` runs two rows in front (this warpgroup's next row)
     cur.init(g_begin, g_end, p.ep.hout, p.batch);
     if (g == 1 && cur.valid()) cur.next_row();
-    if constexpr (BN == 32 || BN == 64) {
-      if (p.n_halves > 0) {
-        // ---- data-gradient mode: the shared mode-driven epilogue, one 128-pixel row = one tile ----
-        const EpiGeom gm{kRowsW, 1, 7, 0, p.batch};
-        const uint32_t b0 = smem_u32(staging) + (warp - 2) * p.stage_tiles * EpiStage<32>::TILE_BYTES;
-        const uint32_t b1 = b0 + EpiStage<32>::TILE_BYTES, b2 = b1 + EpiStage<32>::TILE_BYTES;
-        uint32_t cntb = 0;
-        const float* sc = p.ep.scale != nullptr ? s_scale : nullptr;  // data gradients: identity, skip the loads
-        const float* sh = p.ep.scale != nullptr ? s_shift : nullptr;
-        while (cur.valid()) {
-          mbar_wait(&acc_full[g], cntb & 1);
-          tc_fence_after();
-          if (p.n_halves == 1) {
-            tile_epilogue_staged<BN, 32>(p.bwd[0], gm, sc, sh, trow, b0, b1, b2, lane, q, 0, cur.n, cur.h,
-                                         cur.w0, &acc_empty[g]);
-          } else {
-            if constexpr (BN == 64) {
-              tile_epilogue_staged<32, 32>(p.bwd[0], gm, sc, sh, trow, b0, b1, b2, lane, q, 0, cur.n, cur.h,
-                                           cur.w0, nullptr);
-              tile_epilogue_staged<32, 32>(p.bwd[1], gm, sc ? sc + 32 : nullptr, sh ? sh + 32 : nullptr, trow + 32, b0, b1, b2, lane, q, 0,
-                                           cur.n, cur.h, cur.w0, &acc_empty[g]);
+    if constexpr (BWD && (BN == 32 || BN == 64)) {
+      // ---- data-gradient mode: dx = ELU'(mask) * acc + addend + addend2 per source (half) ----
+      // The warp's 32 pixels are ONE contiguous block of every tensor, so all addresses are `block + lane * C`.
+      // The epilogue inputs do not depend on the accumulator: the first 32-channel group's loads are issued
+      // BEFORE waiting for the MMA, the next group's as soon as the registers are free again.
+      const uint32_t st = smem_u32(staging) + (warp - 2) * p.stage_tiles * EpiStage<32>::TILE_BYTES;
+      const bool two = p.n_halves == 2;
+      constexpr int NG = BN / 32;
+      uint32_t cntb = 0;
+      uint4 va[4], vm[4], vb[4];
+      while (cur.valid()) {
+        const long long pix = ((long long)cur.n * p.ep.hout + cur.h) * p.ep.wout + cur.w0 + q * 32;  // warp's first pixel
+        auto load_group = [&](int gi) {
+          const TileEpi& e = p.bwd[two ? gi : 0];
+          const long long off = (pix + lane) * e.out_c + (two ? 0 : gi * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            va[j] = vm[j] = vb[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (e.addend != nullptr) va[j] = *reinterpret_cast<const uint4*>(e.addend + off + 8 * j);  // may alias dx
+            if (e.mask_elu != nullptr) vm[j] = __ldg(reinterpret_cast<const uint4*>(e.mask_elu + off + 8 * j));
+            if (e.addend2 != nullptr) vb[j] = *reinterpret_cast<const uint4*>(e.addend2 + off + 8 * j);
+          }
+        };
+        load_group(0);
+        mbar_wait(&acc_full[g], cntb & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int gi = 0; gi < NG; ++gi) {
+          const TileEpi& e = p.bwd[two ? gi : 0];
+          uint32_t acc[32];
+          tmem_ld32(trow + gi * 32, acc);
+          tmem_ld_wait();
+          if (gi == NG - 1) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[g]);
+          }
+          float y[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(acc[i]);
+          if (e.mask_elu != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float ev[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              add_bf16x8(vm[j], ev);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) y[8 * j + i] *= ev[i] > 0.f ? 1.0f : ev[i] + 1.0f;
             }
           }
-          ++cntb;
-          cur.next_row();
-          if (cur.valid()) cur.next_row();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            add_bf16x8(va[j], &y[8 * j]);
+            add_bf16x8(vb[j], &y[8 * j]);
+          }
+          if (gi + 1 < NG) load_group(gi + 1);
+          if (two || NG == 1) {  // a 32-channel half (or the whole 32-channel tensor): stage, flush
+            stage_put32<32>(st, lane, 0, y);
+            __syncwarp();
+            stage_flush_linear<32>(st, e.out_raw + pix * 32, lane);
+            __syncwarp();
+          } else {               // one 64-channel tensor in two groups
+            stage_put32<64>(st, lane, gi * 32, y);
+            if (gi == NG - 1) {
+              __syncwarp();
+              stage_flush_linear<64>(st, e.out_raw + pix * 64, lane);
+              __syncwarp();
+            }
+          }
         }
+        ++cntb;
+        cur.next_row();
+        if (cur.valid()) cur.next_row();
       }
     }
+    if constexpr (!BWD) {
     ahead = cur;
     if (STAGED && has_res && bf16_out && cur.valid()) prefetch_res(cur);
     uint32_t cnt = 0;  // rows this warpgroup has processed (its TMEM buffer's phase counter)
@@ -535,6 +588,7 @@ __global__ void __launch_bounds__(ELU_IN ? kRowsThreadsElu : kRowsThreads, 1)
       ++cnt;
       cur = ahead;
     }
+    }  // !BWD
   }
 
   tc_fence_before();
@@ -546,29 +600,37 @@ __global__ void __launch_bounds__(ELU_IN ? kRowsThreadsElu : kRowsThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int BN, int BKC, int NTAPS, int NSRC, bool ELU_IN = false>
+template <int BN, int BKC, int NTAPS, int NSRC, int MODE = kRowsFwd>
 static int launch_rows_t(const RowsKParams& kp, int grid, size_t smem, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_rows_kernel<BN, BKC, NTAPS, NSRC, ELU_IN>,
+    attr_err = cudaFuncSetAttribute(conv_rows_kernel<BN, BKC, NTAPS, NSRC, MODE>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
   });
   if (attr_err != cudaSuccess)
     return fail(static_cast<int>(attr_err), "cudaFuncSetAttribute(conv_rows<%d,%d>): %s", BN, BKC,
                 cudaGetErrorString(attr_err));
-  conv_rows_kernel<BN, BKC, NTAPS, NSRC, ELU_IN><<<grid, ELU_IN ? kRowsThreadsElu : kRowsThreads, smem, stream>>>(kp);
+  conv_rows_kernel<BN, BKC, NTAPS, NSRC, MODE><<<grid, MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsThreads, smem, stream>>>(kp);
   return check_launch("conv_rows");
 }
 
 template <int BN, int BKC>
 static int launch_rows(const RowsKParams& kp, int grid, size_t smem, cudaStream_t stream) {
+  if (kp.n_halves > 0) {  // data gradient: one source (dy), 32 or 64 accumulator columns
+    if constexpr (BN == 32 || BN == 64) {
+      if (kp.nsrc == 1 && kp.ntaps == 9) return launch_rows_t<BN, BKC, 9, 1, kRowsBwd>(kp, grid, smem, stream);
+      if (kp.nsrc == 1 && kp.ntaps == 1) return launch_rows_t<BN, BKC, 1, 1, kRowsBwd>(kp, grid, smem, stream);
+    }
+    return fail(VUB_E_SHAPE, "conv_rows: no data-gradient variant for BN %d BKC %d taps %d nsrc %d", BN, BKC, kp.ntaps,
+                kp.nsrc);
+  }
   if (kp.elu_in) {  // ELU-on-load: the square layers of the residual blocks and their 1x1 skip convs
     if constexpr (BN == BKC && (BN == 32 || BN == 64)) {
-      if (kp.ntaps == 9 && kp.nsrc == 1) return launch_rows_t<BN, BKC, 9, 1, true>(kp, grid, smem, stream);
-      if (kp.ntaps == 1 && kp.nsrc == 1) return launch_rows_t<BN, BKC, 1, 1, true>(kp, grid, smem, stream);
+      if (kp.ntaps == 9 && kp.nsrc == 1) return launch_rows_t<BN, BKC, 9, 1, kRowsFwdElu>(kp, grid, smem, stream);
+      if (kp.ntaps == 1 && kp.nsrc == 1) return launch_rows_t<BN, BKC, 1, 1, kRowsFwdElu>(kp, grid, smem, stream);
       if constexpr (BN == 32) {
-        if (kp.ntaps == 9 && kp.nsrc == 2) return launch_rows_t<BN, BKC, 9, 2, true>(kp, grid, smem, stream);
+        if (kp.ntaps == 9 && kp.nsrc == 2) return launch_rows_t<BN, BKC, 9, 2, kRowsFwdElu>(kp, grid, smem, stream);
       }
     }
     return fail(VUB_E_FLAGS, "conv_rows: no ELU-on-load variant for BN %d BKC %d taps %d nsrc %d", BN, BKC, kp.ntaps,

@@ -422,6 +422,9 @@ def run_ours(args):
         if tr:  # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture
             roofline["traffic"] = tr["dram_read"] + tr["dram_write"]
             roofline["traffic_source"] = "profiles/ncu_traffic.json (ncu --set full, per launch, same workload)"
+    if "@256x256" in top["kernel"] or "@128x128" in top["kernel"]:
+        roofline["note"] = ("row-streaming kernel: per ncu it is limited by the SM's shared-memory data pipe (tensor-core "
+                            "operand reads + epilogue staging), not by HBM; profiles/r01_ncu_rows_smem.txt")
     roofline["algorithmic_bytes_per_launch"] = prof[top["kernel"]]["bytes"] / top["launches"]
     roofline["algorithmic_flops_per_launch"] = prof[top["kernel"]]["flops"] / top["launches"]
     roofline.update({"kernel": top["kernel"], "launches_per_step": top["launches"], "share_of_step": top["share"],
