@@ -418,6 +418,11 @@ static int wgrad_plan_kp(const vub_wgrad_desc* d, WgKParams& kp, int* best_split
     if (n_sm <= 0) n_sm = 148;
   }
   int n_split = n_sm / (kp.n_groups * kp.n_mtiles);
+  // Every split writes (and vub_wn_bwd reads back) a full [cout_k x K] fp32 partial: on the small maps the
+  // partials of 49 splits were several times the layer's own input bytes.  Keep at least kMinSteps pixel
+  // k-steps per split so that a CTA's MMA time is comparable to the time it needs to store its partial.
+  static const int min_steps = getenv("VUB_WGRAD_MIN_STEPS") ? atoi(getenv("VUB_WGRAD_MIN_STEPS")) : 4;
+  if (min_steps > 1 && n_split > kp.total_tiles / min_steps) n_split = kp.total_tiles / min_steps;
   if (n_split < 1) n_split = 1;
   if (n_split > kp.total_tiles) n_split = kp.total_tiles;
   *best_split = n_split;
