@@ -213,12 +213,10 @@ __global__ void __launch_bounds__(kSlabThreads, 1) conv_slab_kernel(const __grid
       const TileEpi& e = p.ep[ei];
       const int ecol = (n_tile - (ei ? p.n_split : 0)) * kSlabBN;
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * (2 * kSlabBN) + g * kSlabBN;
-      mbar_wait(&acc_full[buf], (li >> 1) & 1);
-      tc_fence_after();
       const bool affine = p.ep[0].scale != nullptr;  // data gradients run with the identity
       tile_epilogue_staged<kSlabBN, kSlabGW>(e, gm, affine ? s_scale + n_tile * kSlabBN : nullptr,
                                              affine ? s_shift + n_tile * kSlabBN : nullptr, trow, t0, t1,
-                                             t2, lane, q, ecol, n, h0 + g * (p.R / 2), 0, &acc_empty[buf]);
+                                             t2, lane, q, ecol, n, h0 + g * (p.R / 2), 0, &acc_empty[buf], &acc_full[buf], (li >> 1) & 1);
     }
   }
 

@@ -292,7 +292,7 @@ int conv_tiles_launch(const TileJob& job, cudaStream_t stream) {
   kp.total_tiles = kp.tiles_w * kp.tiles_h * tiles_n * kp.n_ntiles;
 
   const int gw = bn >= 64 ? 64 : 32;
-  const size_t staging = bn >= 32 ? (size_t)8 * kp.stage_tiles * 32 * (gw * 2 + 16) : 0;
+  const size_t staging = bn >= 32 ? (size_t)8 * kp.stage_tiles * 32 * (gw * 2) : 0;
   const size_t stage_bytes = (size_t)(128 + bn) * bkc * 2;
   int stages = static_cast<int>((212 * 1024 - staging) / stage_bytes);
   if (stages > kTilesMaxStages) stages = kTilesMaxStages;

@@ -187,51 +187,55 @@ __global__ void __launch_bounds__(kStemThreads)
     s_shift[co] = fmaf(gamma[co], bias[co], beta[co]);
   }
   __syncthreads();
-  const long long pix_raw = (long long)blockIdx.x * kStemThreads + threadIdx.x;
-  const bool valid = pix_raw < total_pix;
-  const long long pix = valid ? pix_raw : total_pix - 1;  // tail threads compute a duplicate, store nothing
-  const long long n = pix / hw;
-  const long long sp = pix - n * hw;
-  const float* xp = x + n * cx * hw + sp;
-  float acc[COUT];
-#pragma unroll
-  for (int co = 0; co < COUT; ++co) acc[co] = s_shift[co];
-  for (int ci = 0; ci < cx; ++ci) {
-    const float xv = __ldg(xp + (long long)ci * hw);
-#pragma unroll
-    for (int co = 0; co < COUT; ++co) acc[co] = fmaf(xv, s_w[ci * COUT + co], acc[co]);
-  }
-  // Coalesced stores: a thread owns one pixel (COUT*2 contiguous bytes), so direct 16-byte stores from the
-  // 32 lanes of a warp hit 32 different 64/128-byte segments per instruction.  The block's 128 pixels are one
-  // contiguous span of the NHWC output: stage them in shared memory (swizzled, see EpiStage) and write the span linearly.
+  // Persistent: the weight-norm prologue above costs two dependent global round trips, so a block handles many
+  // 128-pixel chunks (grid-stride) instead of one.
   constexpr int CPR = COUT / 8;  // 16-byte chunks per pixel
   __shared__ __align__(128) uint8_t s_out[kStemThreads * COUT * 2];
-  const long long pix0 = (long long)blockIdx.x * kStemThreads;
+  for (long long pix0 = (long long)blockIdx.x * kStemThreads; pix0 < total_pix; pix0 += (long long)gridDim.x * kStemThreads) {
+    const long long pix_raw = pix0 + threadIdx.x;
+    const bool valid = pix_raw < total_pix;
+    const long long pix = valid ? pix_raw : total_pix - 1;  // tail threads compute a duplicate, store nothing
+    const long long n = pix / hw;
+    const long long sp = pix - n * hw;
+    const float* xp = x + n * cx * hw + sp;
+    float acc[COUT];
 #pragma unroll
-  for (int which = 0; which < 2; ++which) {
-    __nv_bfloat16* out = which == 0 ? out_raw : out_elu;
-    if (out == nullptr) continue;
-    __syncthreads();  // previous pass has been read back
-    if (valid) {
+    for (int co = 0; co < COUT; ++co) acc[co] = s_shift[co];
+    for (int ci = 0; ci < cx; ++ci) {
+      const float xv = __ldg(xp + (long long)ci * hw);
 #pragma unroll
-      for (int j = 0; j < CPR; ++j) {
-        float t[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) t[i] = which == 0 ? acc[8 * j + i] : elu1(acc[8 * j + i]);
-        __nv_bfloat162 a = __floats2bfloat162_rn(t[0], t[1]), b2 = __floats2bfloat162_rn(t[2], t[3]);
-        __nv_bfloat162 c2 = __floats2bfloat162_rn(t[4], t[5]), d2 = __floats2bfloat162_rn(t[6], t[7]);
-        *reinterpret_cast<uint4*>(s_out + EpiStage<COUT>::off(threadIdx.x, j)) =
-            make_uint4(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b2),
-                       *reinterpret_cast<uint32_t*>(&c2), *reinterpret_cast<uint32_t*>(&d2));
-      }
+      for (int co = 0; co < COUT; ++co) acc[co] = fmaf(xv, s_w[ci * COUT + co], acc[co]);
     }
-    __syncthreads();
-    uint4* dst = reinterpret_cast<uint4*>(out + pix0 * COUT);
+    // Coalesced stores: a thread owns one pixel (COUT*2 contiguous bytes), so direct 16-byte stores from the
+    // 32 lanes of a warp hit 32 different 64/128-byte segments per instruction.  The block's 128 pixels are one
+    // contiguous span of the NHWC output: stage them in shared memory (swizzled, see EpiStage) and write the span
+    // linearly.
 #pragma unroll
-    for (int k = 0; k < CPR; ++k) {
-      const int c = threadIdx.x + kStemThreads * k;  // chunk index inside the block's span
-      const int row = c / CPR, col = c - row * CPR;
-      if (pix0 + row < total_pix) dst[c] = *reinterpret_cast<const uint4*>(s_out + EpiStage<COUT>::off(row, col));
+    for (int which = 0; which < 2; ++which) {
+      __nv_bfloat16* out = which == 0 ? out_raw : out_elu;
+      if (out == nullptr) continue;
+      __syncthreads();  // previous pass has been read back
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < CPR; ++j) {
+          float t[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[i] = which == 0 ? acc[8 * j + i] : elu1(acc[8 * j + i]);
+          __nv_bfloat162 a = __floats2bfloat162_rn(t[0], t[1]), b2 = __floats2bfloat162_rn(t[2], t[3]);
+          __nv_bfloat162 c2 = __floats2bfloat162_rn(t[4], t[5]), d2 = __floats2bfloat162_rn(t[6], t[7]);
+          *reinterpret_cast<uint4*>(s_out + EpiStage<COUT>::off(threadIdx.x, j)) =
+              make_uint4(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b2),
+                         *reinterpret_cast<uint32_t*>(&c2), *reinterpret_cast<uint32_t*>(&d2));
+        }
+      }
+      __syncthreads();
+      uint4* dst = reinterpret_cast<uint4*>(out + pix0 * COUT);
+#pragma unroll
+      for (int k = 0; k < CPR; ++k) {
+        const int c = threadIdx.x + kStemThreads * k;  // chunk index inside the block's span
+        const int row = c / CPR, col = c - row * CPR;
+        if (pix0 + row < total_pix) dst[c] = *reinterpret_cast<const uint4*>(s_out + EpiStage<COUT>::off(row, col));
+      }
     }
   }
 }
@@ -403,7 +407,16 @@ extern "C" int vub_stem_fwd(const float* x_nchw, const float* v, const float* g,
   if ((out_raw && !aligned16(out_raw)) || (out_elu && !aligned16(out_elu)))
     return fail(VUB_E_ALIGN, "stem_fwd: outputs must be 16B aligned");
   const long long hw = (long long)h * w, total = hw * batch;
-  const unsigned grid = static_cast<unsigned>((total + kStemThreads - 1) / kStemThreads);
+  const long long chunks = (total + kStemThreads - 1) / kStemThreads;
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  const long long max_grid = (long long)n_sm * 8;  // persistent blocks, each looping over 128-pixel chunks
+  const unsigned grid = static_cast<unsigned>(chunks < max_grid ? chunks : max_grid);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (cout == 32)
     stem_kernel<32><<<grid, kStemThreads, 0, s>>>(x_nchw, v, g, gamma, beta, bias, cx, hw, total,

@@ -34,12 +34,14 @@ __device__ __forceinline__ long long tile_out_offset(const TileEpi& e, int col, 
 // staging tiles (EpiStage<GW>::TILE_BYTES each; t2 only when an addend2 is present); `s_scale/s_shift`: already
 // offset to the tile's first GEMM column (both NULL = identity); `ecol`: the tile's first column as the epilogue `e` numbers it;
 // (n0, h0, w0): tile origin.  Arrives once (lane 0) on `acc_empty` (unless NULL) as soon as the accumulator has
-// been read.
+// been read.  With `acc_full` given, the function itself waits for the accumulator — AFTER it has put the first
+// channel group's input loads (addend / mask / addend2) in flight, which do not depend on it.
 template <int BN, int GW>
 __device__ __forceinline__ void tile_epilogue_staged(const TileEpi& e, const EpiGeom gm, const float* s_scale,
                                                      const float* s_shift, uint32_t trow, uint32_t t0, uint32_t t1,
                                                      uint32_t t2, int lane, int q, int ecol, int n0, int h0, int w0,
-                                                     uint64_t* acc_empty) {
+                                                     uint64_t* acc_empty, uint64_t* acc_full = nullptr,
+                                                     uint32_t acc_parity = 0) {
   constexpr int CPR = GW / 8;
   const int m = q * 32 + lane;
   const int n = n0 + (m >> (gm.tw_log2 + gm.th_log2));
@@ -118,6 +120,10 @@ __device__ __forceinline__ void tile_epilogue_staged(const TileEpi& e, const Epi
         if (e.addend2 != nullptr) stage_fill(t2, e.addend2, col0);
       }
       __syncwarp();
+    }
+    if (g0 == 0 && acc_full != nullptr) {
+      mbar_wait(acc_full, acc_parity);
+      tc_fence_after();
     }
 #pragma unroll 1
     for (int c0 = g0; c0 < g0 + GW; c0 += 32) {
