@@ -14,6 +14,7 @@
 //
 // Replaces autograd's convolution_backward (input gradient) of lib/modules.py:143 plus the ELU / cat /
 // add backward kernels of lib/modules.py:225-233.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.h"
@@ -61,6 +62,15 @@ extern "C" int vub_conv_dgrad(const vub_dgrad_desc* d, void* stream_v) {
   job.ktot = (long long)taps * cout_k;
   job.n_total = d->nsrc * C;
   job.bn = C;
+  {
+    // small maps: a handful of 128-pixel tiles cannot fill 148 SMs and each CTA would walk all k-steps behind a
+    // 2-3 stage pipeline.  Split N (more CTAs, 20 KB stages -> 8-deep pipeline), as the forward per-tap kernel does.
+    const long long pix_tiles = ((long long)d->batch * (d->hin / d->stride) * (d->win / d->stride) + 127) / 128;
+    int bn = C;
+    while (bn > 32 && pix_tiles * (d->nsrc * C / bn) < 96) bn >>= 1;
+    static const bool no_split = getenv("VUB_DGRAD_NSPLIT") && getenv("VUB_DGRAD_NSPLIT")[0] == '0';
+    if (!no_split) job.bn = bn;
+  }
   job.n_split = d->nsrc == 2 ? C : 0;
   job.batch = d->batch;
   for (int s = 0; s < d->nsrc; ++s) {

@@ -242,7 +242,7 @@ def run_train_section(args, device, world, rank, barrier, peaks):
                      "tflops": round(a["flops"] / (a["ms"] * 1e-3) / 1e12, 1) if a["ms"] > 0 else 0.0,
                      "gbs": round(a["bytes"] / (a["ms"] * 1e-3) / 1e9, 1) if a["ms"] > 0 else 0.0}
                     for f, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])]
-        for name, r in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:16]:
+        for name, r in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:64]:
             tk.append({"kernel": name, "launches": r["launches"], "ms": round(r["ms"], 4), "share": round(r["ms"] / tot, 4),
                        "tflops": round(r["flops"] / (r["ms"] * 1e-3) / 1e12, 1) if r["ms"] > 0 else 0.0,
                        "gbs": round(r["bytes"] / (r["ms"] * 1e-3) / 1e9, 1) if r["ms"] > 0 else 0.0})
