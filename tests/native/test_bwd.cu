@@ -570,6 +570,15 @@ int main(int argc, char** argv) {
       {"rows 3x3 32->3(32) out_conv @32x128 B2",              2, 32, 128, 32, 1, 32, 3, 1, false, false, false, false, false},
   };
   for (const BwdCase& c : rows_cases) run_dgrad(c);
+  // weight gradient of the wide 32-channel layers: pixel splits crossing images / column strips
+  {
+    const BwdCase w1 = {"wgrad wide 3x3 32->32 @64x256 B3", 3, 64, 256, 32, 1, 32, 3, 1, false, false, false, false, false};
+    const BwdCase w2 = {"wgrad wide 3x3 [32|32]->32 @32x128 B5", 5, 32, 128, 32, 2, 32, 3, 1, false, false, false, false, false};
+    const BwdCase w3 = {"wgrad wide 3x3 32->3(32) @2x128 B7 (2-row images)", 7, 2, 128, 32, 1, 32, 3, 1, false, false, false, false, false};
+    run_wgrad(w1);
+    run_wgrad(w2);
+    run_wgrad(w3);
+  }
   setenv("VUB_ROWS_GRID", "5", 1);  // few persistent CTAs: row ranges cross image boundaries, ring wraps
   {
     const BwdCase c1 = {"rows grid=5: 3x3 [32|32]->32 @32x128 B5 cat mask+add2", 5, 32, 128, 32, 2, 32, 3, 1, false, true, false, true, false};
