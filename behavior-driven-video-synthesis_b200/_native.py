@@ -46,7 +46,7 @@ EXPORTED_SYMBOLS = (
     "vub_stem_bwd",
     "vub_latent_bwd",
 )
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class ConvDesc(C.Structure):
@@ -72,6 +72,7 @@ class ConvDesc(C.Structure):
         ("stride", C.c_int32),
         ("flags", C.c_uint32),
         ("stages", C.c_int32),
+        ("w_tiled", C.c_void_p),
     ]
 
 
@@ -97,6 +98,10 @@ class WnEntry(C.Structure):
         ("wd_cout", C.c_int32),
         ("wd_col0", C.c_int32),
         ("w32", C.c_void_p),
+        ("w_tiled", C.c_void_p),
+        ("wd_tiled", C.c_void_p),
+        ("tiled_rows", C.c_int32),
+        ("pad_", C.c_int32),
     ]
 
 
@@ -143,6 +148,8 @@ class DgradDesc(C.Structure):
         ("ksize", C.c_int32),
         ("stride", C.c_int32),
         ("flags", C.c_uint32),
+        ("pad_", C.c_int32),
+        ("wd_tiled", C.c_void_p),
     ]
 
 

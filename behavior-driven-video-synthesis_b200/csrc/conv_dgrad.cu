@@ -59,6 +59,8 @@ extern "C" int vub_conv_dgrad(const vub_dgrad_desc* d, void* stream_v) {
   memset(&job, 0, sizeof(job));
   job.bkc = bkc;
   job.w = d->wd;
+  job.w_tiled = d->wd_tiled;  // rows = input channels of all sources, K = (tap, output channel)
+  job.w_rows = d->nsrc * C;
   job.ktot = (long long)taps * cout_k;
   job.n_total = d->nsrc * C;
   job.bn = C;
@@ -103,6 +105,8 @@ extern "C" int vub_conv_dgrad(const vub_dgrad_desc* d, void* stream_v) {
     sj.h = d->hin;
     sj.w = d->win;
     sj.w_packed = d->wd;
+    sj.w_tiled = d->wd_tiled;
+    sj.w_rows = d->nsrc * C;
     sj.ktot = (long long)taps * cout_k;
     sj.n_total = d->nsrc * C;
     sj.flip = 1;

@@ -44,6 +44,8 @@ struct ConvKParams {
   int tw, th, tn, tw_log2, th_log2;
   int tiles_w, tiles_h;
   int stages;
+  const uint8_t* w_tiled;  // tile-major pre-swizzled weights [K/64][w_rows][128 B], or nullptr (BKC == 64 only)
+  int w_rows;
 };
 
 // Epilogue for CH (16 or 32) consecutive channels of one pixel held in registers.
@@ -149,7 +151,10 @@ __global__ void __launch_bounds__(kConvThreads)
             mbar_expect_tx(&full_bar[st], STAGE_BYTES);
             uint8_t* a = smem + st * STAGE_BYTES;
             tma_load_4d(a, &p.tmA[mi], &full_bar[st], cb * BKC, w0 + dw, h0 + dh, n0);
-            tma_load_2d(a + A_BYTES, &p.tmB, &full_bar[st], ks * BKC, n_tile * BN);
+            if (BKC == 64 && p.w_tiled != nullptr)  // one 1-D bulk copy instead of a BN-row tensor box
+              bulk_load_1d(a + A_BYTES, p.w_tiled + ((size_t)ks * p.w_rows + n_tile * BN) * 128, B_BYTES, &full_bar[st]);
+            else
+              tma_load_2d(a + A_BYTES, &p.tmB, &full_bar[st], ks * BKC, n_tile * BN);
           }
           __syncwarp();
           if (++st == S) {
@@ -373,6 +378,8 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
     job.h = d->hin;
     job.w = d->win;
     job.w_packed = d->w;
+    job.w_tiled = d->w_tiled;
+    job.w_rows = cout;
     job.ktot = (long long)d->nsrc * 9 * d->c_src;
     job.n_total = cout;
     TileEpi& e = job.epi[0];
@@ -400,7 +407,9 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
   const char* force = getenv("VUB_FWD_TILES");
   const long long px_tiles = ((long long)d->batch * hout * wout + kTileM - 1) / kTileM;
   const bool small_grid = px_tiles * (cout > 256 ? cout / 256 : 1) < 148;
-  const bool want_tiles = force ? force[0] == '1' : ((d->stride == 2 || cout >= 256) && !small_grid);
+  // With the contiguous-tile epilogue (tile_epilogue_contig) the persistent kernel also wins the stride-1 N <= 128
+  // layers (128->128 @64^2, B=64: 0.091 ms vs 0.136 ms per-tap), so everything with a full grid goes there.
+  const bool want_tiles = force ? force[0] == '1' : !small_grid;
   if (want_tiles && d->stages >= 0) {
     // persistent tile kernel, k-step table = (source, tap, channel block)
     TileJob job;
@@ -411,6 +420,8 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
     const int taps = d->ksize * d->ksize;
     job.bkc = bkc_;
     job.w = d->w;
+    job.w_tiled = bkc_ == 64 ? d->w_tiled : nullptr;
+    job.w_rows = cout;
     job.ktot = (long long)d->nsrc * taps * C;
     job.n_total = cout;
     job.batch = d->batch;
@@ -503,6 +514,8 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
   kp.th_log2 = ilog2(kp.th);
   kp.tiles_w = wout / kp.tw;
   kp.tiles_h = hout / kp.th;
+  kp.w_tiled = bkc == 64 ? static_cast<const uint8_t*>(d->w_tiled) : nullptr;
+  kp.w_rows = cout;
   const int tiles_n = (d->batch + kp.tn - 1) / kp.tn;
   const int ksteps = kp.nsrc * kp.ntaps * kp.cblocks;
   kp.stages = d->stages > 0 ? d->stages : default_stages(bn, bkc, ksteps);  // stages < 0: force this kernel

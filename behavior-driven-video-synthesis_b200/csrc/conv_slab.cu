@@ -51,6 +51,9 @@ struct SlabKParams {
   int n_ntiles, total_items, n_total;
   int flip;         // 0: forward (input pixel = output pixel + tap - 1); 1: data gradient (output - tap + 1)
   int sa, sb;       // ring depths
+  const uint8_t* w_tiled;
+  int w_rows;
+  int contig;       // outputs written 1:1 (no DepthToSpace / scatter / fp32): lean linear-addressing epilogue
 };
 
 __global__ void __launch_bounds__(kSlabThreads, 1) conv_slab_kernel(const __grid_constant__ SlabKParams p) {
@@ -137,7 +140,11 @@ __global__ void __launch_bounds__(kSlabThreads, 1) conv_slab_kernel(const __grid
               mbar_wait(&b_empty[sb], phb ^ 1);
               if (elect_one()) {
                 mbar_expect_tx(&b_full[sb], kSlabBBytes);
-                tma_load_2d(b_ring + sb * kSlabBBytes, &p.tmB, &b_full[sb], bblk * 64, n_tile * kSlabBN);
+                if (p.w_tiled != nullptr)  // one 1-D bulk copy instead of a 128-row tensor box
+                  bulk_load_1d(b_ring + sb * kSlabBBytes, p.w_tiled + ((size_t)bblk * p.w_rows + n_tile * kSlabBN) * 128,
+                               kSlabBBytes, &b_full[sb]);
+                else
+                  tma_load_2d(b_ring + sb * kSlabBBytes, &p.tmB, &b_full[sb], bblk * 64, n_tile * kSlabBN);
               }
               __syncwarp();
               if (++sb == p.sb) {
@@ -214,6 +221,13 @@ __global__ void __launch_bounds__(kSlabThreads, 1) conv_slab_kernel(const __grid
       const int ecol = (n_tile - (ei ? p.n_split : 0)) * kSlabBN;
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * (2 * kSlabBN) + g * kSlabBN;
       const bool affine = p.ep[0].scale != nullptr;  // data gradients run with the identity
+      if (p.contig) {  // an M tile = R/2 full-width rows of one image = one contiguous run of the output
+        const long long pix0 = ((long long)n * p.H + h0 + g * (p.R / 2)) * p.W + q * 32;
+        tile_epilogue_contig<kSlabBN, kSlabGW>(e, affine ? s_scale + n_tile * kSlabBN : nullptr,
+                                               affine ? s_shift + n_tile * kSlabBN : nullptr, trow, t0, t1, t2, lane, ecol,
+                                               pix0, 32, &acc_empty[buf], &acc_full[buf], (li >> 1) & 1);
+        continue;
+      }
       tile_epilogue_staged<kSlabBN, kSlabGW>(e, gm, affine ? s_scale + n_tile * kSlabBN : nullptr,
                                              affine ? s_shift + n_tile * kSlabBN : nullptr, trow, t0, t1,
                                              t2, lane, q, ecol, n, h0 + g * (p.R / 2), 0, &acc_empty[buf], &acc_full[buf], (li >> 1) & 1);
@@ -229,8 +243,8 @@ __global__ void __launch_bounds__(kSlabThreads, 1) conv_slab_kernel(const __grid
 bool conv_slab_shape_ok(int c_src, int h, int w, int n_total, int k_total) {
   // Measured on B200 (profiles/r01_bench_v5.json vs r01_bench_slab.json): the kernel halves the L2 -> SM traffic
   // and wins where the K loop or the N extent is long enough to amortise its deeper, coarser pipeline — the
-  // concat layers (K >= 2304: +10 % forward) and their data gradients (N = 256: +43 %) — but loses to the
-  // two-CTAs-per-SM per-tap kernel on the single-source 128 -> 128 layers.
+  // concat layers (K >= 2304: +10 % forward) and their data gradients — but not on the single-source 128 -> 128
+  // layers or the N >= 256 up-sampling layers, which the persistent tile kernel serves better.
   // VUB_ENABLE_SLAB=1 forces it for every supported shape, =0 disables it.
   static const char* env = getenv("VUB_ENABLE_SLAB");
   if (env != nullptr && env[0] == '0') return false;
@@ -238,7 +252,7 @@ bool conv_slab_shape_ok(int c_src, int h, int w, int n_total, int k_total) {
   const int R = 256 / w;
   if (h % R != 0 || n_total % kSlabBN != 0 || n_total > kSlabMaxN) return false;
   if (env != nullptr && env[0] == '1') return true;
-  return k_total >= 2304 || n_total >= 256;
+  return k_total >= 2304;
 }
 
 int conv_slab_launch(const SlabJob& job, cudaStream_t stream) {
@@ -271,6 +285,15 @@ int conv_slab_launch(const SlabJob& job, cudaStream_t stream) {
   kp.total_items = job.batch * kp.tiles_h * kp.n_ntiles;
   kp.n_total = job.n_total;
   kp.flip = job.flip;
+  kp.contig = 1;
+  for (int i = 0; i < n_epi; ++i) {
+    const TileEpi& e = job.epi[i];
+    if (e.flags != 0 || e.pix_stride != 1 || e.pix_off_h != 0 || e.pix_off_w != 0 || e.out_h != job.h || e.out_w != job.w ||
+        e.out_f32 != nullptr)
+      kp.contig = 0;
+  }
+  kp.w_tiled = static_cast<const uint8_t*>(job.w_tiled);
+  kp.w_rows = job.w_rows;
   const size_t staging = (size_t)8 * kp.stage_tiles * EpiStage<kSlabGW>::TILE_BYTES;
   kp.sa = 2;
   kp.sb = static_cast<int>((222 * 1024 - 4608 - staging - (size_t)kp.sa * kSlabABytes) / kSlabBBytes);

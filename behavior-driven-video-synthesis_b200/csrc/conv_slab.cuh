@@ -12,6 +12,8 @@ struct SlabJob {
   int nsrc, c_src;       // c_src multiple of 64
   int batch, h, w;       // w in {32, 64}; h multiple of 256 / w
   const void* w_packed;  // B: [n_total rows][ktot] bf16, K order (source, tap, channel)
+  const void* w_tiled;   // optional tile-major pre-swizzled copy [ktot/64][w_rows][64], else nullptr
+  int w_rows;
   long long ktot;
   int n_total;           // multiple of 128
   int flip;              // 0 forward, 1 data gradient (taps mirrored)

@@ -46,9 +46,14 @@ struct TilesKParams {
   int n_ntiles;
   int total_tiles;
   int stages;
+  const uint8_t* w_tiled;
+  int w_rows;
+  long long total_pix;  // CONTIG kernels: pixels of the output tensor
 };
 
-template <int BN, int BKC>
+// CONTIG: every tile is one contiguous run of the NHWC output (full-width tiles, stride 1, no DepthToSpace, bf16
+// outputs) -> the lean linear-addressing epilogue.
+template <int BN, int BKC, bool CONTIG>
 __global__ void __launch_bounds__(kTilesThreads, 1)
     conv_tiles_kernel(const __grid_constant__ TilesKParams p) {
   constexpr int ROWB = BKC * 2;
@@ -131,7 +136,10 @@ __global__ void __launch_bounds__(kTilesThreads, 1)
           mbar_expect_tx(&full_bar[st], STAGE_BYTES);
           uint8_t* a = smem + st * STAGE_BYTES;
           tma_load_4d(a, &p.tmA[k.map], &full_bar[st], k.cblk * BKC, w0 + k.dw, h0 + k.dh, n0);
-          tma_load_2d(a + A_BYTES, &p.tmB, &full_bar[st], k.bblk * BKC, n_tile * BN);
+          if (BKC == 64 && p.w_tiled != nullptr)  // one 1-D bulk copy instead of a BN-row tensor box
+            bulk_load_1d(a + A_BYTES, p.w_tiled + ((size_t)k.bblk * p.w_rows + n_tile * BN) * 128, B_BYTES, &full_bar[st]);
+          else
+            tma_load_2d(a + A_BYTES, &p.tmB, &full_bar[st], k.bblk * BKC, n_tile * BN);
         }
         __syncwarp();
         if (++st == S) {
@@ -199,7 +207,14 @@ __global__ void __launch_bounds__(kTilesThreads, 1)
       const bool f32_out = (e.flags & (VUB_CONV_F32_NHWC | VUB_CONV_F32_NCHW)) != 0;
       mbar_wait(&acc_full[g], cnt & 1);
       tc_fence_after();
-      if constexpr (STAGED) {
+      if constexpr (STAGED && CONTIG) {
+        const bool affine = p.ep[0].scale != nullptr;  // data gradients run with the identity
+        const long long pix0 = ((long long)n0 * p.hout + h0) * p.wout + w0 + q * 32;
+        const long long left = p.total_pix - pix0;
+        tile_epilogue_contig<BN, GW>(e, affine ? s_scale + n_tile * BN : nullptr, affine ? s_shift + n_tile * BN : nullptr,
+                                     trow, t0, t1, t2, lane, ecol, pix0, left > 32 ? 32 : static_cast<int>(left),
+                                     &acc_empty[g], &acc_full[g], cnt & 1);
+      } else if constexpr (STAGED) {
         const bool affine = p.ep[0].scale != nullptr;  // data gradients run with the identity
         tile_epilogue_staged<BN, GW>(e, EpiGeom{p.tw, p.th, p.tw_log2, p.th_log2, p.batch},
                                      affine ? s_scale + n_tile * BN : nullptr, affine ? s_shift + n_tile * BN : nullptr, trow, t0, t1, t2, lane, q, ecol, n0, h0, w0, &acc_empty[g]);
@@ -234,19 +249,27 @@ __global__ void __launch_bounds__(kTilesThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int BN, int BKC>
-static int launch_tiles(const TilesKParams& kp, int grid, size_t smem, cudaStream_t stream) {
+template <int BN, int BKC, bool CONTIG>
+static int launch_tiles_t(const TilesKParams& kp, int grid, size_t smem, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tiles_kernel<BN, BKC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    attr_err = cudaFuncSetAttribute(conv_tiles_kernel<BN, BKC, CONTIG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     220 * 1024);
   });
   if (attr_err != cudaSuccess)
     return fail(static_cast<int>(attr_err), "cudaFuncSetAttribute(conv_tiles<%d,%d>): %s", BN, BKC,
                 cudaGetErrorString(attr_err));
-  conv_tiles_kernel<BN, BKC><<<grid, kTilesThreads, smem, stream>>>(kp);
+  conv_tiles_kernel<BN, BKC, CONTIG><<<grid, kTilesThreads, smem, stream>>>(kp);
   return check_launch("conv_tiles");
+}
+
+template <int BN, int BKC>
+static int launch_tiles(const TilesKParams& kp, bool contig, int grid, size_t smem, cudaStream_t stream) {
+  if constexpr (BN >= 32) {
+    if (contig) return launch_tiles_t<BN, BKC, true>(kp, grid, smem, stream);
+  }
+  return launch_tiles_t<BN, BKC, false>(kp, grid, smem, stream);
 }
 
 int conv_tiles_launch(const TileJob& job, cudaStream_t stream) {
@@ -276,6 +299,8 @@ int conv_tiles_launch(const TileJob& job, cudaStream_t stream) {
   kp.n_split = n_epi == 2 ? job.n_split / bn : n_total / bn;
   kp.stage_tiles = any_addend2 ? 3 : 2;
   kp.n_ksteps = job.n_ksteps;
+  kp.w_tiled = bkc == 64 ? static_cast<const uint8_t*>(job.w_tiled) : nullptr;
+  kp.w_rows = job.w_rows;
   kp.batch = job.batch;
   kp.hout = job.hout;
   kp.wout = job.wout;
@@ -324,9 +349,17 @@ int conv_tiles_launch(const TileJob& job, cudaStream_t stream) {
     if (n_sm <= 0) n_sm = 148;
   }
   const int grid = kp.total_tiles < n_sm ? kp.total_tiles : n_sm;
+  // contiguous tiles: full-width pixel tiles written 1:1 (no shuffle, no scatter, bf16)
+  bool contig = kp.tw == job.wout && !getenv("VUB_TILES_NO_CONTIG");
+  for (int i = 0; i < n_epi; ++i) {
+    const TileEpi& e = job.epi[i];
+    contig = contig && e.flags == 0 && e.pix_stride == 1 && e.pix_off_h == 0 && e.pix_off_w == 0 &&
+             e.out_h == job.hout && e.out_w == job.wout && e.out_f32 == nullptr;
+  }
+  kp.total_pix = (long long)job.batch * job.hout * job.wout;
 
 #define VUB_TILES_DISPATCH(BN_, BKC_) \
-  if (bn == BN_ && bkc == BKC_) return launch_tiles<BN_, BKC_>(kp, grid, smem, stream);
+  if (bn == BN_ && bkc == BKC_) return launch_tiles<BN_, BKC_>(kp, contig, grid, smem, stream);
   VUB_TILES_DISPATCH(16, 32)
   VUB_TILES_DISPATCH(16, 64)
   VUB_TILES_DISPATCH(32, 32)

@@ -52,6 +52,8 @@ struct TileJob {
   int n_src;
   int bkc;               // 32 or 64
   const void* w;         // packed weights [n_total rows][ktot] bf16, K-major
+  const void* w_tiled;   // optional tile-major pre-swizzled copy [ktot/64][w_rows][64] (bkc == 64), else nullptr
+  int w_rows;
   long long ktot;        // row pitch of w in elements
   int n_total;           // GEMM N (rows of w used); multiple of the N tile
   int bn;                // N tile override (0 = min(n_total, 256))

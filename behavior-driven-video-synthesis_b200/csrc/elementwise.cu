@@ -62,6 +62,20 @@ __device__ __forceinline__ void wn_emit_row(const vub_wn_entry& e, int co, float
       out[(src * e.ktaps + tap) * e.c_src + cs] = __float2bfloat16_rn(v[i] * inv);
     }
   }
+  if (e.w_tiled != nullptr) {  // tile-major, pre-swizzled copy of the packed row (see vub_wn_entry.w_tiled)
+    __nv_bfloat16* wt = static_cast<__nv_bfloat16*>(e.w_tiled);
+    const int row = e.wd_col0 + co;
+    for (int i = threadIdx.x; i < len; i += kWnThreads) {
+      const int ci = i / e.ktaps;
+      const int tap = i - ci * e.ktaps;
+      const int src = ci / e.c_src;
+      const int cs = ci - src * e.c_src;
+      const int k = (src * e.ktaps + tap) * e.c_src + cs;
+      const int kb = k >> 6, kc = k & 63;
+      wt[((size_t)kb * e.tiled_rows + row) * 64 + ((((kc >> 3) ^ (row & 7)) << 3) | (kc & 7))] =
+          __float2bfloat16_rn(v[i] * inv);
+    }
+  }
   if (e.w32 != nullptr) {  // fp32 validation path: [k][co], unscaled
     for (int i = threadIdx.x; i < len; i += kWnThreads) {
       const int ci = i / e.ktaps;
@@ -80,6 +94,16 @@ __device__ __forceinline__ void wn_emit_row(const vub_wn_entry& e, int co, float
       const int ci = i / e.ktaps;
       const int tap = i - ci * e.ktaps;
       wd[(size_t)ci * pitch + (size_t)tap * e.wd_cout + e.wd_col0 + co] = __float2bfloat16_rn(v[i] * sc);
+    }
+    if (e.wd_tiled != nullptr) {
+      __nv_bfloat16* wdt = static_cast<__nv_bfloat16*>(e.wd_tiled);
+      for (int i = threadIdx.x; i < len; i += kWnThreads) {
+        const int ci = i / e.ktaps;  // row
+        const int tap = i - ci * e.ktaps;
+        const int k = tap * e.wd_cout + e.wd_col0 + co;
+        const int kb = k >> 6, kc = k & 63;
+        wdt[((size_t)kb * e.cin + ci) * 64 + ((((kc >> 3) ^ (ci & 7)) << 3) | (kc & 7))] = __float2bfloat16_rn(v[i] * sc);
+      }
     }
   }
   if (threadIdx.x == 0 && e.scale != nullptr) {

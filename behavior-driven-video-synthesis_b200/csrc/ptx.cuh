@@ -59,6 +59,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// 1-D bulk copy global -> shared (no tensor map), completion on an mbarrier.  16-byte aligned, size % 16 == 0.
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // TMA loads (tiled mode), completion on an mbarrier
 // ----------------------------------------------------------------------------------------------

@@ -89,9 +89,12 @@ class ConvWeights:
     """Packed bf16 ``v/||v||`` [cout_pad, K] + fp32 scale/shift of one (possibly merged) conv."""
 
     __slots__ = ("w", "scale", "shift", "cout", "cout_pad", "nsrc", "c_src", "ksize", "stride", "wd", "cout_k",
-                 "slot")
+                 "slot", "w_tiled", "wd_tiled")
 
-    def __init__(self, w, scale, shift, cout, cout_pad, nsrc, c_src, ksize, stride, wd=None, cout_k=0, slot=-1):
+    def __init__(self, w, scale, shift, cout, cout_pad, nsrc, c_src, ksize, stride, wd=None, cout_k=0, slot=-1,
+                 w_tiled=None, wd_tiled=None):
+        # tile-major pre-swizzled copies for the tensor-core-bound layers (1-D bulk weight loads), or None
+        self.w_tiled, self.wd_tiled = w_tiled, wd_tiled
         self.w, self.scale, self.shift = w, scale, shift
         self.cout, self.cout_pad = cout, cout_pad
         self.nsrc, self.c_src, self.ksize, self.stride = nsrc, c_src, ksize, stride
@@ -190,6 +193,9 @@ class WeightBank:
             wd_off += k * cout_k
         self._w = torch.zeros(w_off, dtype=torch.bfloat16, device=device)
         self._wd = torch.zeros(wd_off if with_wd else 0, dtype=torch.bfloat16, device=device)
+        # tile-major copies (same offsets; only the slots with >= 64 channels per source / per tap use theirs)
+        self._wt = torch.zeros(w_off, dtype=torch.bfloat16, device=device)
+        self._wdt = torch.zeros(wd_off if with_wd else 0, dtype=torch.bfloat16, device=device)
         self._with_wd = with_wd
         self._scale = torch.zeros(s_off, dtype=torch.float32, device=device)
         self._shift = torch.zeros(s_off, dtype=torch.float32, device=device)
@@ -203,8 +209,10 @@ class WeightBank:
             sh = self._shift[so:so + cpad]
             taps = first.kernel_size ** 2
             wd = self._wd[wdo:wdo + k * cout_k].view(nsrc * c_src, taps * cout_k) if with_wd else None
+            wt = self._wt[wo:wo + cpad * k] if c_src % 64 == 0 else None
+            wdt = self._wdt[wdo:wdo + k * cout_k] if (with_wd and cout_k % 64 == 0) else None
             self._views[id(first)] = ConvWeights(w, sc, sh, cout, cpad, nsrc, c_src, first.kernel_size,
-                                                 first.stride, wd=wd, cout_k=cout_k, slot=si)
+                                                 first.stride, wd=wd, cout_k=cout_k, slot=si, w_tiled=wt, wd_tiled=wdt)
             r = 0
             for m in slot:
                 e = N.WnEntry()
@@ -218,8 +226,13 @@ class WeightBank:
                 e.shift = sh.data_ptr() + r * 4
                 e.cout, e.cin, e.ktaps, e.c_src = m.out_channels, m.in_channels, m.kernel_size ** 2, c_src
                 e.ktot, e.row_start = k, rows
+                e.wd_cout, e.wd_col0 = cout_k, r
+                if wt is not None:
+                    e.w_tiled, e.tiled_rows = wt.data_ptr(), cpad
                 if with_wd:
-                    e.wd, e.wd_cout, e.wd_col0 = wd.data_ptr(), cout_k, r
+                    e.wd = wd.data_ptr()
+                    if wdt is not None:
+                        e.wd_tiled = wdt.data_ptr()
                 rows += m.out_channels
                 r += m.out_channels
                 entries.append(e)
@@ -360,7 +373,7 @@ class NormConv2d(nn.Module):
                 xs.append(a.pick(m))
         raw, elu = ops.conv_fwd(xs, cw.w, cw.scale, cw.shift, ksize=cw.ksize,
                                 stride=cw.stride, residual=None if residual is None else residual.raw,
-                                want_raw=want_raw, want_elu=want_elu, d2s=d2s, elu_in=elu_in)
+                                want_raw=want_raw, want_elu=want_elu, d2s=d2s, elu_in=elu_in, w_tiled=cw.w_tiled)
         out = Act(raw, elu)
         if bank.tape is not None:
             bank.tape.conv(self, srcs, residual, out, d2s)
@@ -374,6 +387,7 @@ class NormConv2d(nn.Module):
                                     want_raw=True, want_elu=False, nchw=layout == "nchw")
             return out, None
         out = ops.conv_fwd_f32([a.pick(m) for a, m in srcs], cw.w, cw.scale, cw.shift, ksize=cw.ksize, layout=layout,
+                               w_tiled=cw.w_tiled,
                                cout_valid=cw.cout)
         slot = None
         if bank.tape is not None:

@@ -22,7 +22,7 @@ _LIB = torch.library.Library("vunet_b200", "DEF")
 _LIB.define(
     "conv_fwd(Tensor x0, Tensor? x1, Tensor w, Tensor scale, Tensor shift, Tensor? residual, "
     "int ksize, int stride, int cout_valid, bool want_raw, bool want_elu, bool d2s, int f32_mode, "
-    "int stages, int elu_in=0) -> Tensor[]"
+    "int stages, int elu_in=0, Tensor? w_tiled=None) -> Tensor[]"
 )
 _LIB.define("wn_prep(Tensor table, int n_entries, int total_rows) -> ()")
 _LIB.define(
@@ -42,7 +42,8 @@ _LIB.define("nchw_to_nhwc32(Tensor x, bool want_raw, bool want_elu) -> Tensor[]"
 # ---- training half (mutating ops: gradient buffers are accumulated in place) ----------------------
 _LIB.define(
     "conv_dgrad(Tensor dy, Tensor wd, Tensor(a!) dx0, Tensor(b!)? dx1, Tensor? mask0, Tensor? mask1, "
-    "Tensor? add0, Tensor? add1, Tensor? add20, Tensor? add21, int ksize, int stride, bool d2s) -> ()"
+    "Tensor? add0, Tensor? add1, Tensor? add20, Tensor? add21, int ksize, int stride, bool d2s, "
+    "Tensor? wd_tiled=None) -> ()"
 )
 _LIB.define(
     "conv_wgrad(Tensor dy, Tensor x0, Tensor? x1, Tensor(a!) gt, Tensor(b!) dy_sum, int ksize, int stride, "
@@ -91,7 +92,7 @@ def _check_act(t: torch.Tensor, name: str) -> None:
 
 
 def _conv_fwd_cuda(x0, x1, w, scale, shift, residual, ksize, stride, cout_valid, want_raw, want_elu,
-                   d2s, f32_mode, stages, elu_in=0) -> List[torch.Tensor]:
+                   d2s, f32_mode, stages, elu_in=0, w_tiled=None) -> List[torch.Tensor]:
     _check_act(x0, "conv_fwd x0")
     B, H, W, c_src = x0.shape
     nsrc = 1
@@ -108,6 +109,10 @@ def _conv_fwd_cuda(x0, x1, w, scale, shift, residual, ksize, stride, cout_valid,
     d.x[0] = x0.data_ptr()
     d.x[1] = _p(x1)
     d.w = w.data_ptr()
+    if w_tiled is not None:
+        if w_tiled.dtype != torch.bfloat16 or w_tiled.numel() != w.numel() or c_src % 64:
+            raise ValueError("conv_fwd: w_tiled must be the tile-major copy of w (c_src a multiple of 64)")
+        d.w_tiled = w_tiled.data_ptr()
     d.scale = scale.data_ptr()
     d.shift = shift.data_ptr()
     d.residual = _p(residual)
@@ -243,7 +248,8 @@ def _nhwc_to_nchw_cuda(x) -> torch.Tensor:
     return out
 
 
-def _conv_dgrad_cuda(dy, wd, dx0, dx1, mask0, mask1, add0, add1, add20, add21, ksize, stride, d2s) -> None:
+def _conv_dgrad_cuda(dy, wd, dx0, dx1, mask0, mask1, add0, add1, add20, add21, ksize, stride, d2s,
+                     wd_tiled=None) -> None:
     _check_act(dy, "conv_dgrad dy")
     _check_act(dx0, "conv_dgrad dx0")
     B, H, W, c_src = dx0.shape
@@ -261,6 +267,10 @@ def _conv_dgrad_cuda(dy, wd, dx0, dx1, mask0, mask1, add0, add1, add20, add21, k
             raise ValueError("conv_dgrad: dx / mask / addend tensors must be contiguous NHWC bf16 of the input shape")
     d = N.DgradDesc()
     d.dy, d.wd = dy.data_ptr(), wd.data_ptr()
+    if wd_tiled is not None:
+        if wd_tiled.dtype != torch.bfloat16 or wd_tiled.numel() != wd.numel() or cout_k % 64:
+            raise ValueError("conv_dgrad: wd_tiled must be the tile-major copy of wd (cout_k a multiple of 64)")
+        d.wd_tiled = wd_tiled.data_ptr()
     d.dx[0], d.dx[1] = dx0.data_ptr(), _p(dx1)
     d.mask_elu[0], d.mask_elu[1] = _p(mask0), _p(mask1)
     d.addend[0], d.addend[1] = _p(add0), _p(add1)
@@ -454,13 +464,13 @@ _ops = torch.ops.vunet_b200
 # ------------------------------------------------------------------------------------------------
 def conv_fwd(x: Sequence[torch.Tensor], w, scale, shift, *, ksize: int, stride: int = 1,
              residual: Optional[torch.Tensor] = None, want_raw: bool = True, want_elu: bool = True,
-             d2s: bool = False, cout_valid: Optional[int] = None, stages: int = 0, elu_in: int = 0
-             ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+             d2s: bool = False, cout_valid: Optional[int] = None, stages: int = 0, elu_in: int = 0,
+             w_tiled: Optional[torch.Tensor] = None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """bf16 NHWC outputs: returns (raw or None, elu or None).  ``elu_in``: bit s set = source s is a RAW
     activation to which the kernel applies ELU while loading (only where :func:`elu_in_ok`)."""
     cv = w.shape[0] if cout_valid is None else cout_valid
     outs = _ops.conv_fwd(x[0], x[1] if len(x) > 1 else None, w, scale, shift, residual, ksize, stride, cv,
-                         want_raw, want_elu, d2s, F32_NONE, stages, elu_in)
+                         want_raw, want_elu, d2s, F32_NONE, stages, elu_in, w_tiled)
     it = iter(outs)
     raw = next(it) if want_raw else None
     elu = next(it) if want_elu else None
@@ -474,12 +484,12 @@ def elu_in_ok(nsrc: int, c_src: int, cout: int, ksize: int, stride: int, h: int,
 
 
 def conv_fwd_f32(x: Sequence[torch.Tensor], w, scale, shift, *, ksize: int, layout: str,
-                 cout_valid: Optional[int] = None, stages: int = 0) -> torch.Tensor:
+                 cout_valid: Optional[int] = None, stages: int = 0, w_tiled: Optional[torch.Tensor] = None) -> torch.Tensor:
     """fp32 output, ``layout`` in {"nhwc", "nchw"} (latent head input / out_conv image)."""
     cv = w.shape[0] if cout_valid is None else cout_valid
     mode = F32_NHWC if layout == "nhwc" else F32_NCHW
     return _ops.conv_fwd(x[0], x[1] if len(x) > 1 else None, w, scale, shift, None, ksize, 1, cv, False, False,
-                         False, mode, stages)[0]
+                         False, mode, stages, 0, w_tiled)[0]
 
 
 def wn_prep(table: torch.Tensor, n_entries: int, total_rows: int) -> None:
@@ -539,14 +549,14 @@ def nchw_to_nhwc32(x, want_raw=True, want_elu=True):
 
 # ---- training half ------------------------------------------------------------------------------
 def conv_dgrad(dy, wd, dx, *, mask=(None, None), addend=(None, None), addend2=(None, None), ksize: int,
-               stride: int = 1, d2s: bool = False) -> None:
+               stride: int = 1, d2s: bool = False, wd_tiled: Optional[torch.Tensor] = None) -> None:
     """``dx[s] = ELU'(mask[s]) * dgrad_s + addend[s] + addend2[s]`` for every source (in place into dx)."""
     dx = list(dx) + [None] * (2 - len(dx))
     mask = list(mask) + [None] * (2 - len(mask))
     addend = list(addend) + [None] * (2 - len(addend))
     addend2 = list(addend2) + [None] * (2 - len(addend2))
     _ops.conv_dgrad(dy, wd, dx[0], dx[1], mask[0], mask[1], addend[0], addend[1], addend2[0], addend2[1], ksize,
-                    stride, d2s)
+                    stride, d2s, wd_tiled)
 
 
 def conv_wgrad(dy, x, gt, dy_sum, *, ksize: int, stride: int = 1, d2s: bool = False) -> None:

@@ -256,7 +256,7 @@ def run_backward(model, bank: WeightBank, tape: Tape, d_imgs: Optional[torch.Ten
                 add1.append(a1)
                 add2.append(a2)
             ops.conv_dgrad(dy, cw.wd, dx, mask=mask, addend=add1, addend2=add2, ksize=cw.ksize, stride=cw.stride,
-                           d2s=d2s)
+                           d2s=d2s, wd_tiled=cw.wd_tiled)
             out.grad = None
         elif kind == "stem":
             _, conv, x, out = rec

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VUB_ABI_VERSION 2
+#define VUB_ABI_VERSION 3
 
 #define VUB_OK 0
 #define VUB_E_NULL (-1)        /* required pointer is NULL */
@@ -77,6 +77,7 @@ typedef struct vub_conv_desc {
   int32_t stride;        /* 1 or 2 */
   uint32_t flags;
   int32_t stages;        /* smem pipeline depth, 0 = library default */
+  const void* w_tiled;   /* optional tile-major copy of w (vub_wn_entry.w_tiled, c_src % 64 == 0), or NULL */
 } vub_conv_desc;
 
 int vub_conv_fwd(const vub_conv_desc* d, void* stream);
@@ -116,6 +117,16 @@ typedef struct vub_wn_entry {
   /* fp32 validation path: w32[(src*ktaps + tap)*c_src + c][wd_col0 + co] = v_hat (row pitch wd_cout floats).
    * NULL = skip.  w_packed may be NULL when only w32 is wanted. */
   float* w32;
+  /* Tile-major copies for the tensor-core-bound layers (c_src a multiple of 64; NULL = skip): the same values as
+   * w_packed / wd, stored as the exact shared-memory image of a SWIZZLE_128B operand tile so that a kernel can fetch
+   * a weight tile with ONE 1-D bulk copy (measured 73 B/clk/SM, and it overlaps a tensor box; a 128-row tensor box
+   * costs 384 cycles = 42.7 B/clk/SM: profiles/r01_exp_bulk.log):
+   *   w_tiled [K/64][tiled_rows][64]   element (row = wd_col0 + co, k):  block k/64, 16-byte chunk ((k%64)/8) ^ (row%8)
+   *   wd_tiled[ktaps*wd_cout/64][cin][64]  element (row = src*c_src + c, k = tap*wd_cout + wd_col0 + co): likewise */
+  void* w_tiled;
+  void* wd_tiled;
+  int32_t tiled_rows;  /* rows of the whole slot in w_tiled (= padded output channels) */
+  int32_t pad_;
 } vub_wn_entry;
 
 int vub_wn_prep(const vub_wn_entry* table_dev, int32_t n_entries, int32_t total_rows, void* stream);
@@ -219,6 +230,8 @@ typedef struct vub_dgrad_desc {
   int32_t cout_k;            /* K extent per tap = output channels padded to a multiple of 32 */
   int32_t ksize, stride;
   uint32_t flags;            /* VUB_CONV_D2S */
+  int32_t pad_;
+  const void* wd_tiled;      /* optional tile-major copy of wd (vub_wn_entry.wd_tiled, cout_k % 64 == 0), or NULL */
 } vub_dgrad_desc;
 
 int vub_conv_dgrad(const vub_dgrad_desc* d, void* stream);

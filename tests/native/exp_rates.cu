@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstring>
 #include <cstdlib>
 #include <vector>
 
@@ -134,6 +135,80 @@ __global__ void __launch_bounds__(64) tma_rate_kernel(const __grid_constant__ CU
   }
 }
 
+// Same ring, but every load is ONE 1-D bulk copy (cp.async.bulk, no tensor map): what a weight tile costs when it is
+// stored in global memory as the exact (pre-swizzled) shared-memory image.  With `mixed` every other load is a
+// 128-row x 128 B tensor box (the activation tile of a k-step), the others are bulk copies of the same size.
+// bulk_load_1d: csrc/ptx.cuh
+
+__global__ void __launch_bounds__(64) bulk_rate_kernel(const __grid_constant__ CUtensorMap tm, const uint8_t* src,
+                                                       int box_bytes, int stages, int n_loads, long long n_boxes,
+                                                       int mixed, long long* cycles_out) {
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~static_cast<uintptr_t>(1023));
+  __shared__ uint64_t full[16];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) mbar_init(&full[i], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // n_boxes is a power of two: no divisions in the issuing thread's loop
+    uint32_t box = blockIdx.x;
+    const uint32_t mask = (uint32_t)n_boxes - 1;
+    int st = 0;
+    uint32_t ph = 0;
+    const long long t0 = clock64();
+    for (int i = 0; i < n_loads + stages; ++i) {
+      if (i >= stages) mbar_wait(&full[st], ph ^ 1);
+      if (i < n_loads) {
+        mbar_expect_tx(&full[st], box_bytes);
+        const uint32_t b = box & mask;
+        if (mixed && (i & 1)) tma_load_2d(smem + st * box_bytes, &tm, &full[st], 0, (int)(b * 128));
+        else bulk_load_1d(smem + st * box_bytes, src + (size_t)b * box_bytes, box_bytes, &full[st]);
+        box += gridDim.x;
+      }
+      if (++st == stages) {
+        st = 0;
+        ph ^= 1;
+      }
+    }
+    cycles_out[blockIdx.x] = clock64() - t0;
+  }
+}
+
+static void run_bulk(EncodeTiledFn enc, int box_bytes, int stages, size_t tensor_bytes, int mixed, const char* what) {
+  void* dA;
+  CK(cudaMalloc(&dA, tensor_bytes));
+  CK(cudaMemset(dA, 0, tensor_bytes));
+  CUtensorMap tm;
+  const int rows_total = (int)(tensor_bytes / 128);
+  cuuint64_t dims[2] = {64, (cuuint64_t)rows_total};
+  cuuint64_t str[1] = {128};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dA, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r) { printf("encode failed %d\n", (int)r); return; }
+  const int n_loads = 2048;
+  long long* d;
+  CK(cudaMalloc(&d, 148 * sizeof(long long)));
+  const size_t smem = (size_t)stages * box_bytes + 2048;
+  CK(cudaFuncSetAttribute(bulk_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long n_boxes = (long long)(tensor_bytes / box_bytes);
+  bulk_rate_kernel<<<148, 64, smem>>>(tm, (const uint8_t*)dA, box_bytes, stages, n_loads, n_boxes, mixed, d);
+  bulk_rate_kernel<<<148, 64, smem>>>(tm, (const uint8_t*)dA, box_bytes, stages, n_loads, n_boxes, mixed, d);
+  CK(cudaDeviceSynchronize());
+  std::vector<long long> h(148);
+  CK(cudaMemcpy(h.data(), d, 148 * sizeof(long long), cudaMemcpyDeviceToHost));
+  double avg = 0;
+  for (long long v : h) avg += v;
+  avg /= 148;
+  printf("[EXP bulk] %-12s %s copy=%5d B stages=%2d : %.1f B/cycle/SM, %.0f cycles/copy\n", what,
+         mixed ? "alternating 1-D bulk / 128x128B box" : "1-D bulk only", box_bytes, stages,
+         (double)n_loads * box_bytes / avg, avg / n_loads);
+  cudaFree(dA); cudaFree(d);
+}
+
 static void run_tma(EncodeTiledFn enc, int row_bytes, int box_rows, int stages, size_t tensor_bytes, const char* what) {
   const int rows_total = (int)(tensor_bytes / row_bytes);
   void* dA;
@@ -174,7 +249,21 @@ static void run_tma(EncodeTiledFn enc, int row_bytes, int box_rows, int stages, 
   cudaFree(dA); cudaFree(d);
 }
 
-int main() {
+int main(int argc, char** argv) {
+  if (argc > 1 && !strcmp(argv[1], "bulk")) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(p);
+    for (int stages : {4, 8}) {
+      run_bulk(enc, 16384, stages, 32ull << 20, 0, "L2-resident");
+      run_bulk(enc, 16384, stages, 32ull << 20, 1, "L2-resident");
+      run_bulk(enc, 8192, stages, 32ull << 20, 0, "L2-resident");
+      run_bulk(enc, 32768, stages > 6 ? 6 : stages, 32ull << 20, 0, "L2-resident");
+    }
+    run_bulk(enc, 16384, 8, 4ull << 30, 0, "HBM");
+    return 0;
+  }
   run_mma<16, 32, 1>();
   run_mma<32, 32, 1>();
   run_mma<32, 32, 2>();

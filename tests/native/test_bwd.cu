@@ -84,6 +84,20 @@ static void sync_or_die(const char* what) {
 }
 
 // ------------------------------------------------------------------------------------------------
+
+// Tile-major, pre-swizzled copy of a K-major bf16 matrix [rows][K] (K % 64 == 0): block k/64, row, 16-byte chunk
+// ((k%64)/8) ^ (row%8) — the shared-memory image of a SWIZZLE_128B operand tile (vub_wn_entry.w_tiled / wd_tiled).
+static std::vector<float> tile_major(const std::vector<float>& w, int rows, int K) {
+  std::vector<float> t(w.size());
+  for (int r = 0; r < rows; ++r)
+    for (int k = 0; k < K; ++k) {
+      const int kb = k >> 6, kc = k & 63;
+      t[((size_t)kb * rows + r) * 64 + ((((kc >> 3) ^ (r & 7)) << 3) | (kc & 7))] = w[(size_t)r * K + k];
+    }
+  return t;
+}
+static int g_tiled = 0;  // 1: also hand the kernels the tile-major weights (1-D bulk weight loads)
+
 struct BwdCase {
   const char* name;
   int B, H, W;  // conv INPUT extents
@@ -152,6 +166,9 @@ static void run_dgrad(const BwdCase& c) {
   DevBuf<__nv_bfloat16> d_dy(dy_elems), d_wd((size_t)N * K);
   d_dy.up(to_bf16(dy));
   d_wd.up(to_bf16(wd));
+  DevBuf<__nv_bfloat16> d_wdt((size_t)N * K);
+  const bool tiled = g_tiled && c.cout_k % 64 == 0;
+  if (tiled) d_wdt.up(to_bf16(tile_major(wd, N, K)));
   DevBuf<__nv_bfloat16>*d_dx[2] = {nullptr, nullptr}, *d_m[2] = {nullptr, nullptr}, *d_a1[2] = {nullptr, nullptr},
                        *d_a2[2] = {nullptr, nullptr};
   vub_dgrad_desc d;
@@ -168,6 +185,7 @@ static void run_dgrad(const BwdCase& c) {
   }
   d.dy = d_dy.p;
   d.wd = d_wd.p;
+  d.wd_tiled = tiled ? d_wdt.p : nullptr;
   d.nsrc = c.nsrc; d.c_src = c.c_src; d.batch = c.B; d.hin = c.H; d.win = c.W; d.cout_k = c.cout_k;
   d.ksize = c.ksize; d.stride = c.stride; d.flags = c.d2s ? VUB_CONV_D2S : 0;
   const int rc = vub_conv_dgrad(&d, nullptr);
@@ -552,6 +570,10 @@ int main(int argc, char** argv) {
       {"3x3 64->128 D2S @32x32 B1",                           1, 32, 32, 64, 1, 128, 3, 1, true, false, false, false, false},
   };
   for (const BwdCase& c : cases) run_dgrad(c);
+  g_tiled = 1;  // the same data gradients with 1-D bulk weight loads from the tile-major wd
+  for (const BwdCase& c : cases)
+    if (c.cout_k % 64 == 0) run_dgrad(c);
+  g_tiled = 0;
   for (const BwdCase& c : cases) run_wgrad(c);
   // shapes the activation-slab kernel takes over (data gradient with mirrored taps)
   const BwdCase slab_cases[] = {
@@ -561,6 +583,9 @@ int main(int argc, char** argv) {
       {"slab 3x3 128->64 @64x64 B1 plain",                    1, 64, 64, 128, 1, 64, 3, 1, false, false, false, false, false},
   };
   for (const BwdCase& c : slab_cases) run_dgrad(c);
+  g_tiled = 1;
+  for (const BwdCase& c : slab_cases) run_dgrad(c);
+  g_tiled = 0;
   // shapes the row-streaming kernel takes over in data-gradient mode (width >= 128, <= 64 channels)
   const BwdCase rows_cases[] = {
       {"rows 1x1 32->32 @8x256 B2 mask+addend inplace",       2, 8, 256, 32, 1, 32, 1, 1, false, true, true, false, true},

@@ -83,6 +83,20 @@ struct ConvCase {
   int stages;
 };
 
+
+// Tile-major, pre-swizzled copy of a K-major bf16 matrix [rows][K] (K % 64 == 0): block k/64, row, 16-byte chunk
+// ((k%64)/8) ^ (row%8) — the shared-memory image of a SWIZZLE_128B operand tile (vub_wn_entry.w_tiled / wd_tiled).
+static std::vector<float> tile_major(const std::vector<float>& w, int rows, int K) {
+  std::vector<float> t(w.size());
+  for (int r = 0; r < rows; ++r)
+    for (int k = 0; k < K; ++k) {
+      const int kb = k >> 6, kc = k & 63;
+      t[((size_t)kb * rows + r) * 64 + ((((kc >> 3) ^ (r & 7)) << 3) | (kc & 7))] = w[(size_t)r * K + k];
+    }
+  return t;
+}
+static int g_tiled = 0;  // 1: also hand the kernels the tile-major weights (1-D bulk weight loads)
+
 static int g_elu_in = 0;  // VUB_CONV_ELU_IN source mask for the next run_conv_case calls
 
 static void run_conv_case(const ConvCase& cc) {
@@ -149,6 +163,12 @@ static void run_conv_case(const ConvCase& cc) {
   dx0.up(to_bf16(xraw[0]));
   if (cc.nsrc == 2) dx1.up(to_bf16(xraw[1]));
   dw.up(to_bf16(w));
+  DevBuf<__nv_bfloat16> dwt(w.size());
+  const bool tiled = g_tiled && cc.c_src % 64 == 0;
+  if (tiled) {
+    dwt.up(to_bf16(tile_major(w, cc.cout, K)));
+    if (getenv("VUB_TEST_ZERO_W")) CK(cudaMemset(dw.p, 0, w.size() * 2));  // prove the kernels read the tiled copy
+  }
   dscale.up(scale);
   dshift.up(shift);
   if (cc.residual) dres.up(to_bf16(res));
@@ -177,6 +197,7 @@ static void run_conv_case(const ConvCase& cc) {
   d.flags = (cc.d2s ? VUB_CONV_D2S : 0) | (cc.f32nhwc ? VUB_CONV_F32_NHWC : 0) | (cc.f32nchw ? VUB_CONV_F32_NCHW : 0) |
             ((g_elu_in & 1) ? VUB_CONV_ELU_IN0 : 0) | ((g_elu_in & 2) ? VUB_CONV_ELU_IN1 : 0);
   d.stages = cc.stages;
+  d.w_tiled = tiled ? dwt.p : nullptr;
   int rc = vub_conv_fwd(&d, nullptr);
   if (rc != 0) {
     printf("[FAIL] %-58s launch rc=%d (%s)\n", cc.name, rc, vub_last_error());
@@ -414,6 +435,11 @@ static void perf_conv(const char* name, int B, int H, int W, int c_src, int nsrc
   d.residual = residual ? dres.p : nullptr; d.out_raw = draw.p; d.out_elu = dual ? delu.p : nullptr;
   d.nsrc = nsrc; d.c_src = c_src; d.batch = B; d.hin = H; d.win = W; d.cout = cout; d.cout_valid = cout;
   d.ksize = ksize; d.stride = stride; d.flags = d2s ? VUB_CONV_D2S : 0; d.stages = stages;
+  DevBuf<__nv_bfloat16> dwt((size_t)cout * K);
+  if (getenv("VUB_TEST_TILED") && c_src % 64 == 0) {
+    CK(cudaMemset(dwt.p, 0, (size_t)cout * K * 2));
+    d.w_tiled = dwt.p;
+  }
   if (g_elu_in) {  // lean I/O: raw source(s) transformed on load; the residual IS the raw source (an L2 hit)
     d.flags |= ((g_elu_in & 1) ? VUB_CONV_ELU_IN0 : 0) | ((g_elu_in & 2) ? VUB_CONV_ELU_IN1 : 0);
     if (residual) d.residual = dx0.p;
@@ -480,6 +506,10 @@ int main(int argc, char** argv) {
       {"3x3 128->128 @32x32 B2 stages=5",                  2, 32, 32, 128, 1, 128, 128, 3, 1, true, true, true, false, false, false, 5},
   };
   for (const ConvCase& c : cases) run_conv_case(c);
+  g_tiled = 1;  // the same shapes with 1-D bulk weight loads from the tile-major copy (>= 64 channels per source)
+  for (const ConvCase& c : cases)
+    if (c.c_src % 64 == 0) run_conv_case(c);
+  g_tiled = 0;
   // activation-slab kernel (3x3 stride 1, >= 64 channels per source, 64x64 / 32x32)
   const ConvCase slab_cases[] = {
       {"slab 3x3 128->128 @64x64 B2 +res dual",            2, 64, 64, 128, 1, 128, 128, 3, 1, true, true, true, false, false, false, 0},
@@ -490,6 +520,9 @@ int main(int argc, char** argv) {
       {"slab 3x3 128->128 @32x32 B41 (items > SMs) +res",  41, 32, 32, 128, 1, 128, 128, 3, 1, true, true, true, false, false, false, 0},
   };
   for (const ConvCase& c : slab_cases) run_conv_case(c);
+  g_tiled = 1;
+  for (const ConvCase& c : slab_cases) run_conv_case(c);
+  g_tiled = 0;
   // row-streaming kernel (output width >= 128, <= 64 channels per source)
   const ConvCase row_cases[] = {
       {"rows 3x3 64->64 @16x128 B2 +res dual",             2, 16, 128, 64, 1, 64, 64, 3, 1, true, true, true, false, false, false, 0},

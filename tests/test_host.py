@@ -117,10 +117,10 @@ def test_library_loads_and_exports_every_symbol():
         assert hasattr(lib, sym), sym
     assert _native.lib().vub_abi_version() == _native.ABI_VERSION
     # struct mirrors must match the C layout (pointers first, then int32 fields)
-    assert ctypes.sizeof(_native.ConvDesc) == 9 * 8 + 11 * 4 + 4  # padded to 8
-    assert ctypes.sizeof(_native.WnEntry) == 8 * 8 + 6 * 4 + 8 + 2 * 4 + 8
+    assert ctypes.sizeof(_native.ConvDesc) == 9 * 8 + 11 * 4 + 4 + 8  # padded to 8, + w_tiled
+    assert ctypes.sizeof(_native.WnEntry) == 8 * 8 + 6 * 4 + 8 + 2 * 4 + 8 + 2 * 8 + 2 * 4
     assert ctypes.sizeof(_native.ConvF32Desc) == 8 * 8 + 10 * 4
-    assert ctypes.sizeof(_native.DgradDesc) == 10 * 8 + 9 * 4 + 4  # padded to 8
+    assert ctypes.sizeof(_native.DgradDesc) == 10 * 8 + 9 * 4 + 4 + 8  # + wd_tiled
     assert ctypes.sizeof(_native.WgradDesc) == 6 * 8 + 12 * 4
     assert ctypes.sizeof(_native.WnbEntry) == 11 * 8 + 8 * 4 + 8 + 2 * 4
     assert ctypes.sizeof(_native.AdamEntry) == ctypes.sizeof(_native.WnEntry) + 15 * 8 + 2 * 4
