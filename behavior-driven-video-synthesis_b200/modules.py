@@ -193,9 +193,13 @@ class WeightBank:
             wd_off += k * cout_k
         self._w = torch.zeros(w_off, dtype=torch.bfloat16, device=device)
         self._wd = torch.zeros(wd_off if with_wd else 0, dtype=torch.bfloat16, device=device)
-        # tile-major copies (same offsets; only the slots with >= 64 channels per source / per tap use theirs)
-        self._wt = torch.zeros(w_off, dtype=torch.bfloat16, device=device)
-        self._wdt = torch.zeros(wd_off if with_wd else 0, dtype=torch.bfloat16, device=device)
+        # Tile-major pre-swizzled copies (1-D bulk weight loads, vub_wn_entry.w_tiled).  Measured neutral in every
+        # kernel although a bulk copy is 1.7x cheaper for the TMA unit than a tensor box (profiles/r01_exp_bulk.log):
+        # the weight tile is not what bounds them.  Opt-in (VUB_TILED_WEIGHTS=1) so that the default path does not
+        # carry a second copy of the weights.
+        tiled = os.environ.get("VUB_TILED_WEIGHTS", "0") == "1"
+        self._wt = torch.zeros(w_off if tiled else 0, dtype=torch.bfloat16, device=device)
+        self._wdt = torch.zeros(wd_off if (with_wd and tiled) else 0, dtype=torch.bfloat16, device=device)
         self._with_wd = with_wd
         self._scale = torch.zeros(s_off, dtype=torch.float32, device=device)
         self._shift = torch.zeros(s_off, dtype=torch.float32, device=device)
@@ -209,8 +213,8 @@ class WeightBank:
             sh = self._shift[so:so + cpad]
             taps = first.kernel_size ** 2
             wd = self._wd[wdo:wdo + k * cout_k].view(nsrc * c_src, taps * cout_k) if with_wd else None
-            wt = self._wt[wo:wo + cpad * k] if c_src % 64 == 0 else None
-            wdt = self._wdt[wdo:wdo + k * cout_k] if (with_wd and cout_k % 64 == 0) else None
+            wt = self._wt[wo:wo + cpad * k] if (tiled and c_src % 64 == 0) else None
+            wdt = self._wdt[wdo:wdo + k * cout_k] if (tiled and with_wd and cout_k % 64 == 0) else None
             self._views[id(first)] = ConvWeights(w, sc, sh, cout, cpad, nsrc, c_src, first.kernel_size,
                                                  first.stride, wd=wd, cout_k=cout_k, slot=si, w_tiled=wt, wd_tiled=wdt)
             r = 0

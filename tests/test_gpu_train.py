@@ -155,3 +155,29 @@ def test_no_grad_forward_is_unchanged_by_training_mode(golden):
     b = m(x.cuda(), c.cuda(), eps=[e.cuda() for e in eps])[0]
     assert not a.requires_grad and b.requires_grad
     assert torch.equal(a, b.detach())
+
+
+def test_tile_major_weights_give_identical_results(golden, monkeypatch):
+    """VUB_TILED_WEIGHTS=1: weight tiles fetched with 1-D bulk copies from the pre-swizzled tile-major copies
+    (vub_wn_entry.w_tiled / wd_tiled) — same operands, so forward and gradients must be bit-identical."""
+    fx = golden("tiny30")
+    cfg = fx["config"]
+    x, c, eps, _ = O.make_inputs(cfg, cfg["batch"])
+    target = O.det_uniform("target", (cfg["batch"], 3, cfg["spatial_size"], cfg["spatial_size"]))
+    results = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("VUB_TILED_WEIGHTS", flag)
+        m, _ = build(cfg)
+        loss, grads = our_loss_and_grads(m, x, c, eps, target)
+        bank = m._bank(with_wd=True)
+        assert (bank._wt.numel() > 0) == (flag == "1")
+        results.append((loss, grads))
+    assert results[0][0] == results[1][0]
+    for k, g in results[0][1].items():
+        if g is None:
+            assert results[1][1][k] is None
+        elif k.startswith(("eu.nin.", "du.nin.")):
+            # the stems' weight gradient accumulates with float atomics: not bit-reproducible run to run
+            torch.testing.assert_close(g, results[1][1][k], rtol=1e-4, atol=1e-6)
+        else:
+            assert torch.equal(g, results[1][1][k]), k
