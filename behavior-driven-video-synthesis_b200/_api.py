@@ -5,6 +5,7 @@ from .losses import compute_kl_with_prior, kl_loss
 from .modules import (Act, DepthToSpace, Downsample, IDAct, NormConv2d, SpaceToDepth, Upsample, VunetRNB,
                       WeightBank, to_act)
 from .optim import FusedAdam
+from .training import GraphedTrainStep
 from .validation import fp32_validation
 from .vunets import DecDownAlter, DecUp, EncDownAlter, EncUp, VunetAlter
 
@@ -12,5 +13,5 @@ __all__ = [
     "VunetAlter", "EncUp", "EncDownAlter", "DecUp", "DecDownAlter",
     "NormConv2d", "VunetRNB", "Downsample", "Upsample", "DepthToSpace", "SpaceToDepth", "IDAct",
     "compute_kl_with_prior", "kl_loss", "Act", "to_act", "WeightBank", "build_native",
-    "fp32_validation", "FusedAdam",
+    "fp32_validation", "FusedAdam", "GraphedTrainStep",
 ]

@@ -43,6 +43,7 @@ EXPORTED_SYMBOLS = (
     "vub_conv_wgrad_splits",
     "vub_wn_bwd",
     "vub_adam_wn_step",
+    "vub_adam_wn_step_dev",
     "vub_stem_bwd",
     "vub_latent_bwd",
 )
@@ -266,6 +267,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.vub_conv_wgrad.argtypes = [C.POINTER(WgradDesc), vp]
     lib.vub_conv_fwd_elu_in_ok.restype = C.c_int
     lib.vub_conv_fwd_elu_in_ok.argtypes = [i32] * 7
+    lib.vub_adam_wn_step_dev.restype = C.c_int
+    lib.vub_adam_wn_step_dev.argtypes = [vp, i32, i32, C.c_float, C.c_float, C.c_float, vp, vp]
     lib.vub_adam_wn_step.restype = C.c_int
     lib.vub_adam_wn_step.argtypes = [vp, i32, i32, C.c_float, C.c_float, C.c_float, i32, vp]
     lib.vub_wn_bwd.restype = C.c_int

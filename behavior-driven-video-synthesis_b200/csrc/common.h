@@ -1,5 +1,7 @@
 // Host-side helpers shared by the C-ABI launchers: error reporting and TMA descriptor encoding.
 #pragma once
+#include <cstdlib>
+#include <cstring>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -17,6 +19,29 @@ void clear_error();
 
 // Returns 0 when the pending launch error state is clean, else the cudaError_t (and records it).
 int check_launch(const char* what);
+
+// Launches `kernel(params)` with the programmatic-stream-serialization attribute (programmatic dependent launch):
+// the kernel may begin its prologue while its predecessor in the stream is still running and MUST execute
+// `pdl_wait()` (ptx.cuh) before it touches anything a predecessor wrote.  VUB_PDL=0 falls back to plain launches.
+template <class Params>
+inline int launch_pdl(void (*kernel)(Params), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const Params& kp,
+                      const char* what) {
+  static const bool pdl = !(getenv("VUB_PDL") && getenv("VUB_PDL")[0] == '0');
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, kernel, kp);
+  if (le != cudaSuccess) return fail(static_cast<int>(le), "%s launch: %s", what, cudaGetErrorString(le));
+  return check_launch(what);
+}
 
 inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 inline int ilog2(int v) {

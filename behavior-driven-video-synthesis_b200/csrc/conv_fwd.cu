@@ -99,6 +99,10 @@ __global__ void __launch_bounds__(kConvThreads)
   const int S = p.stages;
   const int KS = p.nsrc * p.ntaps * p.cblocks;
 
+  // This kernel serves the small maps, where a launch is ~10 us of mostly latency and ~45 of them run back to
+  // back: let the next kernel's CTAs start their prologue now, and do ours (barriers, TMEM, descriptor fetch)
+  // before waiting for the previous kernel's results.
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA[0]);
     tma_prefetch_desc(&p.tmB);
@@ -115,6 +119,7 @@ __global__ void __launch_bounds__(kConvThreads)
     tmem_alloc<TMEM_COLS>(&tmem_base_slot);
     tmem_relinquish();
   }
+  pdl_wait();  // everything below may read what the previous kernel(s) wrote (activations, prepared weights)
   for (int i = threadIdx.x; i < BN; i += kConvThreads) {
     s_scale[i] = p.ep.scale[n_tile * BN + i];
     s_shift[i] = p.ep.shift[n_tile * BN + i];
@@ -289,8 +294,7 @@ static int launch_conv(const ConvKParams& kp, dim3 grid, cudaStream_t stream) {
     if (smem < kStaging) smem = kStaging;  // the epilogue reuses the (then idle) pipeline stages
   }
   smem += 1024;
-  conv_fwd_kernel<BN, BKC><<<grid, kConvThreads, smem, stream>>>(kp);
-  return check_launch("conv_fwd");
+  return launch_pdl(conv_fwd_kernel<BN, BKC>, grid, dim3(kConvThreads), smem, stream, kp, "conv_fwd");
 }
 
 bool conv_rows_applicable(const vub_conv_desc* d);            // conv_rows.cu

@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(kTilesThreads, 1)
   const int KS = p.n_ksteps;
   uint8_t* staging = smem + S * STAGE_BYTES;  // [8 epilogue warps][stage_tiles][32][GW*2+16]
 
+  pdl_launch_dependents();  // programmatic dependent launch: see launch_pdl (common.h)
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA[0]);
     tma_prefetch_desc(&p.tmB);
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(kTilesThreads, 1)
     tmem_alloc<TMEM_COLS>(&tmem_base_slot);
     tmem_relinquish();
   }
+  pdl_wait();  // below: reads of what earlier kernels wrote
   for (int i = threadIdx.x; i < p.n_total; i += kTilesThreads) {
     s_scale[i] = p.ep[0].scale != nullptr ? p.ep[0].scale[i] : 1.0f;
     s_shift[i] = p.ep[0].shift != nullptr ? p.ep[0].shift[i] : 0.0f;
@@ -260,8 +262,7 @@ static int launch_tiles_t(const TilesKParams& kp, int grid, size_t smem, cudaStr
   if (attr_err != cudaSuccess)
     return fail(static_cast<int>(attr_err), "cudaFuncSetAttribute(conv_tiles<%d,%d>): %s", BN, BKC,
                 cudaGetErrorString(attr_err));
-  conv_tiles_kernel<BN, BKC, CONTIG><<<grid, kTilesThreads, smem, stream>>>(kp);
-  return check_launch("conv_tiles");
+  return launch_pdl(conv_tiles_kernel<BN, BKC, CONTIG>, dim3(grid), dim3(kTilesThreads), smem, stream, kp, "conv_tiles");
 }
 
 template <int BN, int BKC>

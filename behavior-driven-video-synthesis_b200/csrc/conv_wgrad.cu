@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
   uint8_t* ones = smem;                 // 2 KB of bf16 1.0
   uint8_t* ring = smem + kWgOnesBytes;  // [S][stage_pitch]
 
+  pdl_launch_dependents();  // programmatic dependent launch: see launch_pdl (common.h)
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA[0]);
     tma_prefetch_desc(&p.tmB[0]);
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // below: reads of what earlier kernels wrote (dy, x) and writes to the shared partial workspace
   const uint32_t tmem_base = tmem_base_slot;
   const int n_cols = nb * ndw * p.cb;  // D columns of this CTA (the ones block follows at column n_cols)
 
@@ -542,6 +544,6 @@ extern "C" int vub_conv_wgrad(const vub_wgrad_desc* d, void* stream_v) {
   if (attr_err != cudaSuccess)
     return fail(static_cast<int>(attr_err), "cudaFuncSetAttribute(conv_wgrad): %s", cudaGetErrorString(attr_err));
   const int grid = kp.n_groups * kp.n_mtiles * kp.n_split;
-  conv_wgrad_kernel<<<grid, kWgThreads, smem, static_cast<cudaStream_t>(stream_v)>>>(kp);
-  return check_launch("conv_wgrad");
+  return launch_pdl(conv_wgrad_kernel, dim3(grid), dim3(kWgThreads), smem, static_cast<cudaStream_t>(stream_v), kp,
+                    "conv_wgrad");
 }

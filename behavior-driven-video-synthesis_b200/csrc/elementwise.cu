@@ -146,10 +146,17 @@ __device__ __forceinline__ float adam_update(float p, float g, float& m, float& 
   return p - step_size * m / (sqrtf(s) * inv_sqrt_bc2 + eps);
 }
 
+__global__ void adam_step_incr_kernel(int32_t* step) { *step += 1; }
+
 __global__ void __launch_bounds__(kWnThreads)
     adam_wn_kernel(const vub_adam_entry* __restrict__ table, int n_entries, float b1, float b2, float eps, float bc1,
-                   float inv_sqrt_bc2) {
+                   float inv_sqrt_bc2, const int32_t* __restrict__ step_dev) {
   __shared__ float red[32];
+  if (step_dev != nullptr) {  // step count lives on the device (CUDA-graph replays): bias corrections computed here
+    const float t = static_cast<float>(*step_dev);
+    bc1 = 1.0f - powf(b1, t);
+    inv_sqrt_bc2 = 1.0f / sqrtf(1.0f - powf(b2, t));
+  }
   const int row = blockIdx.x;
   int lo = 0, hi = n_entries - 1;
   while (lo < hi) {
@@ -416,8 +423,20 @@ extern "C" int vub_adam_wn_step(const vub_adam_entry* table_dev, int32_t n_entri
   const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
   const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
   adam_wn_kernel<<<total_rows, kWnThreads, 0, static_cast<cudaStream_t>(stream)>>>(table_dev, n_entries, beta1, beta2, eps,
-                                                                                  bc1, 1.0f / sqrtf(bc2));
+                                                                                  bc1, 1.0f / sqrtf(bc2), nullptr);
   return check_launch("adam_wn_step");
+}
+
+extern "C" int vub_adam_wn_step_dev(const vub_adam_entry* table_dev, int32_t n_entries, int32_t total_rows, float beta1,
+                                    float beta2, float eps, int32_t* step_dev, void* stream) {
+  clear_error();
+  if (!table_dev || !step_dev) return fail(VUB_E_NULL, "adam_wn_step_dev: table or step counter is NULL");
+  if (n_entries <= 0 || total_rows <= 0) return fail(VUB_E_SHAPE, "adam_wn_step_dev: empty table");
+  if (!(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f)) return fail(VUB_E_SHAPE, "adam_wn_step_dev: betas");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  adam_step_incr_kernel<<<1, 1, 0, s>>>(step_dev);
+  adam_wn_kernel<<<total_rows, kWnThreads, 0, s>>>(table_dev, n_entries, beta1, beta2, eps, 0.f, 0.f, step_dev);
+  return check_launch("adam_wn_step_dev");
 }
 
 extern "C" int vub_stem_fwd(const float* x_nchw, const float* v, const float* g, const float* gamma,

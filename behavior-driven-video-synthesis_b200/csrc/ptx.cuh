@@ -259,6 +259,13 @@ __device__ __forceinline__ float elu1(float v) {
   return v > 0.f ? v : e;
 }
 
+// Programmatic dependent launch: `pdl_launch_dependents` lets the next kernel in the stream (if it was launched with
+// the programmatic-stream-serialization attribute) start its prologue while this grid is still running;
+// `pdl_wait` blocks until every prerequisite grid has COMPLETED and its memory is visible — it must precede the
+// first access to anything a predecessor wrote.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+
 // Explicit shared-space 128-bit accesses (keeps ptxas from falling back to generic LD/ST when a
 // shared pointer flows through selects).
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {

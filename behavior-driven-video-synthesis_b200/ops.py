@@ -51,6 +51,8 @@ _LIB.define(
 )
 _LIB.define("wn_bwd(Tensor table, int n_entries, int total_rows, bool accumulate) -> ()")
 _LIB.define("adam_wn_step(Tensor table, int n_entries, int total_rows, float beta1, float beta2, float eps, int step) -> ()")
+_LIB.define("adam_wn_step_dev(Tensor table, int n_entries, int total_rows, float beta1, float beta2, float eps, "
+            "Tensor(a!) step) -> ()")
 _LIB.define("stem_bwd(Tensor x, Tensor dy, Tensor(a!) gt, Tensor(b!) dy_sum) -> ()")
 _LIB.define("latent_bwd(Tensor logstd, Tensor? eps, Tensor? d_mu, Tensor? d_ls, Tensor? dz) -> Tensor")
 _LIB.define("nchw_to_nhwc_pad(Tensor x, int c_pad) -> Tensor")
@@ -344,6 +346,15 @@ def _adam_wn_step_cuda(table, n_entries, total_rows, beta1, beta2, eps, step) ->
                     step, _stream()), "vub_adam_wn_step")
 
 
+def _adam_wn_step_dev_cuda(table, n_entries, total_rows, beta1, beta2, eps, step) -> None:
+    if step.dtype != torch.int32 or step.numel() != 1:
+        raise ValueError("adam_wn_step_dev: step must be a 1-element int32 tensor")
+    global LAUNCHES
+    LAUNCHES += 1  # the counter increment is a second (1-thread) launch
+    N.check(_launch("adam_wn_step", N.lib().vub_adam_wn_step_dev, table.data_ptr(), n_entries, total_rows, beta1, beta2,
+                    eps, step.data_ptr(), _stream()), "vub_adam_wn_step_dev")
+
+
 def _stem_bwd_cuda(x, dy, gt, dy_sum) -> None:
     if x.dtype != torch.float32 or x.dim() != 4 or not x.is_contiguous():
         raise ValueError("stem_bwd: x must be contiguous NCHW fp32")
@@ -447,6 +458,7 @@ _LIB.impl("conv_dgrad", _conv_dgrad_cuda, "CUDA")
 _LIB.impl("conv_wgrad", _conv_wgrad_cuda, "CUDA")
 _LIB.impl("wn_bwd", _wn_bwd_cuda, "CUDA")
 _LIB.impl("adam_wn_step", _adam_wn_step_cuda, "CUDA")
+_LIB.impl("adam_wn_step_dev", _adam_wn_step_dev_cuda, "CUDA")
 _LIB.impl("stem_bwd", _stem_bwd_cuda, "CUDA")
 _LIB.impl("latent_bwd", _latent_bwd_cuda, "CUDA")
 _LIB.impl("nchw_to_nhwc_pad", _nchw_to_nhwc_pad_cuda, "CUDA")
@@ -570,6 +582,11 @@ def wn_bwd(table: torch.Tensor, n_entries: int, total_rows: int, accumulate: boo
 def adam_wn_step(table: torch.Tensor, n_entries: int, total_rows: int, beta1: float, beta2: float, eps: float,
                  step: int) -> None:
     _ops.adam_wn_step(table, n_entries, total_rows, beta1, beta2, eps, step)
+
+
+def adam_wn_step_dev(table: torch.Tensor, n_entries: int, total_rows: int, beta1: float, beta2: float, eps: float,
+                     step: torch.Tensor) -> None:
+    _ops.adam_wn_step_dev(table, n_entries, total_rows, beta1, beta2, eps, step)
 
 
 def stem_bwd(x, dy, gt, dy_sum) -> None:

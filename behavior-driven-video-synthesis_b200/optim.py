@@ -96,6 +96,9 @@ class FusedAdam:
             self._s[id(p)] = self._exp_avg_sq[o:o + p.numel()].view(p.shape)
             o += p.numel()
         self._step = 0
+        # the step count the kernel uses lives on the device (bias corrections computed in-kernel), so the launch
+        # arguments are the same every step and a captured CUDA graph of the step can be replayed
+        self._step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         self._stepped = set()  # id(param) of every parameter that has Adam state
         self._key = None
         self._table = None
@@ -158,7 +161,7 @@ class FusedAdam:
         self._step += 1
         b1, b2 = self.defaults["betas"]
         table, n, rows = self._table
-        ops.adam_wn_step(table, n, rows, b1, b2, self.defaults["eps"], self._step)
+        ops.adam_wn_step_dev(table, n, rows, b1, b2, self.defaults["eps"], self._step_dev)
         # parameters were written through raw pointers: autograd version counters did not move, so tell every
         # other cache of prepared weights (sub-module banks, the fp32 validation bank) that they are stale; the
         # training bank was re-emitted by this very launch.
@@ -215,4 +218,5 @@ class FusedAdam:
         if len(steps) > 1:
             raise NotImplementedError("FusedAdam keeps one step counter; the checkpoint has several")
         self._step = steps.pop() if steps else 0
+        self._step_dev.fill_(self._step)
         self._key = None

@@ -368,3 +368,129 @@ class BucketReducer:
         if self._stream is not None:
             torch.cuda.current_stream().wait_stream(self._stream)
         self.bytes_per_step, self.bytes_last = self.bytes_last, 0
+
+
+# --------------------------------------------------------------------------------------------------
+class GraphedTrainStep:
+    """One training step — forward, loss, backward (incl. the data-parallel gradient exchange) and the optimizer
+    step — captured in ONE CUDA graph and replayed.
+
+    Why: the step is ~300 launches, many of them 10 us kernels on the small maps, and the Python / ctypes path
+    costs more host time per launch than those kernels run — measured with ``tools/train_host_overhead.py``, the
+    host's enqueue time EQUALS the step time (the GPU is starved).  Replay removes the host from the loop.
+
+    ``loss_fn(imgs, means, logstds, *extra) -> scalar`` is traced once; ``extra`` are additional static inputs
+    (the target image).  The optimizer must be :class:`~bdvs_b200.FusedAdam` (its step count lives on the device,
+    so the captured launch is valid for every step).  Warm-up steps needed before capture run on a snapshot: the
+    parameters and optimizer state are restored afterwards.  Replaces the body of the reference's ``train_fn``
+    (experiments/shape_and_pose_net.py:360-466, minus logging)::
+
+        step = GraphedTrainStep(vunet, opt, loss_fn, x, c, target)
+        for x, c, target in loader:
+            loss = step(x, c, target)        # copies into the static inputs, replays; ``loss`` is a device scalar
+    """
+
+    def __init__(self, model, optimizer, loss_fn, *example_inputs: torch.Tensor, warmup: int = 3,
+                 eps: Optional[Sequence[torch.Tensor]] = None):
+        """``eps``: optional static latent-noise tensors (``model(x, c, eps=...)``; copy new noise into
+        ``self.static_eps`` between steps); default: drawn inside the graph by torch's graph-safe generator."""
+        from .modules import bump_weight_epoch
+        from .optim import FusedAdam
+
+        if not isinstance(optimizer, FusedAdam):
+            raise TypeError("GraphedTrainStep needs bdvs_b200.FusedAdam (device-side step count)")
+        if len(example_inputs) < 2:
+            raise ValueError("GraphedTrainStep(model, optimizer, loss_fn, x, c, *extra)")
+        self.model, self.opt, self.loss_fn = model, optimizer, loss_fn
+        self.static_in = [t.detach().clone() for t in example_inputs]
+        self.static_eps = None if eps is None else [t.detach().clone() for t in eps]
+        params = list(model.parameters())
+        snap = [p.detach().clone() for p in params]
+        m_snap, s_snap, step_snap = optimizer._exp_avg.clone(), optimizer._exp_avg_sq.clone(), optimizer._step
+        stepped_snap = set(optimizer._stepped)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):  # allocates every cache (weight bank, gradient bank, optimizer table)
+                self._one_step()
+        cur.wait_stream(side)
+        with torch.no_grad():
+            for p, s in zip(params, snap):
+                p.copy_(s)
+            optimizer._exp_avg.copy_(m_snap)
+            optimizer._exp_avg_sq.copy_(s_snap)
+        optimizer._step = step_snap
+        optimizer._step_dev.fill_(step_snap)
+        optimizer._stepped = stepped_snap
+        bump_weight_epoch()
+        model._bank(with_wd=True).refresh(with_wd=True)  # re-prepare the restored weights OUTSIDE the graph
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_loss = self._one_step()
+        optimizer._step = step_snap  # capture ran the Python side of step() once without executing a kernel
+        self._live_ids = {id(p) for p in optimizer._params if p.grad is not None}
+
+    # ---- host-resident batches: upload batch k+1 while step k runs ------------------------------------
+    def prefetch(self, *host_inputs: torch.Tensor) -> None:
+        """Enqueue the host -> device copy of the NEXT batch (pinned tensors) on a copy stream; it overlaps the
+        step that is running.  Pair every call with one :meth:`run_prefetched`."""
+        if len(host_inputs) != len(self.static_in):
+            raise ValueError(f"expected {len(self.static_in)} inputs")
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream()
+            self._staging = [[torch.empty_like(t) for t in self.static_in] for _ in range(2)]
+            self._staged_ev = [None, None]   # upload of set k finished
+            self._drained_ev = [None, None]  # set k has been copied into the static inputs
+            self._put, self._get = 0, 0
+        k = self._put & 1
+        with torch.cuda.stream(self._copy_stream):
+            if self._drained_ev[k] is not None:
+                self._copy_stream.wait_event(self._drained_ev[k])
+            for dst, src in zip(self._staging[k], host_inputs):
+                dst.copy_(src, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._staged_ev[k] = ev
+        self._put += 1
+
+    def run_prefetched(self) -> torch.Tensor:
+        """One step on the oldest prefetched batch."""
+        if not hasattr(self, "_copy_stream") or self._get >= self._put:
+            raise RuntimeError("run_prefetched() without a pending prefetch()")
+        k = self._get & 1
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._staged_ev[k])
+        for dst, src in zip(self.static_in, self._staging[k]):
+            dst.copy_(src, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self._drained_ev[k] = ev
+        self._get += 1
+        return self(*self.static_in)
+
+    def _one_step(self) -> torch.Tensor:
+        x, c, *extra = self.static_in
+        if self.static_eps is None:
+            imgs, means, logstds, _ = self.model(x, c)
+        else:
+            imgs, means, logstds, _ = self.model(x, c, eps=self.static_eps)
+        loss = self.loss_fn(imgs, means, logstds, *extra)
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        self.opt.step()
+        return loss.detach()
+
+    def __call__(self, *inputs: torch.Tensor) -> torch.Tensor:
+        if len(inputs) != len(self.static_in):
+            raise ValueError(f"expected {len(self.static_in)} inputs")
+        for dst, src in zip(self.static_in, inputs):
+            if src is not dst:
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        self.opt._step += 1
+        if self._live_ids is not None:
+            self.opt._stepped.update(self._live_ids)
+            self._live_ids = None
+        return self.static_loss

@@ -190,30 +190,64 @@ def run_train_section(args, device, world, rank, barrier, peaks):
         opt.step()
         return loss
 
-    K = max(5, args.steps // 5)
+    K = max(10, args.steps // 2)
     W = 3
     for _ in range(W):
         step(x, c, target)
+    barrier()
+    # The step is ~300 launches and host-bound when issued launch by launch (tools/train_host_overhead.py): the
+    # package's GraphedTrainStep captures forward + loss + backward + all-reduce + optimizer in one CUDA graph.
+    # VUB_BENCH_TRAIN_GRAPH=0 times the eager step instead.
+    graphed, graph_err = None, None
+    if os.environ.get("VUB_BENCH_TRAIN_GRAPH", "1") != "0":
+        try:
+            n0 = ops.LAUNCHES
+            graphed = B.GraphedTrainStep(
+                model, opt, lambda imgs, means, logstds, tt: torch.mean((imgs - tt) ** 2) + 1e-3 * B.compute_kl_with_prior(means, logstds),
+                x, c, target)
+            launches_per_step = (ops.LAUNCHES - n0) // 4  # 3 warm-up steps + 1 captured step
+        except Exception as exc:  # noqa: BLE001 - report and fall back to the eager step
+            graph_err = f"{type(exc).__name__}: {exc}"[:200]
+            graphed = None
+    run = (lambda xx, cc, tt: graphed(xx, cc, tt)) if graphed is not None else step
+    for _ in range(2):
+        run(x, c, target)
     barrier()
     before = ops.LAUNCHES
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(K):
-        loss = step(x, c, target)
+        loss = run(x, c, target)
     ev1.record()
     barrier()
-    launches = ops.LAUNCHES - before
+    launches = launches_per_step * K if graphed is not None else ops.LAUNCHES - before
     ms = ev0.elapsed_time(ev1)
     # e2e: inputs and target from pinned host memory every step, loss read back every step
-    for _ in range(2):
-        step(x.copy_(xh, non_blocking=True), c.copy_(ch, non_blocking=True), target.copy_(th, non_blocking=True))
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K):
-        loss = step(x.copy_(xh, non_blocking=True), c.copy_(ch, non_blocking=True), target.copy_(th, non_blocking=True))
-        loss_h.copy_(loss.detach().reshape(1), non_blocking=True)
-    e1.record()
+    if graphed is not None:
+        # the package's own pipelined path: batch k+1 is uploaded on a copy stream while step k runs
+        graphed.prefetch(xh, ch, th)
+        for _ in range(2):
+            graphed.prefetch(xh, ch, th)
+            graphed.run_prefetched()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            graphed.prefetch(xh, ch, th)
+            loss = graphed.run_prefetched()
+            loss_h.copy_(loss.detach().reshape(1), non_blocking=True)
+        e1.record()
+        graphed.run_prefetched()  # drain the last prefetch (outside the timed region)
+    else:
+        for _ in range(2):
+            run(x.copy_(xh, non_blocking=True), c.copy_(ch, non_blocking=True), target.copy_(th, non_blocking=True))
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            loss = run(x.copy_(xh, non_blocking=True), c.copy_(ch, non_blocking=True), target.copy_(th, non_blocking=True))
+            loss_h.copy_(loss.detach().reshape(1), non_blocking=True)
+        e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
     if world > 1:
@@ -258,6 +292,8 @@ def run_train_section(args, device, world, rank, barrier, peaks):
                 "h2d_bytes_per_step": (xh.numel() + ch.numel() + th.numel()) * 4, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / K},
         "gpu_launches": launches,
+        "cuda_graph": graphed is not None,
+        "cuda_graph_error": graph_err,
         "allreduce_bytes_per_step": getattr(red, "bytes_per_step", 0),
         "conv_tflops_per_gpu": round(TRAIN_GFLOP_PER_SAMPLE * Bt * K / ms, 2),
         "frac_tensor_peak_sustained": round(TRAIN_GFLOP_PER_SAMPLE * Bt * K / ms / peaks["bf16_tflops_sustained"], 4),

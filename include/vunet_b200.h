@@ -317,6 +317,11 @@ typedef struct vub_adam_entry {
 
 int vub_adam_wn_step(const vub_adam_entry* table_dev, int32_t n_entries, int32_t total_rows, float beta1, float beta2,
                      float eps, int32_t step, void* stream);
+/* Same with the step count in device memory: increments *step_dev, then uses it for the bias corrections — the
+ * launch arguments no longer change from step to step, so a captured CUDA graph of the training step can be
+ * replayed (training.GraphedTrainStep). */
+int vub_adam_wn_step_dev(const vub_adam_entry* table_dev, int32_t n_entries, int32_t total_rows, float beta1,
+                         float beta2, float eps, int32_t* step_dev, void* stream);
 
 /*
  * Backward of the stem (first 1x1 NormConv2d on the NCHW fp32 input, vub_stem_fwd): correlation of the

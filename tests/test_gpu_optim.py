@@ -134,3 +134,44 @@ def test_fused_adam_invalidates_other_weight_caches():
     assert any(not torch.equal(p, q) for p, q in zip(before, after))
     for p, q in zip(after, fresh):
         assert torch.equal(p, q)
+
+
+def test_graphed_train_step_matches_eager_steps():
+    """training.GraphedTrainStep (whole step in one CUDA graph, device-side Adam step count) against the same steps
+    issued launch by launch."""
+    import bdvs_b200
+    a = _model(11)
+    b = copy.deepcopy(a)
+    g = torch.Generator(device="cuda:0").manual_seed(4)
+    x = torch.randn(4, 3, 32, 32, device="cuda:0", generator=g).clamp(-1, 1)
+    c = torch.randn(4, 3, 32, 32, device="cuda:0", generator=g).clamp(-1, 1)
+    tgt = torch.randn(4, 3, 32, 32, device="cuda:0", generator=g).clamp(-1, 1)
+    eps = _eps(a, x, c)
+
+    def loss_fn(imgs, means, logstds, target):
+        return ((imgs - target) ** 2).mean() + 1e-3 * bdvs_b200.compute_kl_with_prior(means, logstds)
+
+    opt_a = bdvs_b200.FusedAdam(_groups(a), lr=2e-4, betas=(0.5, 0.9), model=a)
+    opt_b = bdvs_b200.FusedAdam(_groups(b), lr=2e-4, betas=(0.5, 0.9), model=b)
+    losses_a = []
+    for _ in range(4):
+        imgs, means, logstds, _ = a(x, c, eps=eps)
+        loss = loss_fn(imgs, means, logstds, tgt)
+        opt_a.zero_grad()
+        loss.backward()
+        opt_a.step()
+        losses_a.append(float(loss))
+    before = [p.detach().clone() for p in b.parameters()]
+    step = bdvs_b200.GraphedTrainStep(b, opt_b, loss_fn, x, c, tgt, eps=eps)
+    for p, q in zip(b.parameters(), before):   # warm-up ran on a snapshot
+        assert torch.equal(p, q)
+    assert opt_b._step == 0 and int(opt_b._step_dev) == 0
+    losses_b = [float(step(x, c, tgt)) for _ in range(4)]
+    assert opt_b._step == 4 and int(opt_b._step_dev) == 4
+    for la, lb in zip(losses_a, losses_b):
+        assert abs(la - lb) <= 1e-4 * abs(la), (losses_a, losses_b)
+    assert losses_b[-1] < losses_b[0]
+    for (n, pa), pb in zip(a.named_parameters(), b.parameters()):
+        torch.testing.assert_close(pa, pb, rtol=1e-4, atol=2e-6, msg=n)
+    sa, sb = opt_a.state_dict(), opt_b.state_dict()
+    assert set(sa["state"].keys()) == set(sb["state"].keys())
