@@ -18,6 +18,8 @@ Gradients flow from ``imgs``, ``means`` and ``logstds``; the ``activations`` lis
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -224,12 +226,31 @@ def run_backward(model, bank: WeightBank, tape: Tape, d_imgs: Optional[torch.Ten
     gb.zero()
     if d_imgs is not None and tape.img_slot is not None:
         tape.img_slot.grad = ops.nchw_to_nhwc_pad(d_imgs.float(), 32)
+    # The weight gradient and the data gradient of a conv are independent: wgrad runs on a second stream, so the
+    # small-map layers (10 us kernels that fill a fraction of the GPU) overlap pairwise and the tails of the large
+    # ones interleave.  VUB_BWD_STREAMS=1 keeps everything on one stream.
+    main = torch.cuda.current_stream()
+    two = os.environ.get("VUB_BWD_STREAMS", "2") != "1"
+    ws = None
+    if two:
+        ws = getattr(gb, "_wgrad_stream", None)
+        if ws is None or ws.device != main.device:
+            ws = torch.cuda.Stream(device=main.device)
+            gb._wgrad_stream = ws
+    pending: List[tuple] = []  # (dy kept alive, event after its wgrad): dy must not be recycled while wgrad reads it
+
+    def join_wgrads() -> None:
+        if ws is not None:
+            main.wait_stream(ws)
+        pending.clear()
+
     current = None
     for rec in reversed(tape.recs):
         kind = rec[0]
         owner = rec[1]._vub_owner if kind != "latent" else "ed"
         if owner != current:
             if current is not None:
+                join_wgrads()
                 gb.finish_owner(current)
                 if reducer is not None:
                     reducer.bucket_ready(current, gb.buckets.get(current))
@@ -240,8 +261,20 @@ def run_backward(model, bank: WeightBank, tape: Tape, d_imgs: Optional[torch.Ten
             if dy is None:
                 continue
             cw = bank.get(conv)
-            ops.conv_wgrad(dy, [a.pick(m) for a, m in srcs], gb.gt[id(conv)], gb.dy_sum[id(conv)], ksize=cw.ksize,
-                           stride=cw.stride, d2s=d2s)
+            if ws is not None:
+                ws.wait_stream(main)  # dy (and, the first time, the forward activations) are complete
+                with torch.cuda.stream(ws):
+                    ops.conv_wgrad(dy, [a.pick(m) for a, m in srcs], gb.gt[id(conv)], gb.dy_sum[id(conv)],
+                                   ksize=cw.ksize, stride=cw.stride, d2s=d2s)
+                    ev = torch.cuda.Event()
+                    ev.record(ws)
+                pending.append((dy, ev))
+                if len(pending) > 6:  # bound the gradients kept alive: the oldest wgrad has long finished
+                    main.wait_event(pending[0][1])
+                    pending.pop(0)
+            else:
+                ops.conv_wgrad(dy, [a.pick(m) for a, m in srcs], gb.gt[id(conv)], gb.dy_sum[id(conv)], ksize=cw.ksize,
+                               stride=cw.stride, d2s=d2s)
             dx, mask, add1, add2 = [], [], [], []
             for a, m in srcs:
                 existed = a.grad is not None
@@ -270,6 +303,7 @@ def run_backward(model, bank: WeightBank, tape: Tape, d_imgs: Optional[torch.Ten
                 continue
             r["ml_slot"].grad = ops.latent_bwd(r["logstd"], r["eps"], r["d_mu"], r["d_ls"], dz)
             r["z_act"].grad = None
+    join_wgrads()
     if current is not None:
         gb.finish_owner(current)
         if reducer is not None:
