@@ -217,6 +217,9 @@ class GradBank:
 
 
 # --------------------------------------------------------------------------------------------------
+_WGRAD_STREAMS: dict = {}  # one weight-gradient stream per device
+
+
 def run_backward(model, bank: WeightBank, tape: Tape, d_imgs: Optional[torch.Tensor], reducer=None) -> None:
     """Walk the tape in reverse; parameter gradients land in ``param.grad`` (views of flat buckets)."""
     gb: Optional[GradBank] = getattr(model, "_vub_grad_bank", None)
@@ -233,10 +236,9 @@ def run_backward(model, bank: WeightBank, tape: Tape, d_imgs: Optional[torch.Ten
     two = os.environ.get("VUB_BWD_STREAMS", "2") != "1"
     ws = None
     if two:
-        ws = getattr(gb, "_wgrad_stream", None)
-        if ws is None or ws.device != main.device:
-            ws = torch.cuda.Stream(device=main.device)
-            gb._wgrad_stream = ws
+        ws = _WGRAD_STREAMS.get(main.device)
+        if ws is None:
+            ws = _WGRAD_STREAMS[main.device] = torch.cuda.Stream(device=main.device)
     pending: List[tuple] = []  # (dy kept alive, event after its wgrad): dy must not be recycled while wgrad reads it
 
     def join_wgrads() -> None:

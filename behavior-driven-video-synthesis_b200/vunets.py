@@ -10,6 +10,8 @@ SURVEY.md App. B executed by sm_100a kernels; there is no torch conv and no CPU 
 """
 from __future__ import annotations
 
+import os
+
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -232,6 +234,9 @@ class DecDownAlter(nn.Module):
         return self._run(bank, acts, zs, training)
 
 
+_SIDE_STREAMS: dict = {}  # one side stream per device (not a module attribute: models are deep-copied / pickled)
+
+
 def _require_cuda(t: torch.Tensor) -> None:
     if not t.is_cuda:
         raise RuntimeError("vunet_b200 has no CPU path: inputs and the module must live on a CUDA device")
@@ -309,8 +314,7 @@ class VunetAlter(nn.Module):
         return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
     def _forward_impl(self, bank, x, c, eps):
-        _, hs_left, lat = self._encode(bank, x, eps, skip_dead=True, want_elu_mu=False)
-        gs = self.du._run(bank, c.float())
+        _keep, hs_left, lat, gs = self._encode_and_pose(bank, x, c, eps, want_elu_mu=False)
         imgs = self.dd._run(bank, gs, [r["z_act"] for r in lat], True)
         return imgs, lat, hs_left
 
@@ -319,6 +323,27 @@ class VunetAlter(nn.Module):
         hs_all = list(hs)
         es, lat = self.ed._run(bank, hs, eps=eps, skip_dead=skip_dead, want_elu_mu=want_elu_mu)
         return hs_all, hs, lat
+
+    def _encode_and_pose(self, bank, x, c, eps, want_elu_mu):
+        """``eu`` -> ``ed`` and ``du``.  ``ed`` (a chain of ~20 kernels on 4x4 .. 16x16 maps, each a few microseconds
+        on a fraction of the SMs) depends only on ``eu``; it runs on a second stream beside ``du``, whose large
+        kernels hide it.  VUB_FWD_STREAMS=1 keeps one stream."""
+        hs = self.eu._run(bank, x.float())
+        hs_all = list(hs)  # keeps eu's activations alive until the side stream has read them (ed pops from `hs`)
+        if os.environ.get("VUB_FWD_STREAMS", "2") == "1":
+            _, lat = self.ed._run(bank, hs, eps=eps, skip_dead=True, want_elu_mu=want_elu_mu)
+            gs = self.du._run(bank, c.float())
+            return hs_all, hs, lat, gs
+        main = torch.cuda.current_stream()
+        side = _SIDE_STREAMS.get(main.device)
+        if side is None:
+            side = _SIDE_STREAMS[main.device] = torch.cuda.Stream(device=main.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _, lat = self.ed._run(bank, hs, eps=eps, skip_dead=True, want_elu_mu=want_elu_mu)
+        gs = self.du._run(bank, c.float())
+        main.wait_stream(side)
+        return hs_all, hs, lat, gs
 
     def forward(self, x, c, eps: Optional[Sequence[torch.Tensor]] = None):
         """Returns ``(imgs, means, logstds, (hs, means, logstds))`` like the reference.  ``eps`` optionally
@@ -372,6 +397,5 @@ class VunetAlter(nn.Module):
         _require_cuda(x)
         _require_cuda(c)
         bank = self._bank()
-        _, _, lat = self._encode(bank, x, eps, skip_dead=True, want_elu_mu=True)
-        gs = self.du._run(bank, c.float())
+        _keep, _, lat, gs = self._encode_and_pose(bank, x, c, eps, want_elu_mu=True)
         return self.dd._run(bank, gs, [r["mu_act"] for r in lat], True)
