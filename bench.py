@@ -260,8 +260,13 @@ def run_train_section(args, device, world, rank, barrier, peaks):
     tk = []
     # every rank runs the instrumented step (it contains the gradient all-reduce); only rank 0 times it
     from bdvs_b200.profiler import KernelProfiler
-    with (KernelProfiler() if rank == 0 else contextlib.nullcontext()) as kp:
-        step(x, c, target)
+    # single-stream for this one step: with wgrad / ed on their second streams the per-kernel event brackets overlap
+    os.environ["VUB_BWD_STREAMS"] = os.environ["VUB_FWD_STREAMS"] = "1"
+    try:
+        with (KernelProfiler() if rank == 0 else contextlib.nullcontext()) as kp:
+            step(x, c, target)
+    finally:
+        del os.environ["VUB_BWD_STREAMS"], os.environ["VUB_FWD_STREAMS"]
     barrier()
     if rank == 0:
         prof = kp.summary()
@@ -455,8 +460,12 @@ def run_ours(args):
     with torch.no_grad():
         for _ in range(2):
             model.transfer(synth.x, synth.c)
-        with KernelProfiler() as kp:
-            model.transfer(synth.x, synth.c)
+        os.environ["VUB_FWD_STREAMS"] = "1"  # single stream: per-kernel event brackets must not overlap
+        try:
+            with KernelProfiler() as kp:
+                model.transfer(synth.x, synth.c)
+        finally:
+            del os.environ["VUB_FWD_STREAMS"]
         prof = kp.summary()
     total_kernel_ms = sum(r["ms"] for r in prof.values())
     kernels = []
