@@ -49,6 +49,7 @@ struct TilesKParams {
   const uint8_t* w_tiled;
   int w_rows;
   long long total_pix;  // CONTIG kernels: pixels of the output tensor
+  int d2s_w;            // CONTIG kernels: > 0 = DepthToSpace output, width of the conv's own output grid
 };
 
 // CONTIG: every tile is one contiguous run of the NHWC output (full-width tiles, stride 1, no DepthToSpace, bf16
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(kTilesThreads, 1)
         const long long left = p.total_pix - pix0;
         tile_epilogue_contig<BN, GW>(e, affine ? s_scale + n_tile * BN : nullptr, affine ? s_shift + n_tile * BN : nullptr,
                                      trow, t0, t1, t2, lane, ecol, pix0, left > 32 ? 32 : static_cast<int>(left),
-                                     &acc_empty[g], &acc_full[g], cnt & 1);
+                                     &acc_empty[g], &acc_full[g], cnt & 1, p.d2s_w);
       } else if constexpr (STAGED) {
         const bool affine = p.ep[0].scale != nullptr;  // data gradients run with the identity
         tile_epilogue_staged<BN, GW>(e, EpiGeom{p.tw, p.th, p.tw_log2, p.th_log2, p.batch},
@@ -352,11 +353,18 @@ int conv_tiles_launch(const TileJob& job, cudaStream_t stream) {
   const int grid = kp.total_tiles < n_sm ? kp.total_tiles : n_sm;
   // contiguous tiles: full-width pixel tiles written 1:1 (no shuffle, no scatter, bf16)
   bool contig = kp.tw == job.wout && !getenv("VUB_TILES_NO_CONTIG");
+  bool d2s_all = true;
+  const int gw_epi = bn >= 64 ? 64 : 32;
   for (int i = 0; i < n_epi; ++i) {
     const TileEpi& e = job.epi[i];
-    contig = contig && e.flags == 0 && e.pix_stride == 1 && e.pix_off_h == 0 && e.pix_off_w == 0 &&
-             e.out_h == job.hout && e.out_w == job.wout && e.out_f32 == nullptr;
+    const bool plain = e.flags == 0 && e.out_h == job.hout && e.out_w == job.wout;
+    // DepthToSpace: a warp's 32 pixels inside one image row, a channel group inside one quadrant
+    const bool d2s = e.flags == VUB_CONV_D2S && e.out_h == 2 * job.hout && e.out_w == 2 * job.wout && kp.tw >= 32 &&
+                     e.out_c % gw_epi == 0 && e.c_off == 0 && n_epi == 1;
+    d2s_all = d2s_all && d2s;
+    contig = contig && (plain || d2s) && e.pix_stride == 1 && e.pix_off_h == 0 && e.pix_off_w == 0 && e.out_f32 == nullptr;
   }
+  kp.d2s_w = (contig && d2s_all) ? job.wout : 0;
   kp.total_pix = (long long)job.batch * job.hout * job.wout;
 
 #define VUB_TILES_DISPATCH(BN_, BKC_) \

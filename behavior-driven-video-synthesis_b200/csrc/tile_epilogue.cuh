@@ -205,17 +205,37 @@ __device__ __forceinline__ void tile_epilogue_staged(const TileEpi& e, const Epi
 // per warp and tile and the kernels built on it (10 000 SASS instructions) spent 24 % of their warp stalls on
 // instruction fetch (ncu, 128->128 @64^2); it stays for the scattering / fp32 layouts.
 // `pix0`: index of this warp's first pixel in the output tensor; `n_valid`: pixels of this warp inside the tensor.
+// With VUB_CONV_D2S (`d2s_w` = width of the conv's own output grid, the warp's 32 pixels inside one image row, GW
+// channels inside one quadrant): the quadrant's pixels are every second pixel of one row of the shuffled tensor, so
+// the addressing stays linear with twice the row pitch.
 template <int BN, int GW>
 __device__ __forceinline__ void tile_epilogue_contig(const TileEpi& e, const float* s_scale, const float* s_shift,
                                                      uint32_t trow, uint32_t t0, uint32_t t1, uint32_t t2, int lane,
                                                      int ecol, long long pix0, int n_valid, uint64_t* acc_empty,
-                                                     uint64_t* acc_full, uint32_t acc_parity) {
+                                                     uint64_t* acc_full, uint32_t acc_parity, int d2s_w = 0) {
   constexpr int CPR = GW / 8;
-  const long long base = pix0 * e.out_c + e.c_off + ecol;  // element offset of (first pixel, first column of the tile)
-  const int oc = e.out_c;
+  const bool d2s = d2s_w > 0;
   const bool valid = lane < n_valid;
+  long long d2s_row = 0;  // D2S: index of output pixel (2h, 2w) of this warp's first pixel
+  if (d2s) {
+    const long long rowi = pix0 / d2s_w;  // n * H + h
+    const int w = static_cast<int>(pix0 - rowi * d2s_w);
+    d2s_row = (rowi * 2) * (2LL * d2s_w) + 2 * w;
+  }
 #pragma unroll 1
   for (int g0 = 0; g0 < BN; g0 += GW) {
+    // element offset of (first pixel, first column of this channel group) and the pitch between the warp's pixels
+    long long base;
+    int oc;
+    if (!d2s) {
+      oc = e.out_c;
+      base = pix0 * e.out_c + e.c_off + ecol;  // (g0 is added where the group is addressed)
+    } else {
+      const int col = ecol + g0;
+      const int qd = col / e.out_c, cp = col - qd * e.out_c;
+      oc = 2 * e.out_c;
+      base = (d2s_row + (qd >> 1) * (2LL * d2s_w) + (qd & 1)) * e.out_c + cp - g0;
+    }
     uint4 va[4], vm[4], vb[4];  // GW == 32: this lane's addend / mask / addend2 values
     if constexpr (GW == 32) {
 #pragma unroll
