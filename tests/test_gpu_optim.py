@@ -168,10 +168,14 @@ def test_graphed_train_step_matches_eager_steps():
     assert opt_b._step == 0 and int(opt_b._step_dev) == 0
     losses_b = [float(step(x, c, tgt)) for _ in range(4)]
     assert opt_b._step == 4 and int(opt_b._step_dev) == 4
+    # not bit-equal: the stem weight gradient accumulates with float atomics, and Adam turns a last-bit difference
+    # of a near-zero gradient into a visible fraction of lr
     for la, lb in zip(losses_a, losses_b):
-        assert abs(la - lb) <= 1e-4 * abs(la), (losses_a, losses_b)
+        assert abs(la - lb) <= 1e-3 * abs(la), (losses_a, losses_b)
     assert losses_b[-1] < losses_b[0]
     for (n, pa), pb in zip(a.named_parameters(), b.parameters()):
-        torch.testing.assert_close(pa, pb, rtol=1e-4, atol=2e-6, msg=n)
+        torch.testing.assert_close(pa, pb, rtol=1e-3, atol=1e-4, msg=n)   # 4 steps of lr = 2e-4 move a weight by <= 8e-4
+    moved = max(float((pa - q).abs().max()) for pa, q in zip(a.parameters(), before))
+    assert moved > 2e-4
     sa, sb = opt_a.state_dict(), opt_b.state_dict()
     assert set(sa["state"].keys()) == set(sb["state"].keys())
