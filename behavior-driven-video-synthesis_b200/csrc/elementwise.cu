@@ -41,14 +41,19 @@ __device__ __forceinline__ float block_sum(float v, float* red /*[32]*/) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kWnThreads = 128;
 
-// One output channel `co` of one conv: normalise its weight row and emit every prepared form.
-__device__ __forceinline__ void wn_emit_row(const vub_wn_entry& e, int co, float* red /*[32]*/) {
+// One output channel `co` of one conv: normalise its weight row and emit every prepared form.  `ss_partial` >= 0:
+// this thread's share of the row's sum of squares is already known (the fused Adam update computed it).
+__device__ __forceinline__ void wn_emit_row(const vub_wn_entry& e, int co, float* red /*[32]*/, float ss_partial = -1.f) {
   const int len = e.cin * e.ktaps;
   const float* v = e.v + (size_t)co * len;
   float ss = 0.f;
-  for (int i = threadIdx.x; i < len; i += kWnThreads) {
-    const float x = v[i];
-    ss = fmaf(x, x, ss);
+  if (ss_partial >= 0.f) {
+    ss = ss_partial;
+  } else {
+    for (int i = threadIdx.x; i < len; i += kWnThreads) {
+      const float x = v[i];
+      ss = fmaf(x, x, ss);
+    }
   }
   ss = block_sum(ss, red);
   const float inv = 1.0f / sqrtf(ss);
@@ -171,9 +176,12 @@ __global__ void __launch_bounds__(kWnThreads)
   const int len = e.wn.cin * e.wn.ktaps;
   const size_t off = (size_t)co * len;
   float* v = const_cast<float*>(e.wn.v) + off;
+  float ss = 0.f;  // this thread's share of ||v_new||^2 (same elements it would re-read in wn_emit_row)
   for (int i = threadIdx.x; i < len; i += kWnThreads) {
     float m = e.m_v[off + i], sq = e.s_v[off + i];
-    v[i] = adam_update(v[i], e.d_v[off + i], m, sq, b1, b2, step_size, inv_sqrt_bc2, eps);
+    const float vn = adam_update(v[i], e.d_v[off + i], m, sq, b1, b2, step_size, inv_sqrt_bc2, eps);
+    v[i] = vn;
+    ss = fmaf(vn, vn, ss);
     e.m_v[off + i] = m;
     e.s_v[off + i] = sq;
   }
@@ -191,7 +199,7 @@ __global__ void __launch_bounds__(kWnThreads)
     ss[t][co] = sq;
   }
   __syncthreads();  // the updated row and scalars are visible to the whole block
-  wn_emit_row(e.wn, co, red);
+  wn_emit_row(e.wn, co, red, ss);
 }
 
 // ------------------------------------------------------------------------------------------------
