@@ -127,7 +127,23 @@ class FusedAdam:
             entries.append(e)
         arr = (N.AdamEntry * len(entries))(*entries)
         host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
-        self._table = (host.to(self._exp_avg.device), len(entries), rows)
+        if self._table is not None and self._table[0].numel() == host.numel():
+            # same layout (e.g. only a learning rate changed): update IN PLACE, so a CUDA graph that captured the
+            # table's address (training.GraphedTrainStep) sees the new values
+            self._table[0].copy_(host)
+            self._table = (self._table[0], len(entries), rows)
+        else:
+            self._table = (host.to(self._exp_avg.device), len(entries), rows)
+        self._last_build = (live, bank)
+
+    def sync_lr(self) -> None:
+        """Push changed ``param_groups[i]["lr"]`` values into the device table without a step (the table is updated
+        in place; ``GraphedTrainStep`` calls this before every replay, ``step()`` does it implicitly)."""
+        lrs = tuple(float(g["lr"]) for g in self.param_groups)
+        if self._key is not None and lrs != self._key[-1] and getattr(self, "_last_build", None) is not None:
+            live, bank = self._last_build
+            self._build(live, bank)
+            self._key = self._key[:-1] + (lrs,)
 
     @torch.no_grad()
     def step(self, closure=None):

@@ -524,6 +524,7 @@ class GraphedTrainStep:
         for dst, src in zip(self.static_in, inputs):
             if src is not dst:
                 dst.copy_(src, non_blocking=True)
+        self.opt.sync_lr()  # learning-rate schedules: the optimizer's device table is updated in place
         self.graph.replay()
         self.opt._step += 1
         if self._live_ids is not None:

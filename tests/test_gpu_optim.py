@@ -154,7 +154,10 @@ def test_graphed_train_step_matches_eager_steps():
     opt_a = bdvs_b200.FusedAdam(_groups(a), lr=2e-4, betas=(0.5, 0.9), model=a)
     opt_b = bdvs_b200.FusedAdam(_groups(b), lr=2e-4, betas=(0.5, 0.9), model=b)
     losses_a = []
-    for _ in range(4):
+    for it in range(4):
+        if it == 2:  # a learning-rate schedule step, per group (shape_and_pose_net.py:311-319)
+            for g_ in opt_a.param_groups:
+                g_["lr"] = 5e-5 if g_["name"] == "dd" else 1e-4
         imgs, means, logstds, _ = a(x, c, eps=eps)
         loss = loss_fn(imgs, means, logstds, tgt)
         opt_a.zero_grad()
@@ -166,7 +169,12 @@ def test_graphed_train_step_matches_eager_steps():
     for p, q in zip(b.parameters(), before):   # warm-up ran on a snapshot
         assert torch.equal(p, q)
     assert opt_b._step == 0 and int(opt_b._step_dev) == 0
-    losses_b = [float(step(x, c, tgt)) for _ in range(4)]
+    losses_b = []
+    for it in range(4):
+        if it == 2:  # the captured graph must pick the new rates up (device table updated in place)
+            for g_ in opt_b.param_groups:
+                g_["lr"] = 5e-5 if g_["name"] == "dd" else 1e-4
+        losses_b.append(float(step(x, c, tgt)))
     assert opt_b._step == 4 and int(opt_b._step_dev) == 4
     # not bit-equal: the stem weight gradient accumulates with float atomics, and Adam turns a last-bit difference
     # of a near-zero gradient into a visible fraction of lr
