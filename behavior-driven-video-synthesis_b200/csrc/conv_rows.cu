@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
     for (int i = 0; i < R; ++i) {
       mbar_init(&slot_full[i], 1);
       mbar_init(&slot_empty[i], 1);
-      mbar_init(&slot_ready[i], 4);  // one arrival per transform warp
+      mbar_init(&slot_ready[i], 1);  // the transform warp that owns the row
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
@@ -375,44 +375,48 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
     // Elementwise and in place, so the TMA swizzle inside the slot does not matter: the box footprint is the
     // contiguous first (128 + 2*halo) * ROWB bytes of each source's buffer.
     if constexpr (!ELU_IN) return;
+    // Row per warp: warp tw transforms the input rows tw, tw + 4, ... on its own (16-byte chunks, 4 in flight per
+    // lane).  Splitting every row over the four warps instead made each of them pay the per-row overhead
+    // (barrier wait, fence.proxy.async, arrive): ~500 cycles per row against the ~256 the MUFU pipe needs.
     const int tw = warp - 10;
     constexpr int n_chunks = (kRowsW + 2 * halo) * ROWB / 16;
     int st = 0;
     uint32_t ph = 0;
+    int rowc = 0;  // running input-row counter
     RowWalker rw;
     for (rw.init(g_begin, g_end, p.ep.hout, p.batch); rw.valid(); rw.next_segment()) {
       const int n_in_rows = rw.seg_left + 2 * halo;
-      for (int ir = 0; ir < n_in_rows; ++ir) {
-        mbar_wait(&slot_full[st], ph);
+      for (int ir = 0; ir < n_in_rows; ++ir, ++rowc) {
+        if ((rowc & 3) == tw) {
+          mbar_wait(&slot_full[st], ph);
 #pragma unroll
-        for (int s = 0; s < NSRC; ++s) {
-          if (!((p.elu_in >> s) & 1)) continue;
-          const uint32_t base = smem_u32(ring + st * slot_bytes + s * SRC_BYTES);
-          // full passes: 4 independent 16-byte chunks (32 elements) in flight per lane, no branches, so the
-          // MUFU / FP32 latencies of one chunk hide behind the other three
-          constexpr int n_full = n_chunks / 512;
+          for (int s = 0; s < NSRC; ++s) {
+            if (!((p.elu_in >> s) & 1)) continue;
+            const uint32_t base = smem_u32(ring + st * slot_bytes + s * SRC_BYTES);
+            constexpr int n_full = n_chunks / 128;  // passes of 4 x 32 chunks
 #pragma unroll 1
-          for (int it = 0; it < n_full; ++it) {
-            const uint32_t a0 = base + 16 * (it * 512 + tw * 32 + lane);
-            uint4 v[4];
+            for (int it = 0; it < n_full; ++it) {
+              const uint32_t a0 = base + 16 * (it * 128 + lane);
+              uint4 v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = lds128(a0 + u * 2048);
+              for (int u = 0; u < 4; ++u) v[u] = lds128(a0 + u * 512);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) elu_bf16x8(v[u]);
+              for (int u = 0; u < 4; ++u) elu_bf16x8(v[u]);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) sts128(a0 + u * 2048, v[u]);
+              for (int u = 0; u < 4; ++u) sts128(a0 + u * 512, v[u]);
+            }
+            constexpr int n_tail = n_chunks - n_full * 128;  // the halo pixels: 8 (C = 32) or 16 (C = 64) chunks
+            if (n_tail > 0 && lane < n_tail) {
+              const uint32_t a0 = base + 16 * (n_full * 128 + lane);
+              uint4 v = lds128(a0);
+              elu_bf16x8(v);
+              sts128(a0, v);
+            }
           }
-          constexpr int n_tail = n_chunks - n_full * 512;  // the halo pixels: 8 (C = 32) or 16 (C = 64) chunks
-          if (n_tail > 0 && tw == 0 && lane < n_tail) {
-            const uint32_t a0 = base + 16 * (n_full * 512 + lane);
-            uint4 v = lds128(a0);
-            elu_bf16x8(v);
-            sts128(a0, v);
-          }
+          fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&slot_ready[st]);
         }
-        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&slot_ready[st]);
         if (++st == R) {
           st = 0;
           ph ^= 1;
