@@ -160,3 +160,57 @@ def test_bad_arguments_are_reported_not_crashed():
     assert lib.vub_conv_wgrad_splits(ctypes.byref(w)) == 1  # one 64-pixel tile -> one split (pure host planning)
     w.n_split = 5
     assert lib.vub_conv_wgrad(ctypes.byref(w), None) == -2  # more splits than pixel tiles
+
+
+def test_host_side_planning_queries():
+    """Pure host logic of the C ABI that decides data layouts: no GPU needed."""
+    lib = _native.lib()
+    ok = lib.vub_conv_fwd_elu_in_ok
+    # ELU-on-load exists where the row-streaming kernel runs: width >= 128, <= 64 channels, stride 1, square layers
+    assert ok(1, 32, 32, 3, 1, 256, 256) == 1      # residual-block 3x3 at 256^2
+    assert ok(1, 64, 64, 3, 1, 128, 128) == 1      # ... at 128^2
+    assert ok(1, 32, 32, 1, 1, 256, 256) == 1      # skip-connection 1x1
+    assert ok(2, 32, 32, 3, 1, 256, 256) == 1      # concat block, 32 channels per source
+    assert ok(2, 64, 64, 3, 1, 128, 128) == 0      # concat block, 64 per source: weights do not fit beside the ring
+    assert ok(1, 128, 128, 3, 1, 64, 64) == 0      # narrow maps run on the tile kernels
+    assert ok(1, 32, 64, 3, 2, 256, 256) == 0      # stride 2
+    assert ok(1, 32, 64, 3, 1, 256, 256) == 0      # not square
+    # weight-gradient splits: every split keeps >= 4 pixel k-steps (partials below the layer's own input bytes)
+    w = _native.WgradDesc()
+    w.nsrc, w.c_src, w.ksize, w.stride = 1, 128, 3, 1
+    w.cout_k, w.gt_pitch = 128, 1152
+    for batch, hw in ((32, 4), (32, 8), (32, 16), (32, 64)):
+        w.batch, w.hin, w.win = batch, hw, hw
+        n = lib.vub_conv_wgrad_splits(ctypes.byref(w))
+        pixels = batch * hw * hw
+        assert 1 <= n <= max(1, pixels // (4 * 64)), (hw, n)
+    w.batch, w.hin, w.win = 32, 64, 64
+    assert lib.vub_conv_wgrad_splits(ctypes.byref(w)) == 148 // 3   # 3 tap-row groups fill the 148 SMs
+
+
+def test_lean_activation_policy_follows_the_query():
+    from bdvs_b200.modules import lean_elu
+
+    class Bank:  # stands in for a WeightBank
+        lean = True
+
+    assert lean_elu(Bank, 32, 256, 256) and lean_elu(Bank, 64, 128, 128)
+    assert lean_elu(Bank, 32, 256, 256, concat=True)
+    assert not lean_elu(Bank, 64, 128, 128, concat=True)     # dd blocks at 128^2 keep their ELU copies
+    assert not lean_elu(Bank, 128, 64, 64)
+    Bank.lean = False                                         # training (tape) or fp32 validation: pairs everywhere
+    assert not lean_elu(Bank, 32, 256, 256)
+
+
+def test_fused_adam_argument_checks():
+    import torch
+    import bdvs_b200 as B
+    m = B.NormConv2d(32, 32, 3, padding=1)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        B.FusedAdam(m.parameters(), lr=1e-3, model=m)
+    with pytest.raises(NotImplementedError):
+        B.FusedAdam([{"params": list(m.parameters()), "weight_decay": 0.1}], model=m)
+    with pytest.raises(NotImplementedError):
+        B.FusedAdam([torch.nn.Parameter(torch.zeros(3))], model=m)
+    with pytest.raises(ValueError):
+        B.FusedAdam([], model=m)
