@@ -145,8 +145,19 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
   constexpr int COPY_COLS = BKC / 2;
   constexpr int TSLOT_COLS = kdim * NSRC * COPY_COLS;
   constexpr uint32_t ATM_NEED = 2 * BN + 3 * TSLOT_COLS;
-  constexpr uint32_t ATM_COLS = ATM_NEED <= 128 ? 128 : ATM_NEED <= 256 ? 256 : 512;
   constexpr bool ATM_OK = NTAPS == 9 && ATM_NEED <= 512;
+  // TMEM row slots: 3 when the MMA warp fills them itself (tcgen05.cp executes in order with the MMAs); with
+  // ELU-on-load the transform warps write the slots from registers (tcgen05.st), which needs a free / ready handshake
+  // and therefore some slack
+  constexpr int RT_MAX = ATM_OK ? (512 - 2 * BN) / TSLOT_COLS : 3;
+  // Measured (B=64): writing the activated rows to TMEM from registers beats "transform in place + tcgen05.cp" for
+  // the concat layer ([32|32]->32: 0.246 -> 0.216 ms) but not for the single-source ones (32->32: 0.166 -> 0.193 ms,
+  // all four warps then serialise on one row's load -> ELU -> shuffle -> store chain), so only NSRC == 2 uses it.
+  constexpr bool TST = ELU_IN && NSRC == 2;
+  constexpr int RT = !TST ? 3 : (RT_MAX > 6 ? 6 : RT_MAX);
+  constexpr uint32_t ATM_USE = 2 * BN + RT * TSLOT_COLS;
+  constexpr uint32_t ATM_COLS = ATM_USE <= 128 ? 128 : ATM_USE <= 256 ? 256 : 512;
+  static_assert(!ATM_OK || !TST || RT >= 4, "ELU-on-load with the operand in tensor memory needs >= 4 row slots");
 
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
@@ -155,6 +166,7 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
   __shared__ uint64_t slot_full[kRowsMaxRing];
   __shared__ uint64_t slot_empty[kRowsMaxRing];
   __shared__ uint64_t slot_ready[kRowsMaxRing];  // ELU-on-load: the slot's rows have been transformed
+  __shared__ uint64_t tslot_free[8];             // ELU-on-load + A in TMEM: the tensor-memory row slot may be rewritten
   __shared__ uint64_t acc_full[2];
   __shared__ uint64_t acc_empty[2];
   __shared__ uint32_t tmem_base_slot;
@@ -181,8 +193,9 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
     for (int i = 0; i < R; ++i) {
       mbar_init(&slot_full[i], 1);
       mbar_init(&slot_empty[i], 1);
-      mbar_init(&slot_ready[i], 1);  // the transform warp that owns the row
+      mbar_init(&slot_ready[i], (TST && ATM_OK && p.atm) ? 4 : 1);  // all four transform warps / the row's owner
     }
+    for (int i = 0; i < 8; ++i) mbar_init(&tslot_free[i], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 4);  // one arrival per epilogue warp of the owning warpgroup
@@ -257,8 +270,13 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
     if constexpr (ATM_OK) {
       if (atm) {
         // ---- A operand in tensor memory ----
+        // Sources that arrive already activated are copied shared -> tensor memory by this warp (tcgen05.cp, in
+        // order with the MMAs).  RAW sources (ELU-on-load) are written to tensor memory by the transform warps
+        // straight from registers (tcgen05.st): their rows never return to shared memory and need no copies.
         const uint32_t a_tmem0 = tmem_base + 2 * BN;
-        int t_head = 0;   // TMEM row slot the next arriving input row is copied to
+        const int elu_mask = TST ? p.elu_in : 0;
+        const bool any_cp = elu_mask != (1 << NSRC) - 1;
+        int t_head = 0;   // TMEM row slot of the next arriving input row
         int t_first = 0;  // TMEM row slot of the current output row's first input row
         for (rw.init(g_begin, g_end, p.ep.hout, p.batch); rw.valid(); rw.next_segment()) {
           const int th = rw.seg_left;
@@ -273,32 +291,39 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
                 const uint32_t src_lo = ring_lo + wait_slot * slot_units;
                 const uint32_t dst = a_tmem0 + t_head * TSLOT_COLS;
 #pragma unroll
-                for (int s = 0; s < NSRC; ++s)
+                for (int s = 0; s < NSRC; ++s) {
+                  if ((elu_mask >> s) & 1) continue;
 #pragma unroll
                   for (int q = 0; q < kdim; ++q)
 #pragma unroll
                     for (int j = 0; j < BKC / 16; ++j)
                       tmem_cp_128x256b(dst + (s * kdim + q) * COPY_COLS + 8 * j,
                                        umma_desc_join(desc_hi, src_lo + s * (SRC_BYTES >> 4) + q * (ROWB >> 4) + 2 * j));
-                umma_commit(&slot_empty[wait_slot]);  // the shared-memory slot is free once the copies are done
+                }
+                // the shared-memory slot is free once the copies are done (no copies: it is free now)
+                if (any_cp) umma_commit(&slot_empty[wait_slot]);
+                else mbar_arrive(&slot_empty[wait_slot]);
               }
               __syncwarp();
               if (++wait_slot == R) {
                 wait_slot = 0;
                 wait_ph ^= 1;
               }
-              if (++t_head == 3) t_head = 0;
+              if (++t_head == RT) t_head = 0;
             }
             const uint32_t d_tmem = tmem_base + b * BN;
             mbar_wait(&acc_empty[b], ((go >> 1) & 1) ^ 1);
             tc_fence_after();
+            int ts[3];
+            ts[0] = t_first;
+            ts[1] = t_first + 1 >= RT ? t_first + 1 - RT : t_first + 1;
+            ts[2] = t_first + 2 >= RT ? t_first + 2 - RT : t_first + 2;
             if (elect_one()) {
 #pragma unroll
               for (int s = 0; s < NSRC; ++s) {
 #pragma unroll
                 for (int r = 0; r < kdim; ++r) {
-                  const int ts = t_first + r >= 3 ? t_first + r - 3 : t_first + r;
-                  const uint32_t a_row = a_tmem0 + ts * TSLOT_COLS + s * kdim * COPY_COLS;
+                  const uint32_t a_row = a_tmem0 + ts[r] * TSLOT_COLS + s * kdim * COPY_COLS;
 #pragma unroll
                   for (int q = 0; q < kdim; ++q) {
                     const int wt = p.flip ? (NTAPS - 1) - (r * kdim + q) : r * kdim + q;
@@ -311,9 +336,16 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
                 }
               }
               umma_commit(&acc_full[b]);
+              if (TST) {  // input row `orow` is dead: its tensor-memory slot may be rewritten by the transform warps
+                umma_commit(&tslot_free[ts[0]]);
+                if (orow == th - 1) {
+                  umma_commit(&tslot_free[ts[1]]);
+                  umma_commit(&tslot_free[ts[2]]);
+                }
+              }
             }
             __syncwarp();
-            if (++t_first == 3) t_first = 0;
+            t_first = ts[1];
           }
         }
       }
@@ -375,6 +407,88 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
     // Elementwise and in place, so the TMA swizzle inside the slot does not matter: the box footprint is the
     // contiguous first (128 + 2*halo) * ROWB bytes of each source's buffer.
     if constexpr (!ELU_IN) return;
+    if constexpr (ATM_OK && TST) {
+      if (atm) {
+        // ---- A operand in tensor memory: transform from shared memory straight INTO tensor memory ----
+        // TMEM lane m of column-tap copy q holds box pixel m + q.  Each warp serves its own lane quarter: a lane
+        // loads and activates box pixel 32k + lane (and, lanes 0-1, the two pixels past the quarter), the shifted
+        // copies come from warp shuffles, and three tcgen05.st per 32 channels write the copies.  Nothing is
+        // written back to shared memory and the MMA warp issues no tcgen05.cp for this source.
+        const int k = warp & 3;
+        const uint32_t a_tmem0 = tmem_base + 2 * BN + (static_cast<uint32_t>(k * 32) << 16);
+        constexpr int GROUPS = ROWB / 64;  // groups of 32 channels = 16 packed registers = 4 sixteen-byte chunks
+        int st = 0, tt = 0;
+        uint32_t ph = 0, tph = 0;
+        RowWalker rw;
+        for (rw.init(g_begin, g_end, p.ep.hout, p.batch); rw.valid(); rw.next_segment()) {
+          const int n_in_rows = rw.seg_left + 2 * halo;
+          for (int ir = 0; ir < n_in_rows; ++ir) {
+            mbar_wait(&slot_full[st], ph);
+            mbar_wait(&tslot_free[tt], tph ^ 1);
+            tc_fence_after();
+#pragma unroll
+            for (int s = 0; s < NSRC; ++s) {
+              if (!((p.elu_in >> s) & 1)) continue;
+              const uint32_t base = smem_u32(ring + st * slot_bytes + s * SRC_BYTES);
+              const int j0 = k * 32 + lane;                              // own box pixel
+              const int key0 = ROWB == 64 ? ((j0 >> 1) & 3) : (j0 & 7);   // TMA swizzle of the pixel's row
+              // the two pixels past the quarter (box pixels 32k+32, 32k+33): 2 x 16 packed words per channel group,
+              // ONE word per lane (lane = 16 * pixel + word) instead of a second full pass over 32 lanes
+              const int j1 = k * 32 + 32 + (lane >> 4);
+              const int key1 = ROWB == 64 ? ((j1 >> 1) & 3) : (j1 & 7);
+#pragma unroll
+              for (int g = 0; g < GROUPS; ++g) {
+                uint32_t e[16];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  uint4 a = lds128(base + j0 * ROWB + (((4 * g + c) ^ key0) << 4));
+                  elu_bf16x8(a);
+                  e[4 * c] = a.x; e[4 * c + 1] = a.y; e[4 * c + 2] = a.z; e[4 * c + 3] = a.w;
+                }
+                uint32_t hv;
+                {
+                  const int w = 16 * g + (lane & 15);  // 32-bit word (2 channels) of the halo pixel
+                  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(hv)
+                               : "r"(base + j1 * ROWB + ((((w >> 2) ^ key1) << 4) | ((w & 3) << 2))) : "memory");
+                  float f0, f1;
+                  unpack_bf16x2(hv, f0, f1);
+                  hv = pack_bf16x2(elu1(f0), elu1(f1));
+                }
+                uint32_t v1[16], v2[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const uint32_t x1 = __shfl_down_sync(0xffffffffu, e[i], 1);
+                  const uint32_t x2 = __shfl_down_sync(0xffffffffu, e[i], 2);
+                  const uint32_t b0 = __shfl_sync(0xffffffffu, hv, i);        // halo pixel 0, word i
+                  const uint32_t b1 = __shfl_sync(0xffffffffu, hv, 16 + i);   // halo pixel 1, word i
+                  v1[i] = lane == 31 ? b0 : x1;
+                  v2[i] = lane == 30 ? b0 : (lane == 31 ? b1 : x2);
+                }
+                const uint32_t dst = a_tmem0 + tt * TSLOT_COLS + s * kdim * COPY_COLS + 16 * g;
+                tmem_st16(dst, e);
+                tmem_st16(dst + COPY_COLS, v1);
+                tmem_st16(dst + 2 * COPY_COLS, v2);
+              }
+            }
+            // (Deferring this hand-over by one row to overlap the store latency with the next row's work was
+            // measured slower: the MMA warp starves.)
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&slot_ready[st]);
+            if (++st == R) {
+              st = 0;
+              ph ^= 1;
+            }
+            if (++tt == RT) {
+              tt = 0;
+              tph ^= 1;
+            }
+          }
+        }
+      }
+    }
+    if (!(ATM_OK && TST && atm)) {
     // Row per warp: warp tw transforms the input rows tw, tw + 4, ... on its own (16-byte chunks, 4 in flight per
     // lane).  Splitting every row over the four warps instead made each of them pay the per-row overhead
     // (barrier wait, fence.proxy.async, arrive): ~500 cycles per row against the ~256 the MUFU pipe needs.
@@ -423,6 +537,7 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
         }
       }
     }
+    }  // in-place transform (operand stays in shared memory)
   } else {
     // ------------------------------ epilogue (two warpgroups, alternating rows) ----------------
     const int g = (warp - 2) >> 2;  // warpgroup 0: warps 2-5 (even running rows), 1: warps 6-9 (odd)

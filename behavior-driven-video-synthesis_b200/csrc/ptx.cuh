@@ -143,6 +143,18 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Registers -> tensor memory: thread t of the warp writes 16 consecutive 32-bit columns of TMEM lane (lane base + t);
+// a warp may only address its own lane quarter (32 * (warp id % 4)).  Verified on hardware as an A-operand source:
+// tests/native/exp_atmem.cu.
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(
+          taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 // Shared memory -> tensor memory: 128 rows x 256 bits (one K16 slice of a K-major bf16 operand tile, same
 // descriptor format and swizzle as an MMA operand, any start row) into 128 lanes x 8 columns at `taddr`.
 // Executes in issue order with the tcgen05.mma instructions of the same thread.

@@ -118,6 +118,73 @@ __global__ void __launch_bounds__(128)
   if (warp == 1) tmem_dealloc<128>(tmem);
 }
 
+
+// tmem_st16 / tmem_st_wait: csrc/ptx.cuh
+
+// A written to tensor memory by the four warps from REGISTERS (each warp its own lane quarter), then MMA with A from
+// TMEM: the path an ELU-on-load transform would use to skip shared memory for the transformed operand.
+template <int BKC, int N>
+__global__ void __launch_bounds__(128)
+    atmem_st_kernel(const __nv_bfloat16* __restrict__ A /*[R][BKC]*/, const __grid_constant__ CUtensorMap tmB, int shift,
+                    float* __restrict__ out /*[128][N]*/) {
+  constexpr int ROWB = BKC * 2;
+  constexpr uint32_t A_COL = 64;
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sB = smem;
+  __shared__ uint64_t full_bar, done_bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&full_bar, 1);
+    mbar_init(&done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<128>(&tmem_slot);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&full_bar, N * ROWB);
+    tma_load_2d(sB, &tmB, &full_bar, 0, 0);
+  }
+  // every thread: its row of A (row = TMEM lane + shift), 16 channels = 8 packed columns per K16 slice
+  const uint32_t* arow = reinterpret_cast<const uint32_t*>(A + (size_t)(warp * 32 + lane + shift) * BKC);
+#pragma unroll
+  for (int c0 = 0; c0 < BKC / 2; c0 += 16) {
+    uint32_t v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = arow[c0 + i];
+    tmem_st16(tmem + (static_cast<uint32_t>(warp * 32) << 16) + A_COL + c0, v);
+  }
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_wait(&full_bar, 0);
+    tc_fence_after();
+    const uint64_t db = umma_smem_desc_kmajor(smem_u32(sB), ROWB);
+    constexpr uint32_t idesc = umma_idesc_bf16(128, N);
+    for (int j = 0; j < BKC / 16; ++j) umma_bf16_ts(tmem, tmem + A_COL + 8 * j, db + 2 * j, idesc, j != 0);
+    umma_commit(&done_bar);
+  }
+  mbar_wait(&done_bar, 0);
+  tc_fence_after();
+  uint32_t acc[32];
+  for (int c = 0; c < N; c += 32) {
+    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c, acc);
+    tmem_ld_wait();
+    for (int i = 0; i < 32; ++i) out[(warp * 32 + lane) * N + c + i] = __uint_as_float(acc[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<128>(tmem);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -210,6 +277,30 @@ static void run(EncodeTiledFn enc) {
         printf("\n");
       }
     }
+  }
+  CK(cudaFuncSetAttribute(atmem_st_kernel<BKC, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int shift : {0, 1, 2}) {
+    CK(cudaMemset(dO, 0, 128 * N * 4));
+    atmem_st_kernel<BKC, N><<<1, 128, smem>>>(dA, tmB, shift, dO);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("st BKC=%d N=%d shift=%d: CUDA error %s\n", BKC, N, shift, cudaGetErrorString(e)); exit(102); }
+    std::vector<float> O(128 * N);
+    CK(cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost));
+    double maxerr = 0;
+    int badrows = 0;
+    for (int m = 0; m < 128; ++m) {
+      bool bad = false;
+      for (int n = 0; n < N; ++n) {
+        double ref = 0;
+        for (int k = 0; k < BKC; ++k) ref += (double)A[(size_t)(m + shift) * BKC + k] * B[(size_t)n * BKC + k];
+        const double err = fabs(ref - O[m * N + n]);
+        if (err > maxerr) maxerr = err;
+        if (err > 1e-2) bad = true;
+      }
+      badrows += bad;
+    }
+    printf("[EXP atmem-st] row_bytes=%3d N=%2d shift=%d : A written with tcgen05.st from registers, D maxerr=%.4f bad_rows=%d -> %s\n",
+           BKC * 2, N, shift, maxerr, badrows, badrows == 0 ? "OK" : "MISMATCH");
   }
   cudaFree(dA); cudaFree(dB); cudaFree(dO); cudaFree(dI); cudaFree(dC);
 }
