@@ -214,3 +214,11 @@ def test_fused_adam_argument_checks():
         B.FusedAdam([torch.nn.Parameter(torch.zeros(3))], model=m)
     with pytest.raises(ValueError):
         B.FusedAdam([], model=m)
+
+
+def test_integration_md_stub_matches_the_binding():
+    """The ctypes stub shown to reference maintainers must describe the same struct as the package's binding."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = text[text.index("class ConvDesc(ctypes.Structure)"):text.index("lib.vub_conv_fwd.argtypes")]
+    names = re.findall(r'\("(\w+)",\s*ctypes\.', block)
+    assert names == [f[0] for f in _native.ConvDesc._fields_]
