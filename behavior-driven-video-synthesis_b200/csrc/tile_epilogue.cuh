@@ -212,7 +212,9 @@ template <int BN, int GW>
 __device__ __forceinline__ void tile_epilogue_contig(const TileEpi& e, const float* s_scale, const float* s_shift,
                                                      uint32_t trow, uint32_t t0, uint32_t t1, uint32_t t2, int lane,
                                                      int ecol, long long pix0, int n_valid, uint64_t* acc_empty,
-                                                     uint64_t* acc_full, uint32_t acc_parity, int d2s_w = 0) {
+                                                     uint64_t* acc_full, uint32_t acc_parity, int d2s_w = 0,
+                                                     uint32_t acc_empty_cluster = 0) {
+  // acc_empty_cluster: shared::cluster address of the accumulator-empty barrier of a CTA pair's leader (conv_pair)
   constexpr int CPR = GW / 8;
   const bool d2s = d2s_w > 0;
   const bool valid = lane < n_valid;
@@ -285,6 +287,7 @@ __device__ __forceinline__ void tile_epilogue_contig(const TileEpi& e, const flo
         tc_fence_before();
         __syncwarp();
         if (lane == 0 && acc_empty != nullptr) mbar_arrive(acc_empty);
+        if (lane == 0 && acc_empty_cluster != 0) mbar_arrive_cluster(acc_empty_cluster);
       }
       float y[32];
       if (s_scale != nullptr) {

@@ -32,41 +32,7 @@ using namespace vub;
 
 constexpr int kK = 64;  // one 128-byte swizzled row per operand row
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-}
-template <uint32_t kCols>
-__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(dst_smem)), "n"(kCols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
-}
-template <uint32_t kCols>
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "n"(kCols) : "memory");
-}
-__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
-                   smem_u32(bar)),
-               "h"(static_cast<uint16_t>(3))
-               : "memory");
-}
+// CTA-pair PTX helpers: ptx.cuh (moved there once conv_pair_kernel started using them)
 
 template <int N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
@@ -86,7 +52,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
     mbar_init(&done_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc2<512>(&tmem_slot);
+  if (warp == 1) tmem_alloc_pair<512>(&tmem_slot);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -107,9 +73,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
     const uint64_t db = umma_smem_desc_kmajor(smem_u32(sB), ROWB);
     constexpr uint32_t idesc = umma_idesc_bf16(256, N);
     t0 = clock64();
-    for (int j = 0; j < kK / 16; ++j) umma2_bf16(tmem, da + 2 * j, db + 2 * j, idesc, j != 0);
-    for (int it = 0; it < 252; ++it) umma2_bf16(tmem + N, da + 2 * (it & 3), db + 2 * (it & 3), idesc, 1u);  // timing only
-    umma2_commit_both(&done_bar);
+    for (int j = 0; j < kK / 16; ++j) umma_pair_bf16(tmem, da + 2 * j, db + 2 * j, idesc, j != 0);
+    for (int it = 0; it < 252; ++it) umma_pair_bf16(tmem + N, da + 2 * (it & 3), db + 2 * (it & 3), idesc, 1u);  // timing only
+    umma_pair_commit(&done_bar);
   }
   mbar_wait(&done_bar, 0);
   if (rank == 0 && threadIdx.x == 0) cycles[0] = clock64() - t0;
@@ -123,7 +89,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
-  if (warp == 1) tmem_dealloc2<512>(tmem);
+  if (warp == 1) tmem_dealloc_pair<512>(tmem);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -197,27 +163,11 @@ static void run(EncodeTiledFn enc) {
 // full[st] lives in the LEADER: count 2 (leader's arrive.expect_tx + the peer's remote arrive), both CTAs' TMA loads
 // complete_tx on it (the peer through .cta_group::2 with the leader's barrier address); empty[st] lives in every CTA
 // and is signalled in both by the leader's multicast tcgen05.commit.
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m, uint32_t leader_bar_cluster_addr, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
-          smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar_cluster_addr), "r"(c0), "r"(c1)
-      : "memory");
-}
-
-constexpr int kPipeStages = 3;
+constexpr int kPipeStages = 6;
 template <int N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
     cta2_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int ksteps,
-                     float* __restrict__ out /*[256][N]*/) {
+                     float* __restrict__ out /*[256][N]*/, long long* __restrict__ cyc) {
   constexpr int ROWB = 128;
   constexpr int A_BYTES = 128 * ROWB, B_BYTES = (N / 2) * ROWB, STAGE = A_BYTES + B_BYTES;
   extern __shared__ uint8_t smem_dyn[];
@@ -234,12 +184,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
     mbar_init(&done_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc2<512>(&tmem_slot);
+  if (warp == 1) tmem_alloc_pair<512>(&tmem_slot);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  const long long t_start = clock64();
   if (warp == 0 && lane == 0) {
     // producer of this CTA
     int st = 0;
@@ -248,7 +199,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
       mbar_wait(&empty_bar[st], ph ^ 1);
       const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[st]), 0);
       if (rank == 0) mbar_expect_tx(&full_bar[st], 2 * STAGE);   // arrive + expect both CTAs' bytes
-      else mbar_arrive_remote(leader_full);
+      else mbar_arrive_cluster(leader_full);
       uint8_t* a = smem + st * STAGE;
       tma_load_2d_pair(a, &tmA, leader_full, ks * 64, static_cast<int>(rank) * 128);
       tma_load_2d_pair(a + A_BYTES, &tmB, leader_full, ks * 64, static_cast<int>(rank) * (N / 2));
@@ -267,9 +218,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
       tc_fence_after();
       const uint64_t da = umma_smem_desc_kmajor(smem_u32(smem + st * STAGE), ROWB);
       const uint64_t db = umma_smem_desc_kmajor(smem_u32(smem + st * STAGE + A_BYTES), ROWB);
-      for (int j = 0; j < 4; ++j) umma2_bf16(tmem, da + 2 * j, db + 2 * j, idesc, (ks | j) != 0);
-      umma2_commit_both(&empty_bar[st]);
-      if (ks == ksteps - 1) umma2_commit_both(&done_bar);
+      for (int j = 0; j < 4; ++j) umma_pair_bf16(tmem, da + 2 * j, db + 2 * j, idesc, (ks | j) != 0);
+      umma_pair_commit(&empty_bar[st]);
+      if (ks == ksteps - 1) umma_pair_commit(&done_bar);
       if (++st == kPipeStages) {
         st = 0;
         ph ^= 1;
@@ -279,6 +230,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
   __syncwarp();
   mbar_wait(&done_bar, 0);
   tc_fence_after();
+  if (threadIdx.x == 0 && rank == 0) *cyc = clock64() - t_start;
   uint32_t acc[32];
   for (int c = 0; c < N; c += 32) {
     tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c, acc);
@@ -288,7 +240,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
-  if (warp == 1) tmem_dealloc2<512>(tmem);
+  if (warp == 1) tmem_dealloc_pair<512>(tmem);
 }
 
 template <int N>
@@ -325,8 +277,13 @@ static void run_pipe(EncodeTiledFn enc, int ksteps) {
   if (r) { printf("encode B failed %d\n", (int)r); return; }
   const size_t smem = (size_t)kPipeStages * (128 + N / 2) * 128 + 2048;
   CK(cudaFuncSetAttribute(cta2_pipe_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cta2_pipe_kernel<N><<<2, 128, smem>>>(tmA, tmB, ksteps, dO);
+  long long* dC;
+  CK(cudaMalloc(&dC, 8));
+  cta2_pipe_kernel<N><<<2, 128, smem>>>(tmA, tmB, ksteps, dO, dC);
   cudaError_t e = cudaDeviceSynchronize();
+  long long cyc = 0;
+  CK(cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost));
+  cudaFree(dC);
   if (e != cudaSuccess) { printf("[EXP cta2-pipe] N=%d: CUDA error %s\n", N, cudaGetErrorString(e)); exit(104); }
   std::vector<float> O(256 * N);
   CK(cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost));
@@ -343,12 +300,13 @@ static void run_pipe(EncodeTiledFn enc, int ksteps) {
     }
     badrows += bad;
   }
-  printf("[EXP cta2-pipe] M=256 N=%3d K=%4d (%d k-steps, %d-stage ring, peer TMA -> leader barrier, multicast commits): maxerr=%.4f bad_rows=%d -> %s\n",
-         N, K, ksteps, kPipeStages, maxerr, badrows, badrows == 0 ? "OK" : "MISMATCH");
+  printf("[EXP cta2-pipe] M=256 N=%3d K=%4d (%d k-steps, %d-stage ring, peer TMA -> leader barrier, multicast commits): maxerr=%.4f bad_rows=%d -> %s | %lld cycles, %.0f per k-step\n",
+         N, K, ksteps, kPipeStages, maxerr, badrows, badrows == 0 ? "OK" : "MISMATCH", cyc, (double)cyc / ksteps);
   cudaFree(dA); cudaFree(dB); cudaFree(dO);
 }
 
 int main() {
+  setvbuf(stdout, nullptr, _IONBF, 0);
   void* p = nullptr;
   cudaDriverEntryPointQueryResult q;
   CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
@@ -359,6 +317,8 @@ int main() {
   if (getenv("VUB_EXP_PIPE")) {
     run_pipe<128>(reinterpret_cast<EncodeTiledFn>(p), 18);
     run_pipe<128>(reinterpret_cast<EncodeTiledFn>(p), 5);
+    run_pipe<128>(reinterpret_cast<EncodeTiledFn>(p), 180);
+    run_pipe<256>(reinterpret_cast<EncodeTiledFn>(p), 180);
   }
   return 0;
 }
