@@ -94,7 +94,7 @@ extern "C" int vub_conv_dgrad(const vub_dgrad_desc* d, void* stream_v) {
   }
 
   if (d->stride == 1 && !d2s && d->ksize == 3 && (d->nsrc == 1 || C % 128 == 0) &&
-      conv_slab_shape_ok(cout_k, d->hin, d->win, d->nsrc * C, 9 * cout_k)) {
+      conv_slab_shape_ok(cout_k, d->hin, d->win, d->nsrc * C, 9 * cout_k, ((long long)d->batch * d->hin * d->win + 127) / 128)) {
     // same shapes as the forward slab kernel with the channel roles swapped: A = dy, taps mirrored
     SlabJob sj;
     memset(&sj, 0, sizeof(sj));

@@ -371,7 +371,7 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
                              "(see vub_conv_fwd_elu_in_ok) — store an ELU copy for this layer");
 
   // tensor-core-bound 3x3 layers at 64x64 / 32x32: activation-slab kernel (A and weight reuse in smem)
-  if (d->ksize == 3 && d->stride == 1 && d->stages >= 0 && !f32 && conv_slab_shape_ok(d->c_src, d->hin, d->win, cout, d->nsrc * 9 * d->c_src)) {
+  if (d->ksize == 3 && d->stride == 1 && d->stages >= 0 && !f32 && conv_slab_shape_ok(d->c_src, d->hin, d->win, cout, d->nsrc * 9 * d->c_src, ((long long)d->batch * d->hin * d->win + 127) / 128)) {
     SlabJob job;
     memset(&job, 0, sizeof(job));
     job.x[0] = d->x[0];

@@ -21,7 +21,7 @@ struct SlabJob {
   TileEpi epi[2];
 };
 
-bool conv_slab_shape_ok(int c_src, int h, int w, int n_total, int k_total);
+bool conv_slab_shape_ok(int c_src, int h, int w, int n_total, int k_total, long long pix_tiles);
 int conv_slab_launch(const SlabJob& job, cudaStream_t stream);
 
 }  // namespace vub

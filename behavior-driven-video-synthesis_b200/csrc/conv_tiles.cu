@@ -526,7 +526,7 @@ int conv_tiles_launch(const TileJob& job, cudaStream_t stream) {
 
   // CTA pairs (conv_pair_kernel): contiguous epilogues, an even number of pixel tiles, enough items for every pair
   const int pix_tiles = kp.tiles_w * kp.tiles_h * tiles_n;
-  static const int pair_env = getenv("VUB_PAIR") ? atoi(getenv("VUB_PAIR")) : 1;  // VUB_PAIR=0: single-CTA tiles only
+  const int pair_env = getenv("VUB_PAIR") ? atoi(getenv("VUB_PAIR")) : 1;  // VUB_PAIR=0: single-CTA tiles only
   const bool pair = pair_env != 0 && contig && bkc == 64 && (bn == 128 || bn == 256) && pix_tiles % 2 == 0;
   if (pair) kp.total_tiles = (pix_tiles / 2) * kp.n_ntiles;  // work items of a pair
 

@@ -586,6 +586,23 @@ int main(int argc, char** argv) {
   g_tiled = 1;
   for (const BwdCase& c : slab_cases) run_dgrad(c);
   g_tiled = 0;
+  // data gradients through the CTA-pair tile kernel (full grids, 128 channels), then through the single-CTA kernel
+  const BwdCase pair_cases[] = {
+      {"pair 3x3 128->128 @32x32 B16 mask+add+add2 inplace",  16, 32, 32, 128, 1, 128, 3, 1, false, true, true, true, true},
+      {"pair 3x3 [128|128]->128 @32x32 B16 cat mask+add2",    16, 32, 32, 128, 2, 128, 3, 1, false, true, false, true, false},
+      {"pair 1x1 128->128 @64x64 B4 mask",                    4, 64, 64, 128, 1, 128, 1, 1, false, true, false, false, false},
+  };
+  {
+    const char* slab_was = getenv("VUB_ENABLE_SLAB");
+    const std::string slab_keep = slab_was ? slab_was : "";
+    setenv("VUB_ENABLE_SLAB", "0", 1);
+    for (const BwdCase& c : pair_cases) run_dgrad(c);
+    setenv("VUB_PAIR", "0", 1);
+    for (const BwdCase& c : pair_cases) run_dgrad(c);
+    unsetenv("VUB_PAIR");
+    if (slab_was) setenv("VUB_ENABLE_SLAB", slab_keep.c_str(), 1);
+    else unsetenv("VUB_ENABLE_SLAB");
+  }
   // shapes the row-streaming kernel takes over in data-gradient mode (width >= 128, <= 64 channels)
   const BwdCase rows_cases[] = {
       {"rows 1x1 32->32 @8x256 B2 mask+addend inplace",       2, 8, 256, 32, 1, 32, 1, 1, false, true, true, false, true},

@@ -523,6 +523,24 @@ int main(int argc, char** argv) {
   g_tiled = 1;
   for (const ConvCase& c : slab_cases) run_conv_case(c);
   g_tiled = 0;
+  // CTA-pair tile kernel (conv_pair_kernel): full grids of 128-channel layers, contiguous epilogues; then the same
+  // shapes through the single-CTA kernel
+  const ConvCase pair_cases[] = {
+      {"pair 3x3 128->128 @32x32 B19 (76 pairs > 74) +res", 19, 32, 32, 128, 1, 128, 128, 3, 1, true, true, true, false, false, false, 0},
+      {"pair 3x3 [128|128]->128 @32x32 B20 cat +res raw",  20, 32, 32, 128, 2, 128, 128, 3, 1, true, true, false, false, false, false, 0},
+      {"pair 3x3 128->256 D2S @32x32 B20 dual (BN256)",    20, 32, 32, 128, 1, 256, 256, 3, 1, false, true, true, true, false, false, 0},
+      {"pair 3x3 128->512 D2S @32x32 B10 (2 N tiles) elu", 10, 32, 32, 128, 1, 512, 512, 3, 1, false, false, true, true, false, false, 0},
+      {"pair 1x1 128->128 @64x64 B5 elu only",             5, 64, 64, 128, 1, 128, 128, 1, 1, false, false, true, false, false, false, 0},
+  };
+  {
+    const std::string slab_keep = getenv("VUB_ENABLE_SLAB") ? getenv("VUB_ENABLE_SLAB") : "1";
+    setenv("VUB_ENABLE_SLAB", "0", 1);
+    for (const ConvCase& c : pair_cases) run_conv_case(c);
+    setenv("VUB_PAIR", "0", 1);
+    for (const ConvCase& c : pair_cases) run_conv_case(c);
+    unsetenv("VUB_PAIR");
+    setenv("VUB_ENABLE_SLAB", slab_keep.c_str(), 1);
+  }
   // row-streaming kernel (output width >= 128, <= 64 channels per source)
   const ConvCase row_cases[] = {
       {"rows 3x3 64->64 @16x128 B2 +res dual",             2, 16, 128, 64, 1, 64, 64, 3, 1, true, true, true, false, false, false, 0},

@@ -309,7 +309,7 @@ def test_uint8_frame_epilogue_is_bit_exact_with_reference_expression():
 @pytest.mark.parametrize("cfg,batch", [(H256, 1), (M128, 2)])
 def test_activation_layouts_and_kernel_variants_agree(cfg, batch, monkeypatch):
     """The inference path has several equivalent executions: lean activations (ELU on load) vs (raw, ELU) pairs,
-    A operand in tensor vs shared memory, one stream vs two.  All must sit inside the bf16 tolerance of the oracle and
+    A operand in tensor vs shared memory, one stream vs two, CTA-pair vs single-CTA tile kernel.  All must sit inside the bf16 tolerance of the oracle and
     close to each other (they differ by one bf16 rounding of the ELU input at most)."""
     m, sd = build(cfg)
     x, c, eps, _ = O.make_inputs(cfg, batch, tag="variants")
@@ -317,15 +317,16 @@ def test_activation_layouts_and_kernel_variants_agree(cfg, batch, monkeypatch):
         o_t = O.transfer(sd, x, c, eps)
     outs = {}
     for name, env in (("default", {}), ("pairs", {"VUB_LEAN_ACTS": "0"}), ("smem_operand", {"VUB_ROWS_ATM": "0"}),
-                      ("one_stream", {"VUB_FWD_STREAMS": "1"})):
-        for k in ("VUB_LEAN_ACTS", "VUB_ROWS_ATM", "VUB_FWD_STREAMS"):
+                      ("one_stream", {"VUB_FWD_STREAMS": "1"}), ("single_cta", {"VUB_PAIR": "0"})):
+        for k in ("VUB_LEAN_ACTS", "VUB_ROWS_ATM", "VUB_FWD_STREAMS", "VUB_PAIR"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         with torch.no_grad():
             outs[name] = m.transfer(x.cuda(), c.cuda(), eps=cuda(eps)).float().cpu()
         assert rel(outs[name], o_t) < BF16_TOL, name
-    for name in ("pairs", "smem_operand", "one_stream"):
+    for name in ("pairs", "smem_operand", "one_stream", "single_cta"):
         assert rel(outs[name], outs["default"]) < 5e-3, name
     assert torch.equal(outs["one_stream"], outs["default"])          # same kernels, different stream assignment
     assert torch.equal(outs["smem_operand"], outs["default"])        # same operands, fetched differently
+    assert torch.equal(outs["single_cta"], outs["default"])          # same K order, M = 128 vs M = 256 instructions
