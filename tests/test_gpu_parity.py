@@ -151,9 +151,10 @@ def test_latent_noise_is_bit_exact_with_torch_generator():
         assert rel(z[i], mu[i] + torch.exp(ls[i]) * e) < 1e-6
 
 
-def test_batch_independence_and_determinism_at_full_size():
+def test_batch_independence_and_determinism_at_full_size(monkeypatch):
     """Size-independent properties at H256 (BASELINE configs[1] shape): frames are independent units —
-    a frame's result does not depend on what else is in the batch — and a rerun is bit-identical."""
+    a frame's result does not depend on what else is in the batch — and a rerun is bit-identical.  At B = 8 the
+    128-channel layers run on the CTA-pair tile kernel, at B = 3 on the single-CTA / per-tap kernels: same bits."""
     m, _ = build(H256)
     B = 8
     x, c, eps, _ = O.make_inputs(H256, B, tag="prop")
@@ -165,6 +166,10 @@ def test_batch_independence_and_determinism_at_full_size():
     assert torch.equal(full, again)
     assert torch.equal(full[2:5], part)
     assert torch.isfinite(full).all()
+    monkeypatch.setenv("VUB_PAIR", "0")  # single-CTA tile kernel for the layers the pair kernel took above
+    with torch.no_grad():
+        single = m.transfer(x, c, eps=eps)
+    assert torch.equal(full, single)
 
 
 def test_ops_reject_bad_inputs():
