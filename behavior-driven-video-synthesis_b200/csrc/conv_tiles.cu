@@ -527,7 +527,7 @@ int conv_tiles_launch(const TileJob& job, cudaStream_t stream) {
   // CTA pairs (conv_pair_kernel): contiguous epilogues, an even number of pixel tiles, enough items for every pair
   const int pix_tiles = kp.tiles_w * kp.tiles_h * tiles_n;
   const int pair_env = getenv("VUB_PAIR") ? atoi(getenv("VUB_PAIR")) : 1;  // VUB_PAIR=0: single-CTA tiles only
-  const bool pair = pair_env != 0 && contig && bkc == 64 && (bn == 128 || bn == 256) && pix_tiles % 2 == 0;
+  const bool pair = pair_env != 0 && contig && bkc == 64 && (bn == 64 || bn == 128 || bn == 256) && pix_tiles % 2 == 0;
   if (pair) kp.total_tiles = (pix_tiles / 2) * kp.n_ntiles;  // work items of a pair
 
   const int gw = bn >= 64 ? 64 : 32;
@@ -566,6 +566,7 @@ int conv_tiles_launch(const TileJob& job, cudaStream_t stream) {
   if (pair) {
     const int pairs = kp.total_tiles < n_sm / 2 ? kp.total_tiles : n_sm / 2;
     kp.w_tiled = nullptr;
+    if (bn == 64) return launch_pair_t<64, 64>(kp, 2 * pairs, smem, stream);
     if (bn == 128) return launch_pair_t<128, 64>(kp, 2 * pairs, smem, stream);
     return launch_pair_t<256, 64>(kp, 2 * pairs, smem, stream);
   }

@@ -591,6 +591,7 @@ int main(int argc, char** argv) {
       {"pair 3x3 128->128 @32x32 B16 mask+add+add2 inplace",  16, 32, 32, 128, 1, 128, 3, 1, false, true, true, true, true},
       {"pair 3x3 [128|128]->128 @32x32 B16 cat mask+add2",    16, 32, 32, 128, 2, 128, 3, 1, false, true, false, true, false},
       {"pair 1x1 128->128 @64x64 B4 mask",                    4, 64, 64, 128, 1, 128, 1, 1, false, true, false, false, false},
+      {"pair 3x3 64->64 @64x64 B5 mask+add2 (BN64)",          5, 64, 64, 64, 1, 64, 3, 1, false, true, false, true, false},
   };
   {
     const char* slab_was = getenv("VUB_ENABLE_SLAB");

@@ -531,6 +531,8 @@ int main(int argc, char** argv) {
       {"pair 3x3 128->256 D2S @32x32 B20 dual (BN256)",    20, 32, 32, 128, 1, 256, 256, 3, 1, false, true, true, true, false, false, 0},
       {"pair 3x3 128->512 D2S @32x32 B10 (2 N tiles) elu", 10, 32, 32, 128, 1, 512, 512, 3, 1, false, false, true, true, false, false, 0},
       {"pair 1x1 128->128 @64x64 B5 elu only",             5, 64, 64, 128, 1, 128, 128, 1, 1, false, false, true, false, false, false, 0},
+      {"pair 3x3 [64|64]->64 @128x128 B2 cat +res dual (BN64)", 2, 128, 128, 64, 2, 64, 64, 3, 1, true, true, true, false, false, false, 0},
+      {"pair 3x3 64->64 @64x64 B5 +res raw (BN64)",        5, 64, 64, 64, 1, 64, 64, 3, 1, true, true, false, false, false, false, 0},
   };
   {
     const std::string slab_keep = getenv("VUB_ENABLE_SLAB") ? getenv("VUB_ENABLE_SLAB") : "1";
