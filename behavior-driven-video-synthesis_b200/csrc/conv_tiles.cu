@@ -12,6 +12,10 @@
 // through shared memory and written with coalesced 16-byte chunks, DepthToSpace or strided pixel
 // scatter, or fp32 NHWC / NCHW outputs.
 //
+// conv_pair_kernel (below) is the same loop on a CTA pair: tcgen05.mma.cta_group::2 with M = 256 over two
+// neighbouring pixel tiles, half of the weight tile staged per CTA; it takes the launches with BN >= 64, 64-channel
+// k-steps, contiguous epilogues and an even number of pixel tiles.
+//
 // Users: vub_conv_fwd (every conv the row-streaming kernel does not take) and vub_conv_dgrad.
 // Replaces NormConv2d.forward / its autograd backward w.r.t. the input (lib/modules.py:140-145) with the
 // surrounding VunetRNB / Upsample / Downsample elementwise work fused in.
