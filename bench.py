@@ -1,12 +1,14 @@
 #!/usr/bin/env python
 """Benchmark of the VUnet hot path (contract: see the task statement / DESIGN.md §Measurement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload synth|train]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-train] [--no-cpu-baseline]
+                    [--frames-total T]
 
 Default workload = BASELINE.json configs[1]: VunetAlter Human3.6m settings (256x256, bottleneck_factor 2,
 box_factor 2, 3 appearance channels), forward-only frame synthesis (``transfer``), bf16 tensor-core
 compute, 64 frames per GPU per step; frames are sharded over ranks with no collective (weak scaling).
-A "step" is one pass of the hot path over one 64-frame batch of synthetic frames.
+A "step" is one pass of the hot path over one 64-frame batch of synthetic frames.  ``--frames-total T`` is the
+strong-scaling reading of the same config (T frames per step split over the GPUs, "scaling": "strong").
 
   value  frames/s, whole job, inputs resident in HBM, CUDA-graph replay timed with CUDA events
   e2e    frames/s through the public API (FrameSynthesizer.render_host) with pinned HOST buffers:
@@ -362,6 +364,11 @@ def run_ours(args):
     peaks = load_peaks()
     model, sd = build_model(device)
     Bf = FRAMES_PER_GPU
+    strong = args.frames_total > 0  # SURVEY 8(d) literal reading: a fixed number of frames split over the GPUs
+    if strong:
+        if args.frames_total % world:
+            raise SystemExit(f"--frames-total {args.frames_total} is not divisible by {world} GPUs")
+        Bf = args.frames_total // world
     torch.manual_seed(42 + rank)
     synth = FrameSynthesizer(model, Bf, device)
     synth.x.uniform_(-1, 1)
@@ -486,7 +493,7 @@ def run_ours(args):
         roofline = {"bound": "tensor", "achieved": top["tflops"], "peak": peaks["bf16_tflops_sustained"],
                     "unit": "TFLOP/s", "frac": round(top["tflops"] / peaks["bf16_tflops_sustained"], 4), "traffic": None}
     traffic_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(traffic_path):
+    if os.path.exists(traffic_path) and Bf == FRAMES_PER_GPU:  # the captures were taken at 64 frames per GPU
         with open(traffic_path) as f:
             tr = json.load(f).get(top["kernel"])
         if tr:  # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture
@@ -520,11 +527,11 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": Bf, "global_frames_per_step": Bf * world,
                    "parallelism": f"frames sharded over {world} GPU(s), no collective",
-                   "cache": "inputs + activations per step (~14 GB) far exceed the 126 MB L2: no flush needed",
+                   "cache": f"inputs + activations per step (~{14.0 * Bf / 64:.1f} GB) far exceed the 126 MB L2: no flush needed",
                    "execution": "CUDA graph replay of model.transfer (latent noise drawn inside the graph); e2e: "
                                 "FrameSynthesizer.render_host, pinned host buffers, copies double-buffered on their own "
                                 "streams and overlapped with the kernels of the neighbouring batches",
@@ -553,6 +560,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step workload (configs[2])")
+    ap.add_argument("--frames-total", type=int, default=0,
+                    help="strong-scaling reading of configs[1]: this many frames per step split over the GPUs "
+                         "(default 0 = 64 frames per GPU, weak scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
