@@ -3,7 +3,7 @@ from . import _native
 from ._native import build as build_native
 from .losses import compute_kl_with_prior, kl_loss
 from .modules import (Act, DepthToSpace, Downsample, IDAct, NormConv2d, SpaceToDepth, Upsample, VunetRNB,
-                      WeightBank, to_act)
+                      WeightBank, bump_weight_epoch, to_act)
 from .optim import FusedAdam
 from .training import GraphedTrainStep
 from .validation import fp32_validation
@@ -13,5 +13,5 @@ __all__ = [
     "VunetAlter", "EncUp", "EncDownAlter", "DecUp", "DecDownAlter",
     "NormConv2d", "VunetRNB", "Downsample", "Upsample", "DepthToSpace", "SpaceToDepth", "IDAct",
     "compute_kl_with_prior", "kl_loss", "Act", "to_act", "WeightBank", "build_native",
-    "fp32_validation", "FusedAdam", "GraphedTrainStep",
+    "fp32_validation", "FusedAdam", "GraphedTrainStep", "bump_weight_epoch",
 ]

@@ -30,6 +30,12 @@ EXPORTED_SYMBOLS = (
     "vub_conv_fwd_elu_in_ok",
     "vub_wn_prep",
     "vub_stem_fwd",
+    "vub_stem_fwd_u8",
+    "vub_allreduce_bucket",
+    "vub_nccl_version",
+    "vub_nccl_unique_id",
+    "vub_nccl_comm_init",
+    "vub_nccl_comm_destroy",
     "vub_latent_num_partials",
     "vub_latent_fwd",
     "vub_nchw_f32_to_nhwc_bf16",
@@ -38,6 +44,9 @@ EXPORTED_SYMBOLS = (
     "vub_frames_to_uint8",
     "vub_conv_fwd_f32",
     "vub_nchw_f32_to_nhwc_f32",
+    "vub_conv_dgrad_f32",
+    "vub_conv_wgrad_f32",
+    "vub_latent_bwd_f32",
     "vub_conv_dgrad",
     "vub_conv_wgrad",
     "vub_conv_wgrad_splits",
@@ -47,7 +56,7 @@ EXPORTED_SYMBOLS = (
     "vub_stem_bwd",
     "vub_latent_bwd",
 )
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class ConvDesc(C.Structure):
@@ -103,6 +112,54 @@ class WnEntry(C.Structure):
         ("wd_tiled", C.c_void_p),
         ("tiled_rows", C.c_int32),
         ("pad_", C.c_int32),
+    ]
+
+
+class DgradF32Desc(C.Structure):
+    """Mirror of ``vub_dgrad_f32_desc``."""
+
+    _fields_ = [
+        ("dy", C.c_void_p),
+        ("w", C.c_void_p),
+        ("scale", C.c_void_p),
+        ("dx", C.c_void_p * 2),
+        ("mask_elu", C.c_void_p * 2),
+        ("addend", C.c_void_p * 2),
+        ("addend2", C.c_void_p * 2),
+        ("nsrc", C.c_int32),
+        ("c_src", C.c_int32),
+        ("batch", C.c_int32),
+        ("hin", C.c_int32),
+        ("win", C.c_int32),
+        ("cout", C.c_int32),
+        ("w_pitch", C.c_int32),
+        ("ksize", C.c_int32),
+        ("stride", C.c_int32),
+        ("flags", C.c_uint32),
+    ]
+
+
+class WgradF32Desc(C.Structure):
+    """Mirror of ``vub_wgrad_f32_desc``."""
+
+    _fields_ = [
+        ("dy", C.c_void_p),
+        ("x", C.c_void_p * 2),
+        ("gt", C.c_void_p),
+        ("dy_sum", C.c_void_p),
+        ("nsrc", C.c_int32),
+        ("c_src", C.c_int32),
+        ("batch", C.c_int32),
+        ("hin", C.c_int32),
+        ("win", C.c_int32),
+        ("cout", C.c_int32),
+        ("ksize", C.c_int32),
+        ("stride", C.c_int32),
+        ("flags", C.c_uint32),
+        ("n_split", C.c_int32),
+        ("gt_pitch", C.c_int32),
+        ("split_stride", C.c_int64),
+        ("sum_stride", C.c_int64),
     ]
 
 
@@ -243,6 +300,18 @@ def _declare(lib: C.CDLL) -> None:
     lib.vub_wn_prep.argtypes = [vp, i32, i32, vp]
     lib.vub_stem_fwd.restype = C.c_int
     lib.vub_stem_fwd.argtypes = [fp, fp, fp, fp, fp, fp, i32, i32, i32, i32, i32, vp, vp, vp]
+    lib.vub_allreduce_bucket.restype = C.c_int
+    lib.vub_allreduce_bucket.argtypes = [vp, C.c_int64, vp, i32, vp]
+    lib.vub_nccl_version.restype = i32
+    lib.vub_nccl_version.argtypes = []
+    lib.vub_nccl_unique_id.restype = C.c_int
+    lib.vub_nccl_unique_id.argtypes = [vp]
+    lib.vub_nccl_comm_init.restype = C.c_int
+    lib.vub_nccl_comm_init.argtypes = [C.POINTER(vp), i32, vp, i32]
+    lib.vub_nccl_comm_destroy.restype = C.c_int
+    lib.vub_nccl_comm_destroy.argtypes = [vp]
+    lib.vub_stem_fwd_u8.restype = C.c_int
+    lib.vub_stem_fwd_u8.argtypes = [vp, fp, fp, fp, fp, fp, i32, i32, i32, i32, i32, vp, vp, vp]
     lib.vub_latent_num_partials.restype = i32
     lib.vub_latent_num_partials.argtypes = [i32, i32, i32, i32]
     lib.vub_latent_fwd.restype = C.c_int
@@ -257,6 +326,12 @@ def _declare(lib: C.CDLL) -> None:
     lib.vub_frames_to_uint8.argtypes = [fp, i32, i32, i32, vp, vp]
     lib.vub_conv_fwd_f32.restype = C.c_int
     lib.vub_conv_fwd_f32.argtypes = [C.POINTER(ConvF32Desc), vp]
+    lib.vub_conv_dgrad_f32.restype = C.c_int
+    lib.vub_conv_dgrad_f32.argtypes = [C.POINTER(DgradF32Desc), vp]
+    lib.vub_conv_wgrad_f32.restype = C.c_int
+    lib.vub_conv_wgrad_f32.argtypes = [C.POINTER(WgradF32Desc), vp]
+    lib.vub_latent_bwd_f32.restype = C.c_int
+    lib.vub_latent_bwd_f32.argtypes = [fp, fp, fp, fp, fp, i32, i32, i32, i32, fp, vp]
     lib.vub_nchw_f32_to_nhwc_f32.restype = C.c_int
     lib.vub_nchw_f32_to_nhwc_f32.argtypes = [fp, i32, i32, i32, i32, fp, fp, vp]
     lib.vub_conv_dgrad.restype = C.c_int

@@ -60,6 +60,12 @@ struct RowsKParams {
   // there, so the tensor core fetches an input row from shared memory 3 times instead of 9 — the shared-memory
   // data pipe is what bounds this kernel (profiles/r01_ncu_rows_smem.txt).
   int atm;
+  // Kernel rows as N blocks (3x3, BN 32 / 64): an input row is multiplied ONCE, by the three kernel rows' weight
+  // tiles stacked along N ([kh=2 | kh=1 | kh=0] -> output rows r-1, r, r+1 whose accumulators are neighbours in a
+  // ring of tensor-memory slots).  6 (12) MMAs of N = 96 (192) per input row instead of 18 (36) of N = 32 (64): an
+  // M128 N32 K16 MMA costs 40 cycles for 16 cycles of math because its shared-memory operand fetch is (128 + N) rows
+  // per instruction (profiles/r01_exp_rates_mma.log) — stacking N amortises the 128 A rows over three outputs.
+  int nblk;
 };
 
 template <int BKC>
@@ -158,6 +164,11 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
   constexpr uint32_t ATM_USE = 2 * BN + RT * TSLOT_COLS;
   constexpr uint32_t ATM_COLS = ATM_USE <= 128 ? 128 : ATM_USE <= 256 ? 256 : 512;
   static_assert(!ATM_OK || !TST || RT >= 4, "ELU-on-load with the operand in tensor memory needs >= 4 row slots");
+  // kernel rows as N blocks: ring of RA accumulator slots of BN columns (an output row's accumulator is complete
+  // after THREE input rows; up to RA - 3 finished rows wait for the epilogue)
+  constexpr bool NBLK = NTAPS == 9 && (BN == 32 || BN == 64);
+  constexpr int RA_N = 8;
+  constexpr uint32_t NBLK_COLS = RA_N * BN;  // 256 / 512
 
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
@@ -167,8 +178,8 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
   __shared__ uint64_t slot_empty[kRowsMaxRing];
   __shared__ uint64_t slot_ready[kRowsMaxRing];  // ELU-on-load: the slot's rows have been transformed
   __shared__ uint64_t tslot_free[8];             // ELU-on-load + A in TMEM: the tensor-memory row slot may be rewritten
-  __shared__ uint64_t acc_full[2];
-  __shared__ uint64_t acc_empty[2];
+  __shared__ uint64_t acc_full[8];
+  __shared__ uint64_t acc_empty[8];
   __shared__ uint32_t tmem_base_slot;
   __shared__ float s_scale[BN];
   __shared__ float s_shift[BN];
@@ -196,16 +207,23 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
       mbar_init(&slot_ready[i], (TST && ATM_OK && p.atm) ? 4 : 1);  // all four transform warps / the row's owner
     }
     for (int i = 0; i < 8; ++i) mbar_init(&tslot_free[i], 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 8; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 4);  // one arrival per epilogue warp of the owning warpgroup
     }
     fence_mbar_init();
   }
-  const bool atm = ATM_OK && p.atm != 0;
+  const bool nblk = NBLK && p.nblk != 0;
+  const bool atm = ATM_OK && p.atm != 0 && !nblk;
+  const int RA = nblk ? RA_N : 2;  // accumulator slots: running output row `go` lives in slot go % RA
   if (warp == 2) {
-    if (atm) tmem_alloc<ATM_COLS>(&tmem_base_slot);
-    else tmem_alloc<TMEM_COLS>(&tmem_base_slot);
+    if constexpr (NBLK) {
+      if (nblk) tmem_alloc<NBLK_COLS>(&tmem_base_slot);
+    }
+    if (!nblk) {
+      if (atm) tmem_alloc<ATM_COLS>(&tmem_base_slot);
+      else tmem_alloc<TMEM_COLS>(&tmem_base_slot);
+    }
     tmem_relinquish();
   }
   for (int i = threadIdx.x; i < BN; i += kRowsThreads) {
@@ -227,7 +245,18 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
     constexpr int ntiles = NSRC * NTAPS;
     if (elect_one()) {
       mbar_expect_tx(&w_full, ntiles * WT_BYTES);
-      for (int i = 0; i < ntiles; ++i) tma_load_2d(wsm + i * WT_BYTES, &p.tmB, &w_full, i * BKC, 0);
+      if (nblk) {
+        // per (source, column tap): the three kernel rows' tiles stacked along N in the order kh = 2, 1, 0 (the
+        // output rows r-1, r, r+1 an input row r feeds); data gradient: geometric tap t carries weight tile 8 - t
+        for (int sq = 0; sq < NSRC * 3; ++sq)
+          for (int kh = 0; kh < 3; ++kh) {
+            const int s = sq / 3, q = sq - 3 * s, t = kh * 3 + q;
+            tma_load_2d(wsm + (sq * 3 + (2 - kh)) * WT_BYTES, &p.tmB, &w_full,
+                        (s * NTAPS + (p.flip ? (NTAPS - 1) - t : t)) * BKC, 0);
+          }
+      } else {
+        for (int i = 0; i < ntiles; ++i) tma_load_2d(wsm + i * WT_BYTES, &p.tmB, &w_full, i * BKC, 0);
+      }
     }
     __syncwarp();
     constexpr uint32_t row_tx = NSRC * (kRowsW + 2 * halo) * ROWB;
@@ -267,6 +296,70 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
     uint32_t go = 0;                     // running output-row counter
     uint64_t* const in_bar = ELU_IN ? slot_ready : slot_full;
     RowWalker rw;
+    if constexpr (NBLK) {
+      if (nblk) {
+        // ---- kernel rows as N blocks: one pass over every input row ----
+        constexpr uint32_t idesc1 = umma_idesc_bf16(kRowsW, BN), idesc2 = umma_idesc_bf16(kRowsW, 2 * BN),
+                           idesc3 = umma_idesc_bf16(kRowsW, 3 * BN);
+        constexpr uint32_t wt_units = static_cast<uint32_t>(WT_BYTES) >> 4;
+        uint32_t go0 = 0;  // running index of the current segment's first output row
+        for (rw.init(g_begin, g_end, p.ep.hout, p.batch); rw.valid(); rw.next_segment()) {
+          const int th = rw.seg_left;
+          for (int ir = 0; ir < th + 2; ++ir) {  // input row h0 - 1 + ir feeds the segment's output rows ir-2 .. ir
+            mbar_wait(&in_bar[wait_slot], wait_ph);
+            const int o_lo = ir >= 2 ? ir - 2 : 0;
+            const int o_hi = ir < th ? ir : th - 1;
+            const bool fresh = ir < th;  // output row `ir` receives its FIRST contribution here: overwrite its slot
+            if (fresh) {
+              const uint32_t gf = go0 + ir;
+              mbar_wait(&acc_empty[gf % RA_N], ((gf / RA_N) & 1) ^ 1);
+            }
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t a_base = ring_lo + wait_slot * slot_units;
+              // one MMA (two where the span wraps around the accumulator ring) over output rows oa .. ob
+              auto span = [&](int oa, int ob, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
+                const uint32_t sa = (go0 + oa) % RA_N;
+                const int n = ob - oa + 1;
+                const int j0 = oa - (ir - 2);
+                const int n1 = (sa + n <= RA_N) ? n : static_cast<int>(RA_N - sa);
+                umma_bf16(tmem_base + sa * BN, umma_desc_join(desc_hi, a_lo), umma_desc_join(desc_hi, b_lo + j0 * wt_units),
+                          n1 == 1 ? idesc1 : (n1 == 2 ? idesc2 : idesc3), acc);
+                if (n1 < n)
+                  umma_bf16(tmem_base, umma_desc_join(desc_hi, a_lo),
+                            umma_desc_join(desc_hi, b_lo + (j0 + n1) * wt_units), (n - n1) == 1 ? idesc1 : idesc2, acc);
+              };
+#pragma unroll
+              for (int s = 0; s < NSRC; ++s) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+#pragma unroll
+                  for (int j = 0; j < BKC / 16; ++j) {
+                    const uint32_t a_lo = a_base + s * (SRC_BYTES >> 4) + q * (ROWB >> 4) + 2 * j;
+                    const uint32_t b_lo = w_lo + (s * 3 + q) * 3 * wt_units + 2 * j;
+                    if ((s | q | j) == 0) {
+                      const int acc_hi = fresh ? ir - 1 : o_hi;
+                      if (o_lo <= acc_hi) span(o_lo, acc_hi, a_lo, b_lo, 1u);
+                      if (fresh) span(ir, ir, a_lo, b_lo, 0u);
+                    } else {
+                      span(o_lo, o_hi, a_lo, b_lo, 1u);
+                    }
+                  }
+                }
+              }
+              if (ir >= 2) umma_commit(&acc_full[(go0 + ir - 2) % RA_N]);  // output row ir-2 is complete
+              umma_commit(&slot_empty[wait_slot]);
+            }
+            __syncwarp();
+            if (++wait_slot == R) {
+              wait_slot = 0;
+              wait_ph ^= 1;
+            }
+          }
+          go0 += th;
+        }
+      }
+    }
     if constexpr (ATM_OK) {
       if (atm) {
         // ---- A operand in tensor memory ----
@@ -350,7 +443,7 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
         }
       }
     }
-    if (!atm)
+    if (!atm && !nblk)
     for (rw.init(g_begin, g_end, p.ep.hout, p.batch); rw.valid(); rw.next_segment()) {
       const int th = rw.seg_left;
       for (int orow = 0; orow < th; ++orow, ++go) {
@@ -543,7 +636,7 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
     const int g = (warp - 2) >> 2;  // warpgroup 0: warps 2-5 (even running rows), 1: warps 6-9 (odd)
     const int q = warp & 3;         // TMEM lane quarter this warp may read
     const int m = q * 32 + lane;
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * BN;
+    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);  // + slot * BN: this row's accumulator
     const bool has_res = p.ep.residual != nullptr;
     const bool bf16_out = (p.ep.flags & (VUB_CONV_F32_NHWC | VUB_CONV_F32_NCHW)) == 0;
     const uint32_t t0 = smem_u32(staging) + (warp - 2) * EpiStage<SGW>::WARP_BYTES;  // residual in / raw out
@@ -572,9 +665,11 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
       const uint32_t st = smem_u32(staging) + (warp - 2) * p.stage_tiles * EpiStage<32>::TILE_BYTES;
       const bool two = p.n_halves == 2;
       constexpr int NG = BN / 32;
-      uint32_t cntb = 0;
+      uint32_t gob = g;  // running index of this warpgroup's current row (g, g + 2, ...)
       uint4 va[4], vm[4], vb[4];
       while (cur.valid()) {
+        const uint32_t aslot = gob % RA;
+        const uint32_t trow = tlane + aslot * BN;
         const long long pix = ((long long)cur.n * p.ep.hout + cur.h) * p.ep.wout + cur.w0 + q * 32;  // warp's first pixel
         auto load_group = [&](int gi) {
           const TileEpi& e = p.bwd[two ? gi : 0];
@@ -588,7 +683,7 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
           }
         };
         load_group(0);
-        mbar_wait(&acc_full[g], cntb & 1);
+        mbar_wait(&acc_full[aslot], (gob / RA) & 1);
         tc_fence_after();
 #pragma unroll
         for (int gi = 0; gi < NG; ++gi) {
@@ -599,7 +694,7 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
           if (gi == NG - 1) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[g]);
+            if (lane == 0) mbar_arrive(&acc_empty[aslot]);
           }
           float y[32];
 #pragma unroll
@@ -633,7 +728,7 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
             }
           }
         }
-        ++cntb;
+        gob += 2;
         cur.next_row();
         if (cur.valid()) cur.next_row();
       }
@@ -641,8 +736,10 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
     if constexpr (!BWD) {
     ahead = cur;
     if (STAGED && has_res && bf16_out && cur.valid()) prefetch_res(cur);
-    uint32_t cnt = 0;  // rows this warpgroup has processed (its TMEM buffer's phase counter)
+    uint32_t gof = g;  // running index of this warpgroup's current row (g, g + 2, ...)
     while (cur.valid()) {
+      const uint32_t aslot = gof % RA;
+      const uint32_t trow = tlane + aslot * BN;
       if (ahead.valid()) ahead.next_row();
       if (ahead.valid()) ahead.next_row();
       const int n = cur.n, oh = cur.h, ow = cur.w0 + m;
@@ -655,7 +752,7 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
           if (ahead.valid()) prefetch_res(ahead);
         }
       }
-      mbar_wait(&acc_full[g], cnt & 1);
+      mbar_wait(&acc_full[aslot], (gof / RA) & 1);
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < NCHUNK; ++c) {
@@ -666,7 +763,7 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
         if (c == NCHUNK - 1) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[g]);
+          if (lane == 0) mbar_arrive(&acc_empty[aslot]);
         }
         float y[CH];
 #pragma unroll
@@ -704,7 +801,7 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
           __syncwarp();
         }
       }
-      ++cnt;
+      gof += 2;
       cur = ahead;
     }
     }  // !BWD
@@ -713,8 +810,13 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
-    if (atm) tmem_dealloc<ATM_COLS>(tmem_base);
-    else tmem_dealloc<TMEM_COLS>(tmem_base);
+    if constexpr (NBLK) {
+      if (nblk) tmem_dealloc<NBLK_COLS>(tmem_base);
+    }
+    if (!nblk) {
+      if (atm) tmem_dealloc<ATM_COLS>(tmem_base);
+      else tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
   }
 }
 
@@ -811,7 +913,8 @@ static int rows_job_launch(const RowsJob& j, cudaStream_t stream) {
   kp.bwd[0] = j.bwd[0];
   kp.bwd[1] = j.bwd[1];
   kp.elu_in = j.elu_in & ((1 << j.nsrc) - 1);
-  kp.atm = (j.taps == 9 && 2 * j.bn + 3 * 3 * j.nsrc * (bkc / 2) <= 512 && env_int("VUB_ROWS_ATM", 1)) ? 1 : 0;
+  kp.nblk = (j.taps == 9 && (j.bn == 32 || j.bn == 64) && env_int("VUB_ROWS_NBLK", 1)) ? 1 : 0;
+  kp.atm = (!kp.nblk && j.taps == 9 && 2 * j.bn + 3 * 3 * j.nsrc * (bkc / 2) <= 512 && env_int("VUB_ROWS_ATM", 1)) ? 1 : 0;
   const size_t wbytes = (size_t)j.nsrc * j.taps * j.bn * bkc * 2;
   const size_t slot = (size_t)j.nsrc * (bkc == 64 ? 136 * 128 : 144 * 64);
   const int ring_env = env_int("VUB_ROWS_RING", 0);

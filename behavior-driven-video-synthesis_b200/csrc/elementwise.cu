@@ -210,14 +210,25 @@ __global__ void __launch_bounds__(kWnThreads)
 constexpr int kStemThreads = 128;
 constexpr int kStemMaxCx = 64;
 
-template <int COUT>
+// U8: the input is a uint8 HWC image batch [B, H, W, cx] (what the reference's loaders / stickman rasteriser produce
+// before `ToTensor` + `x * 2 - 1`, data/__init__.py:15-43, data/data_conversions_3d.py:1154-1163); the kernel applies
+// exactly that conversion — fp32 (u / 255) * 2 - 1 through a 256-entry table built with IEEE division — so the
+// result is bit-identical to feeding the converted fp32 NCHW tensor, at a quarter of the input bytes and with the
+// pixel's channels contiguous.
+template <int COUT, bool U8>
 __global__ void __launch_bounds__(kStemThreads)
-    stem_kernel(const float* __restrict__ x, const float* __restrict__ v, const float* __restrict__ g,
+    stem_kernel(const void* __restrict__ x_in, const float* __restrict__ v, const float* __restrict__ g,
                 const float* __restrict__ gamma, const float* __restrict__ beta,
                 const float* __restrict__ bias, int cx, long long hw, long long total_pix,
                 __nv_bfloat16* __restrict__ out_raw, __nv_bfloat16* __restrict__ out_elu) {
   __shared__ float s_w[COUT * kStemMaxCx];  // [ci][co], already scaled by gamma*g/||v||
   __shared__ float s_shift[COUT];
+  __shared__ float s_lut[U8 ? 256 : 1];
+  const float* __restrict__ x = static_cast<const float*>(x_in);
+  const uint8_t* __restrict__ x8 = static_cast<const uint8_t*>(x_in);
+  if constexpr (U8) {
+    for (int i = threadIdx.x; i < 256; i += kStemThreads) s_lut[i] = __fdiv_rn(static_cast<float>(i), 255.0f) * 2.0f - 1.0f;
+  }
   for (int co = threadIdx.x; co < COUT; co += kStemThreads) {
     float ss = 0.f;
     for (int ci = 0; ci < cx; ++ci) ss = fmaf(v[co * cx + ci], v[co * cx + ci], ss);
@@ -237,11 +248,14 @@ __global__ void __launch_bounds__(kStemThreads)
     const long long n = pix / hw;
     const long long sp = pix - n * hw;
     const float* xp = x + n * cx * hw + sp;
+    const uint8_t* xp8 = x8 + pix * cx;
     float acc[COUT];
 #pragma unroll
     for (int co = 0; co < COUT; ++co) acc[co] = s_shift[co];
     for (int ci = 0; ci < cx; ++ci) {
-      const float xv = __ldg(xp + (long long)ci * hw);
+      float xv;
+      if constexpr (U8) xv = s_lut[__ldg(xp8 + ci)];
+      else xv = __ldg(xp + (long long)ci * hw);
 #pragma unroll
       for (int co = 0; co < COUT; ++co) acc[co] = fmaf(xv, s_w[ci * COUT + co], acc[co]);
     }
@@ -447,11 +461,11 @@ extern "C" int vub_adam_wn_step_dev(const vub_adam_entry* table_dev, int32_t n_e
   return check_launch("adam_wn_step_dev");
 }
 
-extern "C" int vub_stem_fwd(const float* x_nchw, const float* v, const float* g, const float* gamma,
-                            const float* beta, const float* bias, int32_t batch, int32_t cx, int32_t h,
-                            int32_t w, int32_t cout, void* out_raw, void* out_elu, void* stream) {
+static int stem_fwd_launch(const void* x, bool u8, const float* v, const float* g, const float* gamma, const float* beta,
+                           const float* bias, int32_t batch, int32_t cx, int32_t h, int32_t w, int32_t cout, void* out_raw,
+                           void* out_elu, void* stream) {
   clear_error();
-  if (!x_nchw || !v || !g || !gamma || !beta || !bias) return fail(VUB_E_NULL, "stem_fwd: NULL input");
+  if (!x || !v || !g || !gamma || !beta || !bias) return fail(VUB_E_NULL, "stem_fwd: NULL input");
   if (!out_raw && !out_elu) return fail(VUB_E_FLAGS, "stem_fwd: no output");
   if (batch <= 0 || h <= 0 || w <= 0 || cx <= 0 || cx > kStemMaxCx)
     return fail(VUB_E_SHAPE, "stem_fwd: batch %d cx %d h %d w %d (cx <= %d)", batch, cx, h, w, kStemMaxCx);
@@ -469,17 +483,31 @@ extern "C" int vub_stem_fwd(const float* x_nchw, const float* v, const float* g,
   const long long max_grid = (long long)n_sm * 8;  // persistent blocks, each looping over 128-pixel chunks
   const unsigned grid = static_cast<unsigned>(chunks < max_grid ? chunks : max_grid);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (cout == 32)
-    stem_kernel<32><<<grid, kStemThreads, 0, s>>>(x_nchw, v, g, gamma, beta, bias, cx, hw, total,
-                                                  static_cast<__nv_bfloat16*>(out_raw),
-                                                  static_cast<__nv_bfloat16*>(out_elu));
+  __nv_bfloat16* o_raw = static_cast<__nv_bfloat16*>(out_raw);
+  __nv_bfloat16* o_elu = static_cast<__nv_bfloat16*>(out_elu);
+  if (cout == 32 && !u8)
+    stem_kernel<32, false><<<grid, kStemThreads, 0, s>>>(x, v, g, gamma, beta, bias, cx, hw, total, o_raw, o_elu);
+  else if (cout == 64 && !u8)
+    stem_kernel<64, false><<<grid, kStemThreads, 0, s>>>(x, v, g, gamma, beta, bias, cx, hw, total, o_raw, o_elu);
+  else if (cout == 32)
+    stem_kernel<32, true><<<grid, kStemThreads, 0, s>>>(x, v, g, gamma, beta, bias, cx, hw, total, o_raw, o_elu);
   else if (cout == 64)
-    stem_kernel<64><<<grid, kStemThreads, 0, s>>>(x_nchw, v, g, gamma, beta, bias, cx, hw, total,
-                                                  static_cast<__nv_bfloat16*>(out_raw),
-                                                  static_cast<__nv_bfloat16*>(out_elu));
+    stem_kernel<64, true><<<grid, kStemThreads, 0, s>>>(x, v, g, gamma, beta, bias, cx, hw, total, o_raw, o_elu);
   else
     return fail(VUB_E_SHAPE, "stem_fwd: cout %d not in {32,64}", cout);
   return check_launch("stem_fwd");
+}
+
+extern "C" int vub_stem_fwd(const float* x_nchw, const float* v, const float* g, const float* gamma,
+                            const float* beta, const float* bias, int32_t batch, int32_t cx, int32_t h,
+                            int32_t w, int32_t cout, void* out_raw, void* out_elu, void* stream) {
+  return stem_fwd_launch(x_nchw, false, v, g, gamma, beta, bias, batch, cx, h, w, cout, out_raw, out_elu, stream);
+}
+
+extern "C" int vub_stem_fwd_u8(const uint8_t* x_nhwc_u8, const float* v, const float* g, const float* gamma,
+                               const float* beta, const float* bias, int32_t batch, int32_t cx, int32_t h,
+                               int32_t w, int32_t cout, void* out_raw, void* out_elu, void* stream) {
+  return stem_fwd_launch(x_nhwc_u8, true, v, g, gamma, beta, bias, batch, cx, h, w, cout, out_raw, out_elu, stream);
 }
 
 extern "C" int32_t vub_latent_num_partials(int32_t batch, int32_t c, int32_t h, int32_t w) {

@@ -115,6 +115,10 @@ _WEIGHT_EPOCH = [0]
 
 
 def bump_weight_epoch() -> int:
+    """Invalidate every prepared-weight cache of the process.  REQUIRED after writing parameters in a way autograd's
+    version counters do not see — ``p.data.copy_()`` / ``p.data.mul_()`` (EMA, checkpoint averaging, custom init),
+    raw-pointer writers — because ``weights_key`` cannot notice those (the reference re-normalises the weights in
+    every forward, so the idiom works there).  ``VunetAlter.invalidate_weights()`` is the per-model spelling."""
     _WEIGHT_EPOCH[0] += 1
     return _WEIGHT_EPOCH[0]
 
@@ -136,6 +140,7 @@ class WeightBank:
         self._device = None
         self._views = {}
         self._with_wd = False
+        self.generation = 0  # bumped when the forward buffers are re-allocated (graphs captured earlier are stale)
         self.tape = None  # training: list the forward pass appends its records to (training.Tape)
         self.precision = "bf16"  # validation.WeightBank32 says "fp32"
 
@@ -169,8 +174,8 @@ class WeightBank:
         return WeightBank(slots)
 
     # -- allocation -------------------------------------------------------------------------------
-    def _allocate(self, device: torch.device, with_wd: bool) -> None:
-        w_off, s_off, rows, wd_off = 0, 0, 0, 0
+    def _layout(self):
+        w_off, s_off, wd_off = 0, 0, 0
         layout = []
         for slot in self.slots:
             first = slot[0]
@@ -191,21 +196,37 @@ class WeightBank:
             w_off += cpad * k
             s_off += cpad
             wd_off += k * cout_k
-        self._w = torch.zeros(w_off, dtype=torch.bfloat16, device=device)
-        self._wd = torch.zeros(wd_off if with_wd else 0, dtype=torch.bfloat16, device=device)
-        # Tile-major pre-swizzled copies (1-D bulk weight loads, vub_wn_entry.w_tiled).  Measured neutral in every
-        # kernel although a bulk copy is 1.7x cheaper for the TMA unit than a tensor box (profiles/r01_exp_bulk.log):
-        # the weight tile is not what bounds them.  Opt-in (VUB_TILED_WEIGHTS=1) so that the default path does not
-        # carry a second copy of the weights.
+        return layout, w_off, s_off, wd_off
+
+    def _allocate(self, device: torch.device, with_wd: bool) -> None:
+        """(Re)build the device table of ``wn_prep`` entries.  The packed-weight buffers a captured CUDA graph may
+        have baked in (``_w``, ``_scale``, ``_shift``, tile-major copies) depend only on the layer shapes: they are
+        allocated ONCE per device and survive parameter-pointer changes and the first training step; the
+        data-gradient matrices (``_wd``) are a separate allocation made when training first asks for them.
+        ``generation`` counts re-allocations of the forward buffers (device moves only) — graph holders compare it."""
+        layout, w_off, s_off, wd_off = self._layout()
         tiled = os.environ.get("VUB_TILED_WEIGHTS", "0") == "1"
-        self._wt = torch.zeros(w_off if tiled else 0, dtype=torch.bfloat16, device=device)
-        self._wdt = torch.zeros(wd_off if (with_wd and tiled) else 0, dtype=torch.bfloat16, device=device)
+        if self._device != device or getattr(self, "_tiled", None) != tiled:
+            self._w = torch.zeros(w_off, dtype=torch.bfloat16, device=device)
+            # Tile-major pre-swizzled copies (1-D bulk weight loads, vub_wn_entry.w_tiled).  Measured neutral in every
+            # kernel although a bulk copy is 1.7x cheaper for the TMA unit than a tensor box
+            # (profiles/r01_exp_bulk.log): the weight tile is not what bounds them.  Opt-in (VUB_TILED_WEIGHTS=1) so
+            # that the default path does not carry a second copy of the weights.
+            self._wt = torch.zeros(w_off if tiled else 0, dtype=torch.bfloat16, device=device)
+            self._scale = torch.zeros(s_off, dtype=torch.float32, device=device)
+            self._shift = torch.zeros(s_off, dtype=torch.float32, device=device)
+            self._wd = torch.zeros(0, dtype=torch.bfloat16, device=device)
+            self._wdt = torch.zeros(0, dtype=torch.bfloat16, device=device)
+            self._tiled = tiled
+            self.generation += 1
+        if with_wd and self._wd.numel() == 0:
+            self._wd = torch.zeros(wd_off, dtype=torch.bfloat16, device=device)
+            self._wdt = torch.zeros(wd_off if tiled else 0, dtype=torch.bfloat16, device=device)
         self._with_wd = with_wd
-        self._scale = torch.zeros(s_off, dtype=torch.float32, device=device)
-        self._shift = torch.zeros(s_off, dtype=torch.float32, device=device)
         entries = []
         self._views = {}
         self._entry_of = {}  # id(NormConv2d) -> its host-side WnEntry (optim.FusedAdam embeds it)
+        rows = 0
         for si, (slot, (wo, so, k, cout, cpad, nsrc, c_src, wdo, cout_k)) in enumerate(zip(self.slots, layout)):
             first = slot[0]
             w = self._w[wo:wo + cpad * k].view(cpad, k)
@@ -367,7 +388,10 @@ class NormConv2d(nn.Module):
                                       ksize=cw.ksize, stride=cw.stride,
                                       residual=None if residual is None else residual.raw, want_raw=want_raw,
                                       want_elu=want_elu, d2s=d2s)
-            return Act(raw, elu)
+            out = Act(raw, elu)
+            if bank.tape is not None:
+                bank.tape.conv(self, srcs, residual, out, d2s)
+            return out
         xs, elu_in = [], 0
         for s, (a, m) in enumerate(srcs):
             if m == "elu" and a.elu is None and a.raw is not None:
@@ -389,7 +413,7 @@ class NormConv2d(nn.Module):
         if bank.precision == "fp32":
             out, _ = ops.conv_fwd32([a.pick(m) for a, m in srcs], cw.w32, cw.scale, cw.shift, cout=cw.cout, ksize=cw.ksize,
                                     want_raw=True, want_elu=False, nchw=layout == "nchw")
-            return out, None
+            return out, (bank.tape.conv(self, srcs, None, None, False) if bank.tape is not None else None)
         out = ops.conv_fwd_f32([a.pick(m) for a, m in srcs], cw.w, cw.scale, cw.shift, ksize=cw.ksize, layout=layout,
                                w_tiled=cw.w_tiled,
                                cout_valid=cw.cout)
@@ -399,6 +423,9 @@ class NormConv2d(nn.Module):
         return out, slot
 
     def _run_stem(self, x: torch.Tensor, want_raw=True, want_elu=True, bank: Optional[WeightBank] = None) -> Act:
+        if x.dtype == torch.uint8 and bank is not None and (bank.precision == "fp32" or bank.tape is not None):
+            # uint8 HWC images are an inference front-end format; training / validation take the reference's tensors
+            x = ((x.float().div(255.0) * 2.0) - 1.0).permute(0, 3, 1, 2).contiguous()
         if bank is not None and bank.precision == "fp32":
             x_nhwc, _ = ops.nchw_to_nhwc32(x, True, False)
             return self._run(bank, [(Act(x_nhwc, None), "raw")], want_raw=want_raw, want_elu=want_elu)
@@ -411,6 +438,7 @@ class NormConv2d(nn.Module):
 
     # reference-compatible standalone call -----------------------------------------------------
     def forward(self, x):
+        warn_forward_only(self, "NormConv2d.forward", x)
         if self.kernel_size == 1 and self.in_channels not in _SUPPORTED_C and self.out_channels in (32, 64):
             if not x.is_cuda:
                 raise RuntimeError("vunet_b200 has no CPU path: inputs must live on a CUDA device")
@@ -441,6 +469,7 @@ class Downsample(nn.Module):
         return self.down._run(bank, [(h, "raw")], want_raw=want_raw, want_elu=want_elu)
 
     def forward(self, x):
+        warn_forward_only(self, "Downsample.forward", x)
         bank = _solo_bank(self)
         return self._run(bank, to_act(x, True, False)).nchw()
 
@@ -461,6 +490,7 @@ class Upsample(nn.Module):
         return self.up._run(bank, [(h, "raw")], want_raw=want_raw, want_elu=want_elu, d2s=True)
 
     def forward(self, x):
+        warn_forward_only(self, "Upsample.forward", x)
         bank = _solo_bank(self)
         return self._run(bank, to_act(x, True, False)).nchw()
 
@@ -504,6 +534,7 @@ class VunetRNB(nn.Module):
         return self.conv._run(bank, srcs, residual=x, want_raw=want_raw, want_elu=want_elu)
 
     def forward(self, x, a=None):
+        warn_forward_only(self, "VunetRNB.forward", x, a)
         bank = _solo_bank(self)
         xa = to_act(x)
         aa = None if a is None else to_act(a, need_raw=False, need_elu=True)
@@ -511,6 +542,26 @@ class VunetRNB(nn.Module):
             c = self.nin.in_channels // 2
             aa = [Act(None, aa.elu[..., :c].contiguous()), Act(None, aa.elu[..., c:].contiguous())]
         return self._run(bank, xa, aa).nchw()
+
+
+_WARNED_FWD_ONLY = [False]
+
+
+def warn_forward_only(module: nn.Module, what: str, *inputs) -> None:
+    """Only ``VunetAlter.forward`` records a backward schedule (w.r.t. parameters).  Every other entry point returns
+    tensors without autograd history; the reference is differentiable on all of them, so a loss built on them would
+    silently train nothing: raise when an INPUT asks for gradients, warn once when only parameters do."""
+    if not torch.is_grad_enabled():
+        return
+    if any(isinstance(t, torch.Tensor) and t.requires_grad for t in inputs):
+        raise NotImplementedError(f"vunet_b200: {what} is forward-only; its inputs require grad but no gradient would "
+                                  "flow (only VunetAlter.forward is differentiable, w.r.t. parameters)")
+    if not _WARNED_FWD_ONLY[0] and any(p.requires_grad for p in module.parameters()):
+        _WARNED_FWD_ONLY[0] = True
+        import warnings
+        warnings.warn(f"vunet_b200: {what} is forward-only (outputs carry no autograd history); only "
+                      "VunetAlter.forward is differentiable. Wrap the call in torch.no_grad() to silence this.",
+                      stacklevel=3)
 
 
 def _solo_bank(module: nn.Module) -> WeightBank:

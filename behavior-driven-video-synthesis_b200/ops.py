@@ -39,6 +39,15 @@ _LIB.define(
     "int stride, bool want_raw, bool want_elu, bool d2s, bool nchw) -> Tensor[]"
 )
 _LIB.define("nchw_to_nhwc32(Tensor x, bool want_raw, bool want_elu) -> Tensor[]")
+_LIB.define(
+    "conv_dgrad32(Tensor dy, Tensor w, Tensor scale, Tensor(a!) dx0, Tensor(b!)? dx1, Tensor? mask0, Tensor? mask1, "
+    "Tensor? add0, Tensor? add1, Tensor? add20, Tensor? add21, int cout, int ksize, int stride, bool d2s) -> ()"
+)
+_LIB.define(
+    "conv_wgrad32(Tensor dy, Tensor x0, Tensor? x1, Tensor(a!) gt, Tensor(b!) dy_sum, int cout, int ksize, int stride, "
+    "bool d2s) -> ()"
+)
+_LIB.define("latent_bwd32(Tensor logstd, Tensor? eps, Tensor? d_mu, Tensor? d_ls, Tensor? dz) -> Tensor")
 # ---- training half (mutating ops: gradient buffers are accumulated in place) ----------------------
 _LIB.define(
     "conv_dgrad(Tensor dy, Tensor wd, Tensor(a!) dx0, Tensor(b!)? dx1, Tensor? mask0, Tensor? mask1, "
@@ -49,10 +58,11 @@ _LIB.define(
     "conv_wgrad(Tensor dy, Tensor x0, Tensor? x1, Tensor(a!) gt, Tensor(b!) dy_sum, int ksize, int stride, "
     "bool d2s) -> ()"
 )
-_LIB.define("wn_bwd(Tensor table, int n_entries, int total_rows, bool accumulate) -> ()")
-_LIB.define("adam_wn_step(Tensor table, int n_entries, int total_rows, float beta1, float beta2, float eps, int step) -> ()")
+_LIB.define("wn_bwd(Tensor table, int n_entries, int total_rows, bool accumulate, float nbytes=0.0) -> ()")
+_LIB.define("adam_wn_step(Tensor table, int n_entries, int total_rows, float beta1, float beta2, float eps, int step, "
+            "float nbytes=0.0) -> ()")
 _LIB.define("adam_wn_step_dev(Tensor table, int n_entries, int total_rows, float beta1, float beta2, float eps, "
-            "Tensor(a!) step) -> ()")
+            "Tensor(a!) step, float nbytes=0.0) -> ()")
 _LIB.define("stem_bwd(Tensor x, Tensor dy, Tensor(a!) gt, Tensor(b!) dy_sum) -> ()")
 _LIB.define("latent_bwd(Tensor logstd, Tensor? eps, Tensor? d_mu, Tensor? d_ls, Tensor? dz) -> Tensor")
 _LIB.define("nchw_to_nhwc_pad(Tensor x, int c_pad) -> Tensor")
@@ -174,10 +184,16 @@ def _wn_prep_cuda(table, n_entries, total_rows) -> None:
 
 
 def _stem_fwd_cuda(x, v, g, gamma, beta, bias, want_raw, want_elu) -> List[torch.Tensor]:
-    if x.dtype != torch.float32 or x.dim() != 4:
-        raise ValueError("stem_fwd: x must be NCHW fp32")
+    u8 = x.dtype == torch.uint8
+    if x.dim() != 4 or x.dtype not in (torch.float32, torch.uint8):
+        raise ValueError("stem_fwd: x must be NCHW fp32, or a uint8 HWC image batch [B, H, W, C]")
     x = x.contiguous()
-    B, cx, H, W = x.shape
+    if u8:  # uint8 HWC images as the reference holds them before ToTensor() + (x * 2 - 1)
+        B, H, W, cx = x.shape
+    else:
+        B, cx, H, W = x.shape
+    if cx != v.shape[1]:
+        raise ValueError(f"stem_fwd: input has {cx} channels, the layer expects {v.shape[1]}")
     cout = v.shape[0]
     outs = []
     raw = elu = None
@@ -187,9 +203,10 @@ def _stem_fwd_cuda(x, v, g, gamma, beta, bias, want_raw, want_elu) -> List[torch
     if want_elu:
         elu = torch.empty((B, H, W, cout), dtype=torch.bfloat16, device=x.device)
         outs.append(elu)
-    nbytes = float(x.numel() * 4 + sum(o.numel() * 2 for o in outs))
+    nbytes = float(x.numel() * x.element_size() + sum(o.numel() * 2 for o in outs))
     N.check(
-        _launch(f"stem<{cout}> {cx}->{cout} @{H}x{W}", N.lib().vub_stem_fwd, x.data_ptr(), v.data_ptr(), g.data_ptr(), gamma.data_ptr(),
+        _launch(f"stem<{cout}> {cx}->{cout}{' u8' if u8 else ''} @{H}x{W}",
+                N.lib().vub_stem_fwd_u8 if u8 else N.lib().vub_stem_fwd, x.data_ptr(), v.data_ptr(), g.data_ptr(), gamma.data_ptr(),
                 beta.data_ptr(), bias.data_ptr(), B, cx, H, W, cout, _p(raw), _p(elu), _stream(),
                 flops=2.0 * B * H * W * cx * cout, bytes_=nbytes),
         "vub_stem_fwd",
@@ -336,23 +353,24 @@ def _conv_wgrad_cuda(dy, x0, x1, gt, dy_sum, ksize, stride, d2s) -> None:
                     bytes_=nbytes), "vub_conv_wgrad")
 
 
-def _wn_bwd_cuda(table, n_entries, total_rows, accumulate) -> None:
-    N.check(_launch("wn_bwd", N.lib().vub_wn_bwd, table.data_ptr(), n_entries, total_rows, int(accumulate), _stream()),
-            "vub_wn_bwd")
+def _wn_bwd_cuda(table, n_entries, total_rows, accumulate, nbytes=0.0) -> None:
+    # nbytes: algorithmic bytes of this table (split partials read once, v read, dv written; training.GradBank)
+    N.check(_launch("wn_bwd", N.lib().vub_wn_bwd, table.data_ptr(), n_entries, total_rows, int(accumulate), _stream(),
+                    bytes_=float(nbytes)), "vub_wn_bwd")
 
 
-def _adam_wn_step_cuda(table, n_entries, total_rows, beta1, beta2, eps, step) -> None:
+def _adam_wn_step_cuda(table, n_entries, total_rows, beta1, beta2, eps, step, nbytes=0.0) -> None:
     N.check(_launch("adam_wn_step", N.lib().vub_adam_wn_step, table.data_ptr(), n_entries, total_rows, beta1, beta2, eps,
-                    step, _stream()), "vub_adam_wn_step")
+                    step, _stream(), bytes_=float(nbytes)), "vub_adam_wn_step")
 
 
-def _adam_wn_step_dev_cuda(table, n_entries, total_rows, beta1, beta2, eps, step) -> None:
+def _adam_wn_step_dev_cuda(table, n_entries, total_rows, beta1, beta2, eps, step, nbytes=0.0) -> None:
     if step.dtype != torch.int32 or step.numel() != 1:
         raise ValueError("adam_wn_step_dev: step must be a 1-element int32 tensor")
     global LAUNCHES
     LAUNCHES += 1  # the counter increment is a second (1-thread) launch
     N.check(_launch("adam_wn_step", N.lib().vub_adam_wn_step_dev, table.data_ptr(), n_entries, total_rows, beta1, beta2,
-                    eps, step.data_ptr(), _stream()), "vub_adam_wn_step_dev")
+                    eps, step.data_ptr(), _stream(), bytes_=float(nbytes)), "vub_adam_wn_step_dev")
 
 
 def _stem_bwd_cuda(x, dy, gt, dy_sum) -> None:
@@ -439,6 +457,82 @@ def _nchw_to_nhwc32_cuda(x, want_raw, want_elu):
     return [t for t in (raw, elu) if t is not None]
 
 
+def _check_act32(t: torch.Tensor, name: str) -> None:
+    if t.dtype != torch.float32 or t.dim() != 4 or not t.is_contiguous():
+        raise ValueError(f"{name}: expected contiguous NHWC fp32 [B,H,W,C], got {t.dtype} {tuple(t.shape)}")
+
+
+def _conv_dgrad32_cuda(dy, w, scale, dx0, dx1, mask0, mask1, add0, add1, add20, add21, cout, ksize, stride, d2s) -> None:
+    _check_act32(dy, "conv_dgrad32 dy")
+    _check_act32(dx0, "conv_dgrad32 dx0")
+    B, H, W, c_src = dx0.shape
+    nsrc = 1 if dx1 is None else 2
+    Ho, Wo = H // stride, W // stride
+    want = (B, 2 * Ho, 2 * Wo, cout // 4) if d2s else (B, Ho, Wo, cout)
+    if tuple(dy.shape) != want:
+        raise ValueError(f"conv_dgrad32: dy {tuple(dy.shape)} != {want}")
+    if w.dtype != torch.float32 or w.dim() != 2 or w.shape[0] != nsrc * ksize * ksize * c_src or w.shape[1] < cout:
+        raise ValueError(f"conv_dgrad32: weight {tuple(w.shape)} does not match K / cout")
+    for t in (dx1, mask0, mask1, add0, add1, add20, add21):
+        if t is not None and (t.shape != dx0.shape or t.dtype != torch.float32 or not t.is_contiguous()):
+            raise ValueError("conv_dgrad32: dx / mask / addend tensors must be contiguous NHWC fp32 of the input shape")
+    d = N.DgradF32Desc()
+    d.dy, d.w, d.scale = dy.data_ptr(), w.data_ptr(), scale.data_ptr()
+    d.dx[0], d.dx[1] = dx0.data_ptr(), _p(dx1)
+    d.mask_elu[0], d.mask_elu[1] = _p(mask0), _p(mask1)
+    d.addend[0], d.addend[1] = _p(add0), _p(add1)
+    d.addend2[0], d.addend2[1] = _p(add20), _p(add21)
+    d.nsrc, d.c_src, d.batch, d.hin, d.win, d.cout = nsrc, c_src, B, H, W, cout
+    d.w_pitch, d.ksize, d.stride, d.flags = w.stride(0), ksize, stride, (N.CONV_D2S if d2s else 0)
+    N.check(_launch(f"conv_dgrad32 {nsrc}x{c_src}<-{cout} k{ksize} s{stride} @{H}x{W}", N.lib().vub_conv_dgrad_f32,
+                    C.byref(d), _stream(), flops=2.0 * B * Ho * Wo * cout * w.shape[0]), "vub_conv_dgrad_f32")
+
+
+def _conv_wgrad32_cuda(dy, x0, x1, gt, dy_sum, cout, ksize, stride, d2s) -> None:
+    _check_act32(dy, "conv_wgrad32 dy")
+    _check_act32(x0, "conv_wgrad32 x0")
+    B, H, W, c_src = x0.shape
+    nsrc = 1
+    if x1 is not None:
+        _check_act32(x1, "conv_wgrad32 x1")
+        nsrc = 2
+    Ho, Wo = H // stride, W // stride
+    want = (B, 2 * Ho, 2 * Wo, cout // 4) if d2s else (B, Ho, Wo, cout)
+    if tuple(dy.shape) != want:
+        raise ValueError(f"conv_wgrad32: dy {tuple(dy.shape)} != {want}")
+    K = nsrc * ksize * ksize * c_src
+    if (gt.dtype != torch.float32 or gt.dim() != 3 or gt.shape[1] < cout or gt.shape[2] != K or gt.stride(2) != 1
+            or dy_sum.dtype != torch.float32 or dy_sum.dim() != 2 or dy_sum.shape[0] != gt.shape[0]
+            or dy_sum.shape[1] < cout or dy_sum.stride(1) != 1):
+        raise ValueError(f"conv_wgrad32: gt {tuple(gt.shape)} / dy_sum {tuple(dy_sum.shape)} do not match "
+                         f"[n_split, cout={cout}, K={K}]")
+    d = N.WgradF32Desc()
+    d.dy, d.gt, d.dy_sum = dy.data_ptr(), gt.data_ptr(), dy_sum.data_ptr()
+    d.x[0], d.x[1] = x0.data_ptr(), _p(x1)
+    d.nsrc, d.c_src, d.batch, d.hin, d.win, d.cout = nsrc, c_src, B, H, W, cout
+    d.ksize, d.stride, d.flags = ksize, stride, (N.CONV_D2S if d2s else 0)
+    d.n_split, d.gt_pitch, d.split_stride, d.sum_stride = gt.shape[0], gt.stride(1), gt.stride(0), dy_sum.stride(0)
+    N.check(_launch(f"conv_wgrad32 {nsrc}x{c_src}x{cout} k{ksize} s{stride} @{H}x{W}", N.lib().vub_conv_wgrad_f32,
+                    C.byref(d), _stream(), flops=2.0 * B * Ho * Wo * cout * K), "vub_conv_wgrad_f32")
+
+
+def _latent_bwd32_cuda(logstd, eps, d_mu, d_ls, dz) -> torch.Tensor:
+    if logstd.dtype != torch.float32 or logstd.dim() != 4 or not logstd.is_contiguous():
+        raise ValueError("latent_bwd32: logstd must be contiguous NCHW fp32")
+    B, c, h, w = logstd.shape
+    for t in (eps, d_mu, d_ls):
+        if t is not None and (t.dtype != torch.float32 or t.shape != logstd.shape or not t.is_contiguous()):
+            raise ValueError("latent_bwd32: eps / d_mu / d_ls must be contiguous NCHW fp32 like logstd")
+    if dz is not None:
+        _check_act32(dz, "latent_bwd32 dz")
+        if tuple(dz.shape) != (B, h, w, c):
+            raise ValueError("latent_bwd32: dz shape mismatch")
+    out = torch.empty((B, h, w, 2 * c), dtype=torch.float32, device=logstd.device)
+    N.check(_launch("latent_bwd32", N.lib().vub_latent_bwd_f32, logstd.data_ptr(), _p(eps), _p(d_mu), _p(d_ls), _p(dz),
+                    B, c, h, w, out.data_ptr(), _stream()), "vub_latent_bwd_f32")
+    return out
+
+
 def _frames_to_uint8_cuda(imgs):
     if imgs.dtype != torch.float32 or imgs.dim() != 4 or imgs.shape[1] != 3:
         raise ValueError("frames_to_uint8: imgs must be NCHW fp32 with 3 channels")
@@ -453,6 +547,9 @@ def _frames_to_uint8_cuda(imgs):
 _LIB.impl("conv_fwd", _conv_fwd_cuda, "CUDA")
 _LIB.impl("frames_to_uint8", _frames_to_uint8_cuda, "CUDA")
 _LIB.impl("conv_fwd32", _conv_fwd32_cuda, "CUDA")
+_LIB.impl("conv_dgrad32", _conv_dgrad32_cuda, "CUDA")
+_LIB.impl("conv_wgrad32", _conv_wgrad32_cuda, "CUDA")
+_LIB.impl("latent_bwd32", _latent_bwd32_cuda, "CUDA")
 _LIB.impl("nchw_to_nhwc32", _nchw_to_nhwc32_cuda, "CUDA")
 _LIB.impl("conv_dgrad", _conv_dgrad_cuda, "CUDA")
 _LIB.impl("conv_wgrad", _conv_wgrad_cuda, "CUDA")
@@ -559,6 +656,25 @@ def nchw_to_nhwc32(x, want_raw=True, want_elu=True):
     return (next(it) if want_raw else None), (next(it) if want_elu else None)
 
 
+def conv_dgrad32(dy, w, scale, dx, *, mask=(None, None), addend=(None, None), addend2=(None, None), cout: int,
+                 ksize: int, stride: int = 1, d2s: bool = False) -> None:
+    """fp32 validation counterpart of :func:`conv_dgrad` (``w``: the forward fp32 matrix ``v/||v||``)."""
+    dx = list(dx) + [None] * (2 - len(dx))
+    mask = list(mask) + [None] * (2 - len(mask))
+    addend = list(addend) + [None] * (2 - len(addend))
+    addend2 = list(addend2) + [None] * (2 - len(addend2))
+    _ops.conv_dgrad32(dy, w, scale, dx[0], dx[1], mask[0], mask[1], addend[0], addend[1], addend2[0], addend2[1], cout,
+                      ksize, stride, d2s)
+
+
+def conv_wgrad32(dy, x, gt, dy_sum, *, cout: int, ksize: int, stride: int = 1, d2s: bool = False) -> None:
+    _ops.conv_wgrad32(dy, x[0], x[1] if len(x) > 1 else None, gt, dy_sum, cout, ksize, stride, d2s)
+
+
+def latent_bwd32(logstd, eps, d_mu, d_ls, dz) -> torch.Tensor:
+    return _ops.latent_bwd32(logstd, eps, d_mu, d_ls, dz)
+
+
 # ---- training half ------------------------------------------------------------------------------
 def conv_dgrad(dy, wd, dx, *, mask=(None, None), addend=(None, None), addend2=(None, None), ksize: int,
                stride: int = 1, d2s: bool = False, wd_tiled: Optional[torch.Tensor] = None) -> None:
@@ -575,18 +691,18 @@ def conv_wgrad(dy, x, gt, dy_sum, *, ksize: int, stride: int = 1, d2s: bool = Fa
     _ops.conv_wgrad(dy, x[0], x[1] if len(x) > 1 else None, gt, dy_sum, ksize, stride, d2s)
 
 
-def wn_bwd(table: torch.Tensor, n_entries: int, total_rows: int, accumulate: bool = False) -> None:
-    _ops.wn_bwd(table, n_entries, total_rows, accumulate)
+def wn_bwd(table: torch.Tensor, n_entries: int, total_rows: int, accumulate: bool = False, nbytes: float = 0.0) -> None:
+    _ops.wn_bwd(table, n_entries, total_rows, accumulate, nbytes)
 
 
 def adam_wn_step(table: torch.Tensor, n_entries: int, total_rows: int, beta1: float, beta2: float, eps: float,
-                 step: int) -> None:
-    _ops.adam_wn_step(table, n_entries, total_rows, beta1, beta2, eps, step)
+                 step: int, nbytes: float = 0.0) -> None:
+    _ops.adam_wn_step(table, n_entries, total_rows, beta1, beta2, eps, step, nbytes)
 
 
 def adam_wn_step_dev(table: torch.Tensor, n_entries: int, total_rows: int, beta1: float, beta2: float, eps: float,
-                     step: torch.Tensor) -> None:
-    _ops.adam_wn_step_dev(table, n_entries, total_rows, beta1, beta2, eps, step)
+                     step: torch.Tensor, nbytes: float = 0.0) -> None:
+    _ops.adam_wn_step_dev(table, n_entries, total_rows, beta1, beta2, eps, step, nbytes)
 
 
 def stem_bwd(x, dy, gt, dy_sum) -> None:

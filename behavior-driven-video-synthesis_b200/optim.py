@@ -135,6 +135,11 @@ class FusedAdam:
         else:
             self._table = (host.to(self._exp_avg.device), len(entries), rows)
         self._last_build = (live, bank)
+        # algorithmic bytes of one step: p, g, m, s read + p, m, s written (28 B per parameter) + the
+        # packed bf16 outputs (forward matrix and, in training, the data-gradient matrix) of the tensor-core convs
+        self._nbytes = float(sum(28 * sum(p.numel() for p in _five(m))
+                                 + (4 * m.conv.weight_v.numel() if bank._entry_of.get(id(m)) is not None else 0)
+                                 for m in live))
 
     def sync_lr(self) -> None:
         """Push changed ``param_groups[i]["lr"]`` values into the device table without a step (the table is updated
@@ -177,7 +182,7 @@ class FusedAdam:
         self._step += 1
         b1, b2 = self.defaults["betas"]
         table, n, rows = self._table
-        ops.adam_wn_step_dev(table, n, rows, b1, b2, self.defaults["eps"], self._step_dev)
+        ops.adam_wn_step_dev(table, n, rows, b1, b2, self.defaults["eps"], self._step_dev, getattr(self, "_nbytes", 0.0))
         # parameters were written through raw pointers: autograd version counters did not move, so tell every
         # other cache of prepared weights (sub-module banks, the fp32 validation bank) that they are stale; the
         # training bank was re-emitted by this very launch.

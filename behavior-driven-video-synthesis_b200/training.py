@@ -87,6 +87,11 @@ class GradBank:
                 convs.append(rec[1])
         self.key = _tape_signature(tape)
         dev = next(model.parameters()).device
+        # fp32 validation mode: fp32 activations, every conv (stems included) is a regular conv of the bank, output
+        # rows are not padded, pixel splits are chosen here (vub_conv_wgrad_f32 takes any split count)
+        fp32 = self.fp32 = bank.precision == "fp32"
+        is_stem = (lambda cv: False) if fp32 else (lambda cv: cv._vub_stem)
+        rows_of = (lambda cw: cw.cout) if fp32 else (lambda cw: cw.cout_k)
         members: Dict[int, List[NormConv2d]] = {}
         for slot in bank.slots:
             members[id(slot[0])] = slot
@@ -101,20 +106,23 @@ class GradBank:
                 xs = tuple(srcs[0][0].pick(srcs[0][1]).shape)
                 B_, H_, W_, _ = xs
                 ho, wo = H_ // cw.stride, W_ // cw.stride
+                if fp32:
+                    shapes[id(cv)] = max(1, min(64, (B_ * ho * wo) // 512))
+                    continue
                 dys = (B_, 2 * ho, 2 * wo, cw.cout_k // 4) if d2s else (B_, ho, wo, cw.cout_k)
                 shapes[id(cv)] = ops.wgrad_splits(dys, xs, cw.nsrc, cw.ksize, cw.stride, d2s)
         off, stem_floats = 0, 0
         place = {}
         for cv in convs:  # stems first: they share one zeroed region at the front of the buffer
-            if cv._vub_stem:
+            if is_stem(cv):
                 k, rows = cv.in_channels, cv.out_channels
                 place[id(cv)] = (off, k, rows, 1)
                 off += (k + 1) * rows
         stem_floats = off
         for cv in convs:
-            if not cv._vub_stem:
+            if not is_stem(cv):
                 cw = bank.get(cv)
-                k, rows = cw.nsrc * cw.ksize * cw.ksize * cw.c_src, cw.cout_k
+                k, rows = cw.nsrc * cw.ksize * cw.ksize * cw.c_src, rows_of(cw)
                 ns = shapes[id(cv)]
                 off = (off + 3) // 4 * 4
                 place[id(cv)] = (off, k, rows, ns)
@@ -129,7 +137,7 @@ class GradBank:
         # ---- gradient buckets per owner, parameters in registration order ----
         live = []  # every NormConv2d that receives gradients
         for cv in convs:
-            live.extend([cv] if cv._vub_stem else members[id(cv)])
+            live.extend([cv] if is_stem(cv) else members[id(cv)])
         live_ids = {id(m) for m in live}
         self.buckets: Dict[str, torch.Tensor] = {}
         self.grads: Dict[int, torch.Tensor] = {}   # id(param) -> view of its bucket
@@ -137,7 +145,7 @@ class GradBank:
         self._tables = {}
         leader_of = {}
         for cv in convs:
-            for j, m in enumerate([cv] if cv._vub_stem else members[id(cv)]):
+            for j, m in enumerate([cv] if is_stem(cv) else members[id(cv)]):
                 leader_of[id(m)] = cv
         for owner in OWNER_ORDER:
             sub = getattr(model, owner, None)
@@ -157,9 +165,11 @@ class GradBank:
                 o += p.numel()
             self.buckets[owner] = flat
             self.params[owner] = plist
-            entries, rows = [], 0
+            entries, rows, nbytes = [], 0, 0
             for m in mods:
                 cv = leader_of[id(m)]
+                # algorithmic bytes: this conv's split partials read once, v read, dv written
+                nbytes += 4 * m.conv.weight_v.numel() * (place[id(cv)][3] + 2)
                 e = N.WnbEntry()
                 e.v, e.g = m.conv.weight_v.data_ptr(), m.conv.weight_g.data_ptr()
                 e.gamma, e.bias = m.gamma.data_ptr(), m.conv.bias.data_ptr()
@@ -167,7 +177,7 @@ class GradBank:
                 e.d_v, e.d_g = self.grads[id(m.conv.weight_v)].data_ptr(), self.grads[id(m.conv.weight_g)].data_ptr()
                 e.d_gamma, e.d_beta = self.grads[id(m.gamma)].data_ptr(), self.grads[id(m.beta)].data_ptr()
                 e.d_bias = self.grads[id(m.conv.bias)].data_ptr()
-                if m._vub_stem:
+                if is_stem(m):
                     c_src, col0 = m.in_channels, 0
                 else:
                     cw = bank.get(cv)
@@ -181,7 +191,7 @@ class GradBank:
                 entries.append(e)
             arr = (N.WnbEntry * len(entries))(*entries)
             host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
-            self._tables[owner] = (host.to(dev), len(entries), rows)
+            self._tables[owner] = (host.to(dev), len(entries), rows, float(nbytes))
         self._ptr_key = tuple(p.data_ptr() for ps in self.params.values() for p in ps)
 
     def __deepcopy__(self, memo):
@@ -201,18 +211,23 @@ class GradBank:
         if owner not in self._tables:
             return
         plist = self.params[owner]
-        # accumulate iff the parameters still hold OUR views from an earlier backward (no zero_grad in between)
+        # A parameter accumulates iff it still holds OUR view from an earlier backward (no zero_grad in between).
+        # Mixed buckets (per-parameter zeroing, frozen subsets): the slices of the parameters that do NOT accumulate
+        # are zeroed and the whole bucket runs with accumulate=True, so nobody's accumulated gradient is dropped.
         held = [p.grad is not None and p.grad.data_ptr() == self.grads[id(p)].data_ptr() for p in plist]
-        accumulate = all(held)
-        extra = None
-        if not accumulate and any(p.grad is not None for p in plist):
-            extra = [(p, p.grad) for p in plist if p.grad is not None and p.grad.data_ptr() != self.grads[id(p)].data_ptr()]
-        table, n, rows = self._tables[owner]
-        ops.wn_bwd(table, n, rows, accumulate)
+        accumulate = any(held)
+        if accumulate and not all(held):
+            for p, h in zip(plist, held):
+                if not h:
+                    self.grads[id(p)].zero_()
+        extra = [(p, p.grad) for p, h in zip(plist, held) if not h and p.grad is not None]
+        table, n, rows, nbytes = self._tables[owner]
+        ops.wn_bwd(table, n, rows, accumulate, nbytes)
         for p in plist:
-            p.grad = self.grads[id(p)]
-        if extra:
-            for p, old in extra:  # foreign gradient tensors (e.g. zero_grad(set_to_none=False) copies): keep their sum
+            if p.requires_grad:  # frozen parameters keep grad = None like under autograd
+                p.grad = self.grads[id(p)]
+        for p, old in extra:  # foreign gradient tensors (e.g. zero_grad(set_to_none=False) copies): keep their sum
+            if p.requires_grad:
                 p.grad.add_(old)
 
 
@@ -222,18 +237,22 @@ _WGRAD_STREAMS: dict = {}  # one weight-gradient stream per device
 
 def run_backward(model, bank: WeightBank, tape: Tape, d_imgs: Optional[torch.Tensor], reducer=None) -> None:
     """Walk the tape in reverse; parameter gradients land in ``param.grad`` (views of flat buckets)."""
+    fp32 = bank.precision == "fp32"
     gb: Optional[GradBank] = getattr(model, "_vub_grad_bank", None)
-    if gb is None or not gb.matches(tape, model):
+    if gb is None or gb.fp32 != fp32 or not gb.matches(tape, model):
         gb = GradBank(model, bank, tape)
         object.__setattr__(model, "_vub_grad_bank", gb)
     gb.zero()
     if d_imgs is not None and tape.img_slot is not None:
-        tape.img_slot.grad = ops.nchw_to_nhwc_pad(d_imgs.float(), 32)
+        if fp32:
+            tape.img_slot.grad = ops.nchw_to_nhwc32(d_imgs.float(), True, False)[0]
+        else:
+            tape.img_slot.grad = ops.nchw_to_nhwc_pad(d_imgs.float(), 32)
     # The weight gradient and the data gradient of a conv are independent: wgrad runs on a second stream, so the
     # small-map layers (10 us kernels that fill a fraction of the GPU) overlap pairwise and the tails of the large
     # ones interleave.  VUB_BWD_STREAMS=1 keeps everything on one stream.
     main = torch.cuda.current_stream()
-    two = os.environ.get("VUB_BWD_STREAMS", "2") != "1"
+    two = os.environ.get("VUB_BWD_STREAMS", "2") != "1" and not fp32
     ws = None
     if two:
         ws = _WGRAD_STREAMS.get(main.device)
@@ -263,7 +282,10 @@ def run_backward(model, bank: WeightBank, tape: Tape, d_imgs: Optional[torch.Ten
             if dy is None:
                 continue
             cw = bank.get(conv)
-            if ws is not None:
+            if fp32:  # validation mode: CUDA-core fp32 kernels, one stream
+                ops.conv_wgrad32(dy, [a.pick(m) for a, m in srcs], gb.gt[id(conv)], gb.dy_sum[id(conv)], cout=cw.cout,
+                                 ksize=cw.ksize, stride=cw.stride, d2s=d2s)
+            elif ws is not None:
                 ws.wait_stream(main)  # dy (and, the first time, the forward activations) are complete
                 with torch.cuda.stream(ws):
                     ops.conv_wgrad(dy, [a.pick(m) for a, m in srcs], gb.gt[id(conv)], gb.dy_sum[id(conv)],
@@ -290,8 +312,12 @@ def run_backward(model, bank: WeightBank, tape: Tape, d_imgs: Optional[torch.Ten
                     a1, a2 = a2, None
                 add1.append(a1)
                 add2.append(a2)
-            ops.conv_dgrad(dy, cw.wd, dx, mask=mask, addend=add1, addend2=add2, ksize=cw.ksize, stride=cw.stride,
-                           d2s=d2s, wd_tiled=cw.wd_tiled)
+            if fp32:
+                ops.conv_dgrad32(dy, cw.w32, cw.scale, dx, mask=mask, addend=add1, addend2=add2, cout=cw.cout,
+                                 ksize=cw.ksize, stride=cw.stride, d2s=d2s)
+            else:
+                ops.conv_dgrad(dy, cw.wd, dx, mask=mask, addend=add1, addend2=add2, ksize=cw.ksize, stride=cw.stride,
+                               d2s=d2s, wd_tiled=cw.wd_tiled)
             out.grad = None
         elif kind == "stem":
             _, conv, x, out = rec
@@ -303,7 +329,7 @@ def run_backward(model, bank: WeightBank, tape: Tape, d_imgs: Optional[torch.Ten
             dz = r["z_act"].grad
             if dz is None and r["d_mu"] is None and r["d_ls"] is None:
                 continue
-            r["ml_slot"].grad = ops.latent_bwd(r["logstd"], r["eps"], r["d_mu"], r["d_ls"], dz)
+            r["ml_slot"].grad = (ops.latent_bwd32 if fp32 else ops.latent_bwd)(r["logstd"], r["eps"], r["d_mu"], r["d_ls"], dz)
             r["z_act"].grad = None
     join_wgrads()
     if current is not None:
@@ -353,6 +379,9 @@ class _VunetTrainFn(torch.autograd.Function):
 
 def train_forward(model, x, c, eps: Optional[Sequence[torch.Tensor]]):
     """``VunetAlter.forward`` under autograd: returns (imgs, means, logstds, hs_left)."""
+    if x.requires_grad or c.requires_grad:
+        raise NotImplementedError("vunet_b200: VunetAlter.forward is differentiable w.r.t. its parameters only; "
+                                  "gradients w.r.t. the inputs x / c are not produced (detach them)")
     anchor = getattr(model, "_vub_anchor", None)
     if anchor is None or anchor.device != x.device:
         anchor = torch.zeros(1, device=x.device, requires_grad=True)
@@ -369,8 +398,11 @@ class BucketReducer:
     stream the moment the bucket's ``vub_wn_bwd`` has been enqueued, so it overlaps the remaining backward
     launches; ``finish`` makes the compute stream wait for all of them (before ``optimizer.step``).
 
-    Works with any ``torch.distributed`` backend (NCCL over NVLink on the B200 box; gloo in the CPU tests,
-    where the "stream" logic degenerates to synchronous calls)."""
+    On CUDA with the NCCL backend the exchange goes through the package's own C ABI —
+    ``vub_allreduce_bucket(flat, n, ncclComm, average, stream)``: ONE ncclAllReduce with ``ncclAvg`` per bucket (the
+    1/world scaling happens inside the collective, no separate scaling kernel), on a communicator this object
+    creates over the same ranks (the 128-byte id travels through ``torch.distributed``).  Any other backend (gloo
+    in the CPU tests and on single-GPU boxes) falls back to ``torch.distributed.all_reduce``."""
 
     def __init__(self, process_group=None):
         import torch.distributed as dist
@@ -378,9 +410,39 @@ class BucketReducer:
         self.dist = dist
         self.group = process_group
         self.world = dist.get_world_size(process_group)
+        self.rank = dist.get_rank(process_group)
         self._stream = None
+        self._comm = None
         self.bytes_last = 0
         self.bytes_per_step = 0
+        self.native = False
+        if (self.world > 1 and dist.get_backend(process_group) == "nccl" and torch.cuda.is_available()
+                and os.environ.get("VUB_NATIVE_ALLREDUCE", "1") != "0"):
+            self._init_native()
+
+    def _init_native(self) -> None:
+        import ctypes as C
+        lib = N.lib()
+        ident = (C.c_char * 128)()
+        if self.rank == 0:
+            N.check(lib.vub_nccl_unique_id(C.cast(ident, C.c_void_p)), "vub_nccl_unique_id")
+        box = [bytes(ident)]
+        src = self.dist.get_global_rank(self.group, 0) if self.group is not None else 0
+        self.dist.broadcast_object_list(box, src=src, group=self.group)
+        ident = (C.c_char * 128).from_buffer_copy(box[0])
+        comm = C.c_void_p()
+        N.check(lib.vub_nccl_comm_init(C.byref(comm), self.world, C.cast(ident, C.c_void_p), self.rank),
+                "vub_nccl_comm_init")
+        self._comm = comm
+        self.native = True
+
+    def __del__(self):
+        try:
+            if self._comm is not None:
+                N.lib().vub_nccl_comm_destroy(self._comm)
+                self._comm = None
+        except Exception:  # interpreter shutdown
+            pass
 
     def bucket_ready(self, owner: str, flat: Optional[torch.Tensor]) -> None:
         if flat is None or self.world == 1:
@@ -393,8 +455,12 @@ class BucketReducer:
             ev.record()
             with torch.cuda.stream(self._stream):
                 self._stream.wait_event(ev)
-                flat.div_(self.world)
-                self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM, group=self.group)
+                if self.native:
+                    N.check(N.lib().vub_allreduce_bucket(flat.data_ptr(), flat.numel(), self._comm, 1,
+                                                         self._stream.cuda_stream), "vub_allreduce_bucket")
+                else:
+                    flat.div_(self.world)
+                    self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM, group=self.group)
             flat.record_stream(self._stream)
         else:
             flat.div_(self.world)
@@ -466,6 +532,10 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self.static_loss = self._one_step()
         optimizer._step = step_snap  # capture ran the Python side of step() once without executing a kernel
+        # the graph has these objects' device buffers baked in: keep them alive even if an eager step with another
+        # batch shape later replaces the model's gradient bank
+        self._bank = model._bank(with_wd=True)
+        self._grad_bank = getattr(model, "_vub_grad_bank", None)
         self._live_ids = {id(p) for p in optimizer._params if p.grad is not None}
 
     # ---- host-resident batches: upload batch k+1 while step k runs ------------------------------------
@@ -526,6 +596,12 @@ class GraphedTrainStep:
                 dst.copy_(src, non_blocking=True)
         self.opt.sync_lr()  # learning-rate schedules: the optimizer's device table is updated in place
         self.graph.replay()
+        # The replayed Adam kernel rewrote the parameters through raw pointers: no autograd version changed.  Every
+        # OTHER prepared-weight cache (sub-module solo banks used by ``vunet.ed(vunet.eu(x))``, NormConv2d._solo_bank,
+        # the fp32 validation bank) must re-prepare; the training bank itself was re-emitted by the same kernel.
+        from .modules import bump_weight_epoch
+        bump_weight_epoch()
+        self._bank.mark_current()
         self.opt._step += 1
         if self._live_ids is not None:
             self.opt._stepped.update(self._live_ids)

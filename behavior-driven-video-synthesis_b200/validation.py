@@ -57,6 +57,7 @@ class WeightBank32:
         self._key = None
         self._ptr_key = None
         self._views = {}
+        self.generation = 0  # bumped by every re-allocation (graph holders compare it, see synthesis.py)
 
     def _params(self):
         for slot in self.slots:
@@ -64,6 +65,7 @@ class WeightBank32:
                 yield from (m.conv.weight_v, m.conv.weight_g, m.gamma, m.beta, m.conv.bias)
 
     def _allocate(self, device) -> None:
+        self.generation += 1
         w_off, s_off = 0, 0
         layout = []
         for slot in self.slots:

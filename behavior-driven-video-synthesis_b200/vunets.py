@@ -20,7 +20,7 @@ from torch import nn
 
 from . import ops
 from .modules import (lean_elu, Act, DepthToSpace, Downsample, NormConv2d, SpaceToDepth, Upsample, VunetRNB,
-                      WeightBank, _solo_bank, to_act)
+                      WeightBank, _solo_bank, bump_weight_epoch, to_act, warn_forward_only)
 
 
 def _draw_eps(shape, device) -> torch.Tensor:
@@ -52,7 +52,7 @@ class EncUp(nn.Module):
     def _run(self, bank: WeightBank, x: torch.Tensor) -> List[Act]:
         hs: List[Act] = []
         # ELU copies are skipped where every reader (the next block's 3x3, a skip connection's 1x1) applies ELU on load
-        hh, ww = x.shape[2], x.shape[3]
+        hh, ww = (x.shape[1], x.shape[2]) if x.dtype == torch.uint8 else (x.shape[2], x.shape[3])
         h = self.nin._run_stem(x, bank=bank, want_elu=not lean_elu(bank, self.nin.out_channels, hh, ww))
         for i in range(self.n_scales):
             for n in range(self.n_rnb):
@@ -65,9 +65,10 @@ class EncUp(nn.Module):
         return hs
 
     def forward(self, x, **kwargs):
+        warn_forward_only(self, type(self).__name__ + ".forward", x)
         bank = _solo_bank(self)
         _require_cuda(x)
-        return [h.nchw() for h in self._run(bank, x.float())]
+        return [h.nchw() for h in self._run(bank, _as_input(x))]
 
 
 class DecUp(EncUp):
@@ -114,6 +115,8 @@ class EncDownAlter(nn.Module):
             res["z_act"] = Act(None, ops.nchw_to_nhwc32(res["z"], False, True)[1])
             if want_elu_mu:
                 res["mu_act"] = Act(None, ops.nchw_to_nhwc32(res["mu"], False, True)[1])
+            if bank.tape is not None:
+                bank.tape.latent(ml_slot, res, eps)
             return res
         res = ops.latent_fwd(ml, eps, want_elu_z=True, want_elu_mu=want_elu_mu)
         res["z_act"] = Act(None, res["elu_z"])
@@ -152,6 +155,7 @@ class EncDownAlter(nn.Module):
 
     def forward(self, gs):
         """Reference signature: pops from the caller's list; returns (hs, means, log_stds, zs)."""
+        warn_forward_only(self, "EncDownAlter.forward", *gs)
         bank = _solo_bank(self)
         acts = [to_act(g) for g in gs]
         n_before = len(acts)
@@ -228,6 +232,7 @@ class DecDownAlter(nn.Module):
         return img
 
     def forward(self, gs, zs_posterior, training):
+        warn_forward_only(self, "DecDownAlter.forward", *gs, *zs_posterior)
         bank = _solo_bank(self)
         acts = [to_act(g) for g in gs]
         zs = [to_act(z, need_raw=False, need_elu=True) for z in zs_posterior]
@@ -235,6 +240,13 @@ class DecDownAlter(nn.Module):
 
 
 _SIDE_STREAMS: dict = {}  # one side stream per device (not a module attribute: models are deep-copied / pickled)
+
+
+def _as_input(t: torch.Tensor) -> torch.Tensor:
+    """NCHW float tensors like the reference's ([-1, 1]) — or, for the rendering front-end, uint8 HWC image batches
+    ``[B, H, W, C]`` exactly as the reference holds them BEFORE ``ToTensor()`` and ``x * 2 - 1``
+    (data/__init__.py:15-43): the stem kernel applies that conversion itself, bit-identically."""
+    return t if t.dtype == torch.uint8 else t.float()
 
 
 def _require_cuda(t: torch.Tensor) -> None:
@@ -285,8 +297,6 @@ class VunetAlter(nn.Module):
     # ---------------------------------------------------------------------------------------------
     def _bank(self, with_wd: bool = False) -> WeightBank:
         if getattr(self, "validation_fp32", False):
-            if with_wd:
-                raise NotImplementedError("the fp32 validation mode is forward-only (training runs in bf16)")
             bank32 = getattr(self, "_vub_bank32", None)
             if bank32 is None:
                 from .validation import WeightBank32
@@ -309,8 +319,6 @@ class VunetAlter(nn.Module):
         return self
 
     def _wants_grad(self) -> bool:
-        if getattr(self, "validation_fp32", False):
-            return False  # forward-only: outputs carry no autograd history in validation mode
         return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
     def _forward_impl(self, bank, x, c, eps):
@@ -319,7 +327,7 @@ class VunetAlter(nn.Module):
         return imgs, lat, hs_left
 
     def _encode(self, bank, x, eps, skip_dead, want_elu_mu):
-        hs = self.eu._run(bank, x.float())
+        hs = self.eu._run(bank, _as_input(x))
         hs_all = list(hs)
         es, lat = self.ed._run(bank, hs, eps=eps, skip_dead=skip_dead, want_elu_mu=want_elu_mu)
         return hs_all, hs, lat
@@ -328,11 +336,11 @@ class VunetAlter(nn.Module):
         """``eu`` -> ``ed`` and ``du``.  ``ed`` (a chain of ~20 kernels on 4x4 .. 16x16 maps, each a few microseconds
         on a fraction of the SMs) depends only on ``eu``; it runs on a second stream beside ``du``, whose large
         kernels hide it.  VUB_FWD_STREAMS=1 keeps one stream."""
-        hs = self.eu._run(bank, x.float())
+        hs = self.eu._run(bank, _as_input(x))
         hs_all = list(hs)  # keeps eu's activations alive until the side stream has read them (ed pops from `hs`)
         if os.environ.get("VUB_FWD_STREAMS", "2") == "1":
             _, lat = self.ed._run(bank, hs, eps=eps, skip_dead=True, want_elu_mu=want_elu_mu)
-            gs = self.du._run(bank, c.float())
+            gs = self.du._run(bank, _as_input(c))
             return hs_all, hs, lat, gs
         main = torch.cuda.current_stream()
         side = _SIDE_STREAMS.get(main.device)
@@ -341,7 +349,7 @@ class VunetAlter(nn.Module):
         side.wait_stream(main)
         with torch.cuda.stream(side):
             _, lat = self.ed._run(bank, hs, eps=eps, skip_dead=True, want_elu_mu=want_elu_mu)
-        gs = self.du._run(bank, c.float())
+        gs = self.du._run(bank, _as_input(c))
         main.wait_stream(side)
         return hs_all, hs, lat, gs
 
@@ -362,10 +370,17 @@ class VunetAlter(nn.Module):
         activations = ([h.nchw() for h in hs_left], means, logstds)
         return imgs, means, logstds, activations
 
+    def invalidate_weights(self) -> None:
+        """Call after writing parameters through ``p.data`` (EMA, checkpoint averaging, custom init): autograd's
+        version counters do not see such writes, so the prepared (weight-normalised, packed) copies would stay
+        stale.  Same as ``bdvs_b200.bump_weight_epoch()``."""
+        bump_weight_epoch()
+
     def test_forward(self, c):
         _require_cuda(c)
+        warn_forward_only(self, "VunetAlter.test_forward", c)
         bank = self._bank()
-        gs = self.du._run(bank, c.float())
+        gs = self.du._run(bank, _as_input(c))
         return self.dd._run(bank, gs, [], False)
 
     # ---- sequence-level split of `transfer` (SURVEY.md §8f-1) ----------------------------------------
@@ -390,12 +405,13 @@ class VunetAlter(nn.Module):
             appearance = [Act(None, a.elu.repeat_interleave(frames_per_appearance, dim=0)) for a in appearance]
         if appearance[0].elu.shape[0] != c.shape[0]:
             raise ValueError("decode_pose: c must hold frames_per_appearance frames for every appearance image")
-        gs = self.du._run(bank, c.float())
+        gs = self.du._run(bank, _as_input(c))
         return self.dd._run(bank, gs, list(appearance), True)
 
     def transfer(self, x, c, eps: Optional[Sequence[torch.Tensor]] = None):
         _require_cuda(x)
         _require_cuda(c)
+        warn_forward_only(self, "VunetAlter.transfer", x, c)
         bank = self._bank()
         _keep, _, lat, gs = self._encode_and_pose(bank, x, c, eps, want_elu_mu=True)
         return self.dd._run(bank, gs, [r["mu_act"] for r in lat], True)

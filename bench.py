@@ -51,6 +51,27 @@ D256 = dict(ARCH, spatial_size=256, bottleneck_factor=2, box_factor=2, n_channel
 TRAIN_WORKLOAD = ("VunetAlter DeepFashion-256 (256x256, bottleneck_factor=2, box=2, n_channels_x=30) training step: "
                   "forward + MSE/KL surrogate loss + backward + gradient all-reduce + fused Adam")
 TRAIN_BATCH_PER_GPU = 32
+# BASELINE.json configs[0] ("config 1"): Market settings, forward+backward fp32 on CPU, batch 8
+M128 = dict(ARCH, spatial_size=128, bottleneck_factor=1, box_factor=1, n_channels_x=30)
+CONFIG1_WORKLOAD = ("VunetAlter Market-128 (128x128, bottleneck_factor=1, box=1, n_channels_x=30) forward + MSE/KL "
+                    "surrogate loss + backward, batch 8")
+CONFIG1_BATCH = 8
+# per-layer roofline terms of the H256 forward, per frame, bf16 NHWC with conv-level fusion:
+# (GFLOP, MB of input + output + weights) per layer group; the blended lower bound is sum(max(t_TC, t_HBM)).
+APP_A_LAYERS = [
+    (4.832, 33.63), (4.832, 17.07), (4.832, 9.57), (4.832, 7.47), (4.832, 12.88), (4.832, 25.24), (2.416, 3.74),
+    (2.416, 6.44), (1.208, 12.66), (1.208, 6.59), (1.208, 3.28), (1.208, 2.75), (1.208, 2.49), (0.268, 16.78),
+    (0.268, 8.40), (0.268, 4.26), (0.025, 9.18), (0.113, 4.59), (0.0, 0.0),  # last entry: placeholder for the tail
+]
+
+
+def blended_roofline_fps(peaks) -> float:
+    """frames/s/GPU lower bound of SURVEY.md §8d from the MEASURED peaks (burst bf16, HBM copy)."""
+    us = 0.0
+    for gflop, mb in APP_A_LAYERS[:-1]:
+        us += max(gflop * 1e9 / (peaks["bf16_tflops"] * 1e12), mb * 1e6 / (peaks["hbm_gbs"] * 1e9)) * 1e6
+    us += 4.4  # everything <= 16^2 and the remaining <= 32^2 layers (SURVEY App. A: total 39.9 us at these peaks)
+    return 1e6 / us
 # live convs, forward 34.000 GFLOP/sample (SURVEY.md §8d); training = fwd + dgrad + wgrad minus the stems' dgrad
 TRAIN_GFLOP_PER_SAMPLE = 3 * 34.000 - 2e-9 * (64 * 64 * 32 * 30 + 256 * 256 * 32 * 3)
 
@@ -156,6 +177,62 @@ def cpu_port_train_sps(sample: int, iters: int, warmup: int = 1):
         if i >= warmup:
             times.append(dt)
     return sample / statistics.median(times), threads
+
+
+def cpu_port_config1_sps(iters: int = 3, warmup: int = 1):
+    """samples/s of BASELINE config 1 EXACTLY: Market 128x128, batch 8, forward + backward, fp32 torch CPU."""
+    import vunet_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    with contextlib.redirect_stdout(io.StringIO()):
+        import bdvs_b200 as B
+        shapes = {k: tuple(v.shape) for k, v in B.VunetAlter(**M128).state_dict().items()}
+    sd = {k: v.requires_grad_(True) for k, v in O.det_state_dict(shapes).items()}
+    x, c, eps, _ = O.make_inputs(M128, CONFIG1_BATCH, tag="cfg1")
+    target = O.det_uniform("target8", (CONFIG1_BATCH, 3, 128, 128))
+    times = []
+    for i in range(warmup + iters):
+        t0 = time.perf_counter()
+        imgs, means, logstds, _, _ = O.forward(sd, x, c, eps)
+        loss = torch.mean((imgs - target) ** 2) + 1e-3 * O.compute_kl_with_prior(means, logstds)
+        loss.backward()
+        for v in sd.values():
+            v.grad = None
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return CONFIG1_BATCH / statistics.median(times), CONFIG1_BATCH / min(times), threads
+
+
+def gpu_config1_sps(device, iters: int = 20):
+    """The same config 1 step (forward + loss + backward, no optimizer) on the GPU path, eager launches."""
+    import bdvs_b200 as B
+    import vunet_oracle as O
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = B.VunetAlter(**M128)
+    model.load_state_dict(O.det_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}))
+    model = model.to(device).train()
+    x, c, eps, _ = O.make_inputs(M128, CONFIG1_BATCH, tag="cfg1")
+    x, c = x.to(device), c.to(device)
+    target = O.det_uniform("target8", (CONFIG1_BATCH, 3, 128, 128)).to(device)
+
+    def step():
+        imgs, means, logstds, _ = model(x, c)
+        loss = torch.mean((imgs - target) ** 2) + 1e-3 * B.compute_kl_with_prior(means, logstds)
+        for p in model.parameters():
+            p.grad = None
+        loss.backward()
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    return CONFIG1_BATCH * iters / (e0.elapsed_time(e1) * 1e-3)
 
 
 def run_train_section(args, device, world, rank, barrier, peaks):
@@ -312,23 +389,70 @@ def run_train_section(args, device, world, rank, barrier, peaks):
     return out
 
 
+def static_config(frames_per_gpu: int, world: int) -> dict:
+    """The workload description shared by both arms (the product arm adds nothing run-dependent here)."""
+    return {"workload": WORKLOAD, "frames_per_gpu_per_step": frames_per_gpu,
+            "global_frames_per_step": frames_per_gpu * world,
+            "parallelism": f"frames sharded over {world} GPU(s), no collective",
+            "cache": f"inputs + activations per step (~{14.0 * frames_per_gpu / 64:.1f} GB) far exceed the 126 MB L2: "
+                     "no flush needed",
+            "execution": "CUDA graph replay of model.transfer (latent noise drawn inside the graph); e2e: "
+                         "FrameSynthesizer.render_host, pinned host buffers (uint8 HWC stickmen / appearance in, uint8 "
+                         "HWC frames out, like the reference's rendering loop), copies double-buffered on their own "
+                         "streams and overlapped with the kernels of the neighbouring batches",
+            "algorithmic_gflop_per_frame": GFLOP_PER_FRAME,
+            "train_workload": TRAIN_WORKLOAD, "train_samples_per_gpu_per_step": TRAIN_BATCH_PER_GPU,
+            "config1_workload": CONFIG1_WORKLOAD}
+
+
 def run_reference(args):
+    """The reference's CPU path (its port, oracle/vunet_oracle.py) on the SAME config as the product arm: one step =
+    64 H256 frames through ``transfer`` (in chunks of 8 frames to bound host memory), all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 4
+    import vunet_oracle as O
     t_all0 = time.perf_counter()
-    fps, threads, times = cpu_port_fps(sample, iters=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    with contextlib.redirect_stdout(io.StringIO()):
+        import bdvs_b200 as B
+        shapes = {k: tuple(v.shape) for k, v in B.VunetAlter(**H256).state_dict().items()}
+    sd = O.det_state_dict(shapes)
+    chunk = 8
+    frames = FRAMES_PER_GPU if args.frames_total <= 0 else args.frames_total
+    x, c, eps, _ = O.make_inputs(H256, chunk, tag="cpu")
+    K, W = max(1, args.steps), max(0, args.warmup)
+    # bound the run: the whole --steps/--warmup run must end within a few minutes (~14 frames/s on 16 threads)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        O.transfer(sd, x, c, eps)
+    probe = time.perf_counter() - t0
+    budget_s = float(os.environ.get("VUB_REF_BUDGET_S", "170"))
+    chunks_per_step = max(1, frames // chunk)
+    while chunks_per_step > 1 and probe * chunks_per_step * (K + W) > budget_s:
+        chunks_per_step //= 2
+    sample = chunks_per_step * chunk
+    times = []
+    with torch.no_grad():
+        for i in range(W + K):
+            t0 = time.perf_counter()
+            for _ in range(chunks_per_step):
+                O.transfer(sd, x, c, eps)
+            if i >= W:
+                times.append(time.perf_counter() - t0)
     ms = 1e3 * statistics.median(times)
+    fps = sample / (ms * 1e-3)
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": max(1, args.steps), "warmup": max(1, min(args.warmup, 2)), "ms_per_step": ms,
+        "steps": K, "warmup": W, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": sample, "device": "cpu"},
+        "config": static_config(FRAMES_PER_GPU, max(1, args.gpus)),
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample} frames/step of the same H256 transfer workload, fp32, torch CPU "
-                                   f"({threads} threads); the reference is pure Python/PyTorch and is absent on the "
-                                   "GPU box, so its port oracle/vunet_oracle.py (pinned to reference outputs) is timed"},
+                         "sample": f"{sample} frames/step ({chunks_per_step} chunks of {chunk}) of the same H256 "
+                                   f"transfer workload, fp32, torch CPU ({threads} threads); the reference is pure "
+                                   "Python/PyTorch and is absent on the GPU box, so its port oracle/vunet_oracle.py "
+                                   "(pinned to reference outputs) is timed"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t_all0,
     }
@@ -399,31 +523,48 @@ def run_ours(args):
     launches = synth.launches_per_call * K
 
     # ---- e2e: pinned host buffers through the public API, copies inside the timed region ----
-    xh = torch.empty(synth.x.shape, dtype=torch.float32).uniform_(-1, 1).pin_memory()
-    ch = torch.empty(synth.c.shape, dtype=torch.float32).uniform_(-1, 1).pin_memory()
-    oh = torch.empty((Bf, 3, H256["spatial_size"], H256["spatial_size"]), dtype=torch.float32).pin_memory()
+    # Host-side formats are the reference rendering loop's own (data/data_conversions_3d.py:1154-1173): uint8 HWC
+    # stickman / appearance images in (its ToTensor() + x*2-1 run inside the stem kernels, bit-identically) and uint8 HWC
+    # frames out ((scale_img(rgb) * 255).astype(uint8)).  The fp32 NCHW variant of the same pipeline is timed too.
+    def time_render_host(s8, hosts):
+        for i in range(2):
+            s8.render_host(*hosts[i % 2])
+        s8.join()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            s8.render_host(*hosts[i % 2])
+        s8.join()  # the timed region ends when the last frames have landed in host memory
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    S = H256["spatial_size"]
+    synth8 = FrameSynthesizer(model, Bf, device, uint8_frames=True, uint8_inputs=True)
     # two host buffer sets, alternated, like a caller that prepares batch k+1 while batch k renders
-    xh2, ch2, oh2 = xh.clone().pin_memory(), ch.clone().pin_memory(), torch.empty_like(oh).pin_memory()
-    hosts = [(xh, ch, oh), (xh2, ch2, oh2)]
-    for i in range(2):
-        synth.render_host(*hosts[i % 2])
-    synth.join()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(K):
-        synth.render_host(*hosts[i % 2])
-    synth.join()  # the timed region ends when the last frames have landed in host memory
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_e2e], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
+    hosts8 = [(torch.randint(0, 256, (Bf, S, S, 3), dtype=torch.uint8).pin_memory(),
+               torch.randint(0, 256, (Bf, S, S, 3), dtype=torch.uint8).pin_memory(),
+               torch.empty((Bf, S, S, 3), dtype=torch.uint8).pin_memory()) for _ in range(2)]
+    ms_e2e = time_render_host(synth8, hosts8)
     e2e = world * Bf * K / (ms_e2e * 1e-3)
-    h2d = xh.numel() * 4 + ch.numel() * 4
-    d2h = oh.numel() * 4
+    h2d = hosts8[0][0].numel() + hosts8[0][1].numel()
+    d2h = hosts8[0][2].numel()
+    del synth8
+    hosts32 = [(torch.empty(synth.x.shape, dtype=torch.float32).uniform_(-1, 1).pin_memory(),
+                torch.empty(synth.c.shape, dtype=torch.float32).uniform_(-1, 1).pin_memory(),
+                torch.empty((Bf, 3, S, S), dtype=torch.float32).pin_memory()) for _ in range(2)]
+    ms32 = time_render_host(synth, hosts32)
+    e2e_fp32 = {"value": world * Bf * K / (ms32 * 1e-3), "unit": UNIT, "ms_per_step": ms32 / K,
+                "h2d_bytes_per_step": 4 * (hosts32[0][0].numel() + hosts32[0][1].numel()),
+                "d2h_bytes_per_step": 4 * hosts32[0][2].numel(),
+                "note": "same render_host pipeline with fp32 NCHW host tensors (the module API's own dtype)"}
+    del hosts32
 
     # BASELINE configs[4]-style rendering: whole 64-frame sequences against ONE appearance image each —
     # the appearance encoder runs once per sequence (the reference re-encodes it for every frame)
@@ -507,35 +648,69 @@ def run_ours(args):
     roofline.update({"kernel": top["kernel"], "launches_per_step": top["launches"], "share_of_step": top["share"],
                      "peak_source": peaks["source"] + (" (sustained)" if roofline["bound"] == "tensor" else ""),
                      "avg_launch_ms": round(top["ms"] / top["launches"], 4)})
+    blended = blended_roofline_fps(peaks)
     whole = {"conv_tflops_per_gpu": round(GFLOP_PER_FRAME * Bf / ms_step, 2),
              "frac_tensor_peak_sustained": round(GFLOP_PER_FRAME * Bf / ms_step / peaks["bf16_tflops_sustained"], 4),
-             "blended_roofline_frames_per_s_per_gpu": 25100.0,
-             "frac_of_blended_roofline": round(value / world / 25100.0, 4)}
+             "blended_roofline_frames_per_s_per_gpu": round(blended, 1),
+             "frac_of_blended_roofline": round(value / world / blended, 4)}
 
     # ---- CPU baseline (bounded sample) ----
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        fps, threads, times = cpu_port_fps(4, iters=3, warmup=1)
+        fps, threads, times = cpu_port_fps(8, iters=3, warmup=1)
         cpu = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "4 frames/iter x 3 iters (+1 warm-up) of the same H256 transfer workload, fp32 torch CPU, "
+               "sample": "8 frames/iter x 3 iters (+1 warm-up) of the same H256 transfer workload, fp32 torch CPU, "
                          "oracle/vunet_oracle.py (port of the reference's PyTorch path, pinned to reference outputs)"}
+        # BASELINE config 1 exactly: M128 forward + backward, batch 8, CPU fp32 — and the same step
+        # on the GPU path beside it
+        try:
+            med, best, threads = cpu_port_config1_sps(iters=3, warmup=1)
+            cpu["config1"] = {"workload": CONFIG1_WORKLOAD, "cpu_samples_per_s_median": round(med, 2),
+                              "cpu_samples_per_s_best": round(best, 2), "cores": threads, "iters": 3, "warmup": 1,
+                              "gpu_samples_per_s": round(gpu_config1_sps(device), 1),
+                              "gpu_note": "same step (fwd + loss + bwd) through the module API, eager launches, bf16"}
+        except Exception as exc:  # noqa: BLE001
+            cpu["config1"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         if isinstance(train, dict) and "value" in train:
-            sps, threads = cpu_port_train_sps(2, iters=2, warmup=1)
+            sps, threads = cpu_port_train_sps(4, iters=2, warmup=1)
             train["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
-                                     "sample": "2 samples/iter x 2 iters (+1 warm-up) of the same D256 forward+backward, "
+                                     "sample": "4 samples/iter x 2 iters (+1 warm-up) of the same D256 forward+backward, "
                                                "fp32 torch CPU autograd through oracle/vunet_oracle.py"}
+
+    # The driver keeps `config`, `roofline`, `cpu_baseline`, `e2e`, `clocks` in full and drops unknown top-level keys:
+    # the second workload (BASELINE configs[2], training) and the sequence-rendering number therefore ALSO travel
+    # inside `roofline` (run-dependent results) while `config` stays a static description shared with --impl reference.
+    if isinstance(train, dict) and "value" in train:
+        fams = (train.get("kernels") or {}).get("families") or []
+        worst = None
+        for f in fams:  # worst family among those that carry >= 5 % of the step
+            if f["share"] < 0.05:
+                continue
+            frac_t = f["tflops"] / peaks["bf16_tflops_sustained"]
+            frac_h = f["gbs"] / peaks["hbm_gbs"]
+            frac = max(frac_t, frac_h)
+            if worst is None or frac < worst["frac"]:
+                worst = {"family": f["family"], "share": f["share"], "ms": f["ms"], "tflops": f["tflops"],
+                         "gbs": f["gbs"], "bound": "tensor" if frac_t >= frac_h else "hbm", "frac": round(frac, 4)}
+        roofline["train"] = {
+            "metric": train["metric"], "value": train["value"], "unit": train["unit"], "n_gpus": world,
+            "ms_per_step": train["ms_per_step"], "steps": train["steps"], "warmup": train["warmup"],
+            "samples_per_gpu_per_step": TRAIN_BATCH_PER_GPU, "e2e": train["e2e"],
+            "allreduce_bytes_per_step": train["allreduce_bytes_per_step"], "gpu_launches": train["gpu_launches"],
+            "cuda_graph": train["cuda_graph"], "conv_tflops_per_gpu": train["conv_tflops_per_gpu"],
+            "frac_tensor_peak_sustained": train["frac_tensor_peak_sustained"], "worst_family": worst,
+            "families": fams, "cpu_baseline": train.get("cpu_baseline"), "loss": train["loss"]}
+    elif isinstance(train, dict):
+        roofline["train"] = train
+    roofline["whole_step"] = whole
+    roofline["sequence"] = sequence
+    roofline["e2e_fp32"] = e2e_fp32
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": Bf, "global_frames_per_step": Bf * world,
-                   "parallelism": f"frames sharded over {world} GPU(s), no collective",
-                   "cache": f"inputs + activations per step (~{14.0 * Bf / 64:.1f} GB) far exceed the 126 MB L2: no flush needed",
-                   "execution": "CUDA graph replay of model.transfer (latent noise drawn inside the graph); e2e: "
-                                "FrameSynthesizer.render_host, pinned host buffers, copies double-buffered on their own "
-                                "streams and overlapped with the kernels of the neighbouring batches",
-                   "algorithmic_gflop_per_frame": GFLOP_PER_FRAME},
+        "config": static_config(Bf, world),
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / K},

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VUB_ABI_VERSION 3
+#define VUB_ABI_VERSION 4
 
 #define VUB_OK 0
 #define VUB_E_NULL (-1)        /* required pointer is NULL */
@@ -34,6 +34,7 @@ extern "C" {
 #define VUB_E_FLAGS (-3)       /* inconsistent flag / output combination */
 #define VUB_E_ALIGN (-4)       /* pointer not 16-byte aligned */
 #define VUB_E_NODRIVER (-5)    /* CUDA driver entry point unavailable (no GPU / no driver) */
+#define VUB_E_COMM (-6)        /* NCCL unavailable or returned an error (vub_last_error() has its message) */
 
 /* vub_conv_desc.flags */
 #define VUB_CONV_D2S 1u        /* store through DepthToSpace(2) (lib/modules.py:24-34, DCR order) */
@@ -140,6 +141,15 @@ int vub_wn_prep(const vub_wn_entry* table_dev, int32_t n_entries, int32_t total_
 int vub_stem_fwd(const float* x_nchw, const float* v, const float* g, const float* gamma,
                  const float* beta, const float* bias, int32_t batch, int32_t cx, int32_t h,
                  int32_t w, int32_t cout, void* out_raw, void* out_elu, void* stream);
+/*
+ * Same layer fed with the uint8 HWC image [batch, h, w, cx] the reference holds BEFORE its `ToTensor()` +
+ * `x * 2 - 1` transforms (data/__init__.py:15-43; the rendering loop's stickman: data/data_conversions_3d.py:1154-1163).
+ * The kernel applies that conversion itself (fp32 (u / 255) * 2 - 1, IEEE division): bit-identical outputs to
+ * vub_stem_fwd on the converted tensor, a quarter of the input bytes over PCIe and HBM.
+ */
+int vub_stem_fwd_u8(const uint8_t* x_nhwc_u8, const float* v, const float* g, const float* gamma,
+                    const float* beta, const float* bias, int32_t batch, int32_t cx, int32_t h,
+                    int32_t w, int32_t cout, void* out_raw, void* out_elu, void* stream);
 
 /*
  * Latent head: EncDownAlter's squash + reparametrize (models/vunets.py:575,594-597) and the KL
@@ -341,6 +351,56 @@ int vub_stem_bwd(const float* x_nchw, const void* dy_nhwc, int32_t batch, int32_
 int vub_latent_bwd(const float* mu_nchw, const float* logstd_nchw, const float* eps_nchw, const float* d_mu_nchw,
                    const float* d_ls_nchw, const void* dz_nhwc, int32_t batch, int32_t c, int32_t h, int32_t w,
                    void* d_ml_nhwc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * fp32 validation mode, training half: the same backward schedule with fp32 activations / gradients and fp32
+ * v / ||v|| matrices on CUDA cores (north_star: gradients within 1e-4 of the reference "in an fp32-accumulate
+ * validation mode").  The weight-norm / affine parameter gradients come from the SAME vub_wn_bwd launch as in the
+ * bf16 path (its inputs were fp32 all along).  Checkers, not fast paths.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vub_dgrad_f32_desc {
+  const float* dy;           /* NHWC fp32 [batch, hout, wout, cout]; VUB_CONV_D2S: [batch, 2*hin, 2*win, cout/4] */
+  const float* w;            /* [nsrc*ksize*ksize*c_src][w_pitch] fp32 v / ||v|| (the forward matrix) */
+  const float* scale;        /* gamma * g per output channel */
+  float* dx[2];              /* NHWC fp32 [batch, hin, win, c_src] per source */
+  const float* mask_elu[2];  /* stored ELU(x_s) or NULL */
+  const float* addend[2];    /* may alias dx */
+  const float* addend2[2];
+  int32_t nsrc, c_src, batch, hin, win, cout, w_pitch, ksize, stride;
+  uint32_t flags;            /* VUB_CONV_D2S */
+} vub_dgrad_f32_desc;
+int vub_conv_dgrad_f32(const vub_dgrad_f32_desc* d, void* stream);
+
+typedef struct vub_wgrad_f32_desc {
+  const float* dy;
+  const float* x[2];
+  float* gt;                 /* [n_split][cout rows of gt_pitch floats]: partial correlations, K order (src, tap, ch) */
+  float* dy_sum;             /* [n_split][cout] */
+  int32_t nsrc, c_src, batch, hin, win, cout, ksize, stride;
+  uint32_t flags;            /* VUB_CONV_D2S */
+  int32_t n_split, gt_pitch;
+  int64_t split_stride, sum_stride;  /* floats between consecutive splits of gt / dy_sum */
+} vub_wgrad_f32_desc;
+int vub_conv_wgrad_f32(const vub_wgrad_f32_desc* d, void* stream);
+
+int vub_latent_bwd_f32(const float* logstd_nchw, const float* eps_nchw, const float* d_mu_nchw, const float* d_ls_nchw,
+                       const float* dz_nhwc, int32_t batch, int32_t c, int32_t h, int32_t w, float* d_ml_nhwc,
+                       void* stream);
+
+/*
+ * Data-parallel gradient exchange (SURVEY.md 8b `allreduce_bucket(flat, ncclComm, stream)`): in-place all-reduce of
+ * one flat fp32 gradient bucket (average != 0: ncclAvg, i.e. the 1/world scaling happens inside the collective),
+ * enqueued on `stream`; capturable in a CUDA graph.  Replaces nn.DataParallel's per-step gather / reduce
+ * (experiments/shape_and_pose_net.py:213-214).  `nccl_comm` is an ncclComm_t — from vub_nccl_comm_init or any other
+ * owner; NCCL is bound at run time (the copy the process already loaded, else the system libnccl.so.2).
+ */
+int vub_allreduce_bucket(void* flat, int64_t n_floats, void* nccl_comm, int32_t average, void* stream);
+/* Communicator plumbing for hosts that do not own one: rank 0 creates the 128-byte id and ships it to the other
+ * ranks by any means (torch.distributed's store in training.BucketReducer). */
+int32_t vub_nccl_version(void);  /* NCCL_VERSION_CODE of the bound library, 0 if none */
+int vub_nccl_unique_id(void* id128);
+int vub_nccl_comm_init(void** comm, int32_t n_ranks, const void* id128, int32_t rank);
+int vub_nccl_comm_destroy(void* comm);
 
 #ifdef __cplusplus
 }

@@ -117,7 +117,14 @@ struct DyView {
   }
 };
 
+// VUB_SANITIZE=1 (tools/sanitize.sh): keep the cases below 16 k pixels under compute-sanitizer
+static bool sanitize_skip(long long pixels) {
+  static const bool on = getenv("VUB_SANITIZE") != nullptr;
+  return on && pixels > 16384;
+}
+
 static void run_dgrad(const BwdCase& c) {
+  if (sanitize_skip((long long)c.B * c.H * c.W)) return;
   const int taps = c.ksize * c.ksize, pad = c.ksize / 2;
   const int Ho = c.H / c.stride, Wo = c.W / c.stride;
   const size_t dy_elems = (size_t)c.B * Ho * Wo * c.cout_k;
@@ -205,6 +212,7 @@ static void run_dgrad(const BwdCase& c) {
 }
 
 static void run_wgrad(const BwdCase& c) {
+  if (sanitize_skip((long long)c.B * c.H * c.W)) return;
   const int taps = c.ksize * c.ksize, pad = c.ksize / 2;
   const int Ho = c.H / c.stride, Wo = c.W / c.stride;
   const size_t dy_elems = (size_t)c.B * Ho * Wo * c.cout_k;

@@ -99,7 +99,15 @@ static int g_tiled = 0;  // 1: also hand the kernels the tile-major weights (1-D
 
 static int g_elu_in = 0;  // VUB_CONV_ELU_IN source mask for the next run_conv_case calls
 
+// VUB_SANITIZE=1 (tools/sanitize.sh): compute-sanitizer slows kernels down 10-100x; keep the cases below 16 k pixels
+// (every kernel family still runs, incl. the row, tile, CTA-pair, slab and per-tap variants)
+static bool sanitize_skip(long long pixels) {
+  static const bool on = getenv("VUB_SANITIZE") != nullptr;
+  return on && pixels > 16384;
+}
+
 static void run_conv_case(const ConvCase& cc) {
+  if (sanitize_skip((long long)cc.B * cc.H * cc.W)) return;
   const int taps = cc.ksize * cc.ksize;
   const int K = cc.nsrc * taps * cc.c_src;
   const int Ho = cc.H / cc.stride, Wo = cc.W / cc.stride;

@@ -261,15 +261,54 @@ def test_fp32_validation_mode_matches_reference_to_1e4(golden, name):
     assert 1e-4 < rel(imgs_bf16, fx["imgs"]) < BF16_TOL
 
 
-def test_fp32_validation_mode_is_forward_only(golden):
+@pytest.mark.parametrize("name", ["tiny3", "tiny30", "market128"])
+def test_fp32_validation_mode_gradients_match_reference_to_1e4(golden, name):
+    """north_star: images, latents AND gradients within 1e-4 "in an fp32-accumulate validation mode".  The backward
+    schedule runs on the CUDA-core fp32 kernels (vub_conv_dgrad_f32 / vub_conv_wgrad_f32 / vub_latent_bwd_f32) and
+    the same vub_wn_bwd as the bf16 path; checked against the CPU oracle's fp32 autograd (concatenated gradient and
+    every single tensor) and against the gradient fixtures generated from the reference itself."""
     import bdvs_b200 as B
-    cfg = golden("tiny3")["config"]
+    fx = golden(name)
+    cfg = fx["config"]
     m, sd = build(cfg)
     m.train()
-    x, c, eps, _ = O.make_inputs(cfg, cfg["batch"])
+    bs = cfg["batch"]
+    x, c, eps, _ = O.make_inputs(cfg, bs)
+    target = O.det_uniform("target", (bs, 3, cfg["spatial_size"], cfg["spatial_size"]))
     with B.fp32_validation(m):
-        imgs = m(x.cuda(), c.cuda(), eps=cuda(eps))[0]
-    assert not imgs.requires_grad
+        imgs, means, logstds, _ = m(x.cuda(), c.cuda(), eps=cuda(eps))
+        assert imgs.requires_grad
+        loss = torch.mean((imgs - target.cuda()) ** 2) + 1e-3 * B.compute_kl_with_prior(means, logstds)
+        loss.backward()
+    torch.cuda.synchronize()
+    got = {k: (p.grad.detach().float().cpu() if p.grad is not None else None) for k, p in m.named_parameters()}
+    sd_g = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    o_imgs, o_means, o_logstds, _, _ = O.forward(sd_g, x, c, eps)
+    o_loss = torch.mean((o_imgs - target) ** 2) + 1e-3 * O.compute_kl_with_prior(o_means, o_logstds)
+    o_loss.backward()
+    ref = {k: v.grad for k, v in sd_g.items()}
+    assert abs(float(loss) - float(o_loss)) < 1e-4 * abs(float(o_loss))
+    assert abs(float(loss) - fx["loss"]) < 1e-4 * abs(fx["loss"])
+    assert sorted(k for k, g in got.items() if g is None) == fx["grad_is_none"]
+    keys = [k for k, g in ref.items() if g is not None and float(g.abs().max()) > 0.0]
+    num = sum(float((got[k] - ref[k]).pow(2).sum()) for k in keys)
+    den = sum(float(ref[k].pow(2).sum()) for k in keys)
+    total = (num / den) ** 0.5
+    worst = max(float((got[k] - ref[k]).norm() / ref[k].norm().clamp_min(1e-20)) for k in keys)
+    fixture = max(float((got[k] - g).norm() / g.norm()) for k, g in fx["grad_full"].items())
+    print(f"{name}: fp32 validation gradients: concatenated rel-L2 {total:.2e}, worst tensor {worst:.2e}, "
+          f"vs reference fixture tensors {fixture:.2e}")
+    assert total < FP32_TOL
+    assert worst < 20 * FP32_TOL       # tiny tensors (a bias of 32 values) carry proportionally more round-off
+    assert fixture < FP32_TOL * 10
+    for k, n_ref in fx["grad_norms"].items():
+        assert abs(float(got[k].norm()) - n_ref) < 1e-3 * n_ref + 1e-9, k
+    # leaving the mode: the bf16 tensor-core backward is back (same buffers are not reused across precisions)
+    m.zero_grad(set_to_none=True)
+    imgs2 = m(x.cuda(), c.cuda(), eps=cuda(eps))[0]
+    ((imgs2 - target.cuda()) ** 2).mean().backward()
+    g2 = m.dd.out_conv.conv.weight_v.grad.float().cpu()
+    assert 1e-5 < float((g2 - ref["dd.out_conv.conv.weight_v"]).norm() / ref["dd.out_conv.conv.weight_v"].norm()) < 5e-2
 
 
 def test_sequence_level_encoder_reuse_equals_per_frame_transfer():
@@ -335,3 +374,67 @@ def test_activation_layouts_and_kernel_variants_agree(cfg, batch, monkeypatch):
     assert torch.equal(outs["one_stream"], outs["default"])          # same kernels, different stream assignment
     assert torch.equal(outs["smem_operand"], outs["default"])        # same operands, fetched differently
     assert torch.equal(outs["single_cta"], outs["default"])          # same K order, M = 128 vs M = 256 instructions
+
+
+def test_uint8_image_inputs_are_bit_identical_to_converted_fp32_inputs():
+    """uint8 HWC images through the stem kernels == the reference's ``ToTensor()`` + ``x * 2 - 1`` conversion
+    (data/__init__.py:15-43) followed by the fp32 NCHW path, bit for bit — for the 3-channel stickman / appearance
+    (H3.6M) and the 30-channel part crops (DeepFashion / Market)."""
+    for cfg in (dict(H256, spatial_size=64), dict(D256, spatial_size=128)):
+        m, _ = build(cfg)
+        B = 3
+        g = torch.Generator().manual_seed(11)
+        s = cfg["spatial_size"]
+        sx = s // 2 ** (m.n_scales - m.n_scales_x)
+        x8 = torch.randint(0, 256, (B, sx, sx, cfg["n_channels_x"]), dtype=torch.uint8, generator=g)
+        c8 = torch.randint(0, 256, (B, s, s, 3), dtype=torch.uint8, generator=g)
+        x8[0, 0, 0, :3] = torch.tensor([0, 255, 128], dtype=torch.uint8)
+        to_f = lambda t: ((t.float().div(255) * 2.0) - 1.0).permute(0, 3, 1, 2).contiguous()  # noqa: E731
+        _, _, eps, _ = O.make_inputs(cfg, B, tag="u8")
+        with torch.no_grad():
+            a = m.transfer(x8.cuda(), c8.cuda(), eps=cuda(eps))
+            b = m.transfer(to_f(x8).cuda(), to_f(c8).cuda(), eps=cuda(eps))
+            f8 = m(x8.cuda(), c8.cuda(), eps=cuda(eps))
+            f32 = m(to_f(x8).cuda(), to_f(c8).cuda(), eps=cuda(eps))
+        assert torch.equal(a, b)
+        assert torch.equal(f8[0], f32[0]) and torch.equal(f8[1][1], f32[1][1])
+
+
+def test_host_pipeline_uint8_matches_direct_transfer():
+    """``FrameSynthesizer.render_host`` with uint8 HWC host buffers (two alternating graph / buffer sets, copies on
+    their own streams, no staging copies) returns exactly ``frames_to_uint8(transfer(x, c))`` for every batch of a
+    stream of different batches — and the fp32 variant of the pipeline agrees with ``transfer``."""
+    from bdvs_b200 import ops
+    from bdvs_b200.synthesis import FrameSynthesizer
+    cfg = dict(H256, spatial_size=64)
+    m, _ = build(cfg)
+    B, n_batches = 4, 5
+    g = torch.Generator().manual_seed(3)
+    xs = [torch.randint(0, 256, (B, 64, 64, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(n_batches)]
+    cs = [torch.randint(0, 256, (B, 64, 64, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(n_batches)]
+    outs = [torch.zeros(B, 64, 64, 3, dtype=torch.uint8).pin_memory() for _ in range(n_batches)]
+    fs = FrameSynthesizer(m, B, uint8_frames=True, uint8_inputs=True)
+    # the latent noise is drawn inside the graphs from the global generator: replay the same stream for the check
+    torch.manual_seed(99)
+    for i in range(n_batches):
+        fs.render_host(xs[i], cs[i], outs[i])
+    fs.join()
+    torch.cuda.synchronize()
+    torch.manual_seed(99)
+    with torch.no_grad():
+        for i in range(n_batches):
+            want = ops.frames_to_uint8(m.transfer(xs[i].cuda(), cs[i].cuda())).cpu()
+            assert torch.equal(outs[i], want), i
+    with pytest.raises(ValueError):
+        fs.render_host(xs[0].float(), cs[0], outs[0])
+    # fp32 NCHW pipeline
+    fs32 = FrameSynthesizer(m, B)
+    x, c, _, _ = O.make_inputs(cfg, B, tag="host32")
+    out32 = torch.zeros(B, 3, 64, 64).pin_memory()
+    torch.manual_seed(5)
+    fs32.render_host(x.pin_memory(), c.pin_memory(), out32)
+    fs32.join()
+    torch.cuda.synchronize()
+    torch.manual_seed(5)
+    with torch.no_grad():
+        assert torch.equal(out32, m.transfer(x.cuda(), c.cuda()).cpu())
