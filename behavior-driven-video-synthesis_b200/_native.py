@@ -21,6 +21,7 @@ CONV_F32_NHWC = 2
 CONV_F32_NCHW = 4
 CONV_ELU_IN0 = 8
 CONV_ELU_IN1 = 16
+CONV_U8_HWC = 32
 
 # every extern "C" symbol the header declares; tests check the built library exports all of them
 EXPORTED_SYMBOLS = (
@@ -28,6 +29,7 @@ EXPORTED_SYMBOLS = (
     "vub_last_error",
     "vub_conv_fwd",
     "vub_conv_fwd_elu_in_ok",
+    "vub_conv_fwd_u8_out_ok",
     "vub_wn_prep",
     "vub_stem_fwd",
     "vub_stem_fwd_u8",
@@ -342,6 +344,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.vub_conv_wgrad.argtypes = [C.POINTER(WgradDesc), vp]
     lib.vub_conv_fwd_elu_in_ok.restype = C.c_int
     lib.vub_conv_fwd_elu_in_ok.argtypes = [i32] * 7
+    lib.vub_conv_fwd_u8_out_ok.restype = C.c_int
+    lib.vub_conv_fwd_u8_out_ok.argtypes = [i32] * 7
     lib.vub_adam_wn_step_dev.restype = C.c_int
     lib.vub_adam_wn_step_dev.argtypes = [vp, i32, i32, C.c_float, C.c_float, C.c_float, vp, vp]
     lib.vub_adam_wn_step.restype = C.c_int

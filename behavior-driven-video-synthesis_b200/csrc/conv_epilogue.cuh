@@ -44,6 +44,18 @@ template <int CH>
 __device__ __forceinline__ void epi_store(const EpiParams& p, float (&y)[CH], int c_global, int n, int oh,
                                           int ow) {
   const long long pix = ((long long)n * p.hout + oh) * p.wout + ow;
+  if (p.flags & VUB_CONV_U8_HWC) {
+    // video frame: (clamp((y + 1) / 2, 0, 1) * 255) truncated to uint8, HWC — same fp32 arithmetic as
+    // frames_to_uint8_kernel on the fp32 image, so the bytes are identical
+    uint8_t* o = reinterpret_cast<uint8_t*>(p.out_f32) + pix * p.cout_valid;
+#pragma unroll
+    for (int i = 0; i < CH; ++i)
+      if (c_global + i < p.cout_valid) {
+        const float v = fminf(fmaxf((y[i] + 1.0f) / 2.0f, 0.0f), 1.0f) * 255.0f;
+        o[c_global + i] = static_cast<uint8_t>(static_cast<int>(v));
+      }
+    return;
+  }
   if (p.flags & VUB_CONV_F32_NCHW) {
     const long long plane = (long long)p.hout * p.wout;
     float* o = p.out_f32 + ((long long)n * p.cout_valid) * plane + (long long)oh * p.wout + ow;
@@ -120,6 +132,38 @@ struct EpiStage {
     }
   }
 };
+
+// Staging layout for tiles that a TMA tensor-map copy writes or reads (cp.async.bulk.tensor with 128-byte swizzle):
+// the box row is 128 bytes — one pixel at GW = 64, a PAIR of pixels at GW = 32 (a tensor box moves 3 cycles per box
+// row whatever its width, profiles/r01_exp_rates_tma.log, so 64-byte rows would halve the copy rate) — and the
+// hardware XORs the 16-byte chunk index with (box row & 7).  Tiles must start on a 1024-byte boundary.  Both access
+// patterns of the epilogue stay bank-conflict free: "pixel per lane, fixed chunk" hits 8 different 16-byte columns
+// per quarter warp (rows r, r+1, r+2, r+3 x the two pixel halves for GW = 32).
+template <int GW>
+struct TmaStage {
+  static constexpr int CPR = GW / 8;
+  static constexpr int TILE_BYTES = 32 * GW * 2;
+  static constexpr int BOX_ROWS = GW == 32 ? 16 : 32;   // 128-byte rows per 32-pixel tile
+  __device__ __forceinline__ static uint32_t off(int pix, int chunk) {
+    static_assert(GW == 32 || GW == 64, "TMA staging covers 32- and 64-channel tiles");
+    if constexpr (GW == 64) {
+      return pix * 128 + ((chunk ^ (pix & 7)) << 4);
+    } else {
+      const int row = pix >> 1;
+      return row * 128 + (((((pix & 1) << 2) | chunk) ^ (row & 7)) << 4);
+    }
+  }
+};
+
+// Stage 32 consecutive channels of this lane's pixel into a TMA-layout tile (see TmaStage).
+template <int GW>
+__device__ __forceinline__ void stage_put32_tma(uint32_t tile, int lane, int c, const float (&y)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    sts128(tile + TmaStage<GW>::off(lane, (c >> 3) + j),
+           make_uint4(pack_bf16x2(y[8 * j + 0], y[8 * j + 1]), pack_bf16x2(y[8 * j + 2], y[8 * j + 3]),
+                      pack_bf16x2(y[8 * j + 4], y[8 * j + 5]), pack_bf16x2(y[8 * j + 6], y[8 * j + 7])));
+}
 
 // Stage 32 consecutive channels (starting at channel `c` of the group) of this lane's pixel.
 // `tile` is a shared-space byte address.

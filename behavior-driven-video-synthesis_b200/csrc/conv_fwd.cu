@@ -329,6 +329,21 @@ extern "C" int vub_conv_fwd_elu_in_ok(int32_t nsrc, int32_t c_src, int32_t cout,
   return conv_rows_applicable(&d) ? 1 : 0;
 }
 
+extern "C" int vub_conv_fwd_u8_out_ok(int32_t nsrc, int32_t c_src, int32_t cout, int32_t ksize, int32_t stride,
+                                      int32_t hin, int32_t win) {
+  vub_conv_desc d;
+  memset(&d, 0, sizeof(d));
+  d.nsrc = nsrc;
+  d.c_src = c_src;
+  d.cout = cout;
+  d.ksize = ksize;
+  d.stride = stride;
+  d.hin = hin;
+  d.win = win;
+  d.flags = VUB_CONV_U8_HWC;
+  return (cout == 16 && conv_rows_applicable(&d)) ? 1 : 0;
+}
+
 extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
   clear_error();
   if (!d) return fail(VUB_E_NULL, "conv_fwd: desc is NULL");
@@ -351,14 +366,18 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
     return fail(VUB_E_SHAPE, "conv_fwd: cout %d not in {16,32,64,128,256,512}", cout);
   if (d->cout_valid <= 0 || d->cout_valid > cout) return fail(VUB_E_SHAPE, "conv_fwd: cout_valid");
   const uint32_t f = d->flags;
-  const bool f32 = (f & (VUB_CONV_F32_NHWC | VUB_CONV_F32_NCHW)) != 0;
-  if ((f & VUB_CONV_F32_NHWC) && (f & VUB_CONV_F32_NCHW)) return fail(VUB_E_FLAGS, "conv_fwd: two f32 layouts");
+  const bool f32 = (f & (VUB_CONV_F32_NHWC | VUB_CONV_F32_NCHW | VUB_CONV_U8_HWC)) != 0;  // "not bf16 NHWC"
+  if (((f & VUB_CONV_F32_NHWC) != 0) + ((f & VUB_CONV_F32_NCHW) != 0) + ((f & VUB_CONV_U8_HWC) != 0) > 1)
+    return fail(VUB_E_FLAGS, "conv_fwd: more than one of F32_NHWC / F32_NCHW / U8_HWC");
+  if ((f & VUB_CONV_U8_HWC) && !(cout == 16 && conv_rows_applicable(d)))
+    return fail(VUB_E_FLAGS, "conv_fwd: U8_HWC output is only implemented by the row-streaming kernel for cout 16 "
+                             "(see vub_conv_fwd_u8_out_ok)");
   if (f32 && (!d->out_f32 || d->out_raw || d->out_elu || (f & VUB_CONV_D2S)))
     return fail(VUB_E_FLAGS, "conv_fwd: f32 output excludes bf16 outputs and D2S");
   if (!f32 && (d->out_f32 || (!d->out_raw && !d->out_elu)))
     return fail(VUB_E_FLAGS, "conv_fwd: need out_raw and/or out_elu (and no out_f32)");
-  if (!(f & VUB_CONV_F32_NCHW) && d->cout_valid != cout)
-    return fail(VUB_E_FLAGS, "conv_fwd: cout_valid != cout only with F32_NCHW");
+  if (!(f & (VUB_CONV_F32_NCHW | VUB_CONV_U8_HWC)) && d->cout_valid != cout)
+    return fail(VUB_E_FLAGS, "conv_fwd: cout_valid != cout only with F32_NCHW / U8_HWC");
   if ((f & VUB_CONV_D2S) && (d->residual || cout < 128))
     return fail(VUB_E_FLAGS, "conv_fwd: D2S excludes residual and needs cout >= 128");
   const void* ptrs[] = {d->x[0], d->x[1], d->w, d->residual, d->out_raw, d->out_elu, d->out_f32};

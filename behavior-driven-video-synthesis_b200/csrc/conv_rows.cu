@@ -31,7 +31,7 @@
 namespace vub {
 
 constexpr int kRowsThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue A, warps 6-9 epilogue B
-constexpr int kRowsThreadsElu = 448;  // + warps 10-13: ELU-on-load transform of freshly landed input rows
+constexpr int kRowsThreadsElu = 384;  // + warps 10-11: ELU-on-load transform of freshly landed input rows
 constexpr int kRowsMaxRing = 8;
 constexpr int kRowsW = 128;  // output columns per CTA = UMMA M
 
@@ -51,7 +51,7 @@ struct RowsKParams {
   int n_halves;         // 0 = forward epilogue (ep), 1 or 2 = data-gradient epilogue (bwd[])
   int stage_tiles;      // staging tiles per epilogue warp in data-gradient mode
   TileEpi bwd[2];
-  // ELU-on-load (VUB_CONV_ELU_IN0/1): bit s set = source s holds RAW activations; four extra warps apply ELU to
+  // ELU-on-load (VUB_CONV_ELU_IN0/1): bit s set = source s holds RAW activations; two extra warps apply ELU to
   // every input row in place in its ring slot before the tensor core reads it, so the producer of that tensor
   // never writes an ELU copy to HBM and the residual (the same raw tensor) is an L2 hit.
   int elu_in;
@@ -66,6 +66,12 @@ struct RowsKParams {
   // M128 N32 K16 MMA costs 40 cycles for 16 cycles of math because its shared-memory operand fetch is (128 + N) rows
   // per instruction (profiles/r01_exp_rates_mma.log) — stacking N amortises the 128 A rows over three outputs.
   int nblk;
+  // TMA epilogue (forward, one bf16 output, BN 32 / 64): the finished 32-pixel tiles leave shared memory through
+  // tensor-map stores issued by one lane per warp (tma = 1), and the residual rows arrive the same way (tma = 2),
+  // instead of LDS + STG / LDG + STS passes of all 32 lanes — the kernel is bound by the shared-memory data pipe
+  // (LSU wavefronts, profiles/r01_ncu_rows_smem.txt), which these copies bypass.
+  int tma;
+  CUtensorMap tmO, tmR;
 };
 
 template <int BKC>
@@ -156,17 +162,16 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
   // ELU-on-load the transform warps write the slots from registers (tcgen05.st), which needs a free / ready handshake
   // and therefore some slack
   constexpr int RT_MAX = ATM_OK ? (512 - 2 * BN) / TSLOT_COLS : 3;
-  // Measured (B=64): writing the activated rows to TMEM from registers beats "transform in place + tcgen05.cp" for
-  // the concat layer ([32|32]->32: 0.246 -> 0.216 ms) but not for the single-source ones (32->32: 0.166 -> 0.193 ms,
-  // all four warps then serialise on one row's load -> ELU -> shuffle -> store chain), so only NSRC == 2 uses it.
-  constexpr bool TST = ELU_IN && NSRC == 2;
-  constexpr int RT = !TST ? 3 : (RT_MAX > 6 ? 6 : RT_MAX);
+  // (Round 1 also wrote the activated rows of the concat layer to TMEM from registers with tcgen05.st, 0.246 -> 0.216
+  // ms; stacking the kernel rows along N (nblk) reaches 0.211 ms with the plain in-place transform, so that path is
+  // gone and the transform needs only two warps.)
+  constexpr bool TST = false;
+  constexpr int RT = 3;
   constexpr uint32_t ATM_USE = 2 * BN + RT * TSLOT_COLS;
   constexpr uint32_t ATM_COLS = ATM_USE <= 128 ? 128 : ATM_USE <= 256 ? 256 : 512;
-  static_assert(!ATM_OK || !TST || RT >= 4, "ELU-on-load with the operand in tensor memory needs >= 4 row slots");
   // kernel rows as N blocks: ring of RA accumulator slots of BN columns (an output row's accumulator is complete
   // after THREE input rows; up to RA - 3 finished rows wait for the epilogue)
-  constexpr bool NBLK = NTAPS == 9 && (BN == 32 || BN == 64);
+  constexpr bool NBLK = NTAPS == 9 && (BN == 16 || BN == 32 || BN == 64);
   constexpr int RA_N = 8;
   constexpr uint32_t NBLK_COLS = RA_N * BN;  // 256 / 512
 
@@ -177,9 +182,9 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
   __shared__ uint64_t slot_full[kRowsMaxRing];
   __shared__ uint64_t slot_empty[kRowsMaxRing];
   __shared__ uint64_t slot_ready[kRowsMaxRing];  // ELU-on-load: the slot's rows have been transformed
-  __shared__ uint64_t tslot_free[8];             // ELU-on-load + A in TMEM: the tensor-memory row slot may be rewritten
   __shared__ uint64_t acc_full[8];
   __shared__ uint64_t acc_empty[8];
+  __shared__ uint64_t res_bar[8];  // TMA epilogue: a warp's residual tile has landed
   __shared__ uint32_t tmem_base_slot;
   __shared__ float s_scale[BN];
   __shared__ float s_shift[BN];
@@ -198,18 +203,20 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA[0]);
     tma_prefetch_desc(&p.tmB);
+    if (p.tma) tma_prefetch_desc(&p.tmO);
+    if (p.tma > 1) tma_prefetch_desc(&p.tmR);
   }
   if (warp == 1 && lane == 0) {
     mbar_init(&w_full, 1);
     for (int i = 0; i < R; ++i) {
       mbar_init(&slot_full[i], 1);
       mbar_init(&slot_empty[i], 1);
-      mbar_init(&slot_ready[i], (TST && ATM_OK && p.atm) ? 4 : 1);  // all four transform warps / the row's owner
+      mbar_init(&slot_ready[i], 1);  // the transform warp that owns the row
     }
-    for (int i = 0; i < 8; ++i) mbar_init(&tslot_free[i], 1);
     for (int i = 0; i < 8; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 4);  // one arrival per epilogue warp of the owning warpgroup
+      mbar_init(&res_bar[i], 1);
     }
     fence_mbar_init();
   }
@@ -429,13 +436,6 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
                 }
               }
               umma_commit(&acc_full[b]);
-              if (TST) {  // input row `orow` is dead: its tensor-memory slot may be rewritten by the transform warps
-                umma_commit(&tslot_free[ts[0]]);
-                if (orow == th - 1) {
-                  umma_commit(&tslot_free[ts[1]]);
-                  umma_commit(&tslot_free[ts[2]]);
-                }
-              }
             }
             __syncwarp();
             t_first = ts[1];
@@ -500,91 +500,11 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
     // Elementwise and in place, so the TMA swizzle inside the slot does not matter: the box footprint is the
     // contiguous first (128 + 2*halo) * ROWB bytes of each source's buffer.
     if constexpr (!ELU_IN) return;
-    if constexpr (ATM_OK && TST) {
-      if (atm) {
-        // ---- A operand in tensor memory: transform from shared memory straight INTO tensor memory ----
-        // TMEM lane m of column-tap copy q holds box pixel m + q.  Each warp serves its own lane quarter: a lane
-        // loads and activates box pixel 32k + lane (and, lanes 0-1, the two pixels past the quarter), the shifted
-        // copies come from warp shuffles, and three tcgen05.st per 32 channels write the copies.  Nothing is
-        // written back to shared memory and the MMA warp issues no tcgen05.cp for this source.
-        const int k = warp & 3;
-        const uint32_t a_tmem0 = tmem_base + 2 * BN + (static_cast<uint32_t>(k * 32) << 16);
-        constexpr int GROUPS = ROWB / 64;  // groups of 32 channels = 16 packed registers = 4 sixteen-byte chunks
-        int st = 0, tt = 0;
-        uint32_t ph = 0, tph = 0;
-        RowWalker rw;
-        for (rw.init(g_begin, g_end, p.ep.hout, p.batch); rw.valid(); rw.next_segment()) {
-          const int n_in_rows = rw.seg_left + 2 * halo;
-          for (int ir = 0; ir < n_in_rows; ++ir) {
-            mbar_wait(&slot_full[st], ph);
-            mbar_wait(&tslot_free[tt], tph ^ 1);
-            tc_fence_after();
-#pragma unroll
-            for (int s = 0; s < NSRC; ++s) {
-              if (!((p.elu_in >> s) & 1)) continue;
-              const uint32_t base = smem_u32(ring + st * slot_bytes + s * SRC_BYTES);
-              const int j0 = k * 32 + lane;                              // own box pixel
-              const int key0 = ROWB == 64 ? ((j0 >> 1) & 3) : (j0 & 7);   // TMA swizzle of the pixel's row
-              // the two pixels past the quarter (box pixels 32k+32, 32k+33): 2 x 16 packed words per channel group,
-              // ONE word per lane (lane = 16 * pixel + word) instead of a second full pass over 32 lanes
-              const int j1 = k * 32 + 32 + (lane >> 4);
-              const int key1 = ROWB == 64 ? ((j1 >> 1) & 3) : (j1 & 7);
-#pragma unroll
-              for (int g = 0; g < GROUPS; ++g) {
-                uint32_t e[16];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                  uint4 a = lds128(base + j0 * ROWB + (((4 * g + c) ^ key0) << 4));
-                  elu_bf16x8(a);
-                  e[4 * c] = a.x; e[4 * c + 1] = a.y; e[4 * c + 2] = a.z; e[4 * c + 3] = a.w;
-                }
-                uint32_t hv;
-                {
-                  const int w = 16 * g + (lane & 15);  // 32-bit word (2 channels) of the halo pixel
-                  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(hv)
-                               : "r"(base + j1 * ROWB + ((((w >> 2) ^ key1) << 4) | ((w & 3) << 2))) : "memory");
-                  float f0, f1;
-                  unpack_bf16x2(hv, f0, f1);
-                  hv = pack_bf16x2(elu1(f0), elu1(f1));
-                }
-                uint32_t v1[16], v2[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const uint32_t x1 = __shfl_down_sync(0xffffffffu, e[i], 1);
-                  const uint32_t x2 = __shfl_down_sync(0xffffffffu, e[i], 2);
-                  const uint32_t b0 = __shfl_sync(0xffffffffu, hv, i);        // halo pixel 0, word i
-                  const uint32_t b1 = __shfl_sync(0xffffffffu, hv, 16 + i);   // halo pixel 1, word i
-                  v1[i] = lane == 31 ? b0 : x1;
-                  v2[i] = lane == 30 ? b0 : (lane == 31 ? b1 : x2);
-                }
-                const uint32_t dst = a_tmem0 + tt * TSLOT_COLS + s * kdim * COPY_COLS + 16 * g;
-                tmem_st16(dst, e);
-                tmem_st16(dst + COPY_COLS, v1);
-                tmem_st16(dst + 2 * COPY_COLS, v2);
-              }
-            }
-            // (Deferring this hand-over by one row to overlap the store latency with the next row's work was
-            // measured slower: the MMA warp starves.)
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&slot_ready[st]);
-            if (++st == R) {
-              st = 0;
-              ph ^= 1;
-            }
-            if (++tt == RT) {
-              tt = 0;
-              tph ^= 1;
-            }
-          }
-        }
-      }
-    }
-    if (!(ATM_OK && TST && atm)) {
-    // Row per warp: warp tw transforms the input rows tw, tw + 4, ... on its own (16-byte chunks, 4 in flight per
-    // lane).  Splitting every row over the four warps instead made each of them pay the per-row overhead
-    // (barrier wait, fence.proxy.async, arrive): ~500 cycles per row against the ~256 the MUFU pipe needs.
+    {
+    // Row per warp: warp tw transforms the input rows tw, tw + 2, ... on its own (16-byte chunks, 4 in flight per
+    // lane).  Splitting every row over several warps instead made each of them pay the per-row overhead (barrier
+    // wait, fence.proxy.async, arrive).  Two warps (~800 issue cycles per row each) keep up with the ~900-cycle row
+    // period and leave the kernel at 384 threads = 168 registers, which the epilogue's in-register affine needs.
     const int tw = warp - 10;
     constexpr int n_chunks = (kRowsW + 2 * halo) * ROWB / 16;
     int st = 0;
@@ -594,7 +514,7 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
     for (rw.init(g_begin, g_end, p.ep.hout, p.batch); rw.valid(); rw.next_segment()) {
       const int n_in_rows = rw.seg_left + 2 * halo;
       for (int ir = 0; ir < n_in_rows; ++ir, ++rowc) {
-        if ((rowc & 3) == tw) {
+        if ((rowc & 1) == tw) {
           mbar_wait(&slot_full[st], ph);
 #pragma unroll
           for (int s = 0; s < NSRC; ++s) {
@@ -638,7 +558,7 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
     const int m = q * 32 + lane;
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);  // + slot * BN: this row's accumulator
     const bool has_res = p.ep.residual != nullptr;
-    const bool bf16_out = (p.ep.flags & (VUB_CONV_F32_NHWC | VUB_CONV_F32_NCHW)) == 0;
+    const bool bf16_out = (p.ep.flags & (VUB_CONV_F32_NHWC | VUB_CONV_F32_NCHW | VUB_CONV_U8_HWC)) == 0;
     const uint32_t t0 = smem_u32(staging) + (warp - 2) * EpiStage<SGW>::WARP_BYTES;  // residual in / raw out
     const uint32_t t1 = t0 + EpiStage<SGW>::TILE_BYTES;                               // elu out
     constexpr int CPR = SGW / 8;
@@ -735,7 +655,40 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
     }
     if constexpr (!BWD) {
     ahead = cur;
-    if (STAGED && has_res && bf16_out && cur.valid()) prefetch_res(cur);
+    // ---- TMA epilogue state ----
+    constexpr bool TMA_OK = STAGED;  // BN 32 / 64
+    const bool one_out = (p.ep.out_raw != nullptr) != (p.ep.out_elu != nullptr);
+    const int tma = (TMA_OK && bf16_out && one_out) ? p.tma : 0;
+    const bool tma_res = tma > 1 && has_res;
+    const int wi = warp - 2;
+    const uint32_t tR = t0, tO = has_res ? t1 : t0;  // TMA mode: residual tile / output tile
+    uint32_t rph = 0;
+    // box coordinate of a warp's 32-pixel block in the [pixels (pairs at BN = 32)] x [128 bytes] view
+    auto box_row = [&](const RowWalker& r) {
+      const long long pix = ((long long)r.n * p.ep.hout + r.h) * p.ep.wout + r.w0 + q * 32;
+      return static_cast<int>(BN == 32 ? pix >> 1 : pix);
+    };
+    auto tma_res_issue = [&](const RowWalker& r) {
+      if (lane == 0) {
+        mbar_expect_tx(&res_bar[wi], TmaStage<SGW>::TILE_BYTES);
+        tma_load_2d(reinterpret_cast<void*>(smem + (tR - smem_u32(smem))), &p.tmR, &res_bar[wi], 0, box_row(r));
+      }
+    };
+    // per-channel affine in registers where they fit (BN <= 32): the per-row broadcast reads of s_scale / s_shift were a
+    // quarter of this epilogue's shared-memory wavefronts
+    constexpr bool AFF_REG = BN <= 32;
+    float r_scale[AFF_REG ? BN : 1], r_shift[AFF_REG ? BN : 1];
+    if constexpr (AFF_REG) {
+#pragma unroll
+      for (int i = 0; i < BN; ++i) {
+        r_scale[i] = s_scale[i];
+        r_shift[i] = s_shift[i];
+      }
+    }
+    if (STAGED && has_res && bf16_out && cur.valid()) {
+      if (tma_res) tma_res_issue(cur);
+      else prefetch_res(cur);
+    }
     uint32_t gof = g;  // running index of this warpgroup's current row (g, g + 2, ...)
     while (cur.valid()) {
       const uint32_t aslot = gof % RA;
@@ -747,13 +700,33 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
       // BN = 32 and 18 % slower at BN = 64 — 32 cache lines per load instruction; profiles/r01_ncu_rows_smem.txt.)
       if constexpr (STAGED) {
         if (has_res && bf16_out) {
-          stage_fill_linear<SGW>(t0, rblk, lane);  // residual block -> staging; lanes then read their own row
-          __syncwarp();
-          if (ahead.valid()) prefetch_res(ahead);
+          if (tma_res) {
+            mbar_wait(&res_bar[wi], rph);
+            rph ^= 1;
+          } else if (tma) {
+#pragma unroll
+            for (int k = 0; k < CPR; ++k) {  // linear 16-byte chunks of the block -> TMA-layout tile
+              const int cidx = lane + 32 * k;
+              sts128(tR + TmaStage<SGW>::off(cidx / CPR, cidx % CPR), rblk[k]);
+            }
+            __syncwarp();
+            if (ahead.valid()) prefetch_res(ahead);
+          } else {
+            stage_fill_linear<SGW>(t0, rblk, lane);  // residual block -> staging; lanes then read their own row
+            __syncwarp();
+            if (ahead.valid()) prefetch_res(ahead);
+          }
         }
       }
       mbar_wait(&acc_full[aslot], (gof / RA) & 1);
       tc_fence_after();
+      if constexpr (STAGED) {
+        if (tma) {
+          // the previous tile's store must have finished reading the output tile before it is rewritten
+          if (lane == 0) bulk_wait_read<0>();
+          __syncwarp();
+        }
+      }
 #pragma unroll
       for (int c = 0; c < NCHUNK; ++c) {
         uint32_t acc[CH];
@@ -766,10 +739,28 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
           if (lane == 0) mbar_arrive(&acc_empty[aslot]);
         }
         float y[CH];
+        if constexpr (AFF_REG) {
 #pragma unroll
-        for (int i = 0; i < CH; ++i) y[i] = fmaf(__uint_as_float(acc[i]), s_scale[c * CH + i], s_shift[c * CH + i]);
+          for (int i = 0; i < CH; ++i) y[i] = fmaf(__uint_as_float(acc[i]), r_scale[c * CH + i], r_shift[c * CH + i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < CH; ++i) y[i] = fmaf(__uint_as_float(acc[i]), s_scale[c * CH + i], s_shift[c * CH + i]);
+        }
         if constexpr (STAGED) {
           if (bf16_out) {
+            if (tma) {
+              if (has_res) {
+#pragma unroll
+                for (int j = 0; j < CH / 8; ++j)
+                  add_bf16x8(lds128(tR + TmaStage<SGW>::off(lane, c * (CH / 8) + j)), &y[8 * j]);
+              }
+              if (p.ep.out_elu != nullptr) {
+#pragma unroll
+                for (int i = 0; i < CH; ++i) y[i] = elu1(y[i]);
+              }
+              stage_put32_tma<SGW>(tO, lane, c * CH, y);
+              continue;
+            }
             if (has_res) {
 #pragma unroll
               for (int j = 0; j < CH / 8; ++j)
@@ -794,15 +785,28 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
       }
       if constexpr (STAGED) {
         if (bf16_out) {
-          const long long off = block_off(cur);
-          __syncwarp();
-          if (p.ep.out_raw != nullptr) stage_flush_linear<SGW>(t0, p.ep.out_raw + off, lane);
-          if (p.ep.out_elu != nullptr) stage_flush_linear<SGW>(t1, p.ep.out_elu + off, lane);
-          __syncwarp();
+          if (tma) {
+            fence_proxy_async();  // this lane's tile writes -> visible to the TMA engine
+            __syncwarp();         // ... all 32 lanes' (and every lane has read its residual chunks)
+            if (lane == 0) {
+              tma_store_2d(&p.tmO, tO, 0, box_row(cur));
+              bulk_commit();
+            }
+            if (tma_res && ahead.valid()) tma_res_issue(ahead);  // the residual tile is free again
+          } else {
+            const long long off = block_off(cur);
+            __syncwarp();
+            if (p.ep.out_raw != nullptr) stage_flush_linear<SGW>(t0, p.ep.out_raw + off, lane);
+            if (p.ep.out_elu != nullptr) stage_flush_linear<SGW>(t1, p.ep.out_elu + off, lane);
+            __syncwarp();
+          }
         }
       }
       gof += 2;
       cur = ahead;
+    }
+    if constexpr (STAGED) {
+      if (tma && lane == 0) bulk_wait<0>();  // all tiles written before the CTA's shared memory goes away
     }
     }  // !BWD
   }
@@ -913,7 +917,7 @@ static int rows_job_launch(const RowsJob& j, cudaStream_t stream) {
   kp.bwd[0] = j.bwd[0];
   kp.bwd[1] = j.bwd[1];
   kp.elu_in = j.elu_in & ((1 << j.nsrc) - 1);
-  kp.nblk = (j.taps == 9 && (j.bn == 32 || j.bn == 64) && env_int("VUB_ROWS_NBLK", 1)) ? 1 : 0;
+  kp.nblk = (j.taps == 9 && (j.bn == 16 || j.bn == 32 || j.bn == 64) && env_int("VUB_ROWS_NBLK", 1)) ? 1 : 0;
   kp.atm = (!kp.nblk && j.taps == 9 && 2 * j.bn + 3 * 3 * j.nsrc * (bkc / 2) <= 512 && env_int("VUB_ROWS_ATM", 1)) ? 1 : 0;
   const size_t wbytes = (size_t)j.nsrc * j.taps * j.bn * bkc * 2;
   const size_t slot = (size_t)j.nsrc * (bkc == 64 ? 136 * 128 : 144 * 64);
@@ -943,6 +947,29 @@ static int rows_job_launch(const RowsJob& j, cudaStream_t stream) {
   const uint32_t boxB[2] = {(uint32_t)bkc, (uint32_t)j.bn};
   rc = encode_tmap_bf16(&kp.tmB, j.w_packed, 2, dimsb, stridesb, boxB, bkc * 2, true);
   if (rc) return rc;
+
+  // TMA epilogue: forward, exactly one bf16 NHWC output of 32 / 64 channels (the inference path's lean activations)
+  kp.tma = 0;
+  const bool bf16_one_out = j.n_halves == 0 && (j.ep.flags & (VUB_CONV_F32_NHWC | VUB_CONV_F32_NCHW | VUB_CONV_U8_HWC |
+                                                               VUB_CONV_D2S)) == 0 &&
+                            ((j.ep.out_raw != nullptr) != (j.ep.out_elu != nullptr));
+  if (bf16_one_out && (j.bn == 32 || j.bn == 64)) {
+    kp.tma = env_int("VUB_ROWS_TMA", 2);
+    if (kp.tma) {
+      const uint64_t total_pix = (uint64_t)j.batch * j.h * j.w;
+      const uint64_t rows128 = j.bn == 32 ? total_pix / 2 : total_pix;  // 128-byte rows: pixel pairs at 32 channels
+      const uint64_t dimso[2] = {64, rows128};
+      const uint64_t strideso[1] = {128};
+      const uint32_t boxo[2] = {64, (uint32_t)(j.bn == 32 ? 16 : 32)};
+      void* outp = j.ep.out_raw != nullptr ? (void*)j.ep.out_raw : (void*)j.ep.out_elu;
+      rc = encode_tmap_bf16(&kp.tmO, outp, 2, dimso, strideso, boxo, 128, false);
+      if (rc) return rc;
+      if (kp.tma > 1 && j.ep.residual != nullptr) {
+        rc = encode_tmap_bf16(&kp.tmR, j.ep.residual, 2, dimso, strideso, boxo, 128, false);
+        if (rc) return rc;
+      }
+    }
+  }
 
   static int n_sm = 0;
   if (n_sm == 0) {

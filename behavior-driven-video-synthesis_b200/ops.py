@@ -67,7 +67,7 @@ _LIB.define("stem_bwd(Tensor x, Tensor dy, Tensor(a!) gt, Tensor(b!) dy_sum) -> 
 _LIB.define("latent_bwd(Tensor logstd, Tensor? eps, Tensor? d_mu, Tensor? d_ls, Tensor? dz) -> Tensor")
 _LIB.define("nchw_to_nhwc_pad(Tensor x, int c_pad) -> Tensor")
 
-F32_NONE, F32_NHWC, F32_NCHW = 0, 1, 2
+F32_NONE, F32_NHWC, F32_NCHW, U8_HWC = 0, 1, 2, 3
 
 # ---- launch accounting (bench.py's "gpu_launches" and per-kernel roofline) -----------------------
 LAUNCHES = 0          # kernels of THIS package launched since import (graph replays are counted by the caller)
@@ -152,6 +152,9 @@ def _conv_fwd_cuda(x0, x1, w, scale, shift, residual, ksize, stride, cout_valid,
         if f32_mode == F32_NHWC:
             flags |= N.CONV_F32_NHWC
             out = torch.empty((B, Ho, Wo, cout), dtype=torch.float32, device=x0.device)
+        elif f32_mode == U8_HWC:
+            flags |= N.CONV_U8_HWC
+            out = torch.empty((B, Ho, Wo, cout_valid), dtype=torch.uint8, device=x0.device)
         else:
             flags |= N.CONV_F32_NCHW
             out = torch.empty((B, cout_valid, Ho, Wo), dtype=torch.float32, device=x0.device)
@@ -592,11 +595,18 @@ def elu_in_ok(nsrc: int, c_src: int, cout: int, ksize: int, stride: int, h: int,
     return bool(N.lib().vub_conv_fwd_elu_in_ok(nsrc, c_src, cout, ksize, stride, h, w))
 
 
+@functools.lru_cache(maxsize=None)
+def u8_out_ok(nsrc: int, c_src: int, cout: int, ksize: int, stride: int, h: int, w: int) -> bool:
+    """Host query (vub_conv_fwd_u8_out_ok): can a conv of this geometry store uint8 HWC video frames itself?"""
+    return bool(N.lib().vub_conv_fwd_u8_out_ok(nsrc, c_src, cout, ksize, stride, h, w))
+
+
 def conv_fwd_f32(x: Sequence[torch.Tensor], w, scale, shift, *, ksize: int, layout: str,
                  cout_valid: Optional[int] = None, stages: int = 0, w_tiled: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """fp32 output, ``layout`` in {"nhwc", "nchw"} (latent head input / out_conv image)."""
+    """fp32 output, ``layout`` in {"nhwc", "nchw"} (latent head input / out_conv image); ``"u8_hwc"``: uint8 HWC
+    video frames ``(scale_img(y) * 255).astype(uint8)`` (only where :func:`u8_out_ok`)."""
     cv = w.shape[0] if cout_valid is None else cout_valid
-    mode = F32_NHWC if layout == "nhwc" else F32_NCHW
+    mode = F32_NHWC if layout == "nhwc" else (U8_HWC if layout == "u8_hwc" else F32_NCHW)
     return _ops.conv_fwd(x[0], x[1] if len(x) > 1 else None, w, scale, shift, None, ksize, 1, cv, False, False,
                          False, mode, stages, 0, w_tiled)[0]
 

@@ -93,8 +93,7 @@ class _GraphedSynthesizer:
         raise NotImplementedError
 
     def _step(self, s: _IoSet) -> torch.Tensor:
-        imgs = self._forward(s.x, s.c)
-        return ops.frames_to_uint8(imgs) if self.uint8_frames else imgs
+        return self._forward(s.x, s.c)
 
     def _capture_set(self, s: _IoSet) -> None:
         with torch.no_grad():
@@ -239,7 +238,7 @@ class FrameSynthesizer(_GraphedSynthesizer):
                          uint8_inputs)
 
     def _forward(self, x, c):
-        return self.model.transfer(x, c)
+        return self.model.transfer(x, c, uint8_frames=self.uint8_frames)
 
 
 class SequenceSynthesizer(_GraphedSynthesizer):
@@ -262,4 +261,4 @@ class SequenceSynthesizer(_GraphedSynthesizer):
 
     def _forward(self, x, c):
         app = self.model.encode_appearance(x)
-        return self.model.decode_pose(c, app, self.T)
+        return self.model.decode_pose(c, app, self.T, uint8_frames=self.uint8_frames)

@@ -199,9 +199,11 @@ class DecDownAlter(nn.Module):
                 self.ups.append(Upsample(nf, out_c, subpixel=True))
                 nf = out_c
 
-    def _run(self, bank, gs: List[Act], zs: List[Act], training: bool) -> torch.Tensor:
+    def _run(self, bank, gs: List[Act], zs: List[Act], training: bool, uint8_frames: bool = False) -> torch.Tensor:
         """``zs[i]``: activation holding ELU(z_i) (posterior sample or mean); ignored when ``training`` is
-        False (then z ~ N(0, I) is drawn like the reference, models/vunets.py:352)."""
+        False (then z ~ N(0, I) is drawn like the reference, models/vunets.py:352).  ``uint8_frames``: return uint8
+        HWC video frames, the reference renderer's ``(scale_img(img) * 255).astype(uint8)`` — stored by ``out_conv``'s
+        epilogue where the kernel supports it, else converted from the fp32 image by one more kernel."""
         gs = list(gs)
         zs = list(zs)
         h = self.nin._run(bank, [(gs[-1], "raw")])
@@ -226,10 +228,15 @@ class DecDownAlter(nn.Module):
         assert not gs
         if training:
             assert not zs
+        if uint8_frames and bank.tape is None and bank.precision == "bf16":
+            B_, hh, ww, cc = h.raw.shape
+            cw = bank.get(self.out_conv)
+            if ops.u8_out_ok(1, cc, cw.cout_pad, cw.ksize, 1, hh, ww):
+                return self.out_conv._run_f32(bank, [(h, "raw")], "u8_hwc")[0]
         img, slot = self.out_conv._run_f32(bank, [(h, "raw")], "nchw")
         if bank.tape is not None:
             bank.tape.img_slot = slot
-        return img
+        return ops.frames_to_uint8(img) if uint8_frames else img
 
     def forward(self, gs, zs_posterior, training):
         warn_forward_only(self, "DecDownAlter.forward", *gs, *zs_posterior)
@@ -394,7 +401,7 @@ class VunetAlter(nn.Module):
         _, _, lat = self._encode(bank, x, eps, skip_dead=True, want_elu_mu=True)
         return [r["mu_act"] for r in lat]
 
-    def decode_pose(self, c, appearance, frames_per_appearance: int = 1):
+    def decode_pose(self, c, appearance, frames_per_appearance: int = 1, uint8_frames: bool = False):
         """The pose half of :meth:`transfer` — ``du`` + ``dd`` — for ``c`` = ``[S * T, 3, H, W]`` stickmen of ``S``
         sequences with ``T = frames_per_appearance`` frames each (sequence-major), ``appearance`` from
         :meth:`encode_appearance` on the ``S`` appearance images.  Equals
@@ -406,12 +413,15 @@ class VunetAlter(nn.Module):
         if appearance[0].elu.shape[0] != c.shape[0]:
             raise ValueError("decode_pose: c must hold frames_per_appearance frames for every appearance image")
         gs = self.du._run(bank, _as_input(c))
-        return self.dd._run(bank, gs, list(appearance), True)
+        return self.dd._run(bank, gs, list(appearance), True, uint8_frames=uint8_frames)
 
-    def transfer(self, x, c, eps: Optional[Sequence[torch.Tensor]] = None):
+    def transfer(self, x, c, eps: Optional[Sequence[torch.Tensor]] = None, uint8_frames: bool = False):
+        """``uint8_frames=True`` (extension): return ``[B, H, W, 3]`` uint8 video frames instead of the fp32 NCHW image —
+        bit-identical to ``(scale_img(transfer(x, c)) * 255).permute(0, 2, 3, 1).astype(uint8)`` of the reference's
+        rendering loop (data/data_conversions_3d.py:1166-1173), written directly by ``out_conv``'s epilogue."""
         _require_cuda(x)
         _require_cuda(c)
         warn_forward_only(self, "VunetAlter.transfer", x, c)
         bank = self._bank()
         _keep, _, lat, gs = self._encode_and_pose(bank, x, c, eps, want_elu_mu=True)
-        return self.dd._run(bank, gs, [r["mu_act"] for r in lat], True)
+        return self.dd._run(bank, gs, [r["mu_act"] for r in lat], True, uint8_frames=uint8_frames)

@@ -42,6 +42,10 @@ extern "C" {
 #define VUB_CONV_F32_NCHW 4u   /* out_f32 is [B,cout_valid,Ho,Wo] fp32 */
 #define VUB_CONV_ELU_IN0 8u    /* x[0] holds RAW activations: apply ELU while loading (VunetRNB's ELU(x), */
 #define VUB_CONV_ELU_IN1 16u   /* lib/modules.py:225-231); same for x[1].  Only where vub_conv_fwd_elu_in_ok() */
+#define VUB_CONV_U8_HWC 32u    /* out_f32 points to a uint8 HWC image [B,Ho,Wo,cout_valid]: the reference's video-frame
+                                  conversion (scale_img(y) * 255).astype(uint8) (lib/utils.py:658-668,
+                                  data/data_conversions_3d.py:1166-1173) fused into out_conv's epilogue.  Only where
+                                  vub_conv_fwd_u8_out_ok() */
 
 /* ABI version of the loaded library (== VUB_ABI_VERSION it was built with). */
 int vub_abi_version(void);
@@ -82,6 +86,9 @@ typedef struct vub_conv_desc {
 } vub_conv_desc;
 
 int vub_conv_fwd(const vub_conv_desc* d, void* stream);
+/* 1 when a conv of this geometry can store VUB_CONV_U8_HWC frames (the row-streaming kernel takes it), else 0 */
+int vub_conv_fwd_u8_out_ok(int32_t nsrc, int32_t c_src, int32_t cout, int32_t ksize, int32_t stride, int32_t hin,
+                           int32_t win);
 
 /*
  * Pure host query: 1 when vub_conv_fwd accepts VUB_CONV_ELU_IN0/1 for a conv of this geometry (it is served by

@@ -402,9 +402,10 @@ def test_uint8_image_inputs_are_bit_identical_to_converted_fp32_inputs():
 
 def test_host_pipeline_uint8_matches_direct_transfer():
     """``FrameSynthesizer.render_host`` with uint8 HWC host buffers (two alternating graph / buffer sets, copies on
-    their own streams, no staging copies) returns exactly ``frames_to_uint8(transfer(x, c))`` for every batch of a
-    stream of different batches — and the fp32 variant of the pipeline agrees with ``transfer``."""
-    from bdvs_b200 import ops
+    their own streams, no staging copies) returns exactly ``transfer(x, c, uint8_frames=True)`` for every batch of a
+    stream of different batches.  The latent noise is drawn inside the step from the global generator: an eager
+    synthesizer must reproduce the eager loop bit for bit, and the graphed pipeline must reproduce the same
+    synthesizer's sequential graph replays (same seed -> same Philox offsets per replay)."""
     from bdvs_b200.synthesis import FrameSynthesizer
     cfg = dict(H256, spatial_size=64)
     m, _ = build(cfg)
@@ -412,23 +413,36 @@ def test_host_pipeline_uint8_matches_direct_transfer():
     g = torch.Generator().manual_seed(3)
     xs = [torch.randint(0, 256, (B, 64, 64, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(n_batches)]
     cs = [torch.randint(0, 256, (B, 64, 64, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(n_batches)]
-    outs = [torch.zeros(B, 64, 64, 3, dtype=torch.uint8).pin_memory() for _ in range(n_batches)]
-    fs = FrameSynthesizer(m, B, uint8_frames=True, uint8_inputs=True)
-    # the latent noise is drawn inside the graphs from the global generator: replay the same stream for the check
-    torch.manual_seed(99)
-    for i in range(n_batches):
-        fs.render_host(xs[i], cs[i], outs[i])
-    fs.join()
-    torch.cuda.synchronize()
+
+    def pipeline(fs):
+        outs = [torch.zeros(B, 64, 64, 3, dtype=torch.uint8).pin_memory() for _ in range(n_batches)]
+        torch.manual_seed(99)
+        for i in range(n_batches):
+            fs.render_host(xs[i], cs[i], outs[i])
+        fs.join()
+        torch.cuda.synchronize()
+        return outs
+
+    # (a) eager steps through the pipeline == the plain eager loop
+    outs = pipeline(FrameSynthesizer(m, B, uint8_frames=True, uint8_inputs=True, use_graph=False))
     torch.manual_seed(99)
     with torch.no_grad():
         for i in range(n_batches):
-            want = ops.frames_to_uint8(m.transfer(xs[i].cuda(), cs[i].cuda())).cpu()
+            want = m.transfer(xs[i].cuda(), cs[i].cuda(), uint8_frames=True).cpu()
             assert torch.equal(outs[i], want), i
+    # (b) graphed pipeline (two alternating sets) == sequential replays of the same synthesizer
+    fs = FrameSynthesizer(m, B, uint8_frames=True, uint8_inputs=True)
+    pipeline(fs)  # the first call captures the second graph (its warm-up steps draw noise): settle before seeding
+    outs = pipeline(fs)
+    torch.manual_seed(99)
+    for i in range(n_batches):
+        want = fs(xs[i].cuda(), cs[i].cuda()).cpu()
+        assert torch.equal(outs[i], want), i
+    assert len({int(o.sum()) for o in outs}) == n_batches  # different batches really produced different frames
     with pytest.raises(ValueError):
         fs.render_host(xs[0].float(), cs[0], outs[0])
     # fp32 NCHW pipeline
-    fs32 = FrameSynthesizer(m, B)
+    fs32 = FrameSynthesizer(m, B, use_graph=False)
     x, c, _, _ = O.make_inputs(cfg, B, tag="host32")
     out32 = torch.zeros(B, 3, 64, 64).pin_memory()
     torch.manual_seed(5)
@@ -438,3 +452,19 @@ def test_host_pipeline_uint8_matches_direct_transfer():
     torch.manual_seed(5)
     with torch.no_grad():
         assert torch.equal(out32, m.transfer(x.cuda(), c.cuda()).cpu())
+
+
+@pytest.mark.parametrize("cfg", [H256, M128])
+def test_out_conv_uint8_epilogue_equals_converted_fp32_image(cfg):
+    """``transfer(..., uint8_frames=True)``: at >= 128 pixels wide ``out_conv``'s epilogue stores the uint8 HWC video
+    frame itself (VUB_CONV_U8_HWC); the bytes must equal the reference expression applied to the fp32 image."""
+    from bdvs_b200 import ops
+    m, _ = build(cfg)
+    x, c, eps, _ = O.make_inputs(cfg, 2, tag="u8out")
+    assert ops.u8_out_ok(1, 32, 16, 3, 1, cfg["spatial_size"], cfg["spatial_size"])
+    with torch.no_grad():
+        img = m.transfer(x.cuda(), c.cuda(), eps=cuda(eps))
+        frames = m.transfer(x.cuda(), c.cuda(), eps=cuda(eps), uint8_frames=True)
+    want = (torch.clamp((img + 1.0) / 2.0, 0.0, 1.0) * 255.0).permute(0, 2, 3, 1).cpu().numpy().astype("uint8")
+    assert frames.dtype == torch.uint8 and tuple(frames.shape) == (2, cfg["spatial_size"], cfg["spatial_size"], 3)
+    assert (frames.cpu().numpy() == want).all()
