@@ -31,7 +31,7 @@
 namespace vub {
 
 constexpr int kRowsThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue A, warps 6-9 epilogue B
-constexpr int kRowsThreadsElu = 384;  // + warps 10-11: ELU-on-load transform of freshly landed input rows
+constexpr int kRowsThreadsElu = 448;  // + warps 10-13: ELU-on-load transform of freshly landed input rows
 constexpr int kRowsMaxRing = 8;
 constexpr int kRowsW = 128;  // output columns per CTA = UMMA M
 
@@ -51,7 +51,7 @@ struct RowsKParams {
   int n_halves;         // 0 = forward epilogue (ep), 1 or 2 = data-gradient epilogue (bwd[])
   int stage_tiles;      // staging tiles per epilogue warp in data-gradient mode
   TileEpi bwd[2];
-  // ELU-on-load (VUB_CONV_ELU_IN0/1): bit s set = source s holds RAW activations; two extra warps apply ELU to
+  // ELU-on-load (VUB_CONV_ELU_IN0/1): bit s set = source s holds RAW activations; four extra warps apply ELU to
   // every input row in place in its ring slot before the tensor core reads it, so the producer of that tensor
   // never writes an ELU copy to HBM and the residual (the same raw tensor) is an L2 hit.
   int elu_in;
@@ -163,8 +163,7 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
   // and therefore some slack
   constexpr int RT_MAX = ATM_OK ? (512 - 2 * BN) / TSLOT_COLS : 3;
   // (Round 1 also wrote the activated rows of the concat layer to TMEM from registers with tcgen05.st, 0.246 -> 0.216
-  // ms; stacking the kernel rows along N (nblk) reaches 0.211 ms with the plain in-place transform, so that path is
-  // gone and the transform needs only two warps.)
+  // ms; stacking the kernel rows along N (nblk) reaches 0.211 ms with the plain in-place transform: that path is gone.)
   constexpr bool TST = false;
   constexpr int RT = 3;
   constexpr uint32_t ATM_USE = 2 * BN + RT * TSLOT_COLS;
@@ -501,10 +500,10 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
     // contiguous first (128 + 2*halo) * ROWB bytes of each source's buffer.
     if constexpr (!ELU_IN) return;
     {
-    // Row per warp: warp tw transforms the input rows tw, tw + 2, ... on its own (16-byte chunks, 4 in flight per
-    // lane).  Splitting every row over several warps instead made each of them pay the per-row overhead (barrier
-    // wait, fence.proxy.async, arrive).  Two warps (~800 issue cycles per row each) keep up with the ~900-cycle row
-    // period and leave the kernel at 384 threads = 168 registers, which the epilogue's in-register affine needs.
+    // Row per warp: warp tw transforms the input rows tw, tw + 4, ... on its own (16-byte chunks, 4 in flight per
+    // lane).  Splitting every row over the four warps instead made each of them pay the per-row overhead
+    // (barrier wait, fence.proxy.async, arrive).  A row costs one warp ~2800 cycles (measured: with TWO transform
+    // warps the 1x1 layer fell from 945 to 1400 cycles per row), so four warps are needed for a ~900-cycle row period.
     const int tw = warp - 10;
     constexpr int n_chunks = (kRowsW + 2 * halo) * ROWB / 16;
     int st = 0;
@@ -514,7 +513,7 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
     for (rw.init(g_begin, g_end, p.ep.hout, p.batch); rw.valid(); rw.next_segment()) {
       const int n_in_rows = rw.seg_left + 2 * halo;
       for (int ir = 0; ir < n_in_rows; ++ir, ++rowc) {
-        if ((rowc & 1) == tw) {
+        if ((rowc & 3) == tw) {
           mbar_wait(&slot_full[st], ph);
 #pragma unroll
           for (int s = 0; s < NSRC; ++s) {
@@ -674,9 +673,9 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
         tma_load_2d(reinterpret_cast<void*>(smem + (tR - smem_u32(smem))), &p.tmR, &res_bar[wi], 0, box_row(r));
       }
     };
-    // per-channel affine in registers where they fit (BN <= 32): the per-row broadcast reads of s_scale / s_shift were a
-    // quarter of this epilogue's shared-memory wavefronts
-    constexpr bool AFF_REG = BN <= 32;
+    // (Per-channel affine in registers instead of broadcast reads of s_scale / s_shift was measured SLOWER: 64 more live
+    // registers per lane cost the 320-thread kernels spills and ILP, 32->32 pair I/O 0.174 -> 0.187 ms.)
+    constexpr bool AFF_REG = false;
     float r_scale[AFF_REG ? BN : 1], r_shift[AFF_REG ? BN : 1];
     if constexpr (AFF_REG) {
 #pragma unroll
