@@ -66,6 +66,13 @@ struct RowsKParams {
   // M128 N32 K16 MMA costs 40 cycles for 16 cycles of math because its shared-memory operand fetch is (128 + N) rows
   // per instruction (profiles/r01_exp_rates_mma.log) — stacking N amortises the 128 A rows over three outputs.
   int nblk;
+  // ELU-on-load straight into TENSOR memory (nblk kernels): the four transform warps read a landed row from shared
+  // memory once, apply ELU in registers and write the activated row — and its two column-shifted copies, built with
+  // warp shuffles — into a tensor-memory operand slot (tcgen05.st); the nblk MMAs take A from there.  The activated
+  // row never returns to shared memory and is never read from it by the tensor core: per 128-pixel row at 32
+  // channels the shared-memory pipe carries ~350 LSU + ~170 tensor-core wavefronts instead of 744 + 414
+  // (profiles/r02_ncu_rows.txt) — that pipe, not HBM, bounded the kernel.
+  int tst;
   // TMA epilogue (forward, one bf16 output, BN 32 / 64): the finished 32-pixel tiles leave shared memory through
   // tensor-map stores issued by one lane per warp (tma = 1), and the residual rows arrive the same way (tma = 2),
   // instead of LDS + STG / LDG + STS passes of all 32 lanes — the kernel is bound by the shared-memory data pipe
@@ -171,8 +178,14 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
   // kernel rows as N blocks: ring of RA accumulator slots of BN columns (an output row's accumulator is complete
   // after THREE input rows; up to RA - 3 finished rows wait for the epilogue)
   constexpr bool NBLK = NTAPS == 9 && (BN == 16 || BN == 32 || BN == 64);
-  constexpr int RA_N = 8;
-  constexpr uint32_t NBLK_COLS = RA_N * BN;  // 256 / 512
+  constexpr int RA_N = BN == 64 ? 4 : 8;
+  constexpr uint32_t NBLK_ACC_COLS = RA_N * BN;  // 128 / 256
+  // transform into tensor memory: RTN operand slots of TSLOT_COLS columns behind the accumulators
+  constexpr bool TSTN = ELU_IN && NBLK && BN >= 32 && NSRC == 2;  // (single-source layers: measured slower, see host side)
+  constexpr int RTN_FIT = TSTN ? (512 - static_cast<int>(NBLK_ACC_COLS)) / TSLOT_COLS : 0;
+  constexpr int RTN = RTN_FIT > 4 ? 4 : RTN_FIT;
+  static_assert(!TSTN || RTN >= 2, "tensor-memory operand slots must at least double-buffer");
+  constexpr uint32_t NBLK_COLS = TSTN ? 512u : (NBLK_ACC_COLS < 32 ? 32u : NBLK_ACC_COLS);
 
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
@@ -184,6 +197,7 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
   __shared__ uint64_t acc_full[8];
   __shared__ uint64_t acc_empty[8];
   __shared__ uint64_t res_bar[8];  // TMA epilogue: a warp's residual tile has landed
+  __shared__ uint64_t tslot_free[4];  // ELU into tensor memory: the MMAs that read an operand slot have completed
   __shared__ uint32_t tmem_base_slot;
   __shared__ float s_scale[BN];
   __shared__ float s_shift[BN];
@@ -210,8 +224,9 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
     for (int i = 0; i < R; ++i) {
       mbar_init(&slot_full[i], 1);
       mbar_init(&slot_empty[i], 1);
-      mbar_init(&slot_ready[i], 1);  // the transform warp that owns the row
+      mbar_init(&slot_ready[i], (TSTN && p.tst) ? 4 : 1);  // all four transform warps / the warp that owns the row
     }
+    for (int i = 0; i < 4; ++i) mbar_init(&tslot_free[i], 1);
     for (int i = 0; i < 8; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 4);  // one arrival per epilogue warp of the owning warpgroup
@@ -220,6 +235,7 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
     fence_mbar_init();
   }
   const bool nblk = NBLK && p.nblk != 0;
+  const bool tst = TSTN && nblk && p.tst != 0;
   const bool atm = ATM_OK && p.atm != 0 && !nblk;
   const int RA = nblk ? RA_N : 2;  // accumulator slots: running output row `go` lives in slot go % RA
   if (warp == 2) {
@@ -309,6 +325,7 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
                            idesc3 = umma_idesc_bf16(kRowsW, 3 * BN);
         constexpr uint32_t wt_units = static_cast<uint32_t>(WT_BYTES) >> 4;
         uint32_t go0 = 0;  // running index of the current segment's first output row
+        int tt = 0;        // tensor-memory operand slot of the current input row (tst)
         for (rw.init(g_begin, g_end, p.ep.hout, p.batch); rw.valid(); rw.next_segment()) {
           const int th = rw.seg_left;
           for (int ir = 0; ir < th + 2; ++ir) {  // input row h0 - 1 + ir feeds the segment's output rows ir-2 .. ir
@@ -323,44 +340,53 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
             tc_fence_after();
             if (elect_one()) {
               const uint32_t a_base = ring_lo + wait_slot * slot_units;
-              // one MMA (two where the span wraps around the accumulator ring) over output rows oa .. ob
-              auto span = [&](int oa, int ob, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
+              const uint32_t a_tbase = tmem_base + NBLK_ACC_COLS + tt * TSLOT_COLS;
+              // one MMA (two where the span wraps around the accumulator ring) over output rows oa .. ob; the A
+              // operand comes from tensor memory (ts: a = TMEM column address) or shared memory (a = descriptor lo)
+              auto span = [&](int oa, int ob, bool ts, uint32_t a, uint32_t b_lo, uint32_t acc) {
                 const uint32_t sa = (go0 + oa) % RA_N;
                 const int n = ob - oa + 1;
                 const int j0 = oa - (ir - 2);
                 const int n1 = (sa + n <= RA_N) ? n : static_cast<int>(RA_N - sa);
-                umma_bf16(tmem_base + sa * BN, umma_desc_join(desc_hi, a_lo), umma_desc_join(desc_hi, b_lo + j0 * wt_units),
-                          n1 == 1 ? idesc1 : (n1 == 2 ? idesc2 : idesc3), acc);
-                if (n1 < n)
-                  umma_bf16(tmem_base, umma_desc_join(desc_hi, a_lo),
-                            umma_desc_join(desc_hi, b_lo + (j0 + n1) * wt_units), (n - n1) == 1 ? idesc1 : idesc2, acc);
+                const uint32_t id1 = n1 == 1 ? idesc1 : (n1 == 2 ? idesc2 : idesc3);
+                if (ts) umma_bf16_ts(tmem_base + sa * BN, a, umma_desc_join(desc_hi, b_lo + j0 * wt_units), id1, acc);
+                else umma_bf16(tmem_base + sa * BN, umma_desc_join(desc_hi, a), umma_desc_join(desc_hi, b_lo + j0 * wt_units), id1, acc);
+                if (n1 < n) {
+                  const uint32_t id2 = (n - n1) == 1 ? idesc1 : idesc2;
+                  if (ts) umma_bf16_ts(tmem_base, a, umma_desc_join(desc_hi, b_lo + (j0 + n1) * wt_units), id2, acc);
+                  else umma_bf16(tmem_base, umma_desc_join(desc_hi, a), umma_desc_join(desc_hi, b_lo + (j0 + n1) * wt_units), id2, acc);
+                }
               };
 #pragma unroll
               for (int s = 0; s < NSRC; ++s) {
+                const bool ts = tst && ((p.elu_in >> s) & 1);
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
 #pragma unroll
                   for (int j = 0; j < BKC / 16; ++j) {
-                    const uint32_t a_lo = a_base + s * (SRC_BYTES >> 4) + q * (ROWB >> 4) + 2 * j;
+                    const uint32_t a = ts ? a_tbase + (s * 3 + q) * COPY_COLS + 8 * j
+                                          : a_base + s * (SRC_BYTES >> 4) + q * (ROWB >> 4) + 2 * j;
                     const uint32_t b_lo = w_lo + (s * 3 + q) * 3 * wt_units + 2 * j;
                     if ((s | q | j) == 0) {
                       const int acc_hi = fresh ? ir - 1 : o_hi;
-                      if (o_lo <= acc_hi) span(o_lo, acc_hi, a_lo, b_lo, 1u);
-                      if (fresh) span(ir, ir, a_lo, b_lo, 0u);
+                      if (o_lo <= acc_hi) span(o_lo, acc_hi, ts, a, b_lo, 1u);
+                      if (fresh) span(ir, ir, ts, a, b_lo, 0u);
                     } else {
-                      span(o_lo, o_hi, a_lo, b_lo, 1u);
+                      span(o_lo, o_hi, ts, a, b_lo, 1u);
                     }
                   }
                 }
               }
               if (ir >= 2) umma_commit(&acc_full[(go0 + ir - 2) % RA_N]);  // output row ir-2 is complete
               umma_commit(&slot_empty[wait_slot]);
+              if (tst) umma_commit(&tslot_free[tt]);  // the operand slot may be rewritten by the transform warps
             }
             __syncwarp();
             if (++wait_slot == R) {
               wait_slot = 0;
               wait_ph ^= 1;
             }
+            if (TSTN && ++tt == RTN) tt = 0;
           }
           go0 += th;
         }
@@ -499,7 +525,85 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
     // Elementwise and in place, so the TMA swizzle inside the slot does not matter: the box footprint is the
     // contiguous first (128 + 2*halo) * ROWB bytes of each source's buffer.
     if constexpr (!ELU_IN) return;
-    {
+    if constexpr (TSTN) {
+      if (tst) {
+        // ---- transform from shared memory straight INTO tensor memory (see RowsKParams::tst) ----
+        // TMEM lane m of column-tap copy q holds box pixel m + q.  Each warp serves its own lane quarter: a lane
+        // loads and activates box pixel 32k + lane (and, one word per lane, the two pixels past the quarter), the
+        // shifted copies come from warp shuffles, and three tcgen05.st per 32 channels write the copies.
+        const int k = warp & 3;
+        const uint32_t a_tmem0 = tmem_base + NBLK_ACC_COLS + (static_cast<uint32_t>(k * 32) << 16);
+        constexpr int GROUPS = ROWB / 64;  // groups of 32 channels = 16 packed registers = 4 sixteen-byte chunks
+        int st = 0, tt = 0;
+        uint32_t ph = 0, tph = 0;
+        RowWalker rw;
+        for (rw.init(g_begin, g_end, p.ep.hout, p.batch); rw.valid(); rw.next_segment()) {
+          const int n_in_rows = rw.seg_left + 2 * halo;
+          for (int ir = 0; ir < n_in_rows; ++ir) {
+            mbar_wait(&slot_full[st], ph);
+            mbar_wait(&tslot_free[tt], tph ^ 1);
+            tc_fence_after();
+#pragma unroll
+            for (int s = 0; s < NSRC; ++s) {
+              if (!((p.elu_in >> s) & 1)) continue;
+              const uint32_t base = smem_u32(ring + st * slot_bytes + s * SRC_BYTES);
+              const int j0 = k * 32 + lane;                              // own box pixel
+              const int key0 = ROWB == 64 ? ((j0 >> 1) & 3) : (j0 & 7);   // TMA swizzle of the pixel's row
+              // the two pixels past the quarter (box pixels 32k+32, 32k+33): 2 x 16 packed words per channel group,
+              // ONE word per lane (lane = 16 * pixel + word) instead of a second full pass over 32 lanes
+              const int j1 = k * 32 + 32 + (lane >> 4);
+              const int key1 = ROWB == 64 ? ((j1 >> 1) & 3) : (j1 & 7);
+#pragma unroll
+              for (int g = 0; g < GROUPS; ++g) {
+                uint32_t e[16];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  uint4 a = lds128(base + j0 * ROWB + (((4 * g + c) ^ key0) << 4));
+                  elu_bf16x8(a);
+                  e[4 * c] = a.x; e[4 * c + 1] = a.y; e[4 * c + 2] = a.z; e[4 * c + 3] = a.w;
+                }
+                uint32_t hv;
+                {
+                  const int w = 16 * g + (lane & 15);  // 32-bit word (2 channels) of the halo pixel
+                  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(hv)
+                               : "r"(base + j1 * ROWB + ((((w >> 2) ^ key1) << 4) | ((w & 3) << 2))) : "memory");
+                  float f0, f1;
+                  unpack_bf16x2(hv, f0, f1);
+                  hv = pack_bf16x2(elu1(f0), elu1(f1));
+                }
+                uint32_t v1[16], v2[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const uint32_t x1 = __shfl_down_sync(0xffffffffu, e[i], 1);
+                  const uint32_t x2 = __shfl_down_sync(0xffffffffu, e[i], 2);
+                  const uint32_t b0 = __shfl_sync(0xffffffffu, hv, i);        // halo pixel 0, word i
+                  const uint32_t b1 = __shfl_sync(0xffffffffu, hv, 16 + i);   // halo pixel 1, word i
+                  v1[i] = lane == 31 ? b0 : x1;
+                  v2[i] = lane == 30 ? b0 : (lane == 31 ? b1 : x2);
+                }
+                const uint32_t dst = a_tmem0 + tt * TSLOT_COLS + s * kdim * COPY_COLS + 16 * g;
+                tmem_st16(dst, e);
+                tmem_st16(dst + COPY_COLS, v1);
+                tmem_st16(dst + 2 * COPY_COLS, v2);
+              }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&slot_ready[st]);
+            if (++st == R) {
+              st = 0;
+              ph ^= 1;
+            }
+            if (++tt == RTN) {
+              tt = 0;
+              tph ^= 1;
+            }
+          }
+        }
+      }
+    }
+    if (!tst) {
     // Row per warp: warp tw transforms the input rows tw, tw + 4, ... on its own (16-byte chunks, 4 in flight per
     // lane).  Splitting every row over the four warps instead made each of them pay the per-row overhead
     // (barrier wait, fence.proxy.async, arrive).  A row costs one warp ~2800 cycles (measured: with TWO transform
@@ -519,21 +623,25 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
           for (int s = 0; s < NSRC; ++s) {
             if (!((p.elu_in >> s) & 1)) continue;
             const uint32_t base = smem_u32(ring + st * slot_bytes + s * SRC_BYTES);
-            constexpr int n_full = n_chunks / 128;  // passes of 4 x 32 chunks
+            // 8 independent 16-byte chunks (64 elements) in flight per lane: the loop is latency-bound (ncu: the
+            // transform warps issue at 0.18 IPC, stalled on the congested shared-memory pipe and the MUFU results)
+            constexpr int UNR = 8;
+            constexpr int n_full = n_chunks / (32 * UNR);
 #pragma unroll 1
             for (int it = 0; it < n_full; ++it) {
-              const uint32_t a0 = base + 16 * (it * 128 + lane);
-              uint4 v[4];
+              const uint32_t a0 = base + 16 * (it * 32 * UNR + lane);
+              uint4 v[UNR];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) v[u] = lds128(a0 + u * 512);
+              for (int u = 0; u < UNR; ++u) v[u] = lds128(a0 + u * 512);
 #pragma unroll
-              for (int u = 0; u < 4; ++u) elu_bf16x8(v[u]);
+              for (int u = 0; u < UNR; ++u) elu_bf16x8(v[u]);
 #pragma unroll
-              for (int u = 0; u < 4; ++u) sts128(a0 + u * 512, v[u]);
+              for (int u = 0; u < UNR; ++u) sts128(a0 + u * 512, v[u]);
             }
-            constexpr int n_tail = n_chunks - n_full * 128;  // the halo pixels: 8 (C = 32) or 16 (C = 64) chunks
+            constexpr int n_tail = n_chunks - n_full * 32 * UNR;  // the halo pixels: 8 (C = 32) or 16 (C = 64) chunks
+            static_assert(n_tail <= 32, "tail must fit one pass");
             if (n_tail > 0 && lane < n_tail) {
-              const uint32_t a0 = base + 16 * (n_full * 128 + lane);
+              const uint32_t a0 = base + 16 * (n_full * 32 * UNR + lane);
               uint4 v = lds128(a0);
               elu_bf16x8(v);
               sts128(a0, v);
@@ -917,6 +1025,10 @@ static int rows_job_launch(const RowsJob& j, cudaStream_t stream) {
   kp.bwd[1] = j.bwd[1];
   kp.elu_in = j.elu_in & ((1 << j.nsrc) - 1);
   kp.nblk = (j.taps == 9 && (j.bn == 16 || j.bn == 32 || j.bn == 64) && env_int("VUB_ROWS_NBLK", 1)) ? 1 : 0;
+  // measured (B=64): into-tensor-memory wins for the concat layer (one raw + one activated source: 0.241 -> 0.222 ms)
+  // and loses for the single-source layers (32->32 0.168 -> 0.175, 64->64 0.084 -> 0.111 ms: all four warps serialise
+  // on one row's load -> ELU -> shuffle -> store chain), so only the two-source instantiation carries it
+  kp.tst = (kp.nblk && kp.elu_in && j.bn >= 32 && j.nsrc == 2 && env_int("VUB_ROWS_TST", 1)) ? 1 : 0;
   kp.atm = (!kp.nblk && j.taps == 9 && 2 * j.bn + 3 * 3 * j.nsrc * (bkc / 2) <= 512 && env_int("VUB_ROWS_ATM", 1)) ? 1 : 0;
   const size_t wbytes = (size_t)j.nsrc * j.taps * j.bn * bkc * 2;
   const size_t slot = (size_t)j.nsrc * (bkc == 64 ? 136 * 128 : 144 * 64);

@@ -18,7 +18,7 @@ fi
 stdbuf -oL timeout 200 ./test_kernels perf > ../../$out/perf_fwd.log 2>&1; echo "perf rc=$?" | tee -a ../../$out/summary.txt
 VUB_ROWS_NBLK=0 stdbuf -oL timeout 200 ./test_kernels perf > ../../$out/perf_fwd_nblk0.log 2>&1
 VUB_ROWS_TMA=0 stdbuf -oL timeout 200 ./test_kernels perf > ../../$out/perf_fwd_tma0.log 2>&1
-VUB_ROWS_TMA=1 stdbuf -oL timeout 200 ./test_kernels perf > ../../$out/perf_fwd_tma1.log 2>&1
+VUB_ROWS_TST=0 stdbuf -oL timeout 200 ./test_kernels perf > ../../$out/perf_fwd_tst0.log 2>&1
 stdbuf -oL timeout 200 ./test_bwd perf > ../../$out/perf_bwd.log 2>&1
 cd ../..
 grep PERF $out/perf_fwd.log | head -14
@@ -26,8 +26,9 @@ echo "--- NBLK=0"
 grep PERF $out/perf_fwd_nblk0.log | head -8
 echo "--- TMA=0"
 grep PERF $out/perf_fwd_tma0.log | head -8
-echo "--- TMA=1"
-grep PERF $out/perf_fwd_tma1.log | head -8
+echo "--- TST=0"
+grep PERF $out/perf_fwd_tst0.log | head -8
+if [ "$2" == "quick" ]; then exit 0; fi
 if [ -z "$2" ]; then
   timeout 1100 python -m pytest tests -m gpu -x -q --timeout 400 > $out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $out/summary.txt
   tail -15 $out/pytest_gpu.log
