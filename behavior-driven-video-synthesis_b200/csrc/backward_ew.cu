@@ -328,7 +328,7 @@ extern "C" int vub_stem_bwd(const float* x_nchw, const void* dy_nhwc, int32_t ba
                 kSbMaxCx, kSbPix);
   const long long n_chunks = (long long)batch * (hw / kSbPix);
   const long long blocks = (n_chunks + kSbWarps - 1) / kSbWarps;
-  const unsigned grid = static_cast<unsigned>(blocks < 148 * 4 ? blocks : 148 * 4);
+  const unsigned grid = static_cast<unsigned>(blocks < sm_count() * 4 ? blocks : sm_count() * 4);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const __nv_bfloat16* dyp = static_cast<const __nv_bfloat16*>(dy_nhwc);
   const int hwi = static_cast<int>(hw);

@@ -76,6 +76,17 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
   return 0;
 }
 
+int sm_count() {
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    n_sm = n > 0 ? n : 148;
+  }
+  return n_sm;
+}
+
 }  // namespace vub
 
 extern "C" int vub_abi_version(void) { return VUB_ABI_VERSION; }

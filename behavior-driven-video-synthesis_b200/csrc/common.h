@@ -43,6 +43,10 @@ inline int launch_pdl(void (*kernel)(Params), dim3 grid, dim3 block, size_t smem
   return check_launch(what);
 }
 
+// Number of SMs of the current device (queried once per process; 148 on a B200).  Every grid-size / kernel-choice
+// threshold uses this, never a literal.
+int sm_count();
+
 inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 inline int ilog2(int v) {
   int l = 0;

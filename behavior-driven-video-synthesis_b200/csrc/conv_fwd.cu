@@ -429,7 +429,7 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
   // faster there.
   const char* force = getenv("VUB_FWD_TILES");
   const long long px_tiles = ((long long)d->batch * hout * wout + kTileM - 1) / kTileM;
-  const bool small_grid = px_tiles * (cout > 256 ? cout / 256 : 1) < 148;
+  const bool small_grid = px_tiles * (cout > 256 ? cout / 256 : 1) < sm_count();
   // With the contiguous-tile epilogue (tile_epilogue_contig) the persistent kernel also wins the stride-1 N <= 128
   // layers (128->128 @64^2, B=64: 0.091 ms vs 0.136 ms per-tap), so everything with a full grid goes there.
   const bool want_tiles = force ? force[0] == '1' : !small_grid;
@@ -542,7 +542,7 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
   const int tiles_n = (d->batch + kp.tn - 1) / kp.tn;
   const int ksteps = kp.nsrc * kp.ntaps * kp.cblocks;
   kp.stages = d->stages > 0 ? d->stages : default_stages(bn, bkc, ksteps);  // stages < 0: force this kernel
-  if (d->stages <= 0 && (long long)kp.tiles_w * kp.tiles_h * tiles_n * (cout / bn) <= 148) {
+  if (d->stages <= 0 && (long long)kp.tiles_w * kp.tiles_h * tiles_n * (cout / bn) <= sm_count()) {
     // at most one CTA per SM: nothing to share the shared memory with, and with two stages only 40 KB are in
     // flight per L2/HBM round trip -> take the whole budget (the small-map layers are latency bound)
     const int deep = 190 * 1024 / ((kTileM + bn) * bkc * 2);

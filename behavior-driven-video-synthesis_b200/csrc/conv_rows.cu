@@ -1082,13 +1082,7 @@ static int rows_job_launch(const RowsJob& j, cudaStream_t stream) {
     }
   }
 
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (n_sm <= 0) n_sm = 148;
-  }
+  const int n_sm = sm_count();
   // persistent: one CTA per SM, each with a contiguous balanced range of output rows (>= 2 rows each)
   const int grid_env = env_int("VUB_ROWS_GRID", 0);
   long long want = kp.total_rows / 2 < n_sm ? kp.total_rows / 2 : n_sm;

@@ -326,13 +326,7 @@ int conv_slab_launch(const SlabJob& job, cudaStream_t stream) {
   });
   if (attr_err != cudaSuccess)
     return fail(static_cast<int>(attr_err), "cudaFuncSetAttribute(conv_slab): %s", cudaGetErrorString(attr_err));
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (n_sm <= 0) n_sm = 148;
-  }
+  const int n_sm = sm_count();
   const int grid = kp.total_items < n_sm ? kp.total_items : n_sm;
   conv_slab_kernel<<<grid, kSlabThreads, smem, stream>>>(kp);
   return check_launch("conv_slab");

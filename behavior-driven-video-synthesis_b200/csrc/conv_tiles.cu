@@ -559,13 +559,7 @@ int conv_tiles_launch(const TileJob& job, cudaStream_t stream) {
     rc = encode_tmap_bf16(&kp.tmB, job.w, 2, dims, strides, boxB, bkc * 2, true);
     if (rc) return rc;
   }
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (n_sm <= 0) n_sm = 148;
-  }
+  const int n_sm = sm_count();
   const int grid = kp.total_tiles < n_sm ? kp.total_tiles : n_sm;
   if (pair) {
     const int pairs = kp.total_tiles < n_sm / 2 ? kp.total_tiles : n_sm / 2;

@@ -412,13 +412,7 @@ static int wgrad_plan_kp(const vub_wgrad_desc* d, WgKParams& kp, int* best_split
   if (max_nb * cols_per_box + 16 > 512)
     return fail(VUB_E_SHAPE, "conv_wgrad: %d accumulator columns", max_nb * cols_per_box);
 
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (n_sm <= 0) n_sm = 148;
-  }
+  const int n_sm = sm_count();
   int n_split = n_sm / (kp.n_groups * kp.n_mtiles);
   // Every split writes (and vub_wn_bwd reads back) a full [cout_k x K] fp32 partial: on the small maps the
   // partials of 49 splits were several times the layer's own input bytes.  Keep at least kMinSteps pixel

@@ -473,13 +473,7 @@ static int stem_fwd_launch(const void* x, bool u8, const float* v, const float* 
     return fail(VUB_E_ALIGN, "stem_fwd: outputs must be 16B aligned");
   const long long hw = (long long)h * w, total = hw * batch;
   const long long chunks = (total + kStemThreads - 1) / kStemThreads;
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (n_sm <= 0) n_sm = 148;
-  }
+  const int n_sm = sm_count();
   const long long max_grid = (long long)n_sm * 8;  // persistent blocks, each looping over 128-pixel chunks
   const unsigned grid = static_cast<unsigned>(chunks < max_grid ? chunks : max_grid);
   cudaStream_t s = static_cast<cudaStream_t>(stream);

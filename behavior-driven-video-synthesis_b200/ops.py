@@ -568,7 +568,52 @@ _LIB.impl("latent_fwd", _latent_fwd_cuda, "CUDA")
 _LIB.impl("nchw_to_nhwc", _nchw_to_nhwc_cuda, "CUDA")
 _LIB.impl("nhwc_to_nchw", _nhwc_to_nchw_cuda, "CUDA")
 
-_ops = torch.ops.vunet_b200
+class _Direct:
+    """The module path calls the CUDA implementations of the registered ops DIRECTLY when its first tensor lives on
+    a CUDA device: the torch dispatcher costs ~10 us per call on a Python-registered op, which matters for the
+    launch-by-launch (eager) training step — ~270 launches, host-bound (profiles/r01_train_host_bound.log).  The ops
+    stay registered as ``torch.ops.vunet_b200.*`` (CUDA key only) for every other caller; CPU tensors are still
+    refused here, loudly.  ``VUB_DISPATCH=torch`` routes everything through the dispatcher again."""
+
+    def __init__(self):
+        import os
+        self._via_torch = os.environ.get("VUB_DISPATCH", "direct") == "torch"
+        self._impl = {}
+
+    def register(self, name, fn):
+        self._impl[name] = fn
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        if self._via_torch:
+            return getattr(torch.ops.vunet_b200, name)
+        impl = self._impl[name]
+
+        def call(*args):
+            for a in args:
+                if isinstance(a, torch.Tensor):
+                    if not a.is_cuda:
+                        raise NotImplementedError(
+                            f"vunet_b200::{name}: no CPU implementation (there is no CPU path); got a {a.device} tensor")
+                    break
+            return impl(*args)
+
+        self.__dict__[name] = call
+        return call
+
+
+_ops = _Direct()
+for _name, _fn in (("conv_fwd", _conv_fwd_cuda), ("frames_to_uint8", _frames_to_uint8_cuda),
+                   ("conv_fwd32", _conv_fwd32_cuda), ("conv_dgrad32", _conv_dgrad32_cuda),
+                   ("conv_wgrad32", _conv_wgrad32_cuda), ("latent_bwd32", _latent_bwd32_cuda),
+                   ("nchw_to_nhwc32", _nchw_to_nhwc32_cuda), ("conv_dgrad", _conv_dgrad_cuda),
+                   ("conv_wgrad", _conv_wgrad_cuda), ("wn_bwd", _wn_bwd_cuda), ("adam_wn_step", _adam_wn_step_cuda),
+                   ("adam_wn_step_dev", _adam_wn_step_dev_cuda), ("stem_bwd", _stem_bwd_cuda),
+                   ("latent_bwd", _latent_bwd_cuda), ("nchw_to_nhwc_pad", _nchw_to_nhwc_pad_cuda),
+                   ("wn_prep", _wn_prep_cuda), ("stem_fwd", _stem_fwd_cuda), ("latent_fwd", _latent_fwd_cuda),
+                   ("nchw_to_nhwc", _nchw_to_nhwc_cuda), ("nhwc_to_nchw", _nhwc_to_nchw_cuda)):
+    _ops.register(_name, _fn)
 
 
 # ------------------------------------------------------------------------------------------------
