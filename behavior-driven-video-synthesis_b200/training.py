@@ -382,10 +382,11 @@ def train_forward(model, x, c, eps: Optional[Sequence[torch.Tensor]]):
     if x.requires_grad or c.requires_grad:
         raise NotImplementedError("vunet_b200: VunetAlter.forward is differentiable w.r.t. its parameters only; "
                                   "gradients w.r.t. the inputs x / c are not produced (detach them)")
-    anchor = getattr(model, "_vub_anchor", None)
-    if anchor is None or anchor.device != x.device:
-        anchor = torch.zeros(1, device=x.device, requires_grad=True)
-        object.__setattr__(model, "_vub_anchor", anchor)
+    # A FRESH leaf per call: the autograd engine makes the caller's stream wait for the stream an input's gradient
+    # accumulator was created on.  A cached leaf keeps the accumulator of an earlier (still referenced) graph — e.g. made
+    # on the default stream — and a backward pass under CUDA-graph capture then fails with "dependency created on
+    # uncaptured work in another stream".
+    anchor = torch.zeros(1, device=x.device, requires_grad=True)
     outs = _VunetTrainFn.apply(model, x, c, None if eps is None else list(eps), anchor)
     n = model.ed.n_scales
     imgs, means, logstds, hs = outs[0], list(outs[1:1 + n]), list(outs[1 + n:1 + 2 * n]), list(outs[1 + 2 * n:])
@@ -436,13 +437,15 @@ class BucketReducer:
         self._comm = comm
         self.native = True
 
-    def __del__(self):
-        try:
-            if self._comm is not None:
-                N.lib().vub_nccl_comm_destroy(self._comm)
-                self._comm = None
-        except Exception:  # interpreter shutdown
-            pass
+    def close(self) -> None:
+        """Destroy the communicator.  Call it only after every CUDA graph that captured an exchange on it has been
+        destroyed (NCCL keeps captured graphs' references alive); never called implicitly — at interpreter exit the
+        process simply ends."""
+        if self._comm is not None:
+            torch.cuda.synchronize()
+            N.check(N.lib().vub_nccl_comm_destroy(self._comm), "vub_nccl_comm_destroy")
+            self._comm = None
+            self.native = False
 
     def bucket_ready(self, owner: str, flat: Optional[torch.Tensor]) -> None:
         if flat is None or self.world == 1:
