@@ -30,7 +30,7 @@ echo "--- TST=0"
 grep PERF $out/perf_fwd_tst0.log | head -8
 if [ "$2" == "quick" ]; then exit 0; fi
 if [ -z "$2" ]; then
-  timeout 1100 python -m pytest tests -m gpu -x -q --timeout 400 > $out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $out/summary.txt
+  timeout 1100 python -m pytest tests -m gpu -x -q -s --timeout 400 > $out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $out/summary.txt
   tail -15 $out/pytest_gpu.log
 fi
 timeout 200 python __graft_entry__.py smoke > $out/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $out/summary.txt
