@@ -23,9 +23,6 @@ from .modules import (lean_elu, Act, DepthToSpace, Downsample, NormConv2d, Space
                       WeightBank, _solo_bank, bump_weight_epoch, to_act, warn_forward_only)
 
 
-_SMALL_MAP = 16  # maps up to 16 x 16 run on fewer CTAs than SMs (at 64 frames): launch-latency-bound kernels
-
-
 def _draw_eps(shape, device) -> torch.Tensor:
     """Latent noise exactly as the reference draws it: ``torch.randn_like(std)`` on an NCHW fp32
     tensor of this shape from the global generator (models/vunets.py:596, 352)."""
@@ -52,33 +49,20 @@ class EncUp(nn.Module):
                 self.downs.append(Downsample(nf, out_c))
                 nf = out_c
 
-    def _begin(self, bank: WeightBank, x: torch.Tensor) -> dict:
-        """Stem; returns the running state that :meth:`_scales` advances."""
+    def _run(self, bank: WeightBank, x: torch.Tensor) -> List[Act]:
+        hs: List[Act] = []
         # ELU copies are skipped where every reader (the next block's 3x3, a skip connection's 1x1) applies ELU on load
         hh, ww = (x.shape[1], x.shape[2]) if x.dtype == torch.uint8 else (x.shape[2], x.shape[3])
         h = self.nin._run_stem(x, bank=bank, want_elu=not lean_elu(bank, self.nin.out_channels, hh, ww))
-        return {"h": h, "hh": hh, "ww": ww, "hs": [], "i": 0}
-
-    def _scales(self, bank: WeightBank, st: dict, stop_at_small: bool = False) -> None:
-        """Run the remaining scales; with ``stop_at_small`` return before the first scale whose map is <= 16 x 16 (the
-        launch-latency-bound tail, which ``VunetAlter`` overlaps with the other encoder's tail)."""
-        while st["i"] < self.n_scales:
-            if stop_at_small and st["hh"] <= _SMALL_MAP:
-                return
-            i, h, hh, ww = st["i"], st["h"], st["hh"], st["ww"]
+        for i in range(self.n_scales):
             for n in range(self.n_rnb):
                 blk = self.blocks[2 * i + n]
                 h = blk._run(bank, h, want_elu=not lean_elu(bank, blk.conv.out_channels, hh, ww))
-                st["hs"].append(h)
+                hs.append(h)
             if i + 1 < self.n_scales:
                 hh, ww = hh // 2, ww // 2
                 h = self.downs[i]._run(bank, h, want_elu=not lean_elu(bank, self.downs[i].down.out_channels, hh, ww))
-            st.update(h=h, hh=hh, ww=ww, i=i + 1)
-
-    def _run(self, bank: WeightBank, x: torch.Tensor) -> List[Act]:
-        st = self._begin(bank, x)
-        self._scales(bank, st)
-        return st["hs"]
+        return hs
 
     def forward(self, x, **kwargs):
         warn_forward_only(self, type(self).__name__ + ".forward", x)
@@ -359,54 +343,22 @@ class VunetAlter(nn.Module):
         """``eu`` -> ``ed`` and ``du``.  ``ed`` (a chain of ~20 kernels on 4x4 .. 16x16 maps, each a few microseconds
         on a fraction of the SMs) depends only on ``eu``; it runs on a second stream beside ``du``, whose large
         kernels hide it.  VUB_FWD_STREAMS=1 keeps one stream."""
-        one_stream = os.environ.get("VUB_FWD_STREAMS", "2") == "1"
-        if one_stream or bank.tape is not None:
-            # training records its tape in launch order and finishes one sub-network's gradient bucket after the other:
-            # keep the sub-networks contiguous (eu, ed, du); ed still runs beside du on the side stream
-            hs = self.eu._run(bank, _as_input(x))
-            hs_all = list(hs)  # keeps eu's activations alive until the side stream has read them (ed pops from `hs`)
-            if one_stream:
-                _, lat = self.ed._run(bank, hs, eps=eps, skip_dead=True, want_elu_mu=want_elu_mu)
-                gs = self.du._run(bank, _as_input(c))
-                return hs_all, hs, lat, gs
-            main = torch.cuda.current_stream()
-            side = _SIDE_STREAMS.get(main.device)
-            if side is None:
-                side = _SIDE_STREAMS[main.device] = torch.cuda.Stream(device=main.device)
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                _, lat = self.ed._run(bank, hs, eps=eps, skip_dead=True, want_elu_mu=want_elu_mu)
+        hs = self.eu._run(bank, _as_input(x))
+        hs_all = list(hs)  # keeps eu's activations alive until the side stream has read them (ed pops from `hs`)
+        if os.environ.get("VUB_FWD_STREAMS", "2") == "1":
+            _, lat = self.ed._run(bank, hs, eps=eps, skip_dead=True, want_elu_mu=want_elu_mu)
             gs = self.du._run(bank, _as_input(c))
-            main.wait_stream(side)
             return hs_all, hs, lat, gs
-        # Inference: both encoders' full-GPU scales first, then the launch-latency-bound tails side by side —
-        # side stream: eu's <= 16 x 16 scales followed by ed (which depends on eu only); main stream: du's tail.
-        # The large persistent kernels own every SM, so small kernels overlap only with other small kernels.
         main = torch.cuda.current_stream()
         side = _SIDE_STREAMS.get(main.device)
         if side is None:
             side = _SIDE_STREAMS[main.device] = torch.cuda.Stream(device=main.device)
-        se = self.eu._begin(bank, _as_input(x))
-        self.eu._scales(bank, se, stop_at_small=True)
-        sd = self.du._begin(bank, _as_input(c))
-        self.du._scales(bank, sd, stop_at_small=True)
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            self.eu._scales(bank, se)
-            hs = se["hs"]
-            hs_all = list(hs)
             _, lat = self.ed._run(bank, hs, eps=eps, skip_dead=True, want_elu_mu=want_elu_mu)
-        self.du._scales(bank, sd)
+        gs = self.du._run(bank, _as_input(c))
         main.wait_stream(side)
-        for r in lat:  # produced on the side stream, consumed (and eventually freed) on the main stream
-            for t in r.values():
-                if isinstance(t, torch.Tensor):
-                    t.record_stream(main)
-                elif isinstance(t, Act):
-                    for u in (t.raw, t.elu):
-                        if u is not None:
-                            u.record_stream(main)
-        return hs_all, hs, lat, sd["hs"]
+        return hs_all, hs, lat, gs
 
     def forward(self, x, c, eps: Optional[Sequence[torch.Tensor]] = None):
         """Returns ``(imgs, means, logstds, (hs, means, logstds))`` like the reference.  ``eps`` optionally
