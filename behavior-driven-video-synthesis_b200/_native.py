@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = (
     "vub_wn_prep",
     "vub_stem_fwd",
     "vub_stem_fwd_u8",
+    "vub_stickman_render",
     "vub_allreduce_bucket",
     "vub_nccl_version",
     "vub_nccl_unique_id",
@@ -162,6 +163,23 @@ class WgradF32Desc(C.Structure):
         ("gt_pitch", C.c_int32),
         ("split_stride", C.c_int64),
         ("sum_stride", C.c_int64),
+    ]
+
+
+class StickmanModel(C.Structure):
+    """Mirror of ``vub_stickman_model``."""
+
+    _fields_ = [
+        ("n_body", C.c_int32), ("body", C.c_int32 * 8),
+        ("n_right", C.c_int32), ("right", (C.c_int32 * 2) * 16),
+        ("n_left", C.c_int32), ("left", (C.c_int32 * 2) * 16),
+        ("n_head", C.c_int32), ("head", (C.c_int32 * 2) * 8),
+        ("n_face", C.c_int32), ("face", (C.c_int32 * 2) * 16),
+        ("rshoulder", C.c_int32), ("lshoulder", C.c_int32), ("headup", C.c_int32),
+        ("colored", C.c_int32),
+        ("right_chan", C.c_int32 * 16), ("right_col", C.c_int32 * 16),
+        ("left_chan", C.c_int32 * 16), ("left_col", C.c_int32 * 16),
+        ("head_chan", C.c_int32 * 16), ("head_col", C.c_int32 * 16),
     ]
 
 
@@ -312,6 +330,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.vub_nccl_comm_init.argtypes = [C.POINTER(vp), i32, vp, i32]
     lib.vub_nccl_comm_destroy.restype = C.c_int
     lib.vub_nccl_comm_destroy.argtypes = [vp]
+    lib.vub_stickman_render.restype = C.c_int
+    lib.vub_stickman_render.argtypes = [vp, i32, i32, C.POINTER(StickmanModel), i32, i32, vp, vp, vp]
     lib.vub_stem_fwd_u8.restype = C.c_int
     lib.vub_stem_fwd_u8.argtypes = [vp, fp, fp, fp, fp, fp, i32, i32, i32, i32, i32, vp, vp, vp]
     lib.vub_latent_num_partials.restype = i32

@@ -1,0 +1,133 @@
+"""Rendering front-end of frame synthesis: batched stickman rasterisation on the GPU.
+
+The reference's video-rendering loop (``data/data_conversions_3d.py:1130-1173``) rasterises ONE stickman per frame on
+the host with ``make_joint_img`` (``lib/utils.py:325-513``: ``cv2.fillPoly`` + ``cv2.line`` into three uint8 planes),
+applies ``ToTensor()`` + ``x * 2 - 1``, copies it to the GPU and calls ``transfer`` with batch 1.
+:class:`StickmanRasterizer` draws a whole batch of poses in one launch (``vub_stickman_render``), bit-exactly, as the
+uint8 HWC images that the stem kernel ingests directly (``vub_stem_fwd_u8``) — so a sequence goes from projected 2-D
+joints to video frames without touching the host: ``PoseRenderer(vunet, joint_model)(appearance_u8, joints)``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _native as N
+from . import ops
+
+
+def get_line_colors(n_lines_per_channel: Sequence[int]):
+    """lib/utils.py:51-66 (the ``diff_line_colors`` option of the datasets)."""
+    line_colors = []
+    for channel, nr_lines in enumerate(n_lines_per_channel):
+        interval = int(255 // (nr_lines + 1))
+        cols = []
+        for i in range(nr_lines):
+            col = [0, 0, 0]
+            col[channel] = (i + 1) * interval
+            cols.append(col)
+        line_colors.append(cols)
+    return line_colors
+
+
+class StickmanRasterizer:
+    """``imgs = StickmanRasterizer(joint_model, size)(joints)`` == ``np.stack([make_joint_img([size, size, 3], j,
+    joint_model, line_colors) for j in joints])`` of the reference, as a uint8 ``[B, size, size, 3]`` CUDA tensor.
+
+    ``joint_model``: any object with the reference ``JointModel``'s fields ``body, right_lines, left_lines, head_lines,
+    face, rshoulder, lshoulder, headup`` (``lib/utils.py``); ``line_colors``: ``None`` or the nested list
+    ``get_line_colors`` returns; ``joints``: ``[B, J, 2]`` image coordinates (x, y), float64 like the reference's numpy
+    arrays (the integer pixel is the C truncation of the double), negative = missing.  Line thickness is 1, which is
+    what every shipped config produces (``stickman_scale`` unset -> ``scale_factor=None``)."""
+
+    def __init__(self, joint_model, img_size: int, line_colors=None, scale_factor=None):
+        if scale_factor is not None and int(img_size // scale_factor) != 1:
+            raise NotImplementedError("StickmanRasterizer draws lines of thickness 1 (no shipped config sets stickman_scale)")
+        self.size = int(img_size)
+        if (self.size * self.size * 3) % 16:
+            raise ValueError("img_size**2 * 3 must be a multiple of 16")
+        m = N.StickmanModel()
+
+        def put(n_field, arr_field, lines, cap):
+            lines = list(lines)
+            if len(lines) > cap:
+                raise NotImplementedError(f"joint model has {len(lines)} {arr_field} lines (max {cap})")
+            setattr(m, n_field, len(lines))
+            arr = getattr(m, arr_field)
+            for i, (a, b) in enumerate(lines):
+                arr[i][0], arr[i][1] = int(a), int(b)
+
+        body = list(joint_model.body)
+        if len(body) > 8:
+            raise NotImplementedError("joint model body polygon has more than 8 joints")
+        m.n_body = len(body)
+        for i, j in enumerate(body):
+            m.body[i] = int(j)
+        put("n_right", "right", joint_model.right_lines, 16)
+        put("n_left", "left", joint_model.left_lines, 16)
+        put("n_head", "head", joint_model.head_lines, 8)
+        put("n_face", "face", joint_model.face, 16)
+        m.rshoulder, m.lshoulder, m.headup = int(joint_model.rshoulder), int(joint_model.lshoulder), int(joint_model.headup)
+        m.colored = 0 if line_colors is None else 1
+        if line_colors is not None:
+            def colors(chan_field, col_field, table, n):
+                for i in range(n):
+                    nz = [k for k, v in enumerate(table[i]) if v != 0]
+                    if len(nz) != 1:
+                        raise ValueError("line_colors entries must have exactly one non-zero channel (get_line_colors)")
+                    getattr(m, chan_field)[i] = nz[0]
+                    getattr(m, col_field)[i] = int(table[i][nz[0]])
+            colors("right_chan", "right_col", line_colors[0], m.n_right)
+            colors("left_chan", "left_col", line_colors[1], m.n_left)
+            colors("head_chan", "head_col", line_colors[2], max(m.n_head, m.n_face))
+        self._model = m
+        self.n_joints_min = 1 + max([m.rshoulder, m.lshoulder, m.headup] + body
+                                    + [j for l in (joint_model.right_lines, joint_model.left_lines, joint_model.head_lines,
+                                                   joint_model.face) for ab in l for j in ab])
+
+    def __call__(self, joints: torch.Tensor, out: Optional[torch.Tensor] = None, check: bool = True) -> torch.Tensor:
+        """``check``: read the per-frame "outside the verified domain" flags back (one tiny device->host copy) and raise
+        if any is set; pass False inside CUDA graphs and inspect ``self.unsupported`` afterwards."""
+        if not joints.is_cuda:
+            raise RuntimeError("vunet_b200 has no CPU path: joints must live on a CUDA device")
+        if joints.dim() != 3 or joints.shape[2] != 2 or joints.shape[1] < self.n_joints_min:
+            raise ValueError(f"joints must be [B, J >= {self.n_joints_min}, 2], got {tuple(joints.shape)}")
+        joints = joints.to(torch.float64).contiguous()
+        B = joints.shape[0]
+        s = self.size
+        if out is None:
+            out = torch.empty((B, s, s, 3), dtype=torch.uint8, device=joints.device)
+        elif out.dtype != torch.uint8 or tuple(out.shape) != (B, s, s, 3) or not out.is_contiguous():
+            raise ValueError("out must be a contiguous uint8 [B, size, size, 3] tensor")
+        flags = torch.empty((B,), dtype=torch.int32, device=joints.device)
+        N.check(ops._launch("stickman", N.lib().vub_stickman_render, joints.data_ptr(), B, joints.shape[1],
+                            C.byref(self._model), s, s, out.data_ptr(), flags.data_ptr(), ops._stream(),
+                            bytes_=float(out.numel() + joints.numel() * 8)), "vub_stickman_render")
+        self.unsupported = flags
+        if check and bool(flags.any()):
+            bad = flags.nonzero().flatten().tolist()
+            raise NotImplementedError(
+                f"StickmanRasterizer: frames {bad[:8]} have a body joint at x >= {s}; cv2.fillPoly's handling of polygons "
+                "that leave the image sideways is outside the kernel's verified bit-exact domain (clip the pose or "
+                "render those frames with the reference function)")
+        return out
+
+
+class PoseRenderer:
+    """Joints in, video frames out: ``frames = PoseRenderer(vunet, joint_model)(appearance, joints)`` — stickman
+    rasterisation, ``ToTensor()`` + ``x * 2 - 1``, ``transfer`` and the uint8 frame conversion of the reference's
+    rendering loop (``data/data_conversions_3d.py:1154-1173``) with nothing but kernels of this package in between.
+
+    ``appearance``: one image per frame, uint8 HWC ``[B, Sx, Sx, Cx]`` or fp32 NCHW in [-1, 1]; ``joints``: ``[B, J, 2]``
+    already scaled to the model's ``spatial_size`` (the loop's ``pose_i_rescaled``).  Returns uint8 ``[B, S, S, 3]``."""
+
+    def __init__(self, model, joint_model, line_colors=None):
+        self.model = model.eval()
+        self.raster = StickmanRasterizer(joint_model, model.spatial_size, line_colors)
+
+    @torch.no_grad()
+    def __call__(self, appearance: torch.Tensor, joints: torch.Tensor, uint8_frames: bool = True) -> torch.Tensor:
+        stick = self.raster(joints)
+        return self.model.transfer(appearance, stick, uint8_frames=uint8_frames)

@@ -394,6 +394,30 @@ int vub_latent_bwd_f32(const float* logstd_nchw, const float* eps_nchw, const fl
                        const float* dz_nhwc, int32_t batch, int32_t c, int32_t h, int32_t w, float* d_ml_nhwc,
                        void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Rendering front-end: batched stickman rasteriser, the GPU counterpart of `make_joint_img`
+ * (lib/utils.py:325-513: cv2.fillPoly for the body polygon, cv2.line with thickness 1 for the limbs, three uint8
+ * planes) as called per frame by the rendering loop (data/data_conversions_3d.py:1154-1160).  Output: uint8 HWC
+ * images [batch, height, width, 3] — exactly what vub_stem_fwd_u8 consumes.  Bit-exact with the reference function
+ * (tests/golden/stickman.npz) inside the verified domain: frames whose body polygon has a vertex at x >= width get
+ * unsupported[b] = 1 (the caller must not use them) instead of a guess.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vub_stickman_model {
+  int32_t n_body, body[8];                 /* joint_model.body (polygon, > 2 joints to be drawn) */
+  int32_t n_right, right[16][2];           /* joint_model.right_lines */
+  int32_t n_left, left[16][2];             /* joint_model.left_lines */
+  int32_t n_head, head[8][2];              /* joint_model.head_lines (empty: throat from the shoulder midpoint) */
+  int32_t n_face, face[16][2];             /* joint_model.face (drawn when shorter than the throat) */
+  int32_t rshoulder, lshoulder, headup;
+  int32_t colored;                         /* 0: line_colors=None (right: plane 1 / 255, left: plane 0 / 255, head: planes 0+1 / 127) */
+  int32_t right_chan[16], right_col[16];   /* colored: plane and value of line_colors[0][i] */
+  int32_t left_chan[16], left_col[16];     /* line_colors[1][i] */
+  int32_t head_chan[16], head_col[16];     /* line_colors[2][i] (the face loop indexes the same table from 0) */
+} vub_stickman_model;
+int vub_stickman_render(const double* joints_xy /* [batch][n_joints][2] */, int32_t batch, int32_t n_joints,
+                        const vub_stickman_model* model, int32_t height, int32_t width, uint8_t* out_hwc,
+                        int32_t* unsupported /* [batch] or NULL */, void* stream);
+
 /*
  * Data-parallel gradient exchange (SURVEY.md 8b `allreduce_bucket(flat, ncclComm, stream)`): in-place all-reduce of
  * one flat fp32 gradient bucket (average != 0: ncclAvg, i.e. the 1/world scaling happens inside the collective),
