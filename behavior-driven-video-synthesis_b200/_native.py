@@ -331,7 +331,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.vub_nccl_comm_destroy.restype = C.c_int
     lib.vub_nccl_comm_destroy.argtypes = [vp]
     lib.vub_stickman_render.restype = C.c_int
-    lib.vub_stickman_render.argtypes = [vp, i32, i32, C.POINTER(StickmanModel), i32, i32, vp, vp, vp]
+    lib.vub_stickman_render.argtypes = [vp, i32, i32, C.POINTER(StickmanModel), i32, i32, vp, vp]
     lib.vub_stem_fwd_u8.restype = C.c_int
     lib.vub_stem_fwd_u8.argtypes = [vp, fp, fp, fp, fp, fp, i32, i32, i32, i32, i32, vp, vp, vp]
     lib.vub_latent_num_partials.restype = i32

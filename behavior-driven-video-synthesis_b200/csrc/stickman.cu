@@ -8,12 +8,12 @@
 // 8-connected, shift 0; see oracle/stickman_oracle.py for the algorithm and how it is pinned to the reference):
 //   line     : clipLine (Cohen-Sutherland, double-precision intersection, truncation) + left-to-right Bresenham with
 //              err = dx - 2*dy;
-//   fillPoly : outline lines + scan-line fill of 16.16 fixed-point edges built from the clipped end points,
+//   fillPoly : outline lines + scan-line fill of 16.16 fixed-point edges built from the clipped end points (start
+//              extrapolated back to the unclipped row; a degenerate clip leaves a vertical edge at the border),
 //              spans [ceil(x_a), floor(x_b)] between consecutive sorted crossings.
 // One block per frame: (0) clear, (1) thread 0 builds the frame's primitive list exactly in the reference's drawing
 // order, (2) polygon outline + rows in parallel, (3) one thread per colour plane draws that plane's lines in order
-// (later lines overwrite earlier ones like in the reference).  Frames whose body polygon has a vertex at x >= width are
-// outside the verified domain of the fill (oracle header): they are flagged in `unsupported`, not guessed.
+// (later lines overwrite earlier ones like in the reference).
 #include "common.h"
 
 namespace vub {
@@ -32,7 +32,6 @@ struct StickParams {
   vub_stickman_model m;
   int n_joints, h, w;
   uint8_t* out;          // [batch][h][w][3]
-  int* unsupported;      // [batch] or nullptr
 };
 
 __device__ __forceinline__ bool clip_line_dev(int w, int h, long long& x1, long long& y1, long long& x2, long long& y2) {
@@ -138,19 +137,17 @@ __global__ void __launch_bounds__(kStickThreads) stickman_kernel(const StickPara
                                  static_cast<int>(static_cast<long long>(bx)), static_cast<int>(static_cast<long long>(by)),
                                  chan_mask, color};
     };
-    int np_ = 0, bad = 0;
+    int np_ = 0;
     if (m.n_body > 2) {
       for (int i = 0; i < m.n_body; ++i)
         if (ok(m.body[i])) {
           s_poly[np_][0] = static_cast<int>(static_cast<long long>(jx(m.body[i])));
           s_poly[np_][1] = static_cast<int>(static_cast<long long>(jy(m.body[i])));
-          if (s_poly[np_][0] >= p.w) bad = 1;
           ++np_;
         }
       if (np_ <= 2) np_ = 0;
     }
     s_n_poly = np_;
-    if (p.unsupported != nullptr) p.unsupported[b] = np_ > 0 ? bad : 0;
     for (int i = 0; i < m.n_right; ++i) {
       const int a = m.right[i][0], c = m.right[i][1];
       if (ok(a) && ok(c)) add(jx(a), jy(a), jx(c), jy(c), m.colored ? 1 << m.right_chan[i] : 2, m.colored ? m.right_col[i] * 0x010101 : 0xffffff);
@@ -199,8 +196,11 @@ __global__ void __launch_bounds__(kStickThreads) stickman_kernel(const StickPara
       if (!(x0 >= 0 && x0 < p.w && x1 >= 0 && x1 < p.w && y0 >= 0 && y0 < p.h && y1 >= 0 && y1 < p.h)) {
         long long tx0 = x0, ty0 = y0, tx1 = x1, ty1 = y1;
         clip_line_dev(p.w, p.h, tx0, ty0, tx1, ty1);
+        c0x = tx0 << 16;  // the x's are always the clipped ones; the y's only when the visible part spans > 1 row
+        c1x = tx1 << 16;  // (a degenerate clip leaves a vertical edge at the image border over the original rows)
         if (ty0 != ty1) {
-          c0x = tx0 << 16; c0y = ty0; c1x = tx1 << 16; c1y = ty1;
+          c0y = ty0;
+          c1y = ty1;
         }
       }
       if (y0 != y1) {
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kStickThreads) stickman_kernel(const StickPara
 using namespace vub;
 
 extern "C" int vub_stickman_render(const double* joints, int32_t batch, int32_t n_joints, const vub_stickman_model* model,
-                                   int32_t height, int32_t width, uint8_t* out_hwc, int32_t* unsupported, void* stream) {
+                                   int32_t height, int32_t width, uint8_t* out_hwc, void* stream) {
   clear_error();
   if (!joints || !model || !out_hwc) return fail(VUB_E_NULL, "stickman_render: NULL pointer");
   if (batch <= 0 || n_joints <= 0 || height <= 0 || width <= 0 || (static_cast<long long>(height) * width * 3) % 16)
@@ -301,7 +301,6 @@ extern "C" int vub_stickman_render(const double* joints, int32_t batch, int32_t 
   p.h = height;
   p.w = width;
   p.out = out_hwc;
-  p.unsupported = unsupported;
   stickman_kernel<<<batch, kStickThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("stickman_render");
 }

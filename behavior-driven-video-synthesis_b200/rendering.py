@@ -87,9 +87,7 @@ class StickmanRasterizer:
                                     + [j for l in (joint_model.right_lines, joint_model.left_lines, joint_model.head_lines,
                                                    joint_model.face) for ab in l for j in ab])
 
-    def __call__(self, joints: torch.Tensor, out: Optional[torch.Tensor] = None, check: bool = True) -> torch.Tensor:
-        """``check``: read the per-frame "outside the verified domain" flags back (one tiny device->host copy) and raise
-        if any is set; pass False inside CUDA graphs and inspect ``self.unsupported`` afterwards."""
+    def __call__(self, joints: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         if not joints.is_cuda:
             raise RuntimeError("vunet_b200 has no CPU path: joints must live on a CUDA device")
         if joints.dim() != 3 or joints.shape[2] != 2 or joints.shape[1] < self.n_joints_min:
@@ -101,17 +99,9 @@ class StickmanRasterizer:
             out = torch.empty((B, s, s, 3), dtype=torch.uint8, device=joints.device)
         elif out.dtype != torch.uint8 or tuple(out.shape) != (B, s, s, 3) or not out.is_contiguous():
             raise ValueError("out must be a contiguous uint8 [B, size, size, 3] tensor")
-        flags = torch.empty((B,), dtype=torch.int32, device=joints.device)
         N.check(ops._launch("stickman", N.lib().vub_stickman_render, joints.data_ptr(), B, joints.shape[1],
-                            C.byref(self._model), s, s, out.data_ptr(), flags.data_ptr(), ops._stream(),
+                            C.byref(self._model), s, s, out.data_ptr(), ops._stream(),
                             bytes_=float(out.numel() + joints.numel() * 8)), "vub_stickman_render")
-        self.unsupported = flags
-        if check and bool(flags.any()):
-            bad = flags.nonzero().flatten().tolist()
-            raise NotImplementedError(
-                f"StickmanRasterizer: frames {bad[:8]} have a body joint at x >= {s}; cv2.fillPoly's handling of polygons "
-                "that leave the image sideways is outside the kernel's verified bit-exact domain (clip the pose or "
-                "render those frames with the reference function)")
         return out
 
 

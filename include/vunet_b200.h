@@ -399,8 +399,7 @@ int vub_latent_bwd_f32(const float* logstd_nchw, const float* eps_nchw, const fl
  * (lib/utils.py:325-513: cv2.fillPoly for the body polygon, cv2.line with thickness 1 for the limbs, three uint8
  * planes) as called per frame by the rendering loop (data/data_conversions_3d.py:1154-1160).  Output: uint8 HWC
  * images [batch, height, width, 3] — exactly what vub_stem_fwd_u8 consumes.  Bit-exact with the reference function
- * (tests/golden/stickman.npz) inside the verified domain: frames whose body polygon has a vertex at x >= width get
- * unsupported[b] = 1 (the caller must not use them) instead of a guess.
+ * (tests/golden/stickman.npz) and with cv2 for joints anywhere inside or outside the image.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct vub_stickman_model {
   int32_t n_body, body[8];                 /* joint_model.body (polygon, > 2 joints to be drawn) */
@@ -415,8 +414,7 @@ typedef struct vub_stickman_model {
   int32_t head_chan[16], head_col[16];     /* line_colors[2][i] (the face loop indexes the same table from 0) */
 } vub_stickman_model;
 int vub_stickman_render(const double* joints_xy /* [batch][n_joints][2] */, int32_t batch, int32_t n_joints,
-                        const vub_stickman_model* model, int32_t height, int32_t width, uint8_t* out_hwc,
-                        int32_t* unsupported /* [batch] or NULL */, void* stream);
+                        const vub_stickman_model* model, int32_t height, int32_t width, uint8_t* out_hwc, void* stream);
 
 /*
  * Data-parallel gradient exchange (SURVEY.md 8b `allreduce_bucket(flat, ncclComm, stream)`): in-place all-reduce of

@@ -1,6 +1,6 @@
 """GPU (-m gpu): the batched stickman rasteriser (vub_stickman_render) — bit-exact with the outputs of the unmodified
 reference function (tests/golden/stickman.npz) and with the CPU oracle on random poses incl. missing joints and limbs
-leaving the image; frames outside the verified domain are reported, not guessed; joints -> frames end to end."""
+and bodies leaving the image on every side; joints -> frames end to end."""
 import contextlib
 import io
 
@@ -34,8 +34,6 @@ def test_rasterizer_matches_oracle_on_random_poses():
             lc = S.get_line_colors((5, 5, len(jm.head_lines)))
             joints = rng.normal(size / 2, size * 0.4, size=(48, 32, 2))     # many limbs leave the image
             joints[rng.random((48, 32)) < 0.1] = -3.0                        # missing joints
-            body = np.array(jm.body)
-            joints[:, body, 0] = np.minimum(joints[:, body, 0], size - 1)     # keep the body inside the verified domain
             joints[0, :, :] = -1.0                                            # a frame with nothing to draw
             r = B.StickmanRasterizer(jm, size, lc)
             got = r(torch.from_numpy(joints).cuda()).cpu().numpy()
@@ -43,19 +41,6 @@ def test_rasterizer_matches_oracle_on_random_poses():
                 want = S.make_joint_img([size, size, 3], joints[b], jm, line_colors=lc)
                 assert np.array_equal(got[b], want), (name, size, b)
             assert got[0].max() == 0
-
-
-def test_frames_outside_the_verified_domain_are_reported():
-    import bdvs_b200 as B
-    jm = MODELS["h36m_small"]
-    r = B.StickmanRasterizer(jm, 64)
-    joints = np.full((2, 32, 2), 20.0)
-    joints[:, jm.body, :] = [[10, 10], [40, 12], [38, 50], [12, 48]]
-    joints[1, jm.body[1], 0] = 70.0  # body vertex beyond the right border
-    with pytest.raises(NotImplementedError, match="verified"):
-        r(torch.from_numpy(joints).cuda())
-    r(torch.from_numpy(joints).cuda(), check=False)
-    assert r.unsupported.tolist() == [0, 1]
 
 
 def test_pose_renderer_equals_reference_pipeline():
@@ -72,7 +57,6 @@ def test_pose_renderer_equals_reference_pipeline():
     jm = MODELS["h36m_full"]
     rng = np.random.default_rng(11)
     joints = rng.normal(64, 22, size=(3, 32, 2))
-    joints[:, np.array(jm.body), 0] = np.clip(joints[:, np.array(jm.body), 0], 0, 127)
     app = torch.randint(0, 256, (3, 128, 128, 3), dtype=torch.uint8)
     torch.manual_seed(3)
     frames = B.PoseRenderer(m, jm)(app.cuda(), torch.from_numpy(joints).cuda())

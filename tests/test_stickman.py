@@ -54,8 +54,8 @@ def test_line_and_polygon_primitives_match_cv2():
         got = np.zeros((64, 64), np.uint8)
         S.draw_line(got, a, b, 200)
         assert np.array_equal(got, want), (a, b)
-    for _ in range(3000):  # polygons inside the verified domain: 0 <= x < width, any y, 3-5 vertices
-        pts = [(rnd.randint(0, 63), rnd.randint(-40, 110)) for _ in range(rnd.choice([3, 4, 5]))]
+    for _ in range(6000):  # polygons with 3-6 vertices anywhere up to 40 pixels outside the image
+        pts = [(rnd.randint(-40, 110), rnd.randint(-40, 110)) for _ in range(rnd.choice([3, 4, 5, 6]))]
         want = np.zeros((64, 64), np.uint8)
         cv2.fillPoly(want, np.array([pts], dtype=np.int32), 127)
         got = np.zeros((64, 64), np.uint8)
