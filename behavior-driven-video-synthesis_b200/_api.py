@@ -5,7 +5,7 @@ from .losses import compute_kl_with_prior, kl_loss
 from .modules import (Act, DepthToSpace, Downsample, IDAct, NormConv2d, SpaceToDepth, Upsample, VunetRNB,
                       WeightBank, bump_weight_epoch, to_act)
 from .optim import FusedAdam
-from .rendering import PoseRenderer, StickmanRasterizer, get_line_colors
+from .rendering import PoseRenderer, StickmanRasterizer, get_line_colors, project_poses
 from .training import GraphedTrainStep
 from .validation import fp32_validation
 from .vunets import DecDownAlter, DecUp, EncDownAlter, EncUp, VunetAlter
@@ -15,5 +15,5 @@ __all__ = [
     "NormConv2d", "VunetRNB", "Downsample", "Upsample", "DepthToSpace", "SpaceToDepth", "IDAct",
     "compute_kl_with_prior", "kl_loss", "Act", "to_act", "WeightBank", "build_native",
     "fp32_validation", "FusedAdam", "GraphedTrainStep", "bump_weight_epoch", "StickmanRasterizer", "PoseRenderer",
-    "get_line_colors",
+    "get_line_colors", "project_poses",
 ]

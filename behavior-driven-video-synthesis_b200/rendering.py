@@ -32,6 +32,23 @@ def get_line_colors(n_lines_per_channel: Sequence[int]):
     return line_colors
 
 
+def project_poses(poses3d: torch.Tensor, extrinsics: torch.Tensor, intrinsics, image_size, target_size: int) -> torch.Tensor:
+    """3-D joints ``[B, J, 3]`` -> 2-D joints ``[B, J, 2]`` in the pixel coordinates of a ``target_size`` stickman: the
+    per-frame prologue of the reference's rendering loop (``apply_affine_transform`` with the ``[R|t]`` extrinsics,
+    ``camera_projection`` with ``(f_x, x_0, f_y, y_0)``, rescaling by ``target_size / image_size``;
+    ``data/data_conversions_3d.py:588-605, 892-912, 1131-1132, 1150-1152``) for a whole batch, in float64 like the
+    numpy original.  Plain tensor algebra on a few kilobytes (plumbing, not a kernel of the path)."""
+    x = poses3d.to(torch.float64)
+    M = torch.as_tensor(extrinsics, dtype=torch.float64, device=x.device)
+    fx, x0, fy, y0 = (float(v) for v in intrinsics)
+    cam = torch.tensor([[fx, 0.0, x0], [0.0, fy, y0], [0.0, 0.0, 1.0]], dtype=torch.float64, device=x.device)
+    x_hom = torch.cat([x, torch.ones_like(x[..., :1])], dim=-1)
+    pose_c = x_hom @ M.T
+    pose_i = ((pose_c / pose_c[..., -1:]) @ cam.T)[..., :-1]
+    size = torch.as_tensor(image_size, dtype=torch.float64, device=x.device).reshape(-1, 1, 2)
+    return pose_i * (float(target_size) / size)
+
+
 class StickmanRasterizer:
     """``imgs = StickmanRasterizer(joint_model, size)(joints)`` == ``np.stack([make_joint_img([size, size, 3], j,
     joint_model, line_colors) for j in joints])`` of the reference, as a uint8 ``[B, size, size, 3]`` CUDA tensor.

@@ -77,3 +77,25 @@ def test_rasterizer_host_side_contract():
         B.StickmanRasterizer(jm, 256, scale_factor=64)  # thickness 4
     with pytest.raises(RuntimeError, match="no CPU path"):
         r(torch.zeros(1, 32, 2, dtype=torch.float64))
+
+
+def test_project_poses_matches_reference_formulas():
+    """data/data_conversions_3d.py:588-605 (apply_affine_transform), 892-912 (camera_projection), 1150-1152 (rescaling)
+    restated with numpy exactly as the reference writes them."""
+    import bdvs_b200 as B
+    import torch
+    rng = np.random.default_rng(3)
+    poses = rng.normal(size=(5, 17, 3)) + np.array([0.0, 0.0, 5.0])
+    M = np.concatenate([np.linalg.qr(rng.normal(size=(3, 3)))[0], rng.normal(size=(3, 1))], axis=1)
+    M[2, 3] += 6.0
+    intr = (1145.0, 512.5, 1143.8, 515.4)
+    sizes = np.array([[1000.0, 1002.0]] * 5)
+    want = []
+    for p, s in zip(poses, sizes):
+        x_hom = np.concatenate([p, np.ones((p.shape[0], 1), dtype=p.dtype)], axis=-1)
+        pose_c = x_hom @ M.T
+        cam = np.asarray([[intr[0], 0.0, intr[1]], [0.0, intr[2], intr[3]], [0.0, 0.0, 1.0]])
+        pose_i = ((pose_c / np.expand_dims(pose_c[..., -1], axis=-1)) @ cam.T)[..., :-1]
+        want.append(pose_i * (np.full((1, 2), 256, dtype=float) / np.expand_dims(s, axis=0)))
+    got = B.project_poses(torch.from_numpy(poses), torch.from_numpy(M), intr, torch.from_numpy(sizes), 256).numpy()
+    assert got.dtype == np.float64 and np.allclose(got, np.stack(want), rtol=1e-13, atol=1e-10)
