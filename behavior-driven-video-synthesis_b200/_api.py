@@ -1,17 +1,18 @@
 """Public names of the package (re-exported by ``bdvs_b200``)."""
 from . import _native
 from ._native import build as build_native
-from .losses import compute_kl_with_prior, kl_loss
+from .losses import compute_kl_loss, compute_kl_with_prior, kl_loss, latent_kl
 from .modules import (Act, DepthToSpace, Downsample, IDAct, NormConv2d, SpaceToDepth, Upsample, VunetRNB,
                       WeightBank, bump_weight_epoch, to_act)
 from .optim import FusedAdam
 from .rendering import PoseRenderer, StickmanRasterizer, get_line_colors, project_poses
 from .training import GraphedTrainStep
 from .validation import fp32_validation
-from .vunets import DecDownAlter, DecUp, EncDownAlter, EncUp, VunetAlter
+from .vunets import DecDown, DecDownAlter, DecUp, EncDown, EncDownAlter, EncUp, VunetAlter, VunetOrg
 
 __all__ = [
-    "VunetAlter", "EncUp", "EncDownAlter", "DecUp", "DecDownAlter",
+    "VunetAlter", "EncUp", "EncDownAlter", "DecUp", "DecDownAlter", "VunetOrg", "EncDown", "DecDown",
+    "latent_kl", "compute_kl_loss",
     "NormConv2d", "VunetRNB", "Downsample", "Upsample", "DepthToSpace", "SpaceToDepth", "IDAct",
     "compute_kl_with_prior", "kl_loss", "Act", "to_act", "WeightBank", "build_native",
     "fp32_validation", "FusedAdam", "GraphedTrainStep", "bump_weight_epoch", "StickmanRasterizer", "PoseRenderer",

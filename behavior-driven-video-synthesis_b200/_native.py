@@ -58,8 +58,11 @@ EXPORTED_SYMBOLS = (
     "vub_adam_wn_step_dev",
     "vub_stem_bwd",
     "vub_latent_bwd",
+    "vub_latent_sample",
+    "vub_space_to_depth",
+    "vub_latent_sample_bwd",
 )
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class ConvDesc(C.Structure):
@@ -376,6 +379,12 @@ def _declare(lib: C.CDLL) -> None:
     lib.vub_stem_bwd.argtypes = [fp, vp, i32, i32, i32, i32, i32, fp, fp, vp]
     lib.vub_latent_bwd.restype = C.c_int
     lib.vub_latent_bwd.argtypes = [fp, fp, fp, fp, fp, vp, i32, i32, i32, i32, vp, vp]
+    lib.vub_latent_sample.restype = C.c_int
+    lib.vub_latent_sample.argtypes = [fp, fp, i32, i32, i32, i32, i32, i32, i32, fp, fp, vp, vp, vp, i32, vp]
+    lib.vub_latent_sample_bwd.restype = C.c_int
+    lib.vub_latent_sample_bwd.argtypes = [fp, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]
+    lib.vub_space_to_depth.restype = C.c_int
+    lib.vub_space_to_depth.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp]
 
 
 def lib() -> C.CDLL:

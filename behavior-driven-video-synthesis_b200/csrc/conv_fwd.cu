@@ -46,6 +46,7 @@ struct ConvKParams {
   int stages;
   const uint8_t* w_tiled;  // tile-major pre-swizzled weights [K/64][w_rows][128 B], or nullptr (BKC == 64 only)
   int w_rows;
+  int ksplit;  // split-K instantiation: CTAs per cluster (= gridDim.z), each takes a contiguous range of the k-steps
 };
 
 // Epilogue for CH (16 or 32) consecutive channels of one pixel held in registers.
@@ -67,7 +68,20 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const uint32_
   epi_store<CH>(p, y, c_global, n, oh, ow);
 }
 
-template <int BN, int BKC>
+// fp32 partial accumulators of the non-leader CTAs of a split-K cluster, parked in the LEADER's shared memory behind
+// the epilogue staging tiles: [peer - 1][column][row] (a warp's 32 rows of one column = 128 contiguous bytes).
+template <int BN>
+struct SplitKPart {
+  static constexpr int GW = BN < 128 ? BN : 128;
+  static constexpr int OFF = BN >= 32 ? 4 * EpiStage<(GW < 32 ? 32 : GW)>::WARP_BYTES : 0;
+  static constexpr int PEER_BYTES = BN * kTileM * 4;
+};
+
+// SPLITK: the k-steps of one output tile are split over the CTAs of a thread-block cluster (cluster dims (1,1,ksplit)).
+// Every CTA accumulates its range in its own tensor memory; the peers then push their fp32 partials into the leader's
+// shared memory through DSMEM, and the leader adds them (in rank order: deterministic) before the usual epilogue.
+// For the smallest maps (<= 8x8), where a handful of CTAs would otherwise each stream an 18 .. 144-step K loop.
+template <int BN, int BKC, bool SPLITK>
 __global__ void __launch_bounds__(kConvThreads)
     conv_fwd_kernel(const __grid_constant__ ConvKParams p) {
   constexpr int ROWB = BKC * 2;
@@ -98,6 +112,13 @@ __global__ void __launch_bounds__(kConvThreads)
   const int w0 = twi * p.tw, h0 = thi * p.th, n0 = tni * p.tn;
   const int S = p.stages;
   const int KS = p.nsrc * p.ntaps * p.cblocks;
+  int ks_begin = 0, ks_end = KS;
+  uint32_t crank = 0;
+  if constexpr (SPLITK) {
+    crank = cluster_ctarank();
+    ks_begin = KS * static_cast<int>(crank) / p.ksplit;
+    ks_end = KS * (static_cast<int>(crank) + 1) / p.ksplit;
+  }
 
   // This kernel serves the small maps, where a launch is ~10 us of mostly latency and ~45 of them run back to
   // back: let the next kernel's CTAs start their prologue now, and do ours (barriers, TMEM, descriptor fetch)
@@ -134,39 +155,39 @@ __global__ void __launch_bounds__(kConvThreads)
   // with uniform-register descriptors instead of a per-lane "waterfall" loop around each one.
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    int ks = 0, st = 0;
+    int st = 0;
     uint32_t ph = 0;
-    for (int src = 0; src < p.nsrc; ++src) {
-      for (int tap = 0; tap < p.ntaps; ++tap) {
-        int dh = 0, dw = 0, mi = src;
-        if (p.ntaps == 9) {
-          const int r = tap / 3, s = tap - 3 * r;
-          if (p.stride == 1) {
-            dh = r - 1;
-            dw = s - 1;
-          } else {  // input row 2*oh + r - 1: parity (r != 1), coordinate oh - (r == 0)
-            mi = ((r != 1) ? 2 : 0) + ((s != 1) ? 1 : 0);
-            dh = (r == 0) ? -1 : 0;
-            dw = (s == 0) ? -1 : 0;
-          }
+    for (int ks = ks_begin; ks < ks_end; ++ks) {
+      const int cb = ks % p.cblocks;
+      const int st_ = ks / p.cblocks;
+      const int tap = st_ % p.ntaps;
+      const int src = st_ / p.ntaps;
+      int dh = 0, dw = 0, mi = src;
+      if (p.ntaps == 9) {
+        const int r = tap / 3, s = tap - 3 * r;
+        if (p.stride == 1) {
+          dh = r - 1;
+          dw = s - 1;
+        } else {  // input row 2*oh + r - 1: parity (r != 1), coordinate oh - (r == 0)
+          mi = ((r != 1) ? 2 : 0) + ((s != 1) ? 1 : 0);
+          dh = (r == 0) ? -1 : 0;
+          dw = (s == 0) ? -1 : 0;
         }
-        for (int cb = 0; cb < p.cblocks; ++cb, ++ks) {
-          mbar_wait(&empty_bar[st], ph ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(&full_bar[st], STAGE_BYTES);
-            uint8_t* a = smem + st * STAGE_BYTES;
-            tma_load_4d(a, &p.tmA[mi], &full_bar[st], cb * BKC, w0 + dw, h0 + dh, n0);
-            if (BKC == 64 && p.w_tiled != nullptr)  // one 1-D bulk copy instead of a BN-row tensor box
-              bulk_load_1d(a + A_BYTES, p.w_tiled + ((size_t)ks * p.w_rows + n_tile * BN) * 128, B_BYTES, &full_bar[st]);
-            else
-              tma_load_2d(a + A_BYTES, &p.tmB, &full_bar[st], ks * BKC, n_tile * BN);
-          }
-          __syncwarp();
-          if (++st == S) {
-            st = 0;
-            ph ^= 1;
-          }
-        }
+      }
+      mbar_wait(&empty_bar[st], ph ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&full_bar[st], STAGE_BYTES);
+        uint8_t* a = smem + st * STAGE_BYTES;
+        tma_load_4d(a, &p.tmA[mi], &full_bar[st], cb * BKC, w0 + dw, h0 + dh, n0);
+        if (BKC == 64 && p.w_tiled != nullptr)  // one 1-D bulk copy instead of a BN-row tensor box
+          bulk_load_1d(a + A_BYTES, p.w_tiled + ((size_t)ks * p.w_rows + n_tile * BN) * 128, B_BYTES, &full_bar[st]);
+        else
+          tma_load_2d(a + A_BYTES, &p.tmB, &full_bar[st], ks * BKC, n_tile * BN);
+      }
+      __syncwarp();
+      if (++st == S) {
+        st = 0;
+        ph ^= 1;
       }
     }
   } else if (warp == 1) {
@@ -176,7 +197,7 @@ __global__ void __launch_bounds__(kConvThreads)
     const uint32_t smem_lo = umma_desc_lo(smem_u32(smem));
     int st = 0;
     uint32_t ph = 0;
-    for (int ks = 0; ks < KS; ++ks) {
+    for (int ks = ks_begin; ks < ks_end; ++ks) {
       mbar_wait(&full_bar[st], ph);
       tc_fence_after();
       const uint32_t a_lo = smem_lo + st * (STAGE_BYTES >> 4);
@@ -185,9 +206,9 @@ __global__ void __launch_bounds__(kConvThreads)
 #pragma unroll
         for (int j = 0; j < BKC / 16; ++j)
           umma_bf16(tmem_base, umma_desc_join(desc_hi, a_lo + 2 * j), umma_desc_join(desc_hi, b_lo + 2 * j),
-                    idesc, (ks | j) != 0 ? 1u : 0u);
+                    idesc, (ks != ks_begin || j != 0) ? 1u : 0u);
         umma_commit(&empty_bar[st]);
-        if (ks == KS - 1) umma_commit(&tmem_full_bar);
+        if (ks == ks_end - 1) umma_commit(&tmem_full_bar);
       }
       __syncwarp();
       if (++st == S) {
@@ -196,6 +217,44 @@ __global__ void __launch_bounds__(kConvThreads)
       }
     }
   } else {
+    mbar_wait(&tmem_full_bar, 0);  // epilogue warps: this CTA's accumulator is complete
+    tc_fence_after();
+  }
+
+  if constexpr (SPLITK) {
+    // #1: every CTA of the cluster has its accumulator (its epilogue warps arrive only after the wait above), so the
+    // leader's pipeline stages are idle and may receive the peers' partials.
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    if (crank != 0 && warp >= 2) {
+      const int q = warp & 3;
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t dst = mapa_u32(smem_u32(smem) + SplitKPart<BN>::OFF + (crank - 1) * SplitKPart<BN>::PEER_BYTES +
+                                        (q * 32 + lane) * 4, 0);
+      if constexpr (BN >= 32) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t acc[32];
+          tmem_ld32(trow + c0, acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) st_cluster_u32(dst + (c0 + i) * (kTileM * 4), acc[i]);
+        }
+      } else {
+        uint32_t acc[16];
+        tmem_ld16(trow, acc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) st_cluster_u32(dst + i * (kTileM * 4), acc[i]);
+      }
+    }
+    tc_fence_before();
+    cluster_sync_all();  // #2: the partials are visible in the leader's shared memory
+    tc_fence_after();
+  }
+
+  if (warp >= 2 && (!SPLITK || crank == 0)) {
     // ------------------------------ epilogue -----------------------------------
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int m = q * 32 + lane;
@@ -204,9 +263,20 @@ __global__ void __launch_bounds__(kConvThreads)
     const int dn = m >> (p.tw_log2 + p.th_log2);
     const int n = n0 + dn, oh = h0 + dh, ow = w0 + dw;
     const bool valid = n < p.batch;
-    mbar_wait(&tmem_full_bar, 0);
-    tc_fence_after();
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    // split-K leader: add the peers' partials of columns [c0, c0 + CH) of this thread's row, in rank order
+    auto add_partials = [&](auto& acc, int c0) {
+      if constexpr (SPLITK) {
+        const uint32_t src = smem_u32(smem) + SplitKPart<BN>::OFF + (q * 32 + lane) * 4 + c0 * (kTileM * 4);
+        constexpr int CH = sizeof(acc) / sizeof(uint32_t);
+        for (int r = 1; r < p.ksplit; ++r) {
+#pragma unroll
+          for (int i = 0; i < CH; ++i)
+            acc[i] = __float_as_uint(__uint_as_float(acc[i]) +
+                                     lds_f32(src + (r - 1) * SplitKPart<BN>::PEER_BYTES + i * (kTileM * 4)));
+        }
+      }
+    };
     if constexpr (BN >= 32) {
       const bool bf16_out = (p.ep.flags & (VUB_CONV_F32_NHWC | VUB_CONV_F32_NCHW)) == 0;
       if (bf16_out) {
@@ -229,6 +299,7 @@ __global__ void __launch_bounds__(kConvThreads)
             uint32_t acc[32];
             tmem_ld32(trow + c0, acc);
             tmem_ld_wait();
+            add_partials(acc, c0);
             float y[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) y[i] = fmaf(__uint_as_float(acc[i]), s_scale[c0 + i], s_shift[c0 + i]);
@@ -256,6 +327,7 @@ __global__ void __launch_bounds__(kConvThreads)
           uint32_t acc[32];
           tmem_ld32(trow + c0, acc);
           tmem_ld_wait();
+          add_partials(acc, c0);
           epilogue_chunk<32>(p.ep, acc, s_scale, s_shift, c0, n_tile * BN + c0, valid, n, oh, ow);
         }
       }
@@ -263,6 +335,7 @@ __global__ void __launch_bounds__(kConvThreads)
       uint32_t acc[16];
       tmem_ld16(trow, acc);
       tmem_ld_wait();
+      add_partials(acc, 0);
       epilogue_chunk<16>(p.ep, acc, s_scale, s_shift, 0, n_tile * BN, valid, n, oh, ow);
     }
   }
@@ -275,13 +348,13 @@ __global__ void __launch_bounds__(kConvThreads)
 // ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
-template <int BN, int BKC>
-static int launch_conv(const ConvKParams& kp, dim3 grid, cudaStream_t stream) {
+template <int BN, int BKC, bool SPLITK>
+static int launch_conv_t(const ConvKParams& kp, dim3 grid, cudaStream_t stream) {
   constexpr int STAGE_BYTES = (kTileM + BN) * BKC * 2;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_fwd_kernel<BN, BKC>,
+    attr_err = cudaFuncSetAttribute(conv_fwd_kernel<BN, BKC, SPLITK>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   });
   if (attr_err != cudaSuccess)
@@ -293,8 +366,23 @@ static int launch_conv(const ConvKParams& kp, dim3 grid, cudaStream_t stream) {
   if constexpr (kStaging > 0) {
     if (smem < kStaging) smem = kStaging;  // the epilogue reuses the (then idle) pipeline stages
   }
+  if constexpr (SPLITK) {  // the leader's stages also receive the peers' partial accumulators
+    const size_t need = SplitKPart<BN>::OFF + (size_t)(kp.ksplit - 1) * SplitKPart<BN>::PEER_BYTES;
+    if (smem < need) smem = need;
+  }
   smem += 1024;
-  return launch_pdl(conv_fwd_kernel<BN, BKC>, grid, dim3(kConvThreads), smem, stream, kp, "conv_fwd");
+  if (smem > 200 * 1024) return fail(VUB_E_SHAPE, "conv_fwd<%d,%d>: %zu bytes of shared memory", BN, BKC, smem);
+  return launch_pdl(conv_fwd_kernel<BN, BKC, SPLITK>, grid, dim3(kConvThreads), smem, stream, kp,
+                    SPLITK ? "conv_fwd_splitk" : "conv_fwd", SPLITK ? kp.ksplit : 1);
+}
+
+template <int BN, int BKC>
+static int launch_conv(const ConvKParams& kp, dim3 grid, cudaStream_t stream) {
+  if (kp.ksplit > 1) {
+    if constexpr (BN <= 128) return launch_conv_t<BN, BKC, true>(kp, grid, stream);
+    return fail(VUB_E_SHAPE, "conv_fwd: split-K needs an N tile <= 128");
+  }
+  return launch_conv_t<BN, BKC, false>(kp, grid, stream);
 }
 
 bool conv_rows_applicable(const vub_conv_desc* d);            // conv_rows.cu
@@ -350,8 +438,13 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
   if (!d->x[0] || !d->w || !d->scale || !d->shift) return fail(VUB_E_NULL, "conv_fwd: x/w/scale/shift NULL");
   if (d->nsrc != 1 && d->nsrc != 2) return fail(VUB_E_SHAPE, "conv_fwd: nsrc must be 1 or 2");
   if (d->nsrc == 2 && !d->x[1]) return fail(VUB_E_NULL, "conv_fwd: x[1] NULL with nsrc == 2");
-  if (d->c_src != 32 && d->c_src != 64 && d->c_src != 128)
-    return fail(VUB_E_SHAPE, "conv_fwd: c_src %d not in {32,64,128}", d->c_src);
+  if (d->c_src != 32 && d->c_src != 64 && d->c_src != 128 && d->c_src != 256 && d->c_src != 512)
+    return fail(VUB_E_SHAPE, "conv_fwd: c_src %d not in {32,64,128,256,512}", d->c_src);
+  // 256 / 512 channels per source: the 4-group autoregressive prior of VunetOrg (models/vunets.py:655-676), which
+  // lives on the two smallest latent maps only -- served by the per-tap kernel (any number of channel blocks)
+  const bool wide = d->c_src > 128;
+  if (wide && (d->stride != 1 || (d->flags & VUB_CONV_D2S)))
+    return fail(VUB_E_SHAPE, "conv_fwd: c_src %d needs stride 1 and no D2S", d->c_src);
   if (d->ksize != 1 && d->ksize != 3) return fail(VUB_E_SHAPE, "conv_fwd: ksize must be 1 or 3");
   if (d->stride != 1 && d->stride != 2) return fail(VUB_E_SHAPE, "conv_fwd: stride must be 1 or 2");
   if (d->stride == 2 && (d->ksize != 3 || d->nsrc != 1))
@@ -384,13 +477,23 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
   for (const void* q : ptrs)
     if (q && !aligned16(q)) return fail(VUB_E_ALIGN, "conv_fwd: pointer %p not 16B aligned", q);
 
-  if (conv_rows_applicable(d)) return conv_rows_launch(d, static_cast<cudaStream_t>(stream_v));
+  // Split-K over a thread-block cluster (per-tap kernel, partials reduced through distributed shared memory) for the
+  // smallest maps.  Chosen from the LAYER geometry only -- never from the batch -- so that a frame's bits do not
+  // depend on the batch it is rendered in (the partial sums change the fp32 summation order).
+  int ksplit = 1;
+  {
+    const int ksteps_all = d->nsrc * d->ksize * d->ksize * (d->c_src / (d->c_src >= 64 ? 64 : 32));
+    if (hout * wout <= 64 && ksteps_all >= 12 && !(f & (VUB_CONV_ELU_IN0 | VUB_CONV_ELU_IN1)) && d->stages >= 0 &&
+        env_int("VUB_SPLITK", 1) != 0)
+      ksplit = ksteps_all < 27 ? (ksteps_all % 3 == 0 ? 3 : 2) : ksteps_all < 54 ? 4 : 8;
+  }
+  if (ksplit == 1 && !wide && conv_rows_applicable(d)) return conv_rows_launch(d, static_cast<cudaStream_t>(stream_v));
   if (f & (VUB_CONV_ELU_IN0 | VUB_CONV_ELU_IN1))
     return fail(VUB_E_FLAGS, "conv_fwd: ELU-on-load is only implemented by the row-streaming kernel "
                              "(see vub_conv_fwd_elu_in_ok) — store an ELU copy for this layer");
 
   // tensor-core-bound 3x3 layers at 64x64 / 32x32: activation-slab kernel (A and weight reuse in smem)
-  if (d->ksize == 3 && d->stride == 1 && d->stages >= 0 && !f32 && conv_slab_shape_ok(d->c_src, d->hin, d->win, cout, d->nsrc * 9 * d->c_src, ((long long)d->batch * d->hin * d->win + 127) / 128)) {
+  if (ksplit == 1 && !wide && d->ksize == 3 && d->stride == 1 && d->stages >= 0 && !f32 && conv_slab_shape_ok(d->c_src, d->hin, d->win, cout, d->nsrc * 9 * d->c_src, ((long long)d->batch * d->hin * d->win + 127) / 128)) {
     SlabJob job;
     memset(&job, 0, sizeof(job));
     job.x[0] = d->x[0];
@@ -432,7 +535,7 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
   const bool small_grid = px_tiles * (cout > 256 ? cout / 256 : 1) < sm_count();
   // With the contiguous-tile epilogue (tile_epilogue_contig) the persistent kernel also wins the stride-1 N <= 128
   // layers (128->128 @64^2, B=64: 0.091 ms vs 0.136 ms per-tap), so everything with a full grid goes there.
-  const bool want_tiles = force ? force[0] == '1' : !small_grid;
+  const bool want_tiles = ksplit == 1 && !wide && (force ? force[0] == '1' : !small_grid);
   if (want_tiles && d->stages >= 0) {
     // persistent tile kernel, k-step table = (source, tap, channel block)
     TileJob job;
@@ -509,7 +612,10 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
     // K loop at the per-SM TMA rate.  Split N over more CTAs (each re-reads the A boxes, 4x smaller weight tiles)
     // until the grid covers about two thirds of the chip.
     const long long pix_tiles = ((long long)d->batch * hout * wout + kTileM - 1) / kTileM;
-    while (bn > 32 && pix_tiles * (cout / bn) < 96) bn >>= 1;
+    while (bn > 32 && pix_tiles * (cout / bn) * ksplit < 96) bn >>= 1;
+    // split-K: (ksplit - 1) partial tiles of 128 x bn fp32 must fit the leader's shared memory beside the staging
+    // tiles (3 -> bn <= 128, 4 -> 64, 8 -> 32; a smaller N tile changes no bits)
+    while (ksplit > 1 && bn > 16 && (ksplit - 1) * bn > 320) bn >>= 1;
   }
 
   ConvKParams kp;
@@ -541,12 +647,15 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
   kp.w_rows = cout;
   const int tiles_n = (d->batch + kp.tn - 1) / kp.tn;
   const int ksteps = kp.nsrc * kp.ntaps * kp.cblocks;
-  kp.stages = d->stages > 0 ? d->stages : default_stages(bn, bkc, ksteps);  // stages < 0: force this kernel
-  if (d->stages <= 0 && (long long)kp.tiles_w * kp.tiles_h * tiles_n * (cout / bn) <= sm_count()) {
+  kp.ksplit = ksplit;
+  const int ksteps_cta = (ksteps + ksplit - 1) / ksplit;  // the longest range of a split-K cluster
+  kp.stages = d->stages > 0 ? d->stages : default_stages(bn, bkc, ksteps_cta);  // stages < 0: force this kernel
+  if (kp.stages > ksteps_cta) kp.stages = ksteps_cta;
+  if (d->stages <= 0 && (long long)kp.tiles_w * kp.tiles_h * tiles_n * (cout / bn) * ksplit <= sm_count()) {
     // at most one CTA per SM: nothing to share the shared memory with, and with two stages only 40 KB are in
     // flight per L2/HBM round trip -> take the whole budget (the small-map layers are latency bound)
     const int deep = 190 * 1024 / ((kTileM + bn) * bkc * 2);
-    kp.stages = deep < ksteps ? deep : ksteps;
+    kp.stages = deep < ksteps_cta ? deep : ksteps_cta;
   }
   if (kp.stages > kMaxStages) kp.stages = kMaxStages;
   if ((size_t)kp.stages * (kTileM + bn) * bkc * 2 + 1024 > 200 * 1024)
@@ -583,7 +692,7 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
     if (rc) return rc;
   }
 
-  dim3 grid(kp.tiles_w * kp.tiles_h * tiles_n, cout / bn);
+  dim3 grid(kp.tiles_w * kp.tiles_h * tiles_n, cout / bn, ksplit);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
 #define VUB_DISPATCH(BN_, BKC_) \
   if (bn == BN_ && bkc == BKC_) return launch_conv<BN_, BKC_>(kp, grid, stream);

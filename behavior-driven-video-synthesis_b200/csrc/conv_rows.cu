@@ -974,10 +974,6 @@ static int launch_rows(const RowsKParams& kp, int grid, size_t smem, cudaStream_
   return launch_rows_t<BN, BKC, 1, 2>(kp, grid, smem, stream);
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
 
 static size_t rows_staging_bytes(int bn) {
   return (bn >= 32 && bn <= 64) ? (size_t)8 * 2 * 32 * (bn * 2) : 0;

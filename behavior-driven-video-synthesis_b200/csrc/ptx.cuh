@@ -309,6 +309,15 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// distributed shared memory: plain 32-bit store to a shared::cluster address (mapa_u32), 32-bit load from own smem
+__device__ __forceinline__ void st_cluster_u32(uint32_t cluster_addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;\n" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
 // (default .release.cta semantics: the .release.cluster form compiles to MEMBAR.ALL.GPU, which waits for the
 // issuing thread's outstanding TMA loads / global stores and serialised the pair kernel's producer -- ncu, round 1)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {

@@ -21,18 +21,19 @@ from torch import nn
 from . import _native as N
 from . import ops
 
-_SUPPORTED_C = (32, 64, 128)
+_SUPPORTED_C = (32, 64, 128, 256, 512)  # 256 / 512: the 4-group prior of VunetOrg (smallest maps, stride 1)
 
 
 class Act:
     """One activation of the path, NHWC bf16: ``raw`` = as produced, ``elu`` = ELU(raw)."""
 
-    __slots__ = ("raw", "elu", "grad")
+    __slots__ = ("raw", "elu", "grad", "grad_view")
 
     def __init__(self, raw: Optional[torch.Tensor], elu: Optional[torch.Tensor]):
         self.raw = raw
         self.elu = elu
         self.grad = None  # training: NHWC bf16 gradient w.r.t. the raw value, accumulated by the backward schedule
+        self.grad_view = None  # training: storage the gradient must be created in (a slice of a stacked buffer)
 
     def pick(self, mode: str) -> torch.Tensor:
         """The copy a consumer reads: ``"raw"`` or ``"elu"``."""

@@ -66,6 +66,12 @@ _LIB.define("adam_wn_step_dev(Tensor table, int n_entries, int total_rows, float
 _LIB.define("stem_bwd(Tensor x, Tensor dy, Tensor(a!) gt, Tensor(b!) dy_sum) -> ()")
 _LIB.define("latent_bwd(Tensor logstd, Tensor? eps, Tensor? d_mu, Tensor? d_ls, Tensor? dz) -> Tensor")
 _LIB.define("nchw_to_nhwc_pad(Tensor x, int c_pad) -> Tensor")
+# ---- VunetOrg family: latent_sample + 4-group prior bookkeeping -----------------------------------
+_LIB.define("latent_sample(Tensor p, Tensor? eps, int sub, int gi, int gj, Tensor(a!)? mean, Tensor(b!)? z, "
+            "Tensor(c!)? z_raw, Tensor(d!)? z_elu, bool want_grp_elu) -> Tensor[]")
+_LIB.define("latent_sample_bwd(Tensor? d_mean, Tensor? dz, int sub, int gi, int gj, int h, int w, bool f32) -> Tensor")
+_LIB.define("space_to_depth(Tensor x, bool group_major, bool inverse, bool want_copy, bool want_elu, "
+            "Tensor(a!)? accumulate_into=None) -> Tensor[]")
 
 F32_NONE, F32_NHWC, F32_NCHW, U8_HWC = 0, 1, 2, 3
 
@@ -547,6 +553,103 @@ def _frames_to_uint8_cuda(imgs):
     return out
 
 
+def _latent_sample_cuda(p, eps, sub, gi, gj, mean, z, z_raw, z_elu, want_grp_elu) -> List[torch.Tensor]:
+    """``vub_latent_sample``: z = p + eps for one parameter map (the whole latent, sub = 1, or prior group (gi, gj),
+    sub = 2), written straight to its positions in the merged tensors the caller passes (see include/vunet_b200.h)."""
+    if p.dtype != torch.float32 or p.dim() != 4 or not p.is_contiguous():
+        raise ValueError("latent_sample: p must be contiguous fp32 NHWC [B,h,w,C]")
+    B, h, w, c = p.shape
+    if eps is not None and (eps.dtype != torch.float32 or tuple(eps.shape) != (B, c, h, w) or not eps.is_contiguous()):
+        raise ValueError("latent_sample: eps must be contiguous fp32 NCHW [B,C,h,w]")
+    H, W = h * sub, w * sub
+    for t, name in ((mean, "mean"), (z, "z")):
+        if t is not None and (t.dtype != torch.float32 or tuple(t.shape) != (B, c, H, W) or not t.is_contiguous()):
+            raise ValueError(f"latent_sample: {name} must be contiguous fp32 NCHW [B,C,{H},{W}]")
+    act_dtype = None
+    for t, name in ((z_raw, "z_raw"), (z_elu, "z_elu")):
+        if t is not None:
+            if t.dtype not in (torch.bfloat16, torch.float32) or tuple(t.shape) != (B, H, W, c) or not t.is_contiguous():
+                raise ValueError(f"latent_sample: {name} must be contiguous NHWC [B,{H},{W},C] bf16 / fp32")
+            if act_dtype is not None and t.dtype != act_dtype:
+                raise ValueError("latent_sample: activation outputs must share one dtype")
+            act_dtype = t.dtype
+    if act_dtype is None:
+        act_dtype = torch.bfloat16
+    grp = torch.empty((B, h, w, c), dtype=act_dtype, device=p.device) if want_grp_elu else None
+    n = p.numel()
+    asz = 4 if act_dtype == torch.float32 else 2
+    nbytes = float(n * 4 * (1 + (eps is not None) + (mean is not None) + (z is not None))
+                   + n * asz * ((z_raw is not None) + (z_elu is not None) + want_grp_elu))
+    N.check(_launch("latent_sample", N.lib().vub_latent_sample, p.data_ptr(), _p(eps), B, c, h, w, sub, gi, gj, _p(mean),
+                    _p(z), _p(z_raw), _p(z_elu), _p(grp), 1 if act_dtype == torch.float32 else 0, _stream(),
+                    bytes_=nbytes), "vub_latent_sample")
+    return [grp] if grp is not None else []
+
+
+def _latent_sample_bwd_cuda(d_mean, dz, sub, gi, gj, h, w, f32) -> torch.Tensor:
+    """``vub_latent_sample_bwd``: gradient of the parameter map [B,h,w,C] from the merged d_mean (NCHW fp32) / dz (NHWC)."""
+    if d_mean is None and dz is None:
+        raise ValueError("latent_sample_bwd: no gradient given")
+    act = torch.float32 if f32 else torch.bfloat16
+    if d_mean is not None:
+        if d_mean.dtype != torch.float32 or d_mean.dim() != 4 or d_mean.shape[2] != h * sub or d_mean.shape[3] != w * sub:
+            raise ValueError("latent_sample_bwd: d_mean must be fp32 NCHW [B,C,h*sub,w*sub]")
+        d_mean = d_mean.contiguous()
+        B, c = d_mean.shape[0], d_mean.shape[1]
+    if dz is not None:
+        if dz.dtype != act or dz.dim() != 4 or dz.shape[1] != h * sub or dz.shape[2] != w * sub or not dz.is_contiguous():
+            raise ValueError("latent_sample_bwd: dz must be a contiguous NHWC activation gradient [B,h*sub,w*sub,C]")
+        B, c = dz.shape[0], dz.shape[3]
+    ref = d_mean if d_mean is not None else dz
+    out = torch.empty((B, h, w, c), dtype=act, device=ref.device)
+    N.check(_launch("latent_sample_bwd", N.lib().vub_latent_sample_bwd, _p(d_mean), _p(dz), B, c, h, w, sub, gi, gj,
+                    out.data_ptr(), int(f32), _stream(), bytes_=float(out.numel() * (8 + 2 * out.element_size()))),
+            "vub_latent_sample_bwd")
+    return out
+
+
+def _space_to_depth_cuda(x, group_major, inverse, want_copy, want_elu, accumulate_into=None) -> List[torch.Tensor]:
+    """``vub_space_to_depth`` on an NHWC activation (bf16, or fp32 in validation mode).  ``accumulate_into``: add the
+    regrouped values to this existing tensor instead of returning a copy (gradient accumulation)."""
+    if x.dtype not in (torch.bfloat16, torch.float32) or not x.is_contiguous():
+        raise ValueError("space_to_depth: x must be a contiguous bf16 / fp32 activation")
+    if inverse:  # x is the grouped tensor
+        if group_major:
+            if x.dim() != 5 or x.shape[0] != 4:
+                raise ValueError("space_to_depth: inverse group-major input must be [4,B,h/2,w/2,C]")
+            _, B, h2, w2, c = x.shape
+        else:
+            if x.dim() != 4 or x.shape[3] % 4:
+                raise ValueError("space_to_depth: inverse input must be [B,h/2,w/2,4C]")
+            B, h2, w2, c4 = x.shape
+            c = c4 // 4
+        h, w = 2 * h2, 2 * w2
+        oshape = (B, h, w, c)
+    else:
+        if x.dim() != 4 or x.shape[1] % 2 or x.shape[2] % 2:
+            raise ValueError("space_to_depth: x must be NHWC [B,h,w,C] with even h, w")
+        B, h, w, c = x.shape
+        oshape = (4, B, h // 2, w // 2, c) if group_major else (B, h // 2, w // 2, 4 * c)
+    if accumulate_into is not None:
+        if want_elu or accumulate_into.dtype != x.dtype or tuple(accumulate_into.shape) != oshape \
+                or not accumulate_into.is_contiguous():
+            raise ValueError("space_to_depth: accumulate_into must match the output (and excludes want_elu)")
+        copy = accumulate_into
+    else:
+        copy = torch.empty(oshape, dtype=x.dtype, device=x.device) if want_copy else None
+    elu = torch.empty(oshape, dtype=x.dtype, device=x.device) if want_elu else None
+    nbytes = float(x.numel() * x.element_size() * (1 + (copy is not None) + want_elu + (accumulate_into is not None)))
+    N.check(_launch("space_to_depth", N.lib().vub_space_to_depth, x.data_ptr(), B, h, w, c, int(group_major), int(inverse),
+                    int(accumulate_into is not None), _p(copy), _p(elu), 1 if x.dtype == torch.float32 else 0, _stream(),
+                    bytes_=nbytes), "vub_space_to_depth")
+    if accumulate_into is not None:
+        return []
+    return [t for t in (copy, elu) if t is not None]
+
+
+_LIB.impl("latent_sample", _latent_sample_cuda, "CUDA")
+_LIB.impl("space_to_depth", _space_to_depth_cuda, "CUDA")
+_LIB.impl("latent_sample_bwd", _latent_sample_bwd_cuda, "CUDA")
 _LIB.impl("conv_fwd", _conv_fwd_cuda, "CUDA")
 _LIB.impl("frames_to_uint8", _frames_to_uint8_cuda, "CUDA")
 _LIB.impl("conv_fwd32", _conv_fwd32_cuda, "CUDA")
@@ -612,7 +715,9 @@ for _name, _fn in (("conv_fwd", _conv_fwd_cuda), ("frames_to_uint8", _frames_to_
                    ("adam_wn_step_dev", _adam_wn_step_dev_cuda), ("stem_bwd", _stem_bwd_cuda),
                    ("latent_bwd", _latent_bwd_cuda), ("nchw_to_nhwc_pad", _nchw_to_nhwc_pad_cuda),
                    ("wn_prep", _wn_prep_cuda), ("stem_fwd", _stem_fwd_cuda), ("latent_fwd", _latent_fwd_cuda),
-                   ("nchw_to_nhwc", _nchw_to_nhwc_cuda), ("nhwc_to_nchw", _nhwc_to_nchw_cuda)):
+                   ("nchw_to_nhwc", _nchw_to_nhwc_cuda), ("nhwc_to_nchw", _nhwc_to_nchw_cuda),
+                   ("latent_sample", _latent_sample_cuda), ("space_to_depth", _space_to_depth_cuda),
+                   ("latent_sample_bwd", _latent_sample_bwd_cuda)):
     _ops.register(_name, _fn)
 
 
@@ -770,3 +875,27 @@ def latent_bwd(logstd, eps, d_mu, d_ls, dz) -> torch.Tensor:
 
 def nchw_to_nhwc_pad(x, c_pad: int) -> torch.Tensor:
     return _ops.nchw_to_nhwc_pad(x, c_pad)
+
+
+# ---- VunetOrg family ------------------------------------------------------------------------------
+def latent_sample(p, eps, *, sub: int = 1, group=(0, 0), mean=None, z=None, z_raw=None, z_elu=None,
+                  want_grp_elu: bool = False):
+    """``latent_sample`` (models/vunets.py:151-156) on the fp32 NHWC parameter map ``p``; results are written into the
+    (merged) tensors passed in.  Returns the compact ELU(z) of this map when ``want_grp_elu``."""
+    outs = _ops.latent_sample(p, eps, sub, group[0], group[1], mean, z, z_raw, z_elu, want_grp_elu)
+    return outs[0] if want_grp_elu else None
+
+
+def latent_sample_bwd(d_mean, dz, *, sub: int, group, h: int, w: int, f32: bool) -> torch.Tensor:
+    return _ops.latent_sample_bwd(d_mean, dz, sub, group[0], group[1], h, w, f32)
+
+
+def space_to_depth(x, *, group_major: bool = False, inverse: bool = False, want_copy: bool = True,
+                   want_elu: bool = False, accumulate_into=None):
+    """SpaceToDepth(2) / its inverse on an NHWC activation: returns (copy or None, elu or None); with
+    ``accumulate_into`` the regrouped values are added to that tensor and (None, None) is returned."""
+    outs = _ops.space_to_depth(x, group_major, inverse, want_copy, want_elu, accumulate_into)
+    if accumulate_into is not None:
+        return None, None
+    it = iter(outs)
+    return (next(it) if want_copy else None), (next(it) if want_elu else None)

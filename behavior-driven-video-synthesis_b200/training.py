@@ -47,6 +47,7 @@ class Tape:
         self.recs: List[tuple] = []
         self.img_slot: Optional[GradSlot] = None
         self.latents: List[dict] = []
+        self.samples: List[dict] = []   # VunetOrg: latent_sample records (posterior means first, then prior groups)
 
     def conv(self, conv: NormConv2d, srcs, residual: Optional[Act], out: Optional[Act], d2s: bool):
         slot = out if out is not None else GradSlot()
@@ -55,6 +56,24 @@ class Tape:
 
     def stem(self, conv: NormConv2d, x: torch.Tensor, out: Act):
         self.recs.append(("stem", conv, x.contiguous(), out))
+
+    # ---- VunetOrg family -------------------------------------------------------------------------------
+    def sample(self, owner: str, slot: GradSlot, mean: torch.Tensor, z_act: Optional[Act], sub: int, group) -> None:
+        """``latent_sample`` of the parameter conv whose output gradient is ``slot``: ``mean`` is the (merged) NCHW
+        tensor the module returns, ``z_act`` the (merged) activation of the sample, or None when nothing reads it."""
+        rec = {"owner": owner, "slot": slot, "mean": mean, "z_act": z_act, "sub": sub, "group": tuple(group)}
+        self.samples.append(rec)
+        self.recs.append(("sample", rec))
+
+    def regroup(self, owner: str, src: Act, dsts: List[Act], group_major: bool) -> None:
+        """SpaceToDepth of ``src``: ``dsts`` = [the 4C-channel activation] or, group-major, the four group
+        activations, whose gradients are then created inside ONE stacked buffer (unread groups stay zero)."""
+        buf = None
+        if group_major:
+            buf = torch.zeros((4,) + tuple(dsts[0].any.shape), dtype=dsts[0].any.dtype, device=dsts[0].any.device)
+            for g, d in enumerate(dsts):
+                d.grad_view = buf[g]
+        self.recs.append(("regroup", owner, src, list(dsts), group_major, buf))
 
     def latent(self, ml_slot: GradSlot, res: dict, eps: torch.Tensor):
         rec = {"ml_slot": ml_slot, "logstd": res["logstd"], "eps": eps, "z_act": res["z_act"], "d_mu": None,
@@ -268,7 +287,14 @@ def run_backward(model, bank: WeightBank, tape: Tape, d_imgs: Optional[torch.Ten
     current = None
     for rec in reversed(tape.recs):
         kind = rec[0]
-        owner = rec[1]._vub_owner if kind != "latent" else "ed"
+        if kind == "latent":
+            owner = "ed"
+        elif kind == "sample":
+            owner = rec[1]["owner"]
+        elif kind == "regroup":
+            owner = rec[1]
+        else:
+            owner = rec[1]._vub_owner
         if owner != current:
             if current is not None:
                 join_wgrads()
@@ -303,7 +329,7 @@ def run_backward(model, bank: WeightBank, tape: Tape, d_imgs: Optional[torch.Ten
             for a, m in srcs:
                 existed = a.grad is not None
                 if not existed:
-                    a.grad = torch.empty_like(a.pick(m))
+                    a.grad = a.grad_view if a.grad_view is not None else torch.empty_like(a.pick(m))
                 dx.append(a.grad)
                 mask.append(a.elu if m == "elu" else None)
                 a1 = a.grad if existed else None
@@ -324,6 +350,33 @@ def run_backward(model, bank: WeightBank, tape: Tape, d_imgs: Optional[torch.Ten
             if out.grad is not None:
                 ops.stem_bwd(x, out.grad, gb.gt[id(conv)][0], gb.dy_sum[id(conv)][0])
                 out.grad = None
+        elif kind == "sample":
+            r = rec[1]
+            dz = None if r["z_act"] is None else r["z_act"].grad
+            d_mean = r.get("d_mean")
+            if dz is None and d_mean is None:
+                continue
+            sub = r["sub"]
+            hh, ww = r["mean"].shape[2] // sub, r["mean"].shape[3] // sub
+            r["slot"].grad = ops.latent_sample_bwd(d_mean, dz, sub=sub, group=r["group"], h=hh, w=ww, f32=fp32)
+            if r["z_act"] is not None:
+                r["z_act"].grad = None
+        elif kind == "regroup":
+            _, _, src, dsts, group_major, buf = rec
+            if group_major:
+                if not any(d.grad is not None for d in dsts):
+                    continue
+                g = buf  # the groups' gradients live in its four slices (groups nobody read stay zero)
+            else:
+                g = dsts[0].grad
+                if g is None:
+                    continue
+            if src.grad is None:
+                src.grad = ops.space_to_depth(g, group_major=group_major, inverse=True)[0]
+            else:
+                ops.space_to_depth(g, group_major=group_major, inverse=True, accumulate_into=src.grad)
+            for d in dsts:
+                d.grad = None
         else:
             r = rec[1]
             dz = r["z_act"].grad
@@ -375,6 +428,63 @@ class _VunetTrainFn(torch.autograd.Function):
                      reducer=getattr(ctx.model, "_vub_reducer", None))
         ctx.tape = None  # activations and gradient buffers are released here
         return None, None, None, None, None
+
+
+class _VunetOrgTrainFn(torch.autograd.Function):
+    """The whole VunetOrg forward as ONE autograd node: outputs (imgs, *qs, *ps, *hs, *gs); gradients flow from
+    ``imgs``, the posterior means ``qs`` and the prior means ``ps`` (lib/losses.py:55-65 compares the two)."""
+
+    @staticmethod
+    def forward(ctx, model, x, c, eps, eps_groups, anchor):
+        bank: WeightBank = model._bank(with_wd=True)
+        tape = Tape()
+        bank.tape = tape
+        try:
+            imgs, lat, ps, hs_left, gs = model._forward_impl(bank, x, c, eps, eps_groups)
+        finally:
+            bank.tape = None
+        ctx.model, ctx.bank, ctx.tape = model, bank, tape
+        ctx.set_materialize_grads(False)
+        qs = [r["q"] for r in lat]
+        hs = [h.nchw() for h in hs_left]
+        gsn = [g.nchw() for g in gs]
+        ctx.mark_non_differentiable(*hs, *gsn)
+        ctx.n_lat, ctx.n_hs = len(lat), len(hs)
+        return (imgs, *qs, *ps, *hs, *gsn)
+
+    @staticmethod
+    def backward(ctx, d_imgs, *rest):
+        tape: Tape = ctx.tape
+        if tape is None:
+            raise RuntimeError("vunet_b200: backward through the same forward pass twice is not supported")
+        n = ctx.n_lat
+        # tape.samples: the n posterior-mean records of `ed`, then four prior-group records per latent scale of `dd`
+        for i in range(n):
+            d_q, d_p = rest[i], rest[n + i]
+            tape.samples[i]["d_mean"] = None if d_q is None else d_q.float().contiguous()
+            d_p = None if d_p is None else d_p.float().contiguous()
+            for l in range(4):
+                tape.samples[n + 4 * i + l]["d_mean"] = d_p
+        run_backward(ctx.model, ctx.bank, tape, None if d_imgs is None else d_imgs.contiguous(),
+                     reducer=getattr(ctx.model, "_vub_reducer", None))
+        ctx.tape = None
+        return None, None, None, None, None, None
+
+
+def train_forward_org(model, x, c, eps, eps_groups):
+    """``VunetOrg.forward`` under autograd: returns (imgs, qs, ps, hs_left, gs)."""
+    if x.requires_grad or c.requires_grad:
+        raise NotImplementedError("vunet_b200: VunetOrg.forward is differentiable w.r.t. its parameters only; "
+                                  "gradients w.r.t. the inputs x / c are not produced (detach them)")
+    anchor = torch.zeros(1, device=x.device, requires_grad=True)  # fresh leaf per call, see train_forward
+    outs = _VunetOrgTrainFn.apply(model, x, c, None if eps is None else list(eps),
+                                  None if eps_groups is None else [list(g) for g in eps_groups], anchor)
+    n = model.ed.n_scales
+    n_hs = len(outs) - 1 - 2 * n - 2 * model.du.n_scales
+    imgs, qs, ps = outs[0], list(outs[1:1 + n]), list(outs[1 + n:1 + 2 * n])
+    hs = list(outs[1 + 2 * n:1 + 2 * n + n_hs])
+    gs = list(outs[1 + 2 * n + n_hs:])
+    return imgs, qs, ps, hs, gs
 
 
 def train_forward(model, x, c, eps: Optional[Sequence[torch.Tensor]]):

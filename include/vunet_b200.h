@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VUB_ABI_VERSION 4
+#define VUB_ABI_VERSION 5
 
 #define VUB_OK 0
 #define VUB_E_NULL (-1)        /* required pointer is NULL */
@@ -74,7 +74,8 @@ typedef struct vub_conv_desc {
   void* out_elu;         /* NHWC bf16 or NULL */
   void* out_f32;         /* fp32, layout per flags, or NULL */
   int32_t nsrc;          /* 1 or 2 */
-  int32_t c_src;         /* channels per source: 32, 64 or 128 */
+  int32_t c_src;         /* channels per source: 32, 64 or 128; 256 / 512 (VunetOrg's 4-group prior on the two smallest
+                            latent maps: models/vunets.py:655-676) with stride 1 and no D2S */
   int32_t batch, hin, win;
   int32_t cout;          /* GEMM N = rows of w (padded to 16/32/64/128/256/512) */
   int32_t cout_valid;    /* channels actually stored (== cout except for out_conv) */
@@ -415,6 +416,45 @@ typedef struct vub_stickman_model {
 } vub_stickman_model;
 int vub_stickman_render(const double* joints_xy /* [batch][n_joints][2] */, int32_t batch, int32_t n_joints,
                         const vub_stickman_model* model, int32_t height, int32_t width, uint8_t* out_hwc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * VunetOrg family: latent bookkeeping of `latent_sample` (models/vunets.py:151-156) and of the
+ * 4-group autoregressive prior in DecDown.forward (704-760) with its SpaceToDepth / DepthToSpace regrouping
+ * (lib/modules.py:11-34).  In NHWC, group (gi, gj) of SpaceToDepth(x) is the parity sub-grid x[:, gi::2, gj::2, :].
+ * ---------------------------------------------------------------------------------------------- */
+/*
+ * z = p + eps for the parameter map `p_nhwc` [batch, h, w, c] fp32 (the output of make_latent_params / auto_lp) and
+ * noise `eps_nchw` [batch, c, h, w] (NULL: z = p, the posterior mean fed by `transfer`).  sub == 1: the map is the
+ * whole latent; sub == 2: it is prior group (gi, gj) and every output marked "merged" is the (2h x 2w) map of
+ * `__merge_groups` (DepthToSpace of the concatenated groups), of which this call fills one parity sub-grid.
+ * Outputs, each optional: mean_nchw / z_nchw fp32 [batch, c, h*sub, w*sub] (merged; what the module returns),
+ * z_raw_nhwc / z_elu_nhwc [batch, h*sub, w*sub, c] (merged; the activations the next convs read), grp_elu_nhwc
+ * [batch, h, w, c] = ELU(z) of this map alone (the `feedback` of test_forward).  Activations are bf16, or fp32 when
+ * f32_acts != 0 (fp32 validation mode).
+ */
+int vub_latent_sample(const float* p_nhwc, const float* eps_nchw, int32_t batch, int32_t c, int32_t h, int32_t w,
+                      int32_t sub, int32_t gi, int32_t gj, float* mean_nchw, float* z_nchw, void* z_raw_nhwc,
+                      void* z_elu_nhwc, void* grp_elu_nhwc, int32_t f32_acts, void* stream);
+/*
+ * Backward of vub_latent_sample (what autograd does for `mean + eps`, torch.split / DepthToSpace in the reference):
+ * d_p_nhwc [batch, h, w, c] = d_mean_nchw (gradient of the returned, merged mean; NULL = none) + dz_nhwc (gradient of
+ * the merged NHWC activation z; NULL = none), both gathered from this map's parity positions (sub, gi, gj as above).
+ * d_p is what vub_conv_dgrad / vub_conv_wgrad of the parameter conv take as dy.
+ */
+int vub_latent_sample_bwd(const float* d_mean_nchw, const void* dz_nhwc, int32_t batch, int32_t c, int32_t h, int32_t w,
+                          int32_t sub, int32_t gi, int32_t gj, void* d_p_nhwc, int32_t f32_acts, void* stream);
+/*
+ * SpaceToDepth(2) of an NHWC activation `src` [batch, h, w, c] (lib/modules.py:11-21):
+ *   group_major == 0: dst [batch, h/2, w/2, 4c], channel (gi*2 + gj)*c + ch   (the reference's channel order)
+ *   group_major == 1: dst [4][batch, h/2, w/2, c]   (`__split_groups`: torch.split of the above, each group compact)
+ * dst_copy receives the values, dst_elu ELU(values); either may be NULL.  inverse != 0 runs the index map backwards
+ * (DepthToSpace, lib/modules.py:24-34: `src` is the grouped tensor, dst the [batch, h, w, c] one); accumulate != 0
+ * adds to dst_copy instead of overwriting it (training: the backward of a regrouping is the inverse regrouping of
+ * the gradient, summed with the tensor's other consumers' contributions).
+ */
+int vub_space_to_depth(const void* src, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t group_major,
+                       int32_t inverse, int32_t accumulate, void* dst_copy, void* dst_elu, int32_t f32_acts,
+                       void* stream);
 
 /*
  * Data-parallel gradient exchange (SURVEY.md 8b `allreduce_bucket(flat, ncclComm, stream)`): in-place all-reduce of

@@ -1,8 +1,9 @@
 """CPU oracle for the VUnet hot path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
 A functional fp32 restatement (plain torch CPU ops on a reference-layout ``state_dict``) of the
-algorithm in the reference's ``lib/modules.py:24-34,120-233`` and ``models/vunets.py:109-148,222-414,
-426-597`` plus the KL of ``lib/losses.py:68-78,283-291``.  Only ``tests/``,
+algorithm in the reference's ``lib/modules.py:11-34,120-233`` and ``models/vunets.py:109-148,222-414,
+426-597`` plus the KL of ``lib/losses.py:68-78,283-291`` — and of the ``VunetOrg`` family
+(``models/vunets.py:18-106,151-219,600-783``, ``lib/losses.py:26-65``).  Only ``tests/``,
 ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference`` legs may import
 it — and there only as the checker / the timed CPU baseline, never on the product path.
 
@@ -176,6 +177,120 @@ def kl_loss(mu: torch.Tensor, logstd: torch.Tensor) -> torch.Tensor:
 
 def compute_kl_with_prior(means, logstds) -> torch.Tensor:
     return torch.stack([kl_loss(m, l) for m, l in zip(means, logstds)]).mean()
+
+
+# --------------------------------------------------------------------------------------------------
+# VunetOrg family (models/vunets.py:18-106, 151-219, 600-783; lib/modules.py:11-21; lib/losses.py:26-65)
+# --------------------------------------------------------------------------------------------------
+def space_to_depth(x: torch.Tensor, bs: int = 2) -> torch.Tensor:
+    """SpaceToDepth — lib/modules.py:11-21: out[n,(i*bs+j)*C+c,h,w] = in[n,c,bs*h+i,bs*w+j] (inverse of
+    :func:`depth_to_space`)."""
+    return torch.cat([x[:, :, i::bs, j::bs] for i in range(bs) for j in range(bs)], dim=1)
+
+
+def enc_down(sd: SD, prefix: str, gs: List[torch.Tensor], eps: Sequence[torch.Tensor], n_latent_scales: int = 2):
+    """EncDown.forward — models/vunets.py:191-219.  Pops from ``gs`` like the reference; ``eps[i]`` replaces the
+    ``randn_like`` draw of ``latent_sample`` (151-156: z = q + 1.0 * eps) at scale i."""
+    hs, qs, zs = [], [], []
+    h = norm_conv(sd, prefix + ".nin", gs[-1])
+    for i in range(n_latent_scales):
+        h = rnb(sd, f"{prefix}.blocks.{2 * i}", h, gs.pop())
+        hs.append(h)
+        q = norm_conv(sd, f"{prefix}.make_latent_params.{i}", h)
+        qs.append(q)
+        z = q + eps[i]
+        zs.append(z)
+        h = rnb(sd, f"{prefix}.blocks.{2 * i + 1}", h, torch.cat([gs.pop(), z], dim=1))
+        hs.append(h)
+        h = upsample(sd, f"{prefix}.ups.{i}", h)
+    h = rnb(sd, prefix + ".fin_block", h, gs.pop())
+    hs.append(h)
+    return hs, qs, zs
+
+
+def dec_down(sd: SD, prefix: str, gs: Sequence[torch.Tensor], zs_posterior: Sequence[torch.Tensor], training: bool,
+             eps_groups: Sequence[Sequence[torch.Tensor]], n_latent_scales: int = 2):
+    """DecDown.forward — models/vunets.py:696-772: the decoder with the 4-group autoregressive prior.
+    ``eps_groups[i][l]`` replaces the ``randn_like`` draw of ``latent_sample(p_group)`` for group l of latent
+    scale i (drawn in BOTH modes: with ``training`` the sample is only returned, the posterior groups are fed back).
+    Returns (imgs, hs, ps, zs_prior)."""
+    gs = list(gs)
+    zs_posterior = list(zs_posterior)
+    n_scales = len(gs) // 2
+    hs, ps, zs = [], [], []
+    h = norm_conv(sd, prefix + ".nin", gs[-1])
+    for i in range(n_scales):
+        h = rnb(sd, f"{prefix}.blocks.{2 * i}", h, gs.pop())
+        hs.append(h)
+        if i < n_latent_scales:
+            scale = f"l_{i}"
+            if training:
+                cq = zs_posterior[0].shape[1]
+                post_groups = list(torch.split(space_to_depth(zs_posterior[0]), cq, dim=1))
+            p_groups, z_groups = [], []
+            p_features = space_to_depth(rnb(sd, f"{prefix}.auto_blocks.{scale}.0", h))
+            for l in range(4):
+                p_group = norm_conv(sd, f"{prefix}.auto_lp.{scale}.{l}", p_features)
+                p_groups.append(p_group)
+                z_group = p_group + eps_groups[i][l]
+                z_groups.append(z_group)
+                feedback = post_groups.pop(0) if training else z_group
+                if l + 1 < 4:
+                    p_features = rnb(sd, f"{prefix}.auto_blocks.{scale}.{l + 1}", p_features, feedback)
+            ps.append(depth_to_space(torch.cat(p_groups, dim=1)))
+            z_prior = depth_to_space(torch.cat(z_groups, dim=1))
+            zs.append(z_prior)
+            z = zs_posterior.pop(0) if training else z_prior
+            h = norm_conv(sd, f"{prefix}.latent_nins.{scale}", torch.cat([h, z], dim=1))
+        h = rnb(sd, f"{prefix}.blocks.{2 * i + 1}", h, gs.pop())
+        hs.append(h)
+        if i + 1 < n_scales:
+            h = upsample(sd, f"{prefix}.ups.{i}", h)
+    assert not gs
+    if training:
+        assert not zs_posterior
+    return norm_conv(sd, prefix + ".out_conv", hs[-1]), hs, ps, zs
+
+
+def org_forward(sd: SD, x, c, eps, eps_groups, n_latent_scales: int = 2):
+    """VunetOrg.forward — models/vunets.py:83-94: returns (imgs, qs, ps, zs_posterior, zs_prior, hs_left)."""
+    hs = enc_up(sd, "eu", x)
+    _, qs, zs_post = enc_down(sd, "ed", hs, eps, n_latent_scales)
+    gs = enc_up(sd, "du", c)
+    imgs, _, ps, zs_prior = dec_down(sd, "dd", gs, zs_post, True, eps_groups, n_latent_scales)
+    return imgs, qs, ps, zs_post, zs_prior, hs
+
+
+def org_transfer(sd: SD, x, c, eps, eps_groups, n_latent_scales: int = 2):
+    """VunetOrg.transfer — models/vunets.py:102-110: the decoder is fed the posterior MEANS."""
+    hs = enc_up(sd, "eu", x)
+    _, qs, _ = enc_down(sd, "ed", hs, eps, n_latent_scales)
+    gs = enc_up(sd, "du", c)
+    return dec_down(sd, "dd", gs, list(qs), True, eps_groups, n_latent_scales)[0]
+
+
+def org_test_forward(sd: SD, c, eps_groups, n_latent_scales: int = 2):
+    """VunetOrg.test_forward — models/vunets.py:96-100: appearance sampled group by group from the prior."""
+    gs = enc_up(sd, "du", c)
+    return dec_down(sd, "dd", gs, [], False, eps_groups, n_latent_scales)[0]
+
+
+def latent_kl(prior_mean: torch.Tensor, posterior_mean: torch.Tensor) -> torch.Tensor:
+    """lib/losses.py:26-37."""
+    return (0.5 * (prior_mean - posterior_mean) ** 2).sum(dim=[1, 2, 3]).mean()
+
+
+def compute_kl_loss(prior_means, posterior_means) -> torch.Tensor:
+    """lib/losses.py:55-65: sum over the latent scales."""
+    return torch.stack([latent_kl(p, q) for p, q in zip(prior_means, posterior_means)]).sum()
+
+
+def make_group_eps(cfg: dict, batch: int, tag: str = ""):
+    """Deterministic draws for the 4 prior groups of every latent scale (shape = a quarter-resolution latent)."""
+    ns, _ = n_scales_of(cfg)
+    shp = latent_shapes(batch, cfg["spatial_size"], ns, cfg["nf_max"], cfg["n_latent_scales"])
+    return [[det_normal(f"geps{i}.{l}{tag}", (b, ch, h // 2, w // 2)) for l in range(4)]
+            for i, (b, ch, h, w) in enumerate(shp)]
 
 
 # --------------------------------------------------------------------------------------------------

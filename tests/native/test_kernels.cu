@@ -486,6 +486,51 @@ int main(int argc, char** argv) {
   printf("device: %s  sm_%d%d  SMs=%d  abi=%d\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount,
          vub_abi_version());
 
+  // Smallest maps (<= 8x8): split-K over a thread-block cluster (partials reduced through distributed shared memory),
+  // and the 256 / 512-channel sources of VunetOrg's 4-group prior (models/vunets.py:655-676).
+  const ConvCase small_cases[] = {
+      {"3x3 128->128 @4x4 B5 +res dual (split 3)",         5, 4, 4, 128, 1, 128, 128, 3, 1, true, true, true, false, false, false, 0},
+      {"3x3 128->128 @8x8 B9 +res dual (split 3, 5 tiles)", 9, 8, 8, 128, 1, 128, 128, 3, 1, true, true, true, false, false, false, 0},
+      {"3x3 [128|128]->128 @8x8 B3 cat +res dual (split 4)", 3, 8, 8, 128, 2, 128, 128, 3, 1, true, true, true, false, false, false, 0},
+      {"3x3 [64|64]->64 @4x4 B3 cat +res dual (split 3)",  3, 4, 4, 64, 2, 64, 64, 3, 1, true, true, true, false, false, false, 0},
+      {"3x3 128->512 D2S @4x4 B3 dual (split 3)",          3, 4, 4, 128, 1, 512, 512, 3, 1, false, true, true, true, false, false, 0},
+      {"3x3 128->256 f32 NHWC @8x8 B3 (latent, split 3)",  3, 8, 8, 128, 1, 256, 256, 3, 1, false, false, false, false, true, false, 0},
+      {"3x3 s2 128->128 @8x8 B3 -> 4x4 (split 3)",         3, 8, 8, 128, 1, 128, 128, 3, 2, false, true, true, false, false, false, 0},
+      {"3x3 512->128 f32 NHWC @2x2 B5 (auto_lp, split 8)", 5, 2, 2, 512, 1, 128, 128, 3, 1, false, false, false, false, true, false, 0},
+      {"3x3 512->128 f32 NHWC @4x4 B9 (auto_lp, split 8)", 9, 4, 4, 512, 1, 128, 128, 3, 1, false, false, false, false, true, false, 0},
+      {"3x3 [512|512]->512 @4x4 B3 cat +res dual (split 8)", 3, 4, 4, 512, 2, 512, 512, 3, 1, true, true, true, false, false, false, 0},
+      {"3x3 [512|512]->512 @2x2 B33 cat +res raw (split 8)", 33, 2, 2, 512, 2, 512, 512, 3, 1, true, true, false, false, false, false, 0},
+      {"3x3 [256|256]->256 @1x1 B3 cat +res dual (split 8)", 3, 1, 1, 256, 2, 256, 256, 3, 1, true, true, true, false, false, false, 0},
+      {"3x3 256->64 f32 NHWC @2x2 B2 (auto_lp, split 4)",  2, 2, 2, 256, 1, 64, 64, 3, 1, false, false, false, false, true, false, 0},
+      {"1x1 128->512 @4x4 B3 elu only",                    3, 4, 4, 128, 1, 512, 512, 1, 1, false, false, true, false, false, false, 0},
+      {"1x1 [128|128]->128 @8x8 B3 cat dual (latent_nins)", 3, 8, 8, 128, 2, 128, 128, 1, 1, false, true, true, false, false, false, 0},
+      {"3x3 512->128 f32 NHWC @16x16 B2 (wide, no split)", 2, 16, 16, 512, 1, 128, 128, 3, 1, false, false, false, false, true, false, 0},
+  };
+  if (argc > 1 && !strcmp(argv[1], "splitk")) {
+    for (const ConvCase& c : small_cases) run_conv_case(c);
+    setenv("VUB_SPLITK", "0", 1);
+    for (const ConvCase& c : small_cases) run_conv_case(c);
+    unsetenv("VUB_SPLITK");
+    for (int sk : {1, 0}) {
+      setenv("VUB_SPLITK", sk ? "1" : "0", 1);
+      printf("--- VUB_SPLITK=%d\n", sk);
+      perf_conv("128->128 3x3 @4^2 B64 +res dual", 64, 4, 4, 128, 1, 128, 3, 1, true, true, false, 0);
+      perf_conv("128->128 3x3 @8^2 B64 +res dual", 64, 8, 8, 128, 1, 128, 3, 1, true, true, false, 0);
+      perf_conv("[128|128]->128 3x3 @4^2 B64 +res dual", 64, 4, 4, 128, 2, 128, 3, 1, true, true, false, 0);
+      perf_conv("[128|128]->128 3x3 @8^2 B64 +res dual", 64, 8, 8, 128, 2, 128, 3, 1, true, true, false, 0);
+      perf_conv("128->512 3x3 D2S @8^2 B64 dual", 64, 8, 8, 128, 1, 512, 3, 1, false, true, true, 0);
+      perf_conv("128->128 3x3 @8^2 B8 +res dual", 8, 8, 8, 128, 1, 128, 3, 1, true, true, false, 0);
+      perf_conv("[128|128]->128 3x3 @8^2 B8 +res dual", 8, 8, 8, 128, 2, 128, 3, 1, true, true, false, 0);
+      perf_conv("512->128 3x3 @4^2 B64 (auto_lp)", 64, 4, 4, 512, 1, 128, 3, 1, false, false, false, 0);
+      perf_conv("[512|512]->512 3x3 @4^2 B64 +res dual", 64, 4, 4, 512, 2, 512, 3, 1, true, true, false, 0);
+      perf_conv("[512|512]->512 3x3 @2^2 B64 +res dual", 64, 2, 2, 512, 2, 512, 3, 1, true, true, false, 0);
+    }
+    unsetenv("VUB_SPLITK");
+    printf("%s: %d failed\n", g_fail ? "FAILED" : "ALL PASSED", g_fail);
+    return g_fail;
+  }
+  for (const ConvCase& c : small_cases) run_conv_case(c);
+
   //                name                                   B  H   W  c  ns co  cv k s  res  raw  elu  d2s  f32h f32c st
   const ConvCase cases[] = {
       {"3x3 128->128 @16x16 B2 (BN128,BKC64)",             2, 16, 16, 128, 1, 128, 128, 3, 1, false, true, false, false, false, false, 0},
