@@ -374,7 +374,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.vub_adam_wn_step.restype = C.c_int
     lib.vub_adam_wn_step.argtypes = [vp, i32, i32, C.c_float, C.c_float, C.c_float, i32, vp]
     lib.vub_wn_bwd.restype = C.c_int
-    lib.vub_wn_bwd.argtypes = [vp, i32, i32, i32, vp]
+    lib.vub_wn_bwd.argtypes = [vp, i32, i32, i32, i32, vp]
     lib.vub_stem_bwd.restype = C.c_int
     lib.vub_stem_bwd.argtypes = [fp, vp, i32, i32, i32, i32, i32, fp, fp, vp]
     lib.vub_latent_bwd.restype = C.c_int

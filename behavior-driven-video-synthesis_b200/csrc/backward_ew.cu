@@ -42,12 +42,13 @@ __device__ __forceinline__ float2 block_sum2(float a, float b, float2* red /*[32
 // Weight-norm / affine parameter gradients: one block per output channel of any layer.
 // ------------------------------------------------------------------------------------------------
 constexpr int kWnbThreads = 128;
-constexpr int kWnbMaxLen = 2304;  // cin * k * k of the largest layer (256 x 3 x 3)
+constexpr int kWnbDefaultLen = 2304;  // cin * k * k of the largest VunetAlter layer (256 x 3 x 3)
+constexpr int kWnbMaxLen = 9216;      // ... of the largest VunetOrg layer (1024 x 3 x 3): 36 KB of dynamic shared memory
 
 __global__ void __launch_bounds__(kWnbThreads)
     wn_bwd_kernel(const vub_wnb_entry* __restrict__ table, int n_entries, int accumulate) {
   __shared__ float2 red[32];
-  __shared__ float g_s[kWnbMaxLen];  // this channel's correlation, summed over the pixel splits, in weight order
+  extern __shared__ float g_s[];  // this channel's correlation, summed over the pixel splits, in weight order (max_len floats)
   const int row = blockIdx.x;
   int lo = 0, hi = n_entries - 1;
   while (lo < hi) {
@@ -310,11 +311,14 @@ __global__ void __launch_bounds__(256)
 using namespace vub;
 
 extern "C" int vub_wn_bwd(const vub_wnb_entry* table_dev, int32_t n_entries, int32_t total_rows,
-                          int32_t accumulate, void* stream) {
+                          int32_t accumulate, int32_t max_len, void* stream) {
   clear_error();
   if (!table_dev) return fail(VUB_E_NULL, "wn_bwd: table is NULL");
   if (n_entries <= 0 || total_rows <= 0) return fail(VUB_E_SHAPE, "wn_bwd: empty table");
-  wn_bwd_kernel<<<total_rows, kWnbThreads, 0, static_cast<cudaStream_t>(stream)>>>(table_dev, n_entries, accumulate);
+  if (max_len <= 0) max_len = kWnbDefaultLen;
+  if (max_len > kWnbMaxLen) return fail(VUB_E_SHAPE, "wn_bwd: max_len %d > %d", max_len, kWnbMaxLen);
+  wn_bwd_kernel<<<total_rows, kWnbThreads, (size_t)max_len * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      table_dev, n_entries, accumulate);
   return check_launch("wn_bwd");
 }
 

@@ -482,10 +482,16 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
   // depend on the batch it is rendered in (the partial sums change the fp32 summation order).
   int ksplit = 1;
   {
+    // Measured on B200 at 64 frames (profiles/r02_splitk.log): on 4x4 maps (8 pixel tiles) three k-ranges per tile
+    // beat the N split alone (128->128 3x3 0.010 -> 0.008 ms, [128|128]->128 0.016 -> 0.010 ms), and at 8 frames also on
+    // 8x8 maps; on 8x8 maps at 64 frames (32 pixel tiles) the grid is already full and the clusters only add their
+    // barriers (0.010 -> 0.017 ms).  The rule may not look at the batch, so it stops at 4x4.  VUB_SPLITK=0 disables
+    // it, VUB_SPLITK=n >= 2 forces n ranges on every map up to 8x8 (experiments).
     const int ksteps_all = d->nsrc * d->ksize * d->ksize * (d->c_src / (d->c_src >= 64 ? 64 : 32));
-    if (hout * wout <= 64 && ksteps_all >= 12 && !(f & (VUB_CONV_ELU_IN0 | VUB_CONV_ELU_IN1)) && d->stages >= 0 &&
-        env_int("VUB_SPLITK", 1) != 0)
-      ksplit = ksteps_all < 27 ? (ksteps_all % 3 == 0 ? 3 : 2) : ksteps_all < 54 ? 4 : 8;
+    const int mode = env_int("VUB_SPLITK", 1);
+    const bool eligible = ksteps_all >= 12 && !(f & (VUB_CONV_ELU_IN0 | VUB_CONV_ELU_IN1)) && d->stages >= 0;
+    if (mode == 1 && eligible && hout * wout <= 16) ksplit = 3;
+    if (mode >= 2 && mode <= 8 && eligible && hout * wout <= 64) ksplit = mode;
   }
   if (ksplit == 1 && !wide && conv_rows_applicable(d)) return conv_rows_launch(d, static_cast<cudaStream_t>(stream_v));
   if (f & (VUB_CONV_ELU_IN0 | VUB_CONV_ELU_IN1))
@@ -614,8 +620,8 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
     const long long pix_tiles = ((long long)d->batch * hout * wout + kTileM - 1) / kTileM;
     while (bn > 32 && pix_tiles * (cout / bn) * ksplit < 96) bn >>= 1;
     // split-K: (ksplit - 1) partial tiles of 128 x bn fp32 must fit the leader's shared memory beside the staging
-    // tiles (3 -> bn <= 128, 4 -> 64, 8 -> 32; a smaller N tile changes no bits)
-    while (ksplit > 1 && bn > 16 && (ksplit - 1) * bn > 320) bn >>= 1;
+    // tiles (2, 3 -> bn <= 128, 4, 5, 6 -> 64, 7, 8 -> 32; a smaller N tile changes no bits)
+    while (ksplit > 1 && bn > 16 && ((ksplit - 1) * bn > 320 || bn > 128)) bn >>= 1;
   }
 
   ConvKParams kp;

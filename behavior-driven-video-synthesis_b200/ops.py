@@ -58,7 +58,8 @@ _LIB.define(
     "conv_wgrad(Tensor dy, Tensor x0, Tensor? x1, Tensor(a!) gt, Tensor(b!) dy_sum, int ksize, int stride, "
     "bool d2s) -> ()"
 )
-_LIB.define("wn_bwd(Tensor table, int n_entries, int total_rows, bool accumulate, float nbytes=0.0) -> ()")
+_LIB.define("wn_bwd(Tensor table, int n_entries, int total_rows, bool accumulate, float nbytes=0.0, "
+            "int max_len=0) -> ()")
 _LIB.define("adam_wn_step(Tensor table, int n_entries, int total_rows, float beta1, float beta2, float eps, int step, "
             "float nbytes=0.0) -> ()")
 _LIB.define("adam_wn_step_dev(Tensor table, int n_entries, int total_rows, float beta1, float beta2, float eps, "
@@ -362,9 +363,10 @@ def _conv_wgrad_cuda(dy, x0, x1, gt, dy_sum, ksize, stride, d2s) -> None:
                     bytes_=nbytes), "vub_conv_wgrad")
 
 
-def _wn_bwd_cuda(table, n_entries, total_rows, accumulate, nbytes=0.0) -> None:
+def _wn_bwd_cuda(table, n_entries, total_rows, accumulate, nbytes=0.0, max_len=0) -> None:
     # nbytes: algorithmic bytes of this table (split partials read once, v read, dv written; training.GradBank)
-    N.check(_launch("wn_bwd", N.lib().vub_wn_bwd, table.data_ptr(), n_entries, total_rows, int(accumulate), _stream(),
+    N.check(_launch("wn_bwd", N.lib().vub_wn_bwd, table.data_ptr(), n_entries, total_rows, int(accumulate), int(max_len),
+                    _stream(),
                     bytes_=float(nbytes)), "vub_wn_bwd")
 
 
@@ -851,8 +853,10 @@ def conv_wgrad(dy, x, gt, dy_sum, *, ksize: int, stride: int = 1, d2s: bool = Fa
     _ops.conv_wgrad(dy, x[0], x[1] if len(x) > 1 else None, gt, dy_sum, ksize, stride, d2s)
 
 
-def wn_bwd(table: torch.Tensor, n_entries: int, total_rows: int, accumulate: bool = False, nbytes: float = 0.0) -> None:
-    _ops.wn_bwd(table, n_entries, total_rows, accumulate, nbytes)
+def wn_bwd(table: torch.Tensor, n_entries: int, total_rows: int, accumulate: bool = False, nbytes: float = 0.0,
+           max_len: int = 0) -> None:
+    """``max_len``: the largest ``cin * k * k`` among the table's layers (0 = 2304, the VunetAlter maximum)."""
+    _ops.wn_bwd(table, n_entries, total_rows, accumulate, nbytes, max_len)
 
 
 def adam_wn_step(table: torch.Tensor, n_entries: int, total_rows: int, beta1: float, beta2: float, eps: float,

@@ -185,6 +185,7 @@ class GradBank:
             self.buckets[owner] = flat
             self.params[owner] = plist
             entries, rows, nbytes = [], 0, 0
+            max_len = max(m.in_channels * m.kernel_size ** 2 for m in mods)
             for m in mods:
                 cv = leader_of[id(m)]
                 # algorithmic bytes: this conv's split partials read once, v read, dv written
@@ -210,7 +211,7 @@ class GradBank:
                 entries.append(e)
             arr = (N.WnbEntry * len(entries))(*entries)
             host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
-            self._tables[owner] = (host.to(dev), len(entries), rows, float(nbytes))
+            self._tables[owner] = (host.to(dev), len(entries), rows, float(nbytes), max_len)
         self._ptr_key = tuple(p.data_ptr() for ps in self.params.values() for p in ps)
 
     def __deepcopy__(self, memo):
@@ -240,8 +241,8 @@ class GradBank:
                 if not h:
                     self.grads[id(p)].zero_()
         extra = [(p, p.grad) for p, h in zip(plist, held) if not h and p.grad is not None]
-        table, n, rows, nbytes = self._tables[owner]
-        ops.wn_bwd(table, n, rows, accumulate, nbytes)
+        table, n, rows, nbytes, max_len = self._tables[owner]
+        ops.wn_bwd(table, n, rows, accumulate, nbytes, max_len)
         for p in plist:
             if p.requires_grad:  # frozen parameters keep grad = None like under autograd
                 p.grad = self.grads[id(p)]

@@ -313,8 +313,10 @@ typedef struct vub_wnb_entry {
   int32_t pad;
 } vub_wnb_entry;
 
+/* max_len: the largest cin * ktaps among the entries (the kernel stages one weight row of gradients in shared
+ * memory); <= 0 means 2304, the largest VunetAlter layer; at most 9216 (VunetOrg's 1024 x 3 x 3 prior convs). */
 int vub_wn_bwd(const vub_wnb_entry* table_dev, int32_t n_entries, int32_t total_rows, int32_t accumulate,
-               void* stream);
+               int32_t max_len, void* stream);
 
 /*
  * Fused optimizer step: torch.optim.Adam (no weight decay, no amsgrad; the reference uses

@@ -376,7 +376,7 @@ static void test_wn_bwd() {
   vub_wnb_entry* dtab;
   CK(cudaMalloc(&dtab, sizeof(vub_wnb_entry) * nl));
   CK(cudaMemcpy(dtab, tab.data(), sizeof(vub_wnb_entry) * nl, cudaMemcpyHostToDevice));
-  const int rc = vub_wn_bwd(dtab, nl, rows, 0, nullptr);
+  const int rc = vub_wn_bwd(dtab, nl, rows, 0, 0, nullptr);
   if (rc) { printf("[FAIL] wn_bwd rc=%d %s\n", rc, vub_last_error()); ++g_fail; return; }
   sync_or_die("wn_bwd");
   Cmp cv, cs;

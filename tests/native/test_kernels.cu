@@ -507,12 +507,17 @@ int main(int argc, char** argv) {
       {"3x3 512->128 f32 NHWC @16x16 B2 (wide, no split)", 2, 16, 16, 512, 1, 128, 128, 3, 1, false, false, false, false, true, false, 0},
   };
   if (argc > 1 && !strcmp(argv[1], "splitk")) {
-    for (const ConvCase& c : small_cases) run_conv_case(c);
-    setenv("VUB_SPLITK", "0", 1);
-    for (const ConvCase& c : small_cases) run_conv_case(c);
+    // 1: the library's rule (three k-ranges on maps up to 4x4); 0: off; n >= 2: n ranges on every map up to 8x8
+    for (const char* mode : {"1", "0", "2", "4", "8"}) {
+      setenv("VUB_SPLITK", mode, 1);
+      printf("--- correctness, VUB_SPLITK=%s\n", mode);
+      for (const ConvCase& c : small_cases) run_conv_case(c);
+    }
     unsetenv("VUB_SPLITK");
-    for (int sk : {1, 0}) {
-      setenv("VUB_SPLITK", sk ? "1" : "0", 1);
+    for (int sk : {1, 0, 2}) {
+      char buf[4];
+      snprintf(buf, sizeof buf, "%d", sk);
+      setenv("VUB_SPLITK", buf, 1);
       printf("--- VUB_SPLITK=%d\n", sk);
       perf_conv("128->128 3x3 @4^2 B64 +res dual", 64, 4, 4, 128, 1, 128, 3, 1, true, true, false, 0);
       perf_conv("128->128 3x3 @8^2 B64 +res dual", 64, 8, 8, 128, 1, 128, 3, 1, true, true, false, 0);

@@ -144,7 +144,7 @@ def test_bad_arguments_are_reported_not_crashed():
     # training entry points validate before touching the device too
     assert lib.vub_conv_dgrad(None, None) == -1
     assert lib.vub_conv_wgrad(None, None) == -1
-    assert lib.vub_wn_bwd(None, 1, 1, 0, None) == -1
+    assert lib.vub_wn_bwd(None, 1, 1, 0, 0, None) == -1
     assert lib.vub_stem_bwd(None, None, 1, 3, 8, 8, 32, None, None, None) == -1
     assert lib.vub_latent_bwd(None, None, None, None, None, None, 1, 128, 4, 4, None, None) == -1
     g = _native.DgradDesc()
