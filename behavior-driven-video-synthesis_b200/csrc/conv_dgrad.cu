@@ -33,7 +33,8 @@ extern "C" int vub_conv_dgrad(const vub_dgrad_desc* d, void* stream_v) {
   if (d->nsrc != 1 && d->nsrc != 2) return fail(VUB_E_SHAPE, "conv_dgrad: nsrc must be 1 or 2");
   if (d->nsrc == 2 && !d->dx[1]) return fail(VUB_E_NULL, "conv_dgrad: dx[1] NULL with nsrc == 2");
   const int C = d->c_src;
-  if (C != 32 && C != 64 && C != 128) return fail(VUB_E_SHAPE, "conv_dgrad: c_src %d not in {32,64,128}", C);
+  if (C != 32 && C != 64 && C != 128 && C != 256 && C != 512)
+    return fail(VUB_E_SHAPE, "conv_dgrad: c_src %d not in {32,64,128,256,512}", C);
   if (d->ksize != 1 && d->ksize != 3) return fail(VUB_E_SHAPE, "conv_dgrad: ksize must be 1 or 3");
   if (d->stride != 1 && d->stride != 2) return fail(VUB_E_SHAPE, "conv_dgrad: stride must be 1 or 2");
   const bool d2s = (d->flags & VUB_CONV_D2S) != 0;
@@ -54,6 +55,56 @@ extern "C" int vub_conv_dgrad(const vub_dgrad_desc* d, void* stream_v) {
   const int bkc = cmap >= 64 ? 64 : 32;
   const int cblocks = cmap / bkc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+
+  if (C > 128) {
+    // 256 / 512 channels per source (VunetOrg's 4-group prior, models/vunets.py:655-676, on the two smallest latent
+    // maps): one launch of the tile kernel per 128-channel slice of every source -- the slice's rows of `wd`, and an
+    // epilogue that addresses its channels inside the C-channel pixel (c_off).
+    if (d->stride != 1 || d2s) return fail(VUB_E_SHAPE, "conv_dgrad: c_src %d needs stride 1 and no D2S", C);
+    if (taps * cblocks > kTileMaxKSteps) return fail(VUB_E_SHAPE, "conv_dgrad: too many k-steps");
+    const long long H = d->hin, W = d->win;
+    const long long ktot = (long long)taps * cout_k;
+    for (int s = 0; s < d->nsrc; ++s)
+      for (int c0 = 0; c0 < C; c0 += 128) {
+        TileJob job;
+        memset(&job, 0, sizeof(job));
+        job.bkc = bkc;
+        job.w = static_cast<const char*>(d->wd) + ((long long)(s * C + c0) * ktot) * 2;
+        job.w_rows = 128;
+        job.ktot = ktot;
+        job.n_total = 128;
+        job.bn = 128;
+        const long long pix_tiles = ((long long)d->batch * H * W + 127) / 128;
+        while (job.bn > 32 && pix_tiles * (128 / job.bn) < 96) job.bn >>= 1;
+        job.batch = d->batch;
+        job.hout = d->hin;
+        job.wout = d->win;
+        job.n_src = 1;
+        job.src[0] = TileSrc{d->dy, cout_k, d->win, d->hin, (long long)cout_k, W * cout_k, H * W * cout_k};
+        TileEpi& e = job.epi[0];
+        e.addend = static_cast<const __nv_bfloat16*>(d->addend[s]);
+        e.addend2 = static_cast<const __nv_bfloat16*>(d->addend2[s]);
+        e.mask_elu = static_cast<const __nv_bfloat16*>(d->mask_elu[s]);
+        e.out_raw = static_cast<__nv_bfloat16*>(d->dx[s]);
+        e.out_h = d->hin;
+        e.out_w = d->win;
+        e.out_c = C;
+        e.c_off = c0;
+        e.pix_stride = 1;
+        e.n_valid = 128;
+        int ks = 0;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int r = tap / d->ksize, q = tap % d->ksize;
+          const int dh = taps == 9 ? 1 - r : 0, dw = taps == 9 ? 1 - q : 0;
+          for (int cb = 0; cb < cblocks; ++cb, ++ks)
+            job.ksteps[ks] = KStep{0, (int8_t)dh, (int8_t)dw, (uint8_t)cb, (uint16_t)((tap * cout_k + cb * bkc) / bkc), 0};
+        }
+        job.n_ksteps = ks;
+        const int rc = conv_tiles_launch(job, stream);
+        if (rc) return rc;
+      }
+    return 0;
+  }
 
   TileJob job;
   memset(&job, 0, sizeof(job));

@@ -312,9 +312,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
 
 using namespace vub;
 
+// A launch may cover a 128-channel SLICE of wider sources (VunetOrg's 256 / 512-channel prior convs): `d` then
+// describes the slice as a one-source conv, and this says where the slice sits in the real tensors.
+struct WgSlice {
+  int s_base;   // index of the slice's source among the conv's sources (gt rows are ordered (source, tap, channel))
+  int c_total;  // channels per pixel of the x tensors = channels per (source, tap) block of gt
+  int c_off;    // first channel of the slice
+};
+
 // Fills everything of the launch parameters that depends on shapes only (no pointers, no tensor maps) and
 // returns the best number of pixel splits in *best_split.
-static int wgrad_plan_kp(const vub_wgrad_desc* d, WgKParams& kp, int* best_split, int* max_nb_out, int kp_pix) {
+static int wgrad_plan_kp(const vub_wgrad_desc* d, WgKParams& kp, int* best_split, int* max_nb_out, int kp_pix,
+                         const WgSlice& sl) {
   if (d->nsrc != 1 && d->nsrc != 2) return fail(VUB_E_SHAPE, "conv_wgrad: nsrc must be 1 or 2");
   const int C = d->c_src;
   if (C != 32 && C != 64 && C != 128) return fail(VUB_E_SHAPE, "conv_wgrad: c_src %d not in {32,64,128}", C);
@@ -358,7 +367,7 @@ static int wgrad_plan_kp(const vub_wgrad_desc* d, WgKParams& kp, int* best_split
 
   // ---- B side: x, grouped by (source, tap row) or (source) ----
   kp.cb = C >= 64 ? 64 : 32;
-  kp.c_src = C;
+  kp.c_src = sl.c_total;  // gt row stride between the column taps of a halo box (== C unless a channel slice)
   const int cblocks = C / kp.cb;
   const bool merge_rows = taps == 9 && 9 * C <= 448;  // all 9 taps of a source fit one CTA's TMEM
   static const bool no_halo = getenv("VUB_WGRAD_NO_HALO") != nullptr && getenv("VUB_WGRAD_NO_HALO")[0] == '1';
@@ -377,7 +386,7 @@ static int wgrad_plan_kp(const vub_wgrad_desc* d, WgKParams& kp, int* best_split
           if (n_rowgroups == 3 && r != rg) continue;
           for (int cbk = 0; cbk < cblocks; ++cbk, ++j)
             kp.bbox[g][j] = WgBBox{(int16_t)s, (int8_t)(r - 1), (int8_t)-1, (int16_t)(cbk * kp.cb),
-                                   (s * taps + r * 3) * C + cbk * kp.cb};
+                                   ((sl.s_base + s) * taps + r * 3) * sl.c_total + sl.c_off + cbk * kp.cb};
         }
         kp.nb[g] = j;
         continue;
@@ -399,7 +408,7 @@ static int wgrad_plan_kp(const vub_wgrad_desc* d, WgKParams& kp, int* best_split
         for (int cbk = 0; cbk < cblocks; ++cbk, ++j) {
           if (j >= kWgMaxBoxes) return fail(VUB_E_SHAPE, "conv_wgrad: too many boxes in a tap group");
           kp.bbox[g][j] = WgBBox{(int16_t)mi, (int8_t)dh, (int8_t)dw, (int16_t)(cbk * kp.cb),
-                                 (s * taps + tap) * C + cbk * kp.cb};
+                                 ((sl.s_base + s) * taps + tap) * sl.c_total + sl.c_off + cbk * kp.cb};
         }
       }
       kp.nb[g] = j;
@@ -432,16 +441,33 @@ static size_t wgrad_stage_pitch(const WgKParams& kp, int max_nb) {
 }
 
 // 128-pixel k-steps when the map is large enough and at least 3 pipeline stages fit, else 64-pixel k-steps.
-static int wgrad_plan(const vub_wgrad_desc* d, WgKParams& kp, int* best_split, int* max_nb_out) {
+static int wgrad_plan(const vub_wgrad_desc* d, WgKParams& kp, int* best_split, int* max_nb_out, const WgSlice& sl) {
   static const bool kp64 = getenv("VUB_WGRAD_KP64") != nullptr && getenv("VUB_WGRAD_KP64")[0] == '1';
   const long long pixels = (long long)d->batch * (d->hin / (d->stride > 0 ? d->stride : 1)) *
                            (d->win / (d->stride > 0 ? d->stride : 1));
   if (pixels >= 4 * kWgMaxKP && !kp64) {
-    const int rc = wgrad_plan_kp(d, kp, best_split, max_nb_out, kWgMaxKP);
+    const int rc = wgrad_plan_kp(d, kp, best_split, max_nb_out, kWgMaxKP, sl);
     if (rc) return rc;
     if ((200 * 1024 - kWgOnesBytes) / wgrad_stage_pitch(kp, *max_nb_out) >= 3) return 0;
   }
-  return wgrad_plan_kp(d, kp, best_split, max_nb_out, 64);
+  return wgrad_plan_kp(d, kp, best_split, max_nb_out, 64, sl);
+}
+
+// The slice of source `s` starting at channel `c0` of a wide conv, described as a one-source 128-channel conv.
+static vub_wgrad_desc wgrad_slice_desc(const vub_wgrad_desc* d, int s, int c0) {
+  vub_wgrad_desc sd = *d;
+  sd.nsrc = 1;
+  sd.c_src = 128;
+  sd.x[0] = d->x[s] ? static_cast<const char*>(d->x[s]) + (size_t)c0 * 2 : nullptr;
+  sd.x[1] = nullptr;
+  return sd;
+}
+
+static int wgrad_check_wide(const vub_wgrad_desc* d) {
+  if (d->nsrc != 1 && d->nsrc != 2) return fail(VUB_E_SHAPE, "conv_wgrad: nsrc must be 1 or 2");
+  if (d->stride != 1 || (d->flags & VUB_CONV_D2S))
+    return fail(VUB_E_SHAPE, "conv_wgrad: c_src %d needs stride 1 and no D2S", d->c_src);
+  return 0;
 }
 
 extern "C" int32_t vub_conv_wgrad_splits(const vub_wgrad_desc* d) {
@@ -449,24 +475,50 @@ extern "C" int32_t vub_conv_wgrad_splits(const vub_wgrad_desc* d) {
   if (!d) return fail(VUB_E_NULL, "conv_wgrad_splits: desc is NULL");
   WgKParams kp;
   int best = 0, max_nb = 0;
-  const int rc = wgrad_plan(d, kp, &best, &max_nb);
+  if (d->c_src == 256 || d->c_src == 512) {  // wide sources: the split count of one 128-channel slice launch
+    if (int rcw = wgrad_check_wide(d)) return rcw;
+    const vub_wgrad_desc sd = wgrad_slice_desc(d, 0, 0);
+    const int rc = wgrad_plan(&sd, kp, &best, &max_nb, WgSlice{0, d->c_src, 0});
+    return rc ? rc : best;
+  }
+  const int rc = wgrad_plan(d, kp, &best, &max_nb, WgSlice{0, d->c_src, 0});
   return rc ? rc : best;
 }
+
+static int wgrad_launch(const vub_wgrad_desc* d, const WgSlice& sl, void* stream_v);
 
 extern "C" int vub_conv_wgrad(const vub_wgrad_desc* d, void* stream_v) {
   clear_error();
   if (!d) return fail(VUB_E_NULL, "conv_wgrad: desc is NULL");
   if (!d->dy || !d->x[0] || !d->gt || !d->dy_sum) return fail(VUB_E_NULL, "conv_wgrad: dy/x/gt/dy_sum NULL");
   if (d->nsrc == 2 && !d->x[1]) return fail(VUB_E_NULL, "conv_wgrad: x[1] NULL with nsrc == 2");
+  if (d->c_src == 256 || d->c_src == 512) {
+    // VunetOrg's 4-group prior (models/vunets.py:655-676): one launch per 128-channel slice of every source; each
+    // writes its own (source, tap, channel) rows of gt (all of them write the same dy_sum values)
+    if (int rcw = wgrad_check_wide(d)) return rcw;
+    if (d->gt_pitch < d->nsrc * d->ksize * d->ksize * d->c_src)
+      return fail(VUB_E_SHAPE, "conv_wgrad: gt_pitch %d < K", d->gt_pitch);
+    for (int s = 0; s < d->nsrc; ++s)
+      for (int c0 = 0; c0 < d->c_src; c0 += 128) {
+        const vub_wgrad_desc sd = wgrad_slice_desc(d, s, c0);
+        const int rc = wgrad_launch(&sd, WgSlice{s, d->c_src, c0}, stream_v);
+        if (rc) return rc;
+      }
+    return 0;
+  }
+  return wgrad_launch(d, WgSlice{0, d->c_src, 0}, stream_v);
+}
+
+static int wgrad_launch(const vub_wgrad_desc* d, const WgSlice& sl, void* stream_v) {
   WgKParams kp;
   int best = 0, max_nb = 0;
-  int rc = wgrad_plan(d, kp, &best, &max_nb);
+  int rc = wgrad_plan(d, kp, &best, &max_nb, sl);
   if (rc) return rc;
   const int C = d->c_src, cout_k = d->cout_k;
   const bool d2s = (d->flags & VUB_CONV_D2S) != 0;
   const int cmap = d2s ? cout_k / 4 : cout_k;
   const int ho = d->hin / d->stride, wo = d->win / d->stride;
-  const int ktot = d->nsrc * d->ksize * d->ksize * C;
+  const int ktot = d->nsrc * d->ksize * d->ksize * sl.c_total;
   if (d->gt_pitch < ktot) return fail(VUB_E_SHAPE, "conv_wgrad: gt_pitch %d < K = %d", d->gt_pitch, ktot);
   if (d->n_split < 1 || d->n_split > kp.total_tiles || d->n_split > 1024)
     return fail(VUB_E_SHAPE, "conv_wgrad: n_split %d not in [1, %d] (vub_conv_wgrad_splits suggests %d)", d->n_split,
@@ -510,9 +562,9 @@ extern "C" int vub_conv_wgrad(const vub_wgrad_desc* d, void* stream_v) {
         }
     }
     const uint32_t boxB[4] = {(uint32_t)kp.cb, (uint32_t)(kp.tw + 2 * kp.halo), (uint32_t)kp.th, (uint32_t)kp.tn};
-    const uint64_t Cc = C, Hin = d->hin, Win = d->win;
+    const uint64_t Cc = sl.c_total, Hin = d->hin, Win = d->win;  // channel pitch of a pixel (== C unless a slice)
     if (d->stride == 1) {
-      const uint64_t dims[4] = {Cc, Win, Hin, (uint64_t)d->batch};
+      const uint64_t dims[4] = {(uint64_t)C, Win, Hin, (uint64_t)d->batch};
       const uint64_t str[3] = {Cc * 2, Win * Cc * 2, Hin * Win * Cc * 2};
       for (int s = 0; s < d->nsrc; ++s) {
         rc = encode_tmap_bf16(&kp.tmB[s], d->x[s], 4, dims, str, boxB, kp.cb * 2, false);

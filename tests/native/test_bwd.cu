@@ -577,6 +577,24 @@ int main(int argc, char** argv) {
       {"3x3 128->256 D2S @16x16 B1 addend",                   1, 16, 16, 128, 1, 256, 3, 1, true, false, true, false, false},
       {"3x3 64->128 D2S @32x32 B1",                           1, 32, 32, 64, 1, 128, 3, 1, true, false, false, false, false},
   };
+  // 256 / 512 channels per source (VunetOrg's 4-group prior, models/vunets.py:655-676): one launch per 128-channel slice
+  const BwdCase wide_cases[] = {
+      {"wide 3x3 512->128 (auto_lp) @4x4 B3 addend",          3, 4, 4, 512, 1, 128, 3, 1, false, false, true, false, false},
+      {"wide 3x3 [512|512]->512 @4x4 B3 cat mask+add+add2",   3, 4, 4, 512, 2, 512, 3, 1, false, true, true, true, true},
+      {"wide 3x3 [512|512]->512 @2x2 B9 cat mask+add2",       9, 2, 2, 512, 2, 512, 3, 1, false, true, false, true, false},
+      {"wide 3x3 [256|256]->256 @1x1 B5 cat mask",            5, 1, 1, 256, 2, 256, 3, 1, false, true, false, false, false},
+      {"wide 3x3 256->64 (auto_lp) @2x2 B3",                  3, 2, 2, 256, 1, 64, 3, 1, false, false, false, false, false},
+      {"1x1 128->512 (nin of the prior blocks) @4x4 B3 mask", 3, 4, 4, 128, 1, 512, 1, 1, false, true, false, false, false},
+      {"wide 3x3 512->128 @8x8 B5 mask+addend (5 k-steps)",   5, 8, 8, 512, 1, 128, 3, 1, false, true, true, false, false},
+  };
+  if (argc > 1 && !strcmp(argv[1], "wide")) {
+    for (const BwdCase& c : wide_cases) run_dgrad(c);
+    for (const BwdCase& c : wide_cases) run_wgrad(c);
+    printf("%s: %d failed\n", g_fail ? "FAILED" : "ALL PASSED", g_fail);
+    return g_fail;
+  }
+  for (const BwdCase& c : wide_cases) run_dgrad(c);
+  for (const BwdCase& c : wide_cases) run_wgrad(c);
   for (const BwdCase& c : cases) run_dgrad(c);
   g_tiled = 1;  // the same data gradients with 1-D bulk weight loads from the tile-major wd
   for (const BwdCase& c : cases)

@@ -226,3 +226,96 @@ def test_fp32_validation_mode_matches_reference_to_1e4(golden, name):
     assert fixture < FP32_TOL * 10
     for k, n_ref in fx["grad_norms"].items():
         assert abs(float(got[k].norm()) - n_ref) < 1e-3 * n_ref + 1e-9, k
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# bf16 training: forward + the hand-written backward schedule (tcgen05 dgrad / wgrad, 128-channel slices for the
+# 256 / 512-channel prior convs) against the oracle's autograd and the reference's own gradient fixtures
+# ---------------------------------------------------------------------------------------------------------------
+GRAD_TOL = 1e-2
+
+
+def _bf16_grads(m, sd, cfg, bs, tag, fx=None):
+    import bdvs_b200 as B
+    m.train()
+    x, c, eps, _ = O.make_inputs(cfg, bs)
+    geps = O.make_group_eps(cfg, bs)
+    target = O.det_uniform("target", (bs, 3, cfg["spatial_size"], cfg["spatial_size"]))
+    imgs, qs, ps, _ = m(x.cuda(), c.cuda(), eps=cuda(eps), eps_groups=cuda2(geps))
+    assert imgs.requires_grad and qs[0].requires_grad and ps[1].requires_grad
+    loss = torch.mean((imgs - target.cuda()) ** 2) + 1e-3 * B.compute_kl_loss(ps, qs)
+    loss.backward()
+    torch.cuda.synchronize()
+    got = {k: (p.grad.detach().float().cpu() if p.grad is not None else None) for k, p in m.named_parameters()}
+    sd_g = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    o_imgs, o_qs, o_ps, _, _, _ = O.org_forward(sd_g, x, c, eps, geps)
+    o_loss = torch.mean((o_imgs - target) ** 2) + 1e-3 * O.compute_kl_loss(o_ps, o_qs)
+    o_loss.backward()
+    ref = {k: v.grad for k, v in sd_g.items()}
+    assert abs(float(loss) - float(o_loss)) < 2e-2 * abs(float(o_loss))
+    none_ref = sorted(k for k, g in ref.items() if g is None or float(g.abs().max()) == 0.0)
+    assert sorted(k for k, g in got.items() if g is None) == none_ref
+    keys = [k for k in ref if k not in none_ref]
+    for k in keys:
+        assert torch.isfinite(got[k]).all(), k
+
+    def crel(ks):
+        num = sum(float((got[k] - ref[k]).pow(2).sum()) for k in ks)
+        den = sum(float(ref[k].pow(2).sum()) for k in ks)
+        return (num / den) ** 0.5
+
+    total = crel(keys)
+    per_owner = {o: crel([k for k in keys if k.startswith(o + ".")]) for o in ("eu", "ed", "du", "dd")}
+    prior = crel([k for k in keys if ".auto_lp." in k or ".auto_blocks." in k or ".latent_nins." in k])
+    worst = max(keys, key=lambda k: float((got[k] - ref[k]).norm() / ref[k].norm().clamp_min(1e-12)))
+    worst_err = float((got[worst] - ref[worst]).norm() / ref[worst].norm().clamp_min(1e-12))
+    print(f"{tag}: bf16 concatenated grad rel-L2 {total:.3e}, per sub-network {per_owner}, prior convs {prior:.3e}, "
+          f"worst tensor {worst} {worst_err:.3e}")
+    assert total < GRAD_TOL and prior < 2 * GRAD_TOL
+    assert all(v < 2 * GRAD_TOL for v in per_owner.values()), per_owner
+    assert worst_err < 0.15, (worst, worst_err)
+    if fx is not None:
+        assert abs(float(loss) - fx["loss"]) < 2e-2 * abs(fx["loss"])
+        assert sorted(k for k, g in got.items() if g is None) == fx["grad_is_none"]
+        num = den = 0.0
+        for k, n_ref in fx["grad_norms"].items():
+            num += (float(got[k].norm()) - n_ref) ** 2
+            den += n_ref ** 2
+        assert (num / den) ** 0.5 < GRAD_TOL
+        for k, g_ref in fx["grad_full"].items():
+            assert float((got[k] - g_ref).norm() / g_ref.norm()) < 5e-2, k
+    return got
+
+
+@pytest.mark.parametrize("name", ["org_tiny3", "org_tiny30", "org_m128"])
+def test_bf16_gradients_match_oracle_and_reference_fixture(golden, name):
+    fx = golden(name)
+    cfg = fx["config"]
+    m, sd = build(cfg)
+    got = _bf16_grads(m, sd, cfg, cfg["batch"], name, fx)
+    # gradients accumulate over two backward passes like autograd's, and an optimizer step moves the loss
+    import bdvs_b200 as B
+    x, c, eps, _ = O.make_inputs(cfg, cfg["batch"])
+    geps = O.make_group_eps(cfg, cfg["batch"])
+    target = O.det_uniform("target", (cfg["batch"], 3, cfg["spatial_size"], cfg["spatial_size"])).cuda()
+    imgs, qs, ps, _ = m(x.cuda(), c.cuda(), eps=cuda(eps), eps_groups=cuda2(geps))
+    (torch.mean((imgs - target) ** 2) + 1e-3 * B.compute_kl_loss(ps, qs)).backward()
+    k = "dd.auto_lp.l_1.2.conv.weight_v"
+    g2 = dict(m.named_parameters())[k].grad.float().cpu()
+    assert float((g2 - 2 * got[k]).norm() / (2 * got[k]).norm()) < 1e-3
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3, betas=(0.5, 0.9))
+    losses = []
+    for _ in range(3):
+        opt.zero_grad(set_to_none=True)
+        imgs, qs, ps, _ = m(x.cuda(), c.cuda(), eps=cuda(eps), eps_groups=cuda2(geps))
+        loss = torch.mean((imgs - target) ** 2) + 1e-3 * B.compute_kl_loss(ps, qs)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0]
+
+
+def test_bf16_gradients_full_size():
+    """config/vunet.yaml geometry (256x256, 30 appearance channels), batch 2."""
+    m, sd = build(D256)
+    _bf16_grads(m, sd, D256, 2, "VunetOrg D256 B=2")
