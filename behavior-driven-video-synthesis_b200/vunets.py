@@ -774,3 +774,25 @@ class VunetOrg(_VunetBase):
         _keep, _, lat, gs = self._encode_and_pose(bank, x, c, eps, want_q_act=True)
         return self.dd._run(bank, gs, [r["q_act"] for r in lat], True, eps_groups=eps_groups,
                             uint8_frames=uint8_frames, want_prior=False)[0]
+
+    # ---- sequence-level split of `transfer`, as in VunetAlter ------------------------------------
+    def encode_appearance(self, x, eps: Optional[Sequence[torch.Tensor]] = None):
+        """``eu`` + ``ed`` ONCE per appearance image: the posterior means as activations, for :meth:`decode_pose`."""
+        _require_cuda(x)
+        bank = self._bank()
+        hs = self.eu._run(bank, _as_input(x))
+        _, lat = self.ed._run(bank, hs, eps=eps, skip_dead=True, want_q_act=True)
+        return [r["q_act"] for r in lat]
+
+    def decode_pose(self, c, appearance, frames_per_appearance: int = 1, uint8_frames: bool = False):
+        """``du`` + ``dd`` for ``c`` = ``[S * T, 3, H, W]`` stickmen (sequence-major) against ``S`` encoded appearances:
+        equals ``transfer(x.repeat_interleave(T, 0), c)`` with one latent-noise draw per sequence."""
+        _require_cuda(c)
+        bank = self._bank()
+        if frames_per_appearance > 1:  # tiny tensors (128 x 4^2 / 8^2 per sequence): plain torch indexing
+            appearance = [Act(a.raw.repeat_interleave(frames_per_appearance, dim=0),
+                              a.elu.repeat_interleave(frames_per_appearance, dim=0)) for a in appearance]
+        if appearance[0].raw.shape[0] != c.shape[0]:
+            raise ValueError("decode_pose: c must hold frames_per_appearance frames for every appearance image")
+        gs = self.du._run(bank, _as_input(c))
+        return self.dd._run(bank, gs, list(appearance), True, uint8_frames=uint8_frames, want_prior=False)[0]

@@ -389,6 +389,59 @@ def run_train_section(args, device, world, rank, barrier, peaks):
     return out
 
 
+def run_vunet_org(device, frames: int, steps: int, peaks) -> dict:
+    """``VunetOrg.transfer`` (models/vunets.py:102-110) at the H256 geometry, ``frames`` frames per step, CUDA-graph
+    replay timed with CUDA events on this rank; plus the share of the step the prior's 512 / 1024-channel convs take
+    (one instrumented eager step)."""
+    import bdvs_b200 as B
+    import vunet_oracle as O
+    from bdvs_b200.profiler import KernelProfiler
+    from bdvs_b200.synthesis import FrameSynthesizer
+
+    cfg = {k: v for k, v in H256.items()}
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = B.VunetOrg(**cfg)
+    m.load_state_dict(O.det_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}))
+    m = m.to(device).eval()
+    syn = FrameSynthesizer(m, frames, device)
+    syn.x.uniform_(-1, 1)
+    syn.c.uniform_(-1, 1)
+    for _ in range(3):
+        syn.run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        syn.run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    with torch.no_grad():
+        os.environ["VUB_FWD_STREAMS"] = "1"
+        try:
+            m.transfer(syn.x, syn.c)
+            with KernelProfiler() as kp:
+                m.transfer(syn.x, syn.c)
+        finally:
+            del os.environ["VUB_FWD_STREAMS"]
+    prof = kp.summary()
+    total = sum(r["ms"] for r in prof.values())
+    wide = {k: r for k, r in prof.items() if "x512->" in k or "x256->" in k or "->512 k1" in k}
+    wide_ms = sum(r["ms"] for r in wide.values())
+    wide_fl = sum(r["flops"] for r in wide.values())
+    gflop = 43.96 - 0.277  # SURVEY §8f-3 census (117 convs) minus the dead ed branch
+    return {"metric": "VunetOrg 256x256 frame synthesis throughput (transfer, 4-group autoregressive prior)",
+            "value": frames / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "frames_per_step": frames, "per_gpu": True,
+            "launches_per_step": syn.launches_per_call, "parameters": sum(p.numel() for p in m.parameters()),
+            "conv_tflops": round(gflop * frames / ms, 1),
+            "frac_tensor_peak_sustained": round(gflop * frames / ms / peaks["bf16_tflops_sustained"], 4),
+            "prior_convs": {"launches": sum(r["launches"] for r in wide.values()), "ms": round(wide_ms, 4),
+                            "share_of_instrumented_step": round(wide_ms / total, 4),
+                            "tflops": round(wide_fl / (wide_ms * 1e-3) / 1e12, 1) if wide_ms > 0 else 0.0,
+                            "note": "the 512->128, 128->512 and [512|512]->512 convs of the prior on the 2x2 / 4x4 maps: "
+                                    "per-tap tcgen05 kernel, split-K over 3-CTA clusters (DSMEM reduction)"}}
+
+
 def static_config(frames_per_gpu: int, world: int) -> dict:
     """The workload description shared by both arms (the product arm adds nothing run-dependent here)."""
     return {"workload": WORKLOAD, "frames_per_gpu_per_step": frames_per_gpu,
@@ -737,6 +790,11 @@ def run_ours(args):
             "families": fams, "cpu_baseline": train.get("cpu_baseline"), "loss": train["loss"]}
     elif isinstance(train, dict):
         roofline["train"] = train
+    # ---- the VunetOrg family (4-group autoregressive prior) on the same 64-frame synthesis workload ----
+    try:
+        roofline["vunet_org"] = run_vunet_org(device, Bf, K, peaks)
+    except Exception as exc:  # secondary number: never take the headline down
+        roofline["vunet_org"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     roofline["whole_step"] = whole
     roofline["sequence"] = sequence
     roofline["pose_rendering"] = pose

@@ -319,3 +319,29 @@ def test_bf16_gradients_full_size():
     """config/vunet.yaml geometry (256x256, 30 appearance channels), batch 2."""
     m, sd = build(D256)
     _bf16_grads(m, sd, D256, 2, "VunetOrg D256 B=2")
+
+
+def test_sequence_split_equals_transfer(golden):
+    """encode_appearance once + decode_pose == transfer on the repeated appearance, also through the
+    CUDA-graph synthesizers."""
+    from bdvs_b200.synthesis import FrameSynthesizer, SequenceSynthesizer
+    fx = golden("org_tiny3")
+    cfg = fx["config"]
+    m, sd = build(cfg)
+    x, c, eps, _ = O.make_inputs(cfg, 1)
+    c4 = O.det_uniform("c4", (4, 3, cfg["spatial_size"], cfg["spatial_size"]))
+    with torch.no_grad():
+        app = m.encode_appearance(x.cuda(), eps=cuda(eps))
+        a = m.decode_pose(c4.cuda(), app, frames_per_appearance=4)
+        b = m.transfer(x.cuda().repeat_interleave(4, 0), c4.cuda(), eps=[e.cuda().repeat_interleave(4, 0) for e in eps])
+    assert torch.equal(a, b)
+    torch.manual_seed(3)
+    fs = FrameSynthesizer(m, 4)
+    out = fs(x.cuda().repeat_interleave(4, 0), c4.cuda()).clone()
+    torch.manual_seed(3)
+    with torch.no_grad():
+        ref = m.transfer(x.cuda().repeat_interleave(4, 0), c4.cuda())
+    assert out.shape == ref.shape and torch.isfinite(out).all()
+    assert rel(out, ref) < 5e-2  # different noise draws inside the graph: same distribution, not the same bits
+    ss = SequenceSynthesizer(m, 1, 4)
+    assert ss(x.cuda(), c4.cuda()).shape == ref.shape
