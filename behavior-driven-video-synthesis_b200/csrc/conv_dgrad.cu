@@ -92,6 +92,7 @@ extern "C" int vub_conv_dgrad(const vub_dgrad_desc* d, void* stream_v) {
         e.c_off = c0;
         e.pix_stride = 1;
         e.n_valid = 128;
+        e.flags = d->flags & VUB_CONV_RELU;
         int ks = 0;
         for (int tap = 0; tap < taps; ++tap) {
           const int r = tap / d->ksize, q = tap % d->ksize;
@@ -137,6 +138,7 @@ extern "C" int vub_conv_dgrad(const vub_dgrad_desc* d, void* stream_v) {
     e.out_c = C;
     e.pix_stride = 1;
     e.n_valid = C;
+    e.flags = d->flags & VUB_CONV_RELU;  // ReLU' instead of ELU' from the stored activation
   }
 
   {  // HBM-bound wide, thin layers: row-streaming kernel in data-gradient mode
@@ -144,7 +146,7 @@ extern "C" int vub_conv_dgrad(const vub_dgrad_desc* d, void* stream_v) {
     if (conv_rows_dgrad(d, stream, &rrc)) return rrc;
   }
 
-  if (d->stride == 1 && !d2s && d->ksize == 3 && (d->nsrc == 1 || C % 128 == 0) &&
+  if (d->stride == 1 && !d2s && !(d->flags & VUB_CONV_RELU) && d->ksize == 3 && (d->nsrc == 1 || C % 128 == 0) &&
       conv_slab_shape_ok(cout_k, d->hin, d->win, d->nsrc * C, 9 * cout_k, ((long long)d->batch * d->hin * d->win + 127) / 128)) {
     // same shapes as the forward slab kernel with the channel roles swapped: A = dy, taps mirrored
     SlabJob sj;

@@ -311,8 +311,9 @@ __global__ void __launch_bounds__(kConvThreads)
             }
             if (p.ep.out_raw != nullptr) stage_put32<GW>(st_raw, lane, c0 - g0, y);
             if (p.ep.out_elu != nullptr) {
+              const bool relu = (p.ep.flags & VUB_CONV_RELU) != 0;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) y[i] = elu1(y[i]);
+              for (int i = 0; i < 32; ++i) y[i] = act1(y[i], relu);
               stage_put32<GW>(st_elu, lane, c0 - g0, y);
             }
           }
@@ -499,7 +500,7 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
                              "(see vub_conv_fwd_elu_in_ok) — store an ELU copy for this layer");
 
   // tensor-core-bound 3x3 layers at 64x64 / 32x32: activation-slab kernel (A and weight reuse in smem)
-  if (ksplit == 1 && !wide && d->ksize == 3 && d->stride == 1 && d->stages >= 0 && !f32 && conv_slab_shape_ok(d->c_src, d->hin, d->win, cout, d->nsrc * 9 * d->c_src, ((long long)d->batch * d->hin * d->win + 127) / 128)) {
+  if (ksplit == 1 && !wide && !(f & VUB_CONV_RELU) && d->ksize == 3 && d->stride == 1 && d->stages >= 0 && !f32 && conv_slab_shape_ok(d->c_src, d->hin, d->win, cout, d->nsrc * 9 * d->c_src, ((long long)d->batch * d->hin * d->win + 127) / 128)) {
     SlabJob job;
     memset(&job, 0, sizeof(job));
     job.x[0] = d->x[0];

@@ -732,7 +732,7 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
               float ev[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
               add_bf16x8(vm[j], ev);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) y[8 * j + i] *= ev[i] > 0.f ? 1.0f : ev[i] + 1.0f;
+              for (int i = 0; i < 8; ++i) y[8 * j + i] *= act1_grad(ev[i], (e.flags & VUB_CONV_RELU) != 0);
             }
           }
 #pragma unroll
@@ -862,8 +862,9 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
                   add_bf16x8(lds128(tR + TmaStage<SGW>::off(lane, c * (CH / 8) + j)), &y[8 * j]);
               }
               if (p.ep.out_elu != nullptr) {
+                const bool relu = (p.ep.flags & VUB_CONV_RELU) != 0;
 #pragma unroll
-                for (int i = 0; i < CH; ++i) y[i] = elu1(y[i]);
+                for (int i = 0; i < CH; ++i) y[i] = act1(y[i], relu);
               }
               stage_put32_tma<SGW>(tO, lane, c * CH, y);
               continue;
@@ -875,8 +876,9 @@ __global__ void __launch_bounds__(MODE == kRowsFwdElu ? kRowsThreadsElu : kRowsT
             }
             if (p.ep.out_raw != nullptr) stage_put32<SGW>(t0, lane, c * CH, y);
             if (p.ep.out_elu != nullptr) {
+              const bool relu = (p.ep.flags & VUB_CONV_RELU) != 0;
 #pragma unroll
-              for (int i = 0; i < CH; ++i) y[i] = elu1(y[i]);
+              for (int i = 0; i < CH; ++i) y[i] = act1(y[i], relu);
               stage_put32<SGW>(t1, lane, c * CH, y);
             }
             continue;
@@ -1179,6 +1181,7 @@ bool conv_rows_dgrad(const vub_dgrad_desc* d, cudaStream_t stream, int* rc) {
       e.out_c = C;
       e.pix_stride = 1;
       e.n_valid = C;
+      e.flags = d->flags & VUB_CONV_RELU;
     }
     *rc = rows_job_launch(j, stream);
     if (*rc) return true;

@@ -518,9 +518,9 @@ int conv_tiles_launch(const TileJob& job, cudaStream_t stream) {
   const int gw_epi = bn >= 64 ? 64 : 32;
   for (int i = 0; i < n_epi; ++i) {
     const TileEpi& e = job.epi[i];
-    const bool plain = e.flags == 0 && e.out_h == job.hout && e.out_w == job.wout;
+    const bool plain = (e.flags & ~VUB_CONV_RELU) == 0 && e.out_h == job.hout && e.out_w == job.wout;
     // DepthToSpace: a warp's 32 pixels inside one image row, a channel group inside one quadrant
-    const bool d2s = e.flags == VUB_CONV_D2S && e.out_h == 2 * job.hout && e.out_w == 2 * job.wout && kp.tw >= 32 &&
+    const bool d2s = (e.flags & ~VUB_CONV_RELU) == VUB_CONV_D2S && e.out_h == 2 * job.hout && e.out_w == 2 * job.wout && kp.tw >= 32 &&
                      e.out_c % gw_epi == 0 && e.c_off == 0 && n_epi == 1;
     d2s_all = d2s_all && d2s;
     contig = contig && (plain || d2s) && e.pix_stride == 1 && e.pix_off_h == 0 && e.pix_off_w == 0 && e.out_f32 == nullptr;

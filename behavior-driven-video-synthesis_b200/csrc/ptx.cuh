@@ -290,6 +290,12 @@ __device__ __forceinline__ float elu1(float v) {
   const float e = ex2_approx(v * 1.4426950408889634f) - 1.0f;
   return v > 0.f ? v : e;
 }
+// The activation stored as an epilogue's "elu" output: ELU (the VUnet), or ReLU with VUB_CONV_RELU (VGG19 features of
+// the perceptual loss, models/imagenet_pretrained.py:46-59); and its derivative reconstructed from the stored value.
+__device__ __forceinline__ float act1(float v, bool relu) { return relu ? fmaxf(v, 0.f) : elu1(v); }
+__device__ __forceinline__ float act1_grad(float stored, bool relu) {
+  return stored > 0.f ? 1.0f : (relu ? 0.0f : stored + 1.0f);
+}
 
 // ----------------------------------------------------------------------------------------------
 // CTA pair (cluster of two CTAs, tcgen05 cta_group::2).  Verified on hardware: tests/native/exp_cta2.cu.

@@ -166,7 +166,7 @@ __device__ __forceinline__ void tile_epilogue_staged(const TileEpi& e, const Epi
           if constexpr (GW == 32) add_bf16x8(vm[j], ev);
           else add_bf16x8(lds128(t1 + EpiStage<GW>::off(lane, ch0 + j)), ev);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) y[8 * j + i] *= ev[i] > 0.f ? 1.0f : ev[i] + 1.0f;
+          for (int i = 0; i < 8; ++i) y[8 * j + i] *= act1_grad(ev[i], (e.flags & VUB_CONV_RELU) != 0);
         }
       }
       if (e.addend != nullptr) {
@@ -185,8 +185,9 @@ __device__ __forceinline__ void tile_epilogue_staged(const TileEpi& e, const Epi
       }
       if (e.out_raw != nullptr) stage_put32<GW>(t0, lane, c0 - g0, y);
       if (e.out_elu != nullptr) {
+        const bool relu = (e.flags & VUB_CONV_RELU) != 0;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) y[i] = elu1(y[i]);
+        for (int i = 0; i < 32; ++i) y[i] = act1(y[i], relu);
         stage_put32<GW>(t1, lane, c0 - g0, y);
       }
     }
@@ -305,7 +306,7 @@ __device__ __forceinline__ void tile_epilogue_contig(const TileEpi& e, const flo
           if constexpr (GW == 32) add_bf16x8(vm[j], ev);
           else add_bf16x8(lds128(t1 + EpiStage<GW>::off(lane, ch0 + j)), ev);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) y[8 * j + i] *= ev[i] > 0.f ? 1.0f : ev[i] + 1.0f;
+          for (int i = 0; i < 8; ++i) y[8 * j + i] *= act1_grad(ev[i], (e.flags & VUB_CONV_RELU) != 0);
         }
       }
       if (e.addend != nullptr) {
@@ -324,8 +325,9 @@ __device__ __forceinline__ void tile_epilogue_contig(const TileEpi& e, const flo
       }
       if (e.out_raw != nullptr) stage_put32<GW>(t0, lane, c0 - g0, y);
       if (e.out_elu != nullptr) {
+        const bool relu = (e.flags & VUB_CONV_RELU) != 0;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) y[i] = elu1(y[i]);
+        for (int i = 0; i < 32; ++i) y[i] = act1(y[i], relu);
         stage_put32<GW>(t1, lane, c0 - g0, y);
       }
     }

@@ -22,7 +22,7 @@ _LIB = torch.library.Library("vunet_b200", "DEF")
 _LIB.define(
     "conv_fwd(Tensor x0, Tensor? x1, Tensor w, Tensor scale, Tensor shift, Tensor? residual, "
     "int ksize, int stride, int cout_valid, bool want_raw, bool want_elu, bool d2s, int f32_mode, "
-    "int stages, int elu_in=0, Tensor? w_tiled=None) -> Tensor[]"
+    "int stages, int elu_in=0, Tensor? w_tiled=None, bool relu=False) -> Tensor[]"
 )
 _LIB.define("wn_prep(Tensor table, int n_entries, int total_rows) -> ()")
 _LIB.define(
@@ -52,7 +52,7 @@ _LIB.define("latent_bwd32(Tensor logstd, Tensor? eps, Tensor? d_mu, Tensor? d_ls
 _LIB.define(
     "conv_dgrad(Tensor dy, Tensor wd, Tensor(a!) dx0, Tensor(b!)? dx1, Tensor? mask0, Tensor? mask1, "
     "Tensor? add0, Tensor? add1, Tensor? add20, Tensor? add21, int ksize, int stride, bool d2s, "
-    "Tensor? wd_tiled=None) -> ()"
+    "Tensor? wd_tiled=None, bool relu=False) -> ()"
 )
 _LIB.define(
     "conv_wgrad(Tensor dy, Tensor x0, Tensor? x1, Tensor(a!) gt, Tensor(b!) dy_sum, int ksize, int stride, "
@@ -67,6 +67,14 @@ _LIB.define("adam_wn_step_dev(Tensor table, int n_entries, int total_rows, float
 _LIB.define("stem_bwd(Tensor x, Tensor dy, Tensor(a!) gt, Tensor(b!) dy_sum) -> ()")
 _LIB.define("latent_bwd(Tensor logstd, Tensor? eps, Tensor? d_mu, Tensor? d_ls, Tensor? dz) -> Tensor")
 _LIB.define("nchw_to_nhwc_pad(Tensor x, int c_pad) -> Tensor")
+# ---- VGG19 perceptual loss: memory-bound pieces around the conv kernels ------------------------------
+_LIB.define("vgg_normalize(Tensor x, bool want_nhwc, bool want_nchw) -> Tensor[]")
+_LIB.define("vgg_input_l1(Tensor pred, Tensor target) -> Tensor")
+_LIB.define("vgg_input_bwd(Tensor pred, Tensor target, Tensor? d_xn, Tensor? g0, float scale0) -> Tensor")
+_LIB.define("maxpool2_fwd(Tensor x) -> Tensor")
+_LIB.define("maxpool2_relu_bwd(Tensor x, Tensor dy, Tensor? addend) -> Tensor")
+_LIB.define("l1_partial(Tensor pf, Tensor tf) -> Tensor")
+_LIB.define("l1_relu_grad(Tensor pf, Tensor tf, Tensor g, float scale) -> Tensor")
 # ---- VunetOrg family: latent_sample + 4-group prior bookkeeping -----------------------------------
 _LIB.define("latent_sample(Tensor p, Tensor? eps, int sub, int gi, int gj, Tensor(a!)? mean, Tensor(b!)? z, "
             "Tensor(c!)? z_raw, Tensor(d!)? z_elu, bool want_grp_elu) -> Tensor[]")
@@ -111,7 +119,7 @@ def _check_act(t: torch.Tensor, name: str) -> None:
 
 
 def _conv_fwd_cuda(x0, x1, w, scale, shift, residual, ksize, stride, cout_valid, want_raw, want_elu,
-                   d2s, f32_mode, stages, elu_in=0, w_tiled=None) -> List[torch.Tensor]:
+                   d2s, f32_mode, stages, elu_in=0, w_tiled=None, relu=False) -> List[torch.Tensor]:
     _check_act(x0, "conv_fwd x0")
     B, H, W, c_src = x0.shape
     nsrc = 1
@@ -173,6 +181,8 @@ def _conv_fwd_cuda(x0, x1, w, scale, shift, residual, ksize, stride, cout_valid,
         flags |= N.CONV_ELU_IN0
     if elu_in & 2:
         flags |= N.CONV_ELU_IN1
+    if relu:  # the "elu" output holds ReLU(y): VGG19 feature convs of the perceptual loss
+        flags |= N.CONV_RELU
     d.flags, d.stages = flags, stages
     bn = min(cout, 256)
     bkc = 64 if c_src >= 64 else 32
@@ -278,7 +288,7 @@ def _nhwc_to_nchw_cuda(x) -> torch.Tensor:
 
 
 def _conv_dgrad_cuda(dy, wd, dx0, dx1, mask0, mask1, add0, add1, add20, add21, ksize, stride, d2s,
-                     wd_tiled=None) -> None:
+                     wd_tiled=None, relu=False) -> None:
     _check_act(dy, "conv_dgrad dy")
     _check_act(dx0, "conv_dgrad dx0")
     B, H, W, c_src = dx0.shape
@@ -305,7 +315,7 @@ def _conv_dgrad_cuda(dy, wd, dx0, dx1, mask0, mask1, add0, add1, add20, add21, k
     d.addend[0], d.addend[1] = _p(add0), _p(add1)
     d.addend2[0], d.addend2[1] = _p(add20), _p(add21)
     d.nsrc, d.c_src, d.batch, d.hin, d.win = nsrc, c_src, B, H, W
-    d.cout_k, d.ksize, d.stride, d.flags = cout_k, ksize, stride, (N.CONV_D2S if d2s else 0)
+    d.cout_k, d.ksize, d.stride, d.flags = cout_k, ksize, stride, (N.CONV_D2S if d2s else 0) | (N.CONV_RELU if relu else 0)
     n_extra = sum(t is not None for t in (mask0, mask1, add0, add1, add20, add21))
     nbytes = float(dy.numel() * 2 + wd.numel() * 2 + dx0.numel() * 2 * (nsrc + n_extra))
     flops = 2.0 * B * Ho * Wo * cout_k * taps * nsrc * c_src
@@ -649,6 +659,108 @@ def _space_to_depth_cuda(x, group_major, inverse, want_copy, want_elu, accumulat
     return [t for t in (copy, elu) if t is not None]
 
 
+
+# ---- VGG19 perceptual loss ------------------------------------------------------------------------
+def _check_img(t: torch.Tensor, name: str) -> None:
+    if t.dtype != torch.float32 or t.dim() != 4 or t.shape[1] != 3:
+        raise ValueError(f"{name}: expected NCHW fp32 with 3 channels, got {t.dtype} {tuple(t.shape)}")
+
+
+def _vgg_normalize_cuda(x, want_nhwc, want_nchw) -> List[torch.Tensor]:
+    _check_img(x, "vgg_normalize x")
+    x = x.contiguous()
+    B, _, H, W = x.shape
+    nhwc = torch.empty((B, H, W, 32), dtype=torch.bfloat16, device=x.device) if want_nhwc else None
+    nchw = torch.empty_like(x) if want_nchw else None
+    N.check(_launch("vgg_normalize", N.lib().vub_vgg_normalize, x.data_ptr(), B, H, W, _p(nhwc), _p(nchw), _stream(),
+                    bytes_=float(x.numel() * 4 + (B * H * W * 64 if want_nhwc else 0) + (x.numel() * 4 if want_nchw else 0))),
+            "vub_vgg_normalize")
+    return [t for t in (nhwc, nchw) if t is not None]
+
+
+def _vgg_input_l1_cuda(pred, target) -> torch.Tensor:
+    _check_img(pred, "vgg_input_l1 pred")
+    _check_img(target, "vgg_input_l1 target")
+    if pred.shape != target.shape:
+        raise ValueError("vgg_input_l1: pred / target shapes differ")
+    pred, target = pred.contiguous(), target.contiguous()
+    B, _, H, W = pred.shape
+    part = torch.empty((N.lib().vub_vgg_input_l1_partials(B, H, W),), dtype=torch.float32, device=pred.device)
+    N.check(_launch("vgg_input_l1", N.lib().vub_vgg_input_l1, pred.data_ptr(), target.data_ptr(), B, H, W,
+                    part.data_ptr(), _stream(), bytes_=float(pred.numel() * 8)), "vub_vgg_input_l1")
+    return part
+
+
+def _vgg_input_bwd_cuda(pred, target, d_xn, g0, scale0) -> torch.Tensor:
+    _check_img(pred, "vgg_input_bwd pred")
+    pred, target = pred.contiguous(), target.contiguous()
+    B, _, H, W = pred.shape
+    if d_xn is not None and (d_xn.dtype != torch.bfloat16 or tuple(d_xn.shape) != (B, H, W, 32) or not d_xn.is_contiguous()):
+        raise ValueError("vgg_input_bwd: d_xn must be contiguous NHWC bf16 [B,H,W,32]")
+    if g0 is not None and (g0.dtype != torch.float32 or g0.numel() != 1):
+        raise ValueError("vgg_input_bwd: g0 must be one fp32 value")
+    out = torch.empty_like(pred)
+    N.check(_launch("vgg_input_bwd", N.lib().vub_vgg_input_bwd, pred.data_ptr(), target.data_ptr(), _p(d_xn), _p(g0),
+                    float(scale0), B, H, W, out.data_ptr(), _stream(),
+                    bytes_=float(pred.numel() * 12 + (0 if d_xn is None else d_xn.numel() * 2))), "vub_vgg_input_bwd")
+    return out
+
+
+def _maxpool2_fwd_cuda(x) -> torch.Tensor:
+    _check_act(x, "maxpool2_fwd x")
+    B, H, W, c = x.shape
+    y = torch.empty((B, H // 2, W // 2, c), dtype=torch.bfloat16, device=x.device)
+    N.check(_launch(f"maxpool2 c{c} @{H}x{W}", N.lib().vub_maxpool2_fwd, x.data_ptr(), B, H, W, c, y.data_ptr(), _stream(),
+                    bytes_=float(x.numel() * 2 + y.numel() * 2)), "vub_maxpool2_fwd")
+    return y
+
+
+def _maxpool2_relu_bwd_cuda(x, dy, addend) -> torch.Tensor:
+    _check_act(x, "maxpool2_relu_bwd x")
+    _check_act(dy, "maxpool2_relu_bwd dy")
+    B, H, W, c = x.shape
+    if tuple(dy.shape) != (B, H // 2, W // 2, c):
+        raise ValueError("maxpool2_relu_bwd: dy shape mismatch")
+    if addend is not None:
+        _check_act(addend, "maxpool2_relu_bwd addend")
+        if addend.shape != x.shape:
+            raise ValueError("maxpool2_relu_bwd: addend shape mismatch")
+    dx = torch.empty_like(x)
+    N.check(_launch(f"maxpool2_relu_bwd c{c} @{H}x{W}", N.lib().vub_maxpool2_relu_bwd, x.data_ptr(), dy.data_ptr(),
+                    _p(addend), B, H, W, c, dx.data_ptr(), _stream(),
+                    bytes_=float(x.numel() * 2 * (2 + (addend is not None)) + dy.numel() * 2)), "vub_maxpool2_relu_bwd")
+    return dx
+
+
+def _l1_partial_cuda(pf, tf) -> torch.Tensor:
+    _check_act(pf, "l1_partial pf")
+    _check_act(tf, "l1_partial tf")
+    if pf.shape != tf.shape:
+        raise ValueError("l1_partial: shapes differ")
+    part = torch.empty((N.lib().vub_l1_num_partials(pf.numel()),), dtype=torch.float32, device=pf.device)
+    N.check(_launch("l1_partial", N.lib().vub_l1_partial, pf.data_ptr(), tf.data_ptr(), pf.numel(), part.data_ptr(),
+                    _stream(), bytes_=float(pf.numel() * 4)), "vub_l1_partial")
+    return part
+
+
+def _l1_relu_grad_cuda(pf, tf, g, scale) -> torch.Tensor:
+    _check_act(pf, "l1_relu_grad pf")
+    _check_act(tf, "l1_relu_grad tf")
+    if pf.shape != tf.shape or g.dtype != torch.float32 or g.numel() != 1:
+        raise ValueError("l1_relu_grad: shapes differ / g must be one fp32 value")
+    out = torch.empty_like(pf)
+    N.check(_launch("l1_relu_grad", N.lib().vub_l1_relu_grad, pf.data_ptr(), tf.data_ptr(), pf.numel(), g.data_ptr(),
+                    float(scale), out.data_ptr(), _stream(), bytes_=float(pf.numel() * 6)), "vub_l1_relu_grad")
+    return out
+
+
+_LIB.impl("vgg_normalize", _vgg_normalize_cuda, "CUDA")
+_LIB.impl("vgg_input_l1", _vgg_input_l1_cuda, "CUDA")
+_LIB.impl("vgg_input_bwd", _vgg_input_bwd_cuda, "CUDA")
+_LIB.impl("maxpool2_fwd", _maxpool2_fwd_cuda, "CUDA")
+_LIB.impl("maxpool2_relu_bwd", _maxpool2_relu_bwd_cuda, "CUDA")
+_LIB.impl("l1_partial", _l1_partial_cuda, "CUDA")
+_LIB.impl("l1_relu_grad", _l1_relu_grad_cuda, "CUDA")
 _LIB.impl("latent_sample", _latent_sample_cuda, "CUDA")
 _LIB.impl("space_to_depth", _space_to_depth_cuda, "CUDA")
 _LIB.impl("latent_sample_bwd", _latent_sample_bwd_cuda, "CUDA")
@@ -719,7 +831,10 @@ for _name, _fn in (("conv_fwd", _conv_fwd_cuda), ("frames_to_uint8", _frames_to_
                    ("wn_prep", _wn_prep_cuda), ("stem_fwd", _stem_fwd_cuda), ("latent_fwd", _latent_fwd_cuda),
                    ("nchw_to_nhwc", _nchw_to_nhwc_cuda), ("nhwc_to_nchw", _nhwc_to_nchw_cuda),
                    ("latent_sample", _latent_sample_cuda), ("space_to_depth", _space_to_depth_cuda),
-                   ("latent_sample_bwd", _latent_sample_bwd_cuda)):
+                   ("latent_sample_bwd", _latent_sample_bwd_cuda), ("vgg_normalize", _vgg_normalize_cuda),
+                   ("vgg_input_l1", _vgg_input_l1_cuda), ("vgg_input_bwd", _vgg_input_bwd_cuda),
+                   ("maxpool2_fwd", _maxpool2_fwd_cuda), ("maxpool2_relu_bwd", _maxpool2_relu_bwd_cuda),
+                   ("l1_partial", _l1_partial_cuda), ("l1_relu_grad", _l1_relu_grad_cuda)):
     _ops.register(_name, _fn)
 
 
@@ -729,12 +844,13 @@ for _name, _fn in (("conv_fwd", _conv_fwd_cuda), ("frames_to_uint8", _frames_to_
 def conv_fwd(x: Sequence[torch.Tensor], w, scale, shift, *, ksize: int, stride: int = 1,
              residual: Optional[torch.Tensor] = None, want_raw: bool = True, want_elu: bool = True,
              d2s: bool = False, cout_valid: Optional[int] = None, stages: int = 0, elu_in: int = 0,
-             w_tiled: Optional[torch.Tensor] = None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+             w_tiled: Optional[torch.Tensor] = None,
+             relu: bool = False) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """bf16 NHWC outputs: returns (raw or None, elu or None).  ``elu_in``: bit s set = source s is a RAW
     activation to which the kernel applies ELU while loading (only where :func:`elu_in_ok`)."""
     cv = w.shape[0] if cout_valid is None else cout_valid
     outs = _ops.conv_fwd(x[0], x[1] if len(x) > 1 else None, w, scale, shift, residual, ksize, stride, cv,
-                         want_raw, want_elu, d2s, F32_NONE, stages, elu_in, w_tiled)
+                         want_raw, want_elu, d2s, F32_NONE, stages, elu_in, w_tiled, relu)
     it = iter(outs)
     raw = next(it) if want_raw else None
     elu = next(it) if want_elu else None
@@ -839,14 +955,14 @@ def latent_bwd32(logstd, eps, d_mu, d_ls, dz) -> torch.Tensor:
 
 # ---- training half ------------------------------------------------------------------------------
 def conv_dgrad(dy, wd, dx, *, mask=(None, None), addend=(None, None), addend2=(None, None), ksize: int,
-               stride: int = 1, d2s: bool = False, wd_tiled: Optional[torch.Tensor] = None) -> None:
+               stride: int = 1, d2s: bool = False, wd_tiled: Optional[torch.Tensor] = None, relu: bool = False) -> None:
     """``dx[s] = ELU'(mask[s]) * dgrad_s + addend[s] + addend2[s]`` for every source (in place into dx)."""
     dx = list(dx) + [None] * (2 - len(dx))
     mask = list(mask) + [None] * (2 - len(mask))
     addend = list(addend) + [None] * (2 - len(addend))
     addend2 = list(addend2) + [None] * (2 - len(addend2))
     _ops.conv_dgrad(dy, wd, dx[0], dx[1], mask[0], mask[1], addend[0], addend[1], addend2[0], addend2[1], ksize,
-                    stride, d2s, wd_tiled)
+                    stride, d2s, wd_tiled, relu)
 
 
 def conv_wgrad(dy, x, gt, dy_sum, *, ksize: int, stride: int = 1, d2s: bool = False) -> None:
@@ -903,3 +1019,34 @@ def space_to_depth(x, *, group_major: bool = False, inverse: bool = False, want_
         return None, None
     it = iter(outs)
     return (next(it) if want_copy else None), (next(it) if want_elu else None)
+
+
+# ---- VGG19 perceptual loss ------------------------------------------------------------------------
+def vgg_normalize(x, want_nhwc: bool = True, want_nchw: bool = False):
+    outs = _ops.vgg_normalize(x, want_nhwc, want_nchw)
+    it = iter(outs)
+    return (next(it) if want_nhwc else None), (next(it) if want_nchw else None)
+
+
+def vgg_input_l1(pred, target) -> torch.Tensor:
+    return _ops.vgg_input_l1(pred, target)
+
+
+def vgg_input_bwd(pred, target, d_xn, g0, scale0: float) -> torch.Tensor:
+    return _ops.vgg_input_bwd(pred, target, d_xn, g0, scale0)
+
+
+def maxpool2_fwd(x) -> torch.Tensor:
+    return _ops.maxpool2_fwd(x)
+
+
+def maxpool2_relu_bwd(x, dy, addend=None) -> torch.Tensor:
+    return _ops.maxpool2_relu_bwd(x, dy, addend)
+
+
+def l1_partial(pf, tf) -> torch.Tensor:
+    return _ops.l1_partial(pf, tf)
+
+
+def l1_relu_grad(pf, tf, g, scale: float) -> torch.Tensor:
+    return _ops.l1_relu_grad(pf, tf, g, scale)
