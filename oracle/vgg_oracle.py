@@ -58,18 +58,49 @@ def det_vgg_state_dict() -> Dict[str, torch.Tensor]:
     return sd
 
 
-def perceptual_features(sd: Dict[str, torch.Tensor], x: torch.Tensor) -> Dict[str, torch.Tensor]:
-    """PerceptualVGG.forward — models/imagenet_pretrained.py:45-61 (only the layers up to the last tap)."""
+class _RoundBF16(torch.autograd.Function):
+    """Value AND gradient rounded to bf16: what storing an activation / its gradient as bf16 does."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
+def perceptual_features(sd: Dict[str, torch.Tensor], x: torch.Tensor, bf16_model=False) -> Dict[str, torch.Tensor]:
+    """PerceptualVGG.forward — models/imagenet_pretrained.py:45-61 (only the layers up to the last tap).
+
+    ``bf16_model``: the same graph with the storage precision of a bf16 tensor-core evaluation — weights, the
+    normalised image and every ReLU output (and their gradients) rounded to bf16, fp32 accumulation.  ``True`` rounds
+    the weights as ``bf16(w)``; ``"wn"`` as ``bf16(w / ||w||) * ||w||`` per output channel (a plain conv pushed through
+    a weight-norm representation with an fp32 scale, which is what the product's conv kernels consume).  The L1 terms
+    make the GRADIENT a sign function of feature differences, so ANY two bf16 evaluations that round differently —
+    these two models included — differ from each other and from the fp32 graph by O(0.2) in relative L2 (gradients
+    only; the loss values agree to 1e-3).  A bf16 implementation is therefore checked against the model that rounds
+    where it rounds."""
     x = (x + 1.0) / 2.0
     x = (x - MEAN) / STD
     out = {"input": x}
+    if bf16_model:
+        x = _RoundBF16.apply(x)
     for idx, kind, _, _ in feature_layout():
         if idx > max(TARGET_LAYERS):
             break
         if kind == "conv":
-            x = F.conv2d(x, sd[f"{idx}.weight"], sd[f"{idx}.bias"], padding=1)
+            w = sd[f"{idx}.weight"]
+            if bf16_model == "wn":
+                n = w.reshape(w.shape[0], -1).norm(dim=1).reshape(-1, 1, 1, 1)
+                w = (w / n).bfloat16().float() * n
+            elif bf16_model:
+                w = w.bfloat16().float()
+            x = F.conv2d(x, w, sd[f"{idx}.bias"], padding=1)
         elif kind == "relu":
             x = F.relu(x)
+            if bf16_model:
+                x = _RoundBF16.apply(x)
         else:
             x = F.max_pool2d(x, kernel_size=2, stride=2)
         if idx in TARGET_LAYERS:
@@ -78,9 +109,9 @@ def perceptual_features(sd: Dict[str, torch.Tensor], x: torch.Tensor) -> Dict[st
 
 
 def vgg_loss(sd: Dict[str, torch.Tensor], target: torch.Tensor, pred: torch.Tensor,
-             loss_weights: Sequence[float]) -> Dict[str, torch.Tensor]:
+             loss_weights: Sequence[float], bf16_model=False) -> Dict[str, torch.Tensor]:
     """lib/losses.py:81-104 (the ``weights is None`` branch, the only one a shipped caller takes)."""
-    tf = perceptual_features(sd, target)
-    pf = perceptual_features(sd, pred)
+    tf = perceptual_features(sd, target, bf16_model)
+    pf = perceptual_features(sd, pred, bf16_model)
     return {name: loss_weights[i] * torch.mean(torch.abs(tf[name] - pf[name])).unsqueeze(dim=-1)
             for i, name in enumerate(TAP_NAMES)}
