@@ -389,6 +389,82 @@ def run_train_section(args, device, world, rank, barrier, peaks):
     return out
 
 
+def run_train_vgg(device, steps: int, peaks) -> dict:
+    """The reference's REAL objective (experiments/shape_and_pose_net.py:388-432): likelihood = ll_weight * sum of the
+    VGG19 perceptual terms (lib/losses.py:81-119) + kl_weight * KL, on the D256 training workload (batch 32), as one
+    CUDA-graph step: VUnet forward, VGG19 features of target and prediction, L1 terms, VGG data gradients, VUnet
+    backward, FusedAdam.  The VGG weights are random (ImageNet weights do not exist offline): timing only."""
+    import bdvs_b200 as B
+    import vunet_oracle as O
+    from bdvs_b200 import ops
+    from bdvs_b200.profiler import KernelProfiler
+    from torchvision.models import vgg19
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = B.VunetAlter(**D256)
+    model.load_state_dict(O.det_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}))
+    model = model.to(device).train()
+    torch.manual_seed(7)
+    vgg = B.PerceptualVGG(vgg19(weights=None).eval(), [1.0] * 6).to(device).eval()
+    opt = B.FusedAdam([{"params": list(getattr(model, n).parameters()), "name": n} for n in ("eu", "ed", "du", "dd")],
+                      lr=1e-4, betas=(0.5, 0.9), model=model)
+    Bt = TRAIN_BATCH_PER_GPU
+    g = torch.Generator(device=device).manual_seed(4321)
+    x = torch.rand(Bt, 30, 64, 64, device=device, generator=g) * 2 - 1
+    c = torch.rand(Bt, 3, 256, 256, device=device, generator=g) * 2 - 1
+    target = torch.rand(Bt, 3, 256, 256, device=device, generator=g) * 2 - 1
+
+    def loss_fn(imgs, means, logstds, tt):
+        ll = B.vgg_loss(vgg, tt, imgs)
+        return 5.0 * torch.stack([ll[k] for k in ll]).sum() + 1e-3 * B.compute_kl_with_prior(means, logstds)
+
+    n0 = ops.LAUNCHES
+    graphed = B.GraphedTrainStep(model, opt, loss_fn, x, c, target)
+    launches_per_step = (ops.LAUNCHES - n0) // 4
+    for _ in range(2):
+        graphed(x, c, target)
+    torch.cuda.synchronize()
+    K = max(5, steps // 2)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        loss = graphed(x, c, target)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    # one instrumented eager step of the loss alone (single stream): per-family time of the VGG part
+    imgs = (torch.rand(Bt, 3, 256, 256, device=device, generator=g) * 2 - 1).requires_grad_(True)
+    for _ in range(2):
+        torch.stack(list(B.vgg_loss(vgg, target, imgs).values())).sum().backward()
+    with KernelProfiler() as kp:
+        torch.stack(list(B.vgg_loss(vgg, target, imgs).values())).sum().backward()
+    prof = kp.summary()
+    tot = sum(r["ms"] for r in prof.values())
+    agg = {}
+    for name, r in prof.items():
+        fam = name.split(" ")[0].split("<")[0]
+        a = agg.setdefault(fam, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        for k2 in a:
+            a[k2] += r[k2]
+    fams = [{"family": f, "launches": a["launches"], "ms": round(a["ms"], 3), "share": round(a["ms"] / tot, 4),
+             "tflops": round(a["flops"] / (a["ms"] * 1e-3) / 1e12, 1) if a["ms"] > 0 else 0.0,
+             "gbs": round(a["bytes"] / (a["ms"] * 1e-3) / 1e9, 1) if a["ms"] > 0 else 0.0}
+            for f, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])]
+    vgg_gflop = 3 * 48.4   # conv1_1 .. conv5_2 forward on target and prediction + data gradient, per sample
+    gflop = TRAIN_GFLOP_PER_SAMPLE + vgg_gflop
+    out = {"metric": "VUnet 256x256 training throughput with the VGG19 perceptual loss (fwd+bwd+Adam)",
+           "value": Bt / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "steps": K, "samples_per_step": Bt,
+           "per_gpu": True, "cuda_graph": True, "gpu_launches_per_step": launches_per_step,
+           "algorithmic_gflop_per_sample": round(gflop, 1), "conv_tflops": round(gflop * Bt / ms, 1),
+           "frac_tensor_peak_sustained": round(gflop * Bt / ms / peaks["bf16_tflops_sustained"], 4),
+           "vgg_loss_alone": {"sum_kernel_ms": round(tot, 3), "tflops": round(vgg_gflop * Bt / tot, 1), "families": fams},
+           "loss": float(loss.detach()),
+           "note": "random VGG19 weights (no ImageNet weights offline); single GPU (the VGG part has no collective)"}
+    del model, opt, graphed, vgg
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_vunet_org(device, frames: int, steps: int, peaks) -> dict:
     """``VunetOrg.transfer`` (models/vunets.py:102-110) at the H256 geometry, ``frames`` frames per step, CUDA-graph
     replay timed with CUDA events on this rank; plus the share of the step the prior's 512 / 1024-channel convs take
@@ -795,6 +871,12 @@ def run_ours(args):
         roofline["vunet_org"] = run_vunet_org(device, Bf, K, peaks)
     except Exception as exc:  # secondary number: never take the headline down
         roofline["vunet_org"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    # ---- the training step with the reference's real likelihood, the VGG19 perceptual loss ----
+    if not args.no_train:
+        try:
+            roofline["train_vgg"] = run_train_vgg(device, K, peaks)
+        except Exception as exc:  # secondary number: never take the headline down
+            roofline["train_vgg"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     roofline["whole_step"] = whole
     roofline["sequence"] = sequence
     roofline["pose_rendering"] = pose

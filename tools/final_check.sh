@@ -22,6 +22,7 @@ try:
     print("train", t.get("value"), t.get("ms_per_step"), t.get("worst_family"))
     print("vunet_org", b["roofline"].get("vunet_org"))
     print("sequence", b["roofline"].get("sequence"))
+    print("train_vgg", b["roofline"].get("train_vgg"))
     for k in b["kernels"][:12]:
         print(k["kernel"], k["launches"], k["ms"], k["share"], k["tflops"], k["gbs"])
 except Exception as e:
