@@ -345,3 +345,46 @@ def test_sequence_split_equals_transfer(golden):
     assert rel(out, ref) < 5e-2  # different noise draws inside the graph: same distribution, not the same bits
     ss = SequenceSynthesizer(m, 1, 4)
     assert ss(x.cuda(), c4.cuda()).shape == ref.shape
+
+
+def test_graphed_train_step_with_fused_adam(golden):
+    """bdvs_b200.FusedAdam + GraphedTrainStep on VunetOrg (loss_fn receives (imgs, qs, ps, target)): the replayed
+    graph equals the same steps issued launch by launch."""
+    import copy
+    import bdvs_b200 as B
+    fx = golden("org_tiny3")
+    cfg = fx["config"]
+    a, sd = build(cfg)
+    a.train()
+    b = copy.deepcopy(a)
+    bs = 4
+    x, c, eps, _ = O.make_inputs(cfg, bs)
+    target = O.det_uniform("target", (bs, 3, cfg["spatial_size"], cfg["spatial_size"])).cuda()
+    x, c, eps = x.cuda(), c.cuda(), cuda(eps)
+
+    def loss_fn(imgs, qs, ps, tgt):
+        return ((imgs - tgt) ** 2).mean() + 1e-3 * B.compute_kl_loss(ps, qs)
+
+    def groups(m):
+        return [{"params": list(getattr(m, n).parameters()), "name": n} for n in ("eu", "ed", "du", "dd")]
+
+    opt_a = B.FusedAdam(groups(a), lr=1e-4, betas=(0.5, 0.9), model=a)
+    opt_b = B.FusedAdam(groups(b), lr=1e-4, betas=(0.5, 0.9), model=b)
+    losses_a = []
+    for _ in range(3):
+        imgs, qs, ps, _acts = a(x, c, eps=eps)
+        loss = loss_fn(imgs, qs, ps, target)
+        opt_a.zero_grad()
+        loss.backward()
+        opt_a.step()
+        losses_a.append(float(loss))
+    step = B.GraphedTrainStep(b, opt_b, loss_fn, x, c, target, eps=eps)
+    losses_b = [float(step(x, c, target)) for _ in range(3)]
+    for la, lb in zip(losses_a, losses_b):
+        assert abs(la - lb) <= 2e-3 * abs(la), (losses_a, losses_b)
+    assert losses_b[-1] < losses_b[0]
+    for (n, pa), pb in zip(a.named_parameters(), b.parameters()):
+        torch.testing.assert_close(pa, pb, rtol=1e-3, atol=1e-4, msg=n)
+    # the prior convs were stepped too
+    k = "dd.auto_lp.l_1.2.conv.weight_v"
+    assert float((dict(b.named_parameters())[k].detach().cpu() - sd[k]).abs().max()) > 1e-5

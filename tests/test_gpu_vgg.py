@@ -229,3 +229,33 @@ def test_training_step_through_vunet_matches_oracle(golden):
           f"rel-L2 {err:.3e}")
     assert abs(float(loss) - float(o_loss)) < 1e-2 * abs(float(o_loss))
     assert err < 0.2  # see the module docstring: sign noise of the L1 terms, not the schedule
+
+
+def test_vgg_loss_inside_a_captured_training_step(golden):
+    """The whole step — VUnet forward, vgg_loss (two feature passes + backward), VUnet backward, FusedAdam — replayed
+    from one CUDA graph (the upstream gradients of the loss terms stay in device memory: no host synchronisation)."""
+    import bdvs_b200 as B
+    fx = golden("tiny3")
+    cfg = {k: v for k, v in fx["config"].items() if k != "batch"}
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = B.VunetAlter(**cfg)
+    net.load_state_dict(O.det_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}))
+    net = net.cuda().train()
+    m, _ = make([1.0] * 6)
+    bs = 2
+    x, c, eps, _ = O.make_inputs(fx["config"], bs)
+    target = O.det_uniform("target", (bs, 3, cfg["spatial_size"], cfg["spatial_size"])).cuda()
+    eps = [e.cuda() for e in eps]
+
+    def loss_fn(imgs, means, logstds, tgt):
+        ll = B.vgg_loss(m, tgt, imgs)
+        return 5.0 * torch.stack([ll[k] for k in ll]).sum() + 1e-3 * B.compute_kl_with_prior(means, logstds)
+
+    opt = B.FusedAdam([{"params": list(getattr(net, n).parameters()), "name": n} for n in ("eu", "ed", "du", "dd")],
+                      lr=1e-4, betas=(0.5, 0.9), model=net)
+    with torch.no_grad():
+        first = float(loss_fn(*net(x.cuda(), c.cuda(), eps=eps)[:3], target))
+    step = B.GraphedTrainStep(net, opt, loss_fn, x.cuda(), c.cuda(), target, eps=eps)
+    losses = [float(step(x.cuda(), c.cuda(), target)) for _ in range(4)]
+    assert abs(losses[0] - first) < 1e-3 * abs(first)     # the first replay starts from the untouched parameters
+    assert losses[-1] < losses[0]
