@@ -392,23 +392,23 @@ def _declare(lib: C.CDLL) -> None:
     lib.vub_latent_sample.restype = C.c_int
     lib.vub_latent_sample.argtypes = [fp, fp, i32, i32, i32, i32, i32, i32, i32, fp, fp, vp, vp, vp, i32, vp]
     lib.vub_vgg_normalize.restype = C.c_int
-    lib.vub_vgg_normalize.argtypes = [fp, i32, i32, i32, vp, fp, vp]
+    lib.vub_vgg_normalize.argtypes = [fp, i32, i32, i32, vp, fp, i32, vp]
     lib.vub_vgg_input_l1_partials.restype = i32
     lib.vub_vgg_input_l1_partials.argtypes = [i32, i32, i32]
     lib.vub_vgg_input_l1.restype = C.c_int
     lib.vub_vgg_input_l1.argtypes = [fp, fp, i32, i32, i32, fp, vp]
     lib.vub_vgg_input_bwd.restype = C.c_int
-    lib.vub_vgg_input_bwd.argtypes = [fp, fp, vp, fp, C.c_float, i32, i32, i32, fp, vp]
+    lib.vub_vgg_input_bwd.argtypes = [fp, fp, vp, fp, C.c_float, i32, i32, i32, fp, i32, vp]
     lib.vub_maxpool2_fwd.restype = C.c_int
-    lib.vub_maxpool2_fwd.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+    lib.vub_maxpool2_fwd.argtypes = [vp, i32, i32, i32, i32, vp, i32, vp]
     lib.vub_maxpool2_relu_bwd.restype = C.c_int
-    lib.vub_maxpool2_relu_bwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
+    lib.vub_maxpool2_relu_bwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, i32, vp]
     lib.vub_l1_num_partials.restype = i32
     lib.vub_l1_num_partials.argtypes = [C.c_int64]
     lib.vub_l1_partial.restype = C.c_int
-    lib.vub_l1_partial.argtypes = [vp, vp, C.c_int64, fp, vp]
+    lib.vub_l1_partial.argtypes = [vp, vp, C.c_int64, fp, i32, vp]
     lib.vub_l1_relu_grad.restype = C.c_int
-    lib.vub_l1_relu_grad.argtypes = [vp, vp, C.c_int64, fp, C.c_float, vp, vp]
+    lib.vub_l1_relu_grad.argtypes = [vp, vp, C.c_int64, fp, C.c_float, vp, i32, vp]
     lib.vub_latent_sample_bwd.restype = C.c_int
     lib.vub_latent_sample_bwd.argtypes = [fp, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]
     lib.vub_space_to_depth.restype = C.c_int

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(kF32Threads) conv_f32_kernel(const ConvF32Para
       }
       if (p.residual != nullptr) y += p.residual[o];
       if (p.out_raw != nullptr) p.out_raw[o] = y;
-      if (p.out_elu != nullptr) p.out_elu[o] = y > 0.f ? y : expm1f(y);
+      if (p.out_elu != nullptr) p.out_elu[o] = (p.flags & VUB_CONV_RELU) ? fmaxf(y, 0.f) : (y > 0.f ? y : expm1f(y));
     }
   }
 }
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256) conv_dgrad_f32_kernel(const DgradF32Param
   }
   if (p.mask_elu[s] != nullptr) {
     const float ev = p.mask_elu[s][e];
-    acc *= ev > 0.f ? 1.0f : ev + 1.0f;
+    acc *= ev > 0.f ? 1.0f : ((p.flags & VUB_CONV_RELU) ? 0.0f : ev + 1.0f);
   }
   if (p.addend[s] != nullptr) acc += p.addend[s][e];
   if (p.addend2[s] != nullptr) acc += p.addend2[s][e];

@@ -36,12 +36,13 @@ _LIB.define("frames_to_uint8(Tensor imgs) -> Tensor")
 # ---- fp32 validation path -----------------------------------------------------------------------
 _LIB.define(
     "conv_fwd32(Tensor x0, Tensor? x1, Tensor w, Tensor scale, Tensor shift, Tensor? residual, int cout, int ksize, "
-    "int stride, bool want_raw, bool want_elu, bool d2s, bool nchw) -> Tensor[]"
+    "int stride, bool want_raw, bool want_elu, bool d2s, bool nchw, bool relu=False) -> Tensor[]"
 )
 _LIB.define("nchw_to_nhwc32(Tensor x, bool want_raw, bool want_elu) -> Tensor[]")
 _LIB.define(
     "conv_dgrad32(Tensor dy, Tensor w, Tensor scale, Tensor(a!) dx0, Tensor(b!)? dx1, Tensor? mask0, Tensor? mask1, "
-    "Tensor? add0, Tensor? add1, Tensor? add20, Tensor? add21, int cout, int ksize, int stride, bool d2s) -> ()"
+    "Tensor? add0, Tensor? add1, Tensor? add20, Tensor? add21, int cout, int ksize, int stride, bool d2s, "
+    "bool relu=False) -> ()"
 )
 _LIB.define(
     "conv_wgrad32(Tensor dy, Tensor x0, Tensor? x1, Tensor(a!) gt, Tensor(b!) dy_sum, int cout, int ksize, int stride, "
@@ -68,7 +69,7 @@ _LIB.define("stem_bwd(Tensor x, Tensor dy, Tensor(a!) gt, Tensor(b!) dy_sum) -> 
 _LIB.define("latent_bwd(Tensor logstd, Tensor? eps, Tensor? d_mu, Tensor? d_ls, Tensor? dz) -> Tensor")
 _LIB.define("nchw_to_nhwc_pad(Tensor x, int c_pad) -> Tensor")
 # ---- VGG19 perceptual loss: memory-bound pieces around the conv kernels ------------------------------
-_LIB.define("vgg_normalize(Tensor x, bool want_nhwc, bool want_nchw) -> Tensor[]")
+_LIB.define("vgg_normalize(Tensor x, bool want_nhwc, bool want_nchw, bool f32=False) -> Tensor[]")
 _LIB.define("vgg_input_l1(Tensor pred, Tensor target) -> Tensor")
 _LIB.define("vgg_input_bwd(Tensor pred, Tensor target, Tensor? d_xn, Tensor? g0, float scale0) -> Tensor")
 _LIB.define("maxpool2_fwd(Tensor x) -> Tensor")
@@ -436,7 +437,7 @@ def _nchw_to_nhwc_pad_cuda(x, c_pad) -> torch.Tensor:
     return out
 
 
-def _conv_fwd32_cuda(x0, x1, w, scale, shift, residual, cout, ksize, stride, want_raw, want_elu, d2s, nchw):
+def _conv_fwd32_cuda(x0, x1, w, scale, shift, residual, cout, ksize, stride, want_raw, want_elu, d2s, nchw, relu=False):
     for t in (x0, x1, residual):
         if t is not None and (t.dtype != torch.float32 or t.dim() != 4 or not t.is_contiguous()):
             raise ValueError("conv_fwd32: activations must be contiguous NHWC fp32")
@@ -460,7 +461,7 @@ def _conv_fwd32_cuda(x0, x1, w, scale, shift, residual, cout, ksize, stride, wan
         outs.append(elu)
     d.nsrc, d.c_src, d.batch, d.hin, d.win, d.cout = nsrc, c_src, B, H, W, cout
     d.w_pitch, d.ksize, d.stride = w.stride(0), ksize, stride
-    d.flags = (N.CONV_D2S if d2s else 0) | (N.CONV_F32_NCHW if nchw else 0)
+    d.flags = (N.CONV_D2S if d2s else 0) | (N.CONV_F32_NCHW if nchw else 0) | (N.CONV_RELU if relu else 0)
     N.check(_launch(f"conv_fwd32 {nsrc}x{c_src}->{cout} k{ksize} s{stride} @{H}x{W}", N.lib().vub_conv_fwd_f32, C.byref(d),
                     _stream(), flops=2.0 * B * Ho * Wo * cout * w.shape[0]), "vub_conv_fwd_f32")
     return outs
@@ -483,7 +484,8 @@ def _check_act32(t: torch.Tensor, name: str) -> None:
         raise ValueError(f"{name}: expected contiguous NHWC fp32 [B,H,W,C], got {t.dtype} {tuple(t.shape)}")
 
 
-def _conv_dgrad32_cuda(dy, w, scale, dx0, dx1, mask0, mask1, add0, add1, add20, add21, cout, ksize, stride, d2s) -> None:
+def _conv_dgrad32_cuda(dy, w, scale, dx0, dx1, mask0, mask1, add0, add1, add20, add21, cout, ksize, stride, d2s,
+                       relu=False) -> None:
     _check_act32(dy, "conv_dgrad32 dy")
     _check_act32(dx0, "conv_dgrad32 dx0")
     B, H, W, c_src = dx0.shape
@@ -505,6 +507,8 @@ def _conv_dgrad32_cuda(dy, w, scale, dx0, dx1, mask0, mask1, add0, add1, add20, 
     d.addend2[0], d.addend2[1] = _p(add20), _p(add21)
     d.nsrc, d.c_src, d.batch, d.hin, d.win, d.cout = nsrc, c_src, B, H, W, cout
     d.w_pitch, d.ksize, d.stride, d.flags = w.stride(0), ksize, stride, (N.CONV_D2S if d2s else 0)
+    if relu:
+        d.flags |= N.CONV_RELU
     N.check(_launch(f"conv_dgrad32 {nsrc}x{c_src}<-{cout} k{ksize} s{stride} @{H}x{W}", N.lib().vub_conv_dgrad_f32,
                     C.byref(d), _stream(), flops=2.0 * B * Ho * Wo * cout * w.shape[0]), "vub_conv_dgrad_f32")
 
@@ -666,13 +670,20 @@ def _check_img(t: torch.Tensor, name: str) -> None:
         raise ValueError(f"{name}: expected NCHW fp32 with 3 channels, got {t.dtype} {tuple(t.shape)}")
 
 
-def _vgg_normalize_cuda(x, want_nhwc, want_nchw) -> List[torch.Tensor]:
+def _feat_f32(t: torch.Tensor, name: str) -> int:
+    """Feature maps are contiguous NHWC bf16, or fp32 in the validation mode: returns the C ABI's f32_acts flag."""
+    if t.dtype not in (torch.bfloat16, torch.float32) or t.dim() != 4 or not t.is_contiguous():
+        raise ValueError(f"{name}: expected contiguous NHWC bf16 / fp32 [B,H,W,C], got {t.dtype} {tuple(t.shape)}")
+    return 1 if t.dtype == torch.float32 else 0
+
+
+def _vgg_normalize_cuda(x, want_nhwc, want_nchw, f32=False) -> List[torch.Tensor]:
     _check_img(x, "vgg_normalize x")
     x = x.contiguous()
     B, _, H, W = x.shape
-    nhwc = torch.empty((B, H, W, 32), dtype=torch.bfloat16, device=x.device) if want_nhwc else None
+    nhwc = torch.empty((B, H, W, 32), dtype=torch.float32 if f32 else torch.bfloat16, device=x.device) if want_nhwc else None
     nchw = torch.empty_like(x) if want_nchw else None
-    N.check(_launch("vgg_normalize", N.lib().vub_vgg_normalize, x.data_ptr(), B, H, W, _p(nhwc), _p(nchw), _stream(),
+    N.check(_launch("vgg_normalize", N.lib().vub_vgg_normalize, x.data_ptr(), B, H, W, _p(nhwc), _p(nchw), int(f32), _stream(),
                     bytes_=float(x.numel() * 4 + (B * H * W * 64 if want_nhwc else 0) + (x.numel() * 4 if want_nchw else 0))),
             "vub_vgg_normalize")
     return [t for t in (nhwc, nchw) if t is not None]
@@ -695,62 +706,62 @@ def _vgg_input_bwd_cuda(pred, target, d_xn, g0, scale0) -> torch.Tensor:
     _check_img(pred, "vgg_input_bwd pred")
     pred, target = pred.contiguous(), target.contiguous()
     B, _, H, W = pred.shape
-    if d_xn is not None and (d_xn.dtype != torch.bfloat16 or tuple(d_xn.shape) != (B, H, W, 32) or not d_xn.is_contiguous()):
-        raise ValueError("vgg_input_bwd: d_xn must be contiguous NHWC bf16 [B,H,W,32]")
+    f32 = 0
+    if d_xn is not None:
+        f32 = _feat_f32(d_xn, "vgg_input_bwd d_xn")
+        if tuple(d_xn.shape) != (B, H, W, 32):
+            raise ValueError("vgg_input_bwd: d_xn must be [B,H,W,32]")
     if g0 is not None and (g0.dtype != torch.float32 or g0.numel() != 1):
         raise ValueError("vgg_input_bwd: g0 must be one fp32 value")
     out = torch.empty_like(pred)
     N.check(_launch("vgg_input_bwd", N.lib().vub_vgg_input_bwd, pred.data_ptr(), target.data_ptr(), _p(d_xn), _p(g0),
-                    float(scale0), B, H, W, out.data_ptr(), _stream(),
+                    float(scale0), B, H, W, out.data_ptr(), f32, _stream(),
                     bytes_=float(pred.numel() * 12 + (0 if d_xn is None else d_xn.numel() * 2))), "vub_vgg_input_bwd")
     return out
 
 
 def _maxpool2_fwd_cuda(x) -> torch.Tensor:
-    _check_act(x, "maxpool2_fwd x")
+    f32 = _feat_f32(x, "maxpool2_fwd x")
     B, H, W, c = x.shape
-    y = torch.empty((B, H // 2, W // 2, c), dtype=torch.bfloat16, device=x.device)
-    N.check(_launch(f"maxpool2 c{c} @{H}x{W}", N.lib().vub_maxpool2_fwd, x.data_ptr(), B, H, W, c, y.data_ptr(), _stream(),
-                    bytes_=float(x.numel() * 2 + y.numel() * 2)), "vub_maxpool2_fwd")
+    y = torch.empty((B, H // 2, W // 2, c), dtype=x.dtype, device=x.device)
+    N.check(_launch(f"maxpool2 c{c} @{H}x{W}", N.lib().vub_maxpool2_fwd, x.data_ptr(), B, H, W, c, y.data_ptr(), f32,
+                    _stream(), bytes_=float((x.numel() + y.numel()) * x.element_size())), "vub_maxpool2_fwd")
     return y
 
 
 def _maxpool2_relu_bwd_cuda(x, dy, addend) -> torch.Tensor:
-    _check_act(x, "maxpool2_relu_bwd x")
-    _check_act(dy, "maxpool2_relu_bwd dy")
+    f32 = _feat_f32(x, "maxpool2_relu_bwd x")
     B, H, W, c = x.shape
-    if tuple(dy.shape) != (B, H // 2, W // 2, c):
-        raise ValueError("maxpool2_relu_bwd: dy shape mismatch")
-    if addend is not None:
-        _check_act(addend, "maxpool2_relu_bwd addend")
-        if addend.shape != x.shape:
-            raise ValueError("maxpool2_relu_bwd: addend shape mismatch")
+    if _feat_f32(dy, "maxpool2_relu_bwd dy") != f32 or tuple(dy.shape) != (B, H // 2, W // 2, c):
+        raise ValueError("maxpool2_relu_bwd: dy shape / dtype mismatch")
+    if addend is not None and (_feat_f32(addend, "maxpool2_relu_bwd addend") != f32 or addend.shape != x.shape):
+        raise ValueError("maxpool2_relu_bwd: addend shape / dtype mismatch")
     dx = torch.empty_like(x)
+    es = x.element_size()
     N.check(_launch(f"maxpool2_relu_bwd c{c} @{H}x{W}", N.lib().vub_maxpool2_relu_bwd, x.data_ptr(), dy.data_ptr(),
-                    _p(addend), B, H, W, c, dx.data_ptr(), _stream(),
-                    bytes_=float(x.numel() * 2 * (2 + (addend is not None)) + dy.numel() * 2)), "vub_maxpool2_relu_bwd")
+                    _p(addend), B, H, W, c, dx.data_ptr(), f32, _stream(),
+                    bytes_=float(x.numel() * es * (2 + (addend is not None)) + dy.numel() * es)), "vub_maxpool2_relu_bwd")
     return dx
 
 
 def _l1_partial_cuda(pf, tf) -> torch.Tensor:
-    _check_act(pf, "l1_partial pf")
-    _check_act(tf, "l1_partial tf")
-    if pf.shape != tf.shape:
-        raise ValueError("l1_partial: shapes differ")
+    f32 = _feat_f32(pf, "l1_partial pf")
+    if _feat_f32(tf, "l1_partial tf") != f32 or pf.shape != tf.shape:
+        raise ValueError("l1_partial: shapes / dtypes differ")
     part = torch.empty((N.lib().vub_l1_num_partials(pf.numel()),), dtype=torch.float32, device=pf.device)
-    N.check(_launch("l1_partial", N.lib().vub_l1_partial, pf.data_ptr(), tf.data_ptr(), pf.numel(), part.data_ptr(),
-                    _stream(), bytes_=float(pf.numel() * 4)), "vub_l1_partial")
+    N.check(_launch("l1_partial", N.lib().vub_l1_partial, pf.data_ptr(), tf.data_ptr(), pf.numel(), part.data_ptr(), f32,
+                    _stream(), bytes_=float(pf.numel() * 2 * pf.element_size())), "vub_l1_partial")
     return part
 
 
 def _l1_relu_grad_cuda(pf, tf, g, scale) -> torch.Tensor:
-    _check_act(pf, "l1_relu_grad pf")
-    _check_act(tf, "l1_relu_grad tf")
-    if pf.shape != tf.shape or g.dtype != torch.float32 or g.numel() != 1:
-        raise ValueError("l1_relu_grad: shapes differ / g must be one fp32 value")
+    f32 = _feat_f32(pf, "l1_relu_grad pf")
+    if _feat_f32(tf, "l1_relu_grad tf") != f32 or pf.shape != tf.shape or g.dtype != torch.float32 or g.numel() != 1:
+        raise ValueError("l1_relu_grad: shapes / dtypes differ, or g is not one fp32 value")
     out = torch.empty_like(pf)
     N.check(_launch("l1_relu_grad", N.lib().vub_l1_relu_grad, pf.data_ptr(), tf.data_ptr(), pf.numel(), g.data_ptr(),
-                    float(scale), out.data_ptr(), _stream(), bytes_=float(pf.numel() * 6)), "vub_l1_relu_grad")
+                    float(scale), out.data_ptr(), f32, _stream(), bytes_=float(pf.numel() * 3 * pf.element_size())),
+            "vub_l1_relu_grad")
     return out
 
 
@@ -920,10 +931,10 @@ def frames_to_uint8(imgs: torch.Tensor) -> torch.Tensor:
 # ---- fp32 validation path -------------------------------------------------------------------------
 def conv_fwd32(x: Sequence[torch.Tensor], w, scale, shift, *, cout: int, ksize: int, stride: int = 1,
                residual: Optional[torch.Tensor] = None, want_raw: bool = True, want_elu: bool = True,
-               d2s: bool = False, nchw: bool = False):
+               d2s: bool = False, nchw: bool = False, relu: bool = False):
     """fp32 NHWC (or NCHW image) outputs: returns (raw or None, elu or None)."""
     outs = _ops.conv_fwd32(x[0], x[1] if len(x) > 1 else None, w, scale, shift, residual, cout, ksize, stride,
-                           want_raw, want_elu, d2s, nchw)
+                           want_raw, want_elu, d2s, nchw, relu)
     it = iter(outs)
     return (next(it) if want_raw else None), (next(it) if want_elu else None)
 
@@ -935,14 +946,14 @@ def nchw_to_nhwc32(x, want_raw=True, want_elu=True):
 
 
 def conv_dgrad32(dy, w, scale, dx, *, mask=(None, None), addend=(None, None), addend2=(None, None), cout: int,
-                 ksize: int, stride: int = 1, d2s: bool = False) -> None:
+                 ksize: int, stride: int = 1, d2s: bool = False, relu: bool = False) -> None:
     """fp32 validation counterpart of :func:`conv_dgrad` (``w``: the forward fp32 matrix ``v/||v||``)."""
     dx = list(dx) + [None] * (2 - len(dx))
     mask = list(mask) + [None] * (2 - len(mask))
     addend = list(addend) + [None] * (2 - len(addend))
     addend2 = list(addend2) + [None] * (2 - len(addend2))
     _ops.conv_dgrad32(dy, w, scale, dx[0], dx[1], mask[0], mask[1], addend[0], addend[1], addend2[0], addend2[1], cout,
-                      ksize, stride, d2s)
+                      ksize, stride, d2s, relu)
 
 
 def conv_wgrad32(dy, x, gt, dy_sum, *, cout: int, ksize: int, stride: int = 1, d2s: bool = False) -> None:
@@ -1022,8 +1033,8 @@ def space_to_depth(x, *, group_major: bool = False, inverse: bool = False, want_
 
 
 # ---- VGG19 perceptual loss ------------------------------------------------------------------------
-def vgg_normalize(x, want_nhwc: bool = True, want_nchw: bool = False):
-    outs = _ops.vgg_normalize(x, want_nhwc, want_nchw)
+def vgg_normalize(x, want_nhwc: bool = True, want_nchw: bool = False, f32: bool = False):
+    outs = _ops.vgg_normalize(x, want_nhwc, want_nchw, f32)
     it = iter(outs)
     return (next(it) if want_nhwc else None), (next(it) if want_nchw else None)
 

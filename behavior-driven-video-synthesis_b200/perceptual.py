@@ -108,21 +108,45 @@ class PerceptualVGG(nn.Module):
             adapters = [_PlainConv(c, device) for c in convs]
             bank = WeightBank([[a] for a in adapters])
             bank.refresh(with_wd=True)
-            object.__setattr__(self, "_prep", (key, bank, adapters))
+            object.__setattr__(self, "_prep", (key, bank, adapters, None))
+        if getattr(self, "validation_fp32", False):
+            # fp32 validation mode (``with bdvs_b200.fp32_validation(custom_vgg): ...``): the same schedule with fp32
+            # feature maps and fp32 weights on the CUDA-core kernels (vub_conv_fwd_f32 / vub_conv_dgrad_f32 with
+            # VUB_CONV_RELU) -- a checker: loss terms AND d loss / d pred within 1e-4 of the reference
+            if self._prep[3] is None:
+                from .validation import WeightBank32
+                bank32 = WeightBank32(slots=[[a] for a in self._prep[2]])
+                bank32.refresh()
+                object.__setattr__(self, "_prep", self._prep[:3] + (bank32,))
+            return self._prep[3], self._prep[2]
         return self._prep[1], self._prep[2]
+
+    @staticmethod
+    def _conv_relu(bank, cw, h: torch.Tensor) -> torch.Tensor:
+        if bank.precision == "fp32":
+            return ops.conv_fwd32([h], cw.w32, cw.scale, cw.shift, cout=cw.cout, ksize=3, want_raw=False, want_elu=True,
+                                  relu=True)[1]
+        return ops.conv_fwd([h], cw.w, cw.scale, cw.shift, ksize=3, want_raw=False, want_elu=True, relu=True)[1]
+
+    @staticmethod
+    def _conv_relu_dgrad(bank, cw, dy, dx, mask=None, addend=None) -> None:
+        if bank.precision == "fp32":
+            ops.conv_dgrad32(dy, cw.w32, cw.scale, [dx], mask=[mask], addend=[addend], cout=cw.cout, ksize=3, relu=True)
+        else:
+            ops.conv_dgrad(dy, cw.wd, [dx], mask=[mask], addend=[addend], ksize=3, relu=True)
 
     def _run_features(self, x: torch.Tensor, keep: bool):
         """``x``: NCHW fp32 in [-1, 1].  Returns (taps: NHWC bf16 feature maps relu1_2 .. relu5_2, records for the
         backward pass: per plan entry (kind, conv weights, input activation, output activation))."""
         bank, adapters = self._prepared(x.device)
-        h, _ = ops.vgg_normalize(x.float())
+        h, _ = ops.vgg_normalize(x.float(), f32=bank.precision == "fp32")
         taps, recs = [], []
         ci = 0
         for entry in self._plan:
             if entry[0] == "conv":
                 cw = bank.get(adapters[ci])
                 ci += 1
-                _, out = ops.conv_fwd([h], cw.w, cw.scale, cw.shift, ksize=3, want_raw=False, want_elu=True, relu=True)
+                out = self._conv_relu(bank, cw, h)
                 if keep:
                     recs.append(("conv", cw, h, out, entry[2]))
                 if entry[2] is not None:
@@ -145,7 +169,7 @@ class PerceptualVGG(nn.Module):
             taps, _ = self._run_features(x, keep=False)
         out = {"input": xn}
         for name, t in zip(TAP_NAMES[1:], taps):
-            out[name] = t.permute(0, 3, 1, 2)
+            out[name] = t.permute(0, 3, 1, 2)   # NCHW-shaped view of the NHWC feature map (bf16; fp32 in validation mode)
         return out
 
 
@@ -166,6 +190,7 @@ class _VggLossFn(torch.autograd.Function):
         for i, (pf, tf) in enumerate(zip(taps_p, taps_t)):
             losses.append(ops.l1_partial(pf, tf).sum().reshape(1) * (w[i + 1] / pf.numel()))
         ctx.vgg, ctx.w = vgg, w
+        ctx.bank = vgg._prepared(pred_c.device)[0]
         ctx.recs = recs if keep else None
         ctx.taps_t = taps_t if keep else None
         ctx.pred, ctx.target = pred_c, target_c
@@ -202,9 +227,9 @@ class _VggLossFn(torch.autograd.Function):
                     prev = recs[k - 1] if k > 0 else None
                     dx = torch.empty_like(a_in)
                     if prev is not None and prev[0] == "conv":  # a_in = ReLU output of the previous conv
-                        ops.conv_dgrad(d_out, cw.wd, [dx], mask=[a_in], addend=[tap_grad(prev[4], a_in)], ksize=3, relu=True)
+                        PerceptualVGG._conv_relu_dgrad(ctx.bank, cw, d_out, dx, a_in, tap_grad(prev[4], a_in))
                     else:  # a_in = a pooled map, or the normalised image
-                        ops.conv_dgrad(d_out, cw.wd, [dx], ksize=3, relu=True)
+                        PerceptualVGG._conv_relu_dgrad(ctx.bank, cw, d_out, dx)
                     d_in = dx
                 if d_in is None and k > 0 and recs[k - 1][0] == "conv":
                     d_in = tap_grad(recs[k - 1][4], a_in)

@@ -39,20 +39,25 @@ class WeightBank32:
     def __deepcopy__(self, memo):
         return None  # pointer cache of one module tree (see WeightBank.__deepcopy__)
 
-    def __init__(self, root: nn.Module):
+    def __init__(self, root: nn.Module = None, slots=None):
+        """``root``: a module tree (every NormConv2d of it, merged pairs in one slot); or ``slots``: an explicit list of
+        lists of NormConv2d-like objects (perceptual.PerceptualVGG's frozen plain convs)."""
         from .modules import NormConv2d
-        merged_second = {}
-        for m in root.modules():
-            for a, b in getattr(m, "_vub_merged_pairs", ()):
-                merged_second[id(b)] = a
-        self.slots, index = [], {}
-        for m in root.modules():
-            if isinstance(m, NormConv2d) and id(m) not in merged_second:
-                index[id(m)] = len(self.slots)
-                self.slots.append([m])
-        for m in root.modules():
-            if isinstance(m, NormConv2d) and id(m) in merged_second:
-                self.slots[index[id(merged_second[id(m)])]].append(m)
+        if slots is not None:
+            self.slots = [list(sl) for sl in slots]
+        else:
+            merged_second = {}
+            for m in root.modules():
+                for a, b in getattr(m, "_vub_merged_pairs", ()):
+                    merged_second[id(b)] = a
+            self.slots, index = [], {}
+            for m in root.modules():
+                if isinstance(m, NormConv2d) and id(m) not in merged_second:
+                    index[id(m)] = len(self.slots)
+                    self.slots.append([m])
+            for m in root.modules():
+                if isinstance(m, NormConv2d) and id(m) in merged_second:
+                    self.slots[index[id(merged_second[id(m)])]].append(m)
         self.tape = None
         self._key = None
         self._ptr_key = None

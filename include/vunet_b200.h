@@ -466,13 +466,14 @@ int vub_space_to_depth(const void* src, int32_t batch, int32_t h, int32_t w, int
  * VGG19 perceptual loss: `vgg_loss` (lib/losses.py:81-119) over `PerceptualVGG`
  * (models/imagenet_pretrained.py:8-61).  The 3x3 conv + ReLU layers of torchvision's vgg19.features[0:32] run on
  * vub_conv_fwd / vub_conv_dgrad with VUB_CONV_RELU (frozen weights: no weight gradient); these are the memory-bound
- * pieces around them.  Feature maps are NHWC bf16.
+ * pieces around them.  Feature maps are NHWC bf16 — or fp32 when f32_acts != 0: the fp32 validation mode, whose convs
+ * are vub_conv_fwd_f32 / vub_conv_dgrad_f32 with VUB_CONV_RELU.
  * ---------------------------------------------------------------------------------------------- */
 /* x = (x + 1) / 2; x = (x - mean) / std (imagenet_pretrained.py:46-47) of an NCHW fp32 image batch [batch, 3, h, w]:
  * out_nhwc32 = NHWC bf16 padded to 32 channels (conv1_1's input; NULL = skip), out_nchw = the fp32 tensor the module
  * returns as "input" (NULL = skip). */
 int vub_vgg_normalize(const float* x_nchw, int32_t batch, int32_t h, int32_t w, void* out_nhwc32, float* out_nchw,
-                      void* stream);
+                      int32_t f32_acts, void* stream);
 /* "input" tap of vgg_loss: partial[i] = per-block sums of |xn(pred) - xn(target)| (vub_vgg_input_l1_partials blocks;
  * the caller sums them and divides by 3*batch*h*w). */
 int32_t vub_vgg_input_l1_partials(int32_t batch, int32_t h, int32_t w);
@@ -482,20 +483,22 @@ int vub_vgg_input_l1(const float* pred_nchw, const float* target_nchw, int32_t b
  * sign(xn(pred) - xn(target))) / (2 std_c); g0 = upstream gradient of the "input" loss term (device scalar, NULL = 0),
  * scale0 = loss_weights[0] / (3*batch*h*w). */
 int vub_vgg_input_bwd(const float* pred_nchw, const float* target_nchw, const void* d_xn_nhwc32, const float* g0_dev,
-                      float scale0, int32_t batch, int32_t h, int32_t w, float* d_pred_nchw, void* stream);
+                      float scale0, int32_t batch, int32_t h, int32_t w, float* d_pred_nchw, int32_t f32_acts,
+                      void* stream);
 /* nn.MaxPool2d(kernel_size=2, stride=2) on [batch, h, w, c] -> [batch, h/2, w/2, c]. */
-int vub_maxpool2_fwd(const void* x_nhwc, int32_t batch, int32_t h, int32_t w, int32_t c, void* y_nhwc, void* stream);
+int vub_maxpool2_fwd(const void* x_nhwc, int32_t batch, int32_t h, int32_t w, int32_t c, void* y_nhwc, int32_t f32_acts,
+                     void* stream);
 /* Its backward fused with the ReLU in front of it and the tap gradient: dx = (x is the first maximum of its window ?
  * dy : 0) * (x > 0) + addend, x = the ReLU output that was pooled [batch, h, w, c], dy [batch, h/2, w/2, c]. */
 int vub_maxpool2_relu_bwd(const void* x_nhwc, const void* dy_nhwc, const void* addend_nhwc, int32_t batch, int32_t h,
-                          int32_t w, int32_t c, void* dx_nhwc, void* stream);
+                          int32_t w, int32_t c, void* dx_nhwc, int32_t f32_acts, void* stream);
 /* torch.mean(torch.abs(tf - pf)) of a feature tap: per-block partial sums of |pf - tf| (vub_l1_num_partials(numel)
  * of them), and the gradient w.r.t. the pre-activation of pf = ReLU(u): g * scale * sign(pf - tf) * (pf > 0) with the
  * upstream gradient g in device memory and scale = loss_weights[i] / numel. */
 int32_t vub_l1_num_partials(int64_t numel);
-int vub_l1_partial(const void* pf, const void* tf, int64_t numel, float* partial, void* stream);
+int vub_l1_partial(const void* pf, const void* tf, int64_t numel, float* partial, int32_t f32_acts, void* stream);
 int vub_l1_relu_grad(const void* pf, const void* tf, int64_t numel, const float* g_dev, float scale, void* out,
-                     void* stream);
+                     int32_t f32_acts, void* stream);
 
 /*
  * Data-parallel gradient exchange (SURVEY.md 8b `allreduce_bucket(flat, ncclComm, stream)`): in-place all-reduce of

@@ -259,3 +259,69 @@ def test_vgg_loss_inside_a_captured_training_step(golden):
     losses = [float(step(x.cuda(), c.cuda(), target)) for _ in range(4)]
     assert abs(losses[0] - first) < 1e-3 * abs(first)     # the first replay starts from the untouched parameters
     assert losses[-1] < losses[0]
+
+
+FP32_TOL = 1e-4  # BASELINE.json north_star: "1e-4 in an fp32-accumulate validation mode"
+
+
+def test_fp32_validation_mode_matches_reference_to_1e4(golden):
+    """The same schedule with fp32 feature maps and weights (CUDA-core conv kernels with VUB_CONV_RELU): every loss term
+    AND d loss / d pred within 1e-4 of the reference's own tensors — the O(0.2) gradient difference of the bf16 path
+    is the L1 loss's sign noise, not the schedule."""
+    import bdvs_b200 as B
+    fx = golden("vgg_tiny")
+    m, sd = make(fx["weights"])
+    Bs, S = fx["batch"], fx["size"]
+    target = O.det_uniform("vgg_target", (Bs, 3, S, S)).cuda()
+    pred = (O.det_uniform("vgg_pred", (Bs, 3, S, S)) * 0.9).cuda().requires_grad_(True)
+    with B.fp32_validation(m):
+        losses = B.vgg_loss(m, target, pred)
+        sum(c * losses[k] for c, k in zip(fx["coeff"], losses)).sum().backward()
+        feats = m(target)
+    errs = {k: abs(float(losses[k]) - v) / abs(v) for k, v in fx["losses"].items()}
+    errs["d_pred"] = rel(pred.grad, fx["d_pred"])
+    errs["relu5_2"] = max(errs["relu5_2"], rel(feats["relu5_2"], fx["relu5_2"]))
+    print("vgg_tiny, fp32 validation:", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert feats["relu5_2"].dtype == torch.float32
+    assert max(errs.values()) < FP32_TOL, errs
+    # leaving the mode restores the bf16 tensor-core path
+    p2 = pred.detach().clone().requires_grad_(True)
+    l2 = B.vgg_loss(m, target, p2)
+    assert 1e-6 < abs(float(l2["relu5_2"]) - fx["losses"]["relu5_2"]) / fx["losses"]["relu5_2"] < LOSS_TOL
+
+
+def test_fp32_validation_training_step_through_vunet(golden):
+    """VunetAlter and the VGG term both in fp32 validation mode: the concatenated VUnet parameter gradient through the
+    perceptual loss vs the oracle's fp32 autograd."""
+    import bdvs_b200 as B
+    fx = golden("tiny3")
+    cfg = {k: v for k, v in fx["config"].items() if k != "batch"}
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = B.VunetAlter(**cfg)
+    nsd = O.det_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()})
+    net.load_state_dict(nsd)
+    net = net.cuda().train()
+    weights = [1.0] * 6
+    m, vsd = make(weights)
+    bs = 2
+    x, c, eps, _ = O.make_inputs(fx["config"], bs)
+    target = O.det_uniform("target", (bs, 3, cfg["spatial_size"], cfg["spatial_size"]))
+    with B.fp32_validation(net), B.fp32_validation(m):
+        imgs, means, logstds, _ = net(x.cuda(), c.cuda(), eps=[e.cuda() for e in eps])
+        ll = B.vgg_loss(m, target.cuda(), imgs)
+        loss = 5.0 * torch.stack([ll[k] for k in ll]).sum() + 1e-3 * B.compute_kl_with_prior(means, logstds)
+        loss.backward()
+    torch.cuda.synchronize()
+    got = {k: p.grad.detach().float().cpu() for k, p in net.named_parameters() if p.grad is not None}
+    sd_g = {k: v.clone().requires_grad_(True) for k, v in nsd.items()}
+    o_imgs, o_means, o_logstds, _, _ = O.forward(sd_g, x, c, eps)
+    o_ll = V.vgg_loss(vsd, target, o_imgs, weights)
+    o_loss = 5.0 * torch.stack([o_ll[k] for k in o_ll]).sum() + 1e-3 * O.compute_kl_with_prior(o_means, o_logstds)
+    o_loss.backward()
+    num = sum(float((got[k] - sd_g[k].grad).pow(2).sum()) for k in got)
+    den = sum(float(sd_g[k].grad.pow(2).sum()) for k in got)
+    err = (num / den) ** 0.5
+    print(f"VunetAlter + vgg_loss, fp32 validation: loss {float(loss):.6f} (oracle {float(o_loss):.6f}), concatenated "
+          f"parameter gradient rel-L2 {err:.3e}")
+    assert abs(float(loss) - float(o_loss)) < 1e-4 * abs(float(o_loss))
+    assert err < FP32_TOL
