@@ -23,6 +23,8 @@ CONV_ELU_IN0 = 8
 CONV_ELU_IN1 = 16
 CONV_U8_HWC = 32
 CONV_RELU = 64
+CONV_LRELU = 128
+CONV_TANH = 256
 
 # every extern "C" symbol the header declares; tests check the built library exports all of them
 EXPORTED_SYMBOLS = (
@@ -71,6 +73,11 @@ EXPORTED_SYMBOLS = (
     "vub_l1_num_partials",
     "vub_l1_partial",
     "vub_l1_relu_grad",
+    "vub_gather_affine",
+    "vub_couple_inv",
+    "vub_lstm_cell",
+    "vub_decoder_step",
+    "vub_decoder_init",
 )
 ABI_VERSION = 5
 
@@ -409,6 +416,16 @@ def _declare(lib: C.CDLL) -> None:
     lib.vub_l1_partial.argtypes = [vp, vp, C.c_int64, fp, i32, vp]
     lib.vub_l1_relu_grad.restype = C.c_int
     lib.vub_l1_relu_grad.argtypes = [vp, vp, C.c_int64, fp, C.c_float, vp, i32, vp]
+    lib.vub_gather_affine.restype = C.c_int
+    lib.vub_gather_affine.argtypes = [fp, vp, fp, fp, i32, i32, fp, vp, i32, i32, vp]
+    lib.vub_couple_inv.restype = C.c_int
+    lib.vub_couple_inv.argtypes = [fp, fp, fp, i32, i32, i32, i32, fp, vp, vp]
+    lib.vub_lstm_cell.restype = C.c_int
+    lib.vub_lstm_cell.argtypes = [fp, fp, i32, i32, vp, vp, i32, vp]
+    lib.vub_decoder_step.restype = C.c_int
+    lib.vub_decoder_step.argtypes = [fp, fp, i32, i32, i32, i32, i32, i32, fp, fp, vp, i32, i32, vp]
+    lib.vub_decoder_init.restype = C.c_int
+    lib.vub_decoder_init.argtypes = [fp, fp, i32, i32, i32, i32, fp, fp, vp, i32, vp]
     lib.vub_latent_sample_bwd.restype = C.c_int
     lib.vub_latent_sample_bwd.argtypes = [fp, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]
     lib.vub_space_to_depth.restype = C.c_int

@@ -90,9 +90,9 @@ __device__ __forceinline__ void epi_store(const EpiParams& p, float (&y)[CH], in
                         pack_bf16x2(y[8 * j + 4], y[8 * j + 5]), pack_bf16x2(y[8 * j + 6], y[8 * j + 7]));
   }
   if (p.out_elu != nullptr) {
-    const bool relu = (p.flags & VUB_CONV_RELU) != 0;
+    const int mode = act_mode_of(p.flags);
 #pragma unroll
-    for (int i = 0; i < CH; ++i) y[i] = act1(y[i], relu);
+    for (int i = 0; i < CH; ++i) y[i] = act_apply(y[i], mode);
     uint4* o = reinterpret_cast<uint4*>(p.out_elu + obase);
 #pragma unroll
     for (int j = 0; j < CH / 8; ++j)

@@ -311,9 +311,9 @@ __global__ void __launch_bounds__(kConvThreads)
             }
             if (p.ep.out_raw != nullptr) stage_put32<GW>(st_raw, lane, c0 - g0, y);
             if (p.ep.out_elu != nullptr) {
-              const bool relu = (p.ep.flags & VUB_CONV_RELU) != 0;
+              const int mode = act_mode_of(p.ep.flags);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) y[i] = act1(y[i], relu);
+              for (int i = 0; i < 32; ++i) y[i] = act_apply(y[i], mode);
               stage_put32<GW>(st_elu, lane, c0 - g0, y);
             }
           }
@@ -439,11 +439,16 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
   if (!d->x[0] || !d->w || !d->scale || !d->shift) return fail(VUB_E_NULL, "conv_fwd: x/w/scale/shift NULL");
   if (d->nsrc != 1 && d->nsrc != 2) return fail(VUB_E_SHAPE, "conv_fwd: nsrc must be 1 or 2");
   if (d->nsrc == 2 && !d->x[1]) return fail(VUB_E_NULL, "conv_fwd: x[1] NULL with nsrc == 2");
-  if (d->c_src != 32 && d->c_src != 64 && d->c_src != 128 && d->c_src != 256 && d->c_src != 512)
-    return fail(VUB_E_SHAPE, "conv_fwd: c_src %d not in {32,64,128,256,512}", d->c_src);
+  // "linear layer": ksize 1 on a 1x1 map = nn.Linear / nn.LSTMCell rows (behavior net, models/pose_behavior_rnn.py,
+  // lib/modules.py:236-257): any K that is a multiple of 64 up to 2048, any N that is a multiple of 128 up to 4096
+  const bool linear = d->ksize == 1 && d->stride == 1 && d->hin == 1 && d->win == 1 && !(d->flags & VUB_CONV_D2S);
+  if (d->c_src != 32 && d->c_src != 64 && d->c_src != 128 && d->c_src != 256 && d->c_src != 512 &&
+      !(linear && d->c_src % 64 == 0 && d->c_src >= 64 && d->c_src <= 2048))
+    return fail(VUB_E_SHAPE, "conv_fwd: c_src %d not in {32,64,128,256,512} (linear layers: multiples of 64 <= 2048)",
+                d->c_src);
   // 256 / 512 channels per source: the 4-group autoregressive prior of VunetOrg (models/vunets.py:655-676), which
   // lives on the two smallest latent maps only -- served by the per-tap kernel (any number of channel blocks)
-  const bool wide = d->c_src > 128;
+  const bool wide = d->c_src > 128 || d->cout > 512 || (d->flags & (VUB_CONV_LRELU | VUB_CONV_TANH)) != 0;
   if (wide && (d->stride != 1 || (d->flags & VUB_CONV_D2S)))
     return fail(VUB_E_SHAPE, "conv_fwd: c_src %d needs stride 1 and no D2S", d->c_src);
   if (d->ksize != 1 && d->ksize != 3) return fail(VUB_E_SHAPE, "conv_fwd: ksize must be 1 or 3");
@@ -456,8 +461,10 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
   const int hout = d->hin / d->stride, wout = d->win / d->stride;
   if (hout < 1 || wout < 1) return fail(VUB_E_SHAPE, "conv_fwd: empty output");
   const int cout = d->cout;
-  if (!(cout == 16 || cout == 32 || cout == 64 || cout == 128 || cout == 256 || cout == 512))
-    return fail(VUB_E_SHAPE, "conv_fwd: cout %d not in {16,32,64,128,256,512}", cout);
+  if (!(cout == 16 || cout == 32 || cout == 64 || cout == 128 || cout == 256 || cout == 512 ||
+        (linear && cout % 128 == 0 && cout > 0 && cout <= 4096)))
+    return fail(VUB_E_SHAPE, "conv_fwd: cout %d not in {16,32,64,128,256,512} (linear layers: multiples of 128 <= 4096)",
+                cout);
   if (d->cout_valid <= 0 || d->cout_valid > cout) return fail(VUB_E_SHAPE, "conv_fwd: cout_valid");
   const uint32_t f = d->flags;
   const bool f32 = (f & (VUB_CONV_F32_NHWC | VUB_CONV_F32_NCHW | VUB_CONV_U8_HWC)) != 0;  // "not bf16 NHWC"
@@ -623,6 +630,7 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
     // split-K: (ksplit - 1) partial tiles of 128 x bn fp32 must fit the leader's shared memory beside the staging
     // tiles (2, 3 -> bn <= 128, 4, 5, 6 -> 64, 7, 8 -> 32; a smaller N tile changes no bits)
     while (ksplit > 1 && bn > 16 && ((ksplit - 1) * bn > 320 || bn > 128)) bn >>= 1;
+    while (cout % bn) bn >>= 1;  // linear layers: N is a multiple of 128, not necessarily of 256
   }
 
   ConvKParams kp;

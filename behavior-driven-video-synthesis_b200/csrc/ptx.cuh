@@ -293,6 +293,18 @@ __device__ __forceinline__ float elu1(float v) {
 // The activation stored as an epilogue's "elu" output: ELU (the VUnet), or ReLU with VUB_CONV_RELU (VGG19 features of
 // the perceptual loss, models/imagenet_pretrained.py:46-59); and its derivative reconstructed from the stored value.
 __device__ __forceinline__ float act1(float v, bool relu) { return relu ? fmaxf(v, 0.f) : elu1(v); }
+// All four epilogue activations (per-tap kernel): 0 ELU, 1 ReLU, 2 LeakyReLU(0.01), 3 tanh.
+__device__ __forceinline__ int act_mode_of(uint32_t flags) {
+  return (flags & 64u) ? 1 : (flags & 128u) ? 2 : (flags & 256u) ? 3 : 0;
+}
+__device__ __forceinline__ float act_apply(float v, int mode) {
+  switch (mode) {
+    case 1: return fmaxf(v, 0.f);
+    case 2: return v > 0.f ? v : 0.01f * v;
+    case 3: return tanhf(v);
+    default: return elu1(v);
+  }
+}
 __device__ __forceinline__ float act1_grad(float stored, bool relu) {
   return stored > 0.f ? 1.0f : (relu ? 0.0f : stored + 1.0f);
 }

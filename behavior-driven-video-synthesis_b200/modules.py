@@ -187,11 +187,14 @@ class WeightBank:
                     raise ValueError("merged convs must share their input geometry")
             nsrc = first._vub_split
             c_src = first.in_channels // nsrc
-            if c_src not in _SUPPORTED_C:
+            linear = getattr(first, "_vub_linear", False)  # nn.Linear as a 1x1 conv on a 1x1 map (behavior.py)
+            if linear and (c_src % 64 or c_src > 2048):
+                raise NotImplementedError(f"linear layers take a multiple of 64 (<= 2048) input features, got {c_src}")
+            if not linear and c_src not in _SUPPORTED_C:
                 raise NotImplementedError(
                     f"no tensor-core kernel for {first.in_channels} input channels split {nsrc} ways "
                     f"(supported per-source channel counts: {_SUPPORTED_C})")
-            cpad = _pad_cout(cout)
+            cpad = _pad_cout(cout) if cout <= 512 else (cout + 127) // 128 * 128
             cout_k = (cout + 31) // 32 * 32
             layout.append((w_off, s_off, k, cout, cpad, nsrc, c_src, wd_off, cout_k))
             w_off += cpad * k

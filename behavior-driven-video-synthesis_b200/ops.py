@@ -22,7 +22,7 @@ _LIB = torch.library.Library("vunet_b200", "DEF")
 _LIB.define(
     "conv_fwd(Tensor x0, Tensor? x1, Tensor w, Tensor scale, Tensor shift, Tensor? residual, "
     "int ksize, int stride, int cout_valid, bool want_raw, bool want_elu, bool d2s, int f32_mode, "
-    "int stages, int elu_in=0, Tensor? w_tiled=None, bool relu=False) -> Tensor[]"
+    "int stages, int elu_in=0, Tensor? w_tiled=None, bool relu=False, int act=0) -> Tensor[]"
 )
 _LIB.define("wn_prep(Tensor table, int n_entries, int total_rows) -> ()")
 _LIB.define(
@@ -120,7 +120,7 @@ def _check_act(t: torch.Tensor, name: str) -> None:
 
 
 def _conv_fwd_cuda(x0, x1, w, scale, shift, residual, ksize, stride, cout_valid, want_raw, want_elu,
-                   d2s, f32_mode, stages, elu_in=0, w_tiled=None, relu=False) -> List[torch.Tensor]:
+                   d2s, f32_mode, stages, elu_in=0, w_tiled=None, relu=False, act=0) -> List[torch.Tensor]:
     _check_act(x0, "conv_fwd x0")
     B, H, W, c_src = x0.shape
     nsrc = 1
@@ -184,6 +184,10 @@ def _conv_fwd_cuda(x0, x1, w, scale, shift, residual, ksize, stride, cout_valid,
         flags |= N.CONV_ELU_IN1
     if relu:  # the "elu" output holds ReLU(y): VGG19 feature convs of the perceptual loss
         flags |= N.CONV_RELU
+    if act == 2:  # LeakyReLU(0.01) / tanh: the MLPs of the behavior net's latent flow (per-tap kernel only)
+        flags |= N.CONV_LRELU
+    elif act == 3:
+        flags |= N.CONV_TANH
     d.flags, d.stages = flags, stages
     bn = min(cout, 256)
     bkc = 64 if c_src >= 64 else 32
@@ -855,13 +859,13 @@ for _name, _fn in (("conv_fwd", _conv_fwd_cuda), ("frames_to_uint8", _frames_to_
 def conv_fwd(x: Sequence[torch.Tensor], w, scale, shift, *, ksize: int, stride: int = 1,
              residual: Optional[torch.Tensor] = None, want_raw: bool = True, want_elu: bool = True,
              d2s: bool = False, cout_valid: Optional[int] = None, stages: int = 0, elu_in: int = 0,
-             w_tiled: Optional[torch.Tensor] = None,
-             relu: bool = False) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+             w_tiled: Optional[torch.Tensor] = None, relu: bool = False,
+             act: int = 0) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """bf16 NHWC outputs: returns (raw or None, elu or None).  ``elu_in``: bit s set = source s is a RAW
     activation to which the kernel applies ELU while loading (only where :func:`elu_in_ok`)."""
     cv = w.shape[0] if cout_valid is None else cout_valid
     outs = _ops.conv_fwd(x[0], x[1] if len(x) > 1 else None, w, scale, shift, residual, ksize, stride, cv,
-                         want_raw, want_elu, d2s, F32_NONE, stages, elu_in, w_tiled, relu)
+                         want_raw, want_elu, d2s, F32_NONE, stages, elu_in, w_tiled, relu, act)
     it = iter(outs)
     raw = next(it) if want_raw else None
     elu = next(it) if want_elu else None

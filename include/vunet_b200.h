@@ -51,6 +51,9 @@ extern "C" {
                                   VGG19 feature convs of the perceptual loss (models/imagenet_pretrained.py:46-59,
                                   lib/losses.py:81-119) */
 
+#define VUB_CONV_LRELU 128u    /* the "elu" output holds LeakyReLU(y, 0.01) / tanh(y): the coupling MLPs of the behavior net's */
+#define VUB_CONV_TANH 256u     /* latent flow (lib/modules.py:236-257 BasicFullyConnectedNet).  Per-tap kernel only */
+
 /* ABI version of the loaded library (== VUB_ABI_VERSION it was built with). */
 int vub_abi_version(void);
 /* Message for the last non-zero return on this thread ("" if none). */
@@ -79,9 +82,10 @@ typedef struct vub_conv_desc {
   void* out_f32;         /* fp32, layout per flags, or NULL */
   int32_t nsrc;          /* 1 or 2 */
   int32_t c_src;         /* channels per source: 32, 64 or 128; 256 / 512 (VunetOrg's 4-group prior on the two smallest
-                            latent maps: models/vunets.py:655-676) with stride 1 and no D2S */
+                            latent maps: models/vunets.py:655-676) with stride 1 and no D2S; any multiple of 64 up to
+                            2048 for a "linear layer" (ksize 1 on a 1x1 map: nn.Linear / nn.LSTMCell of the behavior net) */
   int32_t batch, hin, win;
-  int32_t cout;          /* GEMM N = rows of w (padded to 16/32/64/128/256/512) */
+  int32_t cout;          /* GEMM N = rows of w (padded to 16/32/64/128/256/512; linear layers: any multiple of 128 <= 4096) */
   int32_t cout_valid;    /* channels actually stored (== cout except for out_conv) */
   int32_t ksize;         /* 1 or 3 */
   int32_t stride;        /* 1 or 2 */
@@ -499,6 +503,36 @@ int32_t vub_l1_num_partials(int64_t numel);
 int vub_l1_partial(const void* pf, const void* tf, int64_t numel, float* partial, int32_t f32_acts, void* stream);
 int vub_l1_relu_grad(const void* pf, const void* tf, int64_t numel, const float* g_dev, float scale, void* out,
                      int32_t f32_acts, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Behavior-net sampling (BASELINE.json configs[3]): b = flow.reverse(z) through the 15-block latent
+ * flow (models/flow/simple_flow.py:136-180 UnsupervisedTransformer2 -> models/flow/blocks.py:95-128, 531-559), then
+ * ResidualBehaviorNet.generate_seq (models/pose_behavior_rnn.py:603-626) with the residual LSTM decoder (463-506).
+ * Every matrix product (coupling MLPs, LSTM gates, n_out) is a "linear layer" launch of vub_conv_fwd (ksize 1 on a
+ * 1x1 map, VUB_CONV_LRELU epilogues); these are the elementwise pieces between them, on fp32 rows [batch, d].
+ * ---------------------------------------------------------------------------------------------- */
+/* y[b, j] = x[b, idx[j]] / scale[idx[j]] - loc[idx[j]]: Shuffle.reverse (blocks.py:700-704, idx = backward_shuffle_idx;
+ * NULL = identity) fused with the ActNorm.reverse (lib/modules.py:318-330) of the block processed before it (scale /
+ * loc NULL = none).  y_bf16 (optional): compact bf16 copy [batch, bf_cols] of columns [bf_col0, bf_col0 + bf_cols). */
+int vub_gather_affine(const float* x, const int32_t* idx, const float* scale, const float* loc, int32_t batch, int32_t d,
+                      float* y, void* y_bf16, int32_t bf_col0, int32_t bf_cols, void* stream);
+/* Reverse affine coupling (blocks.py:311-318): state_out[:, col0 : col0 + d2] = (state_in[:, col0 : col0 + d2] - t) *
+ * exp(-tanh(s_raw)), s_raw / t = fp32 [batch, d2] outputs of the two MLPs' last linear layers (the s-net's nn.Tanh is
+ * applied here); out_bf16: compact bf16 copy [batch, d2] or NULL.  state_in may equal state_out. */
+int vub_couple_inv(const float* state_in, const float* s_raw, const float* t, int32_t batch, int32_t d, int32_t d2,
+                   int32_t col0, float* state_out, void* out_bf16, void* stream);
+/* nn.LSTMCell from the gate pre-activations [batch, 4*hdim] (chunks i, f, g, o): c updated in place (fp32), h' written
+ * as bf16 compact [batch, hdim] and into columns [0, hdim) of the next step's gate input [batch, cat_pitch]. */
+int vub_lstm_cell(const float* gates, float* c, int32_t batch, int32_t hdim, void* h_lin_bf16, void* h_cat_bf16,
+                  int32_t cat_pitch, void* stream);
+/* ResidualRNNDecoder.forward's `out + res, res` (pose_behavior_rnn.py:487-506) for step t: x <- x + v (v fp32
+ * [batch, vpitch], first n columns), xs[:, t] = new x, cs[:, t] = old x ([batch, steps, n] fp32), bf16 copy of the new
+ * x (zero-padded to xpad) into columns [hdim, hdim + xpad) of the gate input. */
+int vub_decoder_step(float* x, const float* v, int32_t batch, int32_t n, int32_t vpitch, int32_t xpad, int32_t t,
+                     int32_t steps, float* xs, float* cs, void* x_cat_bf16, int32_t cat_pitch, int32_t hdim, void* stream);
+/* generate_seq's start: hidden = cell = b (pose_behavior_rnn.py:612-614), x = x_pose[:, start_frame]. */
+int vub_decoder_init(const float* b_lat, const float* x0, int32_t batch, int32_t hdim, int32_t n, int32_t xpad, float* c,
+                     float* x, void* cat_bf16, int32_t cat_pitch, void* stream);
 
 /*
  * Data-parallel gradient exchange (SURVEY.md 8b `allreduce_bucket(flat, ncclComm, stream)`): in-place all-reduce of

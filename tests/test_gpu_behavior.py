@@ -1,0 +1,80 @@
+"""GPU (-m gpu): behavior-net sampling (BASELINE.json configs[3]) on the CUDA path — the flow's reverse pass and the
+residual LSTM decoder, every matrix product a tcgen05 "linear layer" launch — against the golden vector generated from
+the unmodified reference classes and against the CPU oracle at the real sizes of config/behavior_net.yaml
+(dim_hidden_b 1024, 15 flow blocks with 2048-wide MLPs, 50-step sequences, batch 256).  Tolerance: rel-L2 <= 1e-2 (bf16)."""
+import pytest
+import torch
+
+import behavior_oracle as BO
+import vunet_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def make(cfg):
+    import bdvs_b200 as B
+    flow = B.UnsupervisedTransformer2(flow_in_channels=cfg["dim_hidden_b"], n_flows=cfg["n_flows"],
+                                      flow_hidden_depth=cfg["flow_hidden_depth"],
+                                      flow_mid_channels=cfg["dim_hidden_b"] * cfg["flow_mid_channels_factor"])
+    net = B.ResidualBehaviorNet(n_kps=cfg["n_kps"], dim_hidden_b=cfg["dim_hidden_b"], decoder_arch="lstm",
+                                linear_in_decoder=False)
+    fsd = BO.det_flow_state_dict({k: tuple(v.shape) for k, v in flow.state_dict().items()})
+    nsd = BO.det_net_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()})
+    flow.load_state_dict(fsd)
+    net.load_state_dict(nsd)
+    return flow.cuda().eval(), net.cuda().eval(), fsd, nsd
+
+
+def test_matches_reference_golden(golden):
+    import bdvs_b200 as B
+    fx = golden("behavior_tiny")
+    cfg = fx["config"]
+    flow, net, fsd, nsd = make(cfg)
+    Bs, T, n, D = cfg["batch"], cfg["length"], cfg["n_kps"], cfg["dim_hidden_b"]
+    z = O.det_normal("bz", (Bs, D)).cuda()
+    x_pose = O.det_uniform("bx", (Bs, T, n)).cuda()
+    with torch.no_grad():
+        b = flow.reverse(z)
+        assert tuple(b.shape) == (Bs, D, 1, 1)
+        xs, cs, zs, bb = net.generate_seq(b.squeeze(-1).squeeze(-1), x_pose, len=T, start_frame=0)
+    errs = {"b": rel(b.reshape(Bs, D), fx["b"]), "xs": rel(xs, fx["xs"]), "cs": rel(cs, fx["cs"])}
+    print("behavior_tiny:", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < TOL, errs
+    assert zs == [] and tuple(xs.shape) == (Bs, T, n)
+    # the graph-captured sampler equals the two calls; flow(z, reverse=True) and sample() are the same path
+    smp = B.PoseSequenceSampler(flow, net, Bs, T)
+    out = smp(z, x_pose[:, :1])
+    assert torch.equal(out, xs)
+    assert torch.equal(flow(z, reverse=True), b)
+    torch.manual_seed(5)
+    s1 = flow.sample((Bs, D), device="cuda")
+    torch.manual_seed(5)
+    s2 = flow.reverse(torch.randn((Bs, D)).cuda()).reshape(Bs, D)
+    assert torch.equal(s1, s2)
+
+
+def test_full_size_matches_oracle():
+    """config/behavior_net.yaml: dim_hidden_b 1024, 15 blocks, MLP width 2048, depth 2; batch 256, 50 steps."""
+    cfg = dict(dim_hidden_b=1024, flow_mid_channels_factor=2, n_flows=15, flow_hidden_depth=2, n_kps=51)
+    flow, net, fsd, nsd = make(cfg)
+    Bs, T = 256, 50
+    z = O.det_normal("bz_full", (Bs, 1024))
+    x0 = O.det_uniform("bx_full", (Bs, 1, 51))
+    with torch.no_grad():
+        b = flow.reverse(z.cuda()).reshape(Bs, 1024)
+        xs, cs, _, _ = net.generate_seq(b, x0.cuda(), T, 0)
+        o_b = BO.flow_reverse(fsd, z, 15, 2)
+        o_xs, o_cs = BO.generate_seq(nsd, o_b, x0[:, 0], T)
+        # the decoder alone from the oracle's b (isolates it from the flow's rounding)
+        xs2, _, _, _ = net.generate_seq(o_b.cuda(), x0.cuda(), T, 0)
+    errs = {"b": rel(b, o_b), "xs": rel(xs, o_xs), "cs": rel(cs, o_cs), "xs_from_oracle_b": rel(xs2, o_xs),
+            "velocities": rel(xs - cs, o_xs - o_cs)}
+    print("behavior net, full size B=256 T=50:", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < TOL, errs
+    assert torch.isfinite(xs).all()
