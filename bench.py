@@ -465,6 +465,85 @@ def run_train_vgg(device, steps: int, peaks) -> dict:
     return out
 
 
+def run_behavior_sampling(device, steps: int, peaks) -> dict:
+    """BASELINE.json configs[3]: behavior-net sampling, batch 256 — noise -> latent flow reverse (15 coupling blocks,
+    2048-wide MLPs, 630 M parameters) -> residual LSTM-1024 decoder, 50-step 3-D pose sequences (51 coordinates), as ONE
+    CUDA graph (PoseSequenceSampler); plus a per-kernel breakdown of one instrumented eager call and the CPU oracle on
+    a bounded sample."""
+    import time
+    import behavior_oracle as BO
+    import bdvs_b200 as B
+    from bdvs_b200.profiler import KernelProfiler
+
+    cfg = dict(dim_hidden_b=1024, mid=2048, n_flows=15, depth=2, n_kps=51)
+    Bs, T = 256, 50
+    flow = B.UnsupervisedTransformer2(flow_in_channels=1024, n_flows=15, flow_hidden_depth=2, flow_mid_channels=2048)
+    net = B.ResidualBehaviorNet(n_kps=51, dim_hidden_b=1024, decoder_arch="lstm", linear_in_decoder=False)
+    fsd = BO.det_flow_state_dict({k: tuple(v.shape) for k, v in flow.state_dict().items()})
+    nsd = BO.det_net_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()})
+    flow.load_state_dict(fsd)
+    net.load_state_dict(nsd)
+    flow, net = flow.to(device).eval(), net.to(device).eval()
+    smp = B.PoseSequenceSampler(flow, net, Bs, T)
+    g = torch.Generator(device=device).manual_seed(99)
+    z = torch.randn(Bs, 1024, device=device, generator=g)
+    x0 = torch.rand(Bs, 1, 51, device=device, generator=g) * 2 - 1
+    zh, xh = z.cpu().pin_memory(), x0.cpu().pin_memory()
+    outh = torch.empty((Bs, T, 51), dtype=torch.float32).pin_memory()
+    for _ in range(3):
+        smp(z, x0)
+    torch.cuda.synchronize()
+    K = max(5, steps)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        smp.run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    e0.record()
+    for _ in range(K):   # e2e: noise and start poses from pinned host memory, sequences back to it
+        outh.copy_(smp(zh, xh), non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1) / K
+    with torch.no_grad():
+        smp._step()
+        with KernelProfiler() as kp:
+            smp._step()
+    prof = kp.summary()
+    tot = sum(r["ms"] for r in prof.values())
+    rows = []
+    for name, r in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]:
+        rows.append({"kernel": name, "launches": r["launches"], "ms": round(r["ms"], 4), "share": round(r["ms"] / tot, 4),
+                     "tflops": round(r["flops"] / (r["ms"] * 1e-3) / 1e12, 1) if r["ms"] > 0 else 0.0,
+                     "gbs": round(r["bytes"] / (r["ms"] * 1e-3) / 1e9, 1) if r["ms"] > 0 else 0.0})
+    n_flow_w = sum(p.numel() for n_, p in flow.named_parameters() if n_.endswith("weight"))
+    gflop = (2.0 * Bs * n_flow_w + T * 2.0 * Bs * (4096 * (1024 + 51) + 1024 * 51)) / 1e9
+    w_bytes = 2.0 * (n_flow_w + 4096 * 1088 + 64 * 1024)
+    # CPU oracle on a bounded sample (16 sequences)
+    torch.set_num_threads(os.cpu_count() or 1)
+    zc, xc = z[:16].cpu(), x0[:16, 0].cpu()
+    with torch.no_grad():
+        BO.generate_seq(nsd, BO.flow_reverse(fsd, zc, 15, 2), xc, T)
+        t0 = time.time()
+        for _ in range(2):
+            BO.generate_seq(nsd, BO.flow_reverse(fsd, zc, 15, 2), xc, T)
+        cpu_s = (time.time() - t0) / 2
+    return {"metric": "behavior-net sampling throughput (flow reverse + LSTM decoder, 50-step 3-D pose sequences)",
+            "value": Bs / (ms * 1e-3), "unit": "sequences/s", "ms_per_batch": ms, "batch": Bs, "steps_per_sequence": T,
+            "per_gpu": True, "cuda_graph": True, "gpu_launches_per_batch": smp.launches_per_call,
+            "e2e": {"value": Bs / (ms_e2e * 1e-3), "unit": "sequences/s", "h2d_bytes_per_step": zh.numel() * 4 + xh.numel() * 4,
+                    "d2h_bytes_per_step": outh.numel() * 4},
+            "algorithmic_gflop_per_batch": round(gflop, 1), "tflops": round(gflop / ms, 1),
+            "weight_bytes_per_batch": w_bytes, "weight_stream_gbs": round(w_bytes / (ms * 1e-3) / 1e9, 1),
+            "frac_hbm_weight_stream": round(w_bytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+            "parameters": sum(p.numel() for p in flow.parameters()) + sum(p.numel() for p in net.parameters()),
+            "kernels": {"sum_kernel_ms": round(tot, 3), "top": rows},
+            "cpu_baseline": {"value": 16 / cpu_s, "unit": "sequences/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": "16 sequences x 2 iters (+1 warm-up), oracle/behavior_oracle.py fp32 torch CPU"}}
+
+
 def run_vunet_org(device, frames: int, steps: int, peaks) -> dict:
     """``VunetOrg.transfer`` (models/vunets.py:102-110) at the H256 geometry, ``frames`` frames per step, CUDA-graph
     replay timed with CUDA events on this rank; plus the share of the step the prior's 512 / 1024-channel convs take
@@ -871,6 +950,11 @@ def run_ours(args):
         roofline["vunet_org"] = run_vunet_org(device, Bf, K, peaks)
     except Exception as exc:  # secondary number: never take the headline down
         roofline["vunet_org"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    # ---- SURVEY §8f-4 / BASELINE configs[3]: behavior-net sampling, batch 256 ----
+    try:
+        roofline["behavior_sampling"] = run_behavior_sampling(device, K, peaks)
+    except Exception as exc:  # secondary number: never take the headline down
+        roofline["behavior_sampling"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     # ---- the training step with the reference's real likelihood, the VGG19 perceptual loss ----
     if not args.no_train:
         try:

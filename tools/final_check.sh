@@ -23,6 +23,7 @@ try:
     print("vunet_org", b["roofline"].get("vunet_org"))
     print("sequence", b["roofline"].get("sequence"))
     print("train_vgg", b["roofline"].get("train_vgg"))
+    print("behavior_sampling", b["roofline"].get("behavior_sampling"))
     for k in b["kernels"][:12]:
         print(k["kernel"], k["launches"], k["ms"], k["share"], k["tflops"], k["gbs"])
 except Exception as e:
