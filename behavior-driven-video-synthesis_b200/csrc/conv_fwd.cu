@@ -499,6 +499,10 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
     const int mode = env_int("VUB_SPLITK", 1);
     const bool eligible = ksteps_all >= 12 && !(f & (VUB_CONV_ELU_IN0 | VUB_CONV_ELU_IN1)) && d->stages >= 0;
     if (mode == 1 && eligible && hout * wout <= 16) ksplit = 3;
+    // linear layers (batch rows as pixels: 2 pixel tiles at batch 256) with many output features already fill the chip
+    // through their N tiles; measured (tools/linear_sweep.sh): 2048->2048 0.014 -> 0.013 ms, 1088->4096 0.021 -> 0.010 ms
+    // without the split, 2048->512 0.013 -> 0.008 ms with it
+    if (mode == 1 && linear && cout > 512) ksplit = 1;
     if (mode >= 2 && mode <= 8 && eligible && hout * wout <= 64) ksplit = mode;
   }
   if (ksplit == 1 && !wide && conv_rows_applicable(d)) return conv_rows_launch(d, static_cast<cudaStream_t>(stream_v));
