@@ -670,7 +670,10 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
   const int ksteps_cta = (ksteps + ksplit - 1) / ksplit;  // the longest range of a split-K cluster
   kp.stages = d->stages > 0 ? d->stages : default_stages(bn, bkc, ksteps_cta);  // stages < 0: force this kernel
   if (kp.stages > ksteps_cta) kp.stages = ksteps_cta;
-  if (d->stages <= 0 && (long long)kp.tiles_w * kp.tiles_h * tiles_n * (cout / bn) * ksplit <= sm_count()) {
+  // (not for linear layers: two of them -- the scale and the translation net of a coupling -- run side by side on two
+  // streams and must be able to share an SM; VUB_LINEAR_DEEP=1 gives them the whole budget too)
+  if (d->stages <= 0 && (!linear || env_int("VUB_LINEAR_DEEP", 0)) &&
+      (long long)kp.tiles_w * kp.tiles_h * tiles_n * (cout / bn) * ksplit <= sm_count()) {
     // at most one CTA per SM: nothing to share the shared memory with, and with two stages only 40 KB are in
     // flight per L2/HBM round trip -> take the whole budget (the small-map layers are latency bound)
     const int deep = 190 * 1024 / ((kTileM + bn) * bkc * 2);
