@@ -47,6 +47,7 @@ struct ConvKParams {
   const uint8_t* w_tiled;  // tile-major pre-swizzled weights [K/64][w_rows][128 B], or nullptr (BKC == 64 only)
   int w_rows;
   int ksplit;  // split-K instantiation: CTAs per cluster (= gridDim.z), each takes a contiguous range of the k-steps
+  int reduce_scatter;  // split-K by reduce-scatter (every CTA owns 32 columns of the tile) instead of a reducing leader
 };
 
 // Epilogue for CH (16 or 32) consecutive channels of one pixel held in registers.
@@ -81,7 +82,14 @@ struct SplitKPart {
 // Every CTA accumulates its range in its own tensor memory; the peers then push their fp32 partials into the leader's
 // shared memory through DSMEM, and the leader adds them (in rank order: deterministic) before the usual epilogue.
 // For the smallest maps (<= 8x8), where a handful of CTAs would otherwise each stream an 18 .. 144-step K loop.
-template <int BN, int BKC, bool SPLITK>
+//
+// SPLITK == 2, reduce-scatter (linear layers: few pixel tiles, thousands of output features): instead of one leader
+// collecting (ksplit - 1) full partial tiles -- which caps ksplit at 320 / BN -- every CTA of the cluster OWNS the
+// column slice [rank * BN / ksplit, +BN / ksplit) of the tile: it pushes the other slices of its accumulator to their
+// owners through DSMEM, keeps its own in tensor memory, and after the second cluster barrier reduces and stores its
+// 32 columns itself.  With BN = 256 and eight ranges a CTA streams an eighth of the activation rows and of its weight
+// tile, receives 7 x 16 KB, and all eight epilogues run in parallel.
+template <int BN, int BKC, int SPLITK>
 __global__ void __launch_bounds__(kConvThreads)
     conv_fwd_kernel(const __grid_constant__ ConvKParams p) {
   constexpr int ROWB = BKC * 2;
@@ -114,7 +122,7 @@ __global__ void __launch_bounds__(kConvThreads)
   const int KS = p.nsrc * p.ntaps * p.cblocks;
   int ks_begin = 0, ks_end = KS;
   uint32_t crank = 0;
-  if constexpr (SPLITK) {
+  if constexpr (SPLITK != 0) {
     crank = cluster_ctarank();
     ks_begin = KS * static_cast<int>(crank) / p.ksplit;
     ks_end = KS * (static_cast<int>(crank) + 1) / p.ksplit;
@@ -221,7 +229,56 @@ __global__ void __launch_bounds__(kConvThreads)
     tc_fence_after();
   }
 
-  if constexpr (SPLITK) {
+  if constexpr (SPLITK == 2) {
+    // ---- reduce-scatter over the cluster: slice width W = BN / ksplit = 32 columns ----
+    constexpr int W = 32;
+    tc_fence_before();
+    cluster_sync_all();  // #1: every CTA's accumulator is complete, every CTA's pipeline stages are idle
+    tc_fence_after();
+    if (warp >= 2) {
+      const int q = warp & 3;
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+      for (int peer = 0; peer < p.ksplit; ++peer) {
+        if (peer == static_cast<int>(crank)) continue;
+        const int slot = static_cast<int>(crank) < peer ? static_cast<int>(crank) : static_cast<int>(crank) - 1;
+        uint32_t acc[32];
+        tmem_ld32(trow + peer * W, acc);
+        tmem_ld_wait();
+        const uint32_t dst = mapa_u32(smem_u32(smem) + slot * (W * kTileM * 4) + (q * 32 + lane) * 4, peer);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) st_cluster_u32(dst + i * (kTileM * 4), acc[i]);
+      }
+    }
+    tc_fence_before();
+    cluster_sync_all();  // #2: this CTA's slice has all its partials
+    tc_fence_after();
+    if (warp >= 2) {
+      const int q = warp & 3;
+      const int m = q * 32 + lane;
+      const int dw = m & (p.tw - 1);
+      const int dh = (m >> p.tw_log2) & (p.th - 1);
+      const int dn = m >> (p.tw_log2 + p.th_log2);
+      const int n = n0 + dn, oh = h0 + dh, ow = w0 + dw;
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+      uint32_t acc[32];
+      tmem_ld32(trow + crank * W, acc);
+      tmem_ld_wait();
+      const uint32_t src = smem_u32(smem) + (q * 32 + lane) * 4;
+      for (int slot = 0; slot < p.ksplit - 1; ++slot) {  // ranks in increasing order, this CTA's own range at its place
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          acc[i] = __float_as_uint(__uint_as_float(acc[i]) + lds_f32(src + slot * (W * kTileM * 4) + i * (kTileM * 4)));
+      }
+      const int c_local = static_cast<int>(crank) * W;
+      epilogue_chunk<32>(p.ep, acc, s_scale, s_shift, c_local, n_tile * BN + c_local, n < p.batch, n, oh, ow);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+    return;
+  }
+
+  if constexpr (SPLITK == 1) {
     // #1: every CTA of the cluster has its accumulator (its epilogue warps arrive only after the wait above), so the
     // leader's pipeline stages are idle and may receive the peers' partials.
     tc_fence_before();
@@ -254,7 +311,7 @@ __global__ void __launch_bounds__(kConvThreads)
     tc_fence_after();
   }
 
-  if (warp >= 2 && (!SPLITK || crank == 0)) {
+  if (warp >= 2 && (SPLITK == 0 || crank == 0)) {
     // ------------------------------ epilogue -----------------------------------
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int m = q * 32 + lane;
@@ -266,7 +323,7 @@ __global__ void __launch_bounds__(kConvThreads)
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     // split-K leader: add the peers' partials of columns [c0, c0 + CH) of this thread's row, in rank order
     auto add_partials = [&](auto& acc, int c0) {
-      if constexpr (SPLITK) {
+      if constexpr (SPLITK == 1) {
         const uint32_t src = smem_u32(smem) + SplitKPart<BN>::OFF + (q * 32 + lane) * 4 + c0 * (kTileM * 4);
         constexpr int CH = sizeof(acc) / sizeof(uint32_t);
         for (int r = 1; r < p.ksplit; ++r) {
@@ -349,7 +406,7 @@ __global__ void __launch_bounds__(kConvThreads)
 // ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
-template <int BN, int BKC, bool SPLITK>
+template <int BN, int BKC, int SPLITK>
 static int launch_conv_t(const ConvKParams& kp, dim3 grid, cudaStream_t stream) {
   constexpr int STAGE_BYTES = (kTileM + BN) * BKC * 2;
   static std::once_flag once;
@@ -367,8 +424,12 @@ static int launch_conv_t(const ConvKParams& kp, dim3 grid, cudaStream_t stream) 
   if constexpr (kStaging > 0) {
     if (smem < kStaging) smem = kStaging;  // the epilogue reuses the (then idle) pipeline stages
   }
-  if constexpr (SPLITK) {  // the leader's stages also receive the peers' partial accumulators
+  if constexpr (SPLITK == 1) {  // the leader's stages also receive the peers' partial accumulators
     const size_t need = SplitKPart<BN>::OFF + (size_t)(kp.ksplit - 1) * SplitKPart<BN>::PEER_BYTES;
+    if (smem < need) smem = need;
+  }
+  if constexpr (SPLITK == 2) {  // every CTA receives (ksplit - 1) slices of 128 x 32 fp32
+    const size_t need = (size_t)(kp.ksplit - 1) * 32 * kTileM * 4;
     if (smem < need) smem = need;
   }
   smem += 1024;
@@ -379,11 +440,17 @@ static int launch_conv_t(const ConvKParams& kp, dim3 grid, cudaStream_t stream) 
 
 template <int BN, int BKC>
 static int launch_conv(const ConvKParams& kp, dim3 grid, cudaStream_t stream) {
+  if (kp.ksplit > 1 && kp.reduce_scatter) {
+    if constexpr (BN >= 64 && BKC == 64) {
+      if (BN == 32 * kp.ksplit) return launch_conv_t<BN, BKC, 2>(kp, grid, stream);
+    }
+    return fail(VUB_E_SHAPE, "conv_fwd: reduce-scatter split-K needs N tile = 32 x ranges (64 / 128 / 256)");
+  }
   if (kp.ksplit > 1) {
-    if constexpr (BN <= 128) return launch_conv_t<BN, BKC, true>(kp, grid, stream);
+    if constexpr (BN <= 128) return launch_conv_t<BN, BKC, 1>(kp, grid, stream);
     return fail(VUB_E_SHAPE, "conv_fwd: split-K needs an N tile <= 128");
   }
-  return launch_conv_t<BN, BKC, false>(kp, grid, stream);
+  return launch_conv_t<BN, BKC, 0>(kp, grid, stream);
 }
 
 bool conv_rows_applicable(const vub_conv_desc* d);            // conv_rows.cu
@@ -636,6 +703,21 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
     while (ksplit > 1 && bn > 16 && ((ksplit - 1) * bn > 320 || bn > 128)) bn >>= 1;
     while (cout % bn) bn >>= 1;  // linear layers: N is a multiple of 128, not necessarily of 256
   }
+  // Linear layers with thousands of output features: split-K by reduce-scatter over the cluster (N tile = 32 x ranges,
+  // every CTA owns 32 columns).  VUB_LINEAR_RS=0 disables it, 2 / 4 / 8 choose the range count.  Measured on the
+  // behavior net's sampler (batch 256, one CUDA graph, profiles/r02_linear_rs.log): 3.22 ms without, 2.77 ms with two
+  // ranges, 3.02 ms with four; eight-CTA clusters are slower than no split (2048->2048: 0.027 vs 0.015 ms) -- a cluster
+  // needs all its SMs free in one GPC at once, and 7/8 of every accumulator crosses the cluster network.
+  int reduce_scatter = 0;
+  if (linear && cout > 512 && d->c_src >= 64 && d->stages >= 0) {
+    const int want = env_int("VUB_LINEAR_RS", 2);
+    const int ksteps_lin = d->nsrc * (d->c_src / 64);
+    if ((want == 2 || want == 4 || want == 8) && ksteps_lin >= 2 * want && cout % (32 * want) == 0) {
+      ksplit = want;
+      bn = 32 * want;
+      reduce_scatter = 1;
+    }
+  }
 
   ConvKParams kp;
   memset(&kp, 0, sizeof(kp));
@@ -667,6 +749,7 @@ extern "C" int vub_conv_fwd(const vub_conv_desc* d, void* stream_v) {
   const int tiles_n = (d->batch + kp.tn - 1) / kp.tn;
   const int ksteps = kp.nsrc * kp.ntaps * kp.cblocks;
   kp.ksplit = ksplit;
+  kp.reduce_scatter = reduce_scatter;
   const int ksteps_cta = (ksteps + ksplit - 1) / ksplit;  // the longest range of a split-K cluster
   kp.stages = d->stages > 0 ? d->stages : default_stages(bn, bkc, ksteps_cta);  // stages < 0: force this kernel
   if (kp.stages > ksteps_cta) kp.stages = ksteps_cta;

@@ -505,6 +505,12 @@ int main(int argc, char** argv) {
       {"1x1 128->512 @4x4 B3 elu only",                    3, 4, 4, 128, 1, 512, 512, 1, 1, false, false, true, false, false, false, 0},
       {"1x1 [128|128]->128 @8x8 B3 cat dual (latent_nins)", 3, 8, 8, 128, 2, 128, 128, 1, 1, false, true, true, false, false, false, 0},
       {"3x3 512->128 f32 NHWC @16x16 B2 (wide, no split)", 2, 16, 16, 512, 1, 128, 128, 3, 1, false, false, false, false, true, false, 0},
+      // linear layers of the behavior net (nn.Linear / LSTMCell rows as a 1x1 conv on a 1x1 map): reduce-scatter split-K
+      {"linear 2048->2048 B200 elu only (reduce-scatter)",  200, 1, 1, 2048, 1, 2048, 2048, 1, 1, false, false, true, false, false, false, 0},
+      {"linear 1088->4096 B256 f32 (LSTM gates)",           256, 1, 1, 1088, 1, 4096, 4096, 1, 1, false, false, false, false, true, false, 0},
+      {"linear 2048->512 B130 f32 (last MLP layer)",        130, 1, 1, 2048, 1, 512, 512, 1, 1, false, false, false, false, true, false, 0},
+      {"linear 512->2048 B256 dual +res (no split: 8 k-steps)", 256, 1, 1, 512, 1, 2048, 2048, 1, 1, true, true, true, false, false, false, 0},
+      {"linear 1024->1024 B64 raw",                          64, 1, 1, 1024, 1, 1024, 1024, 1, 1, false, true, false, false, false, false, 0},
   };
   if (argc > 1 && !strcmp(argv[1], "splitk")) {
     // 1: the library's rule (three k-ranges on maps up to 4x4); 0: off; n >= 2: n ranges on every map up to 8x8
@@ -514,6 +520,16 @@ int main(int argc, char** argv) {
       for (const ConvCase& c : small_cases) run_conv_case(c);
     }
     unsetenv("VUB_SPLITK");
+    for (const char* rs : {"8", "4", "2", "0"}) {  // reduce-scatter ranges for the linear layers
+      setenv("VUB_LINEAR_RS", rs, 1);
+      printf("--- correctness + timing, VUB_LINEAR_RS=%s\n", rs);
+      for (const ConvCase& c : small_cases)
+        if (!strncmp(c.name, "linear", 6)) run_conv_case(c);
+      perf_conv("linear 2048->2048 B256 elu", 256, 1, 1, 2048, 1, 2048, 1, 1, false, false, false, 0);
+      perf_conv("linear 1088->4096 B256", 256, 1, 1, 1088, 1, 4096, 1, 1, false, false, false, 0);
+      perf_conv("linear 1024->1024 B256", 256, 1, 1, 1024, 1, 1024, 1, 1, false, false, false, 0);
+    }
+    unsetenv("VUB_LINEAR_RS");
     for (int sk : {1, 0, 2}) {
       char buf[4];
       snprintf(buf, sizeof buf, "%d", sk);
