@@ -8,7 +8,7 @@ timeout 300 python __graft_entry__.py smoke > $out/smoke.log 2>&1; echo "smoke r
 grep smoke: $out/smoke.log; tail -3 $out/smoke.log | grep -v smoke:
 shift
 if [ -n "$1" ]; then
-  timeout 600 python -m pytest "$@" -m gpu -x -q -s --timeout 300 > $out/pytest.log 2>&1; echo "pytest rc=$?" | tee -a $out/summary.txt
+  timeout 900 python -m pytest "$@" -m gpu -x -q -s --timeout 600 > $out/pytest.log 2>&1; echo "pytest rc=$?" | tee -a $out/summary.txt
   grep -v "^$" $out/pytest.log | tail -12
 fi
 timeout 500 python bench.py --steps 20 --warmup 5 > $out/bench.json 2> $out/bench.err; echo "bench rc=$?" | tee -a $out/summary.txt
