@@ -247,7 +247,8 @@ int vub_nchw_f32_to_nhwc_f32(const float* src, int32_t batch, int32_t c, int32_t
 typedef struct vub_dgrad_desc {
   const void* dy;
   const void* wd;            /* [nsrc*c_src, ksize*ksize*cout_k] bf16 (vub_wn_entry.wd) */
-  void* dx[2];               /* NHWC bf16 [batch, hin, win, c_src] per source */
+  void* dx[2];               /* NHWC bf16 [batch, hin, win, c_src] per source; c_src 32 / 64 / 128, or 256 / 512 (stride 1, no
+                                D2S: one launch per 128-channel slice of every source) */
   const void* mask_elu[2];
   const void* addend[2];
   const void* addend2[2];
@@ -274,7 +275,8 @@ int vub_conv_dgrad(const vub_dgrad_desc* d, void* stream);
  */
 typedef struct vub_wgrad_desc {
   const void* dy;            /* as in vub_dgrad_desc */
-  const void* x[2];          /* NHWC bf16 [batch, hin, win, c_src] */
+  const void* x[2];          /* NHWC bf16 [batch, hin, win, c_src]; c_src 32 / 64 / 128, or 256 / 512 (stride 1, no D2S: one
+                                launch per 128-channel slice of every source, each writing its own rows of gt) */
   float* gt;                 /* [n_split][cout_k][gt_pitch] (slices split_stride floats apart) */
   float* dy_sum;             /* [n_split][cout_k] (slices sum_stride floats apart) */
   int64_t split_stride;
