@@ -76,6 +76,7 @@ EXPORTED_SYMBOLS = (
     "vub_gather_affine",
     "vub_couple_inv",
     "vub_lstm_cell",
+    "vub_lstm_input",
     "vub_decoder_step",
     "vub_decoder_init",
 )
@@ -421,7 +422,9 @@ def _declare(lib: C.CDLL) -> None:
     lib.vub_couple_inv.restype = C.c_int
     lib.vub_couple_inv.argtypes = [fp, fp, fp, i32, i32, i32, i32, fp, vp, vp]
     lib.vub_lstm_cell.restype = C.c_int
-    lib.vub_lstm_cell.argtypes = [fp, fp, i32, i32, vp, vp, i32, vp]
+    lib.vub_lstm_cell.argtypes = [fp, fp, i32, i32, vp, vp, i32, fp, vp]
+    lib.vub_lstm_input.restype = C.c_int
+    lib.vub_lstm_input.argtypes = [fp, C.c_int64, i32, i32, i32, vp, i32, i32, vp]
     lib.vub_decoder_step.restype = C.c_int
     lib.vub_decoder_step.argtypes = [fp, fp, i32, i32, i32, i32, i32, i32, fp, fp, vp, i32, i32, vp]
     lib.vub_decoder_init.restype = C.c_int

@@ -10,8 +10,9 @@ uses to turn Gaussian noise into 3-D pose sequences (lib/logging.py:280-300): ``
 the LSTM gates and ``n_out`` of every time step — is a "linear layer" launch of the tcgen05 per-tap kernel (1x1 conv on
 a [batch, 1, 1, features] tensor, split-K over a thread-block cluster, LeakyReLU epilogue); the glue between them
 (shuffle + ActNorm, the coupling update, the LSTM cell, the residual step) are the small kernels of ``csrc/behavior.cu``.
-:class:`PoseSequenceSampler` captures noise -> sequences in one CUDA graph.  Training of these models (flow forward /
-log-determinants, the LSTM encoder) is outside the hot path: those entry points raise.
+:class:`PoseSequenceSampler` captures noise -> sequences in one CUDA graph.  ``ResidualBehaviorNet.forward`` /
+``infer_b`` (the LSTM encoder: behavior transfer and reconstruction) run on the same kernels.  Training of these models
+and the flow's density direction are outside the hot path: those entry points raise or are inference-only.
 """
 from __future__ import annotations
 
@@ -324,8 +325,8 @@ _FLOW_STREAMS: dict = {}  # one side stream per device for the translation nets
 # models/pose_behavior_rnn.py
 # ------------------------------------------------------------------------------------------------
 class BEncoder(nn.Module):
-    """models/pose_behavior_rnn.py:125-210 — the LSTM encoder that infers b from a sequence (parameter holder: the
-    sampling path draws b from the flow instead)."""
+    """models/pose_behavior_rnn.py:125-210 — the LSTM encoder that infers the behavior code b from a pose sequence
+    (behavior transfer / reconstruction; the sampling path draws b from the flow instead)."""
 
     def __init__(self, n_in, n_layers, dim_hidden, use_linear, dim_linear, ib=False):
         super().__init__()
@@ -338,8 +339,59 @@ class BEncoder(nn.Module):
         self.use_linear = use_linear
         self.linear = nn.Linear(self.dim_hidden, dim_linear) if self.use_linear else None
 
+        self._prep = _Prepared()
+        self.hidden = None
+
+    def init_hidden(self, bs, device):
+        self.hidden = (torch.zeros((self.n_layer, bs, self.dim_hidden), device=device),
+                       torch.zeros((self.n_layer, bs, self.dim_hidden), device=device))
+
+    def set_hidden(self, bs, device, hidden=None, cell=None):
+        if hidden is None and cell is None:
+            self.init_hidden(bs, device)
+        elif hidden is None:
+            self.hidden = (torch.zeros_like(cell), cell)
+        elif cell is None:
+            self.hidden = (hidden, torch.zeros_like(hidden))
+        else:
+            self.hidden = (hidden, cell)
+
     def forward(self, x, sample=False):
-        raise NotImplementedError("vunet_b200: BEncoder (behavior inference from a sequence) is outside the sampling path")
+        """``out, self.hidden = self.rnn(x, self.hidden)``; returns ``pre = self.hidden[0][-1]`` (the behavior code b):
+        one gate GEMM on the concatenated [h | x_t] row + one cell launch per time step."""
+        if not x.is_cuda:
+            raise RuntimeError("vunet_b200 has no CPU path: inputs must live on a CUDA device")
+        if self.n_layer != 1:
+            raise NotImplementedError("vunet_b200: BEncoder with one LSTM layer (ResidualBehaviorNet builds it with 1)")
+        rnn = self.rnn
+        n = rnn.input_size
+
+        def build():
+            xpad = (n + 63) // 64 * 64
+            wx = torch.zeros((rnn.weight_ih_l0.shape[0], xpad), dtype=torch.float32, device=rnn.weight_ih_l0.device)
+            wx[:, :n] = rnn.weight_ih_l0.detach()
+            return [_LinearAdapter(torch.cat([rnn.weight_hh_l0.detach(), wx], dim=1),
+                                   rnn.bias_ih_l0.detach() + rnn.bias_hh_l0.detach())]
+        bank, (ad_g,) = self._prep.get([rnn.weight_ih_l0, rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0], build)
+        lib, st = N.lib(), ops._stream
+        B, T, H = x.shape[0], x.shape[1], self.dim_hidden
+        xpad = (n + 63) // 64 * 64
+        xs = x.float().contiguous()
+        if self.hidden is None or self.hidden[0].shape[1] != B or self.hidden[0].device != x.device:
+            self.init_hidden(B, x.device)
+        h0, c0 = self.hidden[0][-1].float().contiguous(), self.hidden[1][-1].float().contiguous()
+        c = c0.clone()
+        h32 = h0.clone()
+        cat = torch.zeros((B, 1, 1, H + xpad), dtype=torch.bfloat16, device=x.device)
+        cat.view(B, H + xpad)[:, :H] = h0.to(torch.bfloat16)      # initial hidden state (zeros after init_hidden)
+        for t in range(T):
+            N.check(ops._launch("lstm_input", lib.vub_lstm_input, xs.data_ptr() + t * n * 4, T * n, B, n, xpad, cat.data_ptr(),
+                                H + xpad, H, st()), "vub_lstm_input")
+            gates = _linear(bank, ad_g, cat, f32=True)
+            N.check(ops._launch("lstm_cell", lib.vub_lstm_cell, gates.data_ptr(), c.data_ptr(), B, H, None, cat.data_ptr(),
+                                H + xpad, h32.data_ptr(), st()), "vub_lstm_cell")
+        self.hidden = (h32.unsqueeze(0), c.unsqueeze(0))
+        return h32
 
 
 class ResidualRNNDecoder(nn.Module):
@@ -407,17 +459,23 @@ class ResidualBehaviorNet(nn.Module):
         for t in range(len):
             gates = _linear(bank, ad_g, cat, f32=True)            # [B, 1, 1, 4H] fp32
             N.check(ops._launch("lstm_cell", lib.vub_lstm_cell, gates.data_ptr(), c.data_ptr(), B, H, h_lin.data_ptr(),
-                                cat.data_ptr(), H + xpad, st()), "vub_lstm_cell")
+                                cat.data_ptr(), H + xpad, None, st()), "vub_lstm_cell")
             v = _linear(bank, ad_o, h_lin, f32=True)              # [B, 1, 1, npad] fp32
             N.check(ops._launch("decoder_step", lib.vub_decoder_step, x.data_ptr(), v.data_ptr(), B, n, v.shape[-1], xpad, t,
                                 len, xs.data_ptr(), cs.data_ptr(), cat.data_ptr(), H + xpad, H, st()), "vub_decoder_step")
         return xs, cs, [], b
 
     def infer_b(self, s, sample):
-        raise NotImplementedError("vunet_b200: infer_b (the LSTM encoder) is outside the sampling path")
+        """models/pose_behavior_rnn.py:587-601: the behavior code of a sequence, b = last hidden state of the LSTM encoder."""
+        self.b_enc.init_hidden(s.shape[0], device=s.device)
+        return self.b_enc(s, sample)
 
     def forward(self, x1, x2, len, start_frame=0, sample=False):
-        raise NotImplementedError("vunet_b200: ResidualBehaviorNet.forward needs infer_b; use flow.reverse + generate_seq")
+        """models/pose_behavior_rnn.py:574-585: behavior of ``x1`` re-enacted from the start pose of ``x2``:
+        returns (xs, cs, zs_gen, b)."""
+        b = self.infer_b(x1, sample)
+        xs, cs, zs_gen, _ = self.generate_seq(b, x2, len, start_frame=start_frame)
+        return xs, cs, zs_gen, b
 
 
 class PoseSequenceSampler:

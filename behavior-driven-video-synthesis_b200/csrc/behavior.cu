@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(kBhThreads)
 // the next step's concatenated gate input [B, H + xpad].
 __global__ void __launch_bounds__(kBhThreads)
     lstm_cell_kernel(const float* __restrict__ gates, float* __restrict__ c, int hdim, long long total,
-                     __nv_bfloat16* __restrict__ h_lin, __nv_bfloat16* __restrict__ h_cat, int cat_pitch) {
+                     __nv_bfloat16* __restrict__ h_lin, __nv_bfloat16* __restrict__ h_cat, int cat_pitch,
+                     float* __restrict__ h_f32) {
   const long long i = (long long)blockIdx.x * kBhThreads + threadIdx.x;
   if (i >= total) return;
   const long long b = i / hdim;
@@ -65,9 +66,23 @@ __global__ void __launch_bounds__(kBhThreads)
   const float ig = sigmoidf_(g[j]), fg = sigmoidf_(g[hdim + j]), gg = tanhf(g[2 * hdim + j]), og = sigmoidf_(g[3 * hdim + j]);
   const float cn = fg * c[i] + ig * gg;
   c[i] = cn;
-  const __nv_bfloat16 h = __float2bfloat16_rn(og * tanhf(cn));
-  h_lin[i] = h;
+  const float hf = og * tanhf(cn);
+  const __nv_bfloat16 h = __float2bfloat16_rn(hf);
+  if (h_lin != nullptr) h_lin[i] = h;
   h_cat[b * cat_pitch + j] = h;
+  if (h_f32 != nullptr) h_f32[i] = hf;
+}
+
+// BEncoder's nn.LSTM over a given sequence (models/pose_behavior_rnn.py:177-178): the step's input x[:, t] (fp32, row
+// pitch x_pitch floats) as bf16, zero-padded to xpad, into columns [hdim, hdim + xpad) of the gate input.
+__global__ void __launch_bounds__(kBhThreads)
+    lstm_input_kernel(const float* __restrict__ x_t, long long x_pitch, int n, int xpad, long long total,
+                      __nv_bfloat16* __restrict__ cat, int cat_pitch, int hdim) {
+  const long long i = (long long)blockIdx.x * kBhThreads + threadIdx.x;
+  if (i >= total) return;
+  const long long b = i / xpad;
+  const int j = static_cast<int>(i - b * xpad);
+  cat[b * cat_pitch + hdim + j] = __float2bfloat16_rn(j < n ? x_t[b * x_pitch + j] : 0.f);
 }
 
 // ResidualRNNDecoder.forward's `out + res, res` for step t: x_{t+1} = x_t + v (v = n_out(h), fp32 [B, vpitch]):
@@ -147,14 +162,26 @@ extern "C" int vub_couple_inv(const float* state_in, const float* s_raw, const f
   return check_launch("couple_inv");
 }
 
-extern "C" int vub_lstm_cell(const float* gates, float* c, int32_t batch, int32_t hdim, void* h_lin_bf16, void* h_cat_bf16,
-                             int32_t cat_pitch, void* stream) {
+extern "C" int vub_lstm_input(const float* x_t, int64_t x_pitch, int32_t batch, int32_t n, int32_t xpad, void* cat_bf16,
+                              int32_t cat_pitch, int32_t hdim, void* stream) {
   clear_error();
-  if (!gates || !c || !h_lin_bf16 || !h_cat_bf16) return fail(VUB_E_NULL, "lstm_cell: NULL pointer");
+  if (!x_t || !cat_bf16) return fail(VUB_E_NULL, "lstm_input: NULL pointer");
+  if (batch <= 0 || n <= 0 || n > xpad || x_pitch < n || cat_pitch < hdim + xpad) return fail(VUB_E_SHAPE, "lstm_input: bad shape");
+  const long long total = (long long)batch * xpad;
+  lstm_input_kernel<<<bh_blocks(total), kBhThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_t, x_pitch, n, xpad, total, static_cast<__nv_bfloat16*>(cat_bf16), cat_pitch, hdim);
+  return check_launch("lstm_input");
+}
+
+extern "C" int vub_lstm_cell(const float* gates, float* c, int32_t batch, int32_t hdim, void* h_lin_bf16, void* h_cat_bf16,
+                             int32_t cat_pitch, float* h_f32, void* stream) {
+  clear_error();
+  if (!gates || !c || !h_cat_bf16) return fail(VUB_E_NULL, "lstm_cell: NULL pointer");
   if (batch <= 0 || hdim <= 0 || cat_pitch < hdim) return fail(VUB_E_SHAPE, "lstm_cell: bad shape");
   const long long total = (long long)batch * hdim;
   lstm_cell_kernel<<<bh_blocks(total), kBhThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      gates, c, hdim, total, static_cast<__nv_bfloat16*>(h_lin_bf16), static_cast<__nv_bfloat16*>(h_cat_bf16), cat_pitch);
+      gates, c, hdim, total, static_cast<__nv_bfloat16*>(h_lin_bf16), static_cast<__nv_bfloat16*>(h_cat_bf16), cat_pitch,
+      h_f32);
   return check_launch("lstm_cell");
 }
 

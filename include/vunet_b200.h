@@ -526,7 +526,11 @@ int vub_couple_inv(const float* state_in, const float* s_raw, const float* t, in
 /* nn.LSTMCell from the gate pre-activations [batch, 4*hdim] (chunks i, f, g, o): c updated in place (fp32), h' written
  * as bf16 compact [batch, hdim] and into columns [0, hdim) of the next step's gate input [batch, cat_pitch]. */
 int vub_lstm_cell(const float* gates, float* c, int32_t batch, int32_t hdim, void* h_lin_bf16, void* h_cat_bf16,
-                  int32_t cat_pitch, void* stream);
+                  int32_t cat_pitch, float* h_f32, void* stream);   /* h_lin_bf16 / h_f32 optional */
+/* The step input of BEncoder's nn.LSTM over a given sequence (pose_behavior_rnn.py:177-178): x_t [batch, n] fp32 with
+ * row pitch x_pitch floats (x[:, t] of a [batch, T, n] tensor) as bf16, zero-padded, into columns [hdim, hdim + xpad). */
+int vub_lstm_input(const float* x_t, int64_t x_pitch, int32_t batch, int32_t n, int32_t xpad, void* cat_bf16,
+                   int32_t cat_pitch, int32_t hdim, void* stream);
 /* ResidualRNNDecoder.forward's `out + res, res` (pose_behavior_rnn.py:487-506) for step t: x <- x + v (v fp32
  * [batch, vpitch], first n columns), xs[:, t] = new x, cs[:, t] = old x ([batch, steps, n] fp32), bf16 copy of the new
  * x (zero-padded to xpad) into columns [hdim, hdim + xpad) of the gate input. */

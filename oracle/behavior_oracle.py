@@ -5,7 +5,8 @@ configs[3]: ``b = flow.reverse(z)`` through ``UnsupervisedTransformer2`` (models
 models/flow/blocks.py:95-128 ``UnconditionalFlow2``, 531-559 ``UnconditionalFlatDoubleCouplingFlowBlock2``, 276-319
 ``DoubleVectorCouplingBlock2``, 692-704 ``Shuffle``; lib/modules.py:236-257 ``BasicFullyConnectedNet``, 260-330
 ``ActNorm``) and ``ResidualBehaviorNet.generate_seq`` (models/pose_behavior_rnn.py:603-626) with ``ResidualRNNDecoder``
-(463-506: ``nn.LSTMCell`` + ``n_out``, ``x_{t+1} = x_t + n_out(h_t)``).
+(463-506: ``nn.LSTMCell`` + ``n_out``, ``x_{t+1} = x_t + n_out(h_t)``), plus ``infer_b`` (587-601, the LSTM encoder of
+``BEncoder`` 125-201) for behavior transfer.
 
 Parity pinning: ``oracle/gen_golden_behavior.py`` imports the UNMODIFIED reference classes (they import with torch
 alone), loads deterministic hashed parameters and checks this restatement against them (``tests/golden/behavior_tiny.pt``).
@@ -73,6 +74,22 @@ def generate_seq(sd: SD, b: torch.Tensor, x_start: torch.Tensor, length: int, pr
         x = x + F.linear(h, sd[f"{prefix}.n_out.weight"], sd[f"{prefix}.n_out.bias"])
         xs.append(x)
     return torch.stack(xs, dim=1), torch.stack(cs, dim=1)
+
+
+def infer_b(sd: SD, s: torch.Tensor, prefix: str = "b_enc.rnn") -> torch.Tensor:
+    """ResidualBehaviorNet.infer_b — pose_behavior_rnn.py:587-601 -> BEncoder.forward (177-201, ib = False): a one-layer
+    nn.LSTM from zero state over the sequence s [B, T, n]; returns the last hidden state."""
+    B = s.shape[0]
+    hdim = sd[f"{prefix}.weight_hh_l0"].shape[1]
+    h = torch.zeros(B, hdim)
+    c = torch.zeros(B, hdim)
+    for t in range(s.shape[1]):
+        gates = F.linear(s[:, t], sd[f"{prefix}.weight_ih_l0"], sd[f"{prefix}.bias_ih_l0"]) + \
+            F.linear(h, sd[f"{prefix}.weight_hh_l0"], sd[f"{prefix}.bias_hh_l0"])
+        i, f, g, o = gates.chunk(4, dim=1)
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+        h = torch.sigmoid(o) * torch.tanh(c)
+    return h
 
 
 # ---- deterministic parameters ------------------------------------------------------------------------

@@ -56,14 +56,19 @@ def main() -> None:
             xs.append(x)
             cs.append(v)
         xs, cs = torch.stack(xs, dim=1), torch.stack(cs, dim=1)
+        # behavior inference from a sequence (infer_b asks for s.get_device(): run BEncoder the way it does, on CPU)
+        seq = O.det_uniform("bseq", (B, T + 3, n))
+        net.b_enc.init_hidden(B, "cpu")
+        b_inf = net.b_enc(seq, False)
+        o_inf = BO.infer_b(nsd, seq)
         o_b = BO.flow_reverse(fsd, z, CFG["n_flows"], CFG["flow_hidden_depth"])
         o_xs, o_cs = BO.generate_seq(nsd, o_b, x_pose[:, 0], T)
     rel = lambda a, r: float((a - r).norm() / r.norm())
-    errs = {"b": rel(o_b, b2), "xs": rel(o_xs, xs), "cs": rel(o_cs, cs)}
+    errs = {"b": rel(o_b, b2), "xs": rel(o_xs, xs), "cs": rel(o_cs, cs), "infer_b": rel(o_inf, b_inf)}
     print("oracle vs reference:", {k: f"{v:.2e}" for k, v in errs.items()})
     assert max(errs.values()) < 1e-5, errs
     fixture = {"config": CFG, "flow_shapes": list(fshapes.items()), "net_shapes": list(nshapes.items()),
-               "b": b2.clone(), "xs": xs.clone(), "cs": cs.clone(), "oracle_vs_reference": errs,
+               "b": b2.clone(), "xs": xs.clone(), "cs": cs.clone(), "infer_b": b_inf.clone(), "oracle_vs_reference": errs,
                "torch_version": torch.__version__}
     path = os.path.join(args.out, "behavior_tiny.pt")
     torch.save(fixture, path)

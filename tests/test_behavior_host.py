@@ -29,6 +29,7 @@ def test_oracle_matches_reference_golden(golden):
     b = BO.flow_reverse(fsd, z, cfg["n_flows"], cfg["flow_hidden_depth"])
     xs, cs = BO.generate_seq(nsd, b, x_pose[:, 0], T)
     assert rel(b, fx["b"]) < 1e-5 and rel(xs, fx["xs"]) < 1e-5 and rel(cs, fx["cs"]) < 1e-5
+    assert rel(BO.infer_b(nsd, O.det_uniform("bseq", (Bs, T + 3, n))), fx["infer_b"]) < 1e-5
     # the flow is a bijection: the oracle's forward direction (restated here from blocks.py:540-550) inverts reverse
     h = b
     for i in range(cfg["n_flows"]):
@@ -93,5 +94,5 @@ def test_no_cpu_fallback_and_out_of_scope_entry_points(golden):
         net.generate_seq(torch.zeros(2, 128), torch.zeros(2, 3, 51), 3, 0)
     with pytest.raises(NotImplementedError):
         flow(torch.zeros(2, 128))          # density direction: training only
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="no CPU path"):
         net.infer_b(torch.zeros(2, 3, 51), False)

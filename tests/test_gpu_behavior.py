@@ -47,6 +47,15 @@ def test_matches_reference_golden(golden):
     print("behavior_tiny:", {k: f"{v:.2e}" for k, v in errs.items()})
     assert max(errs.values()) < TOL, errs
     assert zs == [] and tuple(xs.shape) == (Bs, T, n)
+    # behavior inference from a sequence (the LSTM encoder) and the net's forward = infer_b + generate_seq
+    seq = O.det_uniform("bseq", (Bs, T + 3, n)).cuda()
+    with torch.no_grad():
+        b_inf = net.infer_b(seq, False)
+        fx_xs, fx_cs, _, fx_b = net(seq, x_pose, T, start_frame=0)
+        o_xs, _ = BO.generate_seq(nsd, fx["infer_b"], x_pose[:, 0].cpu(), T)
+    e_inf, e_fwd = rel(b_inf, fx["infer_b"]), rel(fx_xs, o_xs)
+    print(f"  infer_b {e_inf:.2e}, forward (behavior transfer) {e_fwd:.2e}")
+    assert e_inf < TOL and e_fwd < TOL and torch.equal(fx_b, b_inf)
     # the graph-captured sampler equals the two calls; flow(z, reverse=True) and sample() are the same path
     smp = B.PoseSequenceSampler(flow, net, Bs, T)
     out = smp(z, x_pose[:, :1])
@@ -73,8 +82,11 @@ def test_full_size_matches_oracle():
         o_xs, o_cs = BO.generate_seq(nsd, o_b, x0[:, 0], T)
         # the decoder alone from the oracle's b (isolates it from the flow's rounding)
         xs2, _, _, _ = net.generate_seq(o_b.cuda(), x0.cuda(), T, 0)
+        seq = O.det_uniform("bseq_full", (Bs, T, 51))
+        b_inf = net.infer_b(seq.cuda(), False)
+        o_inf = BO.infer_b(nsd, seq)
     errs = {"b": rel(b, o_b), "xs": rel(xs, o_xs), "cs": rel(cs, o_cs), "xs_from_oracle_b": rel(xs2, o_xs),
-            "velocities": rel(xs - cs, o_xs - o_cs)}
+            "velocities": rel(xs - cs, o_xs - o_cs), "infer_b (50-step LSTM-1024 encoder)": rel(b_inf, o_inf)}
     print("behavior net, full size B=256 T=50:", {k: f"{v:.2e}" for k, v in errs.items()})
     assert max(errs.values()) < TOL, errs
     assert torch.isfinite(xs).all()
