@@ -544,6 +544,76 @@ def run_behavior_sampling(device, steps: int, peaks) -> dict:
                              "sample": "16 sequences x 2 iters (+1 warm-up), oracle/behavior_oracle.py fp32 torch CPU"}}
 
 
+def run_behavior_transfer(device, model, steps: int) -> dict:
+    """BASELINE.json configs[4], one GPU's share: behavior-net pose sequences (64 frames) -> camera projection ->
+    GPU stickman rasteriser -> VUnet 256x256 synthesis with the appearance encoded once per sequence -> uint8 frames.
+    Nothing leaves the GPU between the noise and the frames.  256 sequences are sampled per PoseSequenceSampler replay;
+    every sequence is one SequenceSynthesizer replay (64 frames)."""
+    import collections
+    import behavior_oracle as BO
+    import bdvs_b200 as B
+    from bdvs_b200.rendering import StickmanRasterizer, project_poses
+    from bdvs_b200.synthesis import SequenceSynthesizer
+
+    T, S_batch = 64, 256
+    flow = B.UnsupervisedTransformer2(flow_in_channels=1024, n_flows=15, flow_hidden_depth=2, flow_mid_channels=2048)
+    net = B.ResidualBehaviorNet(n_kps=51, dim_hidden_b=1024, decoder_arch="lstm", linear_in_decoder=False)
+    flow.load_state_dict(BO.det_flow_state_dict({k: tuple(v.shape) for k, v in flow.state_dict().items()}))
+    net.load_state_dict(BO.det_net_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}))
+    flow, net = flow.to(device).eval(), net.to(device).eval()
+    smp = B.PoseSequenceSampler(flow, net, S_batch, T)
+    JM = collections.namedtuple("JointModel", "body right_lines left_lines head_lines face rshoulder lshoulder headup")
+    jm = JM(body=[0, 14, 8, 11, 3], right_lines=[(0, 1), (1, 2), (0, 14), (14, 15), (15, 16)],
+            left_lines=[(3, 4), (4, 5), (3, 11), (11, 12), (12, 13)], head_lines=[(8, 9), (9, 10)], face=[],
+            rshoulder=14, lshoulder=11, headup=10)   # data/human36m.py:136-152, keypoints_3d_world (17 joints)
+    raster = StickmanRasterizer(jm, 256)
+    seq = SequenceSynthesizer(model, 1, T, uint8_frames=True, uint8_inputs=True)
+    g = torch.Generator(device=device).manual_seed(5)
+    z = torch.randn(S_batch, 1024, device=device, generator=g)
+    x0 = torch.rand(S_batch, 1, 51, device=device, generator=g) * 0.6 - 0.3
+    app = torch.randint(0, 256, (S_batch, 256, 256, 3), dtype=torch.uint8, device=device, generator=g)
+    extr = torch.tensor([[1.0, 0, 0, 0], [0, 1.0, 0, 0], [0, 0, 1.0, 4.0]], dtype=torch.float64)   # synthetic camera
+    intr = (1100.0, 500.0, 1100.0, 500.0)
+    frames_h = torch.empty((T, 256, 256, 3), dtype=torch.uint8).pin_memory()
+
+    def render(n_seq: int):
+        poses = smp(z, x0)                                             # [256, T, 51] 3-D poses, one graph replay
+        j3 = poses[:n_seq].reshape(n_seq * T, 17, 3).clamp(-1.5, 1.5)
+        j2 = project_poses(j3, extr, intr, (1000.0, 1000.0), 256)      # [n_seq * T, 17, 2]
+        for i in range(n_seq):
+            raster(j2[i * T:(i + 1) * T], out=seq.c)                   # stickmen straight into the graph's input
+            seq.x.copy_(app[i:i + 1])
+            frames_h.copy_(seq.run(), non_blocking=True)               # video frames back to pinned host memory
+
+    n_seq = 8
+    render(2)
+    torch.cuda.synchronize()
+    K = max(2, steps // 10)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        render(n_seq)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    e0.record()
+    for _ in range(5):
+        smp.run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_sample = e0.elapsed_time(e1) / 5
+    ms_per_seq = (ms - ms_sample) / n_seq + ms_sample / S_batch   # sampling amortised over the 256 sequences it yields
+    return {"metric": "end-to-end behavior transfer: sampled 64-frame pose sequences -> stickmen -> 256x256 video (1 GPU)",
+            "value": 1e3 / ms_per_seq, "unit": "sequences/s", "frames_per_s": T * 1e3 / ms_per_seq, "per_gpu": True,
+            "ms_per_sequence": ms_per_seq, "ms_sampling_256_sequences": ms_sample,
+            "sequences_per_step_rendered": n_seq, "frames_per_sequence": T,
+            "d2h_bytes_per_sequence": frames_h.numel(),
+            "seconds_for_512_sequences_1gpu": 512 * ms_per_seq * 1e-3,
+            "seconds_for_512_sequences_8gpu_no_collective": 64 * ms_per_seq * 1e-3,
+            "note": "sequences are independent: 8 GPUs take 64 each (synthesis.shard_range), no collective; random weights, "
+                    "synthetic camera"}
+
+
 def run_vunet_org(device, frames: int, steps: int, peaks) -> dict:
     """``VunetOrg.transfer`` (models/vunets.py:102-110) at the H256 geometry, ``frames`` frames per step, CUDA-graph
     replay timed with CUDA events on this rank; plus the share of the step the prior's 512 / 1024-channel convs take
@@ -955,6 +1025,11 @@ def run_ours(args):
         roofline["behavior_sampling"] = run_behavior_sampling(device, K, peaks)
     except Exception as exc:  # secondary number: never take the headline down
         roofline["behavior_sampling"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    # ---- BASELINE configs[4]: sampled pose sequences -> stickmen -> video, everything on the GPU ----
+    try:
+        roofline["behavior_transfer_e2e"] = run_behavior_transfer(device, model, K)
+    except Exception as exc:  # secondary number: never take the headline down
+        roofline["behavior_transfer_e2e"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     # ---- the training step with the reference's real likelihood, the VGG19 perceptual loss ----
     if not args.no_train:
         try:

@@ -23,7 +23,9 @@ try:
     print("vunet_org", b["roofline"].get("vunet_org"))
     print("sequence", b["roofline"].get("sequence"))
     print("train_vgg", b["roofline"].get("train_vgg"))
-    print("behavior_sampling", b["roofline"].get("behavior_sampling"))
+    bs = b["roofline"].get("behavior_sampling") or {}
+    print("behavior_sampling", {k: bs.get(k) for k in ("value", "ms_per_batch", "e2e", "error")})
+    print("behavior_transfer_e2e", b["roofline"].get("behavior_transfer_e2e"))
     for k in b["kernels"][:12]:
         print(k["kernel"], k["launches"], k["ms"], k["share"], k["tflops"], k["gbs"])
 except Exception as e:
