@@ -7,7 +7,7 @@ from .modules import (Act, DepthToSpace, Downsample, IDAct, NormConv2d, SpaceToD
                       WeightBank, bump_weight_epoch, to_act)
 from .optim import FusedAdam
 from .perceptual import PerceptualVGG, vgg_loss
-from .rendering import PoseRenderer, StickmanRasterizer, get_line_colors, project_poses
+from .rendering import BehaviorVideoRenderer, PoseRenderer, StickmanRasterizer, get_line_colors, project_poses
 from .training import GraphedTrainStep
 from .validation import fp32_validation
 from .vunets import DecDown, DecDownAlter, DecUp, EncDown, EncDownAlter, EncUp, VunetAlter, VunetOrg
@@ -19,5 +19,5 @@ __all__ = [
     "NormConv2d", "VunetRNB", "Downsample", "Upsample", "DepthToSpace", "SpaceToDepth", "IDAct",
     "compute_kl_with_prior", "kl_loss", "Act", "to_act", "WeightBank", "build_native",
     "fp32_validation", "FusedAdam", "GraphedTrainStep", "bump_weight_epoch", "StickmanRasterizer", "PoseRenderer",
-    "get_line_colors", "project_poses",
+    "get_line_colors", "project_poses", "BehaviorVideoRenderer",
 ]

@@ -138,3 +138,48 @@ class PoseRenderer:
     def __call__(self, appearance: torch.Tensor, joints: torch.Tensor, uint8_frames: bool = True) -> torch.Tensor:
         stick = self.raster(joints)
         return self.model.transfer(appearance, stick, uint8_frames=uint8_frames)
+
+
+class BehaviorVideoRenderer:
+    """BASELINE.json configs[4] as one object: noise -> behavior-net pose sequences (``PoseSequenceSampler``: latent-flow
+    reverse pass + residual LSTM decoder, one CUDA graph) -> camera projection -> stickman rasterisation -> VUnet
+    synthesis with the appearance encoded once per sequence (``SequenceSynthesizer``, one CUDA graph) -> uint8 frames.
+    The reference does this per frame on the host (lib/logging.py:280-300 for the poses,
+    data/data_conversions_3d.py:1130-1173 for the rendering); here nothing but the frames has to leave the GPU.
+
+    ``n_sampled`` sequences are drawn per sampler replay (256 is the efficient batch); every sequence is rendered by one
+    synthesizer replay.  ``joint_model`` indexes the ``n_kps / 3`` generated joints; ``extrinsics`` (3x4), ``intrinsics``
+    (f_x, x_0, f_y, y_0) and ``image_size`` as for :func:`project_poses`.  Sequences are independent: shard them over
+    GPUs with ``synthesis.shard_range`` (no collective)."""
+
+    def __init__(self, vunet, flow, net, joint_model, extrinsics, intrinsics, image_size, frames: int, n_sampled: int = 256,
+                 line_colors=None, use_graph: bool = True):
+        from .behavior import PoseSequenceSampler
+        from .synthesis import SequenceSynthesizer
+        if net.n_kps % 3:
+            raise ValueError("BehaviorVideoRenderer: the behavior net must generate 3-D joints (n_kps a multiple of 3)")
+        self.frames, self.n_sampled = frames, n_sampled
+        self.sampler = PoseSequenceSampler(flow, net, n_sampled, frames, use_graph=use_graph)
+        self.raster = StickmanRasterizer(joint_model, vunet.spatial_size, line_colors)
+        self.synth = SequenceSynthesizer(vunet, 1, frames, use_graph=use_graph, uint8_frames=True, uint8_inputs=True)
+        self.camera = (extrinsics, intrinsics, image_size)
+        self.size = vunet.spatial_size
+        self.n_joints = net.n_kps // 3
+
+    def sample_poses(self, z: torch.Tensor, x_start: torch.Tensor) -> torch.Tensor:
+        """[n_sampled, frames, J, 2] joints in stickman pixel coordinates for noise ``z`` and start poses ``x_start``."""
+        poses = self.sampler(z, x_start)
+        j3 = poses.reshape(self.n_sampled * self.frames, self.n_joints, 3)
+        j2 = project_poses(j3, self.camera[0], self.camera[1], self.camera[2], self.size)
+        return j2.reshape(self.n_sampled, self.frames, self.n_joints, 2)
+
+    def render_sequence(self, appearance_u8: torch.Tensor, joints: torch.Tensor, out: Optional[torch.Tensor] = None):
+        """One sequence: ``appearance_u8`` [1, Sx, Sx, Cx] uint8, ``joints`` [frames, J, 2] -> uint8 frames
+        [frames, S, S, 3] (the synthesizer's static output, or copied into ``out``, e.g. pinned host memory)."""
+        self.raster(joints, out=self.synth.c)        # stickmen straight into the graph's static input
+        self.synth.x.copy_(appearance_u8, non_blocking=True)
+        frames = self.synth.run()
+        if out is not None:
+            out.copy_(frames, non_blocking=True)
+            return out
+        return frames

@@ -90,3 +90,50 @@ def test_full_size_matches_oracle():
     print("behavior net, full size B=256 T=50:", {k: f"{v:.2e}" for k, v in errs.items()})
     assert max(errs.values()) < TOL, errs
     assert torch.isfinite(xs).all()
+
+
+def test_behavior_video_renderer_equals_the_separate_calls(golden):
+    """configs[4] in one object: sampled pose sequences -> projection -> stickmen -> sequence synthesis == the same steps
+    issued by hand (PoseSequenceSampler, project_poses, StickmanRasterizer, encode_appearance + decode_pose)."""
+    import collections
+    import contextlib
+    import io
+    import bdvs_b200 as B
+    fx = golden("behavior_tiny")
+    cfg = dict(fx["config"])
+    flow, net, fsd, nsd = make(cfg)
+    vfx = golden("tiny3")
+    vcfg = {k: v for k, v in vfx["config"].items() if k != "batch"}
+    with contextlib.redirect_stdout(io.StringIO()):
+        vunet = B.VunetAlter(**vcfg)
+    vunet.load_state_dict(O.det_state_dict({k: tuple(v.shape) for k, v in vunet.state_dict().items()}))
+    vunet = vunet.cuda().eval()
+    JM = collections.namedtuple("JointModel", "body right_lines left_lines head_lines face rshoulder lshoulder headup")
+    jm = JM(body=[0, 14, 8, 11, 3], right_lines=[(0, 1), (1, 2), (0, 14), (14, 15), (15, 16)],
+            left_lines=[(3, 4), (4, 5), (3, 11), (11, 12), (12, 13)], head_lines=[(8, 9), (9, 10)], face=[],
+            rshoulder=14, lshoulder=11, headup=10)
+    extr = torch.tensor([[1.0, 0, 0, 0], [0, 1.0, 0, 0], [0, 0, 1.0, 4.0]], dtype=torch.float64)
+    intr = (60.0, 16.0, 60.0, 16.0)
+    T, S = 4, 4
+    r = B.BehaviorVideoRenderer(vunet, flow, net, jm, extr, intr, (32.0, 32.0), frames=T, n_sampled=S)
+    z = O.det_normal("bz", (S, cfg["dim_hidden_b"])).cuda()
+    x0 = O.det_uniform("bx", (S, 1, cfg["n_kps"])).cuda()
+    app = (O.det_uniform("app", (S, 32, 32, 3), 0.0, 255.0)).to(torch.uint8).cuda()
+    torch.manual_seed(11)
+    joints = r.sample_poses(z, x0)
+    assert tuple(joints.shape) == (S, T, 17, 2)
+    frames = r.render_sequence(app[1:2], joints[1]).clone()
+    # by hand
+    with torch.no_grad():
+        b = flow.reverse(z).reshape(S, -1)
+        poses = net.generate_seq(b, x0, T, 0)[0]
+        j2 = B.project_poses(poses.reshape(S * T, 17, 3), extr, intr, (32.0, 32.0), 32).reshape(S, T, 17, 2)
+        assert torch.equal(j2, joints)
+        stick = B.StickmanRasterizer(jm, 32)(j2[1])
+        torch.manual_seed(11)
+        ref = vunet.decode_pose(stick, vunet.encode_appearance(app[1:2]), T, uint8_frames=True)
+    assert frames.dtype == torch.uint8 and tuple(frames.shape) == (T, 32, 32, 3)
+    # the synthesizer draws its latent noise inside the graph: same distribution, not the same bits as the eager call
+    diff = (frames.float() - ref.float()).abs().mean() / 255.0
+    assert float(diff) < 0.1
+    assert int(stick.max()) > 0   # the sampled poses land inside the image
