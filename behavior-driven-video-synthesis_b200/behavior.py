@@ -23,7 +23,7 @@ from torch import nn
 
 from . import _native as N
 from . import ops
-from .modules import WeightBank
+from .modules import _WEIGHT_EPOCH, WeightBank
 
 
 # ------------------------------------------------------------------------------------------------
@@ -159,21 +159,42 @@ def _linear(bank, ad, x: torch.Tensor, *, act: int = 0, f32: bool = False) -> to
 
 
 class _Prepared:
-    """Packed weights of a set of linear layers, rebuilt when a parameter changes (version / storage)."""
+    """Packed weights of a set of linear layers, re-prepared when a parameter changes (version / storage /
+    ``bump_weight_epoch()``).  The adapters and the bank's packed buffers are allocated ONCE per device and layer
+    shapes: a change of the parameters is copied into the same adapter tensors and prepared into the same packed
+    buffers, so CUDA graphs that have those addresses baked in (``PoseSequenceSampler``) stay valid; only a device move
+    or a change of a layer's shape builds a new bank (``generation`` counts those)."""
 
     def __init__(self):
         self.key = None
         self.bank = None
         self.ads = None
+        self.generation = 0
+        self._flat = None
+
+    @staticmethod
+    def _tensors(ad):
+        return (ad.conv.weight_v, ad.conv.weight_g, ad.conv.bias, ad.gamma, ad.beta)
 
     def get(self, params: List[torch.Tensor], build):
-        key = tuple((p.data_ptr(), p._version) for p in params)
+        key = (_WEIGHT_EPOCH[0],) + tuple((p.data_ptr(), p._version) for p in params)
         if key != self.key:
             if params[0].device.type != "cuda":
                 raise RuntimeError("vunet_b200 has no CPU path: move the module to a CUDA device")
-            self.ads = build()
-            flat = [a for a in _flatten(self.ads)]
-            self.bank = WeightBank([[a] for a in flat])
+            ads = build()
+            flat = list(_flatten(ads))
+            same = self.bank is not None and self._flat is not None and len(flat) == len(self._flat) and all(
+                a.shape == b.shape and a.device == b.device
+                for o, n in zip(self._flat, flat) for a, b in zip(self._tensors(o), self._tensors(n)))
+            if same:
+                for o, n in zip(self._flat, flat):
+                    for a, b in zip(self._tensors(o), self._tensors(n)):
+                        a.copy_(b)
+                self.bank._key = None            # same buffers, new contents: force the preparation pass
+            else:
+                self.ads, self._flat = ads, flat
+                self.bank = WeightBank([[a] for a in flat])
+                self.generation += 1
             self.bank.refresh()
             self.key = key
         return self.bank, self.ads
@@ -206,7 +227,12 @@ class UnsupervisedTransformer2(nn.Module):
         self._prep = _Prepared()
 
     def _prepared(self):
-        params = [p for p in self.parameters()]
+        # the Parameter objects are fixed after construction (load_state_dict / .to() / optimisers write into them):
+        # walking the 300-module tree costs 1.3 ms per call, the cached list 0.1 ms
+        params = self.__dict__.get("_vub_params")
+        if params is None:
+            params = [p for p in self.parameters()]
+            object.__setattr__(self, "_vub_params", params)
 
         def build():
             ads = []
@@ -489,6 +515,19 @@ class PoseSequenceSampler:
         self.z = torch.zeros((batch, flow.in_channels), dtype=torch.float32, device=dev)
         self.x_start = torch.zeros((batch, 1, net.n_kps), dtype=torch.float32, device=dev)
         self.graph = None
+        self._use_graph = use_graph
+        self._dev = dev
+        self._capture()
+
+    def _generations(self):
+        with torch.no_grad():
+            self.flow._prepared()
+            self.net._prepared()
+        return (self.flow._prep.generation, self.net._prep.generation)
+
+    def _capture(self) -> None:
+        dev = self._dev
+        self._gens = self._generations()         # weight preparation happens outside the graph
         with torch.no_grad():
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -498,7 +537,7 @@ class PoseSequenceSampler:
                     self.out = self._step()
                     self.launches_per_call = ops.LAUNCHES - before
             torch.cuda.current_stream(dev).wait_stream(side)
-            if use_graph:
+            if self._use_graph:
                 self.graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self.graph):
                     self.out = self._step()
@@ -507,7 +546,16 @@ class PoseSequenceSampler:
         b = self.flow.reverse(self.z).reshape(self.batch, -1)
         return self.net.generate_seq(b, self.x_start, self.length, 0)[0]
 
+    def refresh_weights(self) -> None:
+        """Re-prepares the packed weights if a parameter of the flow or the decoder changed (``run`` does the same
+        check itself).  The packed buffers keep their addresses across parameter updates (``_Prepared``), so the
+        captured graph normally stays valid; after a device move or a layer-shape change it is captured again."""
+        if self._generations() != self._gens:
+            torch.cuda.current_stream(self._dev).synchronize()
+            self._capture()
+
     def run(self) -> torch.Tensor:
+        self.refresh_weights()
         if self.graph is not None:
             self.graph.replay()
         else:

@@ -68,6 +68,42 @@ def test_matches_reference_golden(golden):
     assert torch.equal(s1, s2)
 
 
+def test_sampler_graph_follows_weight_updates(golden):
+    """A captured PoseSequenceSampler must not replay stale weights: the reference re-reads its parameters in every
+    call.  In-place updates (optimiser step, load_state_dict) re-prepare into the SAME packed buffers — no re-capture."""
+    import bdvs_b200 as B
+    cfg = golden("behavior_tiny")["config"]
+    flow, net, fsd, nsd = make(cfg)
+    Bs, T, n, D = cfg["batch"], cfg["length"], cfg["n_kps"], cfg["dim_hidden_b"]
+    z = O.det_normal("bz", (Bs, D)).cuda()
+    x0 = O.det_uniform("bx", (Bs, 1, n)).cuda()
+    smp = B.PoseSequenceSampler(flow, net, Bs, T)
+    before = smp(z, x0).clone()
+    graph, bank = smp.graph, flow._prep.bank
+    with torch.no_grad():
+        for p in list(flow.parameters())[:40]:
+            p.mul_(1.05)
+        net.decoder.n_out.weight.mul_(0.9)
+        net.decoder.rnn.bias_hh.add_(0.01)
+    after = smp(z, x0).clone()
+    assert smp.graph is graph and flow._prep.bank is bank          # same graph, same packed buffers
+    with torch.no_grad():
+        fresh = net.generate_seq(flow.reverse(z).reshape(Bs, D), x0, T, 0)[0]
+        sd_f = {k: v.detach().cpu() for k, v in flow.state_dict().items()}
+        sd_n = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+        o_xs, _ = BO.generate_seq(sd_n, BO.flow_reverse(sd_f, z.cpu(), cfg["n_flows"], cfg["flow_hidden_depth"]),
+                                  x0[:, 0].cpu(), T)
+    assert torch.equal(after, fresh) and not torch.equal(after, before)
+    assert rel(after, o_xs) < TOL
+    # writes autograd cannot see (p.data): bump_weight_epoch() is the documented call
+    net.decoder.n_out.bias.data.add_(0.05)
+    B.bump_weight_epoch()
+    moved = smp(z, x0)
+    assert not torch.equal(moved, after)
+    with torch.no_grad():
+        assert torch.equal(moved, net.generate_seq(flow.reverse(z).reshape(Bs, D), x0, T, 0)[0])
+
+
 def test_full_size_matches_oracle():
     """config/behavior_net.yaml: dim_hidden_b 1024, 15 blocks, MLP width 2048, depth 2; batch 256, 50 steps."""
     cfg = dict(dim_hidden_b=1024, flow_mid_channels_factor=2, n_flows=15, flow_hidden_depth=2, n_kps=51)
