@@ -22,7 +22,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .modules import _WEIGHT_EPOCH, WeightBank
+from .modules import WeightBank
 
 TAP_NAMES = ("input", "relu1_2", "relu2_2", "relu3_2", "relu4_2", "relu5_2")
 
@@ -101,7 +101,9 @@ class PerceptualVGG(nn.Module):
     # ---- prepared (packed bf16) weights: frozen, built once per device / weight version -----------------------------
     def _prepared(self, device: torch.device):
         convs = [self.vgg_layers._modules[p[1]] for p in self._plan if p[0] == "conv"]
-        key = (device, _WEIGHT_EPOCH[0], tuple((c.weight.data_ptr(), c.weight._version) for c in convs),
+        # (not keyed on modules._WEIGHT_EPOCH: FusedAdam bumps it every step — also inside a captured training step —
+        # and never touches these frozen weights; after a ``.data`` write to the VGG call ``vgg._prep = None``)
+        key = (device, tuple((c.weight.data_ptr(), c.weight._version) for c in convs),
                tuple((c.bias.data_ptr(), c.bias._version) for c in convs if c.bias is not None))
         if self._prep is None or self._prep[0] != key:
             if device.type != "cuda":
